@@ -1,0 +1,186 @@
+/* medseg_b200.h — C ABI of libmedseg_b200.so (hand-written sm_100a CUDA for the MedicalSeg VNet hot path).
+ *
+ * The reference (PaddleCV-SIG/MedicalSeg) has NO FFI / operator-plugin interface: every device op it runs is a
+ * PaddlePaddle kernel reached through paddle.nn.  The entry points below are therefore the
+ * operators that medicalseg/models/vnet.py, medicalseg/models/losses/*.py, cvlibs/config.py (Momentum) and
+ * tools/preprocess_utils/*.py reach inside Paddle / NumPy / CuPy; each one cites the reference call site it
+ * replaces (paths relative to /root/reference).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative msb_status; the message is read with
+ *    msb_last_error_string() (thread-local).  Nothing throws across the ABI, nothing calls exit().
+ *  - the caller owns every buffer (PyTorch caching allocator); the library allocates nothing persistent.
+ *  - all work is enqueued on the cudaStream_t passed as `void* stream`; no function synchronises.
+ *  - activations use the blocked-8 layout "B8": [N][C/8][D][H][W][8] (8 channels innermost), element type
+ *    bf16 or f32.  A msb_tensor may be a channel-slice view of a wider buffer (concat without copy).
+ *  - boundary tensors (network input, logits, labels, parameters, gradients) keep the reference layouts:
+ *    NCDHW f32 / [N,D,H,W] int32 / Paddle parameter shapes.
+ */
+#ifndef MEDSEG_B200_H_
+#define MEDSEG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSB_VERSION 100
+
+typedef enum {
+  MSB_OK = 0,
+  MSB_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  MSB_ERR_CUDA = -2,      /* CUDA runtime or driver error */
+  MSB_ERR_UNSUPPORTED = -3
+} msb_status;
+
+typedef enum { MSB_F32 = 0, MSB_BF16 = 1 } msb_dtype;
+
+/* View of a B8 activation: `ptr` addresses (n=0, first 8-channel plane of the view). */
+typedef struct {
+  void* ptr;
+  int64_t n_stride; /* elements between consecutive n in the underlying buffer (= C8_total*D*H*W*8) */
+  int32_t c;        /* channels of this view, multiple of 8 */
+  int32_t dtype;    /* msb_dtype */
+} msb_tensor;
+
+typedef struct { int32_t d, h, w; } msb_dim3;
+
+int msb_version(void);
+const char* msb_last_error_string(void);
+
+/* ---- layout converters (boundary) ------------------------------------------------------------------ */
+/* NCDHW f32 [N,C,S] -> B8 view (channels >= C zero-filled up to dst.c).  vnet.py:256 (network input side). */
+int msb_to_blocked(const float* src, int n, int c, int64_t s, msb_tensor dst, void* stream);
+/* B8 view -> NCDHW f32 [N,C,S]. */
+int msb_from_blocked(msb_tensor src, float* dst, int n, int c, int64_t s, void* stream);
+
+/* ---- BatchNorm3D + PReLU (+ tile-add / residual-add + second PReLU) --------------------------------
+ * Replaces nn.BatchNorm3D / nn.PReLU / paddle.add / Tensor.tile at vnet.py:41,74-79,107-111,149-154,173.
+ * groups = 1 -> batch statistics (reference semantics); groups = N -> per-instance statistics.       */
+/* sums[2][groups][C] (double) += per-channel sum and sum of squares of x. */
+int msb_bn_stats(msb_tensor x, int n, int64_t s, int groups, double* sums, void* stream);
+/* bnbuf[4][groups][C] f32 = scale, shift, mean, invstd.  training: from sums (biased variance), running stats
+ * updated as running = momentum*running + (1-momentum)*batch (Paddle convention); eval: from running stats. */
+int msb_bn_finalize(const double* sums, double count, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float momentum, float eps, int training,
+                    int c, int groups, float* bnbuf, void* stream);
+/* out = act2( act1( bn(y) [+ tile(tile_src)] ) [+ residual] ); act = PReLU(alpha).  residual.ptr==NULL and
+ * alpha2==NULL skip the second stage; tile_src (NCDHW f32 [N,tile_c,S], channel c reads c % tile_c —
+ * Tensor.tile, vnet.py:76-78) may be NULL. */
+int msb_bn_act_fwd(msb_tensor y, msb_tensor out, msb_tensor residual, const float* tile_src, int tile_c,
+                   const float* bnbuf, const float* alpha1, const float* alpha2,
+                   int n, int64_t s, int groups, void* stream);
+/* red[4][groups][C] (double) += sum g1, sum g1*xhat, dalpha1, dalpha2 (g1 = grad at the BN output). */
+int msb_bn_act_bwd_reduce(msb_tensor y, msb_tensor residual, const float* tile_src, int tile_c, msb_tensor gout,
+                          const float* bnbuf, const float* alpha1, const float* alpha2,
+                          int n, int64_t s, int groups, double* red, void* stream);
+/* dy = BN input gradient; dres (+)= gradient of the residual branch (dres.ptr may be NULL);
+ * dgamma/dbeta/dalpha1/dalpha2 (f32, += when accumulate_params) from red. */
+int msb_bn_act_bwd_apply(msb_tensor y, msb_tensor residual, const float* tile_src, int tile_c, msb_tensor gout,
+                         const float* bnbuf, const float* alpha1, const float* alpha2,
+                         const double* red, double count, int training, msb_tensor dy, msb_tensor dres,
+                         int dres_accumulate, float* dgamma, float* dbeta, float* dalpha1, float* dalpha2,
+                         int n, int64_t s, int groups, void* stream);
+
+/* dst = (accumulate ? dst : 0) + scale[n][c] * src.  nn.Dropout3D fwd/bwd (vnet.py:108,149-150) with the
+ * explicit [N,C] mask (0 or 2); scale==NULL means 1 (plain copy / add). */
+int msb_channel_scale(msb_tensor src, msb_tensor dst, const float* scale, int n, int64_t s, int accumulate,
+                      void* stream);
+
+/* ---- OutputTransition.conv2 (1x1x1, vnet.py:169,174) ------------------------------------------------ */
+/* logits NCDHW f32 [N,Co,S] = W[Co][Ci] * a + b */
+int msb_conv1x1_fwd(msb_tensor a, const float* w, const float* b, float* logits, int n, int ci, int co,
+                    int64_t s, void* stream);
+/* da = W^T dlogits;  dw += a (x) dlogits;  db += sum dlogits   (dw, db f32, accumulated atomically) */
+int msb_conv1x1_bwd(msb_tensor a, const float* w, const float* dlogits, msb_tensor da, float* dw, float* db,
+                    int n, int ci, int co, int64_t s, void* stream);
+
+/* ---- direct (CUDA-core) Conv3D / Conv3DTranspose for the HBM-bound layers ---------------------------
+ * vnet.py:67-68 (in_tr 1->16, k5), :98-99 (down_conv k=kernel,s=stride), :133-137 (up_conv, transposed).
+ * Weights/grads stay in the reference (Paddle) layouts: conv [Cout,Cin,kD,kH,kW]; convT [Cin,Cout,kD,kH,kW]. */
+/* in_tr: x NCDHW f32 [N,1,D,H,W], w [16][1][5][5][5]; out B8 (16 ch); optional BN partial sums (double [2][G][16]) */
+int msb_conv_in_fwd(const float* x, const float* w, const float* bias, msb_tensor out, int n, msb_dim3 dims,
+                    int groups, double* sums, void* stream);
+int msb_conv_in_wgrad(const float* x, msb_tensor dy, float* dw, float* dbias, int n, msb_dim3 dims, void* stream);
+/* c_*_real: channel counts of the weight tensor when the views are zero-padded wider (0 = same as the view).
+ * gather form (zero padding `pad`): out[o, oc] = bias[oc] + sum_{tap, rc} x[o*s + tap - pad, rc] * w[oc][rc][tap].
+ * = forward of nn.Conv3D (w = [Cout,Cin,k]) and input-gradient of nn.Conv3DTranspose (w = [Cin_T,Cout_T,k]). */
+int msb_conv_strided_fwd(msb_tensor x, const float* w, const float* bias, msb_tensor out, int n,
+                         msb_dim3 in_dims, msb_dim3 kernel, msb_dim3 stride, msb_dim3 pad, int c_red_real,
+                         int c_out_real, int groups, double* sums, void* stream);
+/* scatter form: out[i, oc] (+)= bias[oc] + sum_{tap, o: o*s+tap-pad==i} sum_rc x[o, rc] * w[rc][oc][tap].
+ * = input-gradient of nn.Conv3D (w = [Cout,Cin,k]) and forward of nn.Conv3DTranspose (w = [Cin_T,Cout_T,k]);
+ * out_dims = (in-1)*s + k - 2*pad.  Optional BN partial sums of the (rounded) outputs. */
+int msb_conv_strided_bwd_data(msb_tensor x, const float* w, const float* bias, msb_tensor out, int n,
+                              msb_dim3 out_dims, msb_dim3 kernel, msb_dim3 stride, msb_dim3 pad, int c_red_real,
+                              int c_out_real, int accumulate, int groups, double* sums, void* stream);
+/* dw[sc][bc][tap] += sum_o big[o*s+tap-pad, bc] * small[o, sc];  dbias += sum small (bias_from_big=0, nn.Conv3D:
+ * big = x, small = dy) or sum big (bias_from_big=1, nn.Conv3DTranspose: big = dy, small = x). */
+int msb_conv_strided_wgrad(msb_tensor big, msb_tensor small, float* dw, float* dbias, int n,
+                           msb_dim3 big_dims, msb_dim3 kernel, msb_dim3 stride, msb_dim3 pad, int c_big_real,
+                           int c_small_real, int bias_from_big, void* stream);
+
+/* ---- 5x5x5 Conv3D (pad 2, stride 1) on tcgen05 tensor cores ----------------------------------------
+ * vnet.py:36 (LUConv.conv1, 14x), :165-166 (out_tr.conv1).  bf16 operands, f32 accumulation in TMEM.     */
+/* packs the Paddle-layout f32 weight [Cout][Cin][125] into the bf16 UMMA operand image.
+ * mode 0: forward operand; mode 1: input-gradient operand (taps flipped, Cin/Cout swapped).
+ * cin_pad/cout_pad (multiples of 16) are the channel counts of the conv the packed operand will be used in. */
+size_t msb_conv_k5_packed_bytes(int cin_pad, int cout_pad);
+/* N (output-channel) padding the tensor-core kernel uses for an output view of `cout_view` channels */
+int msb_conv_k5_out_pad(int cout_view);
+int msb_conv_k5_pack(const float* w, void* packed, int cout, int cin, int mode, int cin_pad, int cout_pad,
+                     void* stream);
+/* out = conv(x) + bias (bias may be NULL, `cout` real output channels <= out.c); x.c must be a multiple of 16
+ * and the packed operand built with cin_pad = x.c, cout_pad = msb_conv_k5_out_pad(out.c).
+ * Optional BN partial sums (double [2][groups][out.c]) of the rounded outputs.
+ * accumulate: out += result * ch_scale[n][c] (ch_scale may be NULL) - used for input gradients. */
+int msb_conv_k5_fwd(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
+                    msb_dim3 dims, int accumulate, const float* ch_scale, int groups, double* sums, void* stream);
+/* dw [cout][cin][125] f32 += sum_v x[v+tap] (x) dy[v];  dbias[cout] += sum_v dy[v] (dbias may be NULL).
+ * workspace: msb_conv_k5_wgrad_workspace_bytes(cin, cout) bytes of device scratch. */
+size_t msb_conv_k5_wgrad_workspace_bytes(int cin, int cout);
+int msb_conv_k5_wgrad(msb_tensor x, msb_tensor dy, float* dw, float* dbias, int cout, int cin, int n,
+                      msb_dim3 dims, void* workspace, size_t workspace_bytes, void* stream);
+/* debug switches for bring-up (key 0/1: swap LBO/SBO in the fwd / wgrad UMMA descriptors) */
+int msb_debug_set(int key, int value);
+
+/* ---- fused Dice + cross-entropy loss ----------------------------------------------------------------
+ * models/losses/dice_loss.py:76-102, cross_entropy_loss.py:47-87, loss_utils.py:31-40, mixes_losses.py:52-60. */
+/* psum[C] (double) += sum over voxels of softmax(logits)[c]  (class_weights numerator/denominator) */
+int msb_class_weight_sums(const float* logits, int n, int c, int64_t s, double* psum, void* stream);
+int msb_class_weight_finalize(const double* psum, double count, int c, float* weights, void* stream);
+/* acc (double) [3C+2] += { I_c, sum p_c^2, sum t_c, ce_num, ce_den } */
+int msb_dice_ce_fwd(const float* logits, const int32_t* labels, const float* class_w, int n, int c, int64_t s,
+                    int ignore_index, double* acc, void* stream);
+/* result f32 [2+C] = { ce, dice_loss, per_channel_dice[C] } */
+int msb_dice_ce_finalize(const double* acc, int c, float* result, void* stream);
+/* dlogits = coef_ce * dCE/dz + coef_dice * dDice/dz; coef_dev (device f32[2], may be NULL) multiplies the
+ * two host coefficients so upstream gradients need no host synchronisation. */
+int msb_dice_ce_bwd(const float* logits, const int32_t* labels, const float* class_w, const double* acc,
+                    int n, int c, int64_t s, int ignore_index, float coef_ce, float coef_dice,
+                    const float* coef_dev, float* dlogits, void* stream);
+
+/* ---- optimizer.Momentum + L2 (cvlibs/config.py:212-214) on a flat parameter buffer ------------------
+ * g' = grad_scale*g + wd*p;  v = mu*v + g';  p -= lr*v                                                 */
+int msb_momentum_step(float* p, const float* g, float* v, int64_t count, float lr, float mu, float wd,
+                      float grad_scale, void* stream);
+
+/* ---- preprocessing (tools/preprocess_utils/values.py:54-87, geometry.py:31-69) -----------------------*/
+int msb_hunorm(const float* src, float* dst, int64_t count, float hu_min, float hu_max, float hu_nan, void* stream);
+/* minmax[2] f32 = {min, max} over src (NaNs ignored) */
+int msb_minmax(const float* src, int64_t count, float* minmax, void* stream);
+/* dst = clip((src - lo)/(hi - lo), 0, 1); if minmax != NULL lo/hi are read from device memory */
+int msb_normalize(const float* src, float* dst, int64_t count, float lo, float hi, const float* minmax, void* stream);
+/* scipy.ndimage.zoom(mode='nearest', order 0|1) with align-corners mapping.  pre_op: 0 none, 1 HUnorm
+ * applied to every fetched sample before interpolation (fused HUnorm+resample), 2 normalize(lo,hi). */
+int msb_resample_f32(const float* src, msb_dim3 in_dims, float* dst, msb_dim3 out_dims, int order, int pre_op,
+                     float p0, float p1, float p2, void* stream);
+int msb_resample_i32(const int32_t* src, msb_dim3 in_dims, int32_t* dst, msb_dim3 out_dims, void* stream);
+int msb_label_remap(int32_t* labels, int64_t count, const int32_t* keys, const int32_t* vals, int nmap, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEDSEG_B200_H_ */

@@ -1,0 +1,771 @@
+// 5x5x5 Conv3D (pad 2, stride 1) as an implicit GEMM on tcgen05 tensor cores — LUConv.conv1 (vnet.py:36),
+// OutputTransition.conv1 (vnet.py:165-166) and, with flipped/transposed weights, their input gradients.
+//
+// Data layout / mapping:
+//   * activations: B8 bf16 [N][C/8][D][H][W][8]; ONE 4-D TMA box per 16 input channels fetches the haloed tile
+//     [2 c8][TD+4][20][12][8ch] (zero-filled outside the volume = the conv padding) into shared memory.  That
+//     image IS the canonical SWIZZLE_NONE K-major UMMA operand: 8 consecutive w voxels x 16 B form a core matrix,
+//     so every one of the 125 taps is the same buffer viewed through a shifted 16-byte-aligned start address.
+//     The tile is fetched once and reused by 125 x TD MMAs (no im2col, no per-tap reload).
+//   * weights: packed bf16 [Cin/16][125][2][Cout][8] streamed by cp.async.bulk in 5-tap stages.
+//   * M = 128 output voxels (8 w x 16 h) of one d-plane, N = Cout, K = 16 channels per MMA; TD planes share a
+//     weight stage; accumulators (TD x N f32 columns) are double-buffered in TMEM so the epilogue of item i
+//     overlaps the MMAs of item i+1.
+//   * warp roles: w0 halo TMA, w1 MMA issue (one elected lane), w2 TMEM alloc + weight TMA, w4-7 epilogue.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace msb {
+
+constexpr int kTileW = 8, kTileH = 16;
+constexpr int kHaloW = kTileW + 4, kHaloH = kTileH + 4;
+constexpr int kTapsPerStage = 5;
+constexpr int kNumTaps = 125;
+constexpr int kStagesPerChunk = kNumTaps / kTapsPerStage;
+
+template <int NPAD, int TD>
+struct FwdCfg {
+  static constexpr int kHaloPlaneBytes = (TD + 4) * kHaloH * kHaloW * 16;  // one c8 plane of the haloed tile
+  static constexpr int kHaloBytes = 2 * kHaloPlaneBytes;                   // 16 input channels
+  static constexpr int kWTapBytes = 16 * NPAD * 2;                         // one tap, 16 ci x NPAD co bf16
+  static constexpr int kWStageBytes = kTapsPerStage * kWTapBytes;
+  static constexpr int kWStages = (NPAD >= 256) ? 3 : 4;
+  static constexpr int kAccCols = TD * NPAD;
+  static constexpr int kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : (2 * kAccCols <= 128) ? 128
+                                 : (2 * kAccCols <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = 2 * kHaloBytes + kWStages * kWStageBytes + 1024 /*barriers + stats*/ +
+                                    4 * 2 * NPAD * 4 + 128 /*alignment slack*/;
+  static_assert(2 * kAccCols <= 512, "TMEM overflow");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory overflow");
+};
+
+struct FwdParams {
+  int n, cin_pad, cout_real, out_c8;     // out_c8: 8-channel planes actually stored
+  int d, h, w;
+  int tiles_w, tiles_h, dblocks;
+  int x_c8_total;                        // planes per n in the TMA coordinate space of x
+  const void* packed;
+  const float* bias;
+  msb_tensor out;
+  int accumulate;
+  const float* ch_scale;
+  int groups;
+  double* sums;
+  int sums_c;                            // channel count of the sums array
+  int dbg_swap;
+};
+
+// 16 per-lane values -> per-channel totals over the warp; lane L ends up with the total of channel L>>1.
+__device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
+  float a[8], b[4], c[2];
+  bool hi = lane & 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = hi ? v[i] : v[i + 8], keep = hi ? v[i + 8] : v[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  hi = lane & 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = hi ? a[i] : a[i + 4], keep = hi ? a[i + 4] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  hi = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = hi ? b[i] : b[i + 2], keep = hi ? b[i + 2] : b[i];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  hi = lane & 2;
+  const float send = hi ? c[0] : c[1], keep = hi ? c[1] : c[0];
+  float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
+template <int NPAD, int TD>
+__global__ void __launch_bounds__(256, 1)
+    conv_k5_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const FwdParams p) {
+  using Cfg = FwdCfg<NPAD, TD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* halo_smem = smem;                                   // [2][kHaloBytes]
+  uint8_t* w_smem = halo_smem + 2 * Cfg::kHaloBytes;           // [kWStages][kWStageBytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + Cfg::kWStages * Cfg::kWStageBytes);
+  // barrier map: [0,2) halo_full  [2,4) halo_empty  [4,8) w_full  [8,12) w_empty  [12,14) acc_full  [14,16) acc_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  float* stat_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);  // [4 warps][2][NPAD]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = ptx::smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(0 + i), 1); ptx::mbar_init(BAR(2 + i), 1); }
+    for (int i = 0; i < 4; ++i) { ptx::mbar_init(BAR(4 + i), 1); ptx::mbar_init(BAR(8 + i), 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(12 + i), 1); ptx::mbar_init(BAR(14 + i), 4); }
+    ptx::fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 4 * 2 * NPAD; i += 256) stat_smem[i] = 0.f;
+  if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tmap_x);
+  if (warp == 2) ptx::tmem_alloc<Cfg::kTmemCols>(ptx::smem_u32(tmem_slot));
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int chunks = p.cin_pad / 16;
+  const int items_per_n = p.dblocks * p.tiles_h * p.tiles_w;
+  const int num_items = p.n * items_per_n;
+
+  if (warp == 0) {
+    // ================= halo TMA producer =================
+    if (lane == 0) {
+      uint32_t use = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int n = item / items_per_n;
+        int r = item % items_per_n;
+        const int tw = r % p.tiles_w; r /= p.tiles_w;
+        const int th = r % p.tiles_h; const int db = r / p.tiles_h;
+        for (int ck = 0; ck < chunks; ++ck, ++use) {
+          const uint32_t b = use & 1, ph = (use >> 1) & 1;
+          ptx::mbar_wait(BAR(2 + b), ph ^ 1);
+          ptx::mbar_expect_tx(BAR(0 + b), Cfg::kHaloBytes);
+          ptx::tma_load_4d(ptx::smem_u32(halo_smem + b * Cfg::kHaloBytes), &tmap_x, BAR(0 + b),
+                           (tw * kTileW - 2) * 8, th * kTileH - 2, db * TD - 2, n * p.x_c8_total + ck * 2);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================= weight producer =================
+    if (lane == 0) {
+      uint32_t use = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        for (int ck = 0; ck < chunks; ++ck) {
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.packed) + (size_t)ck * kNumTaps * Cfg::kWTapBytes;
+          for (int st = 0; st < kStagesPerChunk; ++st, ++use) {
+            const uint32_t s = use % Cfg::kWStages, ph = (use / Cfg::kWStages) & 1;
+            ptx::mbar_wait(BAR(8 + s), ph ^ 1);
+            ptx::mbar_expect_tx(BAR(4 + s), Cfg::kWStageBytes);
+            ptx::bulk_load(ptx::smem_u32(w_smem + s * Cfg::kWStageBytes), src + (size_t)st * Cfg::kWStageBytes,
+                           Cfg::kWStageBytes, BAR(4 + s));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, NPAD, 0, 0);
+      const uint32_t a_lbo = p.dbg_swap ? (uint32_t)(kHaloW * 16) : (uint32_t)Cfg::kHaloPlaneBytes;
+      const uint32_t a_sbo = p.dbg_swap ? (uint32_t)Cfg::kHaloPlaneBytes : (uint32_t)(kHaloW * 16);
+      const uint32_t b_lbo = p.dbg_swap ? 128u : (uint32_t)(NPAD * 16);
+      const uint32_t b_sbo = p.dbg_swap ? (uint32_t)(NPAD * 16) : 128u;
+      uint32_t huse = 0, wuse = 0, iuse = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
+        const uint32_t as = iuse & 1, aph = (iuse >> 1) & 1;
+        ptx::mbar_wait(BAR(14 + as), aph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_base = tmem_base + as * Cfg::kAccCols;
+        for (int ck = 0; ck < chunks; ++ck, ++huse) {
+          const uint32_t hb = huse & 1, hph = (huse >> 1) & 1;
+          ptx::mbar_wait(BAR(0 + hb), hph);
+          const uint32_t halo_addr = ptx::smem_u32(halo_smem + hb * Cfg::kHaloBytes);
+          const uint64_t a_desc0 = ptx::make_desc(halo_addr, a_lbo, a_sbo);
+          int tap = 0;
+          for (int st = 0; st < kStagesPerChunk; ++st, ++wuse) {
+            const uint32_t s = wuse % Cfg::kWStages, wph = (wuse / Cfg::kWStages) & 1;
+            ptx::mbar_wait(BAR(4 + s), wph);
+            ptx::tc_fence_after();
+            const uint64_t b_desc0 = ptx::make_desc(ptx::smem_u32(w_smem + s * Cfg::kWStageBytes), b_lbo, b_sbo);
+#pragma unroll
+            for (int t = 0; t < kTapsPerStage; ++t, ++tap) {
+              const int kd = tap / 25, kh = (tap / 5) % 5, kw = tap % 5;
+              const uint32_t a_off = (uint32_t)((kd * kHaloH + kh) * kHaloW + kw);  // 16-byte units
+              const uint64_t b_desc = b_desc0 + (uint64_t)((t * Cfg::kWTapBytes) >> 4);
+#pragma unroll
+              for (int td = 0; td < TD; ++td) {
+                const uint64_t a_desc = a_desc0 + (uint64_t)(a_off + td * kHaloH * kHaloW);
+                ptx::mma_bf16(d_base + td * NPAD, a_desc, b_desc, idesc, (ck | tap) != 0 ? 1u : 0u);
+              }
+            }
+            ptx::mma_commit(BAR(8 + s));  // weight stage free once these MMAs retire
+          }
+          ptx::mma_commit(BAR(2 + hb));   // halo buffer free
+        }
+        ptx::mma_commit(BAR(12 + as));    // accumulators complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue: TMEM -> registers -> (bias, accumulate, round, BN sums) -> global =================
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    const int hh = row >> 3, ww = row & 7;
+    const int64_t S = (int64_t)p.d * p.h * p.w;
+    float* my_stats = stat_smem + q * 2 * NPAD;
+    uint32_t iuse = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
+      const int n = item / items_per_n;
+      int r = item % items_per_n;
+      const int tw = r % p.tiles_w; r /= p.tiles_w;
+      const int th = r % p.tiles_h; const int db = r / p.tiles_h;
+      const int h = th * kTileH + hh, w = tw * kTileW + ww;
+      const bool inb = h < p.h && w < p.w;
+      const uint32_t as = iuse & 1, aph = (iuse >> 1) & 1;
+      ptx::mbar_wait(BAR(12 + as), aph);
+      ptx::tc_fence_after();
+      const uint32_t t_base = tmem_base + as * Cfg::kAccCols + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int td = 0; td < TD; ++td) {
+        const int d = db * TD + td;
+        const bool ok = inb && d < p.d;
+        const int64_t v = ((int64_t)d * p.h + h) * p.w + w;
+#pragma unroll 1
+        for (int cb = 0; cb < NPAD / 16; ++cb) {
+          float acc[16];
+          ptx::tmem_ld16(t_base + td * NPAD + cb * 16, acc);
+          float sq[16];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int c8 = cb * 2 + k;
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = c8 * 8 + j;
+              float val = acc[k * 8 + j] + ((p.bias != nullptr && c < p.cout_real) ? __ldg(p.bias + c) : 0.f);
+              o[j] = val;
+            }
+            if (c8 < p.out_c8) {
+              __nv_bfloat16* dst = view_ptr<__nv_bfloat16>(p.out, n, c8, S, ok ? v : 0);
+              if (p.accumulate) {
+                float old[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) old[j] = 0.f;
+                if (ok) Vec8<__nv_bfloat16>::load(dst, old);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float sc = p.ch_scale ? __ldg(p.ch_scale + (int64_t)n * p.out.c + c8 * 8 + j) : 1.f;
+                  o[j] = fmaf(o[j], sc, old[j]);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = ok ? Vec8<__nv_bfloat16>::round(o[j]) : 0.f;
+              if (ok) Vec8<__nv_bfloat16>::store(dst, o);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[k * 8 + j] = o[j]; sq[k * 8 + j] = o[j] * o[j]; }
+          }
+          if (p.sums != nullptr) {
+            const float s1 = warp_reduce16(acc, lane);
+            const float s2 = warp_reduce16(sq, lane);
+            if ((lane & 1) == 0) {
+              my_stats[cb * 16 + (lane >> 1)] += s1;
+              my_stats[NPAD + cb * 16 + (lane >> 1)] += s2;
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(BAR(14 + as));
+      if (p.sums != nullptr && p.groups > 1) {
+        // per-instance statistics: flush after every item (an item never straddles two n)
+        __syncwarp();
+        for (int i = lane; i < 2 * NPAD; i += 32) {
+          const int stat = i / NPAD, c = i % NPAD;
+          if (c < p.sums_c && my_stats[i] != 0.f)
+            atomicAdd(&p.sums[((int64_t)stat * p.groups + n) * p.sums_c + c], (double)my_stats[i]);
+          my_stats[i] = 0.f;
+        }
+        __syncwarp();
+      }
+    }
+    if (p.sums != nullptr && p.groups == 1) {
+      __syncwarp();
+      for (int i = lane; i < 2 * NPAD; i += 32) {
+        const int stat = i / NPAD, c = i % NPAD;
+        if (c < p.sums_c) atomicAdd(&p.sums[(int64_t)stat * p.sums_c + c], (double)my_stats[i]);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// =====================================================================================================
+// Weight gradient: dW[tap][co][ci] = sum_v X[v + tap][ci] * dY[v][co]  (K = voxels).
+//   A = X  tile, MN-major (8 channels contiguous = 16 B, 8 consecutive w voxels = one 128-B core matrix)
+//   B = dY tile, MN-major.   M = 128 rows = QM stacked kd-taps x min(Cin,128) channels: the X tile is stored
+//   [plane q][c8][h][w][8] so that the M-group stride (SBO) is uniform across the stacked planes.
+//   One MMA per (kh,kw) unit per 16-voxel K-step; up to 512/N units keep their accumulators in TMEM.
+// =====================================================================================================
+constexpr int kWgTileW = 16;
+
+template <int NPAD, int TH>
+struct WgCfg {
+  static constexpr int kGroupBytes = (TH + 4) * (kWgTileW + 4) * 16;  // one 8-channel M-group of the X halo tile
+  static constexpr int kXBytes = 16 * kGroupBytes;
+  static constexpr int kDyPlaneBytes = TH * kWgTileW * 16;
+  static constexpr int kDyBytes = (NPAD / 8) * kDyPlaneBytes;
+  static constexpr int kMaxUnits = (512 / NPAD) < 25 ? (512 / NPAD) : 25;
+  static constexpr int kSmemBytes = 2 * (kXBytes + kDyBytes) + 1024 + 128;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory overflow");
+};
+
+struct WgParams {
+  int n, cin_pad, cin_real, cout_real, dy_c8;
+  int d, h, w;
+  int tiles_w, tiles_h;
+  int x_c8_total, dy_c8_total;
+  int qm, kd_groups, mhalves, cin_m;    // stacked planes, ceil(5/qm), Cin/128, min(Cin,128)
+  int units_per_pass, passes_per_group; // (kh,kw) units per pass
+  int num_passes, chunks, tiles_per_chunk, total_tiles;
+  float* ws;                            // [125][cout_real][cin_real] f32
+  int dbg_swap;
+};
+
+template <int NPAD, int TH>
+__global__ void __launch_bounds__(256, 1)
+    conv_k5_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                         const WgParams p) {
+  using Cfg = WgCfg<NPAD, TH>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* x_smem = smem;                           // [2][kXBytes]
+  uint8_t* dy_smem = x_smem + 2 * Cfg::kXBytes;     // [2][kDyBytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dy_smem + 2 * Cfg::kDyBytes);
+  // [0,2) full  [2,4) empty  [4] acc_full  [5] acc_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = ptx::smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(2 + i), 1); }
+    ptx::mbar_init(BAR(4), 1);
+    ptx::mbar_init(BAR(5), 4);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmap_x); ptx::prefetch_tmap(&tmap_dy); }
+  if (warp == 2) ptx::tmem_alloc<512>(ptx::smem_u32(tmem_slot));
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_items = p.num_passes * p.chunks;
+  const int tiles_per_n = p.d * p.tiles_h * p.tiles_w;
+
+  auto decode_pass = [&](int pass, int& mh, int& g, int& u0, int& u1) {
+    const int pg = pass % p.passes_per_group;
+    g = (pass / p.passes_per_group) % p.kd_groups;
+    mh = pass / (p.passes_per_group * p.kd_groups);
+    u0 = pg * p.units_per_pass;
+    u1 = min(25, u0 + p.units_per_pass);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t use = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int pass = item / p.chunks, chunk = item % p.chunks;
+        int mh, g, u0, u1;
+        decode_pass(pass, mh, g, u0, u1);
+        const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+        const int planes_valid = min(p.qm, 5 - g * p.qm);
+        const int x_planes = p.cin_m / 8;  // c8 planes per stacked kd plane
+        const uint32_t bytes = (uint32_t)(planes_valid * x_planes * Cfg::kGroupBytes + p.dy_c8 * Cfg::kDyPlaneBytes);
+        for (int t = t0; t < t1; ++t, ++use) {
+          const int n = t / tiles_per_n;
+          int r = t % tiles_per_n;
+          const int tw = r % p.tiles_w; r /= p.tiles_w;
+          const int th = r % p.tiles_h; const int d = r / p.tiles_h;
+          const uint32_t b = use & 1, ph = (use >> 1) & 1;
+          ptx::mbar_wait(BAR(2 + b), ph ^ 1);
+          ptx::mbar_expect_tx(BAR(b), bytes);
+          for (int q = 0; q < planes_valid; ++q)
+            ptx::tma_load_4d(ptx::smem_u32(x_smem + b * Cfg::kXBytes + q * x_planes * Cfg::kGroupBytes), &tmap_x, BAR(b),
+                             (tw * kWgTileW - 2) * 8, th * TH - 2, d + g * p.qm + q - 2,
+                             n * p.x_c8_total + mh * 16);
+          ptx::tma_load_4d(ptx::smem_u32(dy_smem + b * Cfg::kDyBytes), &tmap_dy, BAR(b), tw * kWgTileW * 8, th * TH, d,
+                           n * p.dy_c8_total);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, NPAD, 1, 1);
+      const uint32_t a_lbo = p.dbg_swap ? (uint32_t)Cfg::kGroupBytes : 128u;
+      const uint32_t a_sbo = p.dbg_swap ? 128u : (uint32_t)Cfg::kGroupBytes;
+      const uint32_t b_lbo = p.dbg_swap ? (uint32_t)Cfg::kDyPlaneBytes : 128u;
+      const uint32_t b_sbo = p.dbg_swap ? 128u : (uint32_t)Cfg::kDyPlaneBytes;
+      uint32_t use = 0, iuse = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
+        const int pass = item / p.chunks, chunk = item % p.chunks;
+        int mh, g, u0, u1;
+        decode_pass(pass, mh, g, u0, u1);
+        const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+        ptx::mbar_wait(BAR(5), (iuse & 1) ^ 1);
+        ptx::tc_fence_after();
+        for (int t = t0; t < t1; ++t, ++use) {
+          const uint32_t b = use & 1, ph = (use >> 1) & 1;
+          ptx::mbar_wait(BAR(b), ph);
+          ptx::tc_fence_after();
+          const uint64_t a_desc0 = ptx::make_desc(ptx::smem_u32(x_smem + b * Cfg::kXBytes), a_lbo, a_sbo);
+          const uint64_t b_desc0 = ptx::make_desc(ptx::smem_u32(dy_smem + b * Cfg::kDyBytes), b_lbo, b_sbo);
+#pragma unroll 1
+          for (int hrow = 0; hrow < TH; ++hrow) {
+            const uint64_t b_desc = b_desc0 + (uint64_t)(hrow * kWgTileW);
+            const uint32_t acc = (t != t0 || hrow != 0) ? 1u : 0u;
+#pragma unroll 1
+            for (int u = u0; u < u1; ++u) {
+              const int kh = u / 5, kw = u % 5;
+              const uint64_t a_desc = a_desc0 + (uint64_t)((hrow + kh) * (kWgTileW + 4) + kw);
+              ptx::mma_bf16(tmem_base + (uint32_t)((u - u0) * NPAD), a_desc, b_desc, idesc, acc);
+            }
+          }
+          ptx::mma_commit(BAR(2 + b));
+        }
+        ptx::mma_commit(BAR(4));
+      }
+    }
+  } else if (warp >= 4) {
+    const int q4 = warp - 4;
+    const int row = q4 * 32 + lane;
+    const int qplane = row / p.cin_m, ci_local = row % p.cin_m;
+    uint32_t iuse = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
+      const int pass = item / p.chunks;
+      int mh, g, u0, u1;
+      decode_pass(pass, mh, g, u0, u1);
+      const int kd = g * p.qm + qplane;
+      const int ci = mh * 128 + ci_local;
+      const bool row_ok = (qplane < p.qm) && kd < 5 && ci < p.cin_real;
+      ptx::mbar_wait(BAR(4), iuse & 1);
+      ptx::tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
+#pragma unroll 1
+      for (int u = u0; u < u1; ++u) {
+        const int tap = kd * 25 + u;
+#pragma unroll 1
+        for (int cb = 0; cb < NPAD / 16; ++cb) {
+          float acc[16];
+          ptx::tmem_ld16(t_base + (u - u0) * NPAD + cb * 16, acc);
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int co = cb * 16 + j;
+              if (co < p.cout_real) atomicAdd(p.ws + ((int64_t)tap * p.cout_real + co) * p.cin_real + ci, acc[j]);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(BAR(5));
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// dw[co][ci][tap] += ws[tap][co][ci]
+__global__ void __launch_bounds__(256) wgrad_unpack_kernel(const float* __restrict__ ws, float* __restrict__ dw,
+                                                           int cout, int cin) {
+  const int64_t total = (int64_t)cout * cin * kNumTaps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % kNumTaps);
+    const int64_t r = i / kNumTaps;  // co*cin + ci
+    dw[i] += ws[(int64_t)tap * cout * cin + r];
+  }
+}
+
+__global__ void __launch_bounds__(256) channel_sum_bf16_kernel(msb_tensor x, int64_t s, int c_real,
+                                                               float* __restrict__ out) {
+  __shared__ float red[8][8];
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const int64_t chunk = 8192;
+  const int64_t v0 = (int64_t)blockIdx.x * chunk, v1 = min(v0 + chunk, s);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += 256) {
+    float a[8];
+    Vec8<__nv_bfloat16>::load(view_ptr<__nv_bfloat16>(x, n, c8, s, v), a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += a[j];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float r = warp_sum(acc[j]);
+    if (lane == 0) red[warp][j] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && c8 * 8 + threadIdx.x < c_real) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) t += red[wv][threadIdx.x];
+    atomicAdd(out + c8 * 8 + threadIdx.x, t);
+  }
+}
+
+// ---- weight packing ----------------------------------------------------------------------------------
+// packed[chunk][tap][k8][oc][j] (bf16), rc = chunk*16 + k8*8 + j
+__global__ void __launch_bounds__(256) pack_k5_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed,
+                                                      int cout, int cin, int mode, int cin_pad, int cout_pad) {
+  const int64_t total = (int64_t)cin_pad * kNumTaps * cout_pad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i & 7);
+    int64_t r = i >> 3;
+    const int oc = (int)(r % cout_pad); r /= cout_pad;
+    const int k8 = (int)(r & 1); r >>= 1;
+    const int tap = (int)(r % kNumTaps);
+    const int chunk = (int)(r / kNumTaps);
+    const int rc = chunk * 16 + k8 * 8 + j;
+    float v = 0.f;
+    if (mode == 0) {
+      if (oc < cout && rc < cin) v = __ldg(w + ((int64_t)oc * cin + rc) * kNumTaps + tap);
+    } else {
+      // input-gradient operand: reduction over the conv's Cout, produces its Cin, taps mirrored
+      if (rc < cout && oc < cin) v = __ldg(w + ((int64_t)rc * cin + oc) * kNumTaps + (kNumTaps - 1 - tap));
+    }
+    packed[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 4-D map over a B8 bf16 view: dims (W*8, H, D, planes), box (box_w*8, box_h, box_d, box_p)
+int make_b8_tmap(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 dims, int box_w, int box_h, int box_d,
+                 int box_p) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return MSB_ERR_CUDA;
+  }
+  const int64_t S = (int64_t)dims.d * dims.h * dims.w;
+  if (t.n_stride % (S * 8) != 0) {
+    set_error("tensor view: n_stride must be a multiple of D*H*W*8");
+    return MSB_ERR_INVALID;
+  }
+  const int64_t planes_total = t.n_stride / (S * 8);
+  const cuuint64_t gdim[4] = {(cuuint64_t)dims.w * 8, (cuuint64_t)dims.h, (cuuint64_t)dims.d,
+                              (cuuint64_t)((n - 1) * planes_total + t.c / 8)};
+  const cuuint64_t gstr[3] = {(cuuint64_t)dims.w * 16, (cuuint64_t)dims.h * dims.w * 16, (cuuint64_t)S * 16};
+  const cuuint32_t box[4] = {(cuuint32_t)box_w * 8, (cuuint32_t)box_h, (cuuint32_t)box_d, (cuuint32_t)box_p};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t.ptr, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (dims %d %d %d, planes %lld)", (int)r, dims.d, dims.h,
+              dims.w, (long long)gdim[3]);
+    return MSB_ERR_CUDA;
+  }
+  return MSB_OK;
+}
+
+int g_debug_flags[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+template <int NPAD, int TD>
+static int launch_fwd(const CUtensorMap& tmap, FwdParams& p, cudaStream_t st) {
+  using Cfg = FwdCfg<NPAD, TD>;
+  p.dblocks = (p.d + TD - 1) / TD;
+  const int items = p.n * p.dblocks * p.tiles_h * p.tiles_w;
+  const int grid = items < kNumSMs ? items : kNumSMs;
+  MSB_CUDA_OK(cudaFuncSetAttribute(conv_k5_fwd_kernel<NPAD, TD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::kSmemBytes));
+  conv_k5_fwd_kernel<NPAD, TD><<<grid, 256, Cfg::kSmemBytes, st>>>(tmap, p);
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+static inline int pad16(int c) { return (c + 15) / 16 * 16; }
+
+template <int NPAD, int TH>
+static int launch_wgrad(const msb_tensor& x, const msb_tensor& dy, WgParams& p, msb_dim3 dims, cudaStream_t st) {
+  using Cfg = WgCfg<NPAD, TH>;
+  p.tiles_w = (dims.w + kWgTileW - 1) / kWgTileW;
+  p.tiles_h = (dims.h + TH - 1) / TH;
+  p.total_tiles = p.n * dims.d * p.tiles_h * p.tiles_w;
+  const int amax = Cfg::kMaxUnits;
+  p.passes_per_group = (25 + amax - 1) / amax;
+  p.units_per_pass = (25 + p.passes_per_group - 1) / p.passes_per_group;
+  p.num_passes = p.mhalves * p.kd_groups * p.passes_per_group;
+  int chunks = (2 * kNumSMs + p.num_passes - 1) / p.num_passes;
+  if (chunks > p.total_tiles) chunks = p.total_tiles;
+  if (chunks < 1) chunks = 1;
+  p.tiles_per_chunk = (p.total_tiles + chunks - 1) / chunks;
+  p.chunks = (p.total_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+  CUtensorMap tmx, tmdy;
+  int rc;
+  if ((rc = make_b8_tmap(&tmx, x, p.n, dims, kWgTileW + 4, TH + 4, 1, p.cin_m / 8))) return rc;
+  if ((rc = make_b8_tmap(&tmdy, dy, p.n, dims, kWgTileW, TH, 1, dy.c / 8))) return rc;
+  const int items = p.num_passes * p.chunks;
+  const int grid = items < kNumSMs ? items : kNumSMs;
+  MSB_CUDA_OK(cudaFuncSetAttribute(conv_k5_wgrad_kernel<NPAD, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::kSmemBytes));
+  conv_k5_wgrad_kernel<NPAD, TH><<<grid, 256, Cfg::kSmemBytes, st>>>(tmx, tmdy, p);
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+
+}  // namespace msb
+
+using namespace msb;
+
+extern "C" {
+
+int msb_debug_set(int key, int value) {
+  if (key < 0 || key >= 8) return MSB_ERR_INVALID;
+  g_debug_flags[key] = value;
+  return MSB_OK;
+}
+
+size_t msb_conv_k5_packed_bytes(int cin_pad, int cout_pad) {
+  return (size_t)cin_pad * kNumTaps * cout_pad * sizeof(__nv_bfloat16);
+}
+
+int msb_conv_k5_pack(const float* w, void* packed, int cout, int cin, int mode, int cin_pad, int cout_pad,
+                     void* stream) {
+  MSB_REQUIRE(w && packed && cout > 0 && cin > 0 && (mode == 0 || mode == 1), "msb_conv_k5_pack: bad arguments");
+  MSB_REQUIRE(cin_pad % 16 == 0 && cout_pad % 16 == 0, "msb_conv_k5_pack: padded channel counts must be multiples of 16");
+  MSB_REQUIRE(mode == 0 ? (cin_pad >= cin && cout_pad >= cout) : (cin_pad >= cout && cout_pad >= cin),
+              "msb_conv_k5_pack: padded channel counts too small");
+  const int64_t total = (int64_t)cin_pad * kNumTaps * cout_pad;
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  pack_k5_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, mode,
+                                                        cin_pad, cout_pad);
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+int msb_conv_k5_fwd(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
+                    msb_dim3 dims, int accumulate, const float* ch_scale, int groups, double* sums, void* stream) {
+  MSB_REQUIRE(view_ok(x) && view_ok(out) && x.dtype == MSB_BF16 && out.dtype == MSB_BF16 && packed && n > 0,
+              "msb_conv_k5_fwd: bf16 B8 views required");
+  MSB_REQUIRE(dims.d > 0 && dims.h > 0 && dims.w > 0, "msb_conv_k5_fwd: bad dims");
+  MSB_REQUIRE(x.c % 16 == 0, "msb_conv_k5_fwd: input channels must be a multiple of 16 (pad the buffer)");
+  MSB_REQUIRE(cout > 0 && cout <= out.c && out.c <= 256, "msb_conv_k5_fwd: cout must fit the output view (<= 256)");
+  MSB_REQUIRE(groups == 1 || groups == n, "msb_conv_k5_fwd: groups must be 1 or n");
+  const int npad = pad16(out.c);
+  const int64_t S = (int64_t)dims.d * dims.h * dims.w;
+  FwdParams p;
+  p.n = n; p.cin_pad = x.c; p.cout_real = cout; p.out_c8 = out.c / 8;
+  p.d = dims.d; p.h = dims.h; p.w = dims.w;
+  p.tiles_w = (dims.w + kTileW - 1) / kTileW;
+  p.tiles_h = (dims.h + kTileH - 1) / kTileH;
+  p.x_c8_total = (int)(x.n_stride / (S * 8));
+  p.packed = packed; p.bias = bias; p.out = out; p.accumulate = accumulate; p.ch_scale = ch_scale;
+  p.groups = groups; p.sums = sums; p.sums_c = out.c; p.dbg_swap = g_debug_flags[0];
+  cudaStream_t st = as_stream(stream);
+  CUtensorMap tmap;
+  int rc;
+  int npad_sel = npad <= 16 ? 16 : npad <= 32 ? 32 : npad <= 64 ? 64 : npad <= 128 ? 128 : 256;
+  // NOTE: the packed operand must have been built with cout_pad == npad_sel.
+  switch (npad_sel) {
+    case 16:
+      if ((rc = make_b8_tmap(&tmap, x, n, dims, kHaloW, kHaloH, 4 + 4, 2))) return rc;
+      return launch_fwd<16, 4>(tmap, p, st);
+    case 32:
+      if ((rc = make_b8_tmap(&tmap, x, n, dims, kHaloW, kHaloH, 4 + 4, 2))) return rc;
+      return launch_fwd<32, 4>(tmap, p, st);
+    case 64:
+      if ((rc = make_b8_tmap(&tmap, x, n, dims, kHaloW, kHaloH, 4 + 4, 2))) return rc;
+      return launch_fwd<64, 4>(tmap, p, st);
+    case 128:
+      if ((rc = make_b8_tmap(&tmap, x, n, dims, kHaloW, kHaloH, 2 + 4, 2))) return rc;
+      return launch_fwd<128, 2>(tmap, p, st);
+    default:
+      if ((rc = make_b8_tmap(&tmap, x, n, dims, kHaloW, kHaloH, 1 + 4, 2))) return rc;
+      return launch_fwd<256, 1>(tmap, p, st);
+  }
+}
+
+int msb_conv_k5_out_pad(int cout_view);
+
+size_t msb_conv_k5_wgrad_workspace_bytes(int cin, int cout) { return (size_t)kNumTaps * cin * cout * sizeof(float); }
+
+int msb_conv_k5_wgrad(msb_tensor x, msb_tensor dy, float* dw, float* dbias, int cout, int cin, int n, msb_dim3 dims,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  MSB_REQUIRE(view_ok(x) && view_ok(dy) && x.dtype == MSB_BF16 && dy.dtype == MSB_BF16 && dw && n > 0,
+              "msb_conv_k5_wgrad: bf16 B8 views required");
+  MSB_REQUIRE(dims.d > 0 && dims.h > 0 && dims.w > 0, "msb_conv_k5_wgrad: bad dims");
+  MSB_REQUIRE(x.c == 16 || x.c == 32 || x.c == 64 || x.c == 128 || x.c == 256,
+              "msb_conv_k5_wgrad: input view must have 16/32/64/128/256 channels");
+  MSB_REQUIRE(cin > 0 && cin <= x.c && cout > 0 && cout <= dy.c && dy.c <= 256, "msb_conv_k5_wgrad: bad channel counts");
+  const size_t need = msb_conv_k5_wgrad_workspace_bytes(cin, cout);
+  MSB_REQUIRE(workspace && workspace_bytes >= need, "msb_conv_k5_wgrad: workspace too small (%zu < %zu)",
+              workspace_bytes, need);
+  cudaStream_t st = as_stream(stream);
+  MSB_CUDA_OK(cudaMemsetAsync(workspace, 0, need, st));
+  const int64_t S = (int64_t)dims.d * dims.h * dims.w;
+  WgParams p;
+  p.n = n; p.cin_pad = x.c; p.cin_real = cin; p.cout_real = cout; p.dy_c8 = dy.c / 8;
+  p.d = dims.d; p.h = dims.h; p.w = dims.w;
+  p.x_c8_total = (int)(x.n_stride / (S * 8));
+  p.dy_c8_total = (int)(dy.n_stride / (S * 8));
+  p.cin_m = x.c < 128 ? x.c : 128;
+  p.mhalves = x.c > 128 ? x.c / 128 : 1;
+  p.qm = 128 / p.cin_m;
+  const int qeff = p.qm < 5 ? p.qm : 5;
+  p.kd_groups = (5 + qeff - 1) / qeff;
+  p.ws = reinterpret_cast<float*>(workspace);
+  p.dbg_swap = g_debug_flags[1];
+  const int npad = msb_conv_k5_out_pad(dy.c);
+  int rc;
+  switch (npad) {
+    case 16: rc = launch_wgrad<16, 8>(x, dy, p, dims, st); break;
+    case 32: rc = launch_wgrad<32, 8>(x, dy, p, dims, st); break;
+    case 64: rc = launch_wgrad<64, 8>(x, dy, p, dims, st); break;
+    case 128: rc = launch_wgrad<128, 8>(x, dy, p, dims, st); break;
+    default: rc = launch_wgrad<256, 4>(x, dy, p, dims, st); break;
+  }
+  if (rc) return rc;
+  const int64_t total = (int64_t)cout * cin * kNumTaps;
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  wgrad_unpack_kernel<<<blocks, 256, 0, st>>>(p.ws, dw, cout, cin);
+  if (dbias != nullptr) {
+    const dim3 grid((unsigned)((S + 8191) / 8192), dy.c / 8, n);
+    channel_sum_bf16_kernel<<<grid, 256, 0, st>>>(dy, S, cout, dbias);
+  }
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+int msb_conv_k5_out_pad(int cout_view) {
+  const int npad = pad16(cout_view);
+  return npad <= 16 ? 16 : npad <= 32 ? 32 : npad <= 64 ? 64 : npad <= 128 ? 128 : 256;
+}
+
+}  // extern "C"

@@ -1,0 +1,665 @@
+// HBM-bound elementwise / reduction kernels of the VNet path (B8 layout), sm_100a.
+// One block owns a fixed (n, 8-channel plane) and a chunk of voxels, so per-channel parameters sit in
+// registers and per-channel reductions finish with one warp-shuffle tree + one double atomic per block.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace msb {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+constexpr int kThreads = 256;
+constexpr int kVoxPerBlock = 2048;
+
+static inline dim3 plane_grid(int n, int c, int64_t s) {
+  return dim3((unsigned)((s + kVoxPerBlock - 1) / kVoxPerBlock), (unsigned)(c / 8), (unsigned)n);
+}
+
+// block-level reduction of K per-thread floats; result valid in threads [0, K) of warp 0.. returned via smem
+template <int K>
+__device__ __forceinline__ void block_reduce_to_smem(float (&v)[K], float* smem /*[kThreads/32][K]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    float r = warp_sum(v[i]);
+    if (lane == 0) smem[warp * K + i] = r;
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) to_blocked_kernel(const float* __restrict__ src, int c, int64_t s,
+                                                               msb_tensor dst) {
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock;
+  const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int ch = c8 * 8 + j;
+      x[j] = ch < c ? __ldg(src + ((int64_t)n * c + ch) * s + v) : 0.f;
+    }
+    Vec8<T>::store(view_ptr<T>(dst, n, c8, s, v), x);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) from_blocked_kernel(msb_tensor src, float* __restrict__ dst, int c,
+                                                                 int64_t s) {
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock;
+  const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
+    float x[8];
+    Vec8<T>::load(view_ptr<T>(src, n, c8, s, v), x);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int ch = c8 * 8 + j;
+      if (ch < c) dst[((int64_t)n * c + ch) * s + v] = x[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bn_stats_kernel(msb_tensor x, int64_t s, int groups, int c_total,
+                                                            double* __restrict__ sums) {
+  __shared__ float red[kThreads / 32][16];
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock;
+  const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
+    float a[8];
+    Vec8<T>::load(view_ptr<T>(x, n, c8, s, v), a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j] += a[j];
+      acc[8 + j] += a[j] * a[j];
+    }
+  }
+  block_reduce_to_smem<16>(acc, &red[0][0]);
+  if (threadIdx.x < 16) {
+    double t = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) t += (double)red[w][threadIdx.x];
+    const int g = groups == 1 ? 0 : n;
+    const int stat = threadIdx.x >> 3, j = threadIdx.x & 7;
+    atomicAdd(&sums[((int64_t)stat * groups + g) * c_total + c8 * 8 + j], t);
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ rmean,
+                                   float* __restrict__ rvar, float momentum, float eps, int training, int c,
+                                   int groups, float* __restrict__ bnbuf) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const int64_t gc = (int64_t)groups * c;
+  double mean_acc = 0, var_acc = 0;
+  for (int g = 0; g < groups; ++g) {
+    double mean, var;
+    if (training) {
+      mean = sums[(int64_t)g * c + ch] / count;
+      var = sums[gc + (int64_t)g * c + ch] / count - mean * mean;
+      if (var < 0) var = 0;
+      mean_acc += mean;
+      var_acc += var;
+    } else {
+      mean = rmean[ch];
+      var = rvar[ch];
+    }
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float scale = gamma[ch] * invstd;
+    bnbuf[0 * gc + (int64_t)g * c + ch] = scale;
+    bnbuf[1 * gc + (int64_t)g * c + ch] = beta[ch] - (float)mean * scale;
+    bnbuf[2 * gc + (int64_t)g * c + ch] = (float)mean;
+    bnbuf[3 * gc + (int64_t)g * c + ch] = invstd;
+  }
+  if (training && rmean != nullptr) {
+    rmean[ch] = momentum * rmean[ch] + (1.f - momentum) * (float)(mean_acc / groups);
+    rvar[ch] = momentum * rvar[ch] + (1.f - momentum) * (float)(var_acc / groups);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct BnActParams {
+  float scale[8], shift[8], a1[8], a2[8];
+};
+
+__device__ __forceinline__ void load_params(BnActParams& p, const float* bnbuf, const float* alpha1,
+                                            const float* alpha2, int c_total, int groups, int g, int c8) {
+  const int64_t gc = (int64_t)groups * c_total;
+  const int64_t off = (int64_t)g * c_total + c8 * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    p.scale[j] = __ldg(bnbuf + off + j);
+    p.shift[j] = __ldg(bnbuf + gc + off + j);
+    p.a1[j] = __ldg(alpha1 + c8 * 8 + j);
+    p.a2[j] = alpha2 ? __ldg(alpha2 + c8 * 8 + j) : 0.f;
+  }
+}
+
+template <typename T, bool HAS_RES, bool HAS_TILE>
+__global__ void __launch_bounds__(kThreads)
+    bn_act_fwd_kernel(msb_tensor y, msb_tensor out, msb_tensor res, const float* __restrict__ tile_src, int tile_c,
+                      const float* __restrict__ bnbuf, const float* __restrict__ alpha1,
+                      const float* __restrict__ alpha2, int64_t s, int groups) {
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  BnActParams p;
+  load_params(p, bnbuf, alpha1, alpha2, y.c, groups, groups == 1 ? 0 : n, c8);
+  const int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock;
+  const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
+    float a[8], r[8];
+    Vec8<T>::load(view_ptr<T>(y, n, c8, s, v), a);
+    if (HAS_RES) Vec8<T>::load(view_ptr<T>(res, n, c8, s, v), r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = fmaf(a[j], p.scale[j], p.shift[j]);
+      if (HAS_TILE) t += __ldg(tile_src + ((int64_t)n * tile_c + ((c8 * 8 + j) % tile_c)) * s + v);
+      t = prelu(t, p.a1[j]);
+      if (HAS_RES) t = prelu(t + r[j], p.a2[j]);
+      a[j] = t;
+    }
+    Vec8<T>::store(view_ptr<T>(out, n, c8, s, v), a);
+  }
+}
+
+// recompute of the forward chain + gradient at the BN output (g1) and after the residual add (g2)
+template <bool HAS_RES>
+__device__ __forceinline__ void bwd_point(float yv, float rv, float tile, float go, float scale, float shift,
+                                          float a1, float a2, float& g1, float& g2, float& da1, float& da2) {
+  const float t = fmaf(yv, scale, shift) + tile;
+  const float act1 = prelu(t, a1);
+  if (HAS_RES) {
+    const float t2 = act1 + rv;
+    g2 = t2 > 0.f ? go : a2 * go;
+    da2 = t2 > 0.f ? 0.f : go * t2;
+  } else {
+    g2 = go;
+    da2 = 0.f;
+  }
+  g1 = t > 0.f ? g2 : a1 * g2;
+  da1 = t > 0.f ? 0.f : g2 * t;
+}
+
+template <typename T, bool HAS_RES, bool HAS_TILE>
+__global__ void __launch_bounds__(kThreads)
+    bn_act_bwd_reduce_kernel(msb_tensor y, msb_tensor res, const float* __restrict__ tile_src, int tile_c,
+                             msb_tensor gout, const float* __restrict__ bnbuf, const float* __restrict__ alpha1,
+                             const float* __restrict__ alpha2, int64_t s, int groups, double* __restrict__ red) {
+  __shared__ float sred[kThreads / 32][32];
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const int g = groups == 1 ? 0 : n;
+  BnActParams p;
+  load_params(p, bnbuf, alpha1, alpha2, y.c, groups, g, c8);
+  float mean[8], invstd[8];
+  {
+    const int64_t gc = (int64_t)groups * y.c, off = (int64_t)g * y.c + c8 * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mean[j] = __ldg(bnbuf + 2 * gc + off + j);
+      invstd[j] = __ldg(bnbuf + 3 * gc + off + j);
+    }
+  }
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  const int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock;
+  const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
+    float a[8], r[8], go[8];
+    Vec8<T>::load(view_ptr<T>(y, n, c8, s, v), a);
+    Vec8<T>::load(view_ptr<T>(gout, n, c8, s, v), go);
+    if (HAS_RES) Vec8<T>::load(view_ptr<T>(res, n, c8, s, v), r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float tile = 0.f;
+      if (HAS_TILE) tile = __ldg(tile_src + ((int64_t)n * tile_c + ((c8 * 8 + j) % tile_c)) * s + v);
+      float g1, g2, da1, da2;
+      bwd_point<HAS_RES>(a[j], HAS_RES ? r[j] : 0.f, tile, go[j], p.scale[j], p.shift[j], p.a1[j], p.a2[j], g1, g2,
+                         da1, da2);
+      const float xhat = (a[j] - mean[j]) * invstd[j];
+      acc[j] += g1;
+      acc[8 + j] += g1 * xhat;
+      acc[16 + j] += da1;
+      acc[24 + j] += da2;
+    }
+  }
+  block_reduce_to_smem<32>(acc, &sred[0][0]);
+  if (threadIdx.x < 32) {
+    double t = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) t += (double)sred[w][threadIdx.x];
+    const int stat = threadIdx.x >> 3, j = threadIdx.x & 7;
+    atomicAdd(&red[((int64_t)stat * groups + g) * y.c + c8 * 8 + j], t);
+  }
+}
+
+template <typename T, bool HAS_RES, bool HAS_TILE, bool HAS_DRES>
+__global__ void __launch_bounds__(kThreads)
+    bn_act_bwd_apply_kernel(msb_tensor y, msb_tensor res, const float* __restrict__ tile_src, int tile_c,
+                            msb_tensor gout, const float* __restrict__ bnbuf, const float* __restrict__ alpha1,
+                            const float* __restrict__ alpha2, const double* __restrict__ red, double count,
+                            int training, msb_tensor dy, msb_tensor dres, int dres_acc, int64_t s, int groups) {
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  const int g = groups == 1 ? 0 : n;
+  BnActParams p;
+  load_params(p, bnbuf, alpha1, alpha2, y.c, groups, g, c8);
+  float mean[8], invstd[8], m_g1[8], m_g1x[8];
+  {
+    const int64_t gc = (int64_t)groups * y.c, off = (int64_t)g * y.c + c8 * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mean[j] = __ldg(bnbuf + 2 * gc + off + j);
+      invstd[j] = __ldg(bnbuf + 3 * gc + off + j);
+      m_g1[j] = training ? (float)(red[off + j] / count) : 0.f;
+      m_g1x[j] = training ? (float)(red[gc + off + j] / count) : 0.f;
+    }
+  }
+  const int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock;
+  const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
+    float a[8], r[8], go[8], dr[8];
+    Vec8<T>::load(view_ptr<T>(y, n, c8, s, v), a);
+    Vec8<T>::load(view_ptr<T>(gout, n, c8, s, v), go);
+    if (HAS_RES) Vec8<T>::load(view_ptr<T>(res, n, c8, s, v), r);
+    if (HAS_DRES && dres_acc) Vec8<T>::load(view_ptr<T>(dres, n, c8, s, v), dr);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float tile = 0.f;
+      if (HAS_TILE) tile = __ldg(tile_src + ((int64_t)n * tile_c + ((c8 * 8 + j) % tile_c)) * s + v);
+      float g1, g2, da1, da2;
+      bwd_point<HAS_RES>(a[j], HAS_RES ? r[j] : 0.f, tile, go[j], p.scale[j], p.shift[j], p.a1[j], p.a2[j], g1, g2,
+                         da1, da2);
+      const float xhat = (a[j] - mean[j]) * invstd[j];
+      a[j] = p.scale[j] * (g1 - m_g1[j] - xhat * m_g1x[j]);
+      if (HAS_DRES) dr[j] = (dres_acc ? dr[j] : 0.f) + g2;
+    }
+    Vec8<T>::store(view_ptr<T>(dy, n, c8, s, v), a);
+    if (HAS_DRES) Vec8<T>::store(view_ptr<T>(dres, n, c8, s, v), dr);
+  }
+}
+
+__global__ void bn_param_grad_kernel(const double* __restrict__ red, int c, int groups, float* dgamma, float* dbeta,
+                                     float* dalpha1, float* dalpha2) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const int64_t gc = (int64_t)groups * c;
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  for (int g = 0; g < groups; ++g) {
+    s0 += red[0 * gc + (int64_t)g * c + ch];
+    s1 += red[1 * gc + (int64_t)g * c + ch];
+    s2 += red[2 * gc + (int64_t)g * c + ch];
+    s3 += red[3 * gc + (int64_t)g * c + ch];
+  }
+  if (dbeta) dbeta[ch] += (float)s0;
+  if (dgamma) dgamma[ch] += (float)s1;
+  if (dalpha1) dalpha1[ch] += (float)s2;
+  if (dalpha2) dalpha2[ch] += (float)s3;
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) channel_scale_kernel(msb_tensor src, msb_tensor dst,
+                                                                 const float* __restrict__ scale, int64_t s,
+                                                                 int accumulate) {
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  float sc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sc[j] = scale ? __ldg(scale + (int64_t)n * src.c + c8 * 8 + j) : 1.f;
+  const int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock;
+  const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
+    float a[8], d[8];
+    Vec8<T>::load(view_ptr<T>(src, n, c8, s, v), a);
+    if (accumulate) Vec8<T>::load(view_ptr<T>(dst, n, c8, s, v), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = (accumulate ? d[j] : 0.f) + a[j] * sc[j];
+    Vec8<T>::store(view_ptr<T>(dst, n, c8, s, v), a);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// OutputTransition.conv2: 1x1x1 conv C->C producing NCDHW f32 logits (vnet.py:169,174)
+constexpr int kHeadMaxC = 32;
+
+template <typename T, int CI8>
+__global__ void __launch_bounds__(kThreads) conv1x1_fwd_kernel(msb_tensor a, const float* __restrict__ w,
+                                                               const float* __restrict__ b,
+                                                               float* __restrict__ logits, int ci, int co, int64_t s) {
+  __shared__ float ws[kHeadMaxC * kHeadMaxC + kHeadMaxC];
+  for (int i = threadIdx.x; i < co * ci; i += kThreads) ws[i] = w[i];
+  for (int i = threadIdx.x; i < co; i += kThreads) ws[kHeadMaxC * kHeadMaxC + i] = b ? b[i] : 0.f;
+  __syncthreads();
+  const int n = blockIdx.z;
+  const int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock;
+  const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
+    float x[CI8 * 8];
+#pragma unroll
+    for (int k = 0; k < CI8; ++k) {
+      float t[8];
+      Vec8<T>::load(view_ptr<T>(a, n, k, s, v), t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[k * 8 + j] = t[j];
+    }
+    for (int o = 0; o < co; ++o) {
+      float acc = ws[kHeadMaxC * kHeadMaxC + o];
+#pragma unroll
+      for (int i = 0; i < CI8 * 8; ++i)
+        if (i < ci) acc = fmaf(ws[o * ci + i], x[i], acc);
+      logits[((int64_t)n * co + o) * s + v] = acc;
+    }
+  }
+}
+
+constexpr int kHeadTile = 128;  // voxels staged per inner step of the backward kernel
+
+template <typename T, int CI8>
+__global__ void __launch_bounds__(kHeadTile)
+    conv1x1_bwd_kernel(msb_tensor a, const float* __restrict__ w, const float* __restrict__ dlogits, msb_tensor da,
+                       float* __restrict__ dw, float* __restrict__ db, int ci, int co, int64_t s) {
+  // smem: W, staged a [ci][tile+1], staged dl [co][tile+1], per-pair accumulators
+  __shared__ float ws[kHeadMaxC * kHeadMaxC];
+  __shared__ float as[CI8 * 8][kHeadTile + 1];
+  __shared__ float ds[CI8 * 8][kHeadTile + 1];
+  __shared__ float accw[kHeadMaxC * kHeadMaxC + kHeadMaxC];
+  for (int i = threadIdx.x; i < co * ci; i += kHeadTile) ws[i] = w[i];
+  for (int i = threadIdx.x; i < kHeadMaxC * kHeadMaxC + kHeadMaxC; i += kHeadTile) accw[i] = 0.f;
+  __syncthreads();
+  const int n = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock;
+  const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
+  const int npairs = co * ci + co;  // last `co` pseudo-pairs accumulate the bias gradient
+  for (int64_t base = v0; base < v1; base += kHeadTile) {
+    const int64_t v = base + threadIdx.x;
+    const bool valid = v < v1;
+    float x[CI8 * 8], g[CI8 * 8];
+#pragma unroll
+    for (int i = 0; i < CI8 * 8; ++i) x[i] = g[i] = 0.f;
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < CI8; ++k) {
+        float t[8];
+        Vec8<T>::load(view_ptr<T>(a, n, k, s, v), t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[k * 8 + j] = t[j];
+      }
+#pragma unroll
+      for (int o = 0; o < CI8 * 8; ++o)
+        if (o < co) g[o] = __ldg(dlogits + ((int64_t)n * co + o) * s + v);
+    }
+#pragma unroll
+    for (int i = 0; i < CI8 * 8; ++i) {
+      as[i][threadIdx.x] = x[i];
+      ds[i][threadIdx.x] = g[i];
+    }
+    if (valid) {
+      // da[i] = sum_o W[o][i] * g[o]
+#pragma unroll
+      for (int k = 0; k < CI8; ++k) {
+        float t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int i = k * 8 + j;
+          float acc = 0.f;
+          if (i < ci) {
+#pragma unroll
+            for (int o = 0; o < CI8 * 8; ++o)
+              if (o < co) acc = fmaf(ws[o * ci + i], g[o], acc);
+          }
+          t[j] = acc;
+        }
+        Vec8<T>::store(view_ptr<T>(da, n, k, s, v), t);
+      }
+    }
+    __syncthreads();
+    for (int pidx = warp; pidx < npairs; pidx += kHeadTile / 32) {
+      float acc = 0.f;
+      if (pidx < co * ci) {
+        const int o = pidx / ci, i = pidx % ci;
+        for (int t = lane; t < kHeadTile; t += 32) acc = fmaf(as[i][t], ds[o][t], acc);
+      } else {
+        const int o = pidx - co * ci;
+        for (int t = lane; t < kHeadTile; t += 32) acc += ds[o][t];
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) accw[pidx] += acc;
+    }
+    __syncthreads();
+  }
+  for (int pidx = threadIdx.x; pidx < npairs; pidx += kHeadTile) {
+    if (pidx < co * ci) atomicAdd(dw + pidx, accw[pidx]);
+    else if (db) atomicAdd(db + (pidx - co * ci), accw[pidx]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) momentum_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                       float* __restrict__ v, int64_t count, float lr, float mu,
+                                                       float wd, float gs) {
+  const int64_t n4 = count >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    vv.x = fmaf(mu, vv.x, fmaf(gs, gg.x, wd * pp.x));
+    vv.y = fmaf(mu, vv.y, fmaf(gs, gg.y, wd * pp.y));
+    vv.z = fmaf(mu, vv.z, fmaf(gs, gg.z, wd * pp.z));
+    vv.w = fmaf(mu, vv.w, fmaf(gs, gg.w, wd * pp.w));
+    pp.x -= lr * vv.x; pp.y -= lr * vv.y; pp.z -= lr * vv.z; pp.w -= lr * vv.w;
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const float vv = fmaf(mu, v[i], fmaf(gs, g[i], wd * p[i]));
+    v[i] = vv;
+    p[i] -= lr * vv;
+  }
+}
+
+}  // namespace msb
+
+using namespace msb;
+
+extern "C" {
+
+int msb_version(void) { return MSB_VERSION; }
+const char* msb_last_error_string(void) { return msb::last_error(); }
+
+int msb_to_blocked(const float* src, int n, int c, int64_t s, msb_tensor dst, void* stream) {
+  MSB_REQUIRE(src && view_ok(dst) && n > 0 && c > 0 && c <= dst.c && s > 0, "msb_to_blocked: bad arguments");
+  MSB_DISPATCH_DTYPE(dst.dtype, to_blocked_kernel<T><<<plane_grid(n, dst.c, s), kThreads, 0, as_stream(stream)>>>(
+                                    src, c, s, dst););
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+int msb_from_blocked(msb_tensor src, float* dst, int n, int c, int64_t s, void* stream) {
+  MSB_REQUIRE(dst && view_ok(src) && n > 0 && c > 0 && c <= src.c && s > 0, "msb_from_blocked: bad arguments");
+  MSB_DISPATCH_DTYPE(src.dtype,
+                     from_blocked_kernel<T><<<plane_grid(n, ((c + 7) / 8) * 8, s), kThreads, 0, as_stream(stream)>>>(
+                         src, dst, c, s););
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+int msb_bn_stats(msb_tensor x, int n, int64_t s, int groups, double* sums, void* stream) {
+  MSB_REQUIRE(view_ok(x) && sums && n > 0 && s > 0 && (groups == 1 || groups == n), "msb_bn_stats: bad arguments");
+  MSB_DISPATCH_DTYPE(x.dtype, bn_stats_kernel<T><<<plane_grid(n, x.c, s), kThreads, 0, as_stream(stream)>>>(
+                                  x, s, groups, x.c, sums););
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+int msb_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, float momentum, float eps, int training, int c, int groups, float* bnbuf,
+                    void* stream) {
+  MSB_REQUIRE(gamma && beta && bnbuf && c > 0 && groups > 0, "msb_bn_finalize: bad arguments");
+  MSB_REQUIRE(training ? (sums != nullptr && count > 0) : (running_mean && running_var),
+              "msb_bn_finalize: training needs sums, eval needs running stats");
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(sums, count, gamma, beta, running_mean,
+                                                                      running_var, momentum, eps, training, c, groups,
+                                                                      bnbuf);
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+#define MSB_BOOL_DISPATCH2(b0, b1, ...)                          \
+  do {                                                           \
+    if (b0) {                                                    \
+      constexpr bool B0 = true;                                  \
+      if (b1) { constexpr bool B1 = true; __VA_ARGS__ }          \
+      else { constexpr bool B1 = false; __VA_ARGS__ }            \
+    } else {                                                     \
+      constexpr bool B0 = false;                                 \
+      if (b1) { constexpr bool B1 = true; __VA_ARGS__ }          \
+      else { constexpr bool B1 = false; __VA_ARGS__ }            \
+    }                                                            \
+  } while (0)
+
+int msb_bn_act_fwd(msb_tensor y, msb_tensor out, msb_tensor residual, const float* tile_src, int tile_c,
+                   const float* bnbuf, const float* alpha1, const float* alpha2, int n, int64_t s, int groups,
+                   void* stream) {
+  const bool has_res = residual.ptr != nullptr;
+  MSB_REQUIRE(view_ok(y) && view_ok(out) && out.c == y.c && out.dtype == y.dtype && bnbuf && alpha1,
+              "msb_bn_act_fwd: bad y/out/bnbuf/alpha1");
+  MSB_REQUIRE(!has_res || (view_ok(residual) && residual.c == y.c && residual.dtype == y.dtype && alpha2),
+              "msb_bn_act_fwd: residual needs matching view and alpha2");
+  MSB_REQUIRE(!tile_src || tile_c > 0, "msb_bn_act_fwd: tile_c must be > 0");
+  MSB_REQUIRE(groups == 1 || groups == n, "msb_bn_act_fwd: groups must be 1 or n");
+  MSB_DISPATCH_DTYPE(y.dtype, MSB_BOOL_DISPATCH2(has_res, tile_src != nullptr,
+                                                 bn_act_fwd_kernel<T, B0, B1>
+                                                 <<<plane_grid(n, y.c, s), kThreads, 0, as_stream(stream)>>>(
+                                                     y, out, residual, tile_src, tile_c, bnbuf, alpha1, alpha2, s,
+                                                     groups);););
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+int msb_bn_act_bwd_reduce(msb_tensor y, msb_tensor residual, const float* tile_src, int tile_c, msb_tensor gout,
+                          const float* bnbuf, const float* alpha1, const float* alpha2, int n, int64_t s, int groups,
+                          double* red, void* stream) {
+  const bool has_res = residual.ptr != nullptr;
+  MSB_REQUIRE(view_ok(y) && view_ok(gout) && gout.c == y.c && gout.dtype == y.dtype && bnbuf && alpha1 && red,
+              "msb_bn_act_bwd_reduce: bad arguments");
+  MSB_REQUIRE(!has_res || (view_ok(residual) && residual.c == y.c && residual.dtype == y.dtype && alpha2),
+              "msb_bn_act_bwd_reduce: residual needs matching view and alpha2");
+  MSB_REQUIRE(groups == 1 || groups == n, "msb_bn_act_bwd_reduce: groups must be 1 or n");
+  MSB_DISPATCH_DTYPE(y.dtype, MSB_BOOL_DISPATCH2(has_res, tile_src != nullptr,
+                                                 bn_act_bwd_reduce_kernel<T, B0, B1>
+                                                 <<<plane_grid(n, y.c, s), kThreads, 0, as_stream(stream)>>>(
+                                                     y, residual, tile_src, tile_c, gout, bnbuf, alpha1, alpha2, s,
+                                                     groups, red);););
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+int msb_bn_act_bwd_apply(msb_tensor y, msb_tensor residual, const float* tile_src, int tile_c, msb_tensor gout,
+                         const float* bnbuf, const float* alpha1, const float* alpha2, const double* red, double count,
+                         int training, msb_tensor dy, msb_tensor dres, int dres_accumulate, float* dgamma,
+                         float* dbeta, float* dalpha1, float* dalpha2, int n, int64_t s, int groups, void* stream) {
+  const bool has_res = residual.ptr != nullptr;
+  const bool has_dres = dres.ptr != nullptr;
+  MSB_REQUIRE(view_ok(y) && view_ok(gout) && view_ok(dy) && gout.c == y.c && dy.c == y.c && gout.dtype == y.dtype &&
+                  dy.dtype == y.dtype && bnbuf && alpha1 && red && count > 0,
+              "msb_bn_act_bwd_apply: bad arguments");
+  MSB_REQUIRE(!has_res || (view_ok(residual) && residual.c == y.c && residual.dtype == y.dtype && alpha2),
+              "msb_bn_act_bwd_apply: residual needs matching view and alpha2");
+  MSB_REQUIRE(!has_dres || (has_res && view_ok(dres) && dres.c == y.c && dres.dtype == y.dtype),
+              "msb_bn_act_bwd_apply: dres needs a residual and a matching view");
+  MSB_REQUIRE(groups == 1 || groups == n, "msb_bn_act_bwd_apply: groups must be 1 or n");
+  cudaStream_t st = as_stream(stream);
+  const dim3 grid = plane_grid(n, y.c, s);
+  MSB_DISPATCH_DTYPE(
+      y.dtype, MSB_BOOL_DISPATCH2(has_res, tile_src != nullptr, {
+        if (has_dres)
+          bn_act_bwd_apply_kernel<T, B0, B1, true><<<grid, kThreads, 0, st>>>(
+              y, residual, tile_src, tile_c, gout, bnbuf, alpha1, alpha2, red, count, training, dy, dres,
+              dres_accumulate, s, groups);
+        else
+          bn_act_bwd_apply_kernel<T, B0, B1, false><<<grid, kThreads, 0, st>>>(
+              y, residual, tile_src, tile_c, gout, bnbuf, alpha1, alpha2, red, count, training, dy, dres,
+              dres_accumulate, s, groups);
+      }););
+  MSB_LAUNCH_OK();
+  if (dgamma || dbeta || dalpha1 || dalpha2) {
+    bn_param_grad_kernel<<<(y.c + 127) / 128, 128, 0, st>>>(red, y.c, groups, dgamma, dbeta, dalpha1,
+                                                            has_res ? dalpha2 : nullptr);
+    MSB_LAUNCH_OK();
+  }
+  return MSB_OK;
+}
+
+int msb_channel_scale(msb_tensor src, msb_tensor dst, const float* scale, int n, int64_t s, int accumulate,
+                      void* stream) {
+  MSB_REQUIRE(view_ok(src) && view_ok(dst) && src.c == dst.c && src.dtype == dst.dtype && n > 0 && s > 0,
+              "msb_channel_scale: bad arguments");
+  MSB_DISPATCH_DTYPE(src.dtype, channel_scale_kernel<T><<<plane_grid(n, src.c, s), kThreads, 0, as_stream(stream)>>>(
+                                    src, dst, scale, s, accumulate););
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+int msb_conv1x1_fwd(msb_tensor a, const float* w, const float* b, float* logits, int n, int ci, int co, int64_t s,
+                    void* stream) {
+  MSB_REQUIRE(view_ok(a) && w && logits && ci > 0 && ci <= a.c && a.c <= kHeadMaxC && co > 0 && co <= a.c,
+              "msb_conv1x1_fwd: needs ci <= a.c <= 32 and co <= a.c");
+  const dim3 grid((unsigned)((s + kVoxPerBlock - 1) / kVoxPerBlock), 1, (unsigned)n);
+  cudaStream_t st = as_stream(stream);
+  MSB_DISPATCH_DTYPE(a.dtype, {
+    if (a.c == 8) conv1x1_fwd_kernel<T, 1><<<grid, kThreads, 0, st>>>(a, w, b, logits, ci, co, s);
+    else if (a.c == 16) conv1x1_fwd_kernel<T, 2><<<grid, kThreads, 0, st>>>(a, w, b, logits, ci, co, s);
+    else if (a.c == 24) conv1x1_fwd_kernel<T, 3><<<grid, kThreads, 0, st>>>(a, w, b, logits, ci, co, s);
+    else conv1x1_fwd_kernel<T, 4><<<grid, kThreads, 0, st>>>(a, w, b, logits, ci, co, s);
+  });
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+int msb_conv1x1_bwd(msb_tensor a, const float* w, const float* dlogits, msb_tensor da, float* dw, float* db, int n,
+                    int ci, int co, int64_t s, void* stream) {
+  MSB_REQUIRE(view_ok(a) && view_ok(da) && da.c == a.c && da.dtype == a.dtype && w && dlogits && dw && ci > 0 &&
+                  ci <= a.c && a.c <= kHeadMaxC && co > 0 && co <= a.c,
+              "msb_conv1x1_bwd: needs ci <= a.c <= 32 and co <= a.c");
+  const dim3 grid((unsigned)((s + kVoxPerBlock - 1) / kVoxPerBlock), 1, (unsigned)n);
+  cudaStream_t st = as_stream(stream);
+  MSB_DISPATCH_DTYPE(a.dtype, {
+    if (a.c == 8) conv1x1_bwd_kernel<T, 1><<<grid, kHeadTile, 0, st>>>(a, w, dlogits, da, dw, db, ci, co, s);
+    else if (a.c == 16) conv1x1_bwd_kernel<T, 2><<<grid, kHeadTile, 0, st>>>(a, w, dlogits, da, dw, db, ci, co, s);
+    else if (a.c == 24) conv1x1_bwd_kernel<T, 3><<<grid, kHeadTile, 0, st>>>(a, w, dlogits, da, dw, db, ci, co, s);
+    else conv1x1_bwd_kernel<T, 4><<<grid, kHeadTile, 0, st>>>(a, w, dlogits, da, dw, db, ci, co, s);
+  });
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+int msb_momentum_step(float* p, const float* g, float* v, int64_t count, float lr, float mu, float wd,
+                      float grad_scale, void* stream) {
+  MSB_REQUIRE(p && g && v && count > 0, "msb_momentum_step: bad arguments");
+  MSB_REQUIRE((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(v)) % 16 == 0,
+              "msb_momentum_step: buffers must be 16-byte aligned");
+  int64_t want = (count / 4 + 255) / 256 + 1;
+  const int blocks = (int)(want < (int64_t)kNumSMs * 8 ? want : (int64_t)kNumSMs * 8);
+  momentum_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, v, count, lr, mu, wd, grad_scale);
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,2 @@
+from .vnet import VNet  # noqa: F401
+from .losses import CrossEntropyLoss, DiceLoss, MixedLoss  # noqa: F401

@@ -1,0 +1,179 @@
+"""DiceLoss / CrossEntropyLoss / MixedLoss with the reference signatures, running on ONE fused CUDA pass.
+
+Reference: medicalseg/models/losses/dice_loss.py:23-102, cross_entropy_loss.py:23-87, loss_utils.py:18-40,
+mixes_losses.py:22-60.  Behaviours kept on purpose:
+  * Dice uses sigmoid(logits), the V-Net squared denominator, eps clip 1e-6, includes background, mean over classes;
+    returns (loss, per_channel_dice ndarray) — the ndarray costs a device->host sync exactly as in the reference.
+  * CrossEntropyLoss(weight=None) computes class weights sum(1-p)/sum(p) from the FIRST logits it ever sees and
+    caches them on the module (cross_entropy_loss.py:68-69).
+  * MixedLoss returns ([coef_i * loss_i], per_channel_dice).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from .. import ops
+
+
+class _DiceCEFunction(torch.autograd.Function):
+    """result[0] = CE, result[1] = Dice loss, result[2:] = per-channel Dice; gradient flows to logits only."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, class_w, ignore_index):
+        n, c = logits.shape[:2]
+        acc = torch.zeros(3 * c + 2, dtype=torch.float64, device=logits.device)
+        result = torch.empty(2 + c, dtype=torch.float32, device=logits.device)
+        ops.dice_ce_fwd(logits, labels, class_w, ignore_index, acc)
+        ops.dice_ce_finalize(acc, c, result)
+        ctx.save_for_backward(logits, labels, class_w, acc)
+        ctx.ignore_index = ignore_index
+        return result
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, labels, class_w, acc = ctx.saved_tensors
+        dlogits = torch.empty_like(logits)
+        coef = g[:2].contiguous().float()
+        ops.dice_ce_bwd(logits, labels, class_w, acc, ctx.ignore_index, 1.0, 1.0, coef, dlogits)
+        return dlogits, None, None, None
+
+
+def _prep(logits, labels):
+    if not logits.is_cuda:
+        raise RuntimeError("medicalseg_b200 losses need CUDA tensors (no CPU fallback)")
+    if logits.dim() == 4:
+        logits = logits.unsqueeze(0)
+    if labels.dim() == 3:
+        labels = labels.unsqueeze(0)
+    assert "int" in str(labels.dtype), "The label should be int but got {}".format(labels.dtype)
+    return logits.float().contiguous(), labels.to(torch.int32).contiguous()
+
+
+def class_weights(logits: torch.Tensor) -> torch.Tensor:
+    """models/losses/loss_utils.py:31-40 on the GPU: w_c = sum(1-softmax_c) / sum(softmax_c)."""
+    n, c = logits.shape[:2]
+    psum = torch.zeros(c, dtype=torch.float64, device=logits.device)
+    w = torch.empty(c, dtype=torch.float32, device=logits.device)
+    ops.class_weight_sums(logits, psum)
+    ops.class_weight_finalize(psum, float(n * logits[0, 0].numel()), c, w)
+    return w
+
+
+class _FusedEval:
+    """one fused forward shared by the CE and Dice objects of a MixedLoss (keyed on the logits tensor identity)"""
+    key = None
+    result = None
+
+
+def _fused(logits, labels, class_w, ignore_index):
+    key = (logits.data_ptr(), labels.data_ptr(), class_w.data_ptr(), logits._version, ignore_index, id(logits))
+    if _FusedEval.key == key and _FusedEval.result is not None:
+        return _FusedEval.result
+    res = _DiceCEFunction.apply(logits, labels, class_w, ignore_index)
+    _FusedEval.key, _FusedEval.result = key, res
+    return res
+
+
+class DiceLoss:
+    def __init__(self, sigmoid_norm=True, weight=None):
+        if not sigmoid_norm:
+            raise NotImplementedError("softmax-normalised Dice is not implemented (reference default is sigmoid)")
+        if weight is not None:
+            raise NotImplementedError("per-class Dice weights are not implemented (reference configs use None)")
+        self.weight, self.eps = weight, 1e-5
+        self._ones = None
+
+    def __call__(self, logits, labels):
+        return self.forward(logits, labels)
+
+    def forward(self, logits, labels, _class_w=None, _ignore_index=255):
+        logits, labels = _prep(logits, labels)
+        c = logits.shape[1]
+        if _class_w is None:
+            if self._ones is None or self._ones.numel() != c:
+                self._ones = torch.ones(c, dtype=torch.float32, device=logits.device)
+            _class_w = self._ones
+        res = _fused(logits, labels, _class_w, _ignore_index)
+        per_channel_dice = res[2:].detach().cpu().numpy()  # D2H sync, as dice_loss.py:99
+        return res[1], per_channel_dice
+
+
+class CrossEntropyLoss:
+    def __init__(self, weight=None, ignore_index=255, data_format="NCDHW"):
+        if data_format != "NCDHW":
+            raise NotImplementedError("only data_format='NCDHW' is supported")
+        self.ignore_index, self.EPS, self.data_format = ignore_index, 1e-8, data_format
+        self.weight = None if weight is None else torch.as_tensor(weight, dtype=torch.float32)
+
+    def __call__(self, logit, label):
+        return self.forward(logit, label)
+
+    def forward(self, logit, label):
+        logit, label = _prep(logit, label)
+        if self.weight is None:
+            self.weight = class_weights(logit.detach())  # cached forever (cross_entropy_loss.py:68-69)
+        self.weight = self.weight.to(logit.device)
+        if logit.shape[1] != len(self.weight):
+            raise ValueError("The number of weights = {} must be the same as the number of classes = {}.".format(
+                len(self.weight), logit.shape[1]))
+        return _fused(logit, label, self.weight, self.ignore_index)[0]
+
+
+class MixedLoss:
+    def __init__(self, losses, coef):
+        if not isinstance(losses, list):
+            raise TypeError("`losses` must be a list!")
+        if not isinstance(coef, list):
+            raise TypeError("`coef` must be a list!")
+        if len(losses) != len(coef):
+            raise ValueError("The length of `losses` should equal to `coef`, but they are {} and {}.".format(
+                len(losses), len(coef)))
+        self.losses, self.coef = losses, coef
+
+    def __call__(self, logits, labels):
+        return self.forward(logits, labels)
+
+    def forward(self, logits, labels):
+        logits, labels = _prep(logits, labels)
+        loss_list, per_channel_dice = [], None
+        ce = next((l for l in self.losses if type(l).__name__ == "CrossEntropyLoss"), None)
+        for i, loss in enumerate(self.losses):
+            if type(loss).__name__ == "DiceLoss":
+                if ce is not None:  # share the CE object's class weights so both run in the same fused pass
+                    if ce.weight is None:
+                        ce.weight = class_weights(logits.detach())
+                    out, per_channel_dice = loss.forward(logits, labels, ce.weight.to(logits.device), ce.ignore_index)
+                else:
+                    out, per_channel_dice = loss(logits, labels)
+            else:
+                out = loss(logits, labels)
+            loss_list.append(out * self.coef[i])
+        return loss_list, per_channel_dice
+
+
+def check_logits_losses(logits_list, losses):
+    if len(logits_list) != len(losses["types"]):
+        raise RuntimeError("The length of logits_list should equal to the types of loss config: {} != {}.".format(
+            len(logits_list), len(losses["types"])))
+
+
+def loss_computation(logits_list, labels, losses, edges=None):
+    """medicalseg/utils/loss_utils.py:25-52"""
+    check_logits_losses(logits_list, losses)
+    loss_list, per_channel_dice = [], None
+    for i in range(len(logits_list)):
+        logits, loss_i, coef_i = logits_list[i], losses["types"][i], losses["coef"][i]
+        name = loss_i.__class__.__name__
+        if name == "MixedLoss":
+            mixed_loss_list, per_channel_dice = loss_i(logits, labels)
+            for mixed_loss in mixed_loss_list:
+                loss_list.append(coef_i * mixed_loss)
+        elif name == "DiceLoss":
+            loss, per_channel_dice = loss_i(logits, labels)
+            loss_list.append(coef_i * loss)
+        else:
+            loss_list.append(coef_i * loss_i(logits, labels))
+    return loss_list, per_channel_dice

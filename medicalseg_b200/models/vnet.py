@@ -1,0 +1,726 @@
+"""VNet on hand-written sm_100a CUDA — drop-in for medicalseg/models/vnet.py:178-267 of the reference.
+
+Same constructor signature, attribute tree, state-dict names (Paddle naming: `*.bn1._mean`, `*.bn1._variance`,
+`*.relu1._weight`) and `forward(x[N,Cin,D,H,W] f32) -> [logits[N,num_classes,D,H,W] f32]` contract.
+
+Host side = Python over PyTorch tensors (memory, streams, autograd plumbing only); every device op is a kernel of
+libmedseg_b200.so called through medicalseg_b200.ops.  Internally activations are blocked-8 ("B8",
+[N][C/8][D][H][W][8]) bf16 (compute_dtype='bf16', tensor-core path) or f32 (compute_dtype='f32', CUDA-core parity
+path).  Skip-concats are free: producers write straight into channel halves of the pre-allocated xcat buffers.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..ops import B8
+
+BN_MOMENTUM = 0.9   # paddle.nn.BatchNorm3D default (running = 0.9*running + 0.1*batch)
+BN_EPS = 1e-5
+
+
+def _pad(c: int, m: int) -> int:
+    return (c + m - 1) // m * m
+
+
+# =========================================================================================================
+# parameter store: ONE flat f32 buffer for parameters, one for gradients (=> single fused optimizer launch and
+# contiguous all-reduce buckets); every parameter is a view.  Physical slots are padded so kernels that work on
+# zero-padded channel counts never read out of bounds.
+# =========================================================================================================
+class _Slot:
+    __slots__ = ("name", "shape", "numel", "phys", "offset", "is_buffer", "init")
+
+    def __init__(self, name, shape, phys, is_buffer, init):
+        self.name, self.shape, self.is_buffer, self.init = name, tuple(shape), is_buffer, init
+        self.numel = int(np.prod(shape))
+        self.phys = _pad(max(phys, self.numel), 4)
+        self.offset = -1
+
+
+class ParamStore:
+    def __init__(self):
+        self.slots: "OrderedDict[str, _Slot]" = OrderedDict()
+        self.flat = self.grad = self.buffers = None
+
+    def add(self, name, shape, init, phys=0, is_buffer=False):
+        self.slots[name] = _Slot(name, shape, phys, is_buffer, init)
+        return name
+
+    def finalize(self, device):
+        po = bo = 0
+        for s in self.slots.values():
+            if s.is_buffer:
+                s.offset, bo = bo, bo + s.phys
+            else:
+                s.offset, po = po, po + s.phys
+        self.flat = torch.zeros(po, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(po, dtype=torch.float32, device=device)
+        self.buffers = torch.zeros(max(bo, 4), dtype=torch.float32, device=device)
+
+    def _base(self, s: _Slot):
+        return self.buffers if s.is_buffer else self.flat
+
+    def view(self, name) -> torch.Tensor:
+        s = self.slots[name]
+        return self._base(s)[s.offset:s.offset + s.numel].view(s.shape)
+
+    def phys(self, name) -> torch.Tensor:
+        """physical (zero-padded) 1-D slot, what kernels index"""
+        s = self.slots[name]
+        return self._base(s)[s.offset:s.offset + s.phys]
+
+    def grad_view(self, name) -> torch.Tensor:
+        s = self.slots[name]
+        return self.grad[s.offset:s.offset + s.numel].view(s.shape)
+
+    def grad_phys(self, name) -> torch.Tensor:
+        s = self.slots[name]
+        return self.grad[s.offset:s.offset + s.phys]
+
+    def span(self, names: Sequence[str]):
+        """[lo, hi) range of the flat parameter buffer covered by `names` (all non-buffers)"""
+        sl = [self.slots[n] for n in names if not self.slots[n].is_buffer]
+        return min(s.offset for s in sl), max(s.offset + s.phys for s in sl)
+
+
+class ParamList(list):
+    """list of parameter views that also carries the flat buffers (used by optimizer.Momentum / parallel)"""
+    store: ParamStore = None
+
+
+# =========================================================================================================
+# layer objects: hold parameter names, run kernels, remember what backward needs
+# =========================================================================================================
+class _Module:
+    """tiny stand-in for nn.Layer so the reference's attribute tree (model.in_tr.conv1 ...) exists"""
+
+    def __init__(self, prefix):
+        self._prefix = prefix
+        self._param_names: List[str] = []
+
+    def named_children(self):
+        for k, v in self.__dict__.items():
+            if isinstance(v, _Module):
+                yield k, v
+            elif isinstance(v, (list, tuple)) and v and isinstance(v[0], _Module):
+                for i, m in enumerate(v):
+                    yield "%s.%d" % (k, i), m
+
+    def all_param_names(self) -> List[str]:
+        out = list(self._param_names)
+        for _, m in self.named_children():
+            out += m.all_param_names()
+        return out
+
+
+class _BN(_Module):
+    def __init__(self, store, prefix, c, c_phys):
+        super().__init__(prefix)
+        self.c, self.c_phys = c, c_phys
+        self.weight = store.add(prefix + ".weight", (c,), ("const", 1.0), c_phys)
+        self.bias = store.add(prefix + ".bias", (c,), ("const", 0.0), c_phys)
+        self.mean = store.add(prefix + "._mean", (c,), ("const", 0.0), c_phys, is_buffer=True)
+        self.var = store.add(prefix + "._variance", (c,), ("const", 1.0), c_phys, is_buffer=True)
+        self._param_names = [self.weight, self.bias, self.mean, self.var]
+
+
+class _PReLU(_Module):
+    def __init__(self, store, prefix, c, c_phys):
+        super().__init__(prefix)
+        self._weight = store.add(prefix + "._weight", (c,), ("const", 0.25), c_phys)
+        self._param_names = [self._weight]
+
+
+class _Conv(_Module):
+    def __init__(self, store, prefix, wshape, bias_c, init, bias_phys=0):
+        super().__init__(prefix)
+        self.weight = store.add(prefix + ".weight", wshape, init)
+        self.bias = store.add(prefix + ".bias", (bias_c,), ("const", 0.0), bias_phys)
+        self._param_names = [self.weight, self.bias]
+
+
+class _BnAct:
+    """BatchNorm3D(+tile | +residual) + PReLU(s) forward/backward around the msb_bn_* kernels."""
+
+    def __init__(self, eng, bn: _BN, relu1: _PReLU, relu2: Optional[_PReLU] = None):
+        self.eng, self.bn, self.relu1, self.relu2 = eng, bn, relu1, relu2
+        self.saved = None
+        self.bnbuf = None
+
+    def fwd(self, y: B8, out: B8, sums, residual: Optional[B8] = None, tile=None, tile_c=0):
+        eng, st = self.eng, self.eng.store
+        g = eng.groups(y.n)
+        c = y.c
+        if self.bnbuf is None or self.bnbuf.numel() != 4 * g * c:
+            self.bnbuf = torch.empty(4 * g * c, dtype=torch.float32, device=y.buf.device)
+        count = y.s * (y.n if g == 1 else 1)
+        ops.bn_finalize(sums if eng.training else None, count, st.phys(self.bn.weight), st.phys(self.bn.bias),
+                        st.phys(self.bn.mean), st.phys(self.bn.var), BN_MOMENTUM, BN_EPS, eng.training, c, g,
+                        self.bnbuf)
+        a2 = st.phys(self.relu2._weight) if (self.relu2 is not None and residual is not None) else None
+        ops.bn_act_fwd(y, out, residual, tile, tile_c, self.bnbuf, st.phys(self.relu1._weight), a2, g)
+        self.saved = (y, residual, tile, tile_c, count, g)
+
+    def bwd(self, gout: B8, dy: B8, dres: Optional[B8] = None, dres_acc=False):
+        eng, st = self.eng, self.eng.store
+        y, residual, tile, tile_c, count, g = self.saved
+        red = eng.scratch_f64(4 * g * y.c)
+        a1 = st.phys(self.relu1._weight)
+        a2 = st.phys(self.relu2._weight) if (self.relu2 is not None and residual is not None) else None
+        ops.bn_act_bwd_reduce(y, residual, tile, tile_c, gout, self.bnbuf, a1, a2, g, red)
+        ops.bn_act_bwd_apply(y, residual, tile, tile_c, gout, self.bnbuf, a1, a2, red, count, eng.bn_training_bwd,
+                             dy, dres, dres_acc, st.grad_phys(self.bn.weight), st.grad_phys(self.bn.bias),
+                             st.grad_phys(self.relu1._weight),
+                             st.grad_phys(self.relu2._weight) if a2 is not None else None, g)
+        self.saved = None
+
+
+class _K5:
+    """5x5x5 pad-2 conv: tcgen05 kernels for bf16, direct kernels for the f32 parity path."""
+
+    def __init__(self, eng, conv: _Conv, cin, cout):
+        self.eng, self.conv, self.cin, self.cout = eng, conv, cin, cout
+        self.packed_f = self.packed_b = None
+        self.packed_version = -1
+
+    def _pack(self, x_c, out_c):
+        eng, st = self.eng, self.eng.store
+        if self.packed_version == eng.param_version and self.packed_f is not None:
+            return
+        w = st.view(self.conv.weight)
+        dev = w.device
+        cin_pad, cout_pad = x_c, ops.k5_out_pad(out_c)
+        if self.packed_f is None:
+            self.packed_f = torch.empty(ops.k5_packed_bytes(cin_pad, cout_pad), dtype=torch.uint8, device=dev)
+            # input-gradient operand: reduces over the (padded) output channels, produces the input channels
+            self.bk_cin_pad, self.bk_cout_pad = _pad(out_c, 16), ops.k5_out_pad(x_c)
+            self.packed_b = torch.empty(ops.k5_packed_bytes(self.bk_cin_pad, self.bk_cout_pad), dtype=torch.uint8,
+                                        device=dev)
+        ops.k5_pack(w, self.packed_f, self.cout, self.cin, 0, cin_pad, cout_pad)
+        ops.k5_pack(w, self.packed_b, self.cout, self.cin, 1, self.bk_cin_pad, self.bk_cout_pad)
+        self.packed_version = eng.param_version
+
+    def fwd(self, x: B8, out: B8, sums):
+        eng, st = self.eng, self.eng.store
+        g = eng.groups(x.n)
+        if eng.dtype == torch.bfloat16:
+            self._pack(x.c, out.c)
+            ops.k5_fwd(x, self.packed_f, st.view(self.conv.bias), self.cout, out, False, None, g, sums)
+        else:
+            ops.conv_strided_fwd(x, st.view(self.conv.weight), st.view(self.conv.bias), out, (5, 5, 5), (1, 1, 1),
+                                 (2, 2, 2), g, sums, self.cin, self.cout)
+
+    def bwd(self, x: B8, dy: B8, dx: Optional[B8], accumulate=False, ch_scale=None):
+        eng, st = self.eng, self.eng.store
+        w, dw, db = st.view(self.conv.weight), st.grad_view(self.conv.weight), st.grad_view(self.conv.bias)
+        if eng.dtype == torch.bfloat16:
+            if dx is not None:
+                ops.k5_fwd(dy, self.packed_b, None, self.cin, dx, accumulate, ch_scale, 1, None)
+            ops.k5_wgrad(x, dy, dw, db, self.cout, self.cin, eng.wgrad_workspace(self.cin, self.cout))
+        else:
+            if dx is not None:
+                if ch_scale is None:
+                    ops.conv_strided_bwd_data(dy, w, None, dx, (5, 5, 5), (1, 1, 1), (2, 2, 2), accumulate, 1, None,
+                                              self.cout, self.cin)
+                else:
+                    tmp = B8(dx.n, dx.c, dx.dims, dx.dtype, device=dx.buf.device)
+                    ops.conv_strided_bwd_data(dy, w, None, tmp, (5, 5, 5), (1, 1, 1), (2, 2, 2), False, 1, None,
+                                              self.cout, self.cin)
+                    ops.channel_scale(tmp, dx, ch_scale, accumulate)
+            ops.conv_strided_wgrad(x, dy, dw, db, (5, 5, 5), (1, 1, 1), (2, 2, 2), False, self.cin, self.cout)
+
+
+class LUConv(_Module):  # vnet.py:32-43
+    def __init__(self, eng, prefix, nchan):
+        super().__init__(prefix)
+        st = eng.store
+        self.relu1 = _PReLU(st, prefix + ".relu1", nchan, nchan)
+        self.conv1 = _Conv(st, prefix + ".conv1", (nchan, nchan, 5, 5, 5), nchan, ("conv", nchan * 125))
+        self.bn1 = _BN(st, prefix + ".bn1", nchan, nchan)
+        self.k5 = _K5(eng, self.conv1, nchan, nchan)
+        self.act = None  # built by the owning transition (the last LUConv fuses the residual + relu2)
+
+
+class InputTransition(_Module):  # vnet.py:57-79
+    def __init__(self, eng, prefix, in_channels):
+        super().__init__(prefix)
+        st = eng.store
+        self.num_features, self.in_channels = 16, in_channels
+        self.conv1 = _Conv(st, prefix + ".conv1", (16, in_channels, 5, 5, 5), 16, ("conv", in_channels * 125))
+        self.bn1 = _BN(st, prefix + ".bn1", 16, 16)
+        self.relu1 = _PReLU(st, prefix + ".relu1", 16, 16)
+        self.act = _BnAct(eng, self.bn1, self.relu1)
+
+
+class DownTransition(_Module):  # vnet.py:82-113
+    def __init__(self, eng, prefix, in_ch, n_convs, dropout, stride, kernel):
+        super().__init__(prefix)
+        st = eng.store
+        out_ch = 2 * in_ch
+        self.in_ch, self.out_ch, self.if_dropout = in_ch, out_ch, dropout
+        self.kernel, self.stride = tuple(kernel), tuple(stride)
+        self.down_conv = _Conv(st, prefix + ".down_conv", (out_ch, in_ch, *self.kernel), out_ch,
+                               ("conv", in_ch * int(np.prod(self.kernel))))
+        self.bn1 = _BN(st, prefix + ".bn1", out_ch, out_ch)
+        self.relu1 = _PReLU(st, prefix + ".relu1", out_ch, out_ch)
+        self.relu2 = _PReLU(st, prefix + ".relu2", out_ch, out_ch)
+        self.ops = [LUConv(eng, "%s.ops.%d" % (prefix, i), out_ch) for i in range(n_convs)]
+        self.act_down = _BnAct(eng, self.bn1, self.relu1)
+        for i, lu in enumerate(self.ops):
+            lu.act = _BnAct(eng, lu.bn1, lu.relu1, self.relu2 if i == n_convs - 1 else None)
+
+
+class UpTransition(_Module):  # vnet.py:116-156
+    def __init__(self, eng, prefix, in_ch, out_ch, n_convs, dropout, dropout2, stride, kernel):
+        super().__init__(prefix)
+        st = eng.store
+        half = out_ch // 2
+        self.in_ch, self.out_ch, self.half = in_ch, out_ch, half
+        self.if_dropout, self.if_dropout2 = dropout, dropout2
+        self.kernel, self.stride = tuple(kernel), tuple(stride)
+        self.up_conv = _Conv(st, prefix + ".up_conv", (in_ch, half, *self.kernel), half,
+                             ("xavier", in_ch * int(np.prod(self.kernel)), half * int(np.prod(self.kernel))))
+        self.bn1 = _BN(st, prefix + ".bn1", half, half)
+        self.relu1 = _PReLU(st, prefix + ".relu1", half, half)
+        self.relu2 = _PReLU(st, prefix + ".relu2", out_ch, out_ch)
+        self.ops = [LUConv(eng, "%s.ops.%d" % (prefix, i), out_ch) for i in range(n_convs)]
+        self.act_up = _BnAct(eng, self.bn1, self.relu1)
+        for i, lu in enumerate(self.ops):
+            lu.act = _BnAct(eng, lu.bn1, lu.relu1, self.relu2 if i == n_convs - 1 else None)
+
+
+class OutputTransition(_Module):  # vnet.py:159-175
+    def __init__(self, eng, prefix, in_channels, num_classes):
+        super().__init__(prefix)
+        st = eng.store
+        self.c, self.cp = num_classes, _pad(num_classes, 16)
+        self.conv1 = _Conv(st, prefix + ".conv1", (num_classes, in_channels, 5, 5, 5), num_classes,
+                           ("conv", in_channels * 125), self.cp)
+        self.bn1 = _BN(st, prefix + ".bn1", num_classes, self.cp)
+        self.conv2 = _Conv(st, prefix + ".conv2", (num_classes, num_classes, 1, 1, 1), num_classes,
+                           ("conv", num_classes))
+        self.relu1 = _PReLU(st, prefix + ".relu1", num_classes, self.cp)
+        self.k5 = _K5(eng, self.conv1, in_channels, num_classes)
+        self.act = _BnAct(eng, self.bn1, self.relu1)
+
+
+class _VNetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, anchor, engine):
+        ctx.engine = engine
+        return engine._forward(x, record=True)
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        ctx.engine._backward(grad_logits)
+        return None, None, None
+
+
+class VNet(_Module):
+    """B200-native VNet (reference: medicalseg/models/vnet.py:178-267).
+
+    Extra keyword arguments (not in the reference): `compute_dtype` ('bf16' tensor-core path | 'f32' parity path),
+    `stat_scope` ('batch' = reference BatchNorm semantics | 'instance'), `device`.
+    """
+
+    def __init__(self, elu=False, in_channels=1, num_classes=4, pretrained=None,
+                 kernel_size=((2, 2, 2), (2, 2, 2), (2, 2, 2), (2, 2, 2)),
+                 stride_size=((2, 2, 2), (2, 2, 2), (2, 2, 2), (2, 2, 2)),
+                 compute_dtype="bf16", stat_scope="batch", device=None, seed=None):
+        super().__init__("")
+        if elu:
+            raise NotImplementedError("elu=True (nn.ELU) is not supported; the reference itself reports NaN gradients "
+                                      "with it (medicalseg/core/train.py:139)")
+        if in_channels != 1:
+            raise NotImplementedError("in_channels != 1 is not supported by the in_tr kernel (reference configs use 1)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("medicalseg_b200.VNet needs a CUDA device (sm_100a); there is no CPU fallback")
+        from .. import _lib
+        _lib.load()  # fail loudly if the CUDA library is missing
+        self.best_loss = 1000000
+        self.num_classes, self.in_channels, self.pretrained = num_classes, in_channels, pretrained
+        self.device = torch.device(device or ("cuda:%d" % torch.cuda.current_device()))
+        self.dtype = {"bf16": torch.bfloat16, "f32": torch.float32}[compute_dtype]
+        self.stat_scope = stat_scope
+        self.training = True
+        self.bn_training_bwd = True
+        self.param_version = 0
+        self.store = ParamStore()
+        k, s = [tuple(v) for v in kernel_size], [tuple(v) for v in stride_size]
+        self.kernel_size, self.stride_size = k, s
+        self.in_tr = InputTransition(self, "in_tr", in_channels)
+        self.down_tr32 = DownTransition(self, "down_tr32", 16, 1, False, s[0], k[0])
+        self.down_tr64 = DownTransition(self, "down_tr64", 32, 2, False, s[1], k[1])
+        self.down_tr128 = DownTransition(self, "down_tr128", 64, 3, True, s[2], k[2])
+        self.down_tr256 = DownTransition(self, "down_tr256", 128, 2, True, s[3], k[3])
+        self.up_tr256 = UpTransition(self, "up_tr256", 256, 256, 2, True, True, s[3], k[3])
+        self.up_tr128 = UpTransition(self, "up_tr128", 256, 128, 2, True, True, s[2], k[2])
+        self.up_tr64 = UpTransition(self, "up_tr64", 128, 64, 1, False, False, s[1], k[1])
+        self.up_tr32 = UpTransition(self, "up_tr32", 64, 32, 1, False, False, s[0], k[0])
+        self.out_tr = OutputTransition(self, "out_tr", 32, num_classes)
+        self.store.finalize(self.device)
+        self._init_parameters(seed)
+        self._anchor = torch.zeros(1, device=self.device, requires_grad=True)
+        self._scratch = torch.zeros(1 << 18, dtype=torch.float64, device=self.device)
+        self._scratch_off = 0
+        self._wg_ws = None
+        self._masks: Optional[Dict[str, torch.Tensor]] = None
+        self._tape = None
+        self.grad_ready_hook = None  # callable(lo, hi) on flat-grad ranges, fired in backward order (DDP buckets)
+        if pretrained is not None:
+            self.init_weight()
+
+    # ---------------------------------------------------------------- nn.Layer-like API
+    def init_weight(self):
+        if self.pretrained is not None:
+            from ..utils import load_entire_model
+            load_entire_model(self, self.pretrained)
+
+    def train(self):
+        self.training = True
+        return self
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def parameters(self) -> ParamList:
+        pl = ParamList()
+        for name, s in self.store.slots.items():
+            if not s.is_buffer:
+                p = self.store.view(name)
+                p.grad = self.store.grad_view(name)
+                pl.append(p)
+        pl.store = self.store
+        pl.owner = self
+        return pl
+
+    def named_parameters(self):
+        for name, s in self.store.slots.items():
+            if not s.is_buffer:
+                yield name, self.store.view(name)
+
+    def state_dict(self):
+        return OrderedDict((name, self.store.view(name).detach().clone()) for name in self.store.slots)
+
+    def set_state_dict(self, sd, strict=True):
+        missing = []
+        for name, s in self.store.slots.items():
+            if name not in sd:
+                missing.append(name)
+                continue
+            v = torch.as_tensor(np.asarray(sd[name]) if not torch.is_tensor(sd[name]) else sd[name])
+            if tuple(v.shape) != s.shape:
+                raise ValueError("shape mismatch for %s: %s vs %s" % (name, tuple(v.shape), s.shape))
+            self.store.view(name).copy_(v.to(self.device, torch.float32))
+        if strict and missing:
+            raise KeyError("missing keys in state dict: %s" % missing[:5])
+        self.param_version += 1
+        return missing
+
+    set_dict = set_state_dict
+    load_state_dict = set_state_dict
+
+    def clear_gradients(self):
+        self.store.grad.zero_()
+
+    clear_grad = clear_gradients
+
+    def mark_parameters_updated(self):
+        """called by the optimizer after a step so packed tensor-core operands are rebuilt"""
+        self.param_version += 1
+
+    def set_dropout_masks(self, masks: Optional[Dict[str, torch.Tensor]]):
+        """explicit Dropout3D masks ([N,C] of 0 / 2) for the next train-mode forward; None -> draw internally"""
+        self._masks = None if masks is None else {k: v.to(self.device, torch.float32).contiguous()
+                                                  for k, v in masks.items()}
+
+    def __call__(self, x):
+        return self.forward(x)
+
+    def forward(self, x):  # vnet.py:256-267 -> [logits]
+        if not x.is_cuda:
+            raise RuntimeError("VNet.forward needs a CUDA tensor (no CPU fallback)")
+        x = x.to(torch.float32).contiguous()
+        if torch.is_grad_enabled():
+            return [_VNetFunction.apply(x, self._anchor, self)]
+        return [self._forward(x, record=False)]
+
+    # ---------------------------------------------------------------- helpers
+    def groups(self, n):
+        return 1 if self.stat_scope == "batch" else n
+
+    def scratch_f64(self, count):
+        count = _pad(count, 2)
+        if self._scratch_off + count > self._scratch.numel():
+            raise RuntimeError("f64 scratch pool exhausted")
+        v = self._scratch[self._scratch_off:self._scratch_off + count]
+        self._scratch_off += count
+        return v
+
+    def wgrad_workspace(self, cin, cout):
+        need = ops.k5_wgrad_workspace_bytes(cin, cout)
+        if self._wg_ws is None or self._wg_ws.numel() < need:
+            self._wg_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._wg_ws
+
+    def _init_parameters(self, seed):
+        g = torch.Generator().manual_seed(0 if seed is None else seed)
+        for name, s in self.store.slots.items():
+            kind = s.init[0]
+            if kind == "const":
+                v = torch.full(s.shape, float(s.init[1]))
+            elif kind == "conv":   # Paddle Conv3D default: Normal(0, sqrt(2/fan_in))
+                v = torch.randn(s.shape, generator=g) * math.sqrt(2.0 / s.init[1])
+            else:                   # Paddle Conv3DTranspose default: XavierUniform
+                bound = math.sqrt(6.0 / (s.init[1] + s.init[2]))
+                v = (torch.rand(s.shape, generator=g) * 2 - 1) * bound
+            self.store.view(name).copy_(v.to(self.device))
+
+    def _new(self, n, c, dims, zero=False):
+        return B8(n, c, dims, self.dtype, device=self.device, zero=zero)
+
+    def _mask(self, site, n, c):
+        if not self.training:
+            return None
+        if self._masks is not None:
+            return self._masks[site]
+        keep = (torch.rand(n, c, device=self.device) >= 0.5).to(torch.float32) * 2.0
+        return keep
+
+    @staticmethod
+    def _down_dims(dims, k, s):
+        return tuple((d - kk) // ss + 1 for d, kk, ss in zip(dims, k, s))
+
+    # ---------------------------------------------------------------- forward
+    def _forward(self, x: torch.Tensor, record: bool = False) -> torch.Tensor:
+        st, T = self.store, self.training
+        n = x.shape[0]
+        g = self.groups(n)
+        self._scratch.zero_()
+        self._scratch_off = 0
+        tape = {"x": x, "n": n}
+        dims = [tuple(x.shape[2:])]
+        for lvl in range(4):
+            dims.append(self._down_dims(dims[-1], self.kernel_size[lvl], self.stride_size[lvl]))
+        tape["dims"] = dims
+
+        def sums(c):
+            return self.scratch_f64(2 * g * c) if T else None
+
+        # concat buffers: [up-branch | skip] (vnet.py:152 order)
+        xcat32 = self._new(n, 32, dims[0])
+        xcat64 = self._new(n, 64, dims[1])
+        xcat128 = self._new(n, 128, dims[2])
+        xcat256 = self._new(n, 256, dims[3])
+
+        # ---- in_tr
+        it = self.in_tr
+        y0 = self._new(n, 16, dims[0])
+        s0 = sums(16)
+        ops.conv_in_fwd(x, st.view(it.conv1.weight), st.view(it.conv1.bias), y0, g, s0)
+        out16 = xcat32.view(16, 16)
+        it.act.fwd(y0, out16, s0, tile=x, tile_c=self.in_channels)
+
+        # ---- encoder
+        def down(tr: DownTransition, xin: B8, lvl: int, out: B8, site: str):
+            c = tr.out_ch
+            yd = self._new(n, c, dims[lvl])
+            sd = sums(c)
+            ops.conv_strided_fwd(xin, st.view(tr.down_conv.weight), st.view(tr.down_conv.bias), yd, tr.kernel,
+                                 tr.stride, (0, 0, 0), g, sd)
+            dwn = self._new(n, c, dims[lvl])
+            tr.act_down.fwd(yd, dwn, sd)
+            mask = self._mask(site, n, c) if tr.if_dropout else None
+            cur = dwn
+            if mask is not None:
+                cur = self._new(n, c, dims[lvl])
+                ops.channel_scale(dwn, cur, mask, False)
+            rec = {"xin": xin, "down": dwn, "mask": mask, "lu_in": []}
+            for i, lu in enumerate(tr.ops):
+                rec["lu_in"].append(cur)
+                y = self._new(n, c, dims[lvl])
+                sl = sums(c)
+                lu.k5.fwd(cur, y, sl)
+                last = i == len(tr.ops) - 1
+                nxt = out if last else self._new(n, c, dims[lvl])
+                lu.act.fwd(y, nxt, sl, residual=dwn if last else None)
+                cur = nxt
+            return rec
+
+        out32 = xcat64.view(32, 32)
+        out64 = self._new(n, 64, dims[2])
+        out128 = self._new(n, 128, dims[3])
+        out256 = self._new(n, 256, dims[4])
+        tape["d32"] = down(self.down_tr32, out16, 1, out32, "down_tr32")
+        tape["d64"] = down(self.down_tr64, out32, 2, out64, "down_tr64")
+        tape["d128"] = down(self.down_tr128, out64, 3, out128, "down_tr128")
+        tape["d256"] = down(self.down_tr256, out128, 4, out256, "down_tr256")
+
+        # ---- decoder
+        def up(tr: UpTransition, xin: B8, skip: Optional[B8], xcat: B8, lvl: int, site: str):
+            half, c = tr.half, tr.out_ch
+            mx = self._mask(site + ".x", n, tr.in_ch) if tr.if_dropout else None
+            ms = self._mask(site + ".skip", n, half) if tr.if_dropout2 else None
+            xd = xin
+            if mx is not None:
+                xd = self._new(n, tr.in_ch, xin.dims)
+                ops.channel_scale(xin, xd, mx, False)
+            if skip is not None:  # skip not already resident in the right half of xcat
+                ops.channel_scale(skip, xcat.view(half, half), ms, False)
+            yu = self._new(n, half, dims[lvl])
+            su = sums(half)
+            ops.conv_strided_bwd_data(xd, st.view(tr.up_conv.weight), st.view(tr.up_conv.bias), yu, tr.kernel,
+                                      tr.stride, (0, 0, 0), False, g, su)
+            tr.act_up.fwd(yu, xcat.view(0, half), su)
+            rec = {"xin": xin, "xd": xd, "mx": mx, "ms": ms, "xcat": xcat, "lu_in": [], "skip_sep": skip is not None}
+            cur = xcat
+            out = self._new(n, c, dims[lvl])
+            for i, lu in enumerate(tr.ops):
+                rec["lu_in"].append(cur)
+                y = self._new(n, c, dims[lvl])
+                sl = sums(c)
+                lu.k5.fwd(cur, y, sl)
+                last = i == len(tr.ops) - 1
+                nxt = out if last else self._new(n, c, dims[lvl])
+                lu.act.fwd(y, nxt, sl, residual=xcat if last else None)
+                cur = nxt
+            rec["out"] = out
+            return rec
+
+        tape["u256"] = up(self.up_tr256, out256, out128, xcat256, 3, "up_tr256")
+        tape["u128"] = up(self.up_tr128, tape["u256"]["out"], out64, xcat128, 2, "up_tr128")
+        tape["u64"] = up(self.up_tr64, tape["u128"]["out"], None, xcat64, 1, "up_tr64")
+        tape["u32"] = up(self.up_tr32, tape["u64"]["out"], None, xcat32, 0, "up_tr32")
+
+        # ---- out_tr
+        ot = self.out_tr
+        cp = ot.cp
+        yo = self._new(n, cp, dims[0])
+        so = sums(cp)
+        ot.k5.fwd(tape["u32"]["out"], yo, so)
+        ao = self._new(n, cp, dims[0])
+        ot.act.fwd(yo, ao, so)
+        logits = torch.empty((n, self.num_classes, *dims[0]), dtype=torch.float32, device=self.device)
+        ops.conv1x1_fwd(ao, st.view(ot.conv2.weight), st.view(ot.conv2.bias), logits, self.num_classes,
+                        self.num_classes)
+        tape["ao"] = ao
+        self._tape = tape if record else None
+        self._masks = None
+        return logits
+
+    # ---------------------------------------------------------------- backward
+    def _fire(self, module: _Module):
+        if self.grad_ready_hook is not None:
+            lo, hi = self.store.span(module.all_param_names())
+            self.grad_ready_hook(lo, hi)
+
+    def _backward(self, dlogits: torch.Tensor):
+        tape = self._tape
+        if tape is None:
+            raise RuntimeError("backward called without a recorded forward")
+        st = self.store
+        n, dims, x = tape["n"], tape["dims"], tape["x"]
+        dlogits = dlogits.contiguous().float()
+        self.bn_training_bwd = self.training
+
+        # ---- out_tr
+        ot = self.out_tr
+        ao = tape["ao"]
+        da = self._new(n, ot.cp, dims[0])
+        ops.conv1x1_bwd(ao, st.view(ot.conv2.weight), dlogits, da, st.grad_view(ot.conv2.weight),
+                        st.grad_view(ot.conv2.bias), self.num_classes, self.num_classes)
+        dyo = self._new(n, ot.cp, dims[0])
+        ot.act.bwd(da, dyo)
+        g_u32 = self._new(n, 32, dims[0])
+        ot.k5.bwd(tape["u32"]["out"], dyo, g_u32)
+        self._fire(ot)
+
+        def lu_chain_bwd(tr, rec, g_out: B8, g_first_in: B8, lvl: int, first_scale):
+            """backward through tr.ops; g_first_in receives (+=) the gradient of the first LUConv's input and is
+            first written with the residual-branch gradient of the fused (add + relu2) stage."""
+            c = tr.out_ch
+            g_cur = g_out
+            for i in range(len(tr.ops) - 1, -1, -1):
+                lu = tr.ops[i]
+                last = i == len(tr.ops) - 1
+                dy = self._new(n, c, dims[lvl])
+                if last:
+                    lu.act.bwd(g_cur, dy, dres=g_first_in, dres_acc=False)
+                else:
+                    lu.act.bwd(g_cur, dy)
+                if i == 0:
+                    lu.k5.bwd(rec["lu_in"][0], dy, g_first_in, accumulate=True, ch_scale=first_scale)
+                else:
+                    g_prev = self._new(n, c, dims[lvl])
+                    lu.k5.bwd(rec["lu_in"][i], dy, g_prev)
+                    g_cur = g_prev
+
+        def up_bwd(tr: UpTransition, rec, g_out: B8, lvl: int, g_skip_sep: Optional[B8]):
+            half = tr.half
+            g_xcat = self._new(n, tr.out_ch, dims[lvl])
+            lu_chain_bwd(tr, rec, g_out, g_xcat, lvl, None)
+            # skip half: either stays as a view (no dropout2) or is scaled into the separate skip gradient
+            if g_skip_sep is not None:
+                ops.channel_scale(g_xcat.view(half, half), g_skip_sep, rec["ms"], False)
+            dyu = self._new(n, half, dims[lvl])
+            tr.act_up.bwd(g_xcat.view(0, half), dyu)
+            g_xin = self._new(n, tr.in_ch, rec["xin"].dims)
+            ops.conv_strided_fwd(dyu, st.view(tr.up_conv.weight), None, g_xin, tr.kernel, tr.stride, (0, 0, 0), 1, None)
+            ops.conv_strided_wgrad(dyu, rec["xd"], st.grad_view(tr.up_conv.weight), st.grad_view(tr.up_conv.bias),
+                                   tr.kernel, tr.stride, (0, 0, 0), True)
+            if rec["mx"] is not None:
+                ops.channel_scale(g_xin, g_xin, rec["mx"], False)
+            self._fire(tr)
+            return g_xin, g_xcat
+
+        g_u64, g_xcat32 = up_bwd(self.up_tr32, tape["u32"], g_u32, 0, None)
+        g_out16 = g_xcat32.view(16, 16)
+        g_u128, g_xcat64 = up_bwd(self.up_tr64, tape["u64"], g_u64, 1, None)
+        g_out32 = g_xcat64.view(32, 32)
+        g_out64 = self._new(n, 64, dims[2])
+        g_u256, _ = up_bwd(self.up_tr128, tape["u128"], g_u128, 2, g_out64)
+        g_out128 = self._new(n, 128, dims[3])
+        g_out256, _ = up_bwd(self.up_tr256, tape["u256"], g_u256, 3, g_out128)
+
+        def down_bwd(tr: DownTransition, rec, g_out: B8, g_xin: B8, lvl: int):
+            c = tr.out_ch
+            g_down = self._new(n, c, dims[lvl])
+            lu_chain_bwd(tr, rec, g_out, g_down, lvl, rec["mask"])
+            dyd = self._new(n, c, dims[lvl])
+            tr.act_down.bwd(g_down, dyd)
+            ops.conv_strided_bwd_data(dyd, st.view(tr.down_conv.weight), None, g_xin, tr.kernel, tr.stride, (0, 0, 0),
+                                      True, 1, None)
+            ops.conv_strided_wgrad(rec["xin"], dyd, st.grad_view(tr.down_conv.weight),
+                                   st.grad_view(tr.down_conv.bias), tr.kernel, tr.stride, (0, 0, 0), False)
+            self._fire(tr)
+
+        down_bwd(self.down_tr256, tape["d256"], g_out256, g_out128, 4)
+        down_bwd(self.down_tr128, tape["d128"], g_out128, g_out64, 3)
+        down_bwd(self.down_tr64, tape["d64"], g_out64, g_out32, 2)
+        down_bwd(self.down_tr32, tape["d32"], g_out32, g_out16, 1)
+
+        # ---- in_tr (no input gradient: the image has stop_gradient=True, core/train.py:123)
+        it = self.in_tr
+        dy0 = self._new(n, 16, dims[0])
+        it.act.bwd(g_out16, dy0)
+        ops.conv_in_wgrad(x, dy0, st.grad_view(it.conv1.weight), st.grad_view(it.conv1.bias))
+        self._fire(it)
+        self._tape = None
+
+    # ---------------------------------------------------------------- reference self-check (vnet.py:269-282)
+    def test(self):
+        np.random.seed(1)
+        a = np.random.rand(1, self.in_channels, 32, 32, 32)
+        x = torch.tensor(a, dtype=torch.float32, device=self.device)
+        with torch.no_grad():
+            out = self.forward(x)[0]
+        print("out", float(out.mean()), float(x.mean()))
+        assert tuple(out.shape) == (1, self.num_classes, 32, 32, 32)
+        print("Vnet test is complete")

@@ -1,0 +1,240 @@
+"""Python-side operator layer: torch tensors in, msb_* C-ABI calls out (include/medseg_b200.h).
+
+Every function enqueues on torch's current CUDA stream and never synchronises.  Tensors must live on a
+CUDA device: there is no CPU fallback (a CPU tensor raises)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import MSB_BF16, MSB_F32, MsbDim3, MsbTensor, call
+
+_TORCH2MSB = {torch.float32: MSB_F32, torch.bfloat16: MSB_BF16}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.MsbError("medicalseg_b200 ops need CUDA tensors (no CPU fallback)")
+    return t.data_ptr()
+
+
+def dim3(d: Sequence[int]) -> MsbDim3:
+    return MsbDim3(int(d[0]), int(d[1]), int(d[2]))
+
+
+class B8:
+    """Blocked-8 activation [N][C/8][D][H][W][8]; may be a channel-slice view of a wider buffer."""
+
+    __slots__ = ("buf", "n", "c", "dims", "c_off", "dtype")
+
+    def __init__(self, n: int, c: int, dims: Sequence[int], dtype: torch.dtype, device=None,
+                 buf: Optional[torch.Tensor] = None, c_off: int = 0, zero: bool = False):
+        assert c % 8 == 0 and c_off % 8 == 0
+        self.n, self.c, self.dims, self.c_off, self.dtype = n, c, tuple(int(v) for v in dims), c_off, dtype
+        if buf is None:
+            alloc = torch.zeros if zero else torch.empty
+            buf = alloc((n, c // 8, *self.dims, 8), dtype=dtype, device=device)
+        self.buf = buf
+
+    @property
+    def s(self) -> int:
+        return self.dims[0] * self.dims[1] * self.dims[2]
+
+    @property
+    def c_total(self) -> int:
+        return self.buf.shape[1] * 8
+
+    def view(self, c_off: int, c: int) -> "B8":
+        assert c_off + c <= self.c
+        return B8(self.n, c, self.dims, self.dtype, buf=self.buf, c_off=self.c_off + c_off)
+
+    @property
+    def mt(self) -> MsbTensor:
+        esz = self.buf.element_size()
+        ptr = self.buf.data_ptr() + (self.c_off // 8) * self.s * 8 * esz
+        return MsbTensor(ptr, self.buf.shape[1] * self.s * 8, self.c, _TORCH2MSB[self.dtype])
+
+    def to_ncdhw(self, c: Optional[int] = None) -> torch.Tensor:
+        c = c or self.c
+        out = torch.empty((self.n, c, *self.dims), dtype=torch.float32, device=self.buf.device)
+        call("msb_from_blocked", self.mt, _ptr(out), self.n, c, self.s, _stream())
+        return out
+
+    @staticmethod
+    def from_ncdhw(x: torch.Tensor, dtype: torch.dtype, c_pad: Optional[int] = None) -> "B8":
+        x = x.contiguous().float()
+        n, c = x.shape[:2]
+        cp = c_pad or ((c + 7) // 8 * 8)
+        out = B8(n, cp, x.shape[2:], dtype, device=x.device)
+        call("msb_to_blocked", _ptr(x), n, c, out.s, out.mt, _stream())
+        return out
+
+
+NULL_T = MsbTensor(None, 0, 0, 0)
+
+
+def _mt(t: Optional[B8]) -> MsbTensor:
+    return NULL_T if t is None else t.mt
+
+
+# ---- BatchNorm + PReLU ---------------------------------------------------------------------------------
+def bn_stats(x: B8, groups: int, sums: torch.Tensor):
+    call("msb_bn_stats", x.mt, x.n, x.s, groups, _ptr(sums), _stream())
+
+
+def bn_finalize(sums, count, gamma, beta, rmean, rvar, momentum, eps, training, c, groups, bnbuf):
+    call("msb_bn_finalize", _ptr(sums), float(count), _ptr(gamma), _ptr(beta), _ptr(rmean), _ptr(rvar),
+         float(momentum), float(eps), int(training), c, groups, _ptr(bnbuf), _stream())
+
+
+def bn_act_fwd(y: B8, out: B8, residual: Optional[B8], tile_src, tile_c, bnbuf, alpha1, alpha2, groups):
+    call("msb_bn_act_fwd", y.mt, out.mt, _mt(residual), _ptr(tile_src), int(tile_c), _ptr(bnbuf), _ptr(alpha1),
+         _ptr(alpha2), y.n, y.s, groups, _stream())
+
+
+def bn_act_bwd_reduce(y: B8, residual, tile_src, tile_c, gout: B8, bnbuf, alpha1, alpha2, groups, red):
+    call("msb_bn_act_bwd_reduce", y.mt, _mt(residual), _ptr(tile_src), int(tile_c), gout.mt, _ptr(bnbuf),
+         _ptr(alpha1), _ptr(alpha2), y.n, y.s, groups, _ptr(red), _stream())
+
+
+def bn_act_bwd_apply(y: B8, residual, tile_src, tile_c, gout: B8, bnbuf, alpha1, alpha2, red, count, training,
+                     dy: B8, dres: Optional[B8], dres_acc, dgamma, dbeta, dalpha1, dalpha2, groups):
+    call("msb_bn_act_bwd_apply", y.mt, _mt(residual), _ptr(tile_src), int(tile_c), gout.mt, _ptr(bnbuf),
+         _ptr(alpha1), _ptr(alpha2), _ptr(red), float(count), int(training), dy.mt, _mt(dres), int(dres_acc),
+         _ptr(dgamma), _ptr(dbeta), _ptr(dalpha1), _ptr(dalpha2), y.n, y.s, groups, _stream())
+
+
+def channel_scale(src: B8, dst: B8, scale: Optional[torch.Tensor], accumulate: bool):
+    call("msb_channel_scale", src.mt, dst.mt, _ptr(scale), src.n, src.s, int(accumulate), _stream())
+
+
+# ---- convolutions --------------------------------------------------------------------------------------------
+def conv1x1_fwd(a: B8, w, b, logits, ci, co):
+    call("msb_conv1x1_fwd", a.mt, _ptr(w), _ptr(b), _ptr(logits), a.n, ci, co, a.s, _stream())
+
+
+def conv1x1_bwd(a: B8, w, dlogits, da: B8, dw, db, ci, co):
+    call("msb_conv1x1_bwd", a.mt, _ptr(w), _ptr(dlogits), da.mt, _ptr(dw), _ptr(db), a.n, ci, co, a.s, _stream())
+
+
+def conv_in_fwd(x, w, bias, out: B8, groups, sums):
+    call("msb_conv_in_fwd", _ptr(x), _ptr(w), _ptr(bias), out.mt, out.n, dim3(out.dims), groups, _ptr(sums),
+         _stream())
+
+
+def conv_in_wgrad(x, dy: B8, dw, dbias):
+    call("msb_conv_in_wgrad", _ptr(x), dy.mt, _ptr(dw), _ptr(dbias), dy.n, dim3(dy.dims), _stream())
+
+
+def conv_strided_fwd(x: B8, w, bias, out: B8, kernel, stride, pad, groups, sums, c_red_real=0, c_out_real=0):
+    call("msb_conv_strided_fwd", x.mt, _ptr(w), _ptr(bias), out.mt, x.n, dim3(x.dims), dim3(kernel), dim3(stride),
+         dim3(pad), c_red_real, c_out_real, groups, _ptr(sums), _stream())
+
+
+def conv_strided_bwd_data(x: B8, w, bias, out: B8, kernel, stride, pad, accumulate, groups, sums, c_red_real=0,
+                          c_out_real=0):
+    call("msb_conv_strided_bwd_data", x.mt, _ptr(w), _ptr(bias), out.mt, x.n, dim3(out.dims), dim3(kernel),
+         dim3(stride), dim3(pad), c_red_real, c_out_real, int(accumulate), groups, _ptr(sums), _stream())
+
+
+def conv_strided_wgrad(big: B8, small: B8, dw, dbias, kernel, stride, pad, bias_from_big, c_big_real=0,
+                       c_small_real=0):
+    call("msb_conv_strided_wgrad", big.mt, small.mt, _ptr(dw), _ptr(dbias), big.n, dim3(big.dims), dim3(kernel),
+         dim3(stride), dim3(pad), c_big_real, c_small_real, int(bias_from_big), _stream())
+
+
+def k5_out_pad(c_view: int) -> int:
+    return call("msb_conv_k5_out_pad", c_view)
+
+
+def k5_packed_bytes(cin_pad: int, cout_pad: int) -> int:
+    return call("msb_conv_k5_packed_bytes", cin_pad, cout_pad)
+
+
+def k5_pack(w, packed, cout, cin, mode, cin_pad, cout_pad):
+    call("msb_conv_k5_pack", _ptr(w), _ptr(packed), cout, cin, mode, cin_pad, cout_pad, _stream())
+
+
+def k5_fwd(x: B8, packed, bias, cout, out: B8, accumulate=False, ch_scale=None, groups=1, sums=None):
+    call("msb_conv_k5_fwd", x.mt, _ptr(packed), _ptr(bias), cout, out.mt, x.n, dim3(x.dims), int(accumulate),
+         _ptr(ch_scale), groups, _ptr(sums), _stream())
+
+
+def k5_wgrad_workspace_bytes(cin: int, cout: int) -> int:
+    return call("msb_conv_k5_wgrad_workspace_bytes", cin, cout)
+
+
+def k5_wgrad(x: B8, dy: B8, dw, dbias, cout, cin, workspace: torch.Tensor):
+    call("msb_conv_k5_wgrad", x.mt, dy.mt, _ptr(dw), _ptr(dbias), cout, cin, x.n, dim3(x.dims), _ptr(workspace),
+         workspace.numel() * workspace.element_size(), _stream())
+
+
+# ---- loss ---------------------------------------------------------------------------------------------------
+def class_weight_sums(logits, psum):
+    n, c = logits.shape[:2]
+    call("msb_class_weight_sums", _ptr(logits), n, c, logits[0, 0].numel(), _ptr(psum), _stream())
+
+
+def class_weight_finalize(psum, count, c, weights):
+    call("msb_class_weight_finalize", _ptr(psum), float(count), c, _ptr(weights), _stream())
+
+
+def dice_ce_fwd(logits, labels, class_w, ignore_index, acc):
+    n, c = logits.shape[:2]
+    call("msb_dice_ce_fwd", _ptr(logits), _ptr(labels), _ptr(class_w), n, c, logits[0, 0].numel(), ignore_index,
+         _ptr(acc), _stream())
+
+
+def dice_ce_finalize(acc, c, result):
+    call("msb_dice_ce_finalize", _ptr(acc), c, _ptr(result), _stream())
+
+
+def dice_ce_bwd(logits, labels, class_w, acc, ignore_index, coef_ce, coef_dice, coef_dev, dlogits):
+    n, c = logits.shape[:2]
+    call("msb_dice_ce_bwd", _ptr(logits), _ptr(labels), _ptr(class_w), _ptr(acc), n, c, logits[0, 0].numel(),
+         ignore_index, float(coef_ce), float(coef_dice), _ptr(coef_dev), _ptr(dlogits), _stream())
+
+
+# ---- optimizer ------------------------------------------------------------------------------------------------
+def momentum_step(p, g, v, lr, mu, wd, grad_scale=1.0):
+    call("msb_momentum_step", _ptr(p), _ptr(g), _ptr(v), p.numel(), float(lr), float(mu), float(wd),
+         float(grad_scale), _stream())
+
+
+# ---- preprocessing --------------------------------------------------------------------------------------------
+def hunorm(src, dst, hu_min, hu_max, hu_nan):
+    call("msb_hunorm", _ptr(src), _ptr(dst), src.numel(), float(hu_min), float(hu_max), float(hu_nan), _stream())
+
+
+def minmax(src, out2):
+    call("msb_minmax", _ptr(src), src.numel(), _ptr(out2), _stream())
+
+
+def normalize(src, dst, lo, hi, minmax_dev=None):
+    call("msb_normalize", _ptr(src), _ptr(dst), src.numel(), float(lo), float(hi), _ptr(minmax_dev), _stream())
+
+
+def resample_f32(src, dst, order, pre_op=0, p0=0.0, p1=0.0, p2=0.0):
+    call("msb_resample_f32", _ptr(src), dim3(src.shape), _ptr(dst), dim3(dst.shape), int(order), int(pre_op),
+         float(p0), float(p1), float(p2), _stream())
+
+
+def resample_i32(src, dst):
+    call("msb_resample_i32", _ptr(src), dim3(src.shape), _ptr(dst), dim3(dst.shape), _stream())
+
+
+def label_remap(labels, keys: Sequence[int], vals: Sequence[int]):
+    n = len(keys)
+    ka = (C.c_int32 * max(n, 1))(*keys)
+    va = (C.c_int32 * max(n, 1))(*vals)
+    call("msb_label_remap", _ptr(labels), labels.numel(), C.cast(ka, C.c_void_p), C.cast(va, C.c_void_p), n,
+         _stream())

@@ -1,0 +1,68 @@
+"""Checkpoint helpers (reference: medicalseg/utils/utils.py:76-135).  `.pdparams` files are pickled dicts of
+numpy arrays keyed by the Paddle parameter names this package keeps, so they load without PaddlePaddle."""
+from __future__ import annotations
+
+import os
+import pickle
+
+import numpy as np
+import torch
+
+
+def _load_any(path):
+    if path.startswith("http://") or path.startswith("https://"):
+        raise RuntimeError("downloading pretrained weights is not supported offline; pass a local file: %s" % path)
+    if os.path.isdir(path):
+        path = os.path.join(path, "model.pdparams")
+    if not os.path.exists(path):
+        raise ValueError("The pretrained model directory is not Found: {}".format(path))
+    try:
+        return torch.load(path, map_location="cpu", weights_only=False)
+    except Exception:
+        with open(path, "rb") as fh:
+            return pickle.load(fh, encoding="latin1")
+
+
+def load_entire_model(model, pretrained):
+    """utils.py:76-82 — load every matching-shape key, warn about the rest (utils.py:84-104)."""
+    if pretrained is None:
+        return
+    sd = _load_any(pretrained)
+    own = model.state_dict()
+    ok = {}
+    for k, v in sd.items():
+        if k not in own:
+            print("[WARNING] {} is not in pretrained model".format(k))
+            continue
+        arr = np.asarray(v) if not torch.is_tensor(v) else v
+        if tuple(arr.shape) != tuple(own[k].shape):
+            print("[WARNING] [SKIP] Shape of pretrained params {} doesn't match.(Pretrained: {}, Actual: {})".format(
+                k, tuple(arr.shape), tuple(own[k].shape)))
+            continue
+        ok[k] = arr
+    model.set_state_dict(ok, strict=False)
+    print("[INFO] There are {}/{} variables loaded into {}.".format(len(ok), len(own), model.__class__.__name__))
+
+
+def save_checkpoint(model, optimizer, save_dir):
+    """core/train.py:230-236 layout: <dir>/model.pdparams + model.pdopt (torch pickles of plain tensors)."""
+    os.makedirs(save_dir, exist_ok=True)
+    torch.save({k: v.cpu() for k, v in model.state_dict().items()}, os.path.join(save_dir, "model.pdparams"))
+    if optimizer is not None:
+        torch.save({k: (v.cpu() if torch.is_tensor(v) else v) for k, v in optimizer.state_dict().items()},
+                   os.path.join(save_dir, "model.pdopt"))
+
+
+def resume(model, optimizer, resume_model):
+    """utils.py:115-135 — returns the iteration parsed from the directory suffix iter_N."""
+    if resume_model is None:
+        return 0
+    resume_model = os.path.normpath(resume_model)
+    if not os.path.exists(resume_model):
+        raise ValueError("Directory of the model needed to resume is not Found: {}".format(resume_model))
+    model.set_state_dict(torch.load(os.path.join(resume_model, "model.pdparams"), map_location="cpu"))
+    if optimizer is not None:
+        opt_sd = torch.load(os.path.join(resume_model, "model.pdopt"), map_location="cpu", weights_only=False)
+        opt_sd["velocity"] = opt_sd["velocity"].to(optimizer.velocity.device)
+        optimizer.set_state_dict(opt_sd)
+    return int(resume_model.split("_")[-1])
