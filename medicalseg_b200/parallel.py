@@ -1,0 +1,100 @@
+"""Data-parallel gradient exchange (reference: core/train.py:81-88 — fleet.distributed_model / DataParallel).
+
+One process per GPU; whole volumes are sharded across ranks; the ONLY collective on the training path is the
+gradient all-reduce (NCCL over NVLink 5 / NVSwitch).  The model keeps all gradients in one flat f32 buffer laid
+out in forward order, so backward completes it from the END towards the front: every transition block that
+finishes its backward fires `grad_ready_hook(lo, hi)`, and we launch the all-reduce of that contiguous slice on a
+side stream right away, overlapping it with the rest of backward.  Small slices are coalesced into buckets.
+Averaging (1/world) is folded into the optimizer kernel (Momentum.grad_scale) — no extra pass over the grads.
+
+BatchNorm statistics stay per-rank (north_star: "allreduce for the gradient step only"); the reference converts
+to SyncBatchNorm (cvlibs/config.py:322), which differs at world > 1 — see DESIGN.md.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+class BucketPlanner:
+    """Pure host logic (testable on CPU/gloo): merges (lo, hi) ranges arriving in backward order into buckets
+    of at least `min_elems` elements; ranges must tile the flat buffer from the end to the front."""
+
+    def __init__(self, total: int, min_elems: int):
+        self.total, self.min_elems = total, min_elems
+        self.reset()
+
+    def reset(self):
+        self.pending_lo = self.pending_hi = self.total
+
+    def add(self, lo: int, hi: int) -> Optional[Tuple[int, int]]:
+        if hi != self.pending_lo:
+            raise ValueError("gradient ranges must arrive contiguously from the end: got [%d,%d) after %d"
+                             % (lo, hi, self.pending_lo))
+        self.pending_lo = lo
+        if self.pending_hi - self.pending_lo >= self.min_elems or lo == 0:
+            out = (self.pending_lo, self.pending_hi)
+            self.pending_hi = self.pending_lo
+            return out
+        return None
+
+    def flush(self) -> Optional[Tuple[int, int]]:
+        if self.pending_hi > self.pending_lo:
+            out = (self.pending_lo, self.pending_hi)
+            self.pending_hi = self.pending_lo
+            return out
+        return None
+
+
+class DistributedGradReducer:
+    """Attach to a model: reducer = DistributedGradReducer(model); after loss.backward() call reducer.wait()
+    before optimizer.step().  Works with any torch.distributed backend (nccl on GPUs, gloo in CPU tests)."""
+
+    def __init__(self, flat_grad: torch.Tensor, bucket_mb: float = 32.0, group=None):
+        self.flat_grad = flat_grad
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.planner = BucketPlanner(flat_grad.numel(), int(bucket_mb * (1 << 20) / 4))
+        self.handles: List = []
+        self.comm_stream = torch.cuda.Stream() if flat_grad.is_cuda else None
+        self.launched: List[Tuple[int, int]] = []
+
+    def attach(self, model):
+        model.grad_ready_hook = self.on_ready
+        return self
+
+    def _launch(self, lo: int, hi: int):
+        self.launched.append((lo, hi))
+        if self.world == 1:
+            return
+        view = self.flat_grad[lo:hi]
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                self.handles.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        else:
+            self.handles.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def on_ready(self, lo: int, hi: int):
+        r = self.planner.add(lo, hi)
+        if r is not None:
+            self._launch(*r)
+
+    def wait(self):
+        r = self.planner.flush()
+        if r is not None:
+            self._launch(*r)
+        for h in self.handles:
+            h.wait()
+        if self.comm_stream is not None and self.world > 1:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self.handles = []
+        self.launched = []
+        self.planner.reset()
+
+    @property
+    def grad_scale(self) -> float:
+        """fold the 1/world averaging into the optimizer (paddle DataParallel averages gradients)"""
+        return 1.0 / self.world

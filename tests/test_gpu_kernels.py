@@ -1,0 +1,348 @@
+"""GPU parity tests of every kernel family, called through the C ABI (medicalseg_b200.ops -> libmedseg_b200.so).
+
+Checker = torch reference ops on the same (rounded) inputs; tolerances are stated per test:
+  f32 storage : relative max error <= 2e-5 (1e-3 for long f32 reductions whose reference is itself f32)
+  bf16 storage: relative max error <= 1.2e-2 (one bf16 rounding of the output is 2^-8 = 3.9e-3 relative)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+F32_TOL, BF16_TOL = 2e-5, 1.2e-2
+
+
+def _imp():
+    from medicalseg_b200 import ops
+    from medicalseg_b200.ops import B8
+    return ops, B8
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def tol(dt):
+    return F32_TOL if dt == torch.float32 else BF16_TOL
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_layout_roundtrip_and_padding(dt):
+    ops, B8 = _imp()
+    x = torch.randn(2, 20, 5, 6, 7, device="cuda")
+    b = B8.from_ncdhw(x, dt, 24)
+    ref = x if dt == torch.float32 else x.bfloat16().float()
+    assert torch.equal(b.to_ncdhw(20), ref)
+    assert float(b.to_ncdhw(24)[:, 20:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("groups", ["batch", "instance"])
+def test_bn_prelu_residual_fwd_bwd(dt, groups):
+    ops, B8 = _imp()
+    torch.manual_seed(0)
+    n, c, dims = 2, 16, (6, 7, 9)
+    g = 1 if groups == "batch" else n
+    y = torch.randn(n, c, *dims, device="cuda") * 2 + 0.5
+    r = torch.randn(n, c, *dims, device="cuda")
+    gamma, beta = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda")
+    a1, a2 = torch.rand(c, device="cuda") * 0.5, torch.rand(c, device="cuda") * 0.5
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    yb, rb = B8.from_ncdhw(y, dt), B8.from_ncdhw(r, dt)
+    yq, rq = yb.to_ncdhw().requires_grad_(True), rb.to_ncdhw().requires_grad_(True)
+    sums = torch.zeros(2 * g * c, dtype=torch.float64, device="cuda")
+    ops.bn_stats(yb, g, sums)
+    bnbuf = torch.empty(4 * g * c, device="cuda")
+    count = yb.s * (n if g == 1 else 1)
+    ops.bn_finalize(sums, count, gamma, beta, rm, rv, 0.9, 1e-5, True, c, g, bnbuf)
+    out = B8(n, c, dims, dt, device="cuda")
+    ops.bn_act_fwd(yb, out, rb, None, 0, bnbuf, a1, a2, g)
+    params = [t.clone().requires_grad_(True) for t in (gamma, beta, a1, a2)]
+    g_, b_, a1_, a2_ = params
+    red_dims = (0, 2, 3, 4) if g == 1 else (2, 3, 4)
+    mean = yq.mean(red_dims, keepdim=True)
+    var = yq.var(red_dims, unbiased=False, keepdim=True)
+    v = lambda p: p.view(1, -1, 1, 1, 1)
+    t = (yq - mean) * torch.rsqrt(var + 1e-5) * v(g_) + v(b_)
+    act1 = torch.where(t > 0, t, v(a1_) * t)
+    t2 = act1 + rq
+    ref = torch.where(t2 > 0, t2, v(a2_) * t2)
+    assert rel(out.to_ncdhw(), ref.detach()) <= tol(dt)
+    if g == 1:  # Paddle running-stat convention: 0.9*running + 0.1*batch, biased variance
+        assert float((rm - 0.1 * mean.flatten()).abs().max()) < 1e-6
+        assert float((rv - (0.9 + 0.1 * var.flatten())).abs().max()) < 1e-5
+    go = torch.randn_like(ref)
+    gob = B8.from_ncdhw(go, dt)
+    ref.backward(gob.to_ncdhw())
+    red = torch.zeros(4 * g * c, dtype=torch.float64, device="cuda")
+    ops.bn_act_bwd_reduce(yb, rb, None, 0, gob, bnbuf, a1, a2, g, red)
+    dy, dres = B8(n, c, dims, dt, device="cuda"), B8(n, c, dims, dt, device="cuda")
+    grads = [torch.zeros(c, device="cuda") for _ in range(4)]
+    ops.bn_act_bwd_apply(yb, rb, None, 0, gob, bnbuf, a1, a2, red, count, True, dy, dres, False, *grads, g)
+    assert rel(dy.to_ncdhw(), yq.grad) <= tol(dt)
+    assert rel(dres.to_ncdhw(), rq.grad) <= tol(dt)
+    for got, p in zip(grads, params):
+        assert rel(got, p.grad) <= max(tol(dt), 1e-5)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_in_tr_tile_add(dt):
+    """InputTransition: PReLU(BN(conv(x)) + tile(x,16)) (vnet.py:74-79)"""
+    ops, B8 = _imp()
+    torch.manual_seed(1)
+    n, dims = 2, (9, 11, 37)
+    x = torch.rand(n, 1, *dims, device="cuda")
+    w = torch.randn(16, 1, 5, 5, 5, device="cuda") * 0.1
+    b = torch.randn(16, device="cuda")
+    ref = F.conv3d(x, w, b, padding=2)
+    out = B8(n, 16, dims, dt, device="cuda")
+    sums = torch.zeros(32, dtype=torch.float64, device="cuda")
+    ops.conv_in_fwd(x, w, b, out, 1, sums)
+    o = out.to_ncdhw()
+    assert rel(o, ref) <= tol(dt)
+    assert float((sums[:16] - o.double().sum((0, 2, 3, 4))).abs().max()) < 1e-2
+    gamma, beta, a1 = torch.ones(16, device="cuda"), torch.zeros(16, device="cuda"), torch.full((16,), 0.25, device="cuda")
+    rm, rv = torch.zeros(16, device="cuda"), torch.ones(16, device="cuda")
+    bnbuf = torch.empty(64, device="cuda")
+    ops.bn_finalize(sums, n * out.s, gamma, beta, rm, rv, 0.9, 1e-5, True, 16, 1, bnbuf)
+    act = B8(n, 16, dims, dt, device="cuda")
+    ops.bn_act_fwd(out, act, None, x, 1, bnbuf, a1, None, 1)
+    bn = F.batch_norm(o, None, None, gamma, beta, True, 0.1, 1e-5)
+    t = bn + x.repeat(1, 16, 1, 1, 1)
+    refa = torch.where(t > 0, t, 0.25 * t)
+    assert rel(act.to_ncdhw(), refa) <= tol(dt)
+    dy = torch.randn(n, 16, *dims, device="cuda")
+    dyb = B8.from_ncdhw(dy, dt)
+    dw, dbias = torch.zeros_like(w), torch.zeros_like(b)
+    ops.conv_in_wgrad(x, dyb, dw, dbias)
+    dw_ref = torch.nn.grad.conv3d_weight(x, w.shape, dyb.to_ncdhw(), padding=2)
+    assert rel(dw, dw_ref) <= 1e-3
+    assert rel(dbias, dyb.to_ncdhw().sum((0, 2, 3, 4))) <= 1e-5
+
+
+CASES = [((2, 2, 2), (2, 2, 2), 16, 32, (8, 10, 12)),   # isotropic k=s (lung config)
+         ((2, 2, 4), (2, 2, 1), 16, 32, (8, 8, 12)),    # MRI level 0: overlap along the last axis
+         ((2, 2, 2), (2, 2, 1), 32, 64, (6, 8, 9))]     # MRI level 1
+
+
+@pytest.mark.parametrize("k,s,ci,co,dims", CASES)
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_down_conv_and_up_conv(k, s, ci, co, dims, dt):
+    ops, B8 = _imp()
+    torch.manual_seed(2)
+    n = 2
+    x = torch.randn(n, ci, *dims, device="cuda")
+    w = torch.randn(co, ci, *k, device="cuda") * 0.1
+    b = torch.randn(co, device="cuda")
+    xb = B8.from_ncdhw(x, dt)
+    xq = xb.to_ncdhw().requires_grad_(True)
+    w_ = w.clone().requires_grad_(True)
+    ref = F.conv3d(xq, w_, b, stride=s)
+    od = ref.shape[2:]
+    out = B8(n, co, od, dt, device="cuda")
+    ops.conv_strided_fwd(xb, w, b, out, k, s, (0, 0, 0), 1, None)
+    assert rel(out.to_ncdhw(), ref.detach()) <= max(tol(dt), 3e-4)
+    dyb = B8.from_ncdhw(torch.randn_like(ref), dt)
+    ref.backward(dyb.to_ncdhw())
+    dx = B8(n, ci, dims, dt, device="cuda")
+    ops.conv_strided_bwd_data(dyb, w, None, dx, k, s, (0, 0, 0), False, 1, None)
+    assert rel(dx.to_ncdhw(), xq.grad) <= max(tol(dt), 3e-4)
+    dw, dbias = torch.zeros_like(w), torch.zeros_like(b)
+    ops.conv_strided_wgrad(xb, dyb, dw, dbias, k, s, (0, 0, 0), False)
+    assert rel(dw, w_.grad) <= 1e-3
+    assert rel(dbias, dyb.to_ncdhw().sum((0, 2, 3, 4))) <= 1e-5
+    # Conv3DTranspose, weight [Cin_T = co, Cout_T = ci, k]
+    wt = torch.randn(co, ci, *k, device="cuda") * 0.1
+    bt = torch.randn(ci, device="cuda")
+    xsb = B8.from_ncdhw(torch.randn(n, co, *od, device="cuda"), dt)
+    xsq = xsb.to_ncdhw().requires_grad_(True)
+    wt_ = wt.clone().requires_grad_(True)
+    reft = F.conv_transpose3d(xsq, wt_, bt, stride=s)
+    outt = B8(n, ci, reft.shape[2:], dt, device="cuda")
+    sums = torch.zeros(2 * ci, dtype=torch.float64, device="cuda")
+    ops.conv_strided_bwd_data(xsb, wt, bt, outt, k, s, (0, 0, 0), False, 1, sums)
+    assert rel(outt.to_ncdhw(), reft.detach()) <= max(tol(dt), 3e-4)
+    assert float((sums[:ci] - outt.to_ncdhw().double().sum((0, 2, 3, 4))).abs().max()) < 1e-2
+    dytb = B8.from_ncdhw(torch.randn_like(reft), dt)
+    reft.backward(dytb.to_ncdhw())
+    dxs = B8(n, co, od, dt, device="cuda")
+    ops.conv_strided_fwd(dytb, wt, None, dxs, k, s, (0, 0, 0), 1, None)
+    assert rel(dxs.to_ncdhw(), xsq.grad) <= max(tol(dt), 3e-4)
+    dwt, dbt = torch.zeros_like(wt), torch.zeros_like(bt)
+    ops.conv_strided_wgrad(dytb, xsb, dwt, dbt, k, s, (0, 0, 0), True)
+    assert rel(dwt, wt_.grad) <= 1e-3
+    assert rel(dbt, dytb.to_ncdhw().sum((0, 2, 3, 4))) <= 1e-5
+
+
+K5_CASES = [(32, 32, (6, 16, 8)), (16, 16, (5, 20, 11)), (64, 64, (4, 16, 16)), (128, 128, (3, 16, 8)),
+            (256, 256, (2, 8, 8)), (32, 2, (6, 18, 10)), (32, 32, (9, 7, 13))]
+
+
+@pytest.mark.parametrize("cin,cout,dims", K5_CASES)
+def test_conv_k5_tcgen05_forward(cin, cout, dims):
+    """5x5x5 conv on tensor cores vs F.conv3d on the same bf16-rounded operands; ragged tiles included."""
+    ops, B8 = _imp()
+    torch.manual_seed(3)
+    n = 2
+    x = torch.randn(n, cin, *dims, device="cuda")
+    w = torch.randn(cout, cin, 5, 5, 5, device="cuda") * (2.0 / (cin * 125)) ** 0.5
+    b = torch.randn(cout, device="cuda")
+    xb = B8.from_ncdhw(x, torch.bfloat16)
+    ref = F.conv3d(xb.to_ncdhw(), w.bfloat16().float(), b, padding=2)
+    oc = 16 if cout < 8 else (cout + 7) // 8 * 8
+    cout_pad = ops.k5_out_pad(oc)
+    packed = torch.empty(ops.k5_packed_bytes(cin, cout_pad), dtype=torch.uint8, device="cuda")
+    ops.k5_pack(w, packed, cout, cin, 0, cin, cout_pad)
+    out = B8(n, oc, dims, torch.bfloat16, device="cuda", zero=True)
+    sums = torch.zeros(2 * oc, dtype=torch.float64, device="cuda")
+    ops.k5_fwd(xb, packed, b, cout, out, False, None, 1, sums)
+    o = out.to_ncdhw(cout)
+    assert rel(o, ref) <= BF16_TOL
+    s_ref = o.double().sum((0, 2, 3, 4))
+    assert float((sums[:cout] - s_ref).abs().max()) <= 1e-3 * float(s_ref.abs().max() + 1)
+    q_ref = (o.double() ** 2).sum((0, 2, 3, 4))
+    assert float((sums[oc:oc + cout] - q_ref).abs().max()) <= 1e-4 * float(q_ref.abs().max() + 1)
+
+
+def test_conv_k5_tcgen05_dgrad_accumulate_scale():
+    ops, B8 = _imp()
+    torch.manual_seed(4)
+    n, cin, cout, dims = 2, 32, 32, (6, 16, 8)
+    w = torch.randn(cout, cin, 5, 5, 5, device="cuda") * 0.02
+    dyb = B8.from_ncdhw(torch.randn(n, cout, *dims, device="cuda"), torch.bfloat16)
+    ref = torch.nn.grad.conv3d_input((n, cin, *dims), w.bfloat16().float(), dyb.to_ncdhw(), padding=2)
+    cp = ops.k5_out_pad(cin)
+    packed = torch.empty(ops.k5_packed_bytes(cout, cp), dtype=torch.uint8, device="cuda")
+    ops.k5_pack(w, packed, cout, cin, 1, cout, cp)
+    dx = B8.from_ncdhw(torch.randn(n, cin, *dims, device="cuda"), torch.bfloat16)
+    base = dx.to_ncdhw()
+    scale = (torch.rand(n, cin, device="cuda") > 0.5).float() * 2
+    ops.k5_fwd(dyb, packed, None, cin, dx, True, scale, 1, None)
+    assert rel(dx.to_ncdhw(), base + ref * scale.view(n, cin, 1, 1, 1)) <= BF16_TOL
+
+
+WG_CASES = [(32, 32, (6, 16, 16)), (64, 64, (4, 9, 20)), (128, 128, (3, 8, 16)), (256, 256, (2, 8, 8)),
+            (32, 2, (5, 10, 18)), (16, 16, (5, 8, 16)), (32, 32, (3, 13, 9))]
+
+
+@pytest.mark.parametrize("cin,cout,dims", WG_CASES)
+def test_conv_k5_tcgen05_wgrad(cin, cout, dims):
+    ops, B8 = _imp()
+    torch.manual_seed(5)
+    n = 2
+    dyc = 16 if cout < 8 else (cout + 7) // 8 * 8
+    dy = torch.zeros(n, dyc, *dims, device="cuda")
+    dy[:, :cout] = torch.randn(n, cout, *dims, device="cuda")
+    xb = B8.from_ncdhw(torch.randn(n, cin, *dims, device="cuda"), torch.bfloat16)
+    dyb = B8.from_ncdhw(dy, torch.bfloat16)
+    ref = torch.nn.grad.conv3d_weight(xb.to_ncdhw(), (cout, cin, 5, 5, 5), dyb.to_ncdhw(cout), padding=2)
+    dw = torch.zeros(cout, cin, 5, 5, 5, device="cuda")
+    db = torch.zeros(cout, device="cuda")
+    ws = torch.empty(ops.k5_wgrad_workspace_bytes(cin, cout), dtype=torch.uint8, device="cuda")
+    ops.k5_wgrad(xb, dyb, dw, db, cout, cin, ws)
+    assert rel(dw, ref) <= 1e-4  # bf16 x bf16 products are exact in f32; only the summation order differs
+    assert rel(db, dyb.to_ncdhw(cout).sum((0, 2, 3, 4))) <= 1e-5
+    ops.k5_wgrad(xb, dyb, dw, db, cout, cin, ws)  # accumulates (+=)
+    assert rel(dw, 2 * ref) <= 1e-4
+
+
+@pytest.mark.parametrize("c", [2, 3, 20])
+def test_fused_dice_ce_loss_matches_oracle(c):
+    from oracle import vnet_oracle as vo
+    from medicalseg_b200.models import losses as L
+    torch.manual_seed(6)
+    logits = torch.randn(2, c, 8, 9, 10) * 2
+    labels = torch.randint(0, c, (2, 8, 9, 10), dtype=torch.int32)
+    labels[0, 0, 0, :3] = 255  # ignore_index voxels (CE only)
+    lo = logits.clone().requires_grad_(True)
+    ll, dice = vo.loss_computation([lo], labels, vo.default_losses())
+    sum(ll).backward()
+    lg = logits.cuda().requires_grad_(True)
+    ours = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1])], "coef": [1]}
+    l2, d2 = L.loss_computation([lg], labels.cuda(), ours)
+    sum(l2).backward()
+    for a, b in zip(ll, l2):
+        assert abs(float(a) - float(b)) <= 1e-5  # CE/Dice abs <= 1e-5 in f32
+    assert float(np.abs(dice - d2).max()) <= 1e-6
+    assert rel(lg.grad.cpu(), lo.grad) <= 1e-5
+
+
+def test_conv1x1_head():
+    ops, B8 = _imp()
+    torch.manual_seed(7)
+    n, c, dims = 2, 3, (5, 6, 7)
+    a = torch.zeros(n, 16, *dims, device="cuda")
+    a[:, :c] = torch.randn(n, c, *dims, device="cuda")
+    w, b = torch.randn(c, c, device="cuda"), torch.randn(c, device="cuda")
+    ab = B8.from_ncdhw(a, torch.float32)
+    logits = torch.empty(n, c, *dims, device="cuda")
+    ops.conv1x1_fwd(ab, w, b, logits, c, c)
+    a_ = a[:, :c].clone().requires_grad_(True)
+    w_ = w.clone().requires_grad_(True)
+    b_ = b.clone().requires_grad_(True)
+    ref = F.conv3d(a_, w_.view(c, c, 1, 1, 1), b_)
+    assert rel(logits, ref.detach()) <= 1e-5
+    dl = torch.randn_like(ref)
+    ref.backward(dl)
+    da = B8(n, 16, dims, torch.float32, device="cuda")
+    dw, db = torch.zeros_like(w), torch.zeros_like(b)
+    ops.conv1x1_bwd(ab, w, dl, da, dw, db, c, c)
+    assert rel(da.to_ncdhw(c), a_.grad) <= 1e-5
+    assert rel(dw, w_.grad) <= 1e-4 and rel(db, b_.grad) <= 1e-5
+    assert float(da.to_ncdhw(16)[:, c:].abs().max()) == 0.0
+
+
+def test_momentum_step_matches_oracle():
+    from medicalseg_b200 import ops
+    torch.manual_seed(8)
+    p, g, v = torch.randn(1003), torch.randn(1003), torch.randn(1003)
+    pc, gc, vc = p.cuda(), g.cuda(), v.cuda()
+    ops.momentum_step(pc, gc, vc, 0.01, 0.9, 1e-4, 0.5)
+    v_ref = 0.9 * v + (0.5 * g + 1e-4 * p)
+    p_ref = p - 0.01 * v_ref
+    assert rel(vc.cpu(), v_ref) <= 1e-6 and rel(pc.cpu(), p_ref) <= 1e-6
+
+
+def test_preprocess_matches_reference_golden():
+    """HUnorm / normalize / resample / label_remap vs outputs of the reference's own functions (tests/golden)."""
+    from medicalseg_b200 import preprocess as P
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "preprocess_ref.npz"))
+    for name, shp in (("iso", (16, 16, 16)), ("aniso", (16, 24, 12)), ("up", (20, 17, 23)), ("one", (1, 4, 8))):
+        assert np.array_equal(P.HUnorm(G[name + "_in"]), G[name + "_hunorm"])  # bit-exact
+        r1, sp = P.resample(G[name + "_hunorm"], spacing=(1.0, 0.7, 0.7), new_shape=list(shp), order=1)
+        assert r1.dtype == np.float32 and r1.shape == G[name + "_resample1"].shape
+        # order 1: abs <= 1e-3 on the 0..255 scale (f32 blend vs SciPy's f64), SURVEY §8d
+        assert float(np.abs(r1 - G[name + "_resample1"]).max()) <= 1e-3
+        np.testing.assert_allclose(np.asarray(sp), G[name + "_spacing"])
+        rf, _ = P.resample(G[name + "_in"], new_shape=list(shp), order=1, pre_op=("hunorm", -1200, 600, -2000))
+        assert float(np.abs(rf - G[name + "_resample1"]).max()) <= 1e-3
+        r0, _ = P.resample(G[name + "_label"], new_shape=list(shp), order=0)
+        assert np.array_equal(r0, G[name + "_resample0"])  # order 0: exact
+        vol = np.nan_to_num(G[name + "_in"], nan=0.0)
+        assert float(np.abs(P.normalize(vol) - G[name + "_norm_minmax"]).max()) <= 1e-7
+        assert float(np.abs(P.normalize(vol, 0, 2650) - G[name + "_norm_fixed"]).max()) <= 1e-7
+    assert np.array_equal(P.label_remap(G["remap_in"], {1: 2, 2: 3, 5: 0}), G["remap_out"])
+    r, _ = P.resample(G["spacing_in"], spacing=(2.0, 1.5, 0.5), new_spacing=[1.0, 1.0, 1.0], order=1)
+    assert r.shape == G["spacing_out"].shape and float(np.abs(r - G["spacing_out"]).max()) <= 1e-3
+
+
+def test_resample_full_size_properties():
+    """size-independent properties at a BASELINE-like size: identity zoom is exact, constant volumes stay constant,
+    order-0 output only contains input labels, monotone ramps stay monotone."""
+    from medicalseg_b200 import preprocess as P
+    x = torch.rand(96, 160, 160, device="cuda") * 255
+    same, _ = P.resample(x, new_shape=[96, 160, 160], order=1)
+    assert torch.equal(same, x)
+    const = torch.full((64, 64, 64), 7.25, device="cuda")
+    out, _ = P.resample(const, new_shape=[24, 40, 56], order=1)
+    assert float((out - 7.25).abs().max()) == 0.0
+    lab = torch.randint(0, 3, (96, 128, 128), device="cuda", dtype=torch.int32)
+    o0, _ = P.resample(lab, new_shape=[32, 32, 32], order=0)
+    assert set(o0.unique().tolist()) <= {0, 1, 2}
+    ramp = torch.arange(256, device="cuda", dtype=torch.float32).view(1, 1, 256).expand(8, 8, 256).contiguous()
+    r, _ = P.resample(ramp, new_shape=[8, 8, 64], order=1)
+    assert bool((r[..., 1:] > r[..., :-1]).all())
