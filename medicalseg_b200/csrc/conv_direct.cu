@@ -213,6 +213,26 @@ __device__ __forceinline__ void stage_weights(const float* __restrict__ w, const
   }
 }
 
+// adds pre-accumulated per-thread sums (st) and sums of squares (sq) of 8 channels to the BN accumulators
+__device__ __forceinline__ void block_bn_sums2(const float (&st)[8], const float (&sq)[8], int groups, int n,
+                                               int c_total, int oc8, double* __restrict__ sums,
+                                               float* red /*[warps][16]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float r0 = warp_sum(st[i]), r1 = warp_sum(sq[i]);
+    if (lane == 0) { red[warp * 16 + i] = r0; red[warp * 16 + 8 + i] = r1; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    double t = 0;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) t += (double)red[wv * 16 + threadIdx.x];
+    const int g = groups == 1 ? 0 : n;
+    const int stat = threadIdx.x >> 3, j = threadIdx.x & 7;
+    atomicAdd(&sums[((int64_t)stat * groups + g) * c_total + oc8 * 8 + j], t);
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ void block_bn_sums(const float (&o)[8], bool valid, int groups, int n, int c_total,
                                               int oc8, double* __restrict__ sums, float* red /*[4][16]*/) {
@@ -238,6 +258,23 @@ __device__ __forceinline__ void block_bn_sums(const float (&o)[8], bool valid, i
   }
 }
 
+constexpr int kGVox = 4;  // output voxels per thread: the 8x8 weight block in registers is reused 4x
+
+__device__ __forceinline__ void fma_8x8(const float (&a)[8], const float (&wr)[64], float (&acc)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(a[i], wr[i * 8 + j], acc[j]);
+}
+
+__device__ __forceinline__ void load_w64(const float* wt, float (&wr)[64]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float4 t = *reinterpret_cast<const float4*>(wt + i * 4);
+    wr[i * 4] = t.x; wr[i * 4 + 1] = t.y; wr[i * 4 + 2] = t.z; wr[i * 4 + 3] = t.w;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kSThreads)
     conv_gather_kernel(msb_tensor x, const float* __restrict__ w, const float* __restrict__ bias, msb_tensor out,
@@ -246,52 +283,76 @@ __global__ void __launch_bounds__(kSThreads)
   __shared__ float red[(kSThreads / 32) * 16];
   const int oc8 = blockIdx.y, n = blockIdx.z;
   const int64_t so = (int64_t)g.out.d * g.out.h * g.out.w, si = (int64_t)g.in.d * g.in.h * g.in.w;
-  const int64_t v = (int64_t)blockIdx.x * kSThreads + threadIdx.x;
-  const bool valid = v < so;
-  const int ow = (int)(v % g.out.w), oh = (int)((v / g.out.w) % g.out.h), od = (int)(v / ((int64_t)g.out.w * g.out.h));
-  float acc[8];
+  const int64_t vbase = (int64_t)blockIdx.x * (kSThreads * kGVox) + threadIdx.x;
+  bool valid[kGVox];
+  int od[kGVox], oh[kGVox], ow[kGVox];
+  float acc[kGVox][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = (bias && oc8 * 8 + j < g.cout_real) ? __ldg(bias + oc8 * 8 + j) : 0.f;
+  for (int i = 0; i < kGVox; ++i) {
+    const int64_t v = vbase + (int64_t)i * kSThreads;
+    valid[i] = v < so;
+    const int64_t vv = valid[i] ? v : 0;
+    ow[i] = (int)(vv % g.out.w);
+    oh[i] = (int)((vv / g.out.w) % g.out.h);
+    od[i] = (int)(vv / ((int64_t)g.out.w * g.out.h));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = (bias && oc8 * 8 + j < g.cout_real) ? __ldg(bias + oc8 * 8 + j) : 0.f;
+  }
   for (int rc0 = 0; rc0 < g.cred; rc0 += rchunk) {
     __syncthreads();
     stage_weights<true>(w, g, oc8, rc0, rchunk, ws);
     __syncthreads();
-    if (!valid) continue;
     int tap = 0;
-    for (int kd = 0; kd < g.k.d; ++kd) {
-      const int id = od * g.s.d + kd - g.p.d;
-      for (int kh = 0; kh < g.k.h; ++kh) {
-        const int ih = oh * g.s.h + kh - g.p.h;
+    for (int kd = 0; kd < g.k.d; ++kd)
+      for (int kh = 0; kh < g.k.h; ++kh)
         for (int kw = 0; kw < g.k.w; ++kw, ++tap) {
-          const int iw = ow * g.s.w + kw - g.p.w;
-          if (id < 0 || id >= g.in.d || ih < 0 || ih >= g.in.h || iw < 0 || iw >= g.in.w) continue;
-          const int64_t vi = ((int64_t)id * g.in.h + ih) * g.in.w + iw;
+          int64_t vi[kGVox];
+          bool ok[kGVox];
+#pragma unroll
+          for (int i = 0; i < kGVox; ++i) {
+            const int id = od[i] * g.s.d + kd - g.p.d, ih = oh[i] * g.s.h + kh - g.p.h, iw = ow[i] * g.s.w + kw - g.p.w;
+            ok[i] = valid[i] && id >= 0 && id < g.in.d && ih >= 0 && ih < g.in.h && iw >= 0 && iw < g.in.w;
+            vi[i] = ok[i] ? ((int64_t)id * g.in.h + ih) * g.in.w + iw : 0;
+          }
           const float* wt = ws + (int64_t)tap * rchunk * 8;
           for (int r8 = 0; r8 < rchunk / 8; ++r8) {
-            float a[8];
-            Vec8<T>::load(view_ptr<T>(x, n, rc0 / 8 + r8, si, vi), a);
+            float a[kGVox][8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 w0 = *reinterpret_cast<const float4*>(wt + (r8 * 8 + i) * 8);
-              const float4 w1 = *reinterpret_cast<const float4*>(wt + (r8 * 8 + i) * 8 + 4);
-              acc[0] = fmaf(a[i], w0.x, acc[0]); acc[1] = fmaf(a[i], w0.y, acc[1]);
-              acc[2] = fmaf(a[i], w0.z, acc[2]); acc[3] = fmaf(a[i], w0.w, acc[3]);
-              acc[4] = fmaf(a[i], w1.x, acc[4]); acc[5] = fmaf(a[i], w1.y, acc[5]);
-              acc[6] = fmaf(a[i], w1.z, acc[6]); acc[7] = fmaf(a[i], w1.w, acc[7]);
+            for (int i = 0; i < kGVox; ++i) {
+              if (ok[i]) Vec8<T>::load(view_ptr<T>(x, n, rc0 / 8 + r8, si, vi[i]), a[i]);
+              else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[i][j] = 0.f;
+              }
             }
+            float wr[64];
+            load_w64(wt + r8 * 64, wr);
+#pragma unroll
+            for (int i = 0; i < kGVox; ++i) fma_8x8(a[i], wr, acc[i]);
           }
         }
-      }
-    }
   }
-  if (valid) {
+  float st[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = Vec8<T>::round(acc[j]);
-    Vec8<T>::store(view_ptr<T>(out, n, oc8, so, v), acc);
+  for (int j = 0; j < 8; ++j) st[j] = 0.f;
+  float sq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sq[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < kGVox; ++i) {
+    if (valid[i]) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[i][j] = Vec8<T>::round(acc[i][j]);
+        st[j] += acc[i][j];
+        sq[j] += acc[i][j] * acc[i][j];
+      }
+      Vec8<T>::store(view_ptr<T>(out, n, oc8, so, vbase + (int64_t)i * kSThreads), acc[i]);
+    }
   }
   if (sums != nullptr) {
     __syncthreads();
-    block_bn_sums<T>(acc, valid, groups, n, g.cout, oc8, sums, red);
+    block_bn_sums2(st, sq, groups, n, g.cout, oc8, sums, red);
   }
 }
 
@@ -361,6 +422,94 @@ __global__ void __launch_bounds__(kSThreads)
   }
 }
 
+// Non-overlapping fast path of the scatter form (kernel == stride, kernel.w == 2): every output voxel receives
+// exactly one tap.  Block = (chunk of small-grid voxels, (8-out-channel plane, kd, kh), n); a thread owns 2 input
+// voxels and both kw taps, so it stores 32 contiguous bytes per (voxel, plane) and reuses each 8x8 weight block.
+constexpr int kXVox = 2;
+
+template <typename T>
+__global__ void __launch_bounds__(kSThreads)
+    conv_expand_k2_kernel(msb_tensor x, const float* __restrict__ w, const float* __restrict__ bias, msb_tensor out,
+                          ConvGeom g, int accumulate, int groups, double* __restrict__ sums) {
+  extern __shared__ __align__(16) float ws[];  // [kw 2][rc][8 oc]
+  __shared__ float red[(kSThreads / 32) * 16];
+  const int dh = g.k.d * g.k.h;
+  const int oc8 = blockIdx.y / dh, kd = (blockIdx.y % dh) / g.k.h, kh = blockIdx.y % g.k.h, n = blockIdx.z;
+  for (int i = threadIdx.x; i < 2 * g.cred * 8; i += blockDim.x) {
+    const int j = i & 7, rc = (i >> 3) % g.cred, kw = i / (8 * g.cred);
+    const int oc = oc8 * 8 + j;
+    const int tap = (kd * g.k.h + kh) * 2 + kw;
+    ws[i] = (oc < g.cout_real && rc < g.cred_real) ? __ldg(w + ((int64_t)rc * g.cout_real + oc) * g.taps + tap) : 0.f;
+  }
+  __syncthreads();
+  const int64_t sl = (int64_t)g.in.d * g.in.h * g.in.w, ss = (int64_t)g.out.d * g.out.h * g.out.w;
+  const int64_t vbase = (int64_t)blockIdx.x * (kSThreads * kXVox) + threadIdx.x;
+  bool valid[kXVox];
+  int64_t vo[kXVox];
+  float acc[kXVox][2][8];
+#pragma unroll
+  for (int i = 0; i < kXVox; ++i) {
+    const int64_t v = vbase + (int64_t)i * kSThreads;
+    valid[i] = v < ss;
+    const int64_t vv = valid[i] ? v : 0;
+    const int ow = (int)(vv % g.out.w), oh = (int)((vv / g.out.w) % g.out.h), od = (int)(vv / ((int64_t)g.out.w * g.out.h));
+    vo[i] = ((int64_t)(od * g.s.d + kd) * g.in.h + (oh * g.s.h + kh)) * g.in.w + ow * 2;
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][k][j] = (bias && oc8 * 8 + j < g.cout_real) ? __ldg(bias + oc8 * 8 + j) : 0.f;
+    if (valid[i] && accumulate) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        float prev[8];
+        Vec8<T>::load(view_ptr<T>(out, n, oc8, sl, vo[i] + k), prev);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][k][j] += prev[j];
+      }
+    }
+  }
+  for (int r8 = 0; r8 < g.cred / 8; ++r8) {
+    float a[kXVox][8];
+#pragma unroll
+    for (int i = 0; i < kXVox; ++i) {
+      if (valid[i]) Vec8<T>::load(view_ptr<T>(x, n, r8, ss, vbase + (int64_t)i * kSThreads), a[i]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[i][j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      float wr[64];
+      load_w64(ws + ((int64_t)k * g.cred + r8 * 8) * 8, wr);
+#pragma unroll
+      for (int i = 0; i < kXVox; ++i) fma_8x8(a[i], wr, acc[i][k]);
+    }
+  }
+  float st[8], sq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) st[j] = sq[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < kXVox; ++i) {
+    if (valid[i]) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[i][k][j] = Vec8<T>::round(acc[i][k][j]);
+          st[j] += acc[i][k][j];
+          sq[j] += acc[i][k][j] * acc[i][k][j];
+        }
+        Vec8<T>::store(view_ptr<T>(out, n, oc8, sl, vo[i] + k), acc[i][k]);
+      }
+    }
+  }
+  if (sums != nullptr) {
+    __syncthreads();
+    block_bn_sums2(st, sq, groups, n, g.cout, oc8, sums, red);
+  }
+}
+
 // wgrad: block = (small-grid voxel chunk, (bc8, sc8) pair, n); loops taps; 8x8 outer products per voxel.
 constexpr int kWThreads = 256;
 constexpr int kWVoxPerBlock = 8192;
@@ -382,19 +531,34 @@ __global__ void __launch_bounds__(kWThreads)
         float acc[64];
 #pragma unroll
         for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-        for (int64_t v = v0 + threadIdx.x; v < v1; v += kWThreads) {
-          const int ow = (int)(v % g.out.w), oh = (int)((v / g.out.w) % g.out.h),
-                    od = (int)(v / ((int64_t)g.out.w * g.out.h));
-          const int bd = od * g.s.d + kd - g.p.d, bh = oh * g.s.h + kh - g.p.h, bw = ow * g.s.w + kw - g.p.w;
-          if (bd < 0 || bd >= g.in.d || bh < 0 || bh >= g.in.h || bw < 0 || bw >= g.in.w) continue;
-          const int64_t vb = ((int64_t)bd * g.in.h + bh) * g.in.w + bw;
-          float a[8], b[8];
-          Vec8<T>::load(view_ptr<T>(big, n, bc8, sb, vb), a);
-          Vec8<T>::load(view_ptr<T>(small, n, sc8, ss, v), b);
+        for (int64_t vb0 = v0 + threadIdx.x; vb0 < v1; vb0 += 4 * kWThreads) {
+          float a[4][8], b[4][8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+          for (int u = 0; u < 4; ++u) {
+            const int64_t v = vb0 + (int64_t)u * kWThreads;
+            bool ok = v < v1;
+            int64_t vb = 0;
+            if (ok) {
+              const int ow = (int)(v % g.out.w), oh = (int)((v / g.out.w) % g.out.h),
+                        od = (int)(v / ((int64_t)g.out.w * g.out.h));
+              const int bd = od * g.s.d + kd - g.p.d, bh = oh * g.s.h + kh - g.p.h, bw = ow * g.s.w + kw - g.p.w;
+              ok = bd >= 0 && bd < g.in.d && bh >= 0 && bh < g.in.h && bw >= 0 && bw < g.in.w;
+              vb = ((int64_t)bd * g.in.h + bh) * g.in.w + bw;
+            }
+            if (ok) {
+              Vec8<T>::load(view_ptr<T>(big, n, bc8, sb, vb), a[u]);
+              Vec8<T>::load(view_ptr<T>(small, n, sc8, ss, v), b[u]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i * 8 + j] = fmaf(b[i], a[j], acc[i * 8 + j]);  // [sc][bc]
+              for (int j = 0; j < 8; ++j) a[u][j] = b[u][j] = 0.f;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[i * 8 + j] = fmaf(b[u][i], a[u][j], acc[i * 8 + j]);  // [sc][bc]
         }
 #pragma unroll
         for (int i = 0; i < 64; ++i) {
@@ -520,7 +684,7 @@ int msb_conv_strided_fwd(msb_tensor x, const float* w, const float* bias, msb_te
   const size_t smem = (size_t)g.taps * rchunk * 8 * sizeof(float);
   MSB_REQUIRE(smem <= 200 * 1024, "msb_conv_strided_fwd: kernel volume too large for shared memory");
   const int64_t so = (int64_t)g.out.d * g.out.h * g.out.w;
-  const dim3 grid((unsigned)((so + kSThreads - 1) / kSThreads), out.c / 8, n);
+  const dim3 grid((unsigned)((so + kSThreads * kGVox - 1) / (kSThreads * kGVox)), out.c / 8, n);
   cudaStream_t st = as_stream(stream);
   MSB_DISPATCH_DTYPE(x.dtype, {
     if (smem > 48 * 1024)
@@ -540,12 +704,26 @@ int msb_conv_strided_bwd_data(msb_tensor x, const float* w, const float* bias, m
   ConvGeom g;
   int rc = make_geom(out_dims, kernel, stride, pad, x.c, out.c, c_red_real, c_out_real, &g);
   if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  const bool fast = kernel.d == stride.d && kernel.h == stride.h && kernel.w == stride.w && kernel.w == 2 &&
+                    pad.d == 0 && pad.h == 0 && pad.w == 0 && out_dims.d == g.out.d * stride.d &&
+                    out_dims.h == g.out.h * stride.h && out_dims.w == g.out.w * 2 &&
+                    (size_t)2 * g.cred * 8 * sizeof(float) <= 48 * 1024;
+  if (fast) {
+    const int64_t ss = (int64_t)g.out.d * g.out.h * g.out.w;
+    const dim3 fgrid((unsigned)((ss + kSThreads * kXVox - 1) / (kSThreads * kXVox)),
+                     (out.c / 8) * kernel.d * kernel.h, n);
+    const size_t fsmem = (size_t)2 * g.cred * 8 * sizeof(float);
+    MSB_DISPATCH_DTYPE(x.dtype, conv_expand_k2_kernel<T><<<fgrid, kSThreads, fsmem, st>>>(x, w, bias, out, g,
+                                                                                          accumulate, groups, sums););
+    MSB_LAUNCH_OK();
+    return MSB_OK;
+  }
   const int rchunk = pick_rchunk(g.taps, g.cred);
   const size_t smem = (size_t)g.taps * rchunk * 8 * sizeof(float);
   MSB_REQUIRE(smem <= 200 * 1024, "msb_conv_strided_bwd_data: kernel volume too large for shared memory");
   const int64_t sl = (int64_t)g.in.d * g.in.h * g.in.w;
   const dim3 grid((unsigned)((sl + kSThreads - 1) / kSThreads), out.c / 8, n);
-  cudaStream_t st = as_stream(stream);
   MSB_DISPATCH_DTYPE(x.dtype, {
     if (smem > 48 * 1024)
       MSB_CUDA_OK(cudaFuncSetAttribute(conv_scatter_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -15,6 +15,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "conv_k5.cuh"
 #include "umma.cuh"
 
 namespace msb {
@@ -22,10 +23,9 @@ namespace msb {
 constexpr int kTileW = 8, kTileH = 16;
 constexpr int kHaloW = kTileW + 4, kHaloH = kTileH + 4;
 constexpr int kTapsPerStage = 5;
-constexpr int kNumTaps = 125;
 constexpr int kStagesPerChunk = kNumTaps / kTapsPerStage;
 
-template <int NPAD, int TD>
+template <int NPAD, int TD, int ACC_SETS = 2, bool TS = false>
 struct FwdCfg {
   static constexpr int kHaloPlaneBytes = (TD + 4) * kHaloH * kHaloW * 16;  // one c8 plane of the haloed tile
   static constexpr int kHaloBytes = 2 * kHaloPlaneBytes;                   // 16 input channels
@@ -33,11 +33,14 @@ struct FwdCfg {
   static constexpr int kWStageBytes = kTapsPerStage * kWTapBytes;
   static constexpr int kWStages = (NPAD >= 256) ? 3 : 4;
   static constexpr int kAccCols = TD * NPAD;
-  static constexpr int kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : (2 * kAccCols <= 128) ? 128
-                                 : (2 * kAccCols <= 256) ? 256 : 512;
+  static constexpr int kASlots = 4;                       // TS mode: K16 activation windows staged in TMEM (8 cols each)
+  static constexpr int kAColBase = ACC_SETS * kAccCols;
+  static constexpr int kColsNeeded = ACC_SETS * kAccCols + (TS ? kASlots * 8 : 0);
+  static constexpr int kTmemCols = (kColsNeeded <= 32) ? 32 : (kColsNeeded <= 64) ? 64 : (kColsNeeded <= 128) ? 128
+                                 : (kColsNeeded <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = 2 * kHaloBytes + kWStages * kWStageBytes + 1024 /*barriers + stats*/ +
                                     4 * 2 * NPAD * 4 + 128 /*alignment slack*/;
-  static_assert(2 * kAccCols <= 512, "TMEM overflow");
+  static_assert(kColsNeeded <= 512, "TMEM overflow");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory overflow");
 };
 
@@ -85,10 +88,10 @@ __device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
   return r;
 }
 
-template <int NPAD, int TD>
+template <int NPAD, int TD, int ACC_SETS, bool TS>
 __global__ void __launch_bounds__(256, 1)
     conv_k5_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const FwdParams p) {
-  using Cfg = FwdCfg<NPAD, TD>;
+  using Cfg = FwdCfg<NPAD, TD, ACC_SETS, TS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* halo_smem = smem;                                   // [2][kHaloBytes]
@@ -163,9 +166,9 @@ __global__ void __launch_bounds__(256, 1)
       const uint32_t a_sbo = p.dbg_swap ? (uint32_t)Cfg::kHaloPlaneBytes : (uint32_t)(kHaloW * 16);
       const uint32_t b_lbo = p.dbg_swap ? 128u : (uint32_t)(NPAD * 16);
       const uint32_t b_sbo = p.dbg_swap ? (uint32_t)(NPAD * 16) : 128u;
-      uint32_t huse = 0, wuse = 0, iuse = 0;
+      uint32_t huse = 0, wuse = 0, iuse = 0, ause = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
-        const uint32_t as = iuse & 1, aph = (iuse >> 1) & 1;
+        const uint32_t as = iuse % ACC_SETS, aph = (iuse / ACC_SETS) & 1;
         ptx::mbar_wait(BAR(14 + as), aph ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_base = tmem_base + as * Cfg::kAccCols;
@@ -174,21 +177,38 @@ __global__ void __launch_bounds__(256, 1)
           ptx::mbar_wait(BAR(0 + hb), hph);
           const uint32_t halo_addr = ptx::smem_u32(halo_smem + hb * Cfg::kHaloBytes);
           const uint64_t a_desc0 = ptx::make_desc(halo_addr, a_lbo, a_sbo);
-          int tap = 0;
+          // weight stage st holds the 5 kd taps of one (kh, kw) column (packed kd-minor)
           for (int st = 0; st < kStagesPerChunk; ++st, ++wuse) {
             const uint32_t s = wuse % Cfg::kWStages, wph = (wuse / Cfg::kWStages) & 1;
             ptx::mbar_wait(BAR(4 + s), wph);
             ptx::tc_fence_after();
             const uint64_t b_desc0 = ptx::make_desc(ptx::smem_u32(w_smem + s * Cfg::kWStageBytes), b_lbo, b_sbo);
+            const int kh = st / 5, kw = st % 5;
+            const uint32_t hw_off = (uint32_t)(kh * kHaloW + kw);  // 16-byte units
+            if constexpr (!TS) {
 #pragma unroll
-            for (int t = 0; t < kTapsPerStage; ++t, ++tap) {
-              const int kd = tap / 25, kh = (tap / 5) % 5, kw = tap % 5;
-              const uint32_t a_off = (uint32_t)((kd * kHaloH + kh) * kHaloW + kw);  // 16-byte units
-              const uint64_t b_desc = b_desc0 + (uint64_t)((t * Cfg::kWTapBytes) >> 4);
+              for (int kd = 0; kd < 5; ++kd) {
+                const uint64_t b_desc = b_desc0 + (uint64_t)((kd * Cfg::kWTapBytes) >> 4);
 #pragma unroll
-              for (int td = 0; td < TD; ++td) {
-                const uint64_t a_desc = a_desc0 + (uint64_t)(a_off + td * kHaloH * kHaloW);
-                ptx::mma_bf16(d_base + td * NPAD, a_desc, b_desc, idesc, (ck | tap) != 0 ? 1u : 0u);
+                for (int td = 0; td < TD; ++td) {
+                  const uint64_t a_desc = a_desc0 + (uint64_t)(hw_off + (td + kd) * kHaloH * kHaloW);
+                  ptx::mma_bf16(d_base + td * NPAD, a_desc, b_desc, idesc, (ck | st | kd) != 0 ? 1u : 0u);
+                }
+              }
+            } else {
+              // each haloed d-plane window is copied smem -> TMEM once and feeds every (td, kd) with td + kd = plane
+#pragma unroll
+              for (int pl = 0; pl < TD + 4; ++pl, ++ause) {
+                const uint32_t a_tmem = tmem_base + Cfg::kAColBase + (ause % Cfg::kASlots) * 8;
+                ptx::tmem_cp_128x256b(a_tmem, a_desc0 + (uint64_t)(hw_off + pl * kHaloH * kHaloW));
+#pragma unroll
+                for (int kd = 0; kd < 5; ++kd) {
+                  const int td = pl - kd;
+                  if (td >= 0 && td < TD) {
+                    const uint64_t b_desc = b_desc0 + (uint64_t)((kd * Cfg::kWTapBytes) >> 4);
+                    ptx::mma_bf16_ts(d_base + td * NPAD, a_tmem, b_desc, idesc, (ck | st | kd) != 0 ? 1u : 0u);
+                  }
+                }
               }
             }
             ptx::mma_commit(BAR(8 + s));  // weight stage free once these MMAs retire
@@ -213,7 +233,7 @@ __global__ void __launch_bounds__(256, 1)
       const int th = r % p.tiles_h; const int db = r / p.tiles_h;
       const int h = th * kTileH + hh, w = tw * kTileW + ww;
       const bool inb = h < p.h && w < p.w;
-      const uint32_t as = iuse & 1, aph = (iuse >> 1) & 1;
+      const uint32_t as = iuse % ACC_SETS, aph = (iuse / ACC_SETS) & 1;
       ptx::mbar_wait(BAR(12 + as), aph);
       ptx::tc_fence_after();
       const uint32_t t_base = tmem_base + as * Cfg::kAccCols + ((uint32_t)(q * 32) << 16);
@@ -533,7 +553,8 @@ __global__ void __launch_bounds__(256) pack_k5_kernel(const float* __restrict__ 
     int64_t r = i >> 3;
     const int oc = (int)(r % cout_pad); r /= cout_pad;
     const int k8 = (int)(r & 1); r >>= 1;
-    const int tap = (int)(r % kNumTaps);
+    const int tslot = (int)(r % kNumTaps);            // packed order: (kh, kw) column major, kd minor
+    const int tap = (tslot % 5) * 25 + tslot / 5;     // natural tap index kd*25 + kh*5 + kw
     const int chunk = (int)(r / kNumTaps);
     const int rc = chunk * 16 + k8 * 8 + j;
     float v = 0.f;
@@ -594,17 +615,52 @@ int make_b8_tmap(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 dims, in
   return MSB_OK;
 }
 
+int make_b8_tmap_hmajor(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 dims, int box_w, int box_p, int box_h,
+                        int box_d) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return MSB_ERR_CUDA;
+  }
+  const int64_t S = (int64_t)dims.d * dims.h * dims.w;
+  if (t.n_stride % (S * 8) != 0) {
+    set_error("tensor view: n_stride must be a multiple of D*H*W*8");
+    return MSB_ERR_INVALID;
+  }
+  const int64_t planes_total = t.n_stride / (S * 8);
+  const cuuint64_t gdim[4] = {(cuuint64_t)dims.w * 8, (cuuint64_t)((n - 1) * planes_total + t.c / 8),
+                              (cuuint64_t)dims.h, (cuuint64_t)dims.d};
+  const cuuint64_t gstr[3] = {(cuuint64_t)S * 16, (cuuint64_t)dims.w * 16, (cuuint64_t)dims.h * dims.w * 16};
+  const cuuint32_t box[4] = {(cuuint32_t)box_w * 8, (cuuint32_t)box_p, (cuuint32_t)box_h, (cuuint32_t)box_d};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t.ptr, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (h-major) failed with CUresult %d", (int)r);
+    return MSB_ERR_CUDA;
+  }
+  return MSB_OK;
+}
+
 int g_debug_flags[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
-template <int NPAD, int TD>
-static int launch_fwd(const CUtensorMap& tmap, FwdParams& p, cudaStream_t st) {
-  using Cfg = FwdCfg<NPAD, TD>;
+template <int NPAD, int TD, int ACC_SETS = 2, bool TS = false>
+static int launch_fwd(const msb_tensor& x, msb_dim3 dims, FwdParams& p, cudaStream_t st) {
+  using Cfg = FwdCfg<NPAD, TD, ACC_SETS, TS>;
+  CUtensorMap tmap;
+  int rc = make_b8_tmap(&tmap, x, p.n, dims, kHaloW, kHaloH, TD + 4, 2);
+  if (rc) return rc;
   p.dblocks = (p.d + TD - 1) / TD;
   const int items = p.n * p.dblocks * p.tiles_h * p.tiles_w;
   const int grid = items < kNumSMs ? items : kNumSMs;
-  MSB_CUDA_OK(cudaFuncSetAttribute(conv_k5_fwd_kernel<NPAD, TD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   Cfg::kSmemBytes));
-  conv_k5_fwd_kernel<NPAD, TD><<<grid, 256, Cfg::kSmemBytes, st>>>(tmap, p);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MSB_CUDA_OK(cudaFuncSetAttribute(conv_k5_fwd_kernel<NPAD, TD, ACC_SETS, TS>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  conv_k5_fwd_kernel<NPAD, TD, ACC_SETS, TS><<<grid, 256, Cfg::kSmemBytes, st>>>(tmap, p);
   MSB_LAUNCH_OK();
   return MSB_OK;
 }
@@ -689,26 +745,15 @@ int msb_conv_k5_fwd(msb_tensor x, const void* packed, const float* bias, int cou
   p.packed = packed; p.bias = bias; p.out = out; p.accumulate = accumulate; p.ch_scale = ch_scale;
   p.groups = groups; p.sums = sums; p.sums_c = out.c; p.dbg_swap = g_debug_flags[0];
   cudaStream_t st = as_stream(stream);
-  CUtensorMap tmap;
-  int rc;
-  int npad_sel = npad <= 16 ? 16 : npad <= 32 ? 32 : npad <= 64 ? 64 : npad <= 128 ? 128 : 256;
+  const int npad_sel = msb_conv_k5_out_pad(out.c);
   // NOTE: the packed operand must have been built with cout_pad == npad_sel.
+  const bool ts = g_debug_flags[3] != 0;  // A operand staged through TMEM (tcgen05.cp) and reused along d
   switch (npad_sel) {
-    case 16:
-      if ((rc = make_b8_tmap(&tmap, x, n, dims, kHaloW, kHaloH, 4 + 4, 2))) return rc;
-      return launch_fwd<16, 4>(tmap, p, st);
-    case 32:
-      if ((rc = make_b8_tmap(&tmap, x, n, dims, kHaloW, kHaloH, 4 + 4, 2))) return rc;
-      return launch_fwd<32, 4>(tmap, p, st);
-    case 64:
-      if ((rc = make_b8_tmap(&tmap, x, n, dims, kHaloW, kHaloH, 4 + 4, 2))) return rc;
-      return launch_fwd<64, 4>(tmap, p, st);
-    case 128:
-      if ((rc = make_b8_tmap(&tmap, x, n, dims, kHaloW, kHaloH, 2 + 4, 2))) return rc;
-      return launch_fwd<128, 2>(tmap, p, st);
-    default:
-      if ((rc = make_b8_tmap(&tmap, x, n, dims, kHaloW, kHaloH, 1 + 4, 2))) return rc;
-      return launch_fwd<256, 1>(tmap, p, st);
+    case 16: return ts ? launch_fwd<16, 4, 2, true>(x, dims, p, st) : launch_fwd<16, 4>(x, dims, p, st);
+    case 32: return ts ? launch_fwd<32, 4, 2, true>(x, dims, p, st) : launch_fwd<32, 4>(x, dims, p, st);
+    case 64: return ts ? launch_fwd<64, 3, 2, true>(x, dims, p, st) : launch_fwd<64, 4>(x, dims, p, st);
+    case 128: return ts ? launch_fwd<128, 3, 1, true>(x, dims, p, st) : launch_fwd<128, 2>(x, dims, p, st);
+    default: return launch_fwd<256, 1>(x, dims, p, st);
   }
 }
 
@@ -743,7 +788,11 @@ int msb_conv_k5_wgrad(msb_tensor x, msb_tensor dy, float* dw, float* dbias, int 
   p.ws = reinterpret_cast<float*>(workspace);
   p.dbg_swap = g_debug_flags[1];
   const int npad = msb_conv_k5_out_pad(dy.c);
-  int rc;
+  int rc = MSB_ERR_UNSUPPORTED;
+  if (g_debug_flags[2] == 0) rc = launch_wgrad_v2(x, dy, cout, cin, n, dims, p.ws, st);
+  if (rc != MSB_ERR_UNSUPPORTED) {
+    if (rc) return rc;
+  } else
   switch (npad) {
     case 16: rc = launch_wgrad<16, 8>(x, dy, p, dims, st); break;
     case 32: rc = launch_wgrad<32, 8>(x, dy, p, dims, st); break;

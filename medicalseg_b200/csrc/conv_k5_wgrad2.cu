@@ -1,0 +1,233 @@
+// Weight gradient of the 5x5x5 conv, "kh-stacked" variant for narrow outputs (Cout <= 48):
+//   dW[kd,kh,kw][ci][co] = sum_u X[u + (kd-2, 0, kw-2)][ci] * dY[u - (0, kh-2, 0)][co]     (u = input voxel)
+// One tcgen05.mma accumulates D[(kd-stack, ci) x (kh-stack, co)]:
+//   * M = 128 rows = QM stacked kd planes x min(Cin,128) channels  (X tile stored [plane][c8][h][w][8])
+//   * N = 5 stacked kh shifts x 8*ceil(Cout/8) channels (padded to 16) — the dY tile is stored [h][c8][w][8] with a
+//     +-2 row halo, so the five row shifts are FIVE CONSECUTIVE 8-channel groups of one MN-major operand with a
+//     uniform group stride: a single descriptor, no copies.
+//   * K = 16 consecutive w voxels of one input row.
+// Versus the per-tap kernel this issues 5x fewer, 5x wider MMAs (operand bytes per MAC drop ~2.8x), which is what
+// bounds small-N tcgen05 work (measured: SWIZZLE_NONE operand fetch ~70 B/clk).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "conv_k5.cuh"
+#include "umma.cuh"
+
+namespace msb {
+
+constexpr int kW2TileW = 16, kW2TileH = 8;
+constexpr int kW2GroupBytes = kW2TileH * (kW2TileW + 4) * 16;  // one 8-channel M-group of the X tile (w halo only)
+constexpr int kW2XBytes = 16 * kW2GroupBytes;                  // 128 M rows
+constexpr int kW2RowBytes = kW2TileW * 16;                     // one (h, c8) row of the dY tile
+constexpr int kW2Stages = 3;
+
+struct Wg2Params {
+  int n, cin_real, cout_real, dyp, npad;
+  int d, h, w, tiles_w, tiles_h;
+  int x_c8_total, dy_c8_total;
+  int qm, kd_groups, mhalves, cin_m;
+  int units_per_pass, passes_per_group, num_passes, chunks, tiles_per_chunk, total_tiles;
+  int dy_stage_bytes;
+  float* ws;
+};
+
+__global__ void __launch_bounds__(256, 1)
+    conv_k5_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                          const Wg2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* dy_smem = smem;                                        // [stages][dy_stage_bytes]
+  uint8_t* x_smem = dy_smem + kW2Stages * p.dy_stage_bytes;       // [stages][kW2XBytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(x_smem + kW2Stages * kW2XBytes);
+  // [0,3) full  [3,6) empty  [6] acc_full  [7] acc_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = ptx::smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kW2Stages; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(3 + i), 1); }
+    ptx::mbar_init(BAR(6), 1);
+    ptx::mbar_init(BAR(7), 4);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmap_x); ptx::prefetch_tmap(&tmap_dy); }
+  if (warp == 2) ptx::tmem_alloc<512>(ptx::smem_u32(tmem_slot));
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_items = p.num_passes * p.chunks;
+  const int tiles_per_n = p.d * p.tiles_h * p.tiles_w;
+  auto decode_pass = [&](int pass, int& mh, int& g, int& kw0, int& kw1) {
+    const int pg = pass % p.passes_per_group;
+    g = (pass / p.passes_per_group) % p.kd_groups;
+    mh = pass / (p.passes_per_group * p.kd_groups);
+    kw0 = pg * p.units_per_pass;
+    kw1 = min(5, kw0 + p.units_per_pass);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t use = 0;
+      const int x_planes = p.cin_m / 8;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int pass = item / p.chunks, chunk = item % p.chunks;
+        int mh, g, kw0, kw1;
+        decode_pass(pass, mh, g, kw0, kw1);
+        const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+        const int planes_valid = min(p.qm, 5 - g * p.qm);
+        const uint32_t bytes =
+            (uint32_t)(planes_valid * x_planes * kW2GroupBytes + (kW2TileH + 4) * p.dyp * kW2RowBytes);
+        for (int t = t0; t < t1; ++t, ++use) {
+          const int n = t / tiles_per_n;
+          int r = t % tiles_per_n;
+          const int tw = r % p.tiles_w; r /= p.tiles_w;
+          const int th = r % p.tiles_h; const int d = r / p.tiles_h;
+          const uint32_t s = use % kW2Stages, ph = (use / kW2Stages) & 1;
+          ptx::mbar_wait(BAR(3 + s), ph ^ 1);
+          ptx::mbar_expect_tx(BAR(s), bytes);
+          for (int q = 0; q < planes_valid; ++q)
+            ptx::tma_load_4d(ptx::smem_u32(x_smem + s * kW2XBytes + q * x_planes * kW2GroupBytes), &tmap_x, BAR(s),
+                             (tw * kW2TileW - 2) * 8, th * kW2TileH, d + g * p.qm + q - 2,
+                             n * p.x_c8_total + mh * 16);
+          ptx::tma_load_4d(ptx::smem_u32(dy_smem + s * p.dy_stage_bytes), &tmap_dy, BAR(s), tw * kW2TileW * 8,
+                           n * p.dy_c8_total, th * kW2TileH - 2, d);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(128, p.npad, 1, 1);
+      const uint32_t b_row16 = (uint32_t)(p.dyp * kW2RowBytes) >> 4;  // one h row of the dY tile, 16-byte units
+      uint32_t use = 0, iuse = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
+        const int pass = item / p.chunks, chunk = item % p.chunks;
+        int mh, g, kw0, kw1;
+        decode_pass(pass, mh, g, kw0, kw1);
+        const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+        ptx::mbar_wait(BAR(7), (iuse & 1) ^ 1);
+        ptx::tc_fence_after();
+        for (int t = t0; t < t1; ++t, ++use) {
+          const uint32_t s = use % kW2Stages, ph = (use / kW2Stages) & 1;
+          ptx::mbar_wait(BAR(s), ph);
+          ptx::tc_fence_after();
+          const uint64_t a_desc0 = ptx::make_desc(ptx::smem_u32(x_smem + s * kW2XBytes), 128u, kW2GroupBytes);
+          const uint64_t b_desc0 = ptx::make_desc(ptx::smem_u32(dy_smem + s * p.dy_stage_bytes), 128u, kW2RowBytes);
+#pragma unroll 1
+          for (int u = 0; u < kW2TileH; ++u) {
+            const uint64_t b_desc = b_desc0 + (uint64_t)(u * b_row16);
+            const uint32_t acc = (t != t0 || u != 0) ? 1u : 0u;
+#pragma unroll 1
+            for (int kw = kw0; kw < kw1; ++kw) {
+              const uint64_t a_desc = a_desc0 + (uint64_t)(u * (kW2TileW + 4) + kw);
+              ptx::mma_bf16(tmem_base + (uint32_t)((kw - kw0) * p.npad), a_desc, b_desc, idesc, acc);
+            }
+          }
+          ptx::mma_commit(BAR(3 + s));
+        }
+        ptx::mma_commit(BAR(6));
+      }
+    }
+  } else if (warp >= 4) {
+    const int q4 = warp - 4;
+    const int row = q4 * 32 + lane;
+    const int qplane = row / p.cin_m, ci_local = row % p.cin_m;
+    const int cw = 8 * p.dyp;  // channels per stacked kh group
+    uint32_t iuse = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
+      const int pass = item / p.chunks;
+      int mh, g, kw0, kw1;
+      decode_pass(pass, mh, g, kw0, kw1);
+      const int kd = g * p.qm + qplane;
+      const int ci = mh * 128 + ci_local;
+      const bool row_ok = (qplane < p.qm) && kd < 5 && ci < p.cin_real;
+      ptx::mbar_wait(BAR(6), iuse & 1);
+      ptx::tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
+#pragma unroll 1
+      for (int kw = kw0; kw < kw1; ++kw) {
+#pragma unroll 1
+        for (int cb = 0; cb < p.npad / 16; ++cb) {
+          float acc[16];
+          ptx::tmem_ld16(t_base + (kw - kw0) * p.npad + cb * 16, acc);
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int col = cb * 16 + j;
+              const int jh = col / cw, co = col % cw;
+              if (jh < 5 && co < p.cout_real) {
+                const int tap = kd * 25 + (4 - jh) * 5 + kw;
+                atomicAdd(p.ws + ((int64_t)tap * p.cout_real + co) * p.cin_real + ci, acc[j]);
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(BAR(7));
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin, int n, msb_dim3 dims, float* ws,
+                    cudaStream_t st) {
+  const int dyp = (cout + 7) / 8;
+  const int npad = (40 * dyp + 15) / 16 * 16;
+  if (npad > 256 || dyp > dy.c / 8) return MSB_ERR_UNSUPPORTED;
+  const int64_t S = (int64_t)dims.d * dims.h * dims.w;
+  Wg2Params p;
+  p.n = n; p.cin_real = cin; p.cout_real = cout; p.dyp = dyp; p.npad = npad;
+  p.d = dims.d; p.h = dims.h; p.w = dims.w;
+  p.tiles_w = (dims.w + kW2TileW - 1) / kW2TileW;
+  p.tiles_h = (dims.h + kW2TileH - 1) / kW2TileH;
+  p.x_c8_total = (int)(x.n_stride / (S * 8));
+  p.dy_c8_total = (int)(dy.n_stride / (S * 8));
+  p.cin_m = x.c < 128 ? x.c : 128;
+  p.mhalves = x.c > 128 ? x.c / 128 : 1;
+  p.qm = 128 / p.cin_m;
+  const int qeff = p.qm < 5 ? p.qm : 5;
+  p.kd_groups = (5 + qeff - 1) / qeff;
+  int amax = 512 / npad;
+  if (amax > 5) amax = 5;
+  p.passes_per_group = (5 + amax - 1) / amax;
+  p.units_per_pass = (5 + p.passes_per_group - 1) / p.passes_per_group;
+  p.num_passes = p.mhalves * p.kd_groups * p.passes_per_group;
+  p.total_tiles = n * dims.d * p.tiles_h * p.tiles_w;
+  int chunks = (2 * kNumSMs + p.num_passes - 1) / p.num_passes;
+  if (chunks > p.total_tiles) chunks = p.total_tiles;
+  if (chunks < 1) chunks = 1;
+  p.tiles_per_chunk = (p.total_tiles + chunks - 1) / chunks;
+  p.chunks = (p.total_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+  int dy_rows = (kW2TileH + 4) * dyp;
+  const int need = (kW2TileH - 1) * dyp + npad / 8;  // padded groups of the last K-step read past the halo rows
+  if (need > dy_rows) dy_rows = need;
+  p.dy_stage_bytes = (dy_rows * kW2RowBytes + 1023) / 1024 * 1024;
+  p.ws = ws;
+  const int smem_bytes = kW2Stages * (p.dy_stage_bytes + kW2XBytes) + 1024 + 128;
+  if (smem_bytes > 227 * 1024) return MSB_ERR_UNSUPPORTED;
+  CUtensorMap tmx, tmdy;
+  int rc;
+  if ((rc = make_b8_tmap(&tmx, x, n, dims, kW2TileW + 4, kW2TileH, 1, p.cin_m / 8))) return rc;
+  if ((rc = make_b8_tmap_hmajor(&tmdy, dy, n, dims, kW2TileW, dyp, kW2TileH + 4, 1))) return rc;
+  const int items = p.num_passes * p.chunks;
+  const int grid = items < kNumSMs ? items : kNumSMs;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MSB_CUDA_OK(cudaFuncSetAttribute(conv_k5_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv_k5_wgrad2_kernel<<<grid, 256, smem_bytes, st>>>(tmx, tmdy, p);
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+}  // namespace msb

@@ -171,10 +171,11 @@ def conv_strided():
                   float((sums[:ci] - outt.to_ncdhw().double().sum((0, 2, 3, 4))).abs().max()))
 
 
-def _k5_case(cin, cout, dims, n=2, swap=0, out_c=None, accumulate=False):
+def _k5_case(cin, cout, dims, n=2, swap=0, out_c=None, accumulate=False, ts=0):
     torch, F, ops, B8, _lib = _imports()
     torch.manual_seed(0)
     _lib.call("msb_debug_set", 0, swap)
+    _lib.call("msb_debug_set", 3, ts)
     x = torch.randn(n, cin, *dims, device="cuda")
     w = torch.randn(cout, cin, 5, 5, 5, device="cuda") * (2.0 / (cin * 125)) ** 0.5
     b = torch.randn(cout, device="cuda")
@@ -205,14 +206,18 @@ def k5_fwd_swap0():
 
 
 @check
-def k5_fwd_swap1():
-    print("k5 fwd swapped LBO/SBO", _k5_case(32, 32, (6, 16, 8), swap=1))
+def k5_fwd_ts():
+    for cin, cout, dims in ((32, 32, (6, 16, 8)), (16, 16, (5, 20, 11)), (64, 64, (7, 16, 16)), (128, 128, (5, 16, 8)),
+                            (32, 2, (6, 18, 10)), (32, 32, (9, 7, 13))):
+        oc = 16 if cout == 2 else None
+        print("k5 fwd TS", cin, cout, dims, _k5_case(cin, cout, dims, swap=0, out_c=oc, ts=1))
 
 
-def _k5_wgrad_case(cin, cout, dims, n=2, swap=0, dy_c=None):
+def _k5_wgrad_case(cin, cout, dims, n=2, swap=0, dy_c=None, v1=0):
     torch, F, ops, B8, _lib = _imports()
     torch.manual_seed(0)
     _lib.call("msb_debug_set", 1, swap)
+    _lib.call("msb_debug_set", 2, v1)
     x = torch.randn(n, cin, *dims, device="cuda")
     dyc = dy_c or ((cout + 7) // 8 * 8)
     dy = torch.zeros(n, dyc, *dims, device="cuda")
@@ -237,8 +242,70 @@ def k5_wgrad_swap0():
 
 
 @check
-def k5_wgrad_swap1():
-    print("k5 wgrad swapped", _k5_wgrad_case(32, 32, (6, 16, 16), swap=1))
+def k5_wgrad_v1():
+    for cin, cout, dims in ((32, 32, (6, 16, 16)), (32, 2, (5, 10, 18)), (16, 16, (5, 8, 16))):
+        dyc = 16 if cout == 2 else None
+        print("k5 wgrad v1", cin, cout, dims, _k5_wgrad_case(cin, cout, dims, swap=0, dy_c=dyc, v1=1))
+
+
+@check
+def timing():
+    """device time of the dominant layers at the benchmark shapes (batch 2)"""
+    torch, F, ops, B8, _lib = _imports()
+
+    def timeit(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    n = 2
+    for cin, cout, dims, oc in ((32, 32, (128,) * 3, 32), (32, 2, (128,) * 3, 16), (16, 32, (128,) * 3, 32),
+                                (64, 64, (64,) * 3, 64), (128, 128, (32,) * 3, 128), (256, 256, (16,) * 3, 256),
+                                (256, 256, (8,) * 3, 256)):
+        x = B8(n, cin, dims, torch.bfloat16, device="cuda"); x.buf.normal_()
+        y = B8(n, oc, dims, torch.bfloat16, device="cuda"); y.buf.normal_()
+        w = torch.randn(cout, cin, 5, 5, 5, device="cuda") * 0.02
+        cp = ops.k5_out_pad(oc)
+        packed = torch.empty(ops.k5_packed_bytes(cin, cp), dtype=torch.uint8, device="cuda")
+        ops.k5_pack(w, packed, cout, cin, 0, cin, cp)
+        sums = torch.zeros(2 * oc, dtype=torch.float64, device="cuda")
+        gf = 2 * n * 125 * cin * cout * dims[0] * dims[1] * dims[2] / 1e9
+        res = {}
+        for ts in (0, 1):
+            if ts == 1 and cp > 128:
+                continue
+            _lib.call("msb_debug_set", 3, ts)
+            res["fwd_ts%d" % ts] = timeit(lambda: ops.k5_fwd(x, packed, None, cout, y, False, None, 1, sums))
+        _lib.call("msb_debug_set", 3, 0)
+        dw = torch.zeros(cout, cin, 5, 5, 5, device="cuda")
+        ws = torch.empty(ops.k5_wgrad_workspace_bytes(cin, cout), dtype=torch.uint8, device="cuda")
+        for v1 in (0, 1):
+            _lib.call("msb_debug_set", 2, v1)
+            res["wgrad_v%d" % (2 - v1)] = timeit(lambda: ops.k5_wgrad(x, y, dw, None, cout, cin, ws))
+        _lib.call("msb_debug_set", 2, 0)
+        print("k5 %3d->%3d @%s  %.1f GF/pass: " % (cin, cout, dims[0], gf) +
+              "  ".join("%s %.3f ms (%.0f TF/s)" % (k, v, gf / v) for k, v in res.items()))
+    # down / up convs of the lung config
+    for ci, co, d in ((16, 32, 128), (32, 64, 64), (64, 128, 32), (128, 256, 16)):
+        x = B8(n, ci, (d,) * 3, torch.bfloat16, device="cuda"); x.buf.normal_()
+        y = B8(n, co, (d // 2,) * 3, torch.bfloat16, device="cuda"); y.buf.normal_()
+        w = torch.randn(co, ci, 2, 2, 2, device="cuda") * 0.1
+        dw = torch.zeros_like(w)
+        k = s = (2, 2, 2)
+        t_f = timeit(lambda: ops.conv_strided_fwd(x, w, None, y, k, s, (0, 0, 0), 1, None))
+        t_d = timeit(lambda: ops.conv_strided_bwd_data(y, w, None, x, k, s, (0, 0, 0), False, 1, None))
+        t_w = timeit(lambda: ops.conv_strided_wgrad(x, y, dw, None, k, s, (0, 0, 0), False))
+        print("k2s2 %3d->%3d @%3d: gather %.3f ms  scatter %.3f ms  wgrad %.3f ms" % (ci, co, d, t_f, t_d, t_w))
+    x = torch.rand(n, 1, 128, 128, 128, device="cuda")
+    y = B8(n, 16, (128,) * 3, torch.bfloat16, device="cuda"); y.buf.normal_()
+    w = torch.randn(16, 1, 5, 5, 5, device="cuda")
+    dw = torch.zeros_like(w)
+    print("in_tr fwd %.3f ms  wgrad %.3f ms" % (timeit(lambda: ops.conv_in_fwd(x, w, None, y, 1, None)),
+                                                timeit(lambda: ops.conv_in_wgrad(x, y, dw, None))))
 
 
 @check
