@@ -25,21 +25,29 @@ constexpr int kHaloW = kTileW + 4, kHaloH = kTileH + 4;
 constexpr int kTapsPerStage = 5;
 constexpr int kStagesPerChunk = kNumTaps / kTapsPerStage;
 
-template <int NPAD, int TD, int ACC_SETS = 2, bool TS = false>
+// NPAD: padded output channels; TD: output d-planes per work item; J: d-planes stacked along N in one MMA
+// (N_mma = J * NPAD, TD % J == 0); ACC_SETS: accumulator sets in TMEM (2 = epilogue overlaps the next item).
+template <int NPAD, int TD, int J = 1, int ACC_SETS = 2>
 struct FwdCfg {
   static constexpr int kHaloPlaneBytes = (TD + 4) * kHaloH * kHaloW * 16;  // one c8 plane of the haloed tile
   static constexpr int kHaloBytes = 2 * kHaloPlaneBytes;                   // 16 input channels
-  static constexpr int kWTapBytes = 16 * NPAD * 2;                         // one tap, 16 ci x NPAD co bf16
-  static constexpr int kWStageBytes = kTapsPerStage * kWTapBytes;
+  // one weight stage = one (kh, kw) column: [k8 (2)][block (NB)][co (NPAD)][8 ci]; blocks hold the 5 kd taps in
+  // REVERSED order (W4..W0) between J-1 zero blocks on each side, so the operand for stacked planes j = 0..J-1 and
+  // input plane kd' is the same image viewed from block J+3-kd' (zero blocks = taps outside the 5-wide kernel).
+  static constexpr int kNB = 5 + 2 * (J - 1);
+  static constexpr int kBlockBytes = NPAD * 16;
+  static constexpr int kWK8Bytes = kNB * kBlockBytes;
+  static constexpr int kWStageBytes = 2 * kWK8Bytes;
+  static constexpr int kWLoadBytes = 5 * kBlockBytes;                      // bytes TMA writes per (stage, k8)
   static constexpr int kWStages = (NPAD >= 256) ? 3 : 4;
   static constexpr int kAccCols = TD * NPAD;
-  static constexpr int kASlots = 4;                       // TS mode: K16 activation windows staged in TMEM (8 cols each)
-  static constexpr int kAColBase = ACC_SETS * kAccCols;
-  static constexpr int kColsNeeded = ACC_SETS * kAccCols + (TS ? kASlots * 8 : 0);
+  static constexpr int kNMma = J * NPAD;
+  static constexpr int kColsNeeded = ACC_SETS * kAccCols;
   static constexpr int kTmemCols = (kColsNeeded <= 32) ? 32 : (kColsNeeded <= 64) ? 64 : (kColsNeeded <= 128) ? 128
                                  : (kColsNeeded <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = 2 * kHaloBytes + kWStages * kWStageBytes + 1024 /*barriers + stats*/ +
                                     4 * 2 * NPAD * 4 + 128 /*alignment slack*/;
+  static_assert(TD % J == 0 && kNMma <= 256, "bad plane stacking");
   static_assert(kColsNeeded <= 512, "TMEM overflow");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory overflow");
 };
@@ -88,10 +96,10 @@ __device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
   return r;
 }
 
-template <int NPAD, int TD, int ACC_SETS, bool TS>
+template <int NPAD, int TD, int J, int ACC_SETS>
 __global__ void __launch_bounds__(256, 1)
     conv_k5_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const FwdParams p) {
-  using Cfg = FwdCfg<NPAD, TD, ACC_SETS, TS>;
+  using Cfg = FwdCfg<NPAD, TD, J, ACC_SETS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* halo_smem = smem;                                   // [2][kHaloBytes]
@@ -112,6 +120,11 @@ __global__ void __launch_bounds__(256, 1)
     ptx::fence_mbar_init();
   }
   for (int i = threadIdx.x; i < 4 * 2 * NPAD; i += 256) stat_smem[i] = 0.f;
+  if (J > 1) {  // zero blocks of the weight stages are never written by TMA
+    uint4* wz = reinterpret_cast<uint4*>(w_smem);
+    for (int i = threadIdx.x; i < Cfg::kWStages * Cfg::kWStageBytes / 16; i += 256) wz[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros visible to the MMA (async proxy)
+  }
   if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tmap_x);
   if (warp == 2) ptx::tmem_alloc<Cfg::kTmemCols>(ptx::smem_u32(tmem_slot));
   ptx::tc_fence_before();
@@ -147,13 +160,17 @@ __global__ void __launch_bounds__(256, 1)
       uint32_t use = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         for (int ck = 0; ck < chunks; ++ck) {
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.packed) + (size_t)ck * kNumTaps * Cfg::kWTapBytes;
+          const uint8_t* src =
+              reinterpret_cast<const uint8_t*>(p.packed) + (size_t)ck * kStagesPerChunk * 2 * Cfg::kWLoadBytes;
           for (int st = 0; st < kStagesPerChunk; ++st, ++use) {
             const uint32_t s = use % Cfg::kWStages, ph = (use / Cfg::kWStages) & 1;
             ptx::mbar_wait(BAR(8 + s), ph ^ 1);
-            ptx::mbar_expect_tx(BAR(4 + s), Cfg::kWStageBytes);
-            ptx::bulk_load(ptx::smem_u32(w_smem + s * Cfg::kWStageBytes), src + (size_t)st * Cfg::kWStageBytes,
-                           Cfg::kWStageBytes, BAR(4 + s));
+            ptx::mbar_expect_tx(BAR(4 + s), 2 * Cfg::kWLoadBytes);
+#pragma unroll
+            for (int k8 = 0; k8 < 2; ++k8)
+              ptx::bulk_load(ptx::smem_u32(w_smem + s * Cfg::kWStageBytes + k8 * Cfg::kWK8Bytes +
+                                           (J - 1) * Cfg::kBlockBytes),
+                             src + (size_t)(st * 2 + k8) * Cfg::kWLoadBytes, Cfg::kWLoadBytes, BAR(4 + s));
           }
         }
       }
@@ -161,12 +178,10 @@ __global__ void __launch_bounds__(256, 1)
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, NPAD, 0, 0);
-      const uint32_t a_lbo = p.dbg_swap ? (uint32_t)(kHaloW * 16) : (uint32_t)Cfg::kHaloPlaneBytes;
-      const uint32_t a_sbo = p.dbg_swap ? (uint32_t)Cfg::kHaloPlaneBytes : (uint32_t)(kHaloW * 16);
-      const uint32_t b_lbo = p.dbg_swap ? 128u : (uint32_t)(NPAD * 16);
-      const uint32_t b_sbo = p.dbg_swap ? (uint32_t)(NPAD * 16) : 128u;
-      uint32_t huse = 0, wuse = 0, iuse = 0, ause = 0;
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, Cfg::kNMma, 0, 0);
+      const uint32_t a_lbo = (uint32_t)Cfg::kHaloPlaneBytes, a_sbo = (uint32_t)(kHaloW * 16);
+      const uint32_t b_lbo = (uint32_t)Cfg::kWK8Bytes, b_sbo = 128u;
+      uint32_t huse = 0, wuse = 0, iuse = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
         const uint32_t as = iuse % ACC_SETS, aph = (iuse / ACC_SETS) & 1;
         ptx::mbar_wait(BAR(14 + as), aph ^ 1);
@@ -177,38 +192,19 @@ __global__ void __launch_bounds__(256, 1)
           ptx::mbar_wait(BAR(0 + hb), hph);
           const uint32_t halo_addr = ptx::smem_u32(halo_smem + hb * Cfg::kHaloBytes);
           const uint64_t a_desc0 = ptx::make_desc(halo_addr, a_lbo, a_sbo);
-          // weight stage st holds the 5 kd taps of one (kh, kw) column (packed kd-minor)
-          for (int st = 0; st < kStagesPerChunk; ++st, ++wuse) {
+          for (int st = 0; st < kStagesPerChunk; ++st, ++wuse) {  // st = kh*5 + kw
             const uint32_t s = wuse % Cfg::kWStages, wph = (wuse / Cfg::kWStages) & 1;
             ptx::mbar_wait(BAR(4 + s), wph);
             ptx::tc_fence_after();
             const uint64_t b_desc0 = ptx::make_desc(ptx::smem_u32(w_smem + s * Cfg::kWStageBytes), b_lbo, b_sbo);
-            const int kh = st / 5, kw = st % 5;
-            const uint32_t hw_off = (uint32_t)(kh * kHaloW + kw);  // 16-byte units
-            if constexpr (!TS) {
+            const uint32_t hw_off = (uint32_t)((st / 5) * kHaloW + (st % 5));  // 16-byte units
 #pragma unroll
-              for (int kd = 0; kd < 5; ++kd) {
-                const uint64_t b_desc = b_desc0 + (uint64_t)((kd * Cfg::kWTapBytes) >> 4);
+            for (int g = 0; g < TD / J; ++g) {
 #pragma unroll
-                for (int td = 0; td < TD; ++td) {
-                  const uint64_t a_desc = a_desc0 + (uint64_t)(hw_off + (td + kd) * kHaloH * kHaloW);
-                  ptx::mma_bf16(d_base + td * NPAD, a_desc, b_desc, idesc, (ck | st | kd) != 0 ? 1u : 0u);
-                }
-              }
-            } else {
-              // each haloed d-plane window is copied smem -> TMEM once and feeds every (td, kd) with td + kd = plane
-#pragma unroll
-              for (int pl = 0; pl < TD + 4; ++pl, ++ause) {
-                const uint32_t a_tmem = tmem_base + Cfg::kAColBase + (ause % Cfg::kASlots) * 8;
-                ptx::tmem_cp_128x256b(a_tmem, a_desc0 + (uint64_t)(hw_off + pl * kHaloH * kHaloW));
-#pragma unroll
-                for (int kd = 0; kd < 5; ++kd) {
-                  const int td = pl - kd;
-                  if (td >= 0 && td < TD) {
-                    const uint64_t b_desc = b_desc0 + (uint64_t)((kd * Cfg::kWTapBytes) >> 4);
-                    ptx::mma_bf16_ts(d_base + td * NPAD, a_tmem, b_desc, idesc, (ck | st | kd) != 0 ? 1u : 0u);
-                  }
-                }
+              for (int kdp = 0; kdp < J + 4; ++kdp) {  // input plane g*J + kdp feeds output planes g*J + j, tap kd = kdp - j
+                const uint64_t a_desc = a_desc0 + (uint64_t)(hw_off + (g * J + kdp) * kHaloH * kHaloW);
+                const uint64_t b_desc = b_desc0 + (uint64_t)(((J + 3 - kdp) * Cfg::kBlockBytes) >> 4);
+                ptx::mma_bf16(d_base + g * Cfg::kNMma, a_desc, b_desc, idesc, (ck | st | kdp) != 0 ? 1u : 0u);
               }
             }
             ptx::mma_commit(BAR(8 + s));  // weight stage free once these MMAs retire
@@ -544,7 +540,7 @@ __global__ void __launch_bounds__(256) channel_sum_bf16_kernel(msb_tensor x, int
 }
 
 // ---- weight packing ----------------------------------------------------------------------------------
-// packed[chunk][tap][k8][oc][j] (bf16), rc = chunk*16 + k8*8 + j
+// packed[chunk][hk = kh*5+kw][k8][kdr = 4-kd][oc][j] (bf16), rc = chunk*16 + k8*8 + j
 __global__ void __launch_bounds__(256) pack_k5_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed,
                                                       int cout, int cin, int mode, int cin_pad, int cout_pad) {
   const int64_t total = (int64_t)cin_pad * kNumTaps * cout_pad;
@@ -552,10 +548,11 @@ __global__ void __launch_bounds__(256) pack_k5_kernel(const float* __restrict__ 
     const int j = (int)(i & 7);
     int64_t r = i >> 3;
     const int oc = (int)(r % cout_pad); r /= cout_pad;
+    const int kdr = (int)(r % 5); r /= 5;
     const int k8 = (int)(r & 1); r >>= 1;
-    const int tslot = (int)(r % kNumTaps);            // packed order: (kh, kw) column major, kd minor
-    const int tap = (tslot % 5) * 25 + tslot / 5;     // natural tap index kd*25 + kh*5 + kw
-    const int chunk = (int)(r / kNumTaps);
+    const int hk = (int)(r % 25);
+    const int chunk = (int)(r / 25);
+    const int tap = (4 - kdr) * 25 + hk;  // natural tap index kd*25 + kh*5 + kw
     const int rc = chunk * 16 + k8 * 8 + j;
     float v = 0.f;
     if (mode == 0) {
@@ -645,9 +642,9 @@ int make_b8_tmap_hmajor(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 d
 
 int g_debug_flags[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
-template <int NPAD, int TD, int ACC_SETS = 2, bool TS = false>
+template <int NPAD, int TD, int J = 1, int ACC_SETS = 2>
 static int launch_fwd(const msb_tensor& x, msb_dim3 dims, FwdParams& p, cudaStream_t st) {
-  using Cfg = FwdCfg<NPAD, TD, ACC_SETS, TS>;
+  using Cfg = FwdCfg<NPAD, TD, J, ACC_SETS>;
   CUtensorMap tmap;
   int rc = make_b8_tmap(&tmap, x, p.n, dims, kHaloW, kHaloH, TD + 4, 2);
   if (rc) return rc;
@@ -656,11 +653,11 @@ static int launch_fwd(const msb_tensor& x, msb_dim3 dims, FwdParams& p, cudaStre
   const int grid = items < kNumSMs ? items : kNumSMs;
   static bool attr_set = false;
   if (!attr_set) {
-    MSB_CUDA_OK(cudaFuncSetAttribute(conv_k5_fwd_kernel<NPAD, TD, ACC_SETS, TS>,
+    MSB_CUDA_OK(cudaFuncSetAttribute(conv_k5_fwd_kernel<NPAD, TD, J, ACC_SETS>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  conv_k5_fwd_kernel<NPAD, TD, ACC_SETS, TS><<<grid, 256, Cfg::kSmemBytes, st>>>(tmap, p);
+  conv_k5_fwd_kernel<NPAD, TD, J, ACC_SETS><<<grid, 256, Cfg::kSmemBytes, st>>>(tmap, p);
   MSB_LAUNCH_OK();
   return MSB_OK;
 }
@@ -743,16 +740,18 @@ int msb_conv_k5_fwd(msb_tensor x, const void* packed, const float* bias, int cou
   p.tiles_h = (dims.h + kTileH - 1) / kTileH;
   p.x_c8_total = (int)(x.n_stride / (S * 8));
   p.packed = packed; p.bias = bias; p.out = out; p.accumulate = accumulate; p.ch_scale = ch_scale;
-  p.groups = groups; p.sums = sums; p.sums_c = out.c; p.dbg_swap = g_debug_flags[0];
+  p.groups = groups; p.sums = sums; p.sums_c = out.c; p.dbg_swap = 0;
   cudaStream_t st = as_stream(stream);
   const int npad_sel = msb_conv_k5_out_pad(out.c);
   // NOTE: the packed operand must have been built with cout_pad == npad_sel.
-  const bool ts = g_debug_flags[3] != 0;  // A operand staged through TMEM (tcgen05.cp) and reused along d
+  // plane stacking along N (debug flag 3 = 1 disables it): narrow outputs are bound by the A-operand fetch, so one
+  // MMA produces J output planes from one activation window (see FwdCfg)
+  const bool stack = g_debug_flags[3] == 0;
   switch (npad_sel) {
-    case 16: return ts ? launch_fwd<16, 4, 2, true>(x, dims, p, st) : launch_fwd<16, 4>(x, dims, p, st);
-    case 32: return ts ? launch_fwd<32, 4, 2, true>(x, dims, p, st) : launch_fwd<32, 4>(x, dims, p, st);
-    case 64: return ts ? launch_fwd<64, 3, 2, true>(x, dims, p, st) : launch_fwd<64, 4>(x, dims, p, st);
-    case 128: return ts ? launch_fwd<128, 3, 1, true>(x, dims, p, st) : launch_fwd<128, 2>(x, dims, p, st);
+    case 16: return stack ? launch_fwd<16, 4, 4>(x, dims, p, st) : launch_fwd<16, 4>(x, dims, p, st);
+    case 32: return stack ? launch_fwd<32, 4, 4>(x, dims, p, st) : launch_fwd<32, 4>(x, dims, p, st);
+    case 64: return stack ? launch_fwd<64, 4, 2>(x, dims, p, st) : launch_fwd<64, 4>(x, dims, p, st);
+    case 128: return launch_fwd<128, 2>(x, dims, p, st);
     default: return launch_fwd<256, 1>(x, dims, p, st);
   }
 }

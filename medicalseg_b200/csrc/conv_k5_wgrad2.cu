@@ -24,6 +24,7 @@ constexpr int kW2Stages = 3;
 
 struct Wg2Params {
   int n, cin_real, cout_real, dyp, npad;
+  int jh, jgroups;                       // kh shifts stacked per MMA, number of kh groups
   int d, h, w, tiles_w, tiles_h;
   int x_c8_total, dy_c8_total;
   int qm, kd_groups, mhalves, cin_m;
@@ -60,10 +61,12 @@ __global__ void __launch_bounds__(256, 1)
 
   const int num_items = p.num_passes * p.chunks;
   const int tiles_per_n = p.d * p.tiles_h * p.tiles_w;
-  auto decode_pass = [&](int pass, int& mh, int& g, int& kw0, int& kw1) {
+  auto decode_pass = [&](int pass, int& mh, int& g, int& jg, int& kw0, int& kw1) {
     const int pg = pass % p.passes_per_group;
-    g = (pass / p.passes_per_group) % p.kd_groups;
-    mh = pass / (p.passes_per_group * p.kd_groups);
+    int r = pass / p.passes_per_group;
+    jg = r % p.jgroups; r /= p.jgroups;
+    g = r % p.kd_groups;
+    mh = r / p.kd_groups;
     kw0 = pg * p.units_per_pass;
     kw1 = min(5, kw0 + p.units_per_pass);
   };
@@ -74,8 +77,8 @@ __global__ void __launch_bounds__(256, 1)
       const int x_planes = p.cin_m / 8;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int pass = item / p.chunks, chunk = item % p.chunks;
-        int mh, g, kw0, kw1;
-        decode_pass(pass, mh, g, kw0, kw1);
+        int mh, g, jg, kw0, kw1;
+        decode_pass(pass, mh, g, jg, kw0, kw1);
         const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
         const int planes_valid = min(p.qm, 5 - g * p.qm);
         const uint32_t bytes =
@@ -104,8 +107,8 @@ __global__ void __launch_bounds__(256, 1)
       uint32_t use = 0, iuse = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
         const int pass = item / p.chunks, chunk = item % p.chunks;
-        int mh, g, kw0, kw1;
-        decode_pass(pass, mh, g, kw0, kw1);
+        int mh, g, jg, kw0, kw1;
+        decode_pass(pass, mh, g, jg, kw0, kw1);
         const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
         ptx::mbar_wait(BAR(7), (iuse & 1) ^ 1);
         ptx::tc_fence_after();
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(256, 1)
           const uint64_t b_desc0 = ptx::make_desc(ptx::smem_u32(dy_smem + s * p.dy_stage_bytes), 128u, kW2RowBytes);
 #pragma unroll 1
           for (int u = 0; u < kW2TileH; ++u) {
-            const uint64_t b_desc = b_desc0 + (uint64_t)(u * b_row16);
+            const uint64_t b_desc = b_desc0 + (uint64_t)((u + jg * p.jh) * b_row16);
             const uint32_t acc = (t != t0 || u != 0) ? 1u : 0u;
 #pragma unroll 1
             for (int kw = kw0; kw < kw1; ++kw) {
@@ -138,8 +141,8 @@ __global__ void __launch_bounds__(256, 1)
     uint32_t iuse = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
       const int pass = item / p.chunks;
-      int mh, g, kw0, kw1;
-      decode_pass(pass, mh, g, kw0, kw1);
+      int mh, g, jg, kw0, kw1;
+      decode_pass(pass, mh, g, jg, kw0, kw1);
       const int kd = g * p.qm + qplane;
       const int ci = mh * 128 + ci_local;
       const bool row_ok = (qplane < p.qm) && kd < 5 && ci < p.cin_real;
@@ -156,8 +159,9 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int col = cb * 16 + j;
-              const int jh = col / cw, co = col % cw;
-              if (jh < 5 && co < p.cout_real) {
+              const int jj = col / cw, co = col % cw;
+              const int jh = jg * p.jh + jj;  // dY row shift: v_h = u_h - 2 + jh  <=>  kh = 4 - jh
+              if (jj < p.jh && jh < 5 && co < p.cout_real) {
                 const int tap = kd * 25 + (4 - jh) * 5 + kw;
                 atomicAdd(p.ws + ((int64_t)tap * p.cout_real + co) * p.cin_real + ci, acc[j]);
               }
@@ -181,11 +185,17 @@ __global__ void __launch_bounds__(256, 1)
 int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin, int n, msb_dim3 dims, float* ws,
                     cudaStream_t st) {
   const int dyp = (cout + 7) / 8;
-  const int npad = (40 * dyp + 15) / 16 * 16;
-  if (npad > 256 || dyp > dy.c / 8) return MSB_ERR_UNSUPPORTED;
+  if (dyp > dy.c / 8 || dyp > 10) return MSB_ERR_UNSUPPORTED;  // wider outputs: per-tap kernel (N = Cout already wide)
+  // stack as many kh shifts per MMA as fit N <= 256, preferring the split of 5 with the least waste
+  int jh = 256 / (8 * dyp);
+  if (jh >= 5) jh = 5;
+  else if (jh == 4) jh = 3;  // 3+2(+1 wasted) beats 4+1(+3 wasted)
+  const int jgroups = (5 + jh - 1) / jh;
+  const int npad = (jh * 8 * dyp + 15) / 16 * 16;
   const int64_t S = (int64_t)dims.d * dims.h * dims.w;
   Wg2Params p;
   p.n = n; p.cin_real = cin; p.cout_real = cout; p.dyp = dyp; p.npad = npad;
+  p.jh = jh; p.jgroups = jgroups;
   p.d = dims.d; p.h = dims.h; p.w = dims.w;
   p.tiles_w = (dims.w + kW2TileW - 1) / kW2TileW;
   p.tiles_h = (dims.h + kW2TileH - 1) / kW2TileH;
@@ -200,7 +210,7 @@ int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin
   if (amax > 5) amax = 5;
   p.passes_per_group = (5 + amax - 1) / amax;
   p.units_per_pass = (5 + p.passes_per_group - 1) / p.passes_per_group;
-  p.num_passes = p.mhalves * p.kd_groups * p.passes_per_group;
+  p.num_passes = p.mhalves * p.kd_groups * p.jgroups * p.passes_per_group;
   p.total_tiles = n * dims.d * p.tiles_h * p.tiles_w;
   int chunks = (2 * kNumSMs + p.num_passes - 1) / p.num_passes;
   if (chunks > p.total_tiles) chunks = p.total_tiles;
@@ -208,7 +218,7 @@ int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin
   p.tiles_per_chunk = (p.total_tiles + chunks - 1) / chunks;
   p.chunks = (p.total_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
   int dy_rows = (kW2TileH + 4) * dyp;
-  const int need = (kW2TileH - 1) * dyp + npad / 8;  // padded groups of the last K-step read past the halo rows
+  const int need = (kW2TileH - 1 + (jgroups - 1) * jh) * dyp + npad / 8;  // groups read past the halo rows
   if (need > dy_rows) dy_rows = need;
   p.dy_stage_bytes = (dy_rows * kW2RowBytes + 1023) / 1024 * 1024;
   p.ws = ws;

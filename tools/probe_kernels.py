@@ -210,7 +210,7 @@ def k5_fwd_ts():
     for cin, cout, dims in ((32, 32, (6, 16, 8)), (16, 16, (5, 20, 11)), (64, 64, (7, 16, 16)), (128, 128, (5, 16, 8)),
                             (32, 2, (6, 18, 10)), (32, 32, (9, 7, 13))):
         oc = 16 if cout == 2 else None
-        print("k5 fwd TS", cin, cout, dims, _k5_case(cin, cout, dims, swap=0, out_c=oc, ts=1))
+        print("k5 fwd unstacked", cin, cout, dims, _k5_case(cin, cout, dims, swap=0, out_c=oc, ts=1))
 
 
 def _k5_wgrad_case(cin, cout, dims, n=2, swap=0, dy_c=None, v1=0):
@@ -276,10 +276,10 @@ def timing():
         gf = 2 * n * 125 * cin * cout * dims[0] * dims[1] * dims[2] / 1e9
         res = {}
         for ts in (0, 1):
-            if ts == 1 and cp > 128:
+            if ts == 1 and cp > 64:
                 continue
             _lib.call("msb_debug_set", 3, ts)
-            res["fwd_ts%d" % ts] = timeit(lambda: ops.k5_fwd(x, packed, None, cout, y, False, None, 1, sums))
+            res["fwd_stacked" if ts == 0 else "fwd_plain"] = timeit(lambda: ops.k5_fwd(x, packed, None, cout, y, False, None, 1, sums))
         _lib.call("msb_debug_set", 3, 0)
         dw = torch.zeros(cout, cin, 5, 5, 5, device="cuda")
         ws = torch.empty(ops.k5_wgrad_workspace_bytes(cin, cout), dtype=torch.uint8, device="cuda")
