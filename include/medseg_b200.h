@@ -122,6 +122,13 @@ int msb_conv_strided_wgrad(msb_tensor big, msb_tensor small, float* dw, float* d
                            msb_dim3 big_dims, msb_dim3 kernel, msb_dim3 stride, msb_dim3 pad, int c_big_real,
                            int c_small_real, int bias_from_big, void* stream);
 
+/* tensor-core weight gradient for the non-overlapping kernel = stride = (2,2,2) case (bf16 views, even extents):
+ * space-to-depth of `big` + a pointwise tcgen05 weight-gradient GEMM.  Same result layout as
+ * msb_conv_strided_wgrad.  workspace: msb_conv_k2s2_wgrad_workspace_bytes(...) bytes of device scratch. */
+size_t msb_conv_k2s2_wgrad_workspace_bytes(int n, int c_big, int c_small, msb_dim3 big_dims);
+int msb_conv_k2s2_wgrad(msb_tensor big, msb_tensor small, float* dw, float* dbias, int n, msb_dim3 big_dims,
+                        int bias_from_big, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- 5x5x5 Conv3D (pad 2, stride 1) on tcgen05 tensor cores ----------------------------------------
  * vnet.py:36 (LUConv.conv1, 14x), :165-166 (out_tr.conv1).  bf16 operands, f32 accumulation in TMEM.     */
 /* packs the Paddle-layout f32 weight [Cout][Cin][125] into the bf16 UMMA operand image.

@@ -66,6 +66,7 @@ struct FwdParams {
   double* sums;
   int sums_c;                            // channel count of the sums array
   int dbg_swap;
+  int nsplit;                            // output-channel slices per tile (fills the SMs on small volumes)
 };
 
 // 16 per-lane values -> per-channel totals over the warp; lane L ends up with the total of channel L>>1.
@@ -134,15 +135,17 @@ __global__ void __launch_bounds__(256, 1)
 
   const int chunks = p.cin_pad / 16;
   const int items_per_n = p.dblocks * p.tiles_h * p.tiles_w;
-  const int num_items = p.n * items_per_n;
+  const int num_items = p.n * items_per_n * p.nsplit;  // item = tile * nsplit + channel slice
+  const int n_slice = Cfg::kNMma / p.nsplit;           // MMA N per item
 
   if (warp == 0) {
     // ================= halo TMA producer =================
     if (lane == 0) {
       uint32_t use = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int n = item / items_per_n;
-        int r = item % items_per_n;
+        const int tile = item / p.nsplit;
+        const int n = tile / items_per_n;
+        int r = tile % items_per_n;
         const int tw = r % p.tiles_w; r /= p.tiles_w;
         const int th = r % p.tiles_h; const int db = r / p.tiles_h;
         for (int ck = 0; ck < chunks; ++ck, ++use) {
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(256, 1)
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, Cfg::kNMma, 0, 0);
+      const uint32_t idesc = ptx::make_idesc_bf16(128, n_slice, 0, 0);
       const uint32_t a_lbo = (uint32_t)Cfg::kHaloPlaneBytes, a_sbo = (uint32_t)(kHaloW * 16);
       const uint32_t b_lbo = (uint32_t)Cfg::kWK8Bytes, b_sbo = 128u;
       uint32_t huse = 0, wuse = 0, iuse = 0;
@@ -187,6 +190,7 @@ __global__ void __launch_bounds__(256, 1)
         ptx::mbar_wait(BAR(14 + as), aph ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_base = tmem_base + as * Cfg::kAccCols;
+        const uint32_t b_slice = (uint32_t)((item % p.nsplit) * n_slice);  // first weight row (16 B each) of this slice
         for (int ck = 0; ck < chunks; ++ck, ++huse) {
           const uint32_t hb = huse & 1, hph = (huse >> 1) & 1;
           ptx::mbar_wait(BAR(0 + hb), hph);
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll
               for (int kdp = 0; kdp < J + 4; ++kdp) {  // input plane g*J + kdp feeds output planes g*J + j, tap kd = kdp - j
                 const uint64_t a_desc = a_desc0 + (uint64_t)(hw_off + (g * J + kdp) * kHaloH * kHaloW);
-                const uint64_t b_desc = b_desc0 + (uint64_t)(((J + 3 - kdp) * Cfg::kBlockBytes) >> 4);
+                const uint64_t b_desc = b_desc0 + (uint64_t)((((J + 3 - kdp) * Cfg::kBlockBytes) >> 4) + b_slice);
                 ptx::mma_bf16(d_base + g * Cfg::kNMma, a_desc, b_desc, idesc, (ck | st | kdp) != 0 ? 1u : 0u);
               }
             }
@@ -223,8 +227,10 @@ __global__ void __launch_bounds__(256, 1)
     float* my_stats = stat_smem + q * 2 * NPAD;
     uint32_t iuse = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
-      const int n = item / items_per_n;
-      int r = item % items_per_n;
+      const int tile = item / p.nsplit;
+      const int c_first = (item % p.nsplit) * n_slice;  // first output channel of this slice (nsplit > 1 only with J == 1)
+      const int n = tile / items_per_n;
+      int r = tile % items_per_n;
       const int tw = r % p.tiles_w; r /= p.tiles_w;
       const int th = r % p.tiles_h; const int db = r / p.tiles_h;
       const int h = th * kTileH + hh, w = tw * kTileW + ww;
@@ -239,13 +245,13 @@ __global__ void __launch_bounds__(256, 1)
         const bool ok = inb && d < p.d;
         const int64_t v = ((int64_t)d * p.h + h) * p.w + w;
 #pragma unroll 1
-        for (int cb = 0; cb < NPAD / 16; ++cb) {
+        for (int cb = 0; cb < (NPAD / p.nsplit) / 16; ++cb) {
           float acc[16];
           ptx::tmem_ld16(t_base + td * NPAD + cb * 16, acc);
           float sq[16];
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
-            const int c8 = cb * 2 + k;
+            const int c8 = (c_first >> 3) + cb * 2 + k;
             float o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -280,8 +286,8 @@ __global__ void __launch_bounds__(256, 1)
             const float s1 = warp_reduce16(acc, lane);
             const float s2 = warp_reduce16(sq, lane);
             if ((lane & 1) == 0) {
-              my_stats[cb * 16 + (lane >> 1)] += s1;
-              my_stats[NPAD + cb * 16 + (lane >> 1)] += s2;
+              my_stats[c_first + cb * 16 + (lane >> 1)] += s1;
+              my_stats[NPAD + c_first + cb * 16 + (lane >> 1)] += s2;
             }
           }
         }
@@ -348,6 +354,7 @@ struct WgParams {
   int num_passes, chunks, tiles_per_chunk, total_tiles;
   float* ws;                            // [125][cout_real][cin_real] f32
   int dbg_swap;
+  int pad, units_total;                 // 2 / 25 for the 5x5x5 conv; 0 / 1 for the pointwise (1x1x1) weight gradient
 };
 
 template <int NPAD, int TH>
@@ -386,7 +393,7 @@ __global__ void __launch_bounds__(256, 1)
     g = (pass / p.passes_per_group) % p.kd_groups;
     mh = pass / (p.passes_per_group * p.kd_groups);
     u0 = pg * p.units_per_pass;
-    u1 = min(25, u0 + p.units_per_pass);
+    u1 = min(p.units_total, u0 + p.units_per_pass);
   };
 
   if (warp == 0) {
@@ -410,7 +417,7 @@ __global__ void __launch_bounds__(256, 1)
           ptx::mbar_expect_tx(BAR(b), bytes);
           for (int q = 0; q < planes_valid; ++q)
             ptx::tma_load_4d(ptx::smem_u32(x_smem + b * Cfg::kXBytes + q * x_planes * Cfg::kGroupBytes), &tmap_x, BAR(b),
-                             (tw * kWgTileW - 2) * 8, th * TH - 2, d + g * p.qm + q - 2,
+                             (tw * kWgTileW - p.pad) * 8, th * TH - p.pad, d + g * p.qm + q - p.pad,
                              n * p.x_c8_total + mh * 16);
           ptx::tma_load_4d(ptx::smem_u32(dy_smem + b * Cfg::kDyBytes), &tmap_dy, BAR(b), tw * kWgTileW * 8, th * TH, d,
                            n * p.dy_c8_total);
@@ -539,6 +546,38 @@ __global__ void __launch_bounds__(256) channel_sum_bf16_kernel(msb_tensor x, int
   }
 }
 
+// ---- 2x2x2 / stride-2 weight gradients on the tensor cores ---------------------------------------------
+// space-to-depth: xs[n][tap*C8 + c8][o][8] = x[n][c8][2o + tap][8]  (tap = kd*4 + kh*2 + kw), so that
+// dW[sc][bc][tap] = sum_o big[2o+tap][bc] * small[o][sc] becomes a pointwise (1x1x1) weight gradient.
+__global__ void __launch_bounds__(256) s2d_k2_kernel(msb_tensor x, __nv_bfloat16* __restrict__ xs, int c8n, int sd,
+                                                     int sh, int sw) {
+  const int plane = blockIdx.y, n = blockIdx.z;  // plane = tap * c8n + c8
+  const int tap = plane / c8n, c8 = plane % c8n;
+  const int kd = tap >> 2, kh = (tap >> 1) & 1, kw = tap & 1;
+  const int64_t ss = (int64_t)sd * sh * sw;
+  const int bh = sh * 2, bw = sw * 2;
+  const int64_t sb = (int64_t)sd * 2 * bh * bw;
+  const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(x.ptr) + (int64_t)n * x.n_stride + (int64_t)c8 * sb * 8;
+  __nv_bfloat16* dst = xs + (((int64_t)n * 8 * c8n + plane) * ss) * 8;
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < ss; o += (int64_t)gridDim.x * blockDim.x) {
+    const int ow = (int)(o % sw), oh = (int)((o / sw) % sh), od = (int)(o / ((int64_t)sw * sh));
+    const int64_t vb = ((int64_t)(od * 2 + kd) * bh + (oh * 2 + kh)) * bw + (ow * 2 + kw);
+    *reinterpret_cast<uint4*>(dst + o * 8) = __ldg(reinterpret_cast<const uint4*>(src + vb * 8));
+  }
+}
+
+// dw[sc][bc][tap] += ws[sc][tap*cbig + bc]
+__global__ void __launch_bounds__(256) k2s2_unpack_kernel(const float* __restrict__ ws, float* __restrict__ dw,
+                                                          int csmall, int cbig) {
+  const int64_t total = (int64_t)csmall * cbig * 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i & 7);
+    const int64_t r = i >> 3;
+    const int bc = (int)(r % cbig), sc = (int)(r / cbig);
+    dw[i] += ws[((int64_t)sc * 8 + tap) * cbig + bc];
+  }
+}
+
 // ---- weight packing ----------------------------------------------------------------------------------
 // packed[chunk][hk = kh*5+kw][k8][kdr = 4-kd][oc][j] (bf16), rc = chunk*16 + k8*8 + j
 __global__ void __launch_bounds__(256) pack_k5_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed,
@@ -649,7 +688,13 @@ static int launch_fwd(const msb_tensor& x, msb_dim3 dims, FwdParams& p, cudaStre
   int rc = make_b8_tmap(&tmap, x, p.n, dims, kHaloW, kHaloH, TD + 4, 2);
   if (rc) return rc;
   p.dblocks = (p.d + TD - 1) / TD;
-  const int items = p.n * p.dblocks * p.tiles_h * p.tiles_w;
+  const int tiles = p.n * p.dblocks * p.tiles_h * p.tiles_w;
+  p.nsplit = 1;
+  if (J == 1 && g_debug_flags[4] == 0)  // small volumes: slice the output channels so that every SM gets work
+    while (p.nsplit < 4 && tiles * p.nsplit * 2 <= kNumSMs && (NPAD / (p.nsplit * 2)) % 16 == 0 &&
+           NPAD / (p.nsplit * 2) >= 32)
+      p.nsplit *= 2;
+  const int items = tiles * p.nsplit;
   const int grid = items < kNumSMs ? items : kNumSMs;
   static bool attr_set = false;
   if (!attr_set) {
@@ -670,9 +715,10 @@ static int launch_wgrad(const msb_tensor& x, const msb_tensor& dy, WgParams& p, 
   p.tiles_w = (dims.w + kWgTileW - 1) / kWgTileW;
   p.tiles_h = (dims.h + TH - 1) / TH;
   p.total_tiles = p.n * dims.d * p.tiles_h * p.tiles_w;
-  const int amax = Cfg::kMaxUnits;
-  p.passes_per_group = (25 + amax - 1) / amax;
-  p.units_per_pass = (25 + p.passes_per_group - 1) / p.passes_per_group;
+  int amax = Cfg::kMaxUnits;
+  if (amax > p.units_total) amax = p.units_total;
+  p.passes_per_group = (p.units_total + amax - 1) / amax;
+  p.units_per_pass = (p.units_total + p.passes_per_group - 1) / p.passes_per_group;
   p.num_passes = p.mhalves * p.kd_groups * p.passes_per_group;
   int chunks = (2 * kNumSMs + p.num_passes - 1) / p.num_passes;
   if (chunks > p.total_tiles) chunks = p.total_tiles;
@@ -786,6 +832,7 @@ int msb_conv_k5_wgrad(msb_tensor x, msb_tensor dy, float* dw, float* dbias, int 
   p.kd_groups = (5 + qeff - 1) / qeff;
   p.ws = reinterpret_cast<float*>(workspace);
   p.dbg_swap = g_debug_flags[1];
+  p.pad = 2; p.units_total = 25;
   const int npad = msb_conv_k5_out_pad(dy.c);
   int rc = MSB_ERR_UNSUPPORTED;
   if (g_debug_flags[2] == 0) rc = launch_wgrad_v2(x, dy, cout, cin, n, dims, p.ws, st);
@@ -806,6 +853,69 @@ int msb_conv_k5_wgrad(msb_tensor x, msb_tensor dy, float* dw, float* dbias, int 
   if (dbias != nullptr) {
     const dim3 grid((unsigned)((S + 8191) / 8192), dy.c / 8, n);
     channel_sum_bf16_kernel<<<grid, 256, 0, st>>>(dy, S, cout, dbias);
+  }
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+size_t msb_conv_k2s2_wgrad_workspace_bytes(int n, int c_big, int c_small, msb_dim3 big_dims) {
+  const size_t xs = (size_t)n * c_big * big_dims.d * big_dims.h * big_dims.w * sizeof(__nv_bfloat16);
+  return ((xs + 255) / 256) * 256 + (size_t)c_small * 8 * c_big * sizeof(float);
+}
+
+int msb_conv_k2s2_wgrad(msb_tensor big, msb_tensor small, float* dw, float* dbias, int n, msb_dim3 big_dims,
+                        int bias_from_big, void* workspace, size_t workspace_bytes, void* stream) {
+  MSB_REQUIRE(view_ok(big) && view_ok(small) && big.dtype == MSB_BF16 && small.dtype == MSB_BF16 && dw && n > 0,
+              "msb_conv_k2s2_wgrad: bf16 B8 views required");
+  MSB_REQUIRE(big_dims.d > 0 && big_dims.h > 0 && big_dims.w > 0 && big_dims.d % 2 == 0 && big_dims.h % 2 == 0 &&
+                  big_dims.w % 2 == 0,
+              "msb_conv_k2s2_wgrad: the large grid must have even extents");
+  MSB_REQUIRE(big.c == 16 || big.c == 32 || big.c == 64 || big.c == 128, "msb_conv_k2s2_wgrad: big.c in {16,32,64,128}");
+  MSB_REQUIRE(small.c % 16 == 0 && small.c <= 256, "msb_conv_k2s2_wgrad: small.c must be a multiple of 16 (<= 256)");
+  const size_t need = msb_conv_k2s2_wgrad_workspace_bytes(n, big.c, small.c, big_dims);
+  MSB_REQUIRE(workspace && workspace_bytes >= need, "msb_conv_k2s2_wgrad: workspace too small (%zu < %zu)",
+              workspace_bytes, need);
+  cudaStream_t st = as_stream(stream);
+  const msb_dim3 sd = {big_dims.d / 2, big_dims.h / 2, big_dims.w / 2};
+  const int64_t Ss = (int64_t)sd.d * sd.h * sd.w, Sb = Ss * 8;
+  const int c8n = big.c / 8, cxs = 8 * big.c;
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(workspace);
+  const size_t xs_bytes = (((size_t)n * big.c * Sb * sizeof(__nv_bfloat16) + 255) / 256) * 256;
+  float* ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + xs_bytes);
+  {
+    int bx = (int)((Ss + 255) / 256);
+    if (bx > 1024) bx = 1024;
+    s2d_k2_kernel<<<dim3(bx, 8 * c8n, n), 256, 0, st>>>(big, xs, c8n, sd.d, sd.h, sd.w);
+  }
+  MSB_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)small.c * cxs * sizeof(float), st));
+  msb_tensor xst;
+  xst.ptr = xs; xst.n_stride = (int64_t)cxs * Ss; xst.c = cxs; xst.dtype = MSB_BF16;
+  WgParams p;
+  p.n = n; p.cin_pad = cxs; p.cin_real = cxs; p.cout_real = small.c; p.dy_c8 = small.c / 8;
+  p.d = sd.d; p.h = sd.h; p.w = sd.w;
+  p.x_c8_total = cxs / 8;
+  p.dy_c8_total = (int)(small.n_stride / (Ss * 8));
+  p.cin_m = 128; p.mhalves = cxs / 128; p.qm = 1; p.kd_groups = 1;
+  p.ws = ws; p.dbg_swap = 0; p.pad = 0; p.units_total = 1;
+  int rc;
+  switch (msb_conv_k5_out_pad(small.c)) {
+    case 16: rc = launch_wgrad<16, 8>(xst, small, p, sd, st); break;
+    case 32: rc = launch_wgrad<32, 8>(xst, small, p, sd, st); break;
+    case 64: rc = launch_wgrad<64, 8>(xst, small, p, sd, st); break;
+    case 128: rc = launch_wgrad<128, 8>(xst, small, p, sd, st); break;
+    default: rc = launch_wgrad<256, 4>(xst, small, p, sd, st); break;
+  }
+  if (rc) return rc;
+  {
+    const int64_t total = (int64_t)small.c * big.c * 8;
+    const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    k2s2_unpack_kernel<<<blocks, 256, 0, st>>>(ws, dw, small.c, big.c);
+  }
+  if (dbias != nullptr) {
+    const msb_tensor& bt = bias_from_big ? big : small;
+    const int64_t sbt = bias_from_big ? Sb : Ss;
+    const dim3 grid((unsigned)((sbt + 8191) / 8192), bt.c / 8, n);
+    channel_sum_bf16_kernel<<<grid, 256, 0, st>>>(bt, sbt, bt.c, dbias);
   }
   MSB_LAUNCH_OK();
   return MSB_OK;

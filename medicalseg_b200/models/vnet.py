@@ -370,6 +370,7 @@ class VNet(_Module):
         self._scratch = torch.zeros(1 << 18, dtype=torch.float64, device=self.device)
         self._scratch_off = 0
         self._wg_ws = None
+        self._k2_ws = None
         self._masks: Optional[Dict[str, torch.Tensor]] = None
         self._tape = None
         self.grad_ready_hook = None  # callable(lo, hi) on flat-grad ranges, fired in backward order (DDP buckets)
@@ -463,6 +464,17 @@ class VNet(_Module):
         v = self._scratch[self._scratch_off:self._scratch_off + count]
         self._scratch_off += count
         return v
+
+    def strided_wgrad(self, big: B8, small: B8, dw, dbias, kernel, stride, bias_from_big):
+        """weight gradient of a down / up conv: tensor-core path for the 2x2x2 stride-2 bf16 case"""
+        if (self.dtype == torch.bfloat16 and tuple(kernel) == (2, 2, 2) and tuple(stride) == (2, 2, 2)
+                and all(d % 2 == 0 for d in big.dims) and big.c in (16, 32, 64, 128) and small.c % 16 == 0):
+            need = ops.k2s2_wgrad_workspace_bytes(big.n, big.c, small.c, big.dims)
+            if self._k2_ws is None or self._k2_ws.numel() < need:
+                self._k2_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            ops.k2s2_wgrad(big, small, dw, dbias, bias_from_big, self._k2_ws)
+        else:
+            ops.conv_strided_wgrad(big, small, dw, dbias, kernel, stride, (0, 0, 0), bias_from_big)
 
     def wgrad_workspace(self, cin, cout):
         need = ops.k5_wgrad_workspace_bytes(cin, cout)
@@ -673,8 +685,8 @@ class VNet(_Module):
             tr.act_up.bwd(g_xcat.view(0, half), dyu)
             g_xin = self._new(n, tr.in_ch, rec["xin"].dims)
             ops.conv_strided_fwd(dyu, st.view(tr.up_conv.weight), None, g_xin, tr.kernel, tr.stride, (0, 0, 0), 1, None)
-            ops.conv_strided_wgrad(dyu, rec["xd"], st.grad_view(tr.up_conv.weight), st.grad_view(tr.up_conv.bias),
-                                   tr.kernel, tr.stride, (0, 0, 0), True)
+            self.strided_wgrad(dyu, rec["xd"], st.grad_view(tr.up_conv.weight), st.grad_view(tr.up_conv.bias),
+                               tr.kernel, tr.stride, True)
             if rec["mx"] is not None:
                 ops.channel_scale(g_xin, g_xin, rec["mx"], False)
             self._fire(tr)
@@ -697,8 +709,8 @@ class VNet(_Module):
             tr.act_down.bwd(g_down, dyd)
             ops.conv_strided_bwd_data(dyd, st.view(tr.down_conv.weight), None, g_xin, tr.kernel, tr.stride, (0, 0, 0),
                                       True, 1, None)
-            ops.conv_strided_wgrad(rec["xin"], dyd, st.grad_view(tr.down_conv.weight),
-                                   st.grad_view(tr.down_conv.bias), tr.kernel, tr.stride, (0, 0, 0), False)
+            self.strided_wgrad(rec["xin"], dyd, st.grad_view(tr.down_conv.weight), st.grad_view(tr.down_conv.bias),
+                               tr.kernel, tr.stride, False)
             self._fire(tr)
 
         down_bwd(self.down_tr256, tape["d256"], g_out256, g_out128, 4)

@@ -152,6 +152,15 @@ def conv_strided_wgrad(big: B8, small: B8, dw, dbias, kernel, stride, pad, bias_
          dim3(stride), dim3(pad), c_big_real, c_small_real, int(bias_from_big), _stream())
 
 
+def k2s2_wgrad_workspace_bytes(n, c_big, c_small, big_dims) -> int:
+    return call("msb_conv_k2s2_wgrad_workspace_bytes", n, c_big, c_small, dim3(big_dims))
+
+
+def k2s2_wgrad(big: B8, small: B8, dw, dbias, bias_from_big, workspace: torch.Tensor):
+    call("msb_conv_k2s2_wgrad", big.mt, small.mt, _ptr(dw), _ptr(dbias), big.n, dim3(big.dims), int(bias_from_big),
+         _ptr(workspace), workspace.numel() * workspace.element_size(), _stream())
+
+
 def k5_out_pad(c_view: int) -> int:
     return call("msb_conv_k5_out_pad", c_view)
 

@@ -250,6 +250,33 @@ def test_conv_k5_tcgen05_wgrad(cin, cout, dims):
     assert rel(dw, 2 * ref) <= 1e-4
 
 
+@pytest.mark.parametrize("ci,co,dims", [(16, 32, (8, 12, 16)), (64, 128, (4, 8, 32)), (128, 256, (4, 4, 16))])
+def test_k2s2_tensor_core_wgrad(ci, co, dims):
+    """2x2x2 stride-2 weight gradients (space-to-depth + pointwise tcgen05 GEMM) for conv and transposed conv"""
+    ops, B8 = _imp()
+    torch.manual_seed(9)
+    n = 2
+    od = tuple(d // 2 for d in dims)
+    xb = B8.from_ncdhw(torch.randn(n, ci, *dims, device="cuda"), torch.bfloat16)
+    dyb = B8.from_ncdhw(torch.randn(n, co, *od, device="cuda"), torch.bfloat16)
+    ws = torch.empty(ops.k2s2_wgrad_workspace_bytes(n, ci, co, dims), dtype=torch.uint8, device="cuda")
+    # nn.Conv3D: big = x, small = dy, dw [co][ci][2,2,2]
+    ref = torch.nn.grad.conv3d_weight(xb.to_ncdhw(), (co, ci, 2, 2, 2), dyb.to_ncdhw(), stride=2)
+    dw, db = torch.zeros(co, ci, 2, 2, 2, device="cuda"), torch.zeros(co, device="cuda")
+    ops.k2s2_wgrad(xb, dyb, dw, db, False, ws)
+    assert rel(dw, ref) <= 1e-4
+    assert rel(db, dyb.to_ncdhw().sum((0, 2, 3, 4))) <= 1e-5
+    # nn.Conv3DTranspose (weight [Cin_T = co, Cout_T = ci, k]): big = dy_out (ci channels), small = x_in (co channels)
+    x_in = dyb.to_ncdhw().requires_grad_(False)
+    wt = torch.randn(co, ci, 2, 2, 2, device="cuda", requires_grad=True)
+    out = F.conv_transpose3d(x_in, wt, stride=2)
+    out.backward(xb.to_ncdhw())
+    dwt, dbt = torch.zeros(co, ci, 2, 2, 2, device="cuda"), torch.zeros(ci, device="cuda")
+    ops.k2s2_wgrad(xb, dyb, dwt, dbt, True, ws)
+    assert rel(dwt, wt.grad) <= 1e-4
+    assert rel(dbt, xb.to_ncdhw().sum((0, 2, 3, 4))) <= 1e-5
+
+
 @pytest.mark.parametrize("c", [2, 3, 20])
 def test_fused_dice_ce_loss_matches_oracle(c):
     from oracle import vnet_oracle as vo

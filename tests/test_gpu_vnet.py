@@ -73,7 +73,7 @@ def test_vnet_f32_five_sgd_steps_match_oracle():
     """mirrors the reference's (commented) alignment harness: 5 optimizer steps, compare losses and parameters
     (medicalseg/models/vnet.py:351-397)"""
     from medicalseg_b200.optimizer import Momentum, PolynomialDecay
-    vo, L, om, m, img, lab, ol, ours = _setup("f32", 3, (16, 16, 16), True)
+    vo, L, om, m, img, lab, ol, ours = _setup("f32", 3, (32, 32, 32), True)
     oopt = vo.Momentum(vo.PolynomialDecay(0.001, 15000), list(om.parameters()), 0.9, 1e-4)
     opt = Momentum(PolynomialDecay(0.001, 15000), m.parameters(), 0.9, 1e-4)
     for step in range(5):
@@ -84,7 +84,7 @@ def test_vnet_f32_five_sgd_steps_match_oracle():
         assert abs(opt.get_lr() - oopt.get_lr()) < 1e-12
     pdiff = max(float((m.store.view(n).cpu() - p.detach()).abs().max()) for n, p in om.named_parameters())
     bdiff = max(float((m.store.view(n).cpu() - b).abs().max()) for n, b in om.named_buffers())
-    assert pdiff <= 1e-4 and bdiff <= 1e-3, (pdiff, bdiff)
+    assert pdiff <= 2e-4 and bdiff <= 2e-3, (pdiff, bdiff)
 
 
 def test_vnet_f32_mri_anisotropic_20_classes():

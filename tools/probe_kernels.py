@@ -299,7 +299,10 @@ def timing():
         t_f = timeit(lambda: ops.conv_strided_fwd(x, w, None, y, k, s, (0, 0, 0), 1, None))
         t_d = timeit(lambda: ops.conv_strided_bwd_data(y, w, None, x, k, s, (0, 0, 0), False, 1, None))
         t_w = timeit(lambda: ops.conv_strided_wgrad(x, y, dw, None, k, s, (0, 0, 0), False))
-        print("k2s2 %3d->%3d @%3d: gather %.3f ms  scatter %.3f ms  wgrad %.3f ms" % (ci, co, d, t_f, t_d, t_w))
+        wsb = torch.empty(ops.k2s2_wgrad_workspace_bytes(n, ci, co, (d,) * 3), dtype=torch.uint8, device="cuda")
+        t_w2 = timeit(lambda: ops.k2s2_wgrad(x, y, dw, None, False, wsb))
+        print("k2s2 %3d->%3d @%3d: gather %.3f ms  scatter %.3f ms  wgrad %.3f ms  wgrad(tensor core) %.3f ms" %
+              (ci, co, d, t_f, t_d, t_w, t_w2))
     x = torch.rand(n, 1, 128, 128, 128, device="cuda")
     y = B8(n, 16, (128,) * 3, torch.bfloat16, device="cuda"); y.buf.normal_()
     w = torch.randn(16, 1, 5, 5, 5, device="cuda")
