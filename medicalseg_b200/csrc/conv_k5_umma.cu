@@ -97,10 +97,11 @@ __device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
   return r;
 }
 
-template <int NPAD, int TD, int J, int ACC_SETS>
+template <int NPAD, int TD, int J, int ACC_SETS, int NS>
 __global__ void __launch_bounds__(256, 1)
     conv_k5_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const FwdParams p) {
   using Cfg = FwdCfg<NPAD, TD, J, ACC_SETS>;
+  static_assert(NS == 1 || J == 1, "channel slicing only without plane stacking");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* halo_smem = smem;                                   // [2][kHaloBytes]
@@ -135,15 +136,15 @@ __global__ void __launch_bounds__(256, 1)
 
   const int chunks = p.cin_pad / 16;
   const int items_per_n = p.dblocks * p.tiles_h * p.tiles_w;
-  const int num_items = p.n * items_per_n * p.nsplit;  // item = tile * nsplit + channel slice
-  const int n_slice = Cfg::kNMma / p.nsplit;           // MMA N per item
+  const int num_items = p.n * items_per_n * NS;        // item = tile * NS + channel slice
+  constexpr int n_slice = Cfg::kNMma / NS;             // MMA N per item
 
   if (warp == 0) {
     // ================= halo TMA producer =================
     if (lane == 0) {
       uint32_t use = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int tile = item / p.nsplit;
+        const int tile = item / NS;
         const int n = tile / items_per_n;
         int r = tile % items_per_n;
         const int tw = r % p.tiles_w; r /= p.tiles_w;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(256, 1)
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16(128, n_slice, 0, 0);
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, n_slice, 0, 0);
       const uint32_t a_lbo = (uint32_t)Cfg::kHaloPlaneBytes, a_sbo = (uint32_t)(kHaloW * 16);
       const uint32_t b_lbo = (uint32_t)Cfg::kWK8Bytes, b_sbo = 128u;
       uint32_t huse = 0, wuse = 0, iuse = 0;
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(256, 1)
         ptx::mbar_wait(BAR(14 + as), aph ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_base = tmem_base + as * Cfg::kAccCols;
-        const uint32_t b_slice = (uint32_t)((item % p.nsplit) * n_slice);  // first weight row (16 B each) of this slice
+        const uint32_t b_slice = (uint32_t)((item % NS) * n_slice);  // first weight row (16 B each) of this slice
         for (int ck = 0; ck < chunks; ++ck, ++huse) {
           const uint32_t hb = huse & 1, hph = (huse >> 1) & 1;
           ptx::mbar_wait(BAR(0 + hb), hph);
@@ -227,8 +228,8 @@ __global__ void __launch_bounds__(256, 1)
     float* my_stats = stat_smem + q * 2 * NPAD;
     uint32_t iuse = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
-      const int tile = item / p.nsplit;
-      const int c_first = (item % p.nsplit) * n_slice;  // first output channel of this slice (nsplit > 1 only with J == 1)
+      const int tile = item / NS;
+      const int c_first = (item % NS) * n_slice;  // first output channel of this slice (nsplit > 1 only with J == 1)
       const int n = tile / items_per_n;
       int r = tile % items_per_n;
       const int tw = r % p.tiles_w; r /= p.tiles_w;
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(256, 1)
         const bool ok = inb && d < p.d;
         const int64_t v = ((int64_t)d * p.h + h) * p.w + w;
 #pragma unroll 1
-        for (int cb = 0; cb < (NPAD / p.nsplit) / 16; ++cb) {
+        for (int cb = 0; cb < (NPAD / NS) / 16; ++cb) {
           float acc[16];
           ptx::tmem_ld16(t_base + td * NPAD + cb * 16, acc);
           float sq[16];
@@ -681,30 +682,39 @@ int make_b8_tmap_hmajor(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 d
 
 int g_debug_flags[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
+template <int NPAD, int TD, int J, int ACC_SETS, int NS>
+static int launch_fwd_ns(const CUtensorMap& tmap, FwdParams& p, int tiles, cudaStream_t st) {
+  using Cfg = FwdCfg<NPAD, TD, J, ACC_SETS>;
+  const int items = tiles * NS;
+  const int grid = items < kNumSMs ? items : kNumSMs;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MSB_CUDA_OK(cudaFuncSetAttribute(conv_k5_fwd_kernel<NPAD, TD, J, ACC_SETS, NS>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  conv_k5_fwd_kernel<NPAD, TD, J, ACC_SETS, NS><<<grid, 256, Cfg::kSmemBytes, st>>>(tmap, p);
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
 template <int NPAD, int TD, int J = 1, int ACC_SETS = 2>
 static int launch_fwd(const msb_tensor& x, msb_dim3 dims, FwdParams& p, cudaStream_t st) {
-  using Cfg = FwdCfg<NPAD, TD, J, ACC_SETS>;
   CUtensorMap tmap;
   int rc = make_b8_tmap(&tmap, x, p.n, dims, kHaloW, kHaloH, TD + 4, 2);
   if (rc) return rc;
   p.dblocks = (p.d + TD - 1) / TD;
   const int tiles = p.n * p.dblocks * p.tiles_h * p.tiles_w;
-  p.nsplit = 1;
+  int nsplit = 1;
   if (J == 1 && g_debug_flags[4] == 0)  // small volumes: slice the output channels so that every SM gets work
-    while (p.nsplit < 4 && tiles * p.nsplit * 2 <= kNumSMs && (NPAD / (p.nsplit * 2)) % 16 == 0 &&
-           NPAD / (p.nsplit * 2) >= 32)
-      p.nsplit *= 2;
-  const int items = tiles * p.nsplit;
-  const int grid = items < kNumSMs ? items : kNumSMs;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MSB_CUDA_OK(cudaFuncSetAttribute(conv_k5_fwd_kernel<NPAD, TD, J, ACC_SETS>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
+    while (nsplit < 4 && tiles * nsplit * 2 <= kNumSMs && (NPAD / (nsplit * 2)) % 16 == 0 && NPAD / (nsplit * 2) >= 32)
+      nsplit *= 2;
+  p.nsplit = nsplit;
+  if constexpr (J == 1 && NPAD >= 128) {
+    if (nsplit == 4) return launch_fwd_ns<NPAD, TD, J, ACC_SETS, 4>(tmap, p, tiles, st);
+    if (nsplit == 2) return launch_fwd_ns<NPAD, TD, J, ACC_SETS, 2>(tmap, p, tiles, st);
   }
-  conv_k5_fwd_kernel<NPAD, TD, J, ACC_SETS><<<grid, 256, Cfg::kSmemBytes, st>>>(tmap, p);
-  MSB_LAUNCH_OK();
-  return MSB_OK;
+  return launch_fwd_ns<NPAD, TD, J, ACC_SETS, 1>(tmap, p, tiles, st);
 }
 
 static inline int pad16(int c) { return (c + 15) / 16 * 16; }
