@@ -444,6 +444,21 @@ def vnet_bf16_32():
     _vnet_case("bf16", 2, (32, 32, 32), steps=1)
 
 
+@check
+def vnet_bf16_cosines():
+    """gradient cosine per conv weight, bf16 path vs f32 oracle, at 32^3 and 64^3"""
+    torch, F, ops, B8, _ = _imports()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_gpu_vnet as tv
+    for shape in ((32, 32, 32), (64, 64, 64)):
+        vo, L, om, m, img, lab, ol, ours = tv._setup("bf16", 2, shape, True)
+        ologits, logits, ll, l2, dice, d2 = tv._step(vo, L, om, m, img, lab, ol, ours, True)
+        worst, cos = tv._grad_errors(om, m)
+        rms = float(torch.sqrt(((logits - ologits) ** 2).mean()) / torch.sqrt((ologits ** 2).mean()))
+        print(shape, "rms", rms, "dice diff", float(abs(dice - d2).max()), "worst rel", worst)
+        print("   ", {k: round(v, 4) for k, v in cos.items()})
+
+
 def main():
     if len(sys.argv) > 2 and sys.argv[1] == "--run":
         CHECKS[sys.argv[2]]()
