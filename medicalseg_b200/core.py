@@ -1,0 +1,153 @@
+"""Train / evaluate loops (reference: medicalseg/core/train.py:30-274, val.py:29-187, infer.py:62-94) on the B200
+path: same iteration order (forward -> loss_computation -> backward -> optimizer.step -> lr step -> clear
+gradients), same log line, same checkpoint layout (iter_N/model.pdparams + model.pdopt, best_model/).  Multi-GPU =
+one process per GPU (torchrun), volumes sharded per rank, one bucketed NCCL gradient all-reduce per step."""
+from __future__ import annotations
+
+import os
+import shutil
+import time
+from collections import deque
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .models.losses import loss_computation
+from .parallel import DistributedGradReducer
+from .utils import resume, save_checkpoint
+
+
+def _log(msg, level="INFO"):
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        print("{} [{}]\t{}".format(time.strftime("%Y-%m-%d %H:%M:%S"), level, msg), flush=True)
+
+
+def _collate(dataset, indices, device):
+    ims, labs = zip(*[dataset[i][:2] for i in indices])
+    return torch.stack(ims).to(device, non_blocking=True), torch.stack(labs).to(device, non_blocking=True)
+
+
+def inference(model, im, ori_shape=None, transforms=None):
+    logits = model(im)
+    if not isinstance(logits, (list, tuple)):
+        raise TypeError("The type of logits must be one of collections.abc.Sequence, e.g. list, tuple. But received {}"
+                        .format(type(logits)))
+    logit = logits[0]
+    pred = torch.argmax(logit, dim=1, keepdim=True).to(torch.int32)
+    return pred, logit
+
+
+def evaluate(model, eval_dataset, losses, num_workers=0, print_detail=True, save_dir=None, **_):
+    new_loss = {"types": [losses["types"][0]], "coef": [losses["coef"][0]]}
+    model.eval()
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    device = model.device
+    indices = list(range(len(eval_dataset)))[rank::world]
+    mdice, channel_dice, loss_all = 0.0, None, 0.0
+    if print_detail:
+        _log("Start evaluating (total_samples: {}, total_iters: {})...".format(len(eval_dataset), len(indices)))
+    with torch.no_grad():
+        for it, idx in enumerate(indices):
+            im, label = _collate(eval_dataset, [idx], device)
+            pred, logits = inference(model, im, ori_shape=label.shape[-3:])
+            loss, per_channel_dice = loss_computation([logits], label.to(torch.int32), new_loss)
+            loss_all += float(sum(loss))
+            mdice += float(np.mean(per_channel_dice))
+            channel_dice = per_channel_dice if channel_dice is None else channel_dice + per_channel_dice
+            if save_dir is not None and it < 5 and rank == 0:
+                os.makedirs(os.path.join(save_dir, str(it)), exist_ok=True)
+                np.save(os.path.join(save_dir, str(it), "pred.npy"), pred.cpu().numpy())
+    n_local = max(len(indices), 1)
+    if world > 1:  # the reference does not reduce metrics across ranks (val.py:168); we report the global figure
+        t = torch.tensor([mdice, loss_all, float(len(indices))], device=device, dtype=torch.float64)
+        cd = torch.as_tensor(channel_dice, device=device, dtype=torch.float64)
+        dist.all_reduce(t); dist.all_reduce(cd)
+        mdice, loss_all, n_local = float(t[0]), float(t[1]), max(float(t[2]), 1.0)
+        channel_dice = cd.cpu().numpy()
+    mdice, loss_all = mdice / n_local, loss_all / n_local
+    channel_dice = channel_dice / n_local
+    if print_detail:
+        _log("[EVAL] #Images: {}, Dice: {:.4f}, Loss: {:6f}".format(len(eval_dataset), mdice, loss_all))
+        _log("[EVAL] Class dice: \n" + str(np.round(channel_dice, 4)))
+    return {"mdice": mdice}
+
+
+def train(model, train_dataset, val_dataset=None, optimizer=None, save_dir="output", iters=10000, batch_size=2,
+          resume_model=None, save_interval=1000, log_iters=10, num_workers=0, use_vdl=False, losses=None,
+          keep_checkpoint_max=5, profiler_options=None, to_static_training=False, seed=0):
+    model.train()
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    device = model.device
+    start_iter = resume(model, optimizer, resume_model) if resume_model is not None else 0
+    os.makedirs(save_dir, exist_ok=True)
+    reducer = DistributedGradReducer(model.store.grad).attach(model)
+    optimizer.grad_scale = reducer.grad_scale
+    prof_range = None
+    if profiler_options:  # "batch_range=[10,20]" -> cudaProfilerStart/Stop window (ncu / nsys --capture-range)
+        import re
+        m = re.search(r"batch_range=\[(\d+),\s*(\d+)\]", profiler_options)
+        prof_range = (int(m.group(1)), int(m.group(2))) if m else None
+    g = torch.Generator().manual_seed(seed)
+    n = len(train_dataset)
+    iters_per_epoch = max((n // world + batch_size - 1) // batch_size, 1)
+    avg_loss, mdice, save_models, best_mean_dice, best_model_iter = 0.0, 0.0, deque(), -1.0, -1
+    it = start_iter
+    batch_start = time.time()
+    reader_cost = batch_cost = 0.0
+    while it < iters:
+        perm = torch.randperm(n, generator=g).tolist()[rank::world]  # DistributedBatchSampler(shuffle=True)
+        for b in range(0, len(perm), batch_size):
+            if it >= iters:
+                break
+            images, labels = _collate(train_dataset, perm[b:b + batch_size], device)
+            reader_cost += time.time() - batch_start
+            if prof_range and it == prof_range[0]:
+                torch.cuda.cudart().cudaProfilerStart()
+            logits_list = model(images)
+            loss_list, per_channel_dice = loss_computation(logits_list, labels.to(torch.int32), losses)
+            loss = sum(loss_list)
+            loss.backward()
+            reducer.wait()
+            optimizer.step()
+            lr = optimizer.get_lr()
+            it += 1
+            if hasattr(optimizer._learning_rate, "step"):
+                optimizer._learning_rate.step()
+            model.clear_gradients()
+            if prof_range and it == prof_range[1]:
+                torch.cuda.cudart().cudaProfilerStop()
+            avg_loss += float(loss.detach())
+            mdice += float(np.mean(per_channel_dice)) * 100
+            batch_cost += time.time() - batch_start
+            if it % log_iters == 0 and rank == 0:
+                avg_loss /= log_iters
+                mdice /= log_iters
+                bc, rc = batch_cost / log_iters, reader_cost / log_iters
+                eta = int((iters - it) * bc)
+                _log("[TRAIN] epoch: {}, iter: {}/{}, loss: {:.4f}, DSC: {:.4f}, lr: {:.6f}, batch_cost: {:.4f}, "
+                     "reader_cost: {:.5f}, ips: {:.4f} samples/sec | ETA {:02d}:{:02d}:{:02d}".format(
+                         it // iters_per_epoch, it, iters, avg_loss, mdice, lr, bc, rc, batch_size / bc,
+                         eta // 3600, (eta % 3600) // 60, eta % 60))
+                avg_loss = mdice = reader_cost = batch_cost = 0.0
+            elif it % log_iters == 0:
+                avg_loss = mdice = reader_cost = batch_cost = 0.0
+            if (it % save_interval == 0 or it == iters) and val_dataset is not None:
+                result = evaluate(model, val_dataset, losses, print_detail=True, save_dir=save_dir)
+                model.train()
+            if (it % save_interval == 0 or it == iters) and rank == 0:
+                cur = os.path.join(save_dir, "iter_{}".format(it))
+                save_checkpoint(model, optimizer, cur)
+                save_models.append(cur)
+                if len(save_models) > keep_checkpoint_max > 0:
+                    shutil.rmtree(save_models.popleft())
+                if val_dataset is not None:
+                    if result["mdice"] > best_mean_dice:
+                        best_mean_dice, best_model_iter = result["mdice"], it
+                        save_checkpoint(model, None, os.path.join(save_dir, "best_model"))
+                    _log("[EVAL] The model with the best validation mDice ({:.4f}) was saved at iter {}.".format(
+                        best_mean_dice, best_model_iter))
+            batch_start = time.time()
+    time.sleep(0.1)

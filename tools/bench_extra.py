@@ -1,0 +1,91 @@
+"""Secondary measurements (not the driver's bench line): BASELINE.json configs[3] (MRI 512x512x12, 20 classes,
+anisotropic kernels) and configs[4] (preprocess 512^3 -> 128^3), each with its CPU baseline on the box's host cores.
+
+    python tools/bench_extra.py mri        # VNet MRISpineSeg train step, batch 2, bf16
+    python tools/bench_extra.py preprocess # HUnorm + resample (order 1) and label resample (order 0)
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def ev_time(fn, reps):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def mri():
+    from medicalseg_b200.models import VNet, losses as L
+    from medicalseg_b200.optimizer import Momentum, PolynomialDecay
+    kw = dict(kernel_size=[[2, 2, 4], [2, 2, 2], [2, 2, 2], [2, 2, 2]], stride_size=[[2, 2, 1], [2, 2, 1], [2, 2, 2], [2, 2, 2]])
+    m = VNet(num_classes=20, compute_dtype="bf16", **kw)
+    m.train()
+    losses = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1])], "coef": [1]}
+    opt = Momentum(PolynomialDecay(0.1, 15000), m.parameters(), 0.9, 1e-4)
+    img = torch.rand(2, 1, 512, 512, 12, device="cuda")
+    lab = torch.randint(0, 20, (2, 512, 512, 12), device="cuda", dtype=torch.int32)
+
+    def step():
+        ll, dice = L.loss_computation(m(img), lab, losses)
+        sum(ll).backward()
+        opt.step(); opt._learning_rate.step(); m.clear_gradients()
+
+    for _ in range(3):
+        step()
+    ms = ev_time(step, 5)
+    print(json.dumps({"metric": "VNet MRISpineSeg 512x512x12 20-class bf16 train-step volumes/sec", "value": round(2e3 / ms, 3),
+                      "unit": "volumes/s", "ms_per_step": round(ms, 2), "n_gpus": 1, "batch": 2,
+                      "tflops": round(2 * 12817 / ms, 1)}))
+
+
+def preprocess():
+    from medicalseg_b200 import preprocess as P
+    from oracle import preprocess_oracle as po
+    import scipy.ndimage
+    rng = np.random.default_rng(0)
+    vol = rng.uniform(-2000, 2000, size=(512, 512, 512)).astype(np.float32)
+    vol[rng.random(vol.shape) < 0.001] = np.nan
+    lab = rng.integers(0, 3, size=(512, 512, 512)).astype(np.int32)
+    dvol, dlab = torch.from_numpy(vol).cuda(), torch.from_numpy(lab).cuda()
+    # device-resident: fused HUnorm+resample, and the reference's two-pass order
+    t_fused = ev_time(lambda: P.resample(dvol, new_shape=[128, 128, 128], order=1, pre_op=("hunorm", -1200, 600, -2000)), 10)
+    t_two = ev_time(lambda: P.resample(P.HUnorm(dvol), new_shape=[128, 128, 128], order=1), 10)
+    t_lab = ev_time(lambda: P.resample(dlab, new_shape=[128, 128, 128], order=0), 10)
+    # host-resident through the public API (numpy in, numpy out; H2D + D2H inside)
+    hv = torch.from_numpy(vol).pin_memory()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        out, _ = P.resample(hv.cuda(non_blocking=True), new_shape=[128, 128, 128], order=1,
+                            pre_op=("hunorm", -1200, 600, -2000))
+        res = out.cpu()
+    t_host = (time.perf_counter() - t0) / 3 * 1e3
+    # CPU baseline: what the reference executes (numpy HUnorm + scipy.ndimage.zoom, single-threaded C)
+    t0 = time.perf_counter()
+    hu = po.HUnorm(vol)
+    ref = scipy.ndimage.zoom(hu.astype(np.float32), 0.25, mode="nearest", order=1)
+    t_cpu = (time.perf_counter() - t0) * 1e3
+    err = float(np.abs(res.numpy() - ref).max())
+    full_scan_mb = (512 ** 3 * 4 + 128 ** 3 * 4) / 1e6
+    print(json.dumps({"metric": "preprocess HUnorm+resample 512^3->128^3 volumes/sec",
+                      "device_fused_ms": round(t_fused, 3), "device_two_pass_ms": round(t_two, 3),
+                      "label_order0_ms": round(t_lab, 3), "host_pinned_e2e_ms": round(t_host, 2),
+                      "cpu_reference_ms": round(t_cpu, 1), "cpu_cores": 1,
+                      "volumes_per_s_device": round(1e3 / t_fused, 1), "volumes_per_s_host": round(1e3 / t_host, 2),
+                      "volumes_per_s_cpu": round(1e3 / t_cpu, 3),
+                      "two_pass_full_scan_GBps": round((full_scan_mb + 2 * 512 ** 3 * 4 / 1e6) / t_two, 1),
+                      "fused_compulsory_GBps": round(142.6 / t_fused, 1), "max_abs_err_vs_scipy": err}))
+
+
+if __name__ == "__main__":
+    {"mri": mri, "preprocess": preprocess}[sys.argv[1]]()
