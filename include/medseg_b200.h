@@ -150,6 +150,36 @@ int msb_conv_k5_fwd(msb_tensor x, const void* packed, const float* bias, int cou
 size_t msb_conv_k5_wgrad_workspace_bytes(int cin, int cout);
 int msb_conv_k5_wgrad(msb_tensor x, msb_tensor dy, float* dw, float* dbias, int cout, int cin, int n,
                       msb_dim3 dims, void* workspace, size_t workspace_bytes, void* stream);
+/* ---- w-folded 5x5x1 variant of the 5x5x5 conv for layers with <= 3 real channels on one side -------------
+ * vnet.py:67-68 (in_tr.conv1, 1 -> 16: fold_side 0 = input folded) and vnet.py:165-166 (out_tr.conv1, 32 -> classes:
+ * fold_side 1 = output folded).  The five kw taps are folded into the zero padding of the 16-channel block:
+ *   fold  : F_s(t)[v,(j,c)] = t[v + s*(j-2) e_w, c]            (j = 0..4; 16-channel B8 bf16 result)
+ *   unfold: y[v,c] = bias[c] + sum_j P[v + (j-2) e_w,(j,c)]    (+ BN partial sums of the rounded y)
+ *   fold_side 0:  conv5(x)  = conv551(F_+1(x));   dW via conv551_wgrad(F_+1(x), dy)
+ *   fold_side 1:  conv5(x)  = unfold(conv551(x)); dx = conv551(F_-1(dy)) with the mode-1 operand;
+ *                 dW via conv551_wgrad(x, F_-1(dy))
+ * so one tcgen05.mma covers all five kw taps (5x fewer MMAs than the plain kernel on these operand-fetch-bound layers). */
+int msb_fold_w_f32(const float* x /* NCDHW f32 [n][c_real][D][H][W] */, int c_real, msb_tensor out, int n,
+                   msb_dim3 dims, int sign, void* stream);
+int msb_fold_w(msb_tensor x, int c_real, msb_tensor out, int n, msb_dim3 dims, int sign, void* stream);
+/* p: 16-channel B8 view (f32 or bf16); out: bf16 B8 view whose channels >= c_real are written as zeros;
+ * sums: optional BN partial sums double [2][groups][out.c] */
+int msb_unfold_w(msb_tensor p, const float* bias, int c_real, msb_tensor out, int n, msb_dim3 dims, int groups,
+                 double* sums, void* stream);
+/* packs the 5-D Paddle weight [cout][cin][5][5][5] into the folded 5x5x1 operand image (mode as msb_conv_k5_pack) */
+size_t msb_conv_k551_packed_bytes(int cin_pad, int cout_pad);
+int msb_conv_k551_pack(const float* w, void* packed, int cout, int cin, int mode, int fold_side, int cin_pad,
+                       int cout_pad, void* stream);
+/* same contract as msb_conv_k5_fwd for the 5x5x1 (kd,kh) kernel, pad (2,2,0); `out` may also be an f32 B8 view
+ * (then accumulate = 0 and sums = NULL) */
+int msb_conv_k551_fwd(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
+                      msb_dim3 dims, int accumulate, const float* ch_scale, int groups, double* sums, void* stream);
+/* dw [cout][cin][125] f32 (the 5-D weight, cout/cin REAL counts) += weight gradient computed on the folded views */
+size_t msb_conv_k551_wgrad_workspace_bytes(int cin, int cout, int fold_side);
+int msb_conv_k551_wgrad(msb_tensor x, msb_tensor dy, float* dw, int cout, int cin, int fold_side, int n,
+                        msb_dim3 dims, void* workspace, size_t workspace_bytes, void* stream);
+/* out[c] (f32) += sum over n, voxels of x[n][c][v] for c < c_real (bias gradients; bf16 B8 view) */
+int msb_channel_sum(msb_tensor x, int c_real, int n, int64_t s, float* out, void* stream);
 /* debug switches for bring-up (key 0/1: swap LBO/SBO in the fwd / wgrad UMMA descriptors) */
 int msb_debug_set(int key, int value);
 

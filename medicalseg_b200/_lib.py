@@ -50,6 +50,15 @@ SIGNATURES = {
     "msb_conv_k5_fwd": (I, [T, P, P, I, T, I, D3, I, P, I, P, P]),
     "msb_conv_k5_wgrad_workspace_bytes": (SZ, [I, I]),
     "msb_conv_k5_wgrad": (I, [T, T, P, P, I, I, I, D3, P, SZ, P]),
+    "msb_fold_w_f32": (I, [P, I, T, I, D3, I, P]),
+    "msb_fold_w": (I, [T, I, T, I, D3, I, P]),
+    "msb_unfold_w": (I, [T, P, I, T, I, D3, I, P, P]),
+    "msb_conv_k551_packed_bytes": (SZ, [I, I]),
+    "msb_conv_k551_pack": (I, [P, P, I, I, I, I, I, I, P]),
+    "msb_conv_k551_fwd": (I, [T, P, P, I, T, I, D3, I, P, I, P, P]),
+    "msb_conv_k551_wgrad_workspace_bytes": (SZ, [I, I, I]),
+    "msb_conv_k551_wgrad": (I, [T, T, P, I, I, I, I, D3, P, SZ, P]),
+    "msb_channel_sum": (I, [T, I, I, L, P, P]),
     "msb_debug_set": (I, [I, I]),
     "msb_class_weight_sums": (I, [P, I, I, L, P, P]),
     "msb_class_weight_finalize": (I, [P, D, I, P, P]),
@@ -67,7 +76,8 @@ SIGNATURES = {
 
 _NO_STATUS = {"msb_version", "msb_last_error_string", "msb_conv_k5_packed_bytes", "msb_conv_k5_out_pad",
               "msb_conv_k2s2_wgrad_workspace_bytes",
-              "msb_conv_k5_wgrad_workspace_bytes"}
+              "msb_conv_k5_wgrad_workspace_bytes", "msb_conv_k551_packed_bytes",
+              "msb_conv_k551_wgrad_workspace_bytes"}
 
 _lock = threading.Lock()
 _lib = None

@@ -18,7 +18,8 @@ int make_b8_tmap_hmajor(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 d
                         int box_d);
 
 // kh-stacked weight-gradient kernel (conv_k5_wgrad2.cu); returns MSB_ERR_UNSUPPORTED when not applicable
+// kw_taps: 5 = 5x5x5 kernel (ws [125][cout][cin]); 1 = 5x5x1 kernel of the w-folded convs (ws [25][cout][cin])
 int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin, int n, msb_dim3 dims, float* ws,
-                    cudaStream_t st);
+                    cudaStream_t st, int kw_taps = 5);
 
 }  // namespace msb

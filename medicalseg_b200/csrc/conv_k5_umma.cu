@@ -22,8 +22,6 @@ namespace msb {
 
 constexpr int kTileW = 8, kTileH = 16;
 constexpr int kHaloW = kTileW + 4, kHaloH = kTileH + 4;
-constexpr int kTapsPerStage = 5;
-constexpr int kStagesPerChunk = kNumTaps / kTapsPerStage;
 
 // NPAD: padded output channels; TD: output d-planes per work item; J: d-planes stacked along N in one MMA
 // (N_mma = J * NPAD, TD % J == 0); ACC_SETS: accumulator sets in TMEM (2 = epilogue overlaps the next item).
@@ -67,6 +65,8 @@ struct FwdParams {
   int sums_c;                            // channel count of the sums array
   int dbg_swap;
   int nsplit;                            // output-channel slices per tile (fills the SMs on small volumes)
+  int kw_taps;                           // 5 = full 5x5x5 kernel; 1 = 5x5x1 (kd,kh) kernel of the w-folded convs
+  int out_f32;                           // store f32 (B8 f32 view) instead of bf16; no accumulate, no BN sums
 };
 
 // 16 per-lane values -> per-channel totals over the warp; lane L ends up with the total of channel L>>1.
@@ -140,35 +140,39 @@ __global__ void __launch_bounds__(256, 1)
   constexpr int n_slice = Cfg::kNMma / NS;             // MMA N per item
 
   if (warp == 0) {
-    // ================= halo TMA producer =================
-    if (lane == 0) {
-      uint32_t use = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int tile = item / NS;
-        const int n = tile / items_per_n;
-        int r = tile % items_per_n;
-        const int tw = r % p.tiles_w; r /= p.tiles_w;
-        const int th = r % p.tiles_h; const int db = r / p.tiles_h;
-        for (int ck = 0; ck < chunks; ++ck, ++use) {
-          const uint32_t b = use & 1, ph = (use >> 1) & 1;
-          ptx::mbar_wait(BAR(2 + b), ph ^ 1);
+    // ================= halo TMA producer (whole warp runs the uniform loop, one elected lane issues) ==========
+    const bool leader = ptx::elect_one();
+    uint32_t use = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int tile = item / NS;
+      const int n = tile / items_per_n;
+      int r = tile % items_per_n;
+      const int tw = r % p.tiles_w; r /= p.tiles_w;
+      const int th = r % p.tiles_h; const int db = r / p.tiles_h;
+      for (int ck = 0; ck < chunks; ++ck, ++use) {
+        const uint32_t b = use & 1, ph = (use >> 1) & 1;
+        ptx::mbar_wait(BAR(2 + b), ph ^ 1);
+        if (leader) {
           ptx::mbar_expect_tx(BAR(0 + b), Cfg::kHaloBytes);
           ptx::tma_load_4d(ptx::smem_u32(halo_smem + b * Cfg::kHaloBytes), &tmap_x, BAR(0 + b),
                            (tw * kTileW - 2) * 8, th * kTileH - 2, db * TD - 2, n * p.x_c8_total + ck * 2);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 2) {
     // ================= weight producer =================
-    if (lane == 0) {
-      uint32_t use = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        for (int ck = 0; ck < chunks; ++ck) {
-          const uint8_t* src =
-              reinterpret_cast<const uint8_t*>(p.packed) + (size_t)ck * kStagesPerChunk * 2 * Cfg::kWLoadBytes;
-          for (int st = 0; st < kStagesPerChunk; ++st, ++use) {
-            const uint32_t s = use % Cfg::kWStages, ph = (use / Cfg::kWStages) & 1;
-            ptx::mbar_wait(BAR(8 + s), ph ^ 1);
+    const bool leader = ptx::elect_one();
+    uint32_t use = 0;
+    const int stages_per_chunk = 5 * p.kw_taps;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      for (int ck = 0; ck < chunks; ++ck) {
+        const uint8_t* src =
+            reinterpret_cast<const uint8_t*>(p.packed) + (size_t)ck * stages_per_chunk * 2 * Cfg::kWLoadBytes;
+        for (int st = 0; st < stages_per_chunk; ++st, ++use) {
+          const uint32_t s = use % Cfg::kWStages, ph = (use / Cfg::kWStages) & 1;
+          ptx::mbar_wait(BAR(8 + s), ph ^ 1);
+          if (leader) {
             ptx::mbar_expect_tx(BAR(4 + s), 2 * Cfg::kWLoadBytes);
 #pragma unroll
             for (int k8 = 0; k8 < 2; ++k8)
@@ -176,48 +180,57 @@ __global__ void __launch_bounds__(256, 1)
                                            (J - 1) * Cfg::kBlockBytes),
                              src + (size_t)(st * 2 + k8) * Cfg::kWLoadBytes, Cfg::kWLoadBytes, BAR(4 + s));
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, n_slice, 0, 0);
-      const uint32_t a_lbo = (uint32_t)Cfg::kHaloPlaneBytes, a_sbo = (uint32_t)(kHaloW * 16);
-      const uint32_t b_lbo = (uint32_t)Cfg::kWK8Bytes, b_sbo = 128u;
-      uint32_t huse = 0, wuse = 0, iuse = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
-        const uint32_t as = iuse % ACC_SETS, aph = (iuse / ACC_SETS) & 1;
-        ptx::mbar_wait(BAR(14 + as), aph ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t d_base = tmem_base + as * Cfg::kAccCols;
-        const uint32_t b_slice = (uint32_t)((item % NS) * n_slice);  // first weight row (16 B each) of this slice
-        for (int ck = 0; ck < chunks; ++ck, ++huse) {
-          const uint32_t hb = huse & 1, hph = (huse >> 1) & 1;
-          ptx::mbar_wait(BAR(0 + hb), hph);
-          const uint32_t halo_addr = ptx::smem_u32(halo_smem + hb * Cfg::kHaloBytes);
-          const uint64_t a_desc0 = ptx::make_desc(halo_addr, a_lbo, a_sbo);
-          for (int st = 0; st < kStagesPerChunk; ++st, ++wuse) {  // st = kh*5 + kw
-            const uint32_t s = wuse % Cfg::kWStages, wph = (wuse / Cfg::kWStages) & 1;
-            ptx::mbar_wait(BAR(4 + s), wph);
-            ptx::tc_fence_after();
-            const uint64_t b_desc0 = ptx::make_desc(ptx::smem_u32(w_smem + s * Cfg::kWStageBytes), b_lbo, b_sbo);
-            const uint32_t hw_off = (uint32_t)((st / 5) * kHaloW + (st % 5));  // 16-byte units
+    // The WHOLE warp runs the (warp-uniform) control flow and descriptor arithmetic so that everything lives in
+    // uniform registers; only the tcgen05 instructions themselves are predicated on one lane.  (Running the loop
+    // under `if (lane == 0)` makes every operand a per-thread value and costs ~11 SASS instructions per MMA -
+    // measured 102 clk per 128x128x16 MMA instead of the 64-clk tensor-core floor, tools/mma_probe.cu.)
+    const bool leader = ptx::elect_one();
+    const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);  // REDUX result = provably warp-uniform
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, n_slice, 0, 0);
+    constexpr uint32_t a_hi = ptx::desc_hi((uint32_t)(kHaloW * 16)), b_hi = ptx::desc_hi(128u);
+    constexpr uint32_t a_lbo16 = (uint32_t)Cfg::kHaloPlaneBytes >> 4, b_lbo16 = (uint32_t)Cfg::kWK8Bytes >> 4;
+    uint32_t huse = 0, wuse = 0, iuse = 0;
+    const int stages_per_chunk = 5 * p.kw_taps;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
+      const uint32_t as = iuse % ACC_SETS, aph = (iuse / ACC_SETS) & 1;
+      ptx::mbar_wait(BAR(14 + as), aph ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_base = tmem_u + as * Cfg::kAccCols;
+      const uint32_t b_slice = (uint32_t)((item % NS) * n_slice);  // first weight row (16 B each) of this slice
+      for (int ck = 0; ck < chunks; ++ck, ++huse) {
+        const uint32_t hb = huse & 1, hph = (huse >> 1) & 1;
+        ptx::mbar_wait(BAR(0 + hb), hph);
+        const uint32_t a_lo0 = ptx::desc_lo(ptx::smem_u32(halo_smem + hb * Cfg::kHaloBytes), a_lbo16);
+        for (int st = 0; st < stages_per_chunk; ++st, ++wuse) {  // st = kh*kw_taps + kw
+          const uint32_t s = wuse % Cfg::kWStages, wph = (wuse / Cfg::kWStages) & 1;
+          ptx::mbar_wait(BAR(4 + s), wph);
+          ptx::tc_fence_after();
+          const uint32_t b_lo0 = ptx::desc_lo(ptx::smem_u32(w_smem + s * Cfg::kWStageBytes), b_lbo16) + b_slice;
+          const uint32_t hw_off =  // 16-byte units; the single w tap of the 5x5x1 kernel is the centre one
+              p.kw_taps == 5 ? (uint32_t)((st / 5) * kHaloW + (st % 5)) : (uint32_t)(st * kHaloW + 2);
+          const uint32_t a_lo1 = a_lo0 + hw_off;
+          const uint32_t first = (ck | st) != 0 ? 1u : 0u;
 #pragma unroll
-            for (int g = 0; g < TD / J; ++g) {
+          for (int g = 0; g < TD / J; ++g) {
 #pragma unroll
-              for (int kdp = 0; kdp < J + 4; ++kdp) {  // input plane g*J + kdp feeds output planes g*J + j, tap kd = kdp - j
-                const uint64_t a_desc = a_desc0 + (uint64_t)(hw_off + (g * J + kdp) * kHaloH * kHaloW);
-                const uint64_t b_desc = b_desc0 + (uint64_t)((((J + 3 - kdp) * Cfg::kBlockBytes) >> 4) + b_slice);
-                ptx::mma_bf16(d_base + g * Cfg::kNMma, a_desc, b_desc, idesc, (ck | st | kdp) != 0 ? 1u : 0u);
-              }
+            for (int kdp = 0; kdp < J + 4; ++kdp) {  // input plane g*J + kdp feeds output planes g*J + j, tap kd = kdp - j
+              const uint32_t a_lo = a_lo1 + (uint32_t)((g * J + kdp) * kHaloH * kHaloW);
+              const uint32_t b_lo = b_lo0 + (uint32_t)(((J + 3 - kdp) * Cfg::kBlockBytes) >> 4);
+              if (leader) ptx::mma_bf16_split(d_base + g * Cfg::kNMma, a_lo, a_hi, b_lo, b_hi, idesc, kdp != 0 ? 1u : first);
             }
-            ptx::mma_commit(BAR(8 + s));  // weight stage free once these MMAs retire
           }
-          ptx::mma_commit(BAR(2 + hb));   // halo buffer free
+          if (leader) ptx::mma_commit(BAR(8 + s));  // weight stage free once these MMAs retire
         }
-        ptx::mma_commit(BAR(12 + as));    // accumulators complete -> epilogue
+        if (leader) ptx::mma_commit(BAR(2 + hb));   // halo buffer free
       }
+      if (leader) ptx::mma_commit(BAR(12 + as));    // accumulators complete -> epilogue
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ================= epilogue: TMEM -> registers -> (bias, accumulate, round, BN sums) -> global =================
@@ -260,7 +273,9 @@ __global__ void __launch_bounds__(256, 1)
               float val = acc[k * 8 + j] + ((p.bias != nullptr && c < p.cout_real) ? __ldg(p.bias + c) : 0.f);
               o[j] = val;
             }
-            if (c8 < p.out_c8) {
+            if (p.out_f32) {
+              if (c8 < p.out_c8 && ok) Vec8<float>::store(view_ptr<float>(p.out, n, c8, S, v), o);
+            } else if (c8 < p.out_c8) {
               __nv_bfloat16* dst = view_ptr<__nv_bfloat16>(p.out, n, c8, S, ok ? v : 0);
               if (p.accumulate) {
                 float old[8];
@@ -426,41 +441,44 @@ __global__ void __launch_bounds__(256, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(128, NPAD, 1, 1);
-      const uint32_t a_lbo = p.dbg_swap ? (uint32_t)Cfg::kGroupBytes : 128u;
-      const uint32_t a_sbo = p.dbg_swap ? 128u : (uint32_t)Cfg::kGroupBytes;
-      const uint32_t b_lbo = p.dbg_swap ? (uint32_t)Cfg::kDyPlaneBytes : 128u;
-      const uint32_t b_sbo = p.dbg_swap ? 128u : (uint32_t)Cfg::kDyPlaneBytes;
-      uint32_t use = 0, iuse = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
-        const int pass = item / p.chunks, chunk = item % p.chunks;
-        int mh, g, u0, u1;
-        decode_pass(pass, mh, g, u0, u1);
-        const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
-        ptx::mbar_wait(BAR(5), (iuse & 1) ^ 1);
+    // whole warp runs the uniform control flow / descriptor arithmetic; one elected lane issues
+    const bool leader = ptx::elect_one();
+    const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, NPAD, 1, 1);
+    const uint32_t a_lbo16 = p.dbg_swap ? (uint32_t)Cfg::kGroupBytes >> 4 : 8u;
+    const uint32_t a_hi = ptx::desc_hi(p.dbg_swap ? 128u : (uint32_t)Cfg::kGroupBytes);
+    const uint32_t b_lbo16 = p.dbg_swap ? (uint32_t)Cfg::kDyPlaneBytes >> 4 : 8u;
+    const uint32_t b_hi = ptx::desc_hi(p.dbg_swap ? 128u : (uint32_t)Cfg::kDyPlaneBytes);
+    uint32_t use = 0, iuse = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
+      const int pass = item / p.chunks, chunk = item % p.chunks;
+      int mh, g, u0, u1;
+      decode_pass(pass, mh, g, u0, u1);
+      const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+      ptx::mbar_wait(BAR(5), (iuse & 1) ^ 1);
+      ptx::tc_fence_after();
+      for (int t = t0; t < t1; ++t, ++use) {
+        const uint32_t b = use & 1, ph = (use >> 1) & 1;
+        ptx::mbar_wait(BAR(b), ph);
         ptx::tc_fence_after();
-        for (int t = t0; t < t1; ++t, ++use) {
-          const uint32_t b = use & 1, ph = (use >> 1) & 1;
-          ptx::mbar_wait(BAR(b), ph);
-          ptx::tc_fence_after();
-          const uint64_t a_desc0 = ptx::make_desc(ptx::smem_u32(x_smem + b * Cfg::kXBytes), a_lbo, a_sbo);
-          const uint64_t b_desc0 = ptx::make_desc(ptx::smem_u32(dy_smem + b * Cfg::kDyBytes), b_lbo, b_sbo);
+        const uint32_t a_lo0 = ptx::desc_lo(ptx::smem_u32(x_smem + b * Cfg::kXBytes), a_lbo16);
+        const uint32_t b_lo0 = ptx::desc_lo(ptx::smem_u32(dy_smem + b * Cfg::kDyBytes), b_lbo16);
 #pragma unroll 1
-          for (int hrow = 0; hrow < TH; ++hrow) {
-            const uint64_t b_desc = b_desc0 + (uint64_t)(hrow * kWgTileW);
-            const uint32_t acc = (t != t0 || hrow != 0) ? 1u : 0u;
+        for (int hrow = 0; hrow < TH; ++hrow) {
+          const uint32_t b_lo = b_lo0 + (uint32_t)(hrow * kWgTileW);
+          const uint32_t acc = (t != t0 || hrow != 0) ? 1u : 0u;
+          uint32_t kh = (uint32_t)u0 / 5u, kw = (uint32_t)u0 % 5u;
 #pragma unroll 1
-            for (int u = u0; u < u1; ++u) {
-              const int kh = u / 5, kw = u % 5;
-              const uint64_t a_desc = a_desc0 + (uint64_t)((hrow + kh) * (kWgTileW + 4) + kw);
-              ptx::mma_bf16(tmem_base + (uint32_t)((u - u0) * NPAD), a_desc, b_desc, idesc, acc);
-            }
+          for (int u = u0; u < u1; ++u) {
+            const uint32_t a_lo = a_lo0 + (uint32_t)(hrow + kh) * (uint32_t)(kWgTileW + 4) + kw;
+            if (leader) ptx::mma_bf16_split(tmem_u + (uint32_t)((u - u0) * NPAD), a_lo, a_hi, b_lo, b_hi, idesc, acc);
+            if (++kw == 5u) { kw = 0u; ++kh; }
           }
-          ptx::mma_commit(BAR(2 + b));
         }
-        ptx::mma_commit(BAR(4));
+        if (leader) ptx::mma_commit(BAR(2 + b));
       }
+      if (leader) ptx::mma_commit(BAR(4));
+      __syncwarp();
     }
   } else if (warp >= 4) {
     const int q4 = warp - 4;
@@ -580,28 +598,90 @@ __global__ void __launch_bounds__(256) k2s2_unpack_kernel(const float* __restric
 }
 
 // ---- weight packing ----------------------------------------------------------------------------------
-// packed[chunk][hk = kh*5+kw][k8][kdr = 4-kd][oc][j] (bf16), rc = chunk*16 + k8*8 + j
+// packed[chunk][hk = kh*5+kw][k8][kdr = 4-kd][oc][j] (bf16), rc = chunk*16 + k8*8 + j.
+// One block per (oc, chunk): the 16 x 125 f32 slab is read with coalesced rows into shared memory, then each
+// thread emits one 16-byte vector of 8 reduction channels (mode 1 = input-gradient operand: reduction over the
+// conv's Cout, produces its Cin, taps mirrored).
 __global__ void __launch_bounds__(256) pack_k5_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed,
                                                       int cout, int cin, int mode, int cin_pad, int cout_pad) {
-  const int64_t total = (int64_t)cin_pad * kNumTaps * cout_pad;
+  __shared__ float slab[16][kNumTaps + 1];
+  const int oc = blockIdx.x, chunk = blockIdx.y;
+  for (int i = threadIdx.x; i < 16 * kNumTaps; i += 256) {
+    const int r = i / kNumTaps, tap = i % kNumTaps;
+    const int rc = chunk * 16 + r;
+    float v = 0.f;
+    if (mode == 0) {
+      if (oc < cout && rc < cin) v = __ldg(w + ((int64_t)oc * cin + rc) * kNumTaps + tap);
+    } else {
+      if (rc < cout && oc < cin) v = __ldg(w + ((int64_t)rc * cin + oc) * kNumTaps + (kNumTaps - 1 - tap));
+    }
+    slab[r][tap] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 250) {
+    const int kdr = threadIdx.x % 5, k8 = (threadIdx.x / 5) & 1, hk = threadIdx.x / 10;
+    const int tap = (4 - kdr) * 25 + hk;  // natural tap index kd*25 + kh*5 + kw
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = slab[k8 * 8 + j][tap];
+    const int64_t o = ((((int64_t)chunk * 25 + hk) * 2 + k8) * 5 + kdr) * cout_pad + oc;
+    Vec8<__nv_bfloat16>::store(packed + o * 8, v);
+  }
+}
+
+// ---- w-folded 5x5x1 convolutions (narrow layers: in_tr 1->16, out_tr 32->classes) -------------------------------
+// A 5x5x5 conv whose input (fold_side 0) or output (fold_side 1) has <= 3 real channels wastes a 16-wide K chunk / N
+// block per kw tap.  Folding the 5 kw taps into the padded channels turns it into ONE 5x5x1 conv (5x fewer MMAs):
+//   fold_side 0:  y = conv551(F(x), Wf),        F(x)[v,(j,ci)] = x[v + (j-2) e_w, ci],  Wf[co,(j,ci),kd,kh] = W[co,ci,kd,kh,j]
+//   fold_side 1:  P = conv551(x, Wp),           Wp[(j,co),ci,kd,kh] = W[co,ci,kd,kh,j],  y[v,co] = sum_j P[v + (j-2) e_w,(j,co)]
+// Logical (folded) weight element; cin / cout are the REAL channel counts of the 5-D weight.
+__device__ __forceinline__ float fold_w_elem(const float* __restrict__ w, int cout, int cin, int fold_side, int oc,
+                                             int rc, int tap25) {
+  int co, ci, jw;
+  if (fold_side == 0) {
+    if (oc >= cout || rc >= 5 * cin) return 0.f;
+    co = oc; jw = rc / cin; ci = rc % cin;
+  } else {
+    if (oc >= 5 * cout || rc >= cin) return 0.f;
+    jw = oc / cout; co = oc % cout; ci = rc;
+  }
+  return __ldg(w + ((int64_t)co * cin + ci) * kNumTaps + tap25 * 5 + jw);
+}
+
+// packed[chunk][kh][k8][kdr = 4-kd][oc][j] (bf16), rc = chunk*16 + k8*8 + j;  mode 1 = input-gradient operand
+__global__ void __launch_bounds__(256) pack_k551_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed,
+                                                        int cout, int cin, int mode, int fold_side, int cin_pad,
+                                                        int cout_pad) {
+  const int64_t total = (int64_t)cin_pad * 25 * cout_pad;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int j = (int)(i & 7);
     int64_t r = i >> 3;
     const int oc = (int)(r % cout_pad); r /= cout_pad;
     const int kdr = (int)(r % 5); r /= 5;
     const int k8 = (int)(r & 1); r >>= 1;
-    const int hk = (int)(r % 25);
-    const int chunk = (int)(r / 25);
-    const int tap = (4 - kdr) * 25 + hk;  // natural tap index kd*25 + kh*5 + kw
+    const int kh = (int)(r % 5);
+    const int chunk = (int)(r / 5);
+    const int tap25 = (4 - kdr) * 5 + kh;
     const int rc = chunk * 16 + k8 * 8 + j;
-    float v = 0.f;
-    if (mode == 0) {
-      if (oc < cout && rc < cin) v = __ldg(w + ((int64_t)oc * cin + rc) * kNumTaps + tap);
-    } else {
-      // input-gradient operand: reduction over the conv's Cout, produces its Cin, taps mirrored
-      if (rc < cout && oc < cin) v = __ldg(w + ((int64_t)rc * cin + oc) * kNumTaps + (kNumTaps - 1 - tap));
-    }
+    const float v = mode == 0 ? fold_w_elem(w, cout, cin, fold_side, oc, rc, tap25)
+                              : fold_w_elem(w, cout, cin, fold_side, rc, oc, 24 - tap25);
     packed[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// dw[co][ci][kd][kh][jw] += ws[kd*5+kh][oc][rc]   (ws strides: cout_f x cin_f = folded channel counts)
+__global__ void __launch_bounds__(256) wgrad551_unpack_kernel(const float* __restrict__ ws, float* __restrict__ dw,
+                                                              int cout, int cin, int fold_side) {
+  const int64_t total = (int64_t)cout * cin * kNumTaps;
+  const int cout_f = fold_side == 0 ? cout : 5 * cout, cin_f = fold_side == 0 ? 5 * cin : cin;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % kNumTaps);
+    const int64_t r = i / kNumTaps;
+    const int ci = (int)(r % cin), co = (int)(r / cin);
+    const int jw = tap % 5, tap25 = tap / 5;
+    const int oc = fold_side == 0 ? co : jw * cout + co;
+    const int rc = fold_side == 0 ? jw * cin + ci : ci;
+    dw[i] += ws[((int64_t)tap25 * cout_f + oc) * cin_f + rc];
   }
 }
 
@@ -771,23 +851,24 @@ int msb_conv_k5_pack(const float* w, void* packed, int cout, int cin, int mode, 
   MSB_REQUIRE(cin_pad % 16 == 0 && cout_pad % 16 == 0, "msb_conv_k5_pack: padded channel counts must be multiples of 16");
   MSB_REQUIRE(mode == 0 ? (cin_pad >= cin && cout_pad >= cout) : (cin_pad >= cout && cout_pad >= cin),
               "msb_conv_k5_pack: padded channel counts too small");
-  const int64_t total = (int64_t)cin_pad * kNumTaps * cout_pad;
-  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  pack_k5_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, mode,
-                                                        cin_pad, cout_pad);
+  pack_k5_kernel<<<dim3(cout_pad, cin_pad / 16), 256, 0, as_stream(stream)>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, mode, cin_pad, cout_pad);
   MSB_LAUNCH_OK();
   return MSB_OK;
 }
 
-int msb_conv_k5_fwd(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
-                    msb_dim3 dims, int accumulate, const float* ch_scale, int groups, double* sums, void* stream) {
-  MSB_REQUIRE(view_ok(x) && view_ok(out) && x.dtype == MSB_BF16 && out.dtype == MSB_BF16 && packed && n > 0,
-              "msb_conv_k5_fwd: bf16 B8 views required");
-  MSB_REQUIRE(dims.d > 0 && dims.h > 0 && dims.w > 0, "msb_conv_k5_fwd: bad dims");
-  MSB_REQUIRE(x.c % 16 == 0, "msb_conv_k5_fwd: input channels must be a multiple of 16 (pad the buffer)");
-  MSB_REQUIRE(cout > 0 && cout <= out.c && out.c <= 256, "msb_conv_k5_fwd: cout must fit the output view (<= 256)");
-  MSB_REQUIRE(groups == 1 || groups == n, "msb_conv_k5_fwd: groups must be 1 or n");
-  const int npad = pad16(out.c);
+int msb_conv_k5_out_pad(int cout_view);
+
+static int conv_k5_fwd_impl(const char* who, msb_tensor x, const void* packed, const float* bias, int cout,
+                           msb_tensor out, int n, msb_dim3 dims, int accumulate, const float* ch_scale, int groups,
+                           double* sums, int kw_taps, void* stream) {
+  MSB_REQUIRE(view_ok(x) && view_ok(out) && x.dtype == MSB_BF16 && packed && n > 0, "%s: bf16 B8 input view required", who);
+  MSB_REQUIRE(out.dtype == MSB_BF16 || (kw_taps == 1 && !accumulate && sums == nullptr),
+              "%s: f32 output only for the 5x5x1 kernel without accumulate / BN sums", who);
+  MSB_REQUIRE(dims.d > 0 && dims.h > 0 && dims.w > 0, "%s: bad dims", who);
+  MSB_REQUIRE(x.c % 16 == 0, "%s: input channels must be a multiple of 16 (pad the buffer)", who);
+  MSB_REQUIRE(cout > 0 && cout <= out.c && out.c <= 256, "%s: cout must fit the output view (<= 256)", who);
+  MSB_REQUIRE(groups == 1 || groups == n, "%s: groups must be 1 or n", who);
   const int64_t S = (int64_t)dims.d * dims.h * dims.w;
   FwdParams p;
   p.n = n; p.cin_pad = x.c; p.cout_real = cout; p.out_c8 = out.c / 8;
@@ -797,6 +878,7 @@ int msb_conv_k5_fwd(msb_tensor x, const void* packed, const float* bias, int cou
   p.x_c8_total = (int)(x.n_stride / (S * 8));
   p.packed = packed; p.bias = bias; p.out = out; p.accumulate = accumulate; p.ch_scale = ch_scale;
   p.groups = groups; p.sums = sums; p.sums_c = out.c; p.dbg_swap = 0;
+  p.kw_taps = kw_taps; p.out_f32 = out.dtype == MSB_F32;
   cudaStream_t st = as_stream(stream);
   const int npad_sel = msb_conv_k5_out_pad(out.c);
   // NOTE: the packed operand must have been built with cout_pad == npad_sel.
@@ -804,7 +886,10 @@ int msb_conv_k5_fwd(msb_tensor x, const void* packed, const float* bias, int cou
   // MMA produces J output planes from one activation window (see FwdCfg)
   const bool stack = g_debug_flags[3] == 0;
   switch (npad_sel) {
-    case 16: return stack ? launch_fwd<16, 4, 4>(x, dims, p, st) : launch_fwd<16, 4>(x, dims, p, st);
+    case 16:
+      // the 5x5x1 kernel issues 5x fewer MMAs per halo tile: deeper d-blocks keep the halo re-fetch (TD+4)/TD low
+      if (kw_taps == 1 && stack && dims.d >= 8) return launch_fwd<16, 8, 4>(x, dims, p, st);
+      return stack ? launch_fwd<16, 4, 4>(x, dims, p, st) : launch_fwd<16, 4>(x, dims, p, st);
     case 32: return stack ? launch_fwd<32, 4, 4>(x, dims, p, st) : launch_fwd<32, 4>(x, dims, p, st);
     case 64: return stack ? launch_fwd<64, 4, 2>(x, dims, p, st) : launch_fwd<64, 4>(x, dims, p, st);
     case 128: return launch_fwd<128, 2>(x, dims, p, st);
@@ -812,7 +897,17 @@ int msb_conv_k5_fwd(msb_tensor x, const void* packed, const float* bias, int cou
   }
 }
 
-int msb_conv_k5_out_pad(int cout_view);
+int msb_conv_k5_fwd(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
+                    msb_dim3 dims, int accumulate, const float* ch_scale, int groups, double* sums, void* stream) {
+  return conv_k5_fwd_impl("msb_conv_k5_fwd", x, packed, bias, cout, out, n, dims, accumulate, ch_scale, groups, sums, 5,
+                          stream);
+}
+
+int msb_conv_k551_fwd(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
+                      msb_dim3 dims, int accumulate, const float* ch_scale, int groups, double* sums, void* stream) {
+  return conv_k5_fwd_impl("msb_conv_k551_fwd", x, packed, bias, cout, out, n, dims, accumulate, ch_scale, groups, sums,
+                          1, stream);
+}
 
 size_t msb_conv_k5_wgrad_workspace_bytes(int cin, int cout) { return (size_t)kNumTaps * cin * cout * sizeof(float); }
 
@@ -864,6 +959,65 @@ int msb_conv_k5_wgrad(msb_tensor x, msb_tensor dy, float* dw, float* dbias, int 
     const dim3 grid((unsigned)((S + 8191) / 8192), dy.c / 8, n);
     channel_sum_bf16_kernel<<<grid, 256, 0, st>>>(dy, S, cout, dbias);
   }
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+size_t msb_conv_k551_packed_bytes(int cin_pad, int cout_pad) {
+  return (size_t)cin_pad * 25 * cout_pad * sizeof(__nv_bfloat16);
+}
+
+int msb_conv_k551_pack(const float* w, void* packed, int cout, int cin, int mode, int fold_side, int cin_pad,
+                       int cout_pad, void* stream) {
+  MSB_REQUIRE(w && packed && cout > 0 && cin > 0 && (mode == 0 || mode == 1) && (fold_side == 0 || fold_side == 1),
+              "msb_conv_k551_pack: bad arguments");
+  MSB_REQUIRE(cin_pad % 16 == 0 && cout_pad % 16 == 0, "msb_conv_k551_pack: padded channel counts must be multiples of 16");
+  const int cin_f = fold_side == 0 ? 5 * cin : cin, cout_f = fold_side == 0 ? cout : 5 * cout;
+  MSB_REQUIRE(mode == 0 ? (cin_pad >= cin_f && cout_pad >= cout_f) : (cin_pad >= cout_f && cout_pad >= cin_f),
+              "msb_conv_k551_pack: padded channel counts too small for the folded channels");
+  const int64_t total = (int64_t)cin_pad * 25 * cout_pad;
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  pack_k551_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, mode,
+                                                          fold_side, cin_pad, cout_pad);
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+size_t msb_conv_k551_wgrad_workspace_bytes(int cin, int cout, int fold_side) {
+  const int cin_f = fold_side == 0 ? 5 * cin : cin, cout_f = fold_side == 0 ? cout : 5 * cout;
+  return (size_t)25 * cin_f * cout_f * sizeof(float);
+}
+
+int msb_conv_k551_wgrad(msb_tensor x, msb_tensor dy, float* dw, int cout, int cin, int fold_side, int n, msb_dim3 dims,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  MSB_REQUIRE(view_ok(x) && view_ok(dy) && x.dtype == MSB_BF16 && dy.dtype == MSB_BF16 && dw && n > 0,
+              "msb_conv_k551_wgrad: bf16 B8 views required");
+  MSB_REQUIRE(dims.d > 0 && dims.h > 0 && dims.w > 0, "msb_conv_k551_wgrad: bad dims");
+  MSB_REQUIRE(fold_side == 0 || fold_side == 1, "msb_conv_k551_wgrad: fold_side must be 0 or 1");
+  MSB_REQUIRE(x.c == 16 || x.c == 32 || x.c == 64 || x.c == 128, "msb_conv_k551_wgrad: input view must have 16..128 channels");
+  const int cin_f = fold_side == 0 ? 5 * cin : cin, cout_f = fold_side == 0 ? cout : 5 * cout;
+  MSB_REQUIRE(cin > 0 && cout > 0 && cin_f <= x.c && cout_f <= dy.c, "msb_conv_k551_wgrad: folded channels exceed the views");
+  const size_t need = msb_conv_k551_wgrad_workspace_bytes(cin, cout, fold_side);
+  MSB_REQUIRE(workspace && workspace_bytes >= need, "msb_conv_k551_wgrad: workspace too small (%zu < %zu)",
+              workspace_bytes, need);
+  cudaStream_t st = as_stream(stream);
+  MSB_CUDA_OK(cudaMemsetAsync(workspace, 0, need, st));
+  float* ws = reinterpret_cast<float*>(workspace);
+  int rc = launch_wgrad_v2(x, dy, cout_f, cin_f, n, dims, ws, st, 1);
+  if (rc == MSB_ERR_UNSUPPORTED) set_error("msb_conv_k551_wgrad: shape not supported by the kh-stacked kernel");
+  if (rc) return rc;
+  const int64_t total = (int64_t)cout * cin * kNumTaps;
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  wgrad551_unpack_kernel<<<blocks, 256, 0, st>>>(ws, dw, cout, cin, fold_side);
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+int msb_channel_sum(msb_tensor x, int c_real, int n, int64_t s, float* out, void* stream) {
+  MSB_REQUIRE(view_ok(x) && x.dtype == MSB_BF16 && out && n > 0 && s > 0 && c_real > 0 && c_real <= x.c,
+              "msb_channel_sum: bf16 B8 view required");
+  const dim3 grid((unsigned)((s + 8191) / 8192), (unsigned)((c_real + 7) / 8), n);
+  channel_sum_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, s, c_real, out);
   MSB_LAUNCH_OK();
   return MSB_OK;
 }

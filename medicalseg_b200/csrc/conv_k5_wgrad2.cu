@@ -31,6 +31,7 @@ struct Wg2Params {
   int units_per_pass, passes_per_group, num_passes, chunks, tiles_per_chunk, total_tiles;
   int dy_stage_bytes;
   float* ws;
+  int kw_taps, kw_base;                  // 5 / 0 for the 5x5x5 kernel, 1 / 2 (centre tap only) for the 5x5x1 kernel
 };
 
 __global__ void __launch_bounds__(256, 1)
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(256, 1)
     g = r % p.kd_groups;
     mh = r / p.kd_groups;
     kw0 = pg * p.units_per_pass;
-    kw1 = min(5, kw0 + p.units_per_pass);
+    kw1 = min(p.kw_taps, kw0 + p.units_per_pass);
   };
 
   if (warp == 0) {
@@ -101,37 +102,44 @@ __global__ void __launch_bounds__(256, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16(128, p.npad, 1, 1);
-      const uint32_t b_row16 = (uint32_t)(p.dyp * kW2RowBytes) >> 4;  // one h row of the dY tile, 16-byte units
-      uint32_t use = 0, iuse = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
-        const int pass = item / p.chunks, chunk = item % p.chunks;
-        int mh, g, jg, kw0, kw1;
-        decode_pass(pass, mh, g, jg, kw0, kw1);
-        const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
-        ptx::mbar_wait(BAR(7), (iuse & 1) ^ 1);
+    // whole warp runs the uniform control flow / descriptor arithmetic; one elected lane issues (see conv_k5_umma.cu)
+    const bool leader = ptx::elect_one();
+    const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);
+    const uint32_t idesc = ptx::make_idesc_bf16(128, p.npad, 1, 1);
+    constexpr uint32_t a_hi = ptx::desc_hi(kW2GroupBytes), b_hi = ptx::desc_hi(kW2RowBytes);
+    const uint32_t b_row16 = (uint32_t)(p.dyp * kW2RowBytes) >> 4;  // one h row of the dY tile, 16-byte units
+    const uint32_t npad = (uint32_t)p.npad;
+    uint32_t use = 0, iuse = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
+      const int pass = item / p.chunks, chunk = item % p.chunks;
+      int mh, g, jg, kw0, kw1;
+      decode_pass(pass, mh, g, jg, kw0, kw1);
+      const int nkw = kw1 - kw0;
+      const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+      ptx::mbar_wait(BAR(7), (iuse & 1) ^ 1);
+      ptx::tc_fence_after();
+      for (int t = t0; t < t1; ++t, ++use) {
+        const uint32_t s = use % kW2Stages, ph = (use / kW2Stages) & 1;
+        ptx::mbar_wait(BAR(s), ph);
         ptx::tc_fence_after();
-        for (int t = t0; t < t1; ++t, ++use) {
-          const uint32_t s = use % kW2Stages, ph = (use / kW2Stages) & 1;
-          ptx::mbar_wait(BAR(s), ph);
-          ptx::tc_fence_after();
-          const uint64_t a_desc0 = ptx::make_desc(ptx::smem_u32(x_smem + s * kW2XBytes), 128u, kW2GroupBytes);
-          const uint64_t b_desc0 = ptx::make_desc(ptx::smem_u32(dy_smem + s * p.dy_stage_bytes), 128u, kW2RowBytes);
-#pragma unroll 1
-          for (int u = 0; u < kW2TileH; ++u) {
-            const uint64_t b_desc = b_desc0 + (uint64_t)((u + jg * p.jh) * b_row16);
-            const uint32_t acc = (t != t0 || u != 0) ? 1u : 0u;
-#pragma unroll 1
-            for (int kw = kw0; kw < kw1; ++kw) {
-              const uint64_t a_desc = a_desc0 + (uint64_t)(u * (kW2TileW + 4) + kw);
-              ptx::mma_bf16(tmem_base + (uint32_t)((kw - kw0) * p.npad), a_desc, b_desc, idesc, acc);
-            }
+        const uint32_t a_lo0 = ptx::desc_lo(ptx::smem_u32(x_smem + s * kW2XBytes), 8u) + (uint32_t)(kw0 + p.kw_base);
+        const uint32_t b_lo0 =
+            ptx::desc_lo(ptx::smem_u32(dy_smem + s * p.dy_stage_bytes), 8u) + (uint32_t)(jg * p.jh) * b_row16;
+#pragma unroll
+        for (int u = 0; u < kW2TileH; ++u) {
+          const uint32_t acc = (t != t0 || u != 0) ? 1u : 0u;
+          const uint32_t b_lo = b_lo0 + (uint32_t)u * b_row16;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            if (k < nkw && leader)
+              ptx::mma_bf16_split(tmem_u + (uint32_t)k * npad, a_lo0 + (uint32_t)(u * (kW2TileW + 4) + k), a_hi, b_lo,
+                                  b_hi, idesc, acc);
           }
-          ptx::mma_commit(BAR(3 + s));
         }
-        ptx::mma_commit(BAR(6));
+        if (leader) ptx::mma_commit(BAR(3 + s));
       }
+      if (leader) ptx::mma_commit(BAR(6));
+      __syncwarp();
     }
   } else if (warp >= 4) {
     const int q4 = warp - 4;
@@ -162,7 +170,7 @@ __global__ void __launch_bounds__(256, 1)
               const int jj = col / cw, co = col % cw;
               const int jh = jg * p.jh + jj;  // dY row shift: v_h = u_h - 2 + jh  <=>  kh = 4 - jh
               if (jj < p.jh && jh < 5 && co < p.cout_real) {
-                const int tap = kd * 25 + (4 - jh) * 5 + kw;
+                const int tap = (kd * 5 + (4 - jh)) * p.kw_taps + kw;
                 atomicAdd(p.ws + ((int64_t)tap * p.cout_real + co) * p.cin_real + ci, acc[j]);
               }
             }
@@ -183,7 +191,7 @@ __global__ void __launch_bounds__(256, 1)
 }
 
 int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin, int n, msb_dim3 dims, float* ws,
-                    cudaStream_t st) {
+                    cudaStream_t st, int kw_taps) {
   const int dyp = (cout + 7) / 8;
   if (dyp > dy.c / 8 || dyp > 10) return MSB_ERR_UNSUPPORTED;  // wider outputs: per-tap kernel (N = Cout already wide)
   // stack as many kh shifts per MMA as fit N <= 256, preferring the split of 5 with the least waste
@@ -206,10 +214,11 @@ int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin
   p.qm = 128 / p.cin_m;
   const int qeff = p.qm < 5 ? p.qm : 5;
   p.kd_groups = (5 + qeff - 1) / qeff;
+  p.kw_taps = kw_taps; p.kw_base = kw_taps == 5 ? 0 : 2;
   int amax = 512 / npad;
-  if (amax > 5) amax = 5;
-  p.passes_per_group = (5 + amax - 1) / amax;
-  p.units_per_pass = (5 + p.passes_per_group - 1) / p.passes_per_group;
+  if (amax > kw_taps) amax = kw_taps;
+  p.passes_per_group = (kw_taps + amax - 1) / amax;
+  p.units_per_pass = (kw_taps + p.passes_per_group - 1) / p.passes_per_group;
   p.num_passes = p.mhalves * p.kd_groups * p.jgroups * p.passes_per_group;
   p.total_tiles = n * dims.d * p.tiles_h * p.tiles_w;
   int chunks = (2 * kNumSMs + p.num_passes - 1) / p.num_passes;

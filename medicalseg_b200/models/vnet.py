@@ -236,6 +236,53 @@ class _K5:
             ops.conv_strided_wgrad(x, dy, dw, db, (5, 5, 5), (1, 1, 1), (2, 2, 2), False, self.cin, self.cout)
 
 
+class _K551:
+    """w-folded 5x5x1 form of a 5x5x5 conv with <= 3 real channels on one side (bf16 tensor-core path only):
+    fold_side 0 = input folded (in_tr.conv1, vnet.py:67-68), 1 = output folded (out_tr.conv1, vnet.py:165-166).
+    See include/medseg_b200.h, "w-folded 5x5x1 variant"."""
+
+    def __init__(self, eng, conv: _Conv, cin, cout, fold_side):
+        self.eng, self.conv, self.cin, self.cout, self.fold_side = eng, conv, cin, cout, fold_side
+        self.cin_f = 5 * cin if fold_side == 0 else cin
+        self.cout_f = cout if fold_side == 0 else 5 * cout
+        assert self.cin_f <= 16 or fold_side == 1
+        assert self.cout_f <= 16 or fold_side == 0
+        self.packed_f = self.packed_b = None
+        self.packed_version = -1
+
+    def _pack(self):
+        eng, st = self.eng, self.eng.store
+        if self.packed_version == eng.param_version and self.packed_f is not None:
+            return
+        w = st.view(self.conv.weight)
+        self.f_cin_pad, self.f_cout_pad = _pad(self.cin_f, 16), ops.k5_out_pad(_pad(self.cout_f, 8))
+        if self.packed_f is None:
+            self.packed_f = torch.empty(ops.k551_packed_bytes(self.f_cin_pad, self.f_cout_pad), dtype=torch.uint8,
+                                        device=w.device)
+        ops.k551_pack(w, self.packed_f, self.cout, self.cin, 0, self.fold_side, self.f_cin_pad, self.f_cout_pad)
+        if self.fold_side == 1:  # input gradient: reduces over the folded outputs, produces the real inputs
+            self.b_cin_pad, self.b_cout_pad = _pad(self.cout_f, 16), ops.k5_out_pad(_pad(self.cin_f, 8))
+            if self.packed_b is None:
+                self.packed_b = torch.empty(ops.k551_packed_bytes(self.b_cin_pad, self.b_cout_pad),
+                                            dtype=torch.uint8, device=w.device)
+            ops.k551_pack(w, self.packed_b, self.cout, self.cin, 1, self.fold_side, self.b_cin_pad, self.b_cout_pad)
+        self.packed_version = eng.param_version
+
+    def fwd(self, x: B8, out: B8, bias, groups=1, sums=None):
+        """x: (folded) input view; out: 16-channel folded output (fold_side 1, f32) or the real output (fold_side 0)"""
+        self._pack()
+        ops.k551_fwd(x, self.packed_f, bias, self.cout_f, out, False, None, groups, sums)
+
+    def bwd_data(self, dp: B8, dx: B8):
+        self._pack()
+        ops.k551_fwd(dp, self.packed_b, None, self.cin_f, dx, False, None, 1, None)
+
+    def wgrad(self, x: B8, dy: B8):
+        st = self.eng.store
+        ws = self.eng.workspace(ops.k551_wgrad_workspace_bytes(self.cin, self.cout, self.fold_side))
+        ops.k551_wgrad(x, dy, st.grad_view(self.conv.weight), self.cout, self.cin, self.fold_side, ws)
+
+
 class LUConv(_Module):  # vnet.py:32-43
     def __init__(self, eng, prefix, nchan):
         super().__init__(prefix)
@@ -256,6 +303,7 @@ class InputTransition(_Module):  # vnet.py:57-79
         self.bn1 = _BN(st, prefix + ".bn1", 16, 16)
         self.relu1 = _PReLU(st, prefix + ".relu1", 16, 16)
         self.act = _BnAct(eng, self.bn1, self.relu1)
+        self.k551 = _K551(eng, self.conv1, in_channels, 16, 0) if eng.dtype == torch.bfloat16 else None
 
 
 class DownTransition(_Module):  # vnet.py:82-113
@@ -299,7 +347,10 @@ class OutputTransition(_Module):  # vnet.py:159-175
     def __init__(self, eng, prefix, in_channels, num_classes):
         super().__init__(prefix)
         st = eng.store
-        self.c, self.cp = num_classes, _pad(num_classes, 16)
+        # folded path (<= 3 classes, bf16): the 5 kw taps ride in the padding of a 16-channel block and the
+        # BN/PReLU/1x1 tail works on a single 8-channel plane
+        self.folded = eng.dtype == torch.bfloat16 and num_classes <= 3
+        self.c, self.cp = num_classes, (8 if self.folded else _pad(num_classes, 16))
         self.conv1 = _Conv(st, prefix + ".conv1", (num_classes, in_channels, 5, 5, 5), num_classes,
                            ("conv", in_channels * 125), self.cp)
         self.bn1 = _BN(st, prefix + ".bn1", num_classes, self.cp)
@@ -307,6 +358,7 @@ class OutputTransition(_Module):  # vnet.py:159-175
                            ("conv", num_classes))
         self.relu1 = _PReLU(st, prefix + ".relu1", num_classes, self.cp)
         self.k5 = _K5(eng, self.conv1, in_channels, num_classes)
+        self.k551 = _K551(eng, self.conv1, in_channels, num_classes, 1) if self.folded else None
         self.act = _BnAct(eng, self.bn1, self.relu1)
 
 
@@ -476,6 +528,11 @@ class VNet(_Module):
         else:
             ops.conv_strided_wgrad(big, small, dw, dbias, kernel, stride, (0, 0, 0), bias_from_big)
 
+    def workspace(self, nbytes):
+        if self._wg_ws is None or self._wg_ws.numel() < nbytes:
+            self._wg_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._wg_ws
+
     def wgrad_workspace(self, cin, cout):
         need = ops.k5_wgrad_workspace_bytes(cin, cout)
         if self._wg_ws is None or self._wg_ws.numel() < need:
@@ -536,7 +593,13 @@ class VNet(_Module):
         it = self.in_tr
         y0 = self._new(n, 16, dims[0])
         s0 = sums(16)
-        ops.conv_in_fwd(x, st.view(it.conv1.weight), st.view(it.conv1.bias), y0, g, s0)
+        if it.k551 is not None:
+            xf = self._new(n, 16, dims[0])
+            ops.fold_w_f32(x, self.in_channels, xf, 1)
+            it.k551.fwd(xf, y0, st.view(it.conv1.bias), g, s0)
+            tape["xf"] = xf
+        else:
+            ops.conv_in_fwd(x, st.view(it.conv1.weight), st.view(it.conv1.bias), y0, g, s0)
         out16 = xcat32.view(16, 16)
         it.act.fwd(y0, out16, s0, tile=x, tile_c=self.in_channels)
 
@@ -616,7 +679,12 @@ class VNet(_Module):
         cp = ot.cp
         yo = self._new(n, cp, dims[0])
         so = sums(cp)
-        ot.k5.fwd(tape["u32"]["out"], yo, so)
+        if ot.folded:
+            pf = B8(n, 16, dims[0], torch.float32, device=self.device)
+            ot.k551.fwd(tape["u32"]["out"], pf, None)
+            ops.unfold_w(pf, st.view(ot.conv1.bias), ot.c, yo, g, so)
+        else:
+            ot.k5.fwd(tape["u32"]["out"], yo, so)
         ao = self._new(n, cp, dims[0])
         ot.act.fwd(yo, ao, so)
         logits = torch.empty((n, self.num_classes, *dims[0]), dtype=torch.float32, device=self.device)
@@ -651,7 +719,14 @@ class VNet(_Module):
         dyo = self._new(n, ot.cp, dims[0])
         ot.act.bwd(da, dyo)
         g_u32 = self._new(n, 32, dims[0])
-        ot.k5.bwd(tape["u32"]["out"], dyo, g_u32)
+        if ot.folded:
+            dpf = self._new(n, 16, dims[0])
+            ops.fold_w(dyo, ot.c, dpf, -1)
+            ot.k551.bwd_data(dpf, g_u32)
+            ot.k551.wgrad(tape["u32"]["out"], dpf)
+            ops.channel_sum(dyo, ot.c, st.grad_view(ot.conv1.bias))
+        else:
+            ot.k5.bwd(tape["u32"]["out"], dyo, g_u32)
         self._fire(ot)
 
         def lu_chain_bwd(tr, rec, g_out: B8, g_first_in: B8, lvl: int, first_scale):
@@ -722,7 +797,11 @@ class VNet(_Module):
         it = self.in_tr
         dy0 = self._new(n, 16, dims[0])
         it.act.bwd(g_out16, dy0)
-        ops.conv_in_wgrad(x, dy0, st.grad_view(it.conv1.weight), st.grad_view(it.conv1.bias))
+        if it.k551 is not None:
+            it.k551.wgrad(tape["xf"], dy0)
+            ops.channel_sum(dy0, 16, st.grad_view(it.conv1.bias))
+        else:
+            ops.conv_in_wgrad(x, dy0, st.grad_view(it.conv1.weight), st.grad_view(it.conv1.bias))
         self._fire(it)
         self._tape = None
 

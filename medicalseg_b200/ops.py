@@ -187,6 +187,45 @@ def k5_wgrad(x: B8, dy: B8, dw, dbias, cout, cin, workspace: torch.Tensor):
          workspace.numel() * workspace.element_size(), _stream())
 
 
+# ---- w-folded 5x5x1 convs (in_tr / out_tr) ------------------------------------------------------------------
+def fold_w_f32(x: torch.Tensor, c_real: int, out: B8, sign: int):
+    call("msb_fold_w_f32", _ptr(x), c_real, out.mt, out.n, dim3(out.dims), sign, _stream())
+
+
+def fold_w(x: B8, c_real: int, out: B8, sign: int):
+    call("msb_fold_w", x.mt, c_real, out.mt, out.n, dim3(out.dims), sign, _stream())
+
+
+def unfold_w(p: B8, bias, c_real: int, out: B8, groups=1, sums=None):
+    call("msb_unfold_w", p.mt, _ptr(bias), c_real, out.mt, out.n, dim3(out.dims), groups, _ptr(sums), _stream())
+
+
+def k551_packed_bytes(cin_pad: int, cout_pad: int) -> int:
+    return call("msb_conv_k551_packed_bytes", cin_pad, cout_pad)
+
+
+def k551_pack(w, packed, cout, cin, mode, fold_side, cin_pad, cout_pad):
+    call("msb_conv_k551_pack", _ptr(w), _ptr(packed), cout, cin, mode, fold_side, cin_pad, cout_pad, _stream())
+
+
+def k551_fwd(x: B8, packed, bias, cout, out: B8, accumulate=False, ch_scale=None, groups=1, sums=None):
+    call("msb_conv_k551_fwd", x.mt, _ptr(packed), _ptr(bias), cout, out.mt, x.n, dim3(x.dims), int(accumulate),
+         _ptr(ch_scale), groups, _ptr(sums), _stream())
+
+
+def k551_wgrad_workspace_bytes(cin: int, cout: int, fold_side: int) -> int:
+    return call("msb_conv_k551_wgrad_workspace_bytes", cin, cout, fold_side)
+
+
+def k551_wgrad(x: B8, dy: B8, dw, cout, cin, fold_side, workspace: torch.Tensor):
+    call("msb_conv_k551_wgrad", x.mt, dy.mt, _ptr(dw), cout, cin, fold_side, x.n, dim3(x.dims), _ptr(workspace),
+         workspace.numel() * workspace.element_size(), _stream())
+
+
+def channel_sum(x: B8, c_real: int, out):
+    call("msb_channel_sum", x.mt, c_real, x.n, x.s, _ptr(out), _stream())
+
+
 # ---- loss ---------------------------------------------------------------------------------------------------
 def class_weight_sums(logits, psum):
     n, c = logits.shape[:2]

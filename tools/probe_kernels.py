@@ -249,6 +249,122 @@ def k5_wgrad_v1():
 
 
 @check
+def k551_folded():
+    """w-folded 5x5x1 path: in_tr (input folded) and out_tr (output folded) vs torch conv3d on the same rounded data"""
+    torch, F, ops, B8, _lib = _imports()
+    torch.manual_seed(0)
+    n = 2
+    for dims in ((6, 18, 10), (9, 16, 24), (4, 7, 5)):
+        # ---- in_tr: 1 -> 16
+        x = torch.rand(n, 1, *dims, device="cuda")
+        w = torch.randn(16, 1, 5, 5, 5, device="cuda") * (2.0 / 125) ** 0.5
+        b = torch.randn(16, device="cuda")
+        xq, wq = x.bfloat16().float(), w.bfloat16().float()
+        ref = F.conv3d(xq, wq, b, padding=2)
+        xf = B8(n, 16, dims, torch.bfloat16, device="cuda")
+        ops.fold_w_f32(x, 1, xf, 1)
+        packed = torch.empty(ops.k551_packed_bytes(16, 16), dtype=torch.uint8, device="cuda")
+        ops.k551_pack(w, packed, 16, 1, 0, 0, 16, 16)
+        y = B8(n, 16, dims, torch.bfloat16, device="cuda", zero=True)
+        sums = torch.zeros(32, dtype=torch.float64, device="cuda")
+        ops.k551_fwd(xf, packed, b, 16, y, False, None, 1, sums)
+        yo = y.to_ncdhw()
+        dy = torch.randn(n, 16, *dims, device="cuda")
+        dyb = B8.from_ncdhw(dy, torch.bfloat16)
+        refw = torch.nn.grad.conv3d_weight(xq, (16, 1, 5, 5, 5), dyb.to_ncdhw(), padding=2)
+        dw = torch.zeros_like(w)
+        ws = torch.empty(ops.k551_wgrad_workspace_bytes(1, 16, 0), dtype=torch.uint8, device="cuda")
+        ops.k551_wgrad(xf, dyb, dw, 16, 1, 0, ws)
+        print("k551 in_tr", dims, "fwd", _rel(yo, ref), "sums",
+              float((sums[:16] - yo.double().sum((0, 2, 3, 4))).abs().max()), "wgrad", _rel(dw, refw))
+        # ---- out_tr: 32 -> C
+        for c in (2, 3):
+            x = torch.randn(n, 32, *dims, device="cuda")
+            w = torch.randn(c, 32, 5, 5, 5, device="cuda") * (2.0 / 4000) ** 0.5
+            b = torch.randn(c, device="cuda")
+            xb = B8.from_ncdhw(x, torch.bfloat16)
+            xq, wq = xb.to_ncdhw(), w.bfloat16().float()
+            ref = F.conv3d(xq, wq, b, padding=2)
+            packed = torch.empty(ops.k551_packed_bytes(32, 16), dtype=torch.uint8, device="cuda")
+            ops.k551_pack(w, packed, c, 32, 0, 1, 32, 16)
+            pf = B8(n, 16, dims, torch.float32, device="cuda")
+            ops.k551_fwd(xb, packed, None, 5 * c, pf, False, None, 1, None)
+            y = B8(n, 8, dims, torch.bfloat16, device="cuda")
+            sums = torch.zeros(16, dtype=torch.float64, device="cuda")
+            ops.unfold_w(pf, b, c, y, 1, sums)
+            yo = y.to_ncdhw(c)
+            pad_zero = float(y.to_ncdhw(8)[:, c:].abs().max())
+            dy = torch.zeros(n, 8, *dims, device="cuda")
+            dy[:, :c] = torch.randn(n, c, *dims, device="cuda")
+            dyb = B8.from_ncdhw(dy, torch.bfloat16)
+            dyq = dyb.to_ncdhw(c)
+            refx = torch.nn.grad.conv3d_input(xq.shape, wq, dyq, padding=2)
+            refw = torch.nn.grad.conv3d_weight(xq, (c, 32, 5, 5, 5), dyq, padding=2)
+            dpf = B8(n, 16, dims, torch.bfloat16, device="cuda")
+            ops.fold_w(dyb, c, dpf, -1)
+            packed_b = torch.empty(ops.k551_packed_bytes(16, 32), dtype=torch.uint8, device="cuda")
+            ops.k551_pack(w, packed_b, c, 32, 1, 1, 16, 32)
+            dx = B8(n, 32, dims, torch.bfloat16, device="cuda")
+            ops.k551_fwd(dpf, packed_b, None, 32, dx, False, None, 1, None)
+            dw = torch.zeros_like(w)
+            ws = torch.empty(ops.k551_wgrad_workspace_bytes(32, c, 1), dtype=torch.uint8, device="cuda")
+            ops.k551_wgrad(xb, dpf, dw, c, 32, 1, ws)
+            db = torch.zeros(c, device="cuda")
+            ops.channel_sum(dyb, c, db)
+            print("k551 out_tr C=%d" % c, dims, "fwd", _rel(yo, ref), "pad", pad_zero, "sums",
+                  float((sums[:c] - yo.double().sum((0, 2, 3, 4))).abs().max()), "dgrad", _rel(dx.to_ncdhw(), refx),
+                  "wgrad", _rel(dw, refw), "dbias", _rel(db, dyq.sum((0, 2, 3, 4))))
+
+
+@check
+def timing_folded():
+    torch, F, ops, B8, _lib = _imports()
+
+    def timeit(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    n, dims = 2, (128, 128, 128)
+    x1 = torch.rand(n, 1, *dims, device="cuda")
+    xf = B8(n, 16, dims, torch.bfloat16, device="cuda")
+    w = torch.randn(16, 1, 5, 5, 5, device="cuda")
+    packed = torch.empty(ops.k551_packed_bytes(16, 16), dtype=torch.uint8, device="cuda")
+    ops.k551_pack(w, packed, 16, 1, 0, 0, 16, 16)
+    y = B8(n, 16, dims, torch.bfloat16, device="cuda"); y.buf.normal_()
+    sums = torch.zeros(32, dtype=torch.float64, device="cuda")
+    dw = torch.zeros_like(w)
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
+    print("in_tr folded: fold %.3f ms  conv551 %.3f ms  wgrad551 %.3f ms" % (
+        timeit(lambda: ops.fold_w_f32(x1, 1, xf, 1)),
+        timeit(lambda: ops.k551_fwd(xf, packed, None, 16, y, False, None, 1, sums)),
+        timeit(lambda: ops.k551_wgrad(xf, y, dw, 16, 1, 0, ws))))
+    c = 2
+    x = B8(n, 32, dims, torch.bfloat16, device="cuda"); x.buf.normal_()
+    w = torch.randn(c, 32, 5, 5, 5, device="cuda")
+    pk = torch.empty(ops.k551_packed_bytes(32, 16), dtype=torch.uint8, device="cuda")
+    ops.k551_pack(w, pk, c, 32, 0, 1, 32, 16)
+    pkb = torch.empty(ops.k551_packed_bytes(16, 32), dtype=torch.uint8, device="cuda")
+    ops.k551_pack(w, pkb, c, 32, 1, 1, 16, 32)
+    pf = B8(n, 16, dims, torch.float32, device="cuda")
+    y8 = B8(n, 8, dims, torch.bfloat16, device="cuda"); y8.buf.normal_()
+    dpf = B8(n, 16, dims, torch.bfloat16, device="cuda")
+    dx = B8(n, 32, dims, torch.bfloat16, device="cuda")
+    dw = torch.zeros_like(w)
+    s8 = torch.zeros(16, dtype=torch.float64, device="cuda")
+    print("out_tr folded: conv551 %.3f ms  unfold %.3f ms  fold(dy) %.3f ms  dgrad551 %.3f ms  wgrad551 %.3f ms" % (
+        timeit(lambda: ops.k551_fwd(x, pk, None, 5 * c, pf, False, None, 1, None)),
+        timeit(lambda: ops.unfold_w(pf, None, c, y8, 1, s8)),
+        timeit(lambda: ops.fold_w(y8, c, dpf, -1)),
+        timeit(lambda: ops.k551_fwd(dpf, pkb, None, 32, dx, False, None, 1, None)),
+        timeit(lambda: ops.k551_wgrad(x, dpf, dw, c, 32, 1, ws))))
+
+
+@check
 def timing():
     """device time of the dominant layers at the benchmark shapes (batch 2)"""
     torch, F, ops, B8, _lib = _imports()
