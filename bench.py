@@ -55,7 +55,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -63,17 +63,21 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, windows):
+        """windows: [(t0, t1), ...] wall-clock intervals during which the GPU was running timed steps"""
         if self.proc is not None:
             self.proc.terminate()
-        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
-        mx = max([int(float(r[2])) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()] or [0])
+        rows = [r for ts, r in self.rows if len(r) >= 8 and any(a <= ts <= b for a, b in windows)]
+        sm = sorted(int(float(r[1])) for r in rows if r[1].replace(".", "").isdigit())
+        mx = max([int(float(r[2])) for r in rows if r[2].replace(".", "").isdigit()] or [0])
+        pw = [float(r[3]) for r in rows if r[3].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower() == "active"})
+        reasons = sorted({names[i] for r in rows for i in range(4) if r[4 + i].lower() == "active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(pw) if pw else None,
+                "sampled_over": "device-resident and e2e timed regions (nvidia-smi -lms 100)"}
 
 
 def synthetic_gpu_batch(device, seed):
@@ -133,14 +137,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # started before the warm-up so that nvidia-smi is already streaming in the timed regions
     for _ in range(args.warmup):
         step(img, lab)
     barrier()
 
     # ---- device-resident timing (value) -------------------------------------------------------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     import medicalseg_b200.ops as ops_mod
     counter = {"n": 0}
 
@@ -151,24 +155,27 @@ def run_ours(args):
     ops_mod.call = counting_call
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    windows = []
+    w0 = time.time()
     e0.record()
     for _ in range(args.steps):
         step(img, lab)
     e1.record()
     barrier()
+    windows.append((w0, time.time()))
     ops_mod.call = orig_call
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the public API with HOST inputs (e2e) -----------------------------------------
     h_img = img.cpu().pin_memory()
     h_lab = lab.cpu().pin_memory()
     e2e_steps = max(3, min(args.steps, 10))
     barrier()
+    w0 = time.time()
     e0.record()
     last = None
     for _ in range(e2e_steps):
@@ -178,6 +185,8 @@ def run_ours(args):
         last = float(loss.item())  # D2H read of the step's result
     e1.record()
     barrier()
+    windows.append((w0, time.time()))
+    clocks = sampler.stop(windows) if rank == 0 else None
     t2 = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
@@ -297,8 +306,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-depth", type=int, default=32, help="depth of the 128x128 slab the CPU arm processes per step")

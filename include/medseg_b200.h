@@ -129,6 +129,21 @@ size_t msb_conv_k2s2_wgrad_workspace_bytes(int n, int c_big, int c_small, msb_di
 int msb_conv_k2s2_wgrad(msb_tensor big, msb_tensor small, float* dw, float* dbias, int n, msb_dim3 big_dims,
                         int bias_from_big, void* workspace, size_t workspace_bytes, void* stream);
 
+/* tensor-core forward / input-gradient of the same non-overlapping case (bf16 views, even extents):
+ *   gather : out(small grid)[v,co] = bias + sum_{tap,cr} x(big)[2v+tap,cr] * w[co][cr][tap]   (nn.Conv3D forward,
+ *            vnet.py:98-99; also the input gradient of nn.Conv3DTranspose with its [Cin][Cout][8] weight)
+ *   scatter: out(big grid)[2v+tap,co] (+)= bias + sum_cr x(small)[v,cr] * w[cr][co][tap]      (nn.Conv3DTranspose
+ *            forward, vnet.py:133-137; also the input gradient of nn.Conv3D)
+ * packed = msb_conv_k2s2_pack(w, ..., mode 0 gather | 1 scatter, c_red_pad = x.c, c_out_pad = pad16(out.c)).
+ * Optional BN partial sums (double [2][groups][out.c]) of the rounded outputs, as msb_conv_strided_fwd. */
+size_t msb_conv_k2s2_packed_bytes(int c_red_pad, int c_out_pad);
+int msb_conv_k2s2_pack(const float* w, void* packed, int c_red, int c_out, int mode, int c_red_pad, int c_out_pad,
+                       void* stream);
+int msb_conv_k2s2_gather(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
+                         msb_dim3 big_dims, int groups, double* sums, void* stream);
+int msb_conv_k2s2_scatter(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
+                          msb_dim3 big_dims, int accumulate, int groups, double* sums, void* stream);
+
 /* ---- 5x5x5 Conv3D (pad 2, stride 1) on tcgen05 tensor cores ----------------------------------------
  * vnet.py:36 (LUConv.conv1, 14x), :165-166 (out_tr.conv1).  bf16 operands, f32 accumulation in TMEM.     */
 /* packs the Paddle-layout f32 weight [Cout][Cin][125] into the bf16 UMMA operand image.
@@ -182,6 +197,9 @@ int msb_conv_k551_wgrad(msb_tensor x, msb_tensor dy, float* dw, int cout, int ci
 int msb_channel_sum(msb_tensor x, int c_real, int n, int64_t s, float* out, void* stream);
 /* debug switches for bring-up (key 0/1: swap LBO/SBO in the fwd / wgrad UMMA descriptors) */
 int msb_debug_set(int key, int value);
+/* key 5 = 1: the next msb_conv_k5(51)_fwd launches record, per CTA, the clocks their MMA-issuing warp spent
+ * {in total, waiting for weight stages, waiting for halo tiles, waiting for a free accumulator}; synchronises. */
+int msb_debug_read_prof(long long* host_out /* [148][4] */);
 
 /* ---- fused Dice + cross-entropy loss ----------------------------------------------------------------
  * models/losses/dice_loss.py:76-102, cross_entropy_loss.py:47-87, loss_utils.py:31-40, mixes_losses.py:52-60. */

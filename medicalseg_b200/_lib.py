@@ -44,6 +44,10 @@ SIGNATURES = {
     "msb_conv_strided_wgrad": (I, [T, T, P, P, I, D3, D3, D3, D3, I, I, I, P]),
     "msb_conv_k2s2_wgrad_workspace_bytes": (SZ, [I, I, I, D3]),
     "msb_conv_k2s2_wgrad": (I, [T, T, P, P, I, D3, I, P, SZ, P]),
+    "msb_conv_k2s2_packed_bytes": (SZ, [I, I]),
+    "msb_conv_k2s2_pack": (I, [P, P, I, I, I, I, I, P]),
+    "msb_conv_k2s2_gather": (I, [T, P, P, I, T, I, D3, I, P, P]),
+    "msb_conv_k2s2_scatter": (I, [T, P, P, I, T, I, D3, I, I, P, P]),
     "msb_conv_k5_packed_bytes": (SZ, [I, I]),
     "msb_conv_k5_out_pad": (I, [I]),
     "msb_conv_k5_pack": (I, [P, P, I, I, I, I, I, P]),
@@ -60,6 +64,7 @@ SIGNATURES = {
     "msb_conv_k551_wgrad": (I, [T, T, P, I, I, I, I, D3, P, SZ, P]),
     "msb_channel_sum": (I, [T, I, I, L, P, P]),
     "msb_debug_set": (I, [I, I]),
+    "msb_debug_read_prof": (I, [P]),
     "msb_class_weight_sums": (I, [P, I, I, L, P, P]),
     "msb_class_weight_finalize": (I, [P, D, I, P, P]),
     "msb_dice_ce_fwd": (I, [P, P, P, I, I, L, I, P, P]),
@@ -76,7 +81,7 @@ SIGNATURES = {
 
 _NO_STATUS = {"msb_version", "msb_last_error_string", "msb_conv_k5_packed_bytes", "msb_conv_k5_out_pad",
               "msb_conv_k2s2_wgrad_workspace_bytes",
-              "msb_conv_k5_wgrad_workspace_bytes", "msb_conv_k551_packed_bytes",
+              "msb_conv_k5_wgrad_workspace_bytes", "msb_conv_k551_packed_bytes", "msb_conv_k2s2_packed_bytes",
               "msb_conv_k551_wgrad_workspace_bytes"}
 
 _lock = threading.Lock()

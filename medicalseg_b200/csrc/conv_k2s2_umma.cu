@@ -1,0 +1,363 @@
+// 2x2x2 / stride-2 Conv3D and Conv3DTranspose (DownTransition.down_conv vnet.py:98-99, UpTransition.up_conv
+// vnet.py:133-137, and each other's input gradients) as pointwise GEMMs on tcgen05 tensor cores.
+//
+// The windows do not overlap, so both directions are plain GEMMs over 128-voxel tiles (8 w x 16 h of one d-plane of
+// the SMALL grid) with bf16 operands and f32 accumulation in TMEM:
+//   gather  (mode 0): out[v, co]       = bias[co] + sum_{tap, cr} x[2v + tap, cr] * w[co][cr][tap]     K = 8 * Cred
+//       A = the tap-(kd,kh,kw) sub-lattice of the big grid, fetched by ONE strided 5-D TMA box per (tap, 16 channels)
+//       (elementStrides 2 along w and h: the space-to-depth never touches memory), B = packed weights.
+//   scatter (mode 1): out[2v + tap, co] (+)= bias[co] + sum_cr x[v, cr] * w[cr][co][tap]                K = Cred
+//       N = (taps of a group, co): one MMA produces up to 8 output voxels per input voxel; the epilogue writes each
+//       tap's 16-byte channel vectors to its depth-to-space position.
+// Both are HBM-bound (AI 26-190 FLOP/B): the kernel's job is to stream x once and write out once.
+// Warp roles as in conv_k5_umma.cu: w0 TMA producer, w1 MMA issue (uniform control flow, one elected lane),
+// w2 TMEM alloc, w4-7 epilogue (bias, optional accumulate, bf16 round, BN partial sums, 128-bit stores).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "conv_k5.cuh"
+#include "umma.cuh"
+
+namespace msb {
+
+constexpr int kK2TileW = 8, kK2TileH = 16;
+constexpr int kK2ABytes = 2 * kK2TileH * kK2TileW * 16;  // [2 c8][16 h][8 w][8 ch] bf16 = 4 KB
+constexpr int kK2BBytesMax = 256 * 32;                   // [2 k8][N <= 256][8 ch] bf16
+constexpr int kK2StageBytes = kK2ABytes + kK2BBytesMax;
+constexpr int kK2Stages = 8;
+constexpr int kK2SmemBytes = kK2Stages * kK2StageBytes + 1024 + 4 * 2 * 256 * 4 + 128;
+
+struct K2Params {
+  int mode;              // 0 gather, 1 scatter
+  int n, chunks;         // chunks = x.c / 16
+  int nmma;              // MMA N: gather = cpad, scatter = tg * cpad
+  int cpad;              // output channels padded to a multiple of 16
+  int tg, tap_groups;    // scatter: taps per MMA and number of tap groups (tg * tap_groups = 8); gather: 1, 1
+  int cout_real, out_c8;
+  int sd, sh, sw;        // small-grid extents
+  int tiles_w, tiles_h;
+  int x_c8_total;        // planes per n in the TMA coordinate space of x
+  const void* packed;
+  const float* bias;
+  msb_tensor out;
+  int accumulate;
+  int groups;
+  double* sums;
+  int sums_c;
+};
+
+__global__ void __launch_bounds__(256, 1)
+    conv_k2s2_kernel(const __grid_constant__ CUtensorMap tmap_x, const K2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* stage_smem = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + kK2Stages * kK2StageBytes);
+  // barrier map: [0,S) full  [S,2S) empty  [2S,2S+2) acc_full  [2S+2,2S+4) acc_empty
+  constexpr int kFull = 0, kEmpty = kK2Stages, kAccFull = 2 * kK2Stages, kAccEmpty = 2 * kK2Stages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kK2Stages + 4);
+  float* stat_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);  // [4 warps][2][256]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = ptx::smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kK2Stages; ++i) { ptx::mbar_init(BAR(kFull + i), 1); ptx::mbar_init(BAR(kEmpty + i), 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(kAccFull + i), 1); ptx::mbar_init(BAR(kAccEmpty + i), 4); }
+    ptx::fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 4 * 2 * 256; i += 256) stat_smem[i] = 0.f;
+  if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tmap_x);
+  if (warp == 2) ptx::tmem_alloc<512>(ptx::smem_u32(tmem_slot));
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_n = p.sd * p.tiles_h * p.tiles_w;
+  const int num_items = p.n * tiles_per_n * p.tap_groups;
+  const int kiters = p.mode == 0 ? 8 * p.chunks : p.chunks;
+  const uint32_t b_bytes = (uint32_t)p.nmma * 32u;
+
+  if (warp == 0) {
+    // ================= TMA producer: one (tap, 16-channel chunk) A tile + its weight block per stage ==========
+    const bool leader = ptx::elect_one();
+    uint32_t use = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int tile = item / p.tap_groups, tgp = item % p.tap_groups;
+      const int n = tile / tiles_per_n;
+      int r = tile % tiles_per_n;
+      const int tw = r % p.tiles_w; r /= p.tiles_w;
+      const int th = r % p.tiles_h; const int d = r / p.tiles_h;
+      for (int ki = 0; ki < kiters; ++ki, ++use) {
+        const int tap = p.mode == 0 ? ki / p.chunks : 0;
+        const int ck = p.mode == 0 ? ki % p.chunks : ki;
+        const uint32_t s = use % kK2Stages, ph = (use / kK2Stages) & 1;
+        ptx::mbar_wait(BAR(kEmpty + s), ph ^ 1);
+        if (leader) {
+          uint8_t* st = stage_smem + s * kK2StageBytes;
+          ptx::mbar_expect_tx(BAR(kFull + s), kK2ABytes + b_bytes);
+          if (p.mode == 0)
+            ptx::tma_load_5d(ptx::smem_u32(st), &tmap_x, BAR(kFull + s), 0, 2 * tw * kK2TileW + (tap & 1),
+                             2 * th * kK2TileH + ((tap >> 1) & 1), 2 * d + (tap >> 2), n * p.x_c8_total + ck * 2);
+          else
+            ptx::tma_load_4d(ptx::smem_u32(st), &tmap_x, BAR(kFull + s), tw * kK2TileW * 8, th * kK2TileH, d,
+                             n * p.x_c8_total + ck * 2);
+          const int blk = (p.mode == 0 ? tap : tgp) * p.chunks + ck;
+          ptx::bulk_load(ptx::smem_u32(st + kK2ABytes), reinterpret_cast<const uint8_t*>(p.packed) + (size_t)blk * b_bytes,
+                         b_bytes, BAR(kFull + s));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    const bool leader = ptx::elect_one();
+    const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);
+    const uint32_t idesc = ptx::make_idesc_bf16(128, p.nmma, 0, 0);
+    constexpr uint32_t a_hi = ptx::desc_hi(128u), b_hi = ptx::desc_hi(128u);
+    const uint32_t a_lbo16 = (uint32_t)(kK2TileH * kK2TileW * 16) >> 4, b_lbo16 = (uint32_t)p.nmma;  // nmma*16 B >> 4
+    uint32_t use = 0, iuse = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
+      const uint32_t as = iuse & 1, aph = (iuse >> 1) & 1;
+      ptx::mbar_wait(BAR(kAccEmpty + as), aph ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_u + as * 256u;
+      for (int ki = 0; ki < kiters; ++ki, ++use) {
+        const uint32_t s = use % kK2Stages, ph = (use / kK2Stages) & 1;
+        ptx::mbar_wait(BAR(kFull + s), ph);
+        ptx::tc_fence_after();
+        const uint32_t st = ptx::smem_u32(stage_smem + s * kK2StageBytes);
+        const uint32_t a_lo = ptx::desc_lo(st, a_lbo16), b_lo = ptx::desc_lo(st + kK2ABytes, b_lbo16);
+        if (leader) {
+          ptx::mma_bf16_split(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, ki != 0 ? 1u : 0u);
+          ptx::mma_commit(BAR(kEmpty + s));
+        }
+        __syncwarp();
+      }
+      if (leader) ptx::mma_commit(BAR(kAccFull + as));
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    const int hh = row >> 3, ww = row & 7;
+    const int64_t Ss = (int64_t)p.sd * p.sh * p.sw;
+    const int64_t So = p.mode == 0 ? Ss : Ss * 8;  // voxels of the output grid
+    float* my_stats = stat_smem + q * 2 * 256;
+    uint32_t iuse = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
+      const int tile = item / p.tap_groups, tgp = item % p.tap_groups;
+      const int n = tile / tiles_per_n;
+      int r = tile % tiles_per_n;
+      const int tw = r % p.tiles_w; r /= p.tiles_w;
+      const int th = r % p.tiles_h; const int d = r / p.tiles_h;
+      const int h = th * kK2TileH + hh, w = tw * kK2TileW + ww;
+      const bool ok = h < p.sh && w < p.sw;
+      const uint32_t as = iuse & 1, aph = (iuse >> 1) & 1;
+      ptx::mbar_wait(BAR(kAccFull + as), aph);
+      ptx::tc_fence_after();
+      const uint32_t t_base = tmem_base + as * 256u + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int cb = 0; cb < p.nmma / 16; ++cb) {
+        float acc[16];
+        ptx::tmem_ld16(t_base + cb * 16, acc);
+        const int col0 = cb * 16;
+        const int t = col0 / p.cpad, co0 = col0 % p.cpad;  // scatter: tap within the group; gather: t = 0
+        int64_t v;
+        if (p.mode == 0) {
+          v = ((int64_t)d * p.sh + h) * p.sw + w;
+        } else {
+          const int tap = tgp * p.tg + t;
+          v = ((int64_t)(2 * d + (tap >> 2)) * (2 * p.sh) + (2 * h + ((tap >> 1) & 1))) * (2 * p.sw) + (2 * w + (tap & 1));
+        }
+        float sq[16];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int c8 = (co0 >> 3) + k;
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = c8 * 8 + j;
+            o[j] = acc[k * 8 + j] + ((p.bias != nullptr && c < p.cout_real) ? __ldg(p.bias + c) : 0.f);
+          }
+          if (c8 < p.out_c8) {
+            __nv_bfloat16* dst = view_ptr<__nv_bfloat16>(p.out, n, c8, So, ok ? v : 0);
+            if (p.accumulate && ok) {
+              float old[8];
+              Vec8<__nv_bfloat16>::load(dst, old);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] += old[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = ok ? Vec8<__nv_bfloat16>::round(o[j]) : 0.f;
+            if (ok) Vec8<__nv_bfloat16>::store(dst, o);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { acc[k * 8 + j] = o[j]; sq[k * 8 + j] = o[j] * o[j]; }
+        }
+        if (p.sums != nullptr) {
+          const float s1 = warp_reduce16(acc, lane);
+          const float s2 = warp_reduce16(sq, lane);
+          if ((lane & 1) == 0) {
+            my_stats[co0 + (lane >> 1)] += s1;
+            my_stats[256 + co0 + (lane >> 1)] += s2;
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(BAR(kAccEmpty + as));
+      if (p.sums != nullptr && p.groups > 1) {
+        __syncwarp();
+        for (int i = lane; i < 2 * 256; i += 32) {
+          const int stat = i / 256, c = i % 256;
+          if (c < p.sums_c && my_stats[i] != 0.f)
+            atomicAdd(&p.sums[((int64_t)stat * p.groups + n) * p.sums_c + c], (double)my_stats[i]);
+          my_stats[i] = 0.f;
+        }
+        __syncwarp();
+      }
+    }
+    if (p.sums != nullptr && p.groups == 1) {
+      __syncwarp();
+      for (int i = lane; i < 2 * 256; i += 32) {
+        const int stat = i / 256, c = i % 256;
+        if (c < p.sums_c && my_stats[i] != 0.f) atomicAdd(&p.sums[(int64_t)stat * p.sums_c + c], (double)my_stats[i]);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// gather : packed[tap][chunk][k8][co < cpad][j]            = w[co][cr][tap]   (w = [c_out][c_red][8])
+// scatter: packed[tgp][chunk][k8][t*cpad + co][j]          = w[cr][co][tap]   (w = [c_red][c_out][8]), tap = tgp*tg + t
+// with cr = chunk*16 + k8*8 + j
+__global__ void __launch_bounds__(256) pack_k2s2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed,
+                                                        int c_red, int c_out, int mode, int c_red_pad, int cpad, int tg) {
+  const int chunks = c_red_pad / 16;
+  const int64_t total = (int64_t)8 * c_red_pad * cpad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i & 7);
+    int64_t r = i >> 3;
+    int tap, co, k8, ck;
+    if (mode == 0) {
+      co = (int)(r % cpad); r /= cpad;
+      k8 = (int)(r & 1); r >>= 1;
+      ck = (int)(r % chunks); tap = (int)(r / chunks);
+    } else {
+      const int nm = tg * cpad;
+      const int col = (int)(r % nm); r /= nm;
+      k8 = (int)(r & 1); r >>= 1;
+      ck = (int)(r % chunks);
+      const int tgp = (int)(r / chunks);
+      tap = tgp * tg + col / cpad; co = col % cpad;
+    }
+    const int cr = ck * 16 + k8 * 8 + j;
+    float v = 0.f;
+    if (cr < c_red && co < c_out)
+      v = mode == 0 ? __ldg(w + ((int64_t)co * c_red + cr) * 8 + tap) : __ldg(w + ((int64_t)cr * c_out + co) * 8 + tap);
+    packed[i] = __float2bfloat16_rn(v);
+  }
+}
+
+static inline int k2_pad16(int c) { return (c + 15) / 16 * 16; }
+static inline int k2_tg(int cpad) { int tg = 8; while (tg > 1 && tg * cpad > 256) tg >>= 1; return tg; }
+
+static int launch_k2s2(int mode, const msb_tensor& x, const void* packed, const float* bias, int cout,
+                       const msb_tensor& out, int n, msb_dim3 big, int accumulate, int groups, double* sums,
+                       cudaStream_t st) {
+  const msb_dim3 sd = {big.d / 2, big.h / 2, big.w / 2};
+  K2Params p;
+  p.mode = mode; p.n = n; p.chunks = x.c / 16;
+  p.cpad = k2_pad16(out.c);
+  p.tg = mode == 0 ? 1 : k2_tg(p.cpad);
+  p.tap_groups = mode == 0 ? 1 : 8 / p.tg;
+  p.nmma = mode == 0 ? p.cpad : p.tg * p.cpad;
+  p.cout_real = cout; p.out_c8 = out.c / 8;
+  p.sd = sd.d; p.sh = sd.h; p.sw = sd.w;
+  p.tiles_w = (sd.w + kK2TileW - 1) / kK2TileW;
+  p.tiles_h = (sd.h + kK2TileH - 1) / kK2TileH;
+  p.packed = packed; p.bias = bias; p.out = out; p.accumulate = accumulate;
+  p.groups = groups; p.sums = sums; p.sums_c = out.c;
+  CUtensorMap tmap;
+  int rc;
+  if (mode == 0) {
+    const int64_t Sb = (int64_t)big.d * big.h * big.w;
+    p.x_c8_total = (int)(x.n_stride / (Sb * 8));
+    if ((rc = make_b8_tmap_s2(&tmap, x, n, big, kK2TileW, kK2TileH, 2))) return rc;
+  } else {
+    const int64_t Ss = (int64_t)sd.d * sd.h * sd.w;
+    p.x_c8_total = (int)(x.n_stride / (Ss * 8));
+    if ((rc = make_b8_tmap(&tmap, x, n, sd, kK2TileW, kK2TileH, 1, 2))) return rc;
+  }
+  const int items = n * sd.d * p.tiles_h * p.tiles_w * p.tap_groups;
+  const int grid = items < kNumSMs ? items : kNumSMs;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MSB_CUDA_OK(cudaFuncSetAttribute(conv_k2s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2SmemBytes));
+    attr_set = true;
+  }
+  conv_k2s2_kernel<<<grid, 256, kK2SmemBytes, st>>>(tmap, p);
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+}  // namespace msb
+
+using namespace msb;
+
+extern "C" {
+
+size_t msb_conv_k2s2_packed_bytes(int c_red_pad, int c_out_pad) {
+  return (size_t)8 * c_red_pad * c_out_pad * sizeof(__nv_bfloat16);
+}
+
+int msb_conv_k2s2_pack(const float* w, void* packed, int c_red, int c_out, int mode, int c_red_pad, int c_out_pad,
+                       void* stream) {
+  MSB_REQUIRE(w && packed && c_red > 0 && c_out > 0 && (mode == 0 || mode == 1), "msb_conv_k2s2_pack: bad arguments");
+  MSB_REQUIRE(c_red_pad % 16 == 0 && c_out_pad % 16 == 0 && c_red_pad >= c_red && c_out_pad >= c_out && c_out_pad <= 256,
+              "msb_conv_k2s2_pack: padded channel counts must be multiples of 16 covering the real ones (out <= 256)");
+  const int64_t total = (int64_t)8 * c_red_pad * c_out_pad;
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  pack_k2s2_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), c_red, c_out,
+                                                          mode, c_red_pad, c_out_pad, k2_tg(c_out_pad));
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+static int k2s2_check(const char* who, const msb_tensor& x, const msb_tensor& out, const void* packed, int cout, int n,
+                      msb_dim3 big, int groups) {
+  MSB_REQUIRE(view_ok(x) && view_ok(out) && x.dtype == MSB_BF16 && out.dtype == MSB_BF16 && packed && n > 0,
+              "%s: bf16 B8 views required", who);
+  MSB_REQUIRE(big.d > 0 && big.h > 0 && big.w > 0 && big.d % 2 == 0 && big.h % 2 == 0 && big.w % 2 == 0,
+              "%s: the large grid must have even extents", who);
+  MSB_REQUIRE(x.c % 16 == 0 && out.c <= 256 && cout > 0 && cout <= out.c, "%s: x.c must be a multiple of 16, out.c <= 256", who);
+  MSB_REQUIRE(groups == 1 || groups == n, "%s: groups must be 1 or n", who);
+  return MSB_OK;
+}
+
+int msb_conv_k2s2_gather(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
+                         msb_dim3 big_dims, int groups, double* sums, void* stream) {
+  int rc = k2s2_check("msb_conv_k2s2_gather", x, out, packed, cout, n, big_dims, groups);
+  if (rc) return rc;
+  return launch_k2s2(0, x, packed, bias, cout, out, n, big_dims, 0, groups, sums, as_stream(stream));
+}
+
+int msb_conv_k2s2_scatter(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
+                          msb_dim3 big_dims, int accumulate, int groups, double* sums, void* stream) {
+  int rc = k2s2_check("msb_conv_k2s2_scatter", x, out, packed, cout, n, big_dims, groups);
+  if (rc) return rc;
+  return launch_k2s2(1, x, packed, bias, cout, out, n, big_dims, accumulate, groups, sums, as_stream(stream));
+}
+
+}  // extern "C"

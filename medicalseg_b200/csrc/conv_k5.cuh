@@ -17,9 +17,40 @@ int make_b8_tmap(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 dims, in
 int make_b8_tmap_hmajor(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 dims, int box_w, int box_p, int box_h,
                         int box_d);
 
+// stride-2 sub-lattice map (5-D, elementStrides 2 along w and h): shared-memory image [plane][box_h][box_w][8]
+int make_b8_tmap_s2(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 dims, int box_w, int box_h, int box_p);
+
 // kh-stacked weight-gradient kernel (conv_k5_wgrad2.cu); returns MSB_ERR_UNSUPPORTED when not applicable
 // kw_taps: 5 = 5x5x5 kernel (ws [125][cout][cin]); 1 = 5x5x1 kernel of the w-folded convs (ws [25][cout][cin])
 int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin, int n, msb_dim3 dims, float* ws,
                     cudaStream_t st, int kw_taps = 5);
+
+// 16 per-lane values -> per-channel totals over the warp; lane L ends up with the total of channel L>>1.
+__device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
+  float a[8], b[4], c[2];
+  bool hi = lane & 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = hi ? v[i] : v[i + 8], keep = hi ? v[i + 8] : v[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  hi = lane & 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = hi ? a[i] : a[i + 4], keep = hi ? a[i + 4] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  hi = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = hi ? b[i] : b[i + 2], keep = hi ? b[i + 2] : b[i];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  hi = lane & 2;
+  const float send = hi ? c[0] : c[1], keep = hi ? c[1] : c[0];
+  float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
 
 }  // namespace msb

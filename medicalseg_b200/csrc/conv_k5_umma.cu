@@ -37,14 +37,17 @@ struct FwdCfg {
   static constexpr int kWK8Bytes = kNB * kBlockBytes;
   static constexpr int kWStageBytes = 2 * kWK8Bytes;
   static constexpr int kWLoadBytes = 5 * kBlockBytes;                      // bytes TMA writes per (stage, k8)
-  static constexpr int kWStages = (NPAD >= 256) ? 3 : 4;
+  // as many weight stages as fit (<= 8): the stage ring has to cover the L2 latency of cp.async.bulk
+  static constexpr int kFixedBytes = 2 * kHaloBytes + 1024 /*barriers + stats*/ + 4 * 2 * NPAD * 4 + 128 /*alignment slack*/;
+  static constexpr int kWStagesFit = (227 * 1024 - kFixedBytes) / kWStageBytes;
+  static constexpr int kWStages = kWStagesFit > 8 ? 8 : kWStagesFit;
   static constexpr int kAccCols = TD * NPAD;
   static constexpr int kNMma = J * NPAD;
   static constexpr int kColsNeeded = ACC_SETS * kAccCols;
   static constexpr int kTmemCols = (kColsNeeded <= 32) ? 32 : (kColsNeeded <= 64) ? 64 : (kColsNeeded <= 128) ? 128
                                  : (kColsNeeded <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = 2 * kHaloBytes + kWStages * kWStageBytes + 1024 /*barriers + stats*/ +
-                                    4 * 2 * NPAD * 4 + 128 /*alignment slack*/;
+  static constexpr int kSmemBytes = kFixedBytes + kWStages * kWStageBytes;
+  static_assert(kWStages >= 2, "weight stages do not fit");
   static_assert(TD % J == 0 && kNMma <= 256, "bad plane stacking");
   static_assert(kColsNeeded <= 512, "TMEM overflow");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory overflow");
@@ -67,35 +70,8 @@ struct FwdParams {
   int nsplit;                            // output-channel slices per tile (fills the SMs on small volumes)
   int kw_taps;                           // 5 = full 5x5x5 kernel; 1 = 5x5x1 (kd,kh) kernel of the w-folded convs
   int out_f32;                           // store f32 (B8 f32 view) instead of bf16; no accumulate, no BN sums
+  long long* prof;                       // bring-up: per-CTA clocks the MMA warp spent {total, w_full, halo_full, acc_empty}
 };
-
-// 16 per-lane values -> per-channel totals over the warp; lane L ends up with the total of channel L>>1.
-__device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane) {
-  float a[8], b[4], c[2];
-  bool hi = lane & 16;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float send = hi ? v[i] : v[i + 8], keep = hi ? v[i + 8] : v[i];
-    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-  hi = lane & 8;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float send = hi ? a[i] : a[i + 4], keep = hi ? a[i + 4] : a[i];
-    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-  hi = lane & 4;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float send = hi ? b[i] : b[i + 2], keep = hi ? b[i + 2] : b[i];
-    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  hi = lane & 2;
-  const float send = hi ? c[0] : c[1], keep = hi ? c[1] : c[0];
-  float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  r += __shfl_xor_sync(0xffffffffu, r, 1);
-  return r;
-}
 
 template <int NPAD, int TD, int J, int ACC_SETS, int NS>
 __global__ void __launch_bounds__(256, 1)
@@ -107,8 +83,9 @@ __global__ void __launch_bounds__(256, 1)
   uint8_t* halo_smem = smem;                                   // [2][kHaloBytes]
   uint8_t* w_smem = halo_smem + 2 * Cfg::kHaloBytes;           // [kWStages][kWStageBytes]
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + Cfg::kWStages * Cfg::kWStageBytes);
-  // barrier map: [0,2) halo_full  [2,4) halo_empty  [4,8) w_full  [8,12) w_empty  [12,14) acc_full  [14,16) acc_empty
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  // barrier map: [0,2) halo_full  [2,4) halo_empty  [4,6) acc_full  [6,8) acc_empty  [8,8+S) w_full  [8+S,8+2S) w_empty
+  constexpr int kWF = 8, kWE = 8 + Cfg::kWStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * Cfg::kWStages);
   float* stat_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);  // [4 warps][2][NPAD]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -117,8 +94,8 @@ __global__ void __launch_bounds__(256, 1)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(0 + i), 1); ptx::mbar_init(BAR(2 + i), 1); }
-    for (int i = 0; i < 4; ++i) { ptx::mbar_init(BAR(4 + i), 1); ptx::mbar_init(BAR(8 + i), 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(12 + i), 1); ptx::mbar_init(BAR(14 + i), 4); }
+    for (int i = 0; i < Cfg::kWStages; ++i) { ptx::mbar_init(BAR(kWF + i), 1); ptx::mbar_init(BAR(kWE + i), 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(4 + i), 1); ptx::mbar_init(BAR(6 + i), 4); }
     ptx::fence_mbar_init();
   }
   for (int i = threadIdx.x; i < 4 * 2 * NPAD; i += 256) stat_smem[i] = 0.f;
@@ -171,14 +148,14 @@ __global__ void __launch_bounds__(256, 1)
             reinterpret_cast<const uint8_t*>(p.packed) + (size_t)ck * stages_per_chunk * 2 * Cfg::kWLoadBytes;
         for (int st = 0; st < stages_per_chunk; ++st, ++use) {
           const uint32_t s = use % Cfg::kWStages, ph = (use / Cfg::kWStages) & 1;
-          ptx::mbar_wait(BAR(8 + s), ph ^ 1);
+          ptx::mbar_wait(BAR(kWE + s), ph ^ 1);
           if (leader) {
-            ptx::mbar_expect_tx(BAR(4 + s), 2 * Cfg::kWLoadBytes);
+            ptx::mbar_expect_tx(BAR(kWF + s), 2 * Cfg::kWLoadBytes);
 #pragma unroll
             for (int k8 = 0; k8 < 2; ++k8)
               ptx::bulk_load(ptx::smem_u32(w_smem + s * Cfg::kWStageBytes + k8 * Cfg::kWK8Bytes +
                                            (J - 1) * Cfg::kBlockBytes),
-                             src + (size_t)(st * 2 + k8) * Cfg::kWLoadBytes, Cfg::kWLoadBytes, BAR(4 + s));
+                             src + (size_t)(st * 2 + k8) * Cfg::kWLoadBytes, Cfg::kWLoadBytes, BAR(kWF + s));
           }
           __syncwarp();
         }
@@ -197,19 +174,27 @@ __global__ void __launch_bounds__(256, 1)
     constexpr uint32_t a_lbo16 = (uint32_t)Cfg::kHaloPlaneBytes >> 4, b_lbo16 = (uint32_t)Cfg::kWK8Bytes >> 4;
     uint32_t huse = 0, wuse = 0, iuse = 0;
     const int stages_per_chunk = 5 * p.kw_taps;
+    const bool prof = p.prof != nullptr;
+    long long t_w = 0, t_h = 0, t_a = 0, t_begin = prof ? clock64() : 0, tq = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
       const uint32_t as = iuse % ACC_SETS, aph = (iuse / ACC_SETS) & 1;
-      ptx::mbar_wait(BAR(14 + as), aph ^ 1);
+      if (prof) tq = clock64();
+      ptx::mbar_wait(BAR(6 + as), aph ^ 1);
+      if (prof) t_a += clock64() - tq;
       ptx::tc_fence_after();
       const uint32_t d_base = tmem_u + as * Cfg::kAccCols;
       const uint32_t b_slice = (uint32_t)((item % NS) * n_slice);  // first weight row (16 B each) of this slice
       for (int ck = 0; ck < chunks; ++ck, ++huse) {
         const uint32_t hb = huse & 1, hph = (huse >> 1) & 1;
+        if (prof) tq = clock64();
         ptx::mbar_wait(BAR(0 + hb), hph);
+        if (prof) t_h += clock64() - tq;
         const uint32_t a_lo0 = ptx::desc_lo(ptx::smem_u32(halo_smem + hb * Cfg::kHaloBytes), a_lbo16);
         for (int st = 0; st < stages_per_chunk; ++st, ++wuse) {  // st = kh*kw_taps + kw
           const uint32_t s = wuse % Cfg::kWStages, wph = (wuse / Cfg::kWStages) & 1;
-          ptx::mbar_wait(BAR(4 + s), wph);
+          if (prof) tq = clock64();
+          ptx::mbar_wait(BAR(kWF + s), wph);
+          if (prof) t_w += clock64() - tq;
           ptx::tc_fence_after();
           const uint32_t b_lo0 = ptx::desc_lo(ptx::smem_u32(w_smem + s * Cfg::kWStageBytes), b_lbo16) + b_slice;
           const uint32_t hw_off =  // 16-byte units; the single w tap of the 5x5x1 kernel is the centre one
@@ -225,12 +210,18 @@ __global__ void __launch_bounds__(256, 1)
               if (leader) ptx::mma_bf16_split(d_base + g * Cfg::kNMma, a_lo, a_hi, b_lo, b_hi, idesc, kdp != 0 ? 1u : first);
             }
           }
-          if (leader) ptx::mma_commit(BAR(8 + s));  // weight stage free once these MMAs retire
+          if (leader) ptx::mma_commit(BAR(kWE + s));  // weight stage free once these MMAs retire
         }
         if (leader) ptx::mma_commit(BAR(2 + hb));   // halo buffer free
       }
-      if (leader) ptx::mma_commit(BAR(12 + as));    // accumulators complete -> epilogue
+      if (leader) ptx::mma_commit(BAR(4 + as));    // accumulators complete -> epilogue
       __syncwarp();
+    }
+    if (prof && lane == 0) {
+      p.prof[blockIdx.x * 4 + 0] = clock64() - t_begin;
+      p.prof[blockIdx.x * 4 + 1] = t_w;
+      p.prof[blockIdx.x * 4 + 2] = t_h;
+      p.prof[blockIdx.x * 4 + 3] = t_a;
     }
   } else if (warp >= 4) {
     // ================= epilogue: TMEM -> registers -> (bias, accumulate, round, BN sums) -> global =================
@@ -250,7 +241,7 @@ __global__ void __launch_bounds__(256, 1)
       const int h = th * kTileH + hh, w = tw * kTileW + ww;
       const bool inb = h < p.h && w < p.w;
       const uint32_t as = iuse % ACC_SETS, aph = (iuse / ACC_SETS) & 1;
-      ptx::mbar_wait(BAR(12 + as), aph);
+      ptx::mbar_wait(BAR(4 + as), aph);
       ptx::tc_fence_after();
       const uint32_t t_base = tmem_base + as * Cfg::kAccCols + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
@@ -310,7 +301,7 @@ __global__ void __launch_bounds__(256, 1)
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(BAR(14 + as));
+      if (lane == 0) ptx::mbar_arrive(BAR(6 + as));
       if (p.sums != nullptr && p.groups > 1) {
         // per-instance statistics: flush after every item (an item never straddles two n)
         __syncwarp();
@@ -760,7 +751,38 @@ int make_b8_tmap_hmajor(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 d
   return MSB_OK;
 }
 
+// 5-D map over a B8 bf16 view that samples every SECOND voxel along w and h (elementStrides 2): dims (8, W, H, D,
+// planes), box (8, 2*box_w, 2*box_h, 1, box_p) -> shared-memory image [plane][box_h][box_w][8].  The start coordinate
+// selects the (kd, kh, kw) sub-lattice of a 2x2x2 / stride-2 window.
+int make_b8_tmap_s2(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 dims, int box_w, int box_h, int box_p) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return MSB_ERR_CUDA;
+  }
+  const int64_t S = (int64_t)dims.d * dims.h * dims.w;
+  if (t.n_stride % (S * 8) != 0) {
+    set_error("tensor view: n_stride must be a multiple of D*H*W*8");
+    return MSB_ERR_INVALID;
+  }
+  const int64_t planes_total = t.n_stride / (S * 8);
+  const cuuint64_t gdim[5] = {8, (cuuint64_t)dims.w, (cuuint64_t)dims.h, (cuuint64_t)dims.d,
+                              (cuuint64_t)((n - 1) * planes_total + t.c / 8)};
+  const cuuint64_t gstr[4] = {16, (cuuint64_t)dims.w * 16, (cuuint64_t)dims.h * dims.w * 16, (cuuint64_t)S * 16};
+  const cuuint32_t box[5] = {8, (cuuint32_t)(2 * box_w), (cuuint32_t)(2 * box_h), 1, (cuuint32_t)box_p};
+  const cuuint32_t estr[5] = {1, 2, 2, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, t.ptr, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (stride-2) failed with CUresult %d", (int)r);
+    return MSB_ERR_CUDA;
+  }
+  return MSB_OK;
+}
+
 int g_debug_flags[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+static long long* g_prof_buf = nullptr;  // debug flag 5: MMA-warp stall profile of the last conv_k5_fwd launch
 
 template <int NPAD, int TD, int J, int ACC_SETS, int NS>
 static int launch_fwd_ns(const CUtensorMap& tmap, FwdParams& p, int tiles, cudaStream_t st) {
@@ -835,6 +857,12 @@ using namespace msb;
 
 extern "C" {
 
+int msb_debug_read_prof(long long* host_out /* [148][4] */) {
+  MSB_REQUIRE(host_out != nullptr && g_prof_buf != nullptr, "msb_debug_read_prof: enable debug flag 5 and run a conv first");
+  MSB_CUDA_OK(cudaMemcpy(host_out, g_prof_buf, kNumSMs * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return MSB_OK;
+}
+
 int msb_debug_set(int key, int value) {
   if (key < 0 || key >= 8) return MSB_ERR_INVALID;
   g_debug_flags[key] = value;
@@ -879,6 +907,12 @@ static int conv_k5_fwd_impl(const char* who, msb_tensor x, const void* packed, c
   p.packed = packed; p.bias = bias; p.out = out; p.accumulate = accumulate; p.ch_scale = ch_scale;
   p.groups = groups; p.sums = sums; p.sums_c = out.c; p.dbg_swap = 0;
   p.kw_taps = kw_taps; p.out_f32 = out.dtype == MSB_F32;
+  p.prof = nullptr;
+  if (g_debug_flags[5]) {
+    if (g_prof_buf == nullptr) MSB_CUDA_OK(cudaMalloc(&g_prof_buf, kNumSMs * 4 * sizeof(long long)));
+    MSB_CUDA_OK(cudaMemsetAsync(g_prof_buf, 0, kNumSMs * 4 * sizeof(long long), as_stream(stream)));
+    p.prof = g_prof_buf;
+  }
   cudaStream_t st = as_stream(stream);
   const int npad_sel = msb_conv_k5_out_pad(out.c);
   // NOTE: the packed operand must have been built with cout_pad == npad_sel.

@@ -236,6 +236,43 @@ class _K5:
             ops.conv_strided_wgrad(x, dy, dw, db, (5, 5, 5), (1, 1, 1), (2, 2, 2), False, self.cin, self.cout)
 
 
+class _K2S2:
+    """tensor-core path of a 2x2x2 / stride-2 down_conv (vnet.py:98-99) or up_conv (vnet.py:133-137) and its input
+    gradient: `gather` reduces 8 big-grid voxels into one small-grid voxel, `scatter` expands one into eight.  The
+    5-D weight is [A][B][2][2][2]: gather produces A channels from B, scatter produces B channels from A."""
+
+    def __init__(self, eng, conv: _Conv, a, b, kernel, stride):
+        self.eng, self.conv, self.a, self.b = eng, conv, a, b
+        self.ok = (eng.dtype == torch.bfloat16 and tuple(kernel) == (2, 2, 2) and tuple(stride) == (2, 2, 2)
+                   and a % 16 == 0 and b % 16 == 0 and a <= 256 and b <= 256)
+        self.packed = [None, None]
+        self.version = [-1, -1]
+
+    def usable(self, big_dims):
+        return self.ok and all(d % 2 == 0 for d in big_dims)
+
+    def _pack(self, mode, c_red_pad, c_out_pad):
+        eng = self.eng
+        if self.version[mode] == eng.param_version and self.packed[mode] is not None:
+            return self.packed[mode]
+        w = eng.store.view(self.conv.weight)
+        if self.packed[mode] is None:
+            self.packed[mode] = torch.empty(ops.k2s2_packed_bytes(c_red_pad, c_out_pad), dtype=torch.uint8,
+                                            device=w.device)
+        c_red, c_out = (self.b, self.a) if mode == 0 else (self.a, self.b)
+        ops.k2s2_pack(w, self.packed[mode], c_red, c_out, mode, c_red_pad, c_out_pad)
+        self.version[mode] = eng.param_version
+        return self.packed[mode]
+
+    def gather(self, x: B8, out: B8, bias, groups=1, sums=None):
+        packed = self._pack(0, x.c, _pad(out.c, 16))
+        ops.k2s2_gather(x, packed, bias, self.a, out, groups, sums)
+
+    def scatter(self, x: B8, out: B8, bias, accumulate=False, groups=1, sums=None):
+        packed = self._pack(1, x.c, _pad(out.c, 16))
+        ops.k2s2_scatter(x, packed, bias, self.b, out, accumulate, groups, sums)
+
+
 class _K551:
     """w-folded 5x5x1 form of a 5x5x5 conv with <= 3 real channels on one side (bf16 tensor-core path only):
     fold_side 0 = input folded (in_tr.conv1, vnet.py:67-68), 1 = output folded (out_tr.conv1, vnet.py:165-166).
@@ -320,6 +357,7 @@ class DownTransition(_Module):  # vnet.py:82-113
         self.relu2 = _PReLU(st, prefix + ".relu2", out_ch, out_ch)
         self.ops = [LUConv(eng, "%s.ops.%d" % (prefix, i), out_ch) for i in range(n_convs)]
         self.act_down = _BnAct(eng, self.bn1, self.relu1)
+        self.k2 = _K2S2(eng, self.down_conv, out_ch, in_ch, self.kernel, self.stride)
         for i, lu in enumerate(self.ops):
             lu.act = _BnAct(eng, lu.bn1, lu.relu1, self.relu2 if i == n_convs - 1 else None)
 
@@ -339,6 +377,7 @@ class UpTransition(_Module):  # vnet.py:116-156
         self.relu2 = _PReLU(st, prefix + ".relu2", out_ch, out_ch)
         self.ops = [LUConv(eng, "%s.ops.%d" % (prefix, i), out_ch) for i in range(n_convs)]
         self.act_up = _BnAct(eng, self.bn1, self.relu1)
+        self.k2 = _K2S2(eng, self.up_conv, in_ch, half, self.kernel, self.stride)
         for i, lu in enumerate(self.ops):
             lu.act = _BnAct(eng, lu.bn1, lu.relu1, self.relu2 if i == n_convs - 1 else None)
 
@@ -608,8 +647,11 @@ class VNet(_Module):
             c = tr.out_ch
             yd = self._new(n, c, dims[lvl])
             sd = sums(c)
-            ops.conv_strided_fwd(xin, st.view(tr.down_conv.weight), st.view(tr.down_conv.bias), yd, tr.kernel,
-                                 tr.stride, (0, 0, 0), g, sd)
+            if tr.k2.usable(xin.dims):
+                tr.k2.gather(xin, yd, st.view(tr.down_conv.bias), g, sd)
+            else:
+                ops.conv_strided_fwd(xin, st.view(tr.down_conv.weight), st.view(tr.down_conv.bias), yd, tr.kernel,
+                                     tr.stride, (0, 0, 0), g, sd)
             dwn = self._new(n, c, dims[lvl])
             tr.act_down.fwd(yd, dwn, sd)
             mask = self._mask(site, n, c) if tr.if_dropout else None
@@ -651,8 +693,11 @@ class VNet(_Module):
                 ops.channel_scale(skip, xcat.view(half, half), ms, False)
             yu = self._new(n, half, dims[lvl])
             su = sums(half)
-            ops.conv_strided_bwd_data(xd, st.view(tr.up_conv.weight), st.view(tr.up_conv.bias), yu, tr.kernel,
-                                      tr.stride, (0, 0, 0), False, g, su)
+            if tr.k2.usable(dims[lvl]):
+                tr.k2.scatter(xd, yu, st.view(tr.up_conv.bias), False, g, su)
+            else:
+                ops.conv_strided_bwd_data(xd, st.view(tr.up_conv.weight), st.view(tr.up_conv.bias), yu, tr.kernel,
+                                          tr.stride, (0, 0, 0), False, g, su)
             tr.act_up.fwd(yu, xcat.view(0, half), su)
             rec = {"xin": xin, "xd": xd, "mx": mx, "ms": ms, "xcat": xcat, "lu_in": [], "skip_sep": skip is not None}
             cur = xcat
@@ -759,7 +804,11 @@ class VNet(_Module):
             dyu = self._new(n, half, dims[lvl])
             tr.act_up.bwd(g_xcat.view(0, half), dyu)
             g_xin = self._new(n, tr.in_ch, rec["xin"].dims)
-            ops.conv_strided_fwd(dyu, st.view(tr.up_conv.weight), None, g_xin, tr.kernel, tr.stride, (0, 0, 0), 1, None)
+            if tr.k2.usable(dims[lvl]):
+                tr.k2.gather(dyu, g_xin, None)
+            else:
+                ops.conv_strided_fwd(dyu, st.view(tr.up_conv.weight), None, g_xin, tr.kernel, tr.stride, (0, 0, 0), 1,
+                                     None)
             self.strided_wgrad(dyu, rec["xd"], st.grad_view(tr.up_conv.weight), st.grad_view(tr.up_conv.bias),
                                tr.kernel, tr.stride, True)
             if rec["mx"] is not None:
@@ -782,8 +831,11 @@ class VNet(_Module):
             lu_chain_bwd(tr, rec, g_out, g_down, lvl, rec["mask"])
             dyd = self._new(n, c, dims[lvl])
             tr.act_down.bwd(g_down, dyd)
-            ops.conv_strided_bwd_data(dyd, st.view(tr.down_conv.weight), None, g_xin, tr.kernel, tr.stride, (0, 0, 0),
-                                      True, 1, None)
+            if tr.k2.usable(g_xin.dims):
+                tr.k2.scatter(dyd, g_xin, None, True)
+            else:
+                ops.conv_strided_bwd_data(dyd, st.view(tr.down_conv.weight), None, g_xin, tr.kernel, tr.stride,
+                                          (0, 0, 0), True, 1, None)
             self.strided_wgrad(rec["xin"], dyd, st.grad_view(tr.down_conv.weight), st.grad_view(tr.down_conv.bias),
                                tr.kernel, tr.stride, False)
             self._fire(tr)

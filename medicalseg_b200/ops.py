@@ -161,6 +161,24 @@ def k2s2_wgrad(big: B8, small: B8, dw, dbias, bias_from_big, workspace: torch.Te
          _ptr(workspace), workspace.numel() * workspace.element_size(), _stream())
 
 
+def k2s2_packed_bytes(c_red_pad: int, c_out_pad: int) -> int:
+    return call("msb_conv_k2s2_packed_bytes", c_red_pad, c_out_pad)
+
+
+def k2s2_pack(w, packed, c_red, c_out, mode, c_red_pad, c_out_pad):
+    call("msb_conv_k2s2_pack", _ptr(w), _ptr(packed), c_red, c_out, mode, c_red_pad, c_out_pad, _stream())
+
+
+def k2s2_gather(x: B8, packed, bias, cout, out: B8, groups=1, sums=None):
+    call("msb_conv_k2s2_gather", x.mt, _ptr(packed), _ptr(bias), cout, out.mt, x.n, dim3(x.dims), groups, _ptr(sums),
+         _stream())
+
+
+def k2s2_scatter(x: B8, packed, bias, cout, out: B8, accumulate=False, groups=1, sums=None):
+    call("msb_conv_k2s2_scatter", x.mt, _ptr(packed), _ptr(bias), cout, out.mt, x.n, dim3(out.dims), int(accumulate),
+         groups, _ptr(sums), _stream())
+
+
 def k5_out_pad(c_view: int) -> int:
     return call("msb_conv_k5_out_pad", c_view)
 

@@ -365,6 +365,115 @@ def timing_folded():
 
 
 @check
+def k2s2_umma():
+    """tensor-core 2x2x2/stride-2 gather (Conv3D fwd, ConvT dgrad) and scatter (ConvT fwd, Conv3D dgrad) vs torch"""
+    torch, F, ops, B8, _lib = _imports()
+    torch.manual_seed(0)
+    n = 2
+    for ci, co, bd in ((16, 32, (8, 32, 16)), (32, 64, (4, 36, 20)), (64, 128, (6, 8, 8)), (128, 256, (2, 4, 16)),
+                       (256, 128, (4, 8, 8)), (64, 16, (8, 32, 16))):
+        sd = tuple(d // 2 for d in bd)
+        # ---- gather: Conv3D(ci -> co) forward on the big grid
+        x = torch.randn(n, ci, *bd, device="cuda")
+        w = torch.randn(co, ci, 2, 2, 2, device="cuda") * (2.0 / (ci * 8)) ** 0.5
+        b = torch.randn(co, device="cuda")
+        xb = B8.from_ncdhw(x, torch.bfloat16)
+        xq, wq = xb.to_ncdhw(), w.bfloat16().float()
+        ref = F.conv3d(xq, wq, b, stride=2)
+        pk = torch.empty(ops.k2s2_packed_bytes(ci, (co + 15) // 16 * 16), dtype=torch.uint8, device="cuda")
+        ops.k2s2_pack(w, pk, ci, co, 0, ci, (co + 15) // 16 * 16)
+        out = B8(n, co, sd, torch.bfloat16, device="cuda", zero=True)
+        sums = torch.zeros(2 * co, dtype=torch.float64, device="cuda")
+        ops.k2s2_gather(xb, pk, b, co, out, 1, sums)
+        o = out.to_ncdhw()
+        e_g = _rel(o, ref)
+        e_s = float((sums[:co] - o.double().sum((0, 2, 3, 4))).abs().max() / (o.double().sum((0, 2, 3, 4)).abs().max() + 1e-9))
+        # ---- scatter: input gradient of the same conv (dy on the small grid -> big grid), accumulating
+        dy = torch.randn(n, co, *sd, device="cuda")
+        dyb = B8.from_ncdhw(dy, torch.bfloat16)
+        refx = torch.nn.grad.conv3d_input(xq.shape, wq, dyb.to_ncdhw(), stride=2)
+        pk1 = torch.empty(ops.k2s2_packed_bytes(co, (ci + 15) // 16 * 16), dtype=torch.uint8, device="cuda")
+        ops.k2s2_pack(w, pk1, co, ci, 1, co, (ci + 15) // 16 * 16)
+        base = torch.randn(n, ci, *bd, device="cuda")
+        dx = B8.from_ncdhw(base, torch.bfloat16)
+        baseq = dx.to_ncdhw()
+        ops.k2s2_scatter(dyb, pk1, None, ci, dx, True, 1, None)
+        e_d = _rel(dx.to_ncdhw(), baseq + refx)
+        # ---- scatter as ConvTranspose3d forward (weight [co][ci]: co -> ci channels) with bias and BN sums
+        wt = torch.randn(co, ci, 2, 2, 2, device="cuda") * (2.0 / co) ** 0.5
+        bt = torch.randn(ci, device="cuda")
+        reft = F.conv_transpose3d(dyb.to_ncdhw(), wt.bfloat16().float(), bt, stride=2)
+        pk2 = torch.empty(ops.k2s2_packed_bytes(co, (ci + 15) // 16 * 16), dtype=torch.uint8, device="cuda")
+        ops.k2s2_pack(wt, pk2, co, ci, 1, co, (ci + 15) // 16 * 16)
+        outt = B8(n, ci, bd, torch.bfloat16, device="cuda", zero=True)
+        sums2 = torch.zeros(2 * ci, dtype=torch.float64, device="cuda")
+        ops.k2s2_scatter(dyb, pk2, bt, ci, outt, False, 1, sums2)
+        ot = outt.to_ncdhw()
+        e_t = _rel(ot, reft)
+        e_s2 = float((sums2[:ci] - ot.double().sum((0, 2, 3, 4))).abs().max() / (ot.double().sum((0, 2, 3, 4)).abs().max() + 1e-9))
+        print("k2s2", ci, co, bd, "gather", e_g, "sums", e_s, "scatter+acc", e_d, "convT", e_t, "sums", e_s2)
+
+
+@check
+def timing_k2s2():
+    torch, F, ops, B8, _lib = _imports()
+
+    def timeit(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    n = 2
+    for ci, co, d in ((16, 32, 128), (32, 64, 64), (64, 128, 32), (128, 256, 16)):
+        x = B8(n, ci, (d,) * 3, torch.bfloat16, device="cuda"); x.buf.normal_()
+        y = B8(n, co, (d // 2,) * 3, torch.bfloat16, device="cuda"); y.buf.normal_()
+        w = torch.randn(co, ci, 2, 2, 2, device="cuda") * 0.1
+        pk = torch.empty(ops.k2s2_packed_bytes(ci, co), dtype=torch.uint8, device="cuda")
+        ops.k2s2_pack(w, pk, ci, co, 0, ci, co)
+        pk1 = torch.empty(ops.k2s2_packed_bytes(co, ci), dtype=torch.uint8, device="cuda")
+        ops.k2s2_pack(w, pk1, co, ci, 1, co, ci)
+        sums = torch.zeros(2 * co, dtype=torch.float64, device="cuda")
+        mb = (x.buf.numel() + y.buf.numel()) * 2 / 1e6
+        t_g = timeit(lambda: ops.k2s2_gather(x, pk, None, co, y, 1, sums))
+        t_s = timeit(lambda: ops.k2s2_scatter(y, pk1, None, ci, x, False, 1, None))
+        print("k2s2 umma %3d<->%3d @%3d: gather %.3f ms (%.0f GB/s)  scatter %.3f ms (%.0f GB/s)" %
+              (ci, co, d, t_g, mb / t_g, t_s, mb / t_s))
+
+
+@check
+def prof_fwd():
+    """where the MMA-issuing warp of the 5x5x5 forward kernel waits (debug flag 5), per layer shape"""
+    import ctypes as C
+    torch, F, ops, B8, _lib = _imports()
+    n = 2
+    for cin, cout, d in ((32, 32, 128), (64, 64, 64), (128, 128, 32), (256, 256, 16)):
+        dims = (d,) * 3
+        x = B8(n, cin, dims, torch.bfloat16, device="cuda"); x.buf.normal_()
+        y = B8(n, cout, dims, torch.bfloat16, device="cuda")
+        w = torch.randn(cout, cin, 5, 5, 5, device="cuda") * 0.02
+        cp = ops.k5_out_pad(cout)
+        packed = torch.empty(ops.k5_packed_bytes(cin, cp), dtype=torch.uint8, device="cuda")
+        ops.k5_pack(w, packed, cout, cin, 0, cin, cp)
+        sums = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
+        ops.k5_fwd(x, packed, None, cout, y, False, None, 1, sums)
+        _lib.call("msb_debug_set", 5, 1)
+        ops.k5_fwd(x, packed, None, cout, y, False, None, 1, sums)
+        torch.cuda.synchronize()
+        buf = (C.c_longlong * (148 * 4))()
+        _lib.call("msb_debug_read_prof", C.cast(buf, C.c_void_p))
+        _lib.call("msb_debug_set", 5, 0)
+        t = torch.tensor(list(buf), dtype=torch.float64).view(148, 4)
+        t = t[t[:, 0] > 0]
+        m = t.mean(0)
+        print("fwd %d->%d @%d: CTAs %d  MMA-warp clocks: total %.0f  wait weights %.1f%%  wait halo %.1f%%  wait accumulator %.1f%%"
+              % (cin, cout, d, t.shape[0], m[0], 100 * m[1] / m[0], 100 * m[2] / m[0], 100 * m[3] / m[0]))
+
+
+@check
 def timing():
     """device time of the dominant layers at the benchmark shapes (batch 2)"""
     torch, F, ops, B8, _lib = _imports()

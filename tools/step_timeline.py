@@ -1,0 +1,79 @@
+"""GPU timeline of the bench train step via torch.profiler (CUPTI): per-kernel device time inside real steps
+(warm caches, real overlap) plus the idle gaps between kernels - complements the serialized ncu launch list.
+
+    python tools/step_timeline.py [steps]        # prints a per-kernel table for the traced steps
+"""
+import collections
+import os
+import re
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def main():
+    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    import bench
+    from medicalseg_b200.models import VNet, losses as L
+    from medicalseg_b200.optimizer import Momentum, PolynomialDecay
+
+    device = torch.device("cuda", 0)
+    model = VNet(num_classes=bench.NUM_CLASSES, compute_dtype="bf16", seed=0)
+    model.train()
+    losses = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1])], "coef": [1]}
+    opt = Momentum(PolynomialDecay(0.001, 15000), model.parameters(), 0.9, 1e-4)
+    img, lab = bench.synthetic_gpu_batch(device, seed=0)
+
+    def step():
+        logits_list = model(img)
+        loss_list, dice = L.loss_computation(logits_list, lab, losses)
+        loss = sum(loss_list)
+        loss.backward()
+        opt.step()
+        opt._learning_rate.step()
+        model.clear_gradients()
+
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in evs), key=lambda t: t[0])
+    if not ks:
+        print("no CUDA events captured (CUPTI unavailable?)")
+        return
+    agg = collections.OrderedDict()
+    busy = 0.0
+    gaps = 0.0
+    biggest = []
+    last_end = ks[0][0]
+    for s, e, name in ks:
+        name = re.sub(r"\(.*$", "", name)
+        name = re.sub(r"^void ", "", name)
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += (e - s)
+        busy += (e - s)
+        if s > last_end:
+            gaps += s - last_end
+            biggest.append((s - last_end, name))
+        last_end = max(last_end, e)
+    span = ks[-1][1] - ks[0][0]
+    print("traced %d steps: span %.3f ms/step, kernel time %.3f ms/step, idle gaps %.3f ms/step, %d launches/step" %
+          (steps, span / steps / 1e3, busy / steps / 1e3, gaps / steps / 1e3, len(ks) // steps))
+    print("%-92s %6s %9s %6s" % ("kernel", "n/step", "ms/step", "share"))
+    for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print("%-92s %6.1f %9.3f %5.1f%%" % (name[:92], n / steps, t / steps / 1e3, 100 * t / busy))
+    biggest.sort(reverse=True)
+    print("largest gaps (us, kernel that followed):", [(round(g, 1), n[:40]) for g, n in biggest[:8]])
+
+
+if __name__ == "__main__":
+    main()
