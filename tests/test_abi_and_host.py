@@ -100,6 +100,7 @@ def test_param_store_layout_matches_reference_parameter_tree():
         pass
     eng = Eng()
     eng.store = V.ParamStore()
+    eng.dtype = torch.float32
     blocks = [V.InputTransition(eng, "in_tr", 1), V.DownTransition(eng, "down_tr32", 16, 1, False, (2, 2, 2), (2, 2, 2)),
               V.UpTransition(eng, "up_tr32", 64, 32, 1, False, False, (2, 2, 2), (2, 2, 2)),
               V.OutputTransition(eng, "out_tr", 32, 3)]
