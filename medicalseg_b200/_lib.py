@@ -52,6 +52,8 @@ SIGNATURES = {
     "msb_conv_k5_out_pad": (I, [I]),
     "msb_conv_k5_pack": (I, [P, P, I, I, I, I, I, P]),
     "msb_conv_k5_fwd": (I, [T, P, P, I, T, I, D3, I, P, I, P, P]),
+    "msb_conv_k5_fwd_workspace_bytes": (SZ, [I, I, D3, I]),
+    "msb_conv_k5_fwd_ws": (I, [T, P, P, I, T, I, D3, I, P, I, P, P, SZ, P]),
     "msb_conv_k5_wgrad_workspace_bytes": (SZ, [I, I]),
     "msb_conv_k5_wgrad": (I, [T, T, P, P, I, I, I, D3, P, SZ, P]),
     "msb_fold_w_f32": (I, [P, I, T, I, D3, I, P]),
@@ -80,7 +82,7 @@ SIGNATURES = {
 }
 
 _NO_STATUS = {"msb_version", "msb_last_error_string", "msb_conv_k5_packed_bytes", "msb_conv_k5_out_pad",
-              "msb_conv_k2s2_wgrad_workspace_bytes",
+              "msb_conv_k2s2_wgrad_workspace_bytes", "msb_conv_k5_fwd_workspace_bytes",
               "msb_conv_k5_wgrad_workspace_bytes", "msb_conv_k551_packed_bytes", "msb_conv_k2s2_packed_bytes",
               "msb_conv_k551_wgrad_workspace_bytes"}
 

@@ -41,6 +41,43 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 constexpr int kNumSMs = 148;
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// Every kernel of the train step is launched with the programmatic-stream-serialization attribute: kernel N+1 may be
+// scheduled while kernel N drains, runs its prologue (barrier init, TMEM allocation, descriptor prefetch, parameter
+// loads from the kernel arguments) and blocks in pdl_wait() until kernel N has completed and its writes are visible.
+// RULES: (1) a kernel launched through MSB_LAUNCH_PDL calls pdl_wait() before its first global-memory access;
+// (2) pdl_trigger() is issued only AFTER the kernel's own TMEM allocation (a dependent CTA that became resident first
+// and grabbed the TMEM columns would otherwise deadlock its predecessor).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+extern int g_pdl_enabled;  // msb_debug_set(7, 1) disables PDL (A/B measurements)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl_enabled;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+#define MSB_LAUNCH_PDL(kernel, grid, block, smem, st, ...)                                           \
+  do {                                                                                               \
+    cudaError_t _e = ::msb::launch_pdl(kernel, grid, block, smem, st, __VA_ARGS__);                  \
+    if (_e != cudaSuccess) {                                                                         \
+      ::msb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return MSB_ERR_CUDA;                                                                           \
+    }                                                                                                \
+  } while (0)
+
 // ---- 8-channel vector load/store in the B8 layout -------------------------------------------------
 template <typename T>
 struct Vec8;

@@ -13,6 +13,8 @@ constexpr int kFoldC = 16;  // folded channel count (two 8-channel planes)
 // ---- fold from an NCDHW f32 tensor with c_real channels -------------------------------------------------------
 __global__ void __launch_bounds__(256) fold_w_f32_kernel(const float* __restrict__ x, int c_real, msb_tensor out, int64_t s,
                                                          int w_ext, int sign) {
+  pdl_wait();
+  pdl_trigger();
   const int n = blockIdx.y;
   const float* xn = x + (int64_t)n * c_real * s;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < s; v += (int64_t)gridDim.x * blockDim.x) {
@@ -43,6 +45,8 @@ __global__ void __launch_bounds__(256) fold_w_f32_kernel(const float* __restrict
 // ---- fold from a B8 bf16 view whose first c_real (<= 3) channels are real -----------------------------------------
 __global__ void __launch_bounds__(256) fold_w_b8_kernel(msb_tensor x, int c_real, msb_tensor out, int64_t s, int w_ext,
                                                         int sign) {
+  pdl_wait();
+  pdl_trigger();
   const int n = blockIdx.y;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < s; v += (int64_t)gridDim.x * blockDim.x) {
     const int w = (int)(v % w_ext);
@@ -77,6 +81,8 @@ template <typename TP>
 __global__ void __launch_bounds__(256) unfold_w_kernel(msb_tensor p, const float* __restrict__ bias, int c_real,
                                                        msb_tensor out, int64_t s, int w_ext, int groups,
                                                        double* __restrict__ sums) {
+  pdl_wait();
+  pdl_trigger();
   const int n = blockIdx.y;
   float b[3] = {0.f, 0.f, 0.f};
   for (int c = 0; c < c_real; ++c) b[c] = bias != nullptr ? __ldg(bias + c) : 0.f;
@@ -161,7 +167,7 @@ int msb_fold_w_f32(const float* x, int c_real, msb_tensor out, int n, msb_dim3 d
   MSB_REQUIRE(c_real > 0 && 5 * c_real <= kFoldC, "msb_fold_w_f32: at most 3 channels can be folded");
   MSB_REQUIRE(dims.d > 0 && dims.h > 0 && dims.w > 0 && (sign == 1 || sign == -1), "msb_fold_w_f32: bad dims / sign");
   const int64_t s = (int64_t)dims.d * dims.h * dims.w;
-  fold_w_f32_kernel<<<dim3(fold_blocks(s), n), 256, 0, as_stream(stream)>>>(x, c_real, out, s, dims.w, sign);
+  MSB_LAUNCH_PDL(fold_w_f32_kernel, dim3(fold_blocks(s), n), dim3(256), 0, as_stream(stream), x, c_real, out, s, dims.w, sign);
   MSB_LAUNCH_OK();
   return MSB_OK;
 }
@@ -172,7 +178,7 @@ int msb_fold_w(msb_tensor x, int c_real, msb_tensor out, int n, msb_dim3 dims, i
   MSB_REQUIRE(c_real > 0 && c_real <= 3 && c_real <= x.c, "msb_fold_w: at most 3 channels can be folded");
   MSB_REQUIRE(dims.d > 0 && dims.h > 0 && dims.w > 0 && (sign == 1 || sign == -1), "msb_fold_w: bad dims / sign");
   const int64_t s = (int64_t)dims.d * dims.h * dims.w;
-  fold_w_b8_kernel<<<dim3(fold_blocks(s), n), 256, 0, as_stream(stream)>>>(x, c_real, out, s, dims.w, sign);
+  MSB_LAUNCH_PDL(fold_w_b8_kernel, dim3(fold_blocks(s), n), dim3(256), 0, as_stream(stream), x, c_real, out, s, dims.w, sign);
   MSB_LAUNCH_OK();
   return MSB_OK;
 }
@@ -186,9 +192,9 @@ int msb_unfold_w(msb_tensor p, const float* bias, int c_real, msb_tensor out, in
   const int64_t s = (int64_t)dims.d * dims.h * dims.w;
   const dim3 grid(fold_blocks(s), n);
   if (p.dtype == MSB_F32)
-    unfold_w_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(p, bias, c_real, out, s, dims.w, groups, sums);
+    MSB_LAUNCH_PDL(unfold_w_kernel<float>, grid, dim3(256), 0, as_stream(stream), p, bias, c_real, out, s, dims.w, groups, sums);
   else
-    unfold_w_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(p, bias, c_real, out, s, dims.w, groups, sums);
+    MSB_LAUNCH_PDL(unfold_w_kernel<__nv_bfloat16>, grid, dim3(256), 0, as_stream(stream), p, bias, c_real, out, s, dims.w, groups, sums);
   MSB_LAUNCH_OK();
   return MSB_OK;
 }

@@ -72,6 +72,8 @@ __global__ void __launch_bounds__(256, 1)
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();  // after our own TMEM allocation (common.cuh, PDL rules)
+  pdl_wait();
 
   const int tiles_per_n = p.sd * p.tiles_h * p.tiles_w;
   const int num_items = p.n * tiles_per_n * p.tap_groups;
@@ -244,6 +246,8 @@ __global__ void __launch_bounds__(256, 1)
 // with cr = chunk*16 + k8*8 + j
 __global__ void __launch_bounds__(256) pack_k2s2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed,
                                                         int c_red, int c_out, int mode, int c_red_pad, int cpad, int tg) {
+  pdl_wait();
+  pdl_trigger();
   const int chunks = c_red_pad / 16;
   const int64_t total = (int64_t)8 * c_red_pad * cpad;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -307,8 +311,7 @@ static int launch_k2s2(int mode, const msb_tensor& x, const void* packed, const 
     MSB_CUDA_OK(cudaFuncSetAttribute(conv_k2s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2SmemBytes));
     attr_set = true;
   }
-  conv_k2s2_kernel<<<grid, 256, kK2SmemBytes, st>>>(tmap, p);
-  MSB_LAUNCH_OK();
+  MSB_LAUNCH_PDL(conv_k2s2_kernel, dim3(grid), dim3(256), kK2SmemBytes, st, tmap, p);
   return MSB_OK;
 }
 
@@ -329,9 +332,8 @@ int msb_conv_k2s2_pack(const float* w, void* packed, int c_red, int c_out, int m
               "msb_conv_k2s2_pack: padded channel counts must be multiples of 16 covering the real ones (out <= 256)");
   const int64_t total = (int64_t)8 * c_red_pad * c_out_pad;
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  pack_k2s2_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), c_red, c_out,
-                                                          mode, c_red_pad, c_out_pad, k2_tg(c_out_pad));
-  MSB_LAUNCH_OK();
+  MSB_LAUNCH_PDL(pack_k2s2_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), w,
+                 reinterpret_cast<__nv_bfloat16*>(packed), c_red, c_out, mode, c_red_pad, c_out_pad, k2_tg(c_out_pad));
   return MSB_OK;
 }
 

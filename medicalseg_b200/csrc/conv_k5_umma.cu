@@ -71,13 +71,25 @@ struct FwdParams {
   int kw_taps;                           // 5 = full 5x5x5 kernel; 1 = 5x5x1 (kd,kh) kernel of the w-folded convs
   int out_f32;                           // store f32 (B8 f32 view) instead of bf16; no accumulate, no BN sums
   long long* prof;                       // bring-up: per-CTA clocks the MMA warp spent {total, w_full, halo_full, acc_empty}
+  float* ws;                             // split-K: f32 partial sums [n][out_c8][D*H*W][8], zero on entry
+  int ksplit, chunks_per_split;          // split-K: item = tile * ksplit + slice; slice covers chunks_per_split 16-channel chunks
 };
 
-template <int NPAD, int TD, int J, int ACC_SETS, int NS>
+// f32 vector reduction into global memory (sm_90+): 4 consecutive floats per instruction
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// SPLITK: small volumes (fewer tiles than SMs).  The reduction over the input channels is split across CTAs (item =
+// (tile, slice of 16-channel chunks)): every CTA streams only ITS slice of the weight set (the layer is otherwise
+// bound by pulling the whole 4-16 MB weight set through every SM) and adds its f32 partial tile into p.ws with vector
+// reductions; splitk_finalize_kernel applies bias / accumulate / rounding / BN sums and re-zeroes the workspace.
+template <int NPAD, int TD, int J, int ACC_SETS, int NS, bool SPLITK = false>
 __global__ void __launch_bounds__(256, 1)
     conv_k5_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const FwdParams p) {
   using Cfg = FwdCfg<NPAD, TD, J, ACC_SETS>;
   static_assert(NS == 1 || J == 1, "channel slicing only without plane stacking");
+  static_assert(!SPLITK || (NS == 1 && J == 1), "split-K works on whole tiles");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* halo_smem = smem;                                   // [2][kHaloBytes]
@@ -110,23 +122,36 @@ __global__ void __launch_bounds__(256, 1)
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();  // after our own TMEM allocation (common.cuh, PDL rules)
+  pdl_wait();
 
   const int chunks = p.cin_pad / 16;
   const int items_per_n = p.dblocks * p.tiles_h * p.tiles_w;
-  const int num_items = p.n * items_per_n * NS;        // item = tile * NS + channel slice
+  const int kdiv = SPLITK ? p.ksplit : NS;             // items per tile
+  const int num_items = p.n * items_per_n * kdiv;      // item = tile * NS + channel slice | tile * ksplit + K slice
   constexpr int n_slice = Cfg::kNMma / NS;             // MMA N per item
+  auto chunk_range = [&](int item, int& ck0, int& ck1) {
+    if (SPLITK) {
+      ck0 = (item % kdiv) * p.chunks_per_split;
+      ck1 = min(chunks, ck0 + p.chunks_per_split);
+    } else {
+      ck0 = 0; ck1 = chunks;
+    }
+  };
 
   if (warp == 0) {
     // ================= halo TMA producer (whole warp runs the uniform loop, one elected lane issues) ==========
     const bool leader = ptx::elect_one();
     uint32_t use = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int tile = item / NS;
+      const int tile = item / kdiv;
       const int n = tile / items_per_n;
       int r = tile % items_per_n;
       const int tw = r % p.tiles_w; r /= p.tiles_w;
       const int th = r % p.tiles_h; const int db = r / p.tiles_h;
-      for (int ck = 0; ck < chunks; ++ck, ++use) {
+      int ck0, ck1;
+      chunk_range(item, ck0, ck1);
+      for (int ck = ck0; ck < ck1; ++ck, ++use) {
         const uint32_t b = use & 1, ph = (use >> 1) & 1;
         ptx::mbar_wait(BAR(2 + b), ph ^ 1);
         if (leader) {
@@ -143,7 +168,9 @@ __global__ void __launch_bounds__(256, 1)
     uint32_t use = 0;
     const int stages_per_chunk = 5 * p.kw_taps;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      for (int ck = 0; ck < chunks; ++ck) {
+      int ck0, ck1;
+      chunk_range(item, ck0, ck1);
+      for (int ck = ck0; ck < ck1; ++ck) {
         const uint8_t* src =
             reinterpret_cast<const uint8_t*>(p.packed) + (size_t)ck * stages_per_chunk * 2 * Cfg::kWLoadBytes;
         for (int st = 0; st < stages_per_chunk; ++st, ++use) {
@@ -183,8 +210,10 @@ __global__ void __launch_bounds__(256, 1)
       if (prof) t_a += clock64() - tq;
       ptx::tc_fence_after();
       const uint32_t d_base = tmem_u + as * Cfg::kAccCols;
-      const uint32_t b_slice = (uint32_t)((item % NS) * n_slice);  // first weight row (16 B each) of this slice
-      for (int ck = 0; ck < chunks; ++ck, ++huse) {
+      const uint32_t b_slice = SPLITK ? 0u : (uint32_t)((item % NS) * n_slice);  // first weight row (16 B each) of this slice
+      int ck0, ck1;
+      chunk_range(item, ck0, ck1);
+      for (int ck = ck0; ck < ck1; ++ck, ++huse) {
         const uint32_t hb = huse & 1, hph = (huse >> 1) & 1;
         if (prof) tq = clock64();
         ptx::mbar_wait(BAR(0 + hb), hph);
@@ -200,7 +229,7 @@ __global__ void __launch_bounds__(256, 1)
           const uint32_t hw_off =  // 16-byte units; the single w tap of the 5x5x1 kernel is the centre one
               p.kw_taps == 5 ? (uint32_t)((st / 5) * kHaloW + (st % 5)) : (uint32_t)(st * kHaloW + 2);
           const uint32_t a_lo1 = a_lo0 + hw_off;
-          const uint32_t first = (ck | st) != 0 ? 1u : 0u;
+          const uint32_t first = ((ck - ck0) | st) != 0 ? 1u : 0u;
 #pragma unroll
           for (int g = 0; g < TD / J; ++g) {
 #pragma unroll
@@ -232,8 +261,8 @@ __global__ void __launch_bounds__(256, 1)
     float* my_stats = stat_smem + q * 2 * NPAD;
     uint32_t iuse = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
-      const int tile = item / NS;
-      const int c_first = (item % NS) * n_slice;  // first output channel of this slice (nsplit > 1 only with J == 1)
+      const int tile = item / kdiv;
+      const int c_first = SPLITK ? 0 : (item % NS) * n_slice;  // first output channel of this slice (nsplit > 1 only with J == 1)
       const int n = tile / items_per_n;
       int r = tile % items_per_n;
       const int tw = r % p.tiles_w; r /= p.tiles_w;
@@ -253,6 +282,18 @@ __global__ void __launch_bounds__(256, 1)
         for (int cb = 0; cb < (NPAD / NS) / 16; ++cb) {
           float acc[16];
           ptx::tmem_ld16(t_base + td * NPAD + cb * 16, acc);
+          if constexpr (SPLITK) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int c8 = cb * 2 + k;
+              if (c8 < p.out_c8 && ok) {
+                float* dst = p.ws + (((int64_t)n * p.out_c8 + c8) * S + v) * 8;
+                red_add_v4(dst, acc[k * 8 + 0], acc[k * 8 + 1], acc[k * 8 + 2], acc[k * 8 + 3]);
+                red_add_v4(dst + 4, acc[k * 8 + 4], acc[k * 8 + 5], acc[k * 8 + 6], acc[k * 8 + 7]);
+              }
+            }
+            continue;
+          }
           float sq[16];
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
@@ -302,7 +343,7 @@ __global__ void __launch_bounds__(256, 1)
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(BAR(6 + as));
-      if (p.sums != nullptr && p.groups > 1) {
+      if (!SPLITK && p.sums != nullptr && p.groups > 1) {
         // per-instance statistics: flush after every item (an item never straddles two n)
         __syncwarp();
         for (int i = lane; i < 2 * NPAD; i += 32) {
@@ -314,7 +355,7 @@ __global__ void __launch_bounds__(256, 1)
         __syncwarp();
       }
     }
-    if (p.sums != nullptr && p.groups == 1) {
+    if (!SPLITK && p.sums != nullptr && p.groups == 1) {
       __syncwarp();
       for (int i = lane; i < 2 * NPAD; i += 32) {
         const int stat = i / NPAD, c = i % NPAD;
@@ -328,6 +369,66 @@ __global__ void __launch_bounds__(256, 1)
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// split-K tail: out = round_bf16(ws + bias [* ch_scale + out]), BN partial sums of the rounded values, ws <- 0
+__global__ void __launch_bounds__(256) splitk_finalize_kernel(float* __restrict__ ws, const float* __restrict__ bias,
+                                                              int cout_real, msb_tensor out, int64_t s, int accumulate,
+                                                              const float* __restrict__ ch_scale, int groups,
+                                                              double* __restrict__ sums, int sums_c) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float red[8][16];
+  const int c8 = blockIdx.y, n = blockIdx.z, out_c8 = gridDim.y;
+  const int64_t v0 = (int64_t)blockIdx.x * 2048, v1 = min(v0 + (int64_t)2048, s);
+  float b[8], sc[8], acc[16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c8 * 8 + j;
+    b[j] = (bias != nullptr && c < cout_real) ? __ldg(bias + c) : 0.f;
+    sc[j] = ch_scale ? __ldg(ch_scale + (int64_t)n * out.c + c) : 1.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  float* wp = ws + ((int64_t)n * out_c8 + c8) * s * 8;
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += 256) {
+    float o[8];
+    Vec8<float>::load(wp + v * 8, o);
+    *reinterpret_cast<float4*>(wp + v * 8) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(wp + v * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    __nv_bfloat16* dst = view_ptr<__nv_bfloat16>(out, n, c8, s, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] += b[j];
+    if (accumulate) {
+      float old[8];
+      Vec8<__nv_bfloat16>::load(dst, old);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(o[j], sc[j], old[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j] = Vec8<__nv_bfloat16>::round(o[j]);
+      acc[j] += o[j];
+      acc[8 + j] += o[j] * o[j];
+    }
+    Vec8<__nv_bfloat16>::store(dst, o);
+  }
+  if (sums == nullptr) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float r = warp_sum(acc[i]);
+    if (lane == 0) red[warp][i] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    double t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += (double)red[w][threadIdx.x];
+    const int stat = threadIdx.x >> 3, j = threadIdx.x & 7, c = c8 * 8 + j;
+    const int g = groups == 1 ? 0 : n;
+    if (c < sums_c) atomicAdd(&sums[((int64_t)stat * groups + g) * sums_c + c], t);
   }
 }
 
@@ -391,6 +492,8 @@ __global__ void __launch_bounds__(256, 1)
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();  // after our own TMEM allocation (common.cuh, PDL rules)
+  pdl_wait();
 
   const int num_items = p.num_passes * p.chunks;
   const int tiles_per_n = p.d * p.tiles_h * p.tiles_w;
@@ -518,6 +621,8 @@ __global__ void __launch_bounds__(256, 1)
 // dw[co][ci][tap] += ws[tap][co][ci]
 __global__ void __launch_bounds__(256) wgrad_unpack_kernel(const float* __restrict__ ws, float* __restrict__ dw,
                                                            int cout, int cin) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t total = (int64_t)cout * cin * kNumTaps;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int tap = (int)(i % kNumTaps);
@@ -528,6 +633,8 @@ __global__ void __launch_bounds__(256) wgrad_unpack_kernel(const float* __restri
 
 __global__ void __launch_bounds__(256) channel_sum_bf16_kernel(msb_tensor x, int64_t s, int c_real,
                                                                float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[8][8];
   const int c8 = blockIdx.y, n = blockIdx.z;
   const int64_t chunk = 8192;
@@ -561,6 +668,8 @@ __global__ void __launch_bounds__(256) channel_sum_bf16_kernel(msb_tensor x, int
 // dW[sc][bc][tap] = sum_o big[2o+tap][bc] * small[o][sc] becomes a pointwise (1x1x1) weight gradient.
 __global__ void __launch_bounds__(256) s2d_k2_kernel(msb_tensor x, __nv_bfloat16* __restrict__ xs, int c8n, int sd,
                                                      int sh, int sw) {
+  pdl_wait();
+  pdl_trigger();
   const int plane = blockIdx.y, n = blockIdx.z;  // plane = tap * c8n + c8
   const int tap = plane / c8n, c8 = plane % c8n;
   const int kd = tap >> 2, kh = (tap >> 1) & 1, kw = tap & 1;
@@ -579,6 +688,8 @@ __global__ void __launch_bounds__(256) s2d_k2_kernel(msb_tensor x, __nv_bfloat16
 // dw[sc][bc][tap] += ws[sc][tap*cbig + bc]
 __global__ void __launch_bounds__(256) k2s2_unpack_kernel(const float* __restrict__ ws, float* __restrict__ dw,
                                                           int csmall, int cbig) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t total = (int64_t)csmall * cbig * 8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int tap = (int)(i & 7);
@@ -595,6 +706,8 @@ __global__ void __launch_bounds__(256) k2s2_unpack_kernel(const float* __restric
 // conv's Cout, produces its Cin, taps mirrored).
 __global__ void __launch_bounds__(256) pack_k5_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed,
                                                       int cout, int cin, int mode, int cin_pad, int cout_pad) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float slab[16][kNumTaps + 1];
   const int oc = blockIdx.x, chunk = blockIdx.y;
   for (int i = threadIdx.x; i < 16 * kNumTaps; i += 256) {
@@ -643,6 +756,8 @@ __device__ __forceinline__ float fold_w_elem(const float* __restrict__ w, int co
 __global__ void __launch_bounds__(256) pack_k551_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed,
                                                         int cout, int cin, int mode, int fold_side, int cin_pad,
                                                         int cout_pad) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t total = (int64_t)cin_pad * 25 * cout_pad;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int j = (int)(i & 7);
@@ -663,6 +778,8 @@ __global__ void __launch_bounds__(256) pack_k551_kernel(const float* __restrict_
 // dw[co][ci][kd][kh][jw] += ws[kd*5+kh][oc][rc]   (ws strides: cout_f x cin_f = folded channel counts)
 __global__ void __launch_bounds__(256) wgrad551_unpack_kernel(const float* __restrict__ ws, float* __restrict__ dw,
                                                               int cout, int cin, int fold_side) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t total = (int64_t)cout * cin * kNumTaps;
   const int cout_f = fold_side == 0 ? cout : 5 * cout, cin_f = fold_side == 0 ? 5 * cin : cin;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -795,8 +912,7 @@ static int launch_fwd_ns(const CUtensorMap& tmap, FwdParams& p, int tiles, cudaS
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  conv_k5_fwd_kernel<NPAD, TD, J, ACC_SETS, NS><<<grid, 256, Cfg::kSmemBytes, st>>>(tmap, p);
-  MSB_LAUNCH_OK();
+  MSB_LAUNCH_PDL((conv_k5_fwd_kernel<NPAD, TD, J, ACC_SETS, NS>), dim3(grid), dim3(256), Cfg::kSmemBytes, st, tmap, p);
   return MSB_OK;
 }
 
@@ -819,6 +935,47 @@ static int launch_fwd(const msb_tensor& x, msb_dim3 dims, FwdParams& p, cudaStre
   return launch_fwd_ns<NPAD, TD, J, ACC_SETS, 1>(tmap, p, tiles, st);
 }
 
+// split-K launch (see conv_k5_fwd_kernel): TD planes x NPAD columns fill the 512 TMEM columns with ONE accumulator set
+template <int NPAD, int TD>
+static int launch_fwd_splitk(const msb_tensor& x, msb_dim3 dims, FwdParams& p, int ksplit, const float* bias,
+                             cudaStream_t st) {
+  using Cfg = FwdCfg<NPAD, TD, 1, 1>;
+  CUtensorMap tmap;
+  int rc = make_b8_tmap(&tmap, x, p.n, dims, kHaloW, kHaloH, TD + 4, 2);
+  if (rc) return rc;
+  p.dblocks = (p.d + TD - 1) / TD;
+  p.nsplit = 1;
+  p.ksplit = ksplit;
+  p.chunks_per_split = (p.cin_pad / 16 + ksplit - 1) / ksplit;
+  const int items = p.n * p.dblocks * p.tiles_h * p.tiles_w * ksplit;
+  const int grid = items < kNumSMs ? items : kNumSMs;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MSB_CUDA_OK(cudaFuncSetAttribute(conv_k5_fwd_kernel<NPAD, TD, 1, 1, 1, true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  MSB_LAUNCH_PDL((conv_k5_fwd_kernel<NPAD, TD, 1, 1, 1, true>), dim3(grid), dim3(256), Cfg::kSmemBytes, st, tmap, p);
+  const int64_t S = (int64_t)p.d * p.h * p.w;
+  const dim3 fgrid((unsigned)((S + 2047) / 2048), (unsigned)p.out_c8, (unsigned)p.n);
+  MSB_LAUNCH_PDL(splitk_finalize_kernel, fgrid, dim3(256), 0, st, p.ws, bias, p.cout_real, p.out, S, p.accumulate,
+                 p.ch_scale, p.groups, p.sums, p.sums_c);
+  return MSB_OK;
+}
+
+// number of K slices the split-K path would use for this shape (0 = use the regular path)
+static int splitk_slices(int npad, int n, msb_dim3 dims, int cin_pad) {
+  if (npad != 128 && npad != 256) return 0;
+  const int td = npad == 256 ? 2 : 4;
+  const int tiles = n * ((dims.d + td - 1) / td) * ((dims.h + kTileH - 1) / kTileH) * ((dims.w + kTileW - 1) / kTileW);
+  if (tiles * 2 > kNumSMs) return 0;  // enough tiles to fill the SMs: whole-K items reuse the weights better
+  const int chunks = cin_pad / 16;
+  int ks = kNumSMs / tiles;
+  if (ks > chunks) ks = chunks;
+  while (ks > 1 && chunks % ks != 0) --ks;
+  return ks >= 2 ? ks : 0;
+}
+
 static inline int pad16(int c) { return (c + 15) / 16 * 16; }
 
 template <int NPAD, int TH>
@@ -832,7 +989,7 @@ static int launch_wgrad(const msb_tensor& x, const msb_tensor& dy, WgParams& p, 
   p.passes_per_group = (p.units_total + amax - 1) / amax;
   p.units_per_pass = (p.units_total + p.passes_per_group - 1) / p.passes_per_group;
   p.num_passes = p.mhalves * p.kd_groups * p.passes_per_group;
-  int chunks = (2 * kNumSMs + p.num_passes - 1) / p.num_passes;
+  int chunks = p.num_passes <= 2 * kNumSMs ? (2 * kNumSMs) / p.num_passes : 1;  // <= 2 items per CTA
   if (chunks > p.total_tiles) chunks = p.total_tiles;
   if (chunks < 1) chunks = 1;
   p.tiles_per_chunk = (p.total_tiles + chunks - 1) / chunks;
@@ -845,8 +1002,7 @@ static int launch_wgrad(const msb_tensor& x, const msb_tensor& dy, WgParams& p, 
   const int grid = items < kNumSMs ? items : kNumSMs;
   MSB_CUDA_OK(cudaFuncSetAttribute(conv_k5_wgrad_kernel<NPAD, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
-  conv_k5_wgrad_kernel<NPAD, TH><<<grid, 256, Cfg::kSmemBytes, st>>>(tmx, tmdy, p);
-  MSB_LAUNCH_OK();
+  MSB_LAUNCH_PDL((conv_k5_wgrad_kernel<NPAD, TH>), dim3(grid), dim3(256), Cfg::kSmemBytes, st, tmx, tmdy, p);
   return MSB_OK;
 }
 
@@ -866,6 +1022,7 @@ int msb_debug_read_prof(long long* host_out /* [148][4] */) {
 int msb_debug_set(int key, int value) {
   if (key < 0 || key >= 8) return MSB_ERR_INVALID;
   g_debug_flags[key] = value;
+  if (key == 7) g_pdl_enabled = value ? 0 : 1;
   return MSB_OK;
 }
 
@@ -879,9 +1036,8 @@ int msb_conv_k5_pack(const float* w, void* packed, int cout, int cin, int mode, 
   MSB_REQUIRE(cin_pad % 16 == 0 && cout_pad % 16 == 0, "msb_conv_k5_pack: padded channel counts must be multiples of 16");
   MSB_REQUIRE(mode == 0 ? (cin_pad >= cin && cout_pad >= cout) : (cin_pad >= cout && cout_pad >= cin),
               "msb_conv_k5_pack: padded channel counts too small");
-  pack_k5_kernel<<<dim3(cout_pad, cin_pad / 16), 256, 0, as_stream(stream)>>>(
-      w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, mode, cin_pad, cout_pad);
-  MSB_LAUNCH_OK();
+  MSB_LAUNCH_PDL(pack_k5_kernel, dim3(cout_pad, cin_pad / 16), dim3(256), 0, as_stream(stream), w,
+                 reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, mode, cin_pad, cout_pad);
   return MSB_OK;
 }
 
@@ -889,7 +1045,8 @@ int msb_conv_k5_out_pad(int cout_view);
 
 static int conv_k5_fwd_impl(const char* who, msb_tensor x, const void* packed, const float* bias, int cout,
                            msb_tensor out, int n, msb_dim3 dims, int accumulate, const float* ch_scale, int groups,
-                           double* sums, int kw_taps, void* stream) {
+                           double* sums, int kw_taps, void* stream, void* workspace = nullptr,
+                           size_t workspace_bytes = 0) {
   MSB_REQUIRE(view_ok(x) && view_ok(out) && x.dtype == MSB_BF16 && packed && n > 0, "%s: bf16 B8 input view required", who);
   MSB_REQUIRE(out.dtype == MSB_BF16 || (kw_taps == 1 && !accumulate && sums == nullptr),
               "%s: f32 output only for the 5x5x1 kernel without accumulate / BN sums", who);
@@ -913,9 +1070,21 @@ static int conv_k5_fwd_impl(const char* who, msb_tensor x, const void* packed, c
     MSB_CUDA_OK(cudaMemsetAsync(g_prof_buf, 0, kNumSMs * 4 * sizeof(long long), as_stream(stream)));
     p.prof = g_prof_buf;
   }
+  p.ws = nullptr; p.ksplit = 1; p.chunks_per_split = x.c / 16;
   cudaStream_t st = as_stream(stream);
   const int npad_sel = msb_conv_k5_out_pad(out.c);
   // NOTE: the packed operand must have been built with cout_pad == npad_sel.
+  if (workspace != nullptr && kw_taps == 5 && out.dtype == MSB_BF16 && g_debug_flags[6] == 0) {
+    const int ks = splitk_slices(npad_sel, n, dims, x.c);
+    if (ks > 0) {
+      const size_t need = (size_t)n * out.c * S * sizeof(float);
+      MSB_REQUIRE(workspace_bytes >= need && reinterpret_cast<uintptr_t>(workspace) % 16 == 0,
+                  "%s: split-K workspace too small or misaligned (%zu < %zu)", who, workspace_bytes, need);
+      p.ws = reinterpret_cast<float*>(workspace);
+      return npad_sel == 256 ? launch_fwd_splitk<256, 2>(x, dims, p, ks, bias, st)
+                             : launch_fwd_splitk<128, 4>(x, dims, p, ks, bias, st);
+    }
+  }
   // plane stacking along N (debug flag 3 = 1 disables it): narrow outputs are bound by the A-operand fetch, so one
   // MMA produces J output planes from one activation window (see FwdCfg)
   const bool stack = g_debug_flags[3] == 0;
@@ -935,6 +1104,19 @@ int msb_conv_k5_fwd(msb_tensor x, const void* packed, const float* bias, int cou
                     msb_dim3 dims, int accumulate, const float* ch_scale, int groups, double* sums, void* stream) {
   return conv_k5_fwd_impl("msb_conv_k5_fwd", x, packed, bias, cout, out, n, dims, accumulate, ch_scale, groups, sums, 5,
                           stream);
+}
+
+size_t msb_conv_k5_fwd_workspace_bytes(int n, int cout_view, msb_dim3 dims, int cin_view) {
+  const int npad = msb_conv_k5_out_pad(cout_view);
+  if (splitk_slices(npad, n, dims, cin_view) == 0) return 0;
+  return (size_t)n * cout_view * dims.d * dims.h * dims.w * sizeof(float);
+}
+
+int msb_conv_k5_fwd_ws(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
+                       msb_dim3 dims, int accumulate, const float* ch_scale, int groups, double* sums, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  return conv_k5_fwd_impl("msb_conv_k5_fwd_ws", x, packed, bias, cout, out, n, dims, accumulate, ch_scale, groups, sums,
+                          5, stream, workspace, workspace_bytes);
 }
 
 int msb_conv_k551_fwd(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
@@ -988,12 +1170,11 @@ int msb_conv_k5_wgrad(msb_tensor x, msb_tensor dy, float* dw, float* dbias, int 
   if (rc) return rc;
   const int64_t total = (int64_t)cout * cin * kNumTaps;
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  wgrad_unpack_kernel<<<blocks, 256, 0, st>>>(p.ws, dw, cout, cin);
+  MSB_LAUNCH_PDL(wgrad_unpack_kernel, dim3(blocks), dim3(256), 0, st, p.ws, dw, cout, cin);
   if (dbias != nullptr) {
     const dim3 grid((unsigned)((S + 8191) / 8192), dy.c / 8, n);
-    channel_sum_bf16_kernel<<<grid, 256, 0, st>>>(dy, S, cout, dbias);
+    MSB_LAUNCH_PDL(channel_sum_bf16_kernel, grid, dim3(256), 0, st, dy, S, cout, dbias);
   }
-  MSB_LAUNCH_OK();
   return MSB_OK;
 }
 
@@ -1011,9 +1192,8 @@ int msb_conv_k551_pack(const float* w, void* packed, int cout, int cin, int mode
               "msb_conv_k551_pack: padded channel counts too small for the folded channels");
   const int64_t total = (int64_t)cin_pad * 25 * cout_pad;
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  pack_k551_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, mode,
-                                                          fold_side, cin_pad, cout_pad);
-  MSB_LAUNCH_OK();
+  MSB_LAUNCH_PDL(pack_k551_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), w,
+                 reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, mode, fold_side, cin_pad, cout_pad);
   return MSB_OK;
 }
 
@@ -1042,8 +1222,7 @@ int msb_conv_k551_wgrad(msb_tensor x, msb_tensor dy, float* dw, int cout, int ci
   if (rc) return rc;
   const int64_t total = (int64_t)cout * cin * kNumTaps;
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  wgrad551_unpack_kernel<<<blocks, 256, 0, st>>>(ws, dw, cout, cin, fold_side);
-  MSB_LAUNCH_OK();
+  MSB_LAUNCH_PDL(wgrad551_unpack_kernel, dim3(blocks), dim3(256), 0, st, ws, dw, cout, cin, fold_side);
   return MSB_OK;
 }
 
@@ -1051,8 +1230,7 @@ int msb_channel_sum(msb_tensor x, int c_real, int n, int64_t s, float* out, void
   MSB_REQUIRE(view_ok(x) && x.dtype == MSB_BF16 && out && n > 0 && s > 0 && c_real > 0 && c_real <= x.c,
               "msb_channel_sum: bf16 B8 view required");
   const dim3 grid((unsigned)((s + 8191) / 8192), (unsigned)((c_real + 7) / 8), n);
-  channel_sum_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, s, c_real, out);
-  MSB_LAUNCH_OK();
+  MSB_LAUNCH_PDL(channel_sum_bf16_kernel, grid, dim3(256), 0, as_stream(stream), x, s, c_real, out);
   return MSB_OK;
 }
 
@@ -1083,7 +1261,7 @@ int msb_conv_k2s2_wgrad(msb_tensor big, msb_tensor small, float* dw, float* dbia
   {
     int bx = (int)((Ss + 255) / 256);
     if (bx > 1024) bx = 1024;
-    s2d_k2_kernel<<<dim3(bx, 8 * c8n, n), 256, 0, st>>>(big, xs, c8n, sd.d, sd.h, sd.w);
+    MSB_LAUNCH_PDL(s2d_k2_kernel, dim3(bx, 8 * c8n, n), dim3(256), 0, st, big, xs, c8n, sd.d, sd.h, sd.w);
   }
   MSB_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)small.c * cxs * sizeof(float), st));
   msb_tensor xst;
@@ -1107,15 +1285,14 @@ int msb_conv_k2s2_wgrad(msb_tensor big, msb_tensor small, float* dw, float* dbia
   {
     const int64_t total = (int64_t)small.c * big.c * 8;
     const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-    k2s2_unpack_kernel<<<blocks, 256, 0, st>>>(ws, dw, small.c, big.c);
+    MSB_LAUNCH_PDL(k2s2_unpack_kernel, dim3(blocks), dim3(256), 0, st, ws, dw, small.c, big.c);
   }
   if (dbias != nullptr) {
     const msb_tensor& bt = bias_from_big ? big : small;
     const int64_t sbt = bias_from_big ? Sb : Ss;
     const dim3 grid((unsigned)((sbt + 8191) / 8192), bt.c / 8, n);
-    channel_sum_bf16_kernel<<<grid, 256, 0, st>>>(bt, sbt, bt.c, dbias);
+    MSB_LAUNCH_PDL(channel_sum_bf16_kernel, grid, dim3(256), 0, st, bt, sbt, bt.c, dbias);
   }
-  MSB_LAUNCH_OK();
   return MSB_OK;
 }
 

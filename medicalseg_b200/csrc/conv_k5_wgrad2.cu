@@ -30,6 +30,8 @@ struct Wg2Params {
   int qm, kd_groups, mhalves, cin_m;
   int units_per_pass, passes_per_group, num_passes, chunks, tiles_per_chunk, total_tiles;
   int dy_stage_bytes;
+  unsigned char pass_order[64];          // passes sorted by MMA cost (heavy first): CTA b gets items b, b+grid, ... =
+                                         // one heavy + one light pass instead of two heavy ones
   float* ws;
   int kw_taps, kw_base;                  // 5 / 0 for the 5x5x5 kernel, 1 / 2 (centre tap only) for the 5x5x1 kernel
 };
@@ -59,10 +61,13 @@ __global__ void __launch_bounds__(256, 1)
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();  // after our own TMEM allocation (common.cuh, PDL rules)
+  pdl_wait();
 
   const int num_items = p.num_passes * p.chunks;
   const int tiles_per_n = p.d * p.tiles_h * p.tiles_w;
-  auto decode_pass = [&](int pass, int& mh, int& g, int& jg, int& kw0, int& kw1) {
+  auto decode_pass = [&](int pass_slot, int& mh, int& g, int& jg, int& kw0, int& kw1) {
+    const int pass = p.pass_order[pass_slot];
     const int pg = pass % p.passes_per_group;
     int r = pass / p.passes_per_group;
     jg = r % p.jgroups; r /= p.jgroups;
@@ -221,11 +226,26 @@ int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin
   p.units_per_pass = (kw_taps + p.passes_per_group - 1) / p.passes_per_group;
   p.num_passes = p.mhalves * p.kd_groups * p.jgroups * p.passes_per_group;
   p.total_tiles = n * dims.d * p.tiles_h * p.tiles_w;
-  int chunks = (2 * kNumSMs + p.num_passes - 1) / p.num_passes;
+  if (p.num_passes > 64) return MSB_ERR_UNSUPPORTED;
+  // items = passes x chunks must not exceed 2 items per CTA (a third item on a few CTAs would set the makespan)
+  int chunks = (2 * kNumSMs) / p.num_passes;
   if (chunks > p.total_tiles) chunks = p.total_tiles;
   if (chunks < 1) chunks = 1;
   p.tiles_per_chunk = (p.total_tiles + chunks - 1) / chunks;
   p.chunks = (p.total_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+  {  // heavy passes (more kw taps per tile) first
+    int cost[64], n_order = 0;
+    for (int pass = 0; pass < p.num_passes; ++pass) {
+      const int pg = pass % p.passes_per_group;
+      const int kw0 = pg * p.units_per_pass;
+      int kw1 = kw0 + p.units_per_pass;
+      if (kw1 > kw_taps) kw1 = kw_taps;
+      cost[pass] = kw1 - kw0;
+    }
+    for (int c = kw_taps; c >= 0; --c)
+      for (int pass = 0; pass < p.num_passes; ++pass)
+        if (cost[pass] == c) p.pass_order[n_order++] = (unsigned char)pass;
+  }
   int dy_rows = (kW2TileH + 4) * dyp;
   const int need = (kW2TileH - 1 + (jgroups - 1) * jh) * dyp + npad / 8;  // groups read past the halo rows
   if (need > dy_rows) dy_rows = need;
@@ -244,8 +264,7 @@ int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin
     MSB_CUDA_OK(cudaFuncSetAttribute(conv_k5_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_k5_wgrad2_kernel<<<grid, 256, smem_bytes, st>>>(tmx, tmdy, p);
-  MSB_LAUNCH_OK();
+  MSB_LAUNCH_PDL(conv_k5_wgrad2_kernel, dim3(grid), dim3(256), smem_bytes, st, tmx, tmdy, p);
   return MSB_OK;
 }
 

@@ -7,6 +7,7 @@
 
 namespace msb {
 
+int g_pdl_enabled = 1;
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -105,6 +106,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
                                    const float* __restrict__ beta, float* __restrict__ rmean,
                                    float* __restrict__ rvar, float momentum, float eps, int training, int c,
                                    int groups, float* __restrict__ bnbuf) {
+  pdl_wait();
+  pdl_trigger();
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   const int64_t gc = (int64_t)groups * c;
@@ -157,6 +160,8 @@ __global__ void __launch_bounds__(kThreads)
     bn_act_fwd_kernel(msb_tensor y, msb_tensor out, msb_tensor res, const float* __restrict__ tile_src, int tile_c,
                       const float* __restrict__ bnbuf, const float* __restrict__ alpha1,
                       const float* __restrict__ alpha2, int64_t s, int groups) {
+  pdl_wait();
+  pdl_trigger();
   const int c8 = blockIdx.y, n = blockIdx.z;
   BnActParams p;
   load_params(p, bnbuf, alpha1, alpha2, y.c, groups, groups == 1 ? 0 : n, c8);
@@ -201,6 +206,8 @@ __global__ void __launch_bounds__(kThreads)
     bn_act_bwd_reduce_kernel(msb_tensor y, msb_tensor res, const float* __restrict__ tile_src, int tile_c,
                              msb_tensor gout, const float* __restrict__ bnbuf, const float* __restrict__ alpha1,
                              const float* __restrict__ alpha2, int64_t s, int groups, double* __restrict__ red) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sred[kThreads / 32][32];
   const int c8 = blockIdx.y, n = blockIdx.z;
   const int g = groups == 1 ? 0 : n;
@@ -255,6 +262,8 @@ __global__ void __launch_bounds__(kThreads)
                             msb_tensor gout, const float* __restrict__ bnbuf, const float* __restrict__ alpha1,
                             const float* __restrict__ alpha2, const double* __restrict__ red, double count,
                             int training, msb_tensor dy, msb_tensor dres, int dres_acc, int64_t s, int groups) {
+  pdl_wait();
+  pdl_trigger();
   const int c8 = blockIdx.y, n = blockIdx.z;
   const int g = groups == 1 ? 0 : n;
   BnActParams p;
@@ -296,6 +305,8 @@ __global__ void __launch_bounds__(kThreads)
 
 __global__ void bn_param_grad_kernel(const double* __restrict__ red, int c, int groups, float* dgamma, float* dbeta,
                                      float* dalpha1, float* dalpha2) {
+  pdl_wait();
+  pdl_trigger();
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   const int64_t gc = (int64_t)groups * c;
@@ -317,6 +328,8 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) channel_scale_kernel(msb_tensor src, msb_tensor dst,
                                                                  const float* __restrict__ scale, int64_t s,
                                                                  int accumulate) {
+  pdl_wait();
+  pdl_trigger();
   const int c8 = blockIdx.y, n = blockIdx.z;
   float sc[8];
 #pragma unroll
@@ -341,6 +354,8 @@ template <typename T, int CI8>
 __global__ void __launch_bounds__(kThreads) conv1x1_fwd_kernel(msb_tensor a, const float* __restrict__ w,
                                                                const float* __restrict__ b,
                                                                float* __restrict__ logits, int ci, int co, int64_t s) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float ws[kHeadMaxC * kHeadMaxC + kHeadMaxC];
   for (int i = threadIdx.x; i < co * ci; i += kThreads) ws[i] = w[i];
   for (int i = threadIdx.x; i < co; i += kThreads) ws[kHeadMaxC * kHeadMaxC + i] = b ? b[i] : 0.f;
@@ -373,6 +388,8 @@ template <typename T, int CI8>
 __global__ void __launch_bounds__(kHeadTile)
     conv1x1_bwd_kernel(msb_tensor a, const float* __restrict__ w, const float* __restrict__ dlogits, msb_tensor da,
                        float* __restrict__ dw, float* __restrict__ db, int ci, int co, int64_t s) {
+  pdl_wait();
+  pdl_trigger();
   // smem: W, staged a [ci][tile+1], staged dl [co][tile+1], per-pair accumulators
   __shared__ float ws[kHeadMaxC * kHeadMaxC];
   __shared__ float as[CI8 * 8][kHeadTile + 1];
@@ -453,6 +470,8 @@ __global__ void __launch_bounds__(kHeadTile)
 __global__ void __launch_bounds__(256) momentum_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                        float* __restrict__ v, int64_t count, float lr, float mu,
                                                        float wd, float gs) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t n4 = count >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -514,10 +533,8 @@ int msb_bn_finalize(const double* sums, double count, const float* gamma, const 
   MSB_REQUIRE(gamma && beta && bnbuf && c > 0 && groups > 0, "msb_bn_finalize: bad arguments");
   MSB_REQUIRE(training ? (sums != nullptr && count > 0) : (running_mean && running_var),
               "msb_bn_finalize: training needs sums, eval needs running stats");
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(sums, count, gamma, beta, running_mean,
-                                                                      running_var, momentum, eps, training, c, groups,
-                                                                      bnbuf);
-  MSB_LAUNCH_OK();
+  MSB_LAUNCH_PDL(bn_finalize_kernel, dim3((c + 127) / 128), dim3(128), 0, as_stream(stream), sums, count, gamma, beta,
+                 running_mean, running_var, momentum, eps, training, c, groups, bnbuf);
   return MSB_OK;
 }
 
@@ -545,11 +562,9 @@ int msb_bn_act_fwd(msb_tensor y, msb_tensor out, msb_tensor residual, const floa
   MSB_REQUIRE(!tile_src || tile_c > 0, "msb_bn_act_fwd: tile_c must be > 0");
   MSB_REQUIRE(groups == 1 || groups == n, "msb_bn_act_fwd: groups must be 1 or n");
   MSB_DISPATCH_DTYPE(y.dtype, MSB_BOOL_DISPATCH2(has_res, tile_src != nullptr,
-                                                 bn_act_fwd_kernel<T, B0, B1>
-                                                 <<<plane_grid(n, y.c, s), kThreads, 0, as_stream(stream)>>>(
-                                                     y, out, residual, tile_src, tile_c, bnbuf, alpha1, alpha2, s,
-                                                     groups);););
-  MSB_LAUNCH_OK();
+                                                 MSB_LAUNCH_PDL((bn_act_fwd_kernel<T, B0, B1>), plane_grid(n, y.c, s),
+                                                                dim3(kThreads), 0, as_stream(stream), y, out, residual,
+                                                                tile_src, tile_c, bnbuf, alpha1, alpha2, s, groups);););
   return MSB_OK;
 }
 
@@ -563,11 +578,10 @@ int msb_bn_act_bwd_reduce(msb_tensor y, msb_tensor residual, const float* tile_s
               "msb_bn_act_bwd_reduce: residual needs matching view and alpha2");
   MSB_REQUIRE(groups == 1 || groups == n, "msb_bn_act_bwd_reduce: groups must be 1 or n");
   MSB_DISPATCH_DTYPE(y.dtype, MSB_BOOL_DISPATCH2(has_res, tile_src != nullptr,
-                                                 bn_act_bwd_reduce_kernel<T, B0, B1>
-                                                 <<<plane_grid(n, y.c, s), kThreads, 0, as_stream(stream)>>>(
-                                                     y, residual, tile_src, tile_c, gout, bnbuf, alpha1, alpha2, s,
-                                                     groups, red);););
-  MSB_LAUNCH_OK();
+                                                 MSB_LAUNCH_PDL((bn_act_bwd_reduce_kernel<T, B0, B1>),
+                                                                plane_grid(n, y.c, s), dim3(kThreads), 0,
+                                                                as_stream(stream), y, residual, tile_src, tile_c, gout,
+                                                                bnbuf, alpha1, alpha2, s, groups, red);););
   return MSB_OK;
 }
 
@@ -590,20 +604,16 @@ int msb_bn_act_bwd_apply(msb_tensor y, msb_tensor residual, const float* tile_sr
   MSB_DISPATCH_DTYPE(
       y.dtype, MSB_BOOL_DISPATCH2(has_res, tile_src != nullptr, {
         if (has_dres)
-          bn_act_bwd_apply_kernel<T, B0, B1, true><<<grid, kThreads, 0, st>>>(
-              y, residual, tile_src, tile_c, gout, bnbuf, alpha1, alpha2, red, count, training, dy, dres,
-              dres_accumulate, s, groups);
+          MSB_LAUNCH_PDL((bn_act_bwd_apply_kernel<T, B0, B1, true>), grid, dim3(kThreads), 0, st, y, residual, tile_src,
+                         tile_c, gout, bnbuf, alpha1, alpha2, red, count, training, dy, dres, dres_accumulate, s, groups);
         else
-          bn_act_bwd_apply_kernel<T, B0, B1, false><<<grid, kThreads, 0, st>>>(
-              y, residual, tile_src, tile_c, gout, bnbuf, alpha1, alpha2, red, count, training, dy, dres,
-              dres_accumulate, s, groups);
+          MSB_LAUNCH_PDL((bn_act_bwd_apply_kernel<T, B0, B1, false>), grid, dim3(kThreads), 0, st, y, residual,
+                         tile_src, tile_c, gout, bnbuf, alpha1, alpha2, red, count, training, dy, dres, dres_accumulate,
+                         s, groups);
       }););
-  MSB_LAUNCH_OK();
-  if (dgamma || dbeta || dalpha1 || dalpha2) {
-    bn_param_grad_kernel<<<(y.c + 127) / 128, 128, 0, st>>>(red, y.c, groups, dgamma, dbeta, dalpha1,
-                                                            has_res ? dalpha2 : nullptr);
-    MSB_LAUNCH_OK();
-  }
+  if (dgamma || dbeta || dalpha1 || dalpha2)
+    MSB_LAUNCH_PDL(bn_param_grad_kernel, dim3((y.c + 127) / 128), dim3(128), 0, st, red, y.c, groups, dgamma, dbeta,
+                   dalpha1, has_res ? dalpha2 : nullptr);
   return MSB_OK;
 }
 
@@ -611,9 +621,8 @@ int msb_channel_scale(msb_tensor src, msb_tensor dst, const float* scale, int n,
                       void* stream) {
   MSB_REQUIRE(view_ok(src) && view_ok(dst) && src.c == dst.c && src.dtype == dst.dtype && n > 0 && s > 0,
               "msb_channel_scale: bad arguments");
-  MSB_DISPATCH_DTYPE(src.dtype, channel_scale_kernel<T><<<plane_grid(n, src.c, s), kThreads, 0, as_stream(stream)>>>(
-                                    src, dst, scale, s, accumulate););
-  MSB_LAUNCH_OK();
+  MSB_DISPATCH_DTYPE(src.dtype, MSB_LAUNCH_PDL(channel_scale_kernel<T>, plane_grid(n, src.c, s), dim3(kThreads), 0,
+                                               as_stream(stream), src, dst, scale, s, accumulate););
   return MSB_OK;
 }
 
@@ -624,10 +633,10 @@ int msb_conv1x1_fwd(msb_tensor a, const float* w, const float* b, float* logits,
   const dim3 grid((unsigned)((s + kVoxPerBlock - 1) / kVoxPerBlock), 1, (unsigned)n);
   cudaStream_t st = as_stream(stream);
   MSB_DISPATCH_DTYPE(a.dtype, {
-    if (a.c == 8) conv1x1_fwd_kernel<T, 1><<<grid, kThreads, 0, st>>>(a, w, b, logits, ci, co, s);
-    else if (a.c == 16) conv1x1_fwd_kernel<T, 2><<<grid, kThreads, 0, st>>>(a, w, b, logits, ci, co, s);
-    else if (a.c == 24) conv1x1_fwd_kernel<T, 3><<<grid, kThreads, 0, st>>>(a, w, b, logits, ci, co, s);
-    else conv1x1_fwd_kernel<T, 4><<<grid, kThreads, 0, st>>>(a, w, b, logits, ci, co, s);
+    if (a.c == 8) MSB_LAUNCH_PDL((conv1x1_fwd_kernel<T, 1>), grid, dim3(kThreads), 0, st, a, w, b, logits, ci, co, s);
+    else if (a.c == 16) MSB_LAUNCH_PDL((conv1x1_fwd_kernel<T, 2>), grid, dim3(kThreads), 0, st, a, w, b, logits, ci, co, s);
+    else if (a.c == 24) MSB_LAUNCH_PDL((conv1x1_fwd_kernel<T, 3>), grid, dim3(kThreads), 0, st, a, w, b, logits, ci, co, s);
+    else MSB_LAUNCH_PDL((conv1x1_fwd_kernel<T, 4>), grid, dim3(kThreads), 0, st, a, w, b, logits, ci, co, s);
   });
   MSB_LAUNCH_OK();
   return MSB_OK;
@@ -641,10 +650,10 @@ int msb_conv1x1_bwd(msb_tensor a, const float* w, const float* dlogits, msb_tens
   const dim3 grid((unsigned)((s + kVoxPerBlock - 1) / kVoxPerBlock), 1, (unsigned)n);
   cudaStream_t st = as_stream(stream);
   MSB_DISPATCH_DTYPE(a.dtype, {
-    if (a.c == 8) conv1x1_bwd_kernel<T, 1><<<grid, kHeadTile, 0, st>>>(a, w, dlogits, da, dw, db, ci, co, s);
-    else if (a.c == 16) conv1x1_bwd_kernel<T, 2><<<grid, kHeadTile, 0, st>>>(a, w, dlogits, da, dw, db, ci, co, s);
-    else if (a.c == 24) conv1x1_bwd_kernel<T, 3><<<grid, kHeadTile, 0, st>>>(a, w, dlogits, da, dw, db, ci, co, s);
-    else conv1x1_bwd_kernel<T, 4><<<grid, kHeadTile, 0, st>>>(a, w, dlogits, da, dw, db, ci, co, s);
+    if (a.c == 8) MSB_LAUNCH_PDL((conv1x1_bwd_kernel<T, 1>), grid, dim3(kHeadTile), 0, st, a, w, dlogits, da, dw, db, ci, co, s);
+    else if (a.c == 16) MSB_LAUNCH_PDL((conv1x1_bwd_kernel<T, 2>), grid, dim3(kHeadTile), 0, st, a, w, dlogits, da, dw, db, ci, co, s);
+    else if (a.c == 24) MSB_LAUNCH_PDL((conv1x1_bwd_kernel<T, 3>), grid, dim3(kHeadTile), 0, st, a, w, dlogits, da, dw, db, ci, co, s);
+    else MSB_LAUNCH_PDL((conv1x1_bwd_kernel<T, 4>), grid, dim3(kHeadTile), 0, st, a, w, dlogits, da, dw, db, ci, co, s);
   });
   MSB_LAUNCH_OK();
   return MSB_OK;
@@ -657,8 +666,8 @@ int msb_momentum_step(float* p, const float* g, float* v, int64_t count, float l
               "msb_momentum_step: buffers must be 16-byte aligned");
   int64_t want = (count / 4 + 255) / 256 + 1;
   const int blocks = (int)(want < (int64_t)kNumSMs * 8 ? want : (int64_t)kNumSMs * 8);
-  momentum_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, v, count, lr, mu, wd, grad_scale);
-  MSB_LAUNCH_OK();
+  MSB_LAUNCH_PDL(momentum_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), p, g, v, count, lr, mu, wd,
+                 grad_scale);
   return MSB_OK;
 }
 

@@ -3,7 +3,10 @@
 Reference: medicalseg/models/losses/dice_loss.py:23-102, cross_entropy_loss.py:23-87, loss_utils.py:18-40,
 mixes_losses.py:22-60.  Behaviours kept on purpose:
   * Dice uses sigmoid(logits), the V-Net squared denominator, eps clip 1e-6, includes background, mean over classes;
-    returns (loss, per_channel_dice ndarray) — the ndarray costs a device->host sync exactly as in the reference.
+    returns (loss, per_channel_dice) where per_channel_dice is a LazyHostArray: the D2H copy into pinned memory is
+    queued on the stream at once, the host only waits for it when the values are first LOOKED AT (np.mean(dice),
+    dice[0], arithmetic ...), so a training loop that logs every N iterations does not drain the GPU every step
+    (the reference syncs in dice_loss.py:99 on every call).
   * CrossEntropyLoss(weight=None) computes class weights sum(1-p)/sum(p) from the FIRST logits it ever sees and
     caches them on the module (cross_entropy_loss.py:68-69).
   * MixedLoss returns ([coef_i * loss_i], per_channel_dice).
@@ -16,6 +19,58 @@ import numpy as np
 import torch
 
 from .. import ops
+
+
+class LazyHostArray:
+    """ndarray stand-in for a small device result: async D2H into pinned memory + event; materialises on first use.
+    Implements the numpy array protocol, so np.mean(x), acc += x, x[i], len(x), float(x[i]) behave like the ndarray
+    the reference returns (dice_loss.py:99-102)."""
+
+    __array_priority__ = 100
+
+    def __init__(self, dev: torch.Tensor):
+        self._pinned = torch.empty(dev.shape, dtype=dev.dtype, pin_memory=True)
+        self._pinned.copy_(dev, non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record()
+        self._np = None
+
+    def numpy(self) -> np.ndarray:
+        if self._np is None:
+            self._event.synchronize()
+            self._np = self._pinned.numpy().copy()
+            self._pinned = None
+        return self._np
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype)
+
+    def __getattr__(self, name):  # shape, dtype, mean, tolist, ...
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.numpy(), name)
+
+    def __getitem__(self, i):
+        return self.numpy()[i]
+
+    def __len__(self):
+        return len(self.numpy())
+
+    def __iter__(self):
+        return iter(self.numpy())
+
+    def __repr__(self):
+        return repr(self.numpy())
+
+    def __add__(self, o): return self.numpy() + o
+    def __radd__(self, o): return o + self.numpy()
+    def __sub__(self, o): return self.numpy() - o
+    def __rsub__(self, o): return o - self.numpy()
+    def __mul__(self, o): return self.numpy() * o
+    def __rmul__(self, o): return o * self.numpy()
+    def __truediv__(self, o): return self.numpy() / o
+    def __rtruediv__(self, o): return o / self.numpy()
 
 
 class _DiceCEFunction(torch.autograd.Function):
@@ -97,7 +152,7 @@ class DiceLoss:
                 self._ones = torch.ones(c, dtype=torch.float32, device=logits.device)
             _class_w = self._ones
         res = _fused(logits, labels, _class_w, _ignore_index)
-        per_channel_dice = res[2:].detach().cpu().numpy()  # D2H sync, as dice_loss.py:99
+        per_channel_dice = LazyHostArray(res[2:].detach())  # dice_loss.py:99 without draining the GPU here
         return res[1], per_channel_dice
 
 

@@ -211,7 +211,8 @@ class _K5:
         g = eng.groups(x.n)
         if eng.dtype == torch.bfloat16:
             self._pack(x.c, out.c)
-            ops.k5_fwd(x, self.packed_f, st.view(self.conv.bias), self.cout, out, False, None, g, sums)
+            ops.k5_fwd(x, self.packed_f, st.view(self.conv.bias), self.cout, out, False, None, g, sums,
+                       eng.splitk_workspace(x.n, out.c, x.dims, x.c))
         else:
             ops.conv_strided_fwd(x, st.view(self.conv.weight), st.view(self.conv.bias), out, (5, 5, 5), (1, 1, 1),
                                  (2, 2, 2), g, sums, self.cin, self.cout)
@@ -219,9 +220,12 @@ class _K5:
     def bwd(self, x: B8, dy: B8, dx: Optional[B8], accumulate=False, ch_scale=None):
         eng, st = self.eng, self.eng.store
         w, dw, db = st.view(self.conv.weight), st.grad_view(self.conv.weight), st.grad_view(self.conv.bias)
+        if eng.bias_grad_is_zero():
+            db = None
         if eng.dtype == torch.bfloat16:
             if dx is not None:
-                ops.k5_fwd(dy, self.packed_b, None, self.cin, dx, accumulate, ch_scale, 1, None)
+                ops.k5_fwd(dy, self.packed_b, None, self.cin, dx, accumulate, ch_scale, 1, None,
+                           eng.splitk_workspace(dy.n, dx.c, dy.dims, dy.c))
             ops.k5_wgrad(x, dy, dw, db, self.cout, self.cin, eng.wgrad_workspace(self.cin, self.cout))
         else:
             if dx is not None:
@@ -462,6 +466,7 @@ class VNet(_Module):
         self._scratch_off = 0
         self._wg_ws = None
         self._k2_ws = None
+        self._sk_ws = None
         self._masks: Optional[Dict[str, torch.Tensor]] = None
         self._tape = None
         self.grad_ready_hook = None  # callable(lo, hi) on flat-grad ranges, fired in backward order (DDP buckets)
@@ -556,8 +561,17 @@ class VNet(_Module):
         self._scratch_off += count
         return v
 
+    def bias_grad_is_zero(self):
+        """A conv bias that feeds a BatchNorm using batch (or instance) statistics has an identically zero gradient:
+        the normalisation subtracts the per-channel mean, so sum_v dL/dy[v, c] = 0 exactly.  The bf16 path leaves the
+        (pre-zeroed) gradient slot untouched instead of summing bf16 rounding noise over millions of voxels; the f32
+        parity path still computes the sum like the reference's autograd does."""
+        return self.dtype == torch.bfloat16 and self.bn_training_bwd
+
     def strided_wgrad(self, big: B8, small: B8, dw, dbias, kernel, stride, bias_from_big):
         """weight gradient of a down / up conv: tensor-core path for the 2x2x2 stride-2 bf16 case"""
+        if self.bias_grad_is_zero():
+            dbias = None
         if (self.dtype == torch.bfloat16 and tuple(kernel) == (2, 2, 2) and tuple(stride) == (2, 2, 2)
                 and all(d % 2 == 0 for d in big.dims) and big.c in (16, 32, 64, 128) and small.c % 16 == 0):
             need = ops.k2s2_wgrad_workspace_bytes(big.n, big.c, small.c, big.dims)
@@ -566,6 +580,16 @@ class VNet(_Module):
             ops.k2s2_wgrad(big, small, dw, dbias, bias_from_big, self._k2_ws)
         else:
             ops.conv_strided_wgrad(big, small, dw, dbias, kernel, stride, (0, 0, 0), bias_from_big)
+
+    def splitk_workspace(self, n, cout_view, dims, cin_view):
+        """zero-initialised scratch for the split-K 5x5x5 conv on small volumes (None when the shape does not use it);
+        every call leaves it all-zero again, so it is allocated and cleared once"""
+        need = ops.k5_fwd_workspace_bytes(n, cout_view, dims, cin_view)
+        if need == 0:
+            return None
+        if self._sk_ws is None or self._sk_ws.numel() < need:
+            self._sk_ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
+        return self._sk_ws
 
     def workspace(self, nbytes):
         if self._wg_ws is None or self._wg_ws.numel() < nbytes:
@@ -769,7 +793,8 @@ class VNet(_Module):
             ops.fold_w(dyo, ot.c, dpf, -1)
             ot.k551.bwd_data(dpf, g_u32)
             ot.k551.wgrad(tape["u32"]["out"], dpf)
-            ops.channel_sum(dyo, ot.c, st.grad_view(ot.conv1.bias))
+            if not self.bias_grad_is_zero():
+                ops.channel_sum(dyo, ot.c, st.grad_view(ot.conv1.bias))
         else:
             ot.k5.bwd(tape["u32"]["out"], dyo, g_u32)
         self._fire(ot)
@@ -851,7 +876,8 @@ class VNet(_Module):
         it.act.bwd(g_out16, dy0)
         if it.k551 is not None:
             it.k551.wgrad(tape["xf"], dy0)
-            ops.channel_sum(dy0, 16, st.grad_view(it.conv1.bias))
+            if not self.bias_grad_is_zero():
+                ops.channel_sum(dy0, 16, st.grad_view(it.conv1.bias))
         else:
             ops.conv_in_wgrad(x, dy0, st.grad_view(it.conv1.weight), st.grad_view(it.conv1.bias))
         self._fire(it)

@@ -191,9 +191,21 @@ def k5_pack(w, packed, cout, cin, mode, cin_pad, cout_pad):
     call("msb_conv_k5_pack", _ptr(w), _ptr(packed), cout, cin, mode, cin_pad, cout_pad, _stream())
 
 
-def k5_fwd(x: B8, packed, bias, cout, out: B8, accumulate=False, ch_scale=None, groups=1, sums=None):
-    call("msb_conv_k5_fwd", x.mt, _ptr(packed), _ptr(bias), cout, out.mt, x.n, dim3(x.dims), int(accumulate),
-         _ptr(ch_scale), groups, _ptr(sums), _stream())
+def k5_fwd(x: B8, packed, bias, cout, out: B8, accumulate=False, ch_scale=None, groups=1, sums=None,
+           workspace: Optional[torch.Tensor] = None):
+    """workspace: zero-initialised scratch of >= k5_fwd_workspace_bytes(...) bytes enables the split-K path on small
+    volumes (left all-zero again by the call); None = regular path only"""
+    if workspace is None:
+        call("msb_conv_k5_fwd", x.mt, _ptr(packed), _ptr(bias), cout, out.mt, x.n, dim3(x.dims), int(accumulate),
+             _ptr(ch_scale), groups, _ptr(sums), _stream())
+    else:
+        call("msb_conv_k5_fwd_ws", x.mt, _ptr(packed), _ptr(bias), cout, out.mt, x.n, dim3(x.dims), int(accumulate),
+             _ptr(ch_scale), groups, _ptr(sums), _ptr(workspace), workspace.numel() * workspace.element_size(),
+             _stream())
+
+
+def k5_fwd_workspace_bytes(n: int, cout_view: int, dims, cin_view: int) -> int:
+    return call("msb_conv_k5_fwd_workspace_bytes", n, cout_view, dim3(dims), cin_view)
 
 
 def k5_wgrad_workspace_bytes(cin: int, cout: int) -> int:

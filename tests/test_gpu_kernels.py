@@ -225,6 +225,58 @@ def test_conv_k5_tcgen05_dgrad_accumulate_scale():
     assert rel(dx.to_ncdhw(), base + ref * scale.view(n, cin, 1, 1, 1)) <= BF16_TOL
 
 
+SPLITK_CASES = [(256, 256, (8, 8, 8)), (256, 256, (16, 16, 16)), (128, 128, (16, 16, 16)), (128, 128, (5, 9, 7)),
+                (256, 128, (3, 8, 8)), (128, 256, (6, 16, 8))]
+
+
+@pytest.mark.parametrize("cin,cout,dims", SPLITK_CASES)
+def test_conv_k5_split_k_small_volumes(cin, cout, dims):
+    """split-K path (msb_conv_k5_fwd_ws) on the small deep-level volumes: forward + BN sums, then the input-gradient
+    form with accumulate + channel scale; the workspace must come back all-zero (header contract)."""
+    ops, B8 = _imp()
+    torch.manual_seed(11)
+    n = 2
+    need = ops.k5_fwd_workspace_bytes(n, cout, dims, cin)
+    assert need > 0, "shape is expected to take the split-K path"
+    ws = torch.zeros(need, dtype=torch.uint8, device="cuda")
+    x = torch.randn(n, cin, *dims, device="cuda")
+    w = torch.randn(cout, cin, 5, 5, 5, device="cuda") * (2.0 / (cin * 125)) ** 0.5
+    b = torch.randn(cout, device="cuda")
+    xb = B8.from_ncdhw(x, torch.bfloat16)
+    ref = F.conv3d(xb.to_ncdhw(), w.bfloat16().float(), b, padding=2)
+    cout_pad = ops.k5_out_pad(cout)
+    packed = torch.empty(ops.k5_packed_bytes(cin, cout_pad), dtype=torch.uint8, device="cuda")
+    ops.k5_pack(w, packed, cout, cin, 0, cin, cout_pad)
+    out = B8(n, cout, dims, torch.bfloat16, device="cuda", zero=True)
+    sums = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
+    ops.k5_fwd(xb, packed, b, cout, out, False, None, 1, sums, ws)
+    o = out.to_ncdhw(cout)
+    assert rel(o, ref) <= BF16_TOL
+    assert int(ws.count_nonzero()) == 0
+    s_ref = o.double().sum((0, 2, 3, 4))
+    assert float((sums[:cout] - s_ref).abs().max()) <= 1e-3 * float(s_ref.abs().max() + 1)
+    q_ref = (o.double() ** 2).sum((0, 2, 3, 4))
+    assert float((sums[cout:] - q_ref).abs().max()) <= 1e-4 * float(q_ref.abs().max() + 1)
+    # regular path gives the same result up to summation order
+    out2 = B8(n, cout, dims, torch.bfloat16, device="cuda", zero=True)
+    ops.k5_fwd(xb, packed, b, cout, out2, False, None, 1, None)
+    assert rel(out2.to_ncdhw(cout), o) <= BF16_TOL
+    # input gradient: dx += scale * conv_T(dy)
+    dyb = B8.from_ncdhw(torch.randn(n, cout, *dims, device="cuda"), torch.bfloat16)
+    refd = torch.nn.grad.conv3d_input((n, cin, *dims), w.bfloat16().float(), dyb.to_ncdhw(), padding=2)
+    cp = ops.k5_out_pad(cin)
+    packed_b = torch.empty(ops.k5_packed_bytes(cout, cp), dtype=torch.uint8, device="cuda")
+    ops.k5_pack(w, packed_b, cout, cin, 1, cout, cp)
+    dx = B8.from_ncdhw(torch.randn(n, cin, *dims, device="cuda"), torch.bfloat16)
+    base = dx.to_ncdhw()
+    scale = (torch.rand(n, cin, device="cuda") > 0.5).float() * 2
+    need_b = ops.k5_fwd_workspace_bytes(n, cin, dims, cout)
+    wsb = torch.zeros(max(need_b, 16), dtype=torch.uint8, device="cuda")
+    ops.k5_fwd(dyb, packed_b, None, cin, dx, True, scale, 1, None, wsb if need_b else None)
+    assert rel(dx.to_ncdhw(), base + refd * scale.view(n, cin, 1, 1, 1)) <= BF16_TOL
+    assert int(wsb.count_nonzero()) == 0
+
+
 WG_CASES = [(32, 32, (6, 16, 16)), (64, 64, (4, 9, 20)), (128, 128, (3, 8, 16)), (256, 256, (2, 8, 8)),
             (32, 2, (5, 10, 18)), (16, 16, (5, 8, 16)), (32, 32, (3, 13, 9))]
 

@@ -1,0 +1,62 @@
+"""Runs ONE kernel family alone a few times (so that `ncu --set full -k regex:<name>` captures exactly it) and prints
+its CUDA-event time.  Shapes are the BASELINE configs[1] ones (batch 2).
+
+    python tools/run_kernel.py fwd32      # conv_k5_fwd   32->32 @128^3  (dominant layer, up_tr32.ops[0].conv1)
+    python tools/run_kernel.py wgrad32    # conv_k5_wgrad 32->32 @128^3
+    python tools/run_kernel.py fwd64 | wgrad64 | fwd128 | wgrad128 | fwd256 | wgrad256 | fwd256s | wgrad256s
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+CASES = {  # name -> (channels, cube edge)
+    "32": (32, 128), "64": (64, 64), "128": (128, 32), "256": (256, 16), "256s": (256, 8), "128s": (128, 16),
+    "64s": (64, 32), "32s": (32, 64),
+}
+GFLOP = lambda c, e: 2 * 125 * c * c * e ** 3 / 1e9  # noqa: E731  (per volume, one pass)
+
+
+def main():
+    from medicalseg_b200 import ops
+    from medicalseg_b200.ops import B8
+    what = sys.argv[1] if len(sys.argv) > 1 else "fwd32"
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    kind = "wgrad" if what.startswith("wgrad") else "fwd"
+    c, e = CASES[what[len(kind):]]
+    n, dims = 2, (e, e, e)
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    x = B8(n, c, dims, torch.bfloat16, device=dev)
+    x.buf.normal_()
+    y = B8(n, c, dims, torch.bfloat16, device=dev)
+    y.buf.normal_()
+    w = torch.randn(c, c, 5, 5, 5, device=dev) * 0.02
+    bias = torch.zeros(c, device=dev)
+    if kind == "fwd":
+        packed = torch.empty(ops.k5_packed_bytes(c, ops.k5_out_pad(c)), dtype=torch.uint8, device=dev)
+        ops.k5_pack(w, packed, c, c, 0, c, ops.k5_out_pad(c))
+        sums = torch.zeros(2 * c, dtype=torch.float64, device=dev)
+        fn = lambda: ops.k5_fwd(x, packed, bias, c, y, False, None, 1, sums)  # noqa: E731
+    else:
+        dw, db = torch.zeros_like(w), torch.zeros(c, device=dev)
+        ws = torch.empty(ops.k5_wgrad_workspace_bytes(c, c), dtype=torch.uint8, device=dev)
+        fn = lambda: ops.k5_wgrad(x, y, dw, db, c, c, ws)  # noqa: E731
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print("%s: %d->%d 5x5x5 @%d^3 batch %d: %.4f ms/call (all kernels of the op), %.1f TFLOP/s" %
+          (what, c, c, e, n, ms, n * GFLOP(c, e) / ms))
+
+
+if __name__ == "__main__":
+    main()
