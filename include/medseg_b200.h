@@ -72,6 +72,12 @@ int msb_bn_finalize(const double* sums, double count, const float* gamma, const 
 int msb_bn_act_fwd(msb_tensor y, msb_tensor out, msb_tensor residual, const float* tile_src, int tile_c,
                    const float* bnbuf, const float* alpha1, const float* alpha2,
                    int n, int64_t s, int groups, void* stream);
+/* msb_bn_finalize + msb_bn_act_fwd in one launch (same arguments; bnbuf is written for the backward kernels and the
+ * running statistics are updated by one designated block). */
+int msb_bn_fwd_fused(msb_tensor y, msb_tensor out, msb_tensor residual, const float* tile_src, int tile_c,
+                     const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float momentum, float eps, int training, float* bnbuf, const float* alpha1,
+                     const float* alpha2, int n, int64_t s, int groups, void* stream);
 /* red[4][groups][C] (double) += sum g1, sum g1*xhat, dalpha1, dalpha2 (g1 = grad at the BN output). */
 int msb_bn_act_bwd_reduce(msb_tensor y, msb_tensor residual, const float* tile_src, int tile_c, msb_tensor gout,
                           const float* bnbuf, const float* alpha1, const float* alpha2,

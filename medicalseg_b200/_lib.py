@@ -32,6 +32,7 @@ SIGNATURES = {
     "msb_bn_stats": (I, [T, I, L, I, P, P]),
     "msb_bn_finalize": (I, [P, D, P, P, P, P, F, F, I, I, I, P, P]),
     "msb_bn_act_fwd": (I, [T, T, T, P, I, P, P, P, I, L, I, P]),
+    "msb_bn_fwd_fused": (I, [T, T, T, P, I, P, D, P, P, P, P, F, F, I, P, P, P, I, L, I, P]),
     "msb_bn_act_bwd_reduce": (I, [T, T, P, I, T, P, P, P, I, L, I, P, P]),
     "msb_bn_act_bwd_apply": (I, [T, T, P, I, T, P, P, P, P, D, I, T, T, I, P, P, P, P, I, L, I, P]),
     "msb_channel_scale": (I, [T, T, P, I, L, I, P]),

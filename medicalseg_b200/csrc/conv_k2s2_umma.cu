@@ -25,7 +25,8 @@ constexpr int kK2ABytes = 2 * kK2TileH * kK2TileW * 16;  // [2 c8][16 h][8 w][8 
 constexpr int kK2BBytesMax = 256 * 32;                   // [2 k8][N <= 256][8 ch] bf16
 constexpr int kK2StageBytes = kK2ABytes + kK2BBytesMax;
 constexpr int kK2Stages = 8;
-constexpr int kK2SmemBytes = kK2Stages * kK2StageBytes + 1024 + 4 * 2 * 256 * 4 + 128;
+constexpr int kK2Threads = 384;  // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4-11 epilogue
+constexpr int kK2SmemBytes = kK2Stages * kK2StageBytes + 1024 + 8 * 2 * 256 * 4 + 128;
 
 struct K2Params {
   int mode;              // 0 gather, 1 scatter
@@ -46,7 +47,7 @@ struct K2Params {
   int sums_c;
 };
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kK2Threads, 1)
     conv_k2s2_kernel(const __grid_constant__ CUtensorMap tmap_x, const K2Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -55,17 +56,17 @@ __global__ void __launch_bounds__(256, 1)
   // barrier map: [0,S) full  [S,2S) empty  [2S,2S+2) acc_full  [2S+2,2S+4) acc_empty
   constexpr int kFull = 0, kEmpty = kK2Stages, kAccFull = 2 * kK2Stages, kAccEmpty = 2 * kK2Stages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kK2Stages + 4);
-  float* stat_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);  // [4 warps][2][256]
+  float* stat_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);  // [8 warps][2][256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = ptx::smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   if (threadIdx.x == 0) {
     for (int i = 0; i < kK2Stages; ++i) { ptx::mbar_init(BAR(kFull + i), 1); ptx::mbar_init(BAR(kEmpty + i), 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(kAccFull + i), 1); ptx::mbar_init(BAR(kAccEmpty + i), 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(kAccFull + i), 1); ptx::mbar_init(BAR(kAccEmpty + i), 8); }
     ptx::fence_mbar_init();
   }
-  for (int i = threadIdx.x; i < 4 * 2 * 256; i += 256) stat_smem[i] = 0.f;
+  for (int i = threadIdx.x; i < 8 * 2 * 256; i += kK2Threads) stat_smem[i] = 0.f;
   if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tmap_x);
   if (warp == 2) ptx::tmem_alloc<512>(ptx::smem_u32(tmem_slot));
   ptx::tc_fence_before();
@@ -140,13 +141,21 @@ __global__ void __launch_bounds__(256, 1)
       __syncwarp();
     }
   } else if (warp >= 4) {
-    // ================= epilogue =================
-    const int q = warp - 4;
+    // ================= epilogue: two warpgroups (warps 4-7, 8-11) take alternate 16-column blocks ==============
+    // (a warp reads the TMEM lane quadrant warp % 4).  The loop is instruction-latency bound (one warp per scheduler),
+    // so everything that does not depend on the item is hoisted and the bf16 conversion is done once.
+    const int wg = (warp - 4) >> 2;
+    const int q = warp & 3;
     const int row = q * 32 + lane;
     const int hh = row >> 3, ww = row & 7;
     const int64_t Ss = (int64_t)p.sd * p.sh * p.sw;
     const int64_t So = p.mode == 0 ? Ss : Ss * 8;  // voxels of the output grid
-    float* my_stats = stat_smem + q * 2 * 256;
+    float* my_stats = stat_smem + (warp - 4) * 2 * 256;
+    const int nblk16 = p.nmma / 16;
+    const int t_start = (wg * 16) / p.cpad, co_start = (wg * 16) % p.cpad;
+    const bool has_bias = p.bias != nullptr;
+    const bool bias_vec = has_bias && (reinterpret_cast<uintptr_t>(p.bias) % 16 == 0);
+    const bool want_stats = p.sums != nullptr;
     uint32_t iuse = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
       const int tile = item / p.tap_groups, tgp = item % p.tap_groups;
@@ -157,51 +166,67 @@ __global__ void __launch_bounds__(256, 1)
       const int h = th * kK2TileH + hh, w = tw * kK2TileW + ww;
       const bool ok = h < p.sh && w < p.sw;
       const uint32_t as = iuse & 1, aph = (iuse >> 1) & 1;
+      const int64_t v_small = ((int64_t)d * p.sh + h) * p.sw + w;
+      const int64_t v_big0 = ((int64_t)(2 * d) * (2 * p.sh) + 2 * h) * (2 * p.sw) + 2 * w;  // tap (0,0,0) voxel
+      __nv_bfloat16* out_n = reinterpret_cast<__nv_bfloat16*>(p.out.ptr) + (int64_t)n * p.out.n_stride;
       ptx::mbar_wait(BAR(kAccFull + as), aph);
       ptx::tc_fence_after();
       const uint32_t t_base = tmem_base + as * 256u + ((uint32_t)(q * 32) << 16);
+      int t = t_start, co0 = co_start;
 #pragma unroll 1
-      for (int cb = 0; cb < p.nmma / 16; ++cb) {
+      for (int cb = wg; cb < nblk16; cb += 2) {
         float acc[16];
         ptx::tmem_ld16(t_base + cb * 16, acc);
-        const int col0 = cb * 16;
-        const int t = col0 / p.cpad, co0 = col0 % p.cpad;  // scatter: tap within the group; gather: t = 0
-        int64_t v;
-        if (p.mode == 0) {
-          v = ((int64_t)d * p.sh + h) * p.sw + w;
-        } else {
+        int64_t v = v_small;
+        if (p.mode != 0) {
           const int tap = tgp * p.tg + t;
-          v = ((int64_t)(2 * d + (tap >> 2)) * (2 * p.sh) + (2 * h + ((tap >> 1) & 1))) * (2 * p.sw) + (2 * w + (tap & 1));
+          v = v_big0 + ((int64_t)(tap >> 2) * (2 * p.sh) + ((tap >> 1) & 1)) * (2 * p.sw) + (tap & 1);
         }
-        float sq[16];
+        if (has_bias) {
+          if (bias_vec && co0 + 16 <= p.cout_real) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co0) + i);
+              acc[4 * i] += b4.x; acc[4 * i + 1] += b4.y; acc[4 * i + 2] += b4.z; acc[4 * i + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (co0 + i < p.cout_real) acc[i] += __ldg(p.bias + co0 + i);
+          }
+        }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const int c8 = (co0 >> 3) + k;
-          float o[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = c8 * 8 + j;
-            o[j] = acc[k * 8 + j] + ((p.bias != nullptr && c < p.cout_real) ? __ldg(p.bias + c) : 0.f);
-          }
-          if (c8 < p.out_c8) {
-            __nv_bfloat16* dst = view_ptr<__nv_bfloat16>(p.out, n, c8, So, ok ? v : 0);
-            if (p.accumulate && ok) {
+          const bool live = ok && c8 < p.out_c8;
+          uint32_t pk[4] = {0u, 0u, 0u, 0u};
+          if (live) {
+            __nv_bfloat16* dst = out_n + ((int64_t)c8 * So + v) * 8;
+            if (p.accumulate) {
               float old[8];
               Vec8<__nv_bfloat16>::load(dst, old);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] += old[j];
+              for (int j = 0; j < 8; ++j) acc[k * 8 + j] += old[j];
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = ok ? Vec8<__nv_bfloat16>::round(o[j]) : 0.f;
-            if (ok) Vec8<__nv_bfloat16>::store(dst, o);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = 0.f;
+            for (int i = 0; i < 4; ++i) {
+              const __nv_bfloat162 hpair = __floats2bfloat162_rn(acc[k * 8 + 2 * i], acc[k * 8 + 2 * i + 1]);
+              pk[i] = *reinterpret_cast<const uint32_t*>(&hpair);
+            }
+            *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
+          if (want_stats) {  // statistics of the ROUNDED values (what the next kernel reads); dead lanes contribute 0
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { acc[k * 8 + j] = o[j]; sq[k * 8 + j] = o[j] * o[j]; }
+            for (int i = 0; i < 4; ++i) {
+              acc[k * 8 + 2 * i] = __uint_as_float(pk[i] << 16);
+              acc[k * 8 + 2 * i + 1] = __uint_as_float(pk[i] & 0xffff0000u);
+            }
+          }
         }
-        if (p.sums != nullptr) {
+        if (want_stats) {
+          float sq[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sq[i] = acc[i] * acc[i];
           const float s1 = warp_reduce16(acc, lane);
           const float s2 = warp_reduce16(sq, lane);
           if ((lane & 1) == 0) {
@@ -209,11 +234,13 @@ __global__ void __launch_bounds__(256, 1)
             my_stats[256 + co0 + (lane >> 1)] += s2;
           }
         }
+        co0 += 32;
+        while (co0 >= p.cpad) { co0 -= p.cpad; ++t; }
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(BAR(kAccEmpty + as));
-      if (p.sums != nullptr && p.groups > 1) {
+      if (want_stats && p.groups > 1) {
         __syncwarp();
         for (int i = lane; i < 2 * 256; i += 32) {
           const int stat = i / 256, c = i % 256;
@@ -224,7 +251,7 @@ __global__ void __launch_bounds__(256, 1)
         __syncwarp();
       }
     }
-    if (p.sums != nullptr && p.groups == 1) {
+    if (want_stats && p.groups == 1) {
       __syncwarp();
       for (int i = lane; i < 2 * 256; i += 32) {
         const int stat = i / 256, c = i % 256;
@@ -311,7 +338,7 @@ static int launch_k2s2(int mode, const msb_tensor& x, const void* packed, const 
     MSB_CUDA_OK(cudaFuncSetAttribute(conv_k2s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2SmemBytes));
     attr_set = true;
   }
-  MSB_LAUNCH_PDL(conv_k2s2_kernel, dim3(grid), dim3(256), kK2SmemBytes, st, tmap, p);
+  MSB_LAUNCH_PDL(conv_k2s2_kernel, dim3(grid), dim3(kK2Threads), kK2SmemBytes, st, tmap, p);
   return MSB_OK;
 }
 

@@ -29,16 +29,16 @@ template <int NPAD, int TD, int J = 1, int ACC_SETS = 2>
 struct FwdCfg {
   static constexpr int kHaloPlaneBytes = (TD + 4) * kHaloH * kHaloW * 16;  // one c8 plane of the haloed tile
   static constexpr int kHaloBytes = 2 * kHaloPlaneBytes;                   // 16 input channels
-  // one weight stage = one (kh, kw) column: [k8 (2)][block (NB)][co (NPAD)][8 ci]; blocks hold the 5 kd taps in
-  // REVERSED order (W4..W0) between J-1 zero blocks on each side, so the operand for stacked planes j = 0..J-1 and
-  // input plane kd' is the same image viewed from block J+3-kd' (zero blocks = taps outside the 5-wide kernel).
-  static constexpr int kNB = 5 + 2 * (J - 1);
+  // one weight stage = one (kh, kw) column: [k8 (2)][block (5)][co (NPAD)][8 ci]; the blocks hold the 5 kd taps in
+  // REVERSED order (W4..W0), so the operand for input plane kd' and the stacked output planes j = j_lo..j_hi (tap
+  // kd = kd' - j) is the same image viewed from block 4 - kd' + j_lo, nblk = j_hi - j_lo + 1 blocks long.
+  static constexpr int kNB = 5;
   static constexpr int kBlockBytes = NPAD * 16;
   static constexpr int kWK8Bytes = kNB * kBlockBytes;
   static constexpr int kWStageBytes = 2 * kWK8Bytes;
   static constexpr int kWLoadBytes = 5 * kBlockBytes;                      // bytes TMA writes per (stage, k8)
   // as many weight stages as fit (<= 8): the stage ring has to cover the L2 latency of cp.async.bulk
-  static constexpr int kFixedBytes = 2 * kHaloBytes + 1024 /*barriers + stats*/ + 4 * 2 * NPAD * 4 + 128 /*alignment slack*/;
+  static constexpr int kFixedBytes = 2 * kHaloBytes + 1024 /*barriers*/ + 8 * 2 * NPAD * 4 /*stats*/ + 128 /*alignment slack*/;
   static constexpr int kWStagesFit = (227 * 1024 - kFixedBytes) / kWStageBytes;
   static constexpr int kWStages = kWStagesFit > 8 ? 8 : kWStagesFit;
   static constexpr int kAccCols = TD * NPAD;
@@ -48,10 +48,28 @@ struct FwdCfg {
                                  : (kColsNeeded <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = kFixedBytes + kWStages * kWStageBytes;
   static_assert(kWStages >= 2, "weight stages do not fit");
-  static_assert(TD % J == 0 && kNMma <= 256, "bad plane stacking");
+  static_assert(TD % J == 0 && (J < 5 ? J : 5) * NPAD <= 256, "bad plane stacking (an MMA covers <= 5 stacked planes)");
   static_assert(kColsNeeded <= 512, "TMEM overflow");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory overflow");
 };
+
+// issue order of the J+4 input planes of a stacked group: the overwriting ("init") planes first (see the MMA loop)
+template <int J>
+__host__ __device__ constexpr int kdp_order(int i) {
+  static_assert(J <= 10, "two init MMAs cover at most 10 stacked planes");
+  constexpr int kA = J - 1 < 4 ? J - 1 : 4;
+  constexpr int kB = 9;
+  constexpr int n_init = J > 5 ? 2 : 1;
+  if (i == 0) return kA;
+  if (n_init == 2 && i == 1) return kB;
+  int idx = i - n_init;
+  for (int k = 0; k < J + 4; ++k) {
+    if (k == kA || (n_init == 2 && k == kB)) continue;
+    if (idx == 0) return k;
+    --idx;
+  }
+  return -1;
+}
 
 struct FwdParams {
   int n, cin_pad, cout_real, out_c8;     // out_c8: 8-channel planes actually stored
@@ -84,8 +102,10 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // (tile, slice of 16-channel chunks)): every CTA streams only ITS slice of the weight set (the layer is otherwise
 // bound by pulling the whole 4-16 MB weight set through every SM) and adds its f32 partial tile into p.ws with vector
 // reductions; splitk_finalize_kernel applies bias / accumulate / rounding / BN sums and re-zeroes the workspace.
+constexpr int kFwdThreads = 384;  // w0 halo TMA, w1 MMA, w2 TMEM alloc + weight TMA, w3 idle, w4-11 epilogue
+
 template <int NPAD, int TD, int J, int ACC_SETS, int NS, bool SPLITK = false>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
     conv_k5_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const FwdParams p) {
   using Cfg = FwdCfg<NPAD, TD, J, ACC_SETS>;
   static_assert(NS == 1 || J == 1, "channel slicing only without plane stacking");
@@ -98,7 +118,7 @@ __global__ void __launch_bounds__(256, 1)
   // barrier map: [0,2) halo_full  [2,4) halo_empty  [4,6) acc_full  [6,8) acc_empty  [8,8+S) w_full  [8+S,8+2S) w_empty
   constexpr int kWF = 8, kWE = 8 + Cfg::kWStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * Cfg::kWStages);
-  float* stat_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);  // [4 warps][2][NPAD]
+  float* stat_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);  // [8 warps][2][NPAD]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = ptx::smem_u32(bars);
@@ -107,15 +127,10 @@ __global__ void __launch_bounds__(256, 1)
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(0 + i), 1); ptx::mbar_init(BAR(2 + i), 1); }
     for (int i = 0; i < Cfg::kWStages; ++i) { ptx::mbar_init(BAR(kWF + i), 1); ptx::mbar_init(BAR(kWE + i), 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(4 + i), 1); ptx::mbar_init(BAR(6 + i), 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(4 + i), 1); ptx::mbar_init(BAR(6 + i), 8); }
     ptx::fence_mbar_init();
   }
-  for (int i = threadIdx.x; i < 4 * 2 * NPAD; i += 256) stat_smem[i] = 0.f;
-  if (J > 1) {  // zero blocks of the weight stages are never written by TMA
-    uint4* wz = reinterpret_cast<uint4*>(w_smem);
-    for (int i = threadIdx.x; i < Cfg::kWStages * Cfg::kWStageBytes / 16; i += 256) wz[i] = make_uint4(0, 0, 0, 0);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros visible to the MMA (async proxy)
-  }
+  for (int i = threadIdx.x; i < 8 * 2 * NPAD; i += kFwdThreads) stat_smem[i] = 0.f;
   if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tmap_x);
   if (warp == 2) ptx::tmem_alloc<Cfg::kTmemCols>(ptx::smem_u32(tmem_slot));
   ptx::tc_fence_before();
@@ -180,8 +195,7 @@ __global__ void __launch_bounds__(256, 1)
             ptx::mbar_expect_tx(BAR(kWF + s), 2 * Cfg::kWLoadBytes);
 #pragma unroll
             for (int k8 = 0; k8 < 2; ++k8)
-              ptx::bulk_load(ptx::smem_u32(w_smem + s * Cfg::kWStageBytes + k8 * Cfg::kWK8Bytes +
-                                           (J - 1) * Cfg::kBlockBytes),
+              ptx::bulk_load(ptx::smem_u32(w_smem + s * Cfg::kWStageBytes + k8 * Cfg::kWK8Bytes),
                              src + (size_t)(st * 2 + k8) * Cfg::kWLoadBytes, Cfg::kWLoadBytes, BAR(kWF + s));
           }
           __syncwarp();
@@ -196,7 +210,6 @@ __global__ void __launch_bounds__(256, 1)
     // measured 102 clk per 128x128x16 MMA instead of the 64-clk tensor-core floor, tools/mma_probe.cu.)
     const bool leader = ptx::elect_one();
     const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);  // REDUX result = provably warp-uniform
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, n_slice, 0, 0);
     constexpr uint32_t a_hi = ptx::desc_hi((uint32_t)(kHaloW * 16)), b_hi = ptx::desc_hi(128u);
     constexpr uint32_t a_lbo16 = (uint32_t)Cfg::kHaloPlaneBytes >> 4, b_lbo16 = (uint32_t)Cfg::kWK8Bytes >> 4;
     uint32_t huse = 0, wuse = 0, iuse = 0;
@@ -233,10 +246,22 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll
           for (int g = 0; g < TD / J; ++g) {
 #pragma unroll
-            for (int kdp = 0; kdp < J + 4; ++kdp) {  // input plane g*J + kdp feeds output planes g*J + j, tap kd = kdp - j
+            for (int i = 0; i < J + 4; ++i) {
+              // input plane g*J + kdp feeds the stacked output planes j = j_lo..j_hi through tap kd = kdp - j.  Only
+              // the valid taps are issued (N = nblk * NPAD: 1..J blocks), which trims the triangular ends of the
+              // Toeplitz band: (J+4) full-width MMAs would spend 2*(J-1)*J/2 of their J*(J+4) blocks on zeros.
+              // An accumulation starts with the MMAs that OVERWRITE: kdp = min(4, J-1) initialises planes 0..4 and,
+              // for J > 5, kdp = 9 initialises planes 5..J-1 (an MMA spans at most 5 planes); all others accumulate.
+              const int kdp = kdp_order<J>(i);
+              const int j_lo = kdp > 4 ? kdp - 4 : 0;
+              const int j_hi = kdp < J - 1 ? kdp : J - 1;
+              const int nblk = j_hi - j_lo + 1;
+              const uint32_t idesc_k = ptx::make_idesc_bf16(128, nblk * (NPAD / NS), 0, 0);
               const uint32_t a_lo = a_lo1 + (uint32_t)((g * J + kdp) * kHaloH * kHaloW);
-              const uint32_t b_lo = b_lo0 + (uint32_t)(((J + 3 - kdp) * Cfg::kBlockBytes) >> 4);
-              if (leader) ptx::mma_bf16_split(d_base + g * Cfg::kNMma, a_lo, a_hi, b_lo, b_hi, idesc, kdp != 0 ? 1u : first);
+              const uint32_t b_lo = b_lo0 + (uint32_t)(((4 - kdp + j_lo) * Cfg::kBlockBytes) >> 4);
+              if (leader)
+                ptx::mma_bf16_split(d_base + g * Cfg::kNMma + j_lo * NPAD, a_lo, a_hi, b_lo, b_hi, idesc_k,
+                                    i >= (J > 5 ? 2 : 1) ? 1u : first);
             }
           }
           if (leader) ptx::mma_commit(BAR(kWE + s));  // weight stage free once these MMAs retire
@@ -254,11 +279,19 @@ __global__ void __launch_bounds__(256, 1)
     }
   } else if (warp >= 4) {
     // ================= epilogue: TMEM -> registers -> (bias, accumulate, round, BN sums) -> global =================
-    const int q = warp - 4;
+    // Two warpgroups (warps 4-7 / 8-11; a warp reads TMEM lane quadrant warp % 4) take alternate (plane, 16-column)
+    // blocks: with one warp per scheduler the loop is instruction-latency bound, and on the narrow layers (in_tr,
+    // out_tr, the 2-chunk 32-channel convs) it - not the MMA stream - set the pace of the kernel.
+    const int wg = (warp - 4) >> 2;
+    const int q = warp & 3;
     const int row = q * 32 + lane;
     const int hh = row >> 3, ww = row & 7;
     const int64_t S = (int64_t)p.d * p.h * p.w;
-    float* my_stats = stat_smem + q * 2 * NPAD;
+    float* my_stats = stat_smem + (warp - 4) * 2 * NPAD;
+    constexpr int kCb = (NPAD / NS) / 16;          // 16-column blocks per plane
+    const bool has_bias = p.bias != nullptr;
+    const bool bias_vec = has_bias && (reinterpret_cast<uintptr_t>(p.bias) % 16 == 0);
+    const bool want_stats = !SPLITK && p.sums != nullptr;
     uint32_t iuse = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
       const int tile = item / kdiv;
@@ -274,68 +307,88 @@ __global__ void __launch_bounds__(256, 1)
       ptx::tc_fence_after();
       const uint32_t t_base = tmem_base + as * Cfg::kAccCols + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int td = 0; td < TD; ++td) {
+      for (int it = wg; it < TD * kCb; it += 2) {
+        const int td = it / kCb, cb = it % kCb;
         const int d = db * TD + td;
         const bool ok = inb && d < p.d;
         const int64_t v = ((int64_t)d * p.h + h) * p.w + w;
-#pragma unroll 1
-        for (int cb = 0; cb < (NPAD / NS) / 16; ++cb) {
-          float acc[16];
-          ptx::tmem_ld16(t_base + td * NPAD + cb * 16, acc);
-          if constexpr (SPLITK) {
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const int c8 = cb * 2 + k;
-              if (c8 < p.out_c8 && ok) {
-                float* dst = p.ws + (((int64_t)n * p.out_c8 + c8) * S + v) * 8;
-                red_add_v4(dst, acc[k * 8 + 0], acc[k * 8 + 1], acc[k * 8 + 2], acc[k * 8 + 3]);
-                red_add_v4(dst + 4, acc[k * 8 + 4], acc[k * 8 + 5], acc[k * 8 + 6], acc[k * 8 + 7]);
-              }
-            }
-            continue;
-          }
-          float sq[16];
+        float acc[16];
+        ptx::tmem_ld16(t_base + td * NPAD + cb * 16, acc);
+        if constexpr (SPLITK) {
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
-            const int c8 = (c_first >> 3) + cb * 2 + k;
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int c = c8 * 8 + j;
-              float val = acc[k * 8 + j] + ((p.bias != nullptr && c < p.cout_real) ? __ldg(p.bias + c) : 0.f);
-              o[j] = val;
+            const int c8 = cb * 2 + k;
+            if (c8 < p.out_c8 && ok) {
+              float* dst = p.ws + (((int64_t)n * p.out_c8 + c8) * S + v) * 8;
+              red_add_v4(dst, acc[k * 8 + 0], acc[k * 8 + 1], acc[k * 8 + 2], acc[k * 8 + 3]);
+              red_add_v4(dst + 4, acc[k * 8 + 4], acc[k * 8 + 5], acc[k * 8 + 6], acc[k * 8 + 7]);
             }
+          }
+        } else {
+          const int c0 = c_first + cb * 16;
+          if (has_bias) {
+            if (bias_vec && c0 + 16 <= p.cout_real) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + i);
+                acc[4 * i] += b4.x; acc[4 * i + 1] += b4.y; acc[4 * i + 2] += b4.z; acc[4 * i + 3] += b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c0 + i < p.cout_real) acc[i] += __ldg(p.bias + c0 + i);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int c8 = (c0 >> 3) + k;
+            const bool live = ok && c8 < p.out_c8;
+            uint32_t pk[4] = {0u, 0u, 0u, 0u};
             if (p.out_f32) {
-              if (c8 < p.out_c8 && ok) Vec8<float>::store(view_ptr<float>(p.out, n, c8, S, v), o);
-            } else if (c8 < p.out_c8) {
-              __nv_bfloat16* dst = view_ptr<__nv_bfloat16>(p.out, n, c8, S, ok ? v : 0);
+              if (live) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = acc[k * 8 + j];
+                Vec8<float>::store(view_ptr<float>(p.out, n, c8, S, v), o);
+              }
+            } else if (live) {
+              __nv_bfloat16* dst = view_ptr<__nv_bfloat16>(p.out, n, c8, S, v);
               if (p.accumulate) {
                 float old[8];
+                Vec8<__nv_bfloat16>::load(dst, old);
+                if (p.ch_scale != nullptr) {
+                  const float* scp = p.ch_scale + (int64_t)n * p.out.c + c8 * 8;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) old[j] = 0.f;
-                if (ok) Vec8<__nv_bfloat16>::load(dst, old);
+                  for (int j = 0; j < 8; ++j) acc[k * 8 + j] = fmaf(acc[k * 8 + j], __ldg(scp + j), old[j]);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float sc = p.ch_scale ? __ldg(p.ch_scale + (int64_t)n * p.out.c + c8 * 8 + j) : 1.f;
-                  o[j] = fmaf(o[j], sc, old[j]);
+                  for (int j = 0; j < 8; ++j) acc[k * 8 + j] += old[j];
                 }
               }
 #pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = ok ? Vec8<__nv_bfloat16>::round(o[j]) : 0.f;
-              if (ok) Vec8<__nv_bfloat16>::store(dst, o);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = 0.f;
+              for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162 hpair = __floats2bfloat162_rn(acc[k * 8 + 2 * i], acc[k * 8 + 2 * i + 1]);
+                pk[i] = *reinterpret_cast<const uint32_t*>(&hpair);
+              }
+              *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
+            if (want_stats) {  // statistics of the ROUNDED values (what the next kernel reads); dead lanes add 0
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { acc[k * 8 + j] = o[j]; sq[k * 8 + j] = o[j] * o[j]; }
+              for (int i = 0; i < 4; ++i) {
+                acc[k * 8 + 2 * i] = __uint_as_float(pk[i] << 16);
+                acc[k * 8 + 2 * i + 1] = __uint_as_float(pk[i] & 0xffff0000u);
+              }
+            }
           }
-          if (p.sums != nullptr) {
+          if (want_stats) {
+            float sq[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sq[i] = acc[i] * acc[i];
             const float s1 = warp_reduce16(acc, lane);
             const float s2 = warp_reduce16(sq, lane);
             if ((lane & 1) == 0) {
-              my_stats[c_first + cb * 16 + (lane >> 1)] += s1;
-              my_stats[NPAD + c_first + cb * 16 + (lane >> 1)] += s2;
+              my_stats[c0 + (lane >> 1)] += s1;
+              my_stats[NPAD + c0 + (lane >> 1)] += s2;
             }
           }
         }
@@ -343,7 +396,7 @@ __global__ void __launch_bounds__(256, 1)
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(BAR(6 + as));
-      if (!SPLITK && p.sums != nullptr && p.groups > 1) {
+      if (want_stats && p.groups > 1) {
         // per-instance statistics: flush after every item (an item never straddles two n)
         __syncwarp();
         for (int i = lane; i < 2 * NPAD; i += 32) {
@@ -355,11 +408,11 @@ __global__ void __launch_bounds__(256, 1)
         __syncwarp();
       }
     }
-    if (!SPLITK && p.sums != nullptr && p.groups == 1) {
+    if (want_stats && p.groups == 1) {
       __syncwarp();
       for (int i = lane; i < 2 * NPAD; i += 32) {
         const int stat = i / NPAD, c = i % NPAD;
-        if (c < p.sums_c) atomicAdd(&p.sums[(int64_t)stat * p.sums_c + c], (double)my_stats[i]);
+        if (c < p.sums_c && my_stats[i] != 0.f) atomicAdd(&p.sums[(int64_t)stat * p.sums_c + c], (double)my_stats[i]);
       }
     }
   }
@@ -912,7 +965,7 @@ static int launch_fwd_ns(const CUtensorMap& tmap, FwdParams& p, int tiles, cudaS
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  MSB_LAUNCH_PDL((conv_k5_fwd_kernel<NPAD, TD, J, ACC_SETS, NS>), dim3(grid), dim3(256), Cfg::kSmemBytes, st, tmap, p);
+  MSB_LAUNCH_PDL((conv_k5_fwd_kernel<NPAD, TD, J, ACC_SETS, NS>), dim3(grid), dim3(kFwdThreads), Cfg::kSmemBytes, st, tmap, p);
   return MSB_OK;
 }
 
@@ -955,7 +1008,7 @@ static int launch_fwd_splitk(const msb_tensor& x, msb_dim3 dims, FwdParams& p, i
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  MSB_LAUNCH_PDL((conv_k5_fwd_kernel<NPAD, TD, 1, 1, 1, true>), dim3(grid), dim3(256), Cfg::kSmemBytes, st, tmap, p);
+  MSB_LAUNCH_PDL((conv_k5_fwd_kernel<NPAD, TD, 1, 1, 1, true>), dim3(grid), dim3(kFwdThreads), Cfg::kSmemBytes, st, tmap, p);
   const int64_t S = (int64_t)p.d * p.h * p.w;
   const dim3 fgrid((unsigned)((S + 2047) / 2048), (unsigned)p.out_c8, (unsigned)p.n);
   MSB_LAUNCH_PDL(splitk_finalize_kernel, fgrid, dim3(256), 0, st, p.ws, bias, p.cout_real, p.out, S, p.accumulate,
@@ -1087,14 +1140,17 @@ static int conv_k5_fwd_impl(const char* who, msb_tensor x, const void* packed, c
   }
   // plane stacking along N (debug flag 3 = 1 disables it): narrow outputs are bound by the A-operand fetch, so one
   // MMA produces J output planes from one activation window (see FwdCfg)
-  const bool stack = g_debug_flags[3] == 0;
+  const bool stack = g_debug_flags[3] != 1;
   switch (npad_sel) {
+    // deep stacks (J = TD = 8) amortise the triangular ends of the tap band best (736 clk per 8 planes vs 416 per 4
+    // for N_pad = 32) and re-fetch less halo ((TD+4)/TD); shallow volumes keep TD = 4
     case 16:
-      // the 5x5x1 kernel issues 5x fewer MMAs per halo tile: deeper d-blocks keep the halo re-fetch (TD+4)/TD low
-      if (kw_taps == 1 && stack && dims.d >= 8) return launch_fwd<16, 8, 4>(x, dims, p, st);
+      if (stack && dims.d >= 8) return launch_fwd<16, 8, 8>(x, dims, p, st);
       return stack ? launch_fwd<16, 4, 4>(x, dims, p, st) : launch_fwd<16, 4>(x, dims, p, st);
-    case 32: return stack ? launch_fwd<32, 4, 4>(x, dims, p, st) : launch_fwd<32, 4>(x, dims, p, st);
-    case 64: return stack ? launch_fwd<64, 4, 2>(x, dims, p, st) : launch_fwd<64, 4>(x, dims, p, st);
+    case 32:
+      if (stack && dims.d >= 8 && g_debug_flags[3] != 2) return launch_fwd<32, 8, 8>(x, dims, p, st);
+      return stack ? launch_fwd<32, 4, 4>(x, dims, p, st) : launch_fwd<32, 4>(x, dims, p, st);
+    case 64: return stack ? launch_fwd<64, 4, 4>(x, dims, p, st) : launch_fwd<64, 4>(x, dims, p, st);
     case 128: return launch_fwd<128, 2>(x, dims, p, st);
     default: return launch_fwd<256, 1>(x, dims, p, st);
   }

@@ -23,6 +23,15 @@ constexpr int kVoxPerBlock = 2048;
 static inline dim3 plane_grid(int n, int c, int64_t s) {
   return dim3((unsigned)((s + kVoxPerBlock - 1) / kVoxPerBlock), (unsigned)(c / 8), (unsigned)n);
 }
+// same planes, but about `target` blocks in total (kernels that loop over chunks and finish with atomics)
+static inline dim3 plane_grid_capped(int n, int c, int64_t s, int target = kNumSMs * 8) {
+  const int64_t chunks = (s + kVoxPerBlock - 1) / kVoxPerBlock;
+  const int64_t planes = (int64_t)(c / 8) * n;
+  int64_t gx = (target + planes - 1) / planes;
+  if (gx > chunks) gx = chunks;
+  if (gx < 1) gx = 1;
+  return dim3((unsigned)gx, (unsigned)(c / 8), (unsigned)n);
+}
 
 // block-level reduction of K per-thread floats; result valid in threads [0, K) of warp 0.. returned via smem
 template <int K>
@@ -167,6 +176,80 @@ __global__ void __launch_bounds__(kThreads)
   load_params(p, bnbuf, alpha1, alpha2, y.c, groups, groups == 1 ? 0 : n, c8);
   const int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock;
   const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
+#pragma unroll 2
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
+    float a[8], r[8];
+    Vec8<T>::load(view_ptr<T>(y, n, c8, s, v), a);
+    if (HAS_RES) Vec8<T>::load(view_ptr<T>(res, n, c8, s, v), r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = fmaf(a[j], p.scale[j], p.shift[j]);
+      if (HAS_TILE) t += __ldg(tile_src + ((int64_t)n * tile_c + ((c8 * 8 + j) % tile_c)) * s + v);
+      t = prelu(t, p.a1[j]);
+      if (HAS_RES) t = prelu(t + r[j], p.a2[j]);
+      a[j] = t;
+    }
+    Vec8<T>::store(view_ptr<T>(out, n, c8, s, v), a);
+  }
+}
+
+// bn_finalize + bn_act_fwd in ONE launch: every block derives the scale/shift of its 8 channels from the f64 sums
+// (training) or the running statistics (eval); block x == 0 of each (n, plane) also publishes them in bnbuf for the
+// backward kernels, and block (x == 0, n == 0) applies the running-statistics update.
+template <typename T, bool HAS_RES, bool HAS_TILE>
+__global__ void __launch_bounds__(kThreads)
+    bn_fwd_fused_kernel(msb_tensor y, msb_tensor out, msb_tensor res, const float* __restrict__ tile_src, int tile_c,
+                        const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
+                        float momentum, float eps, int training, float* __restrict__ bnbuf,
+                        const float* __restrict__ alpha1, const float* __restrict__ alpha2, int64_t s, int groups) {
+  pdl_wait();
+  pdl_trigger();
+  const int c8 = blockIdx.y, n = blockIdx.z, c = y.c;
+  const int g = groups == 1 ? 0 : n;
+  const int64_t gc = (int64_t)groups * c;
+  BnActParams p;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = c8 * 8 + j;
+    double mean, var;
+    if (training) {
+      mean = sums[(int64_t)g * c + ch] / count;
+      var = sums[gc + (int64_t)g * c + ch] / count - mean * mean;
+      if (var < 0) var = 0;
+    } else {
+      mean = rmean[ch];
+      var = rvar[ch];
+    }
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float scale = __ldg(gamma + ch) * invstd;
+    p.scale[j] = scale;
+    p.shift[j] = __ldg(beta + ch) - (float)mean * scale;
+    p.a1[j] = __ldg(alpha1 + ch);
+    p.a2[j] = alpha2 ? __ldg(alpha2 + ch) : 0.f;
+    if (blockIdx.x == 0 && threadIdx.x == j) {
+      bnbuf[0 * gc + (int64_t)g * c + ch] = scale;
+      bnbuf[1 * gc + (int64_t)g * c + ch] = p.shift[j];
+      bnbuf[2 * gc + (int64_t)g * c + ch] = (float)mean;
+      bnbuf[3 * gc + (int64_t)g * c + ch] = invstd;
+    }
+  }
+  if (training && rmean != nullptr && blockIdx.x == 0 && n == 0 && threadIdx.x < 8) {
+    const int ch = c8 * 8 + threadIdx.x;
+    double mean_acc = 0, var_acc = 0;
+    for (int gg = 0; gg < groups; ++gg) {
+      const double mean = sums[(int64_t)gg * c + ch] / count;
+      double var = sums[gc + (int64_t)gg * c + ch] / count - mean * mean;
+      if (var < 0) var = 0;
+      mean_acc += mean;
+      var_acc += var;
+    }
+    rmean[ch] = momentum * rmean[ch] + (1.f - momentum) * (float)(mean_acc / groups);
+    rvar[ch] = momentum * rvar[ch] + (1.f - momentum) * (float)(var_acc / groups);
+  }
+  const int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock;
+  const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
+#pragma unroll 2
   for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
     float a[8], r[8];
     Vec8<T>::load(view_ptr<T>(y, n, c8, s, v), a);
@@ -225,25 +308,29 @@ __global__ void __launch_bounds__(kThreads)
   float acc[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-  const int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock;
-  const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
-  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
-    float a[8], r[8], go[8];
-    Vec8<T>::load(view_ptr<T>(y, n, c8, s, v), a);
-    Vec8<T>::load(view_ptr<T>(gout, n, c8, s, v), go);
-    if (HAS_RES) Vec8<T>::load(view_ptr<T>(res, n, c8, s, v), r);
+  // grid-stride over 2048-voxel chunks: the launch caps the blocks per (n, plane) so that the per-channel f64
+  // atomics at the end (same 32 addresses for every block of a plane) stay a few hundred per address
+  for (int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock; v0 < s; v0 += (int64_t)gridDim.x * kVoxPerBlock) {
+    const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
+#pragma unroll 2
+    for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
+      float a[8], r[8], go[8];
+      Vec8<T>::load(view_ptr<T>(y, n, c8, s, v), a);
+      Vec8<T>::load(view_ptr<T>(gout, n, c8, s, v), go);
+      if (HAS_RES) Vec8<T>::load(view_ptr<T>(res, n, c8, s, v), r);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float tile = 0.f;
-      if (HAS_TILE) tile = __ldg(tile_src + ((int64_t)n * tile_c + ((c8 * 8 + j) % tile_c)) * s + v);
-      float g1, g2, da1, da2;
-      bwd_point<HAS_RES>(a[j], HAS_RES ? r[j] : 0.f, tile, go[j], p.scale[j], p.shift[j], p.a1[j], p.a2[j], g1, g2,
-                         da1, da2);
-      const float xhat = (a[j] - mean[j]) * invstd[j];
-      acc[j] += g1;
-      acc[8 + j] += g1 * xhat;
-      acc[16 + j] += da1;
-      acc[24 + j] += da2;
+      for (int j = 0; j < 8; ++j) {
+        float tile = 0.f;
+        if (HAS_TILE) tile = __ldg(tile_src + ((int64_t)n * tile_c + ((c8 * 8 + j) % tile_c)) * s + v);
+        float g1, g2, da1, da2;
+        bwd_point<HAS_RES>(a[j], HAS_RES ? r[j] : 0.f, tile, go[j], p.scale[j], p.shift[j], p.a1[j], p.a2[j], g1, g2,
+                           da1, da2);
+        const float xhat = (a[j] - mean[j]) * invstd[j];
+        acc[j] += g1;
+        acc[8 + j] += g1 * xhat;
+        acc[16 + j] += da1;
+        acc[24 + j] += da2;
+      }
     }
   }
   block_reduce_to_smem<32>(acc, &sred[0][0]);
@@ -261,11 +348,28 @@ __global__ void __launch_bounds__(kThreads)
     bn_act_bwd_apply_kernel(msb_tensor y, msb_tensor res, const float* __restrict__ tile_src, int tile_c,
                             msb_tensor gout, const float* __restrict__ bnbuf, const float* __restrict__ alpha1,
                             const float* __restrict__ alpha2, const double* __restrict__ red, double count,
-                            int training, msb_tensor dy, msb_tensor dres, int dres_acc, int64_t s, int groups) {
+                            int training, msb_tensor dy, msb_tensor dres, int dres_acc, int64_t s, int groups,
+                            float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dalpha1,
+                            float* __restrict__ dalpha2) {
   pdl_wait();
   pdl_trigger();
   const int c8 = blockIdx.y, n = blockIdx.z;
   const int g = groups == 1 ? 0 : n;
+  if (blockIdx.x == 0 && n == 0 && threadIdx.x < 8) {  // parameter gradients (one block per plane owns them)
+    const int ch = c8 * 8 + threadIdx.x;
+    const int64_t gcc = (int64_t)groups * y.c;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int gg = 0; gg < groups; ++gg) {
+      s0 += red[0 * gcc + (int64_t)gg * y.c + ch];
+      s1 += red[1 * gcc + (int64_t)gg * y.c + ch];
+      s2 += red[2 * gcc + (int64_t)gg * y.c + ch];
+      s3 += red[3 * gcc + (int64_t)gg * y.c + ch];
+    }
+    if (dbeta) dbeta[ch] += (float)s0;
+    if (dgamma) dgamma[ch] += (float)s1;
+    if (dalpha1) dalpha1[ch] += (float)s2;
+    if (dalpha2) dalpha2[ch] += (float)s3;
+  }
   BnActParams p;
   load_params(p, bnbuf, alpha1, alpha2, y.c, groups, g, c8);
   float mean[8], invstd[8], m_g1[8], m_g1x[8];
@@ -281,6 +385,7 @@ __global__ void __launch_bounds__(kThreads)
   }
   const int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock;
   const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
+#pragma unroll 2
   for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
     float a[8], r[8], go[8], dr[8];
     Vec8<T>::load(view_ptr<T>(y, n, c8, s, v), a);
@@ -568,6 +673,28 @@ int msb_bn_act_fwd(msb_tensor y, msb_tensor out, msb_tensor residual, const floa
   return MSB_OK;
 }
 
+int msb_bn_fwd_fused(msb_tensor y, msb_tensor out, msb_tensor residual, const float* tile_src, int tile_c,
+                     const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float momentum, float eps, int training, float* bnbuf, const float* alpha1,
+                     const float* alpha2, int n, int64_t s, int groups, void* stream) {
+  const bool has_res = residual.ptr != nullptr;
+  MSB_REQUIRE(view_ok(y) && view_ok(out) && out.c == y.c && out.dtype == y.dtype && bnbuf && alpha1 && gamma && beta,
+              "msb_bn_fwd_fused: bad y/out/bnbuf/alpha1/gamma/beta");
+  MSB_REQUIRE(!has_res || (view_ok(residual) && residual.c == y.c && residual.dtype == y.dtype && alpha2),
+              "msb_bn_fwd_fused: residual needs matching view and alpha2");
+  MSB_REQUIRE(!tile_src || tile_c > 0, "msb_bn_fwd_fused: tile_c must be > 0");
+  MSB_REQUIRE(groups == 1 || groups == n, "msb_bn_fwd_fused: groups must be 1 or n");
+  MSB_REQUIRE(training ? (sums != nullptr && count > 0) : (running_mean && running_var),
+              "msb_bn_fwd_fused: training needs sums, eval needs running stats");
+  MSB_DISPATCH_DTYPE(y.dtype, MSB_BOOL_DISPATCH2(has_res, tile_src != nullptr,
+                                                 MSB_LAUNCH_PDL((bn_fwd_fused_kernel<T, B0, B1>), plane_grid(n, y.c, s),
+                                                                dim3(kThreads), 0, as_stream(stream), y, out, residual,
+                                                                tile_src, tile_c, sums, count, gamma, beta,
+                                                                running_mean, running_var, momentum, eps, training,
+                                                                bnbuf, alpha1, alpha2, s, groups);););
+  return MSB_OK;
+}
+
 int msb_bn_act_bwd_reduce(msb_tensor y, msb_tensor residual, const float* tile_src, int tile_c, msb_tensor gout,
                           const float* bnbuf, const float* alpha1, const float* alpha2, int n, int64_t s, int groups,
                           double* red, void* stream) {
@@ -579,7 +706,7 @@ int msb_bn_act_bwd_reduce(msb_tensor y, msb_tensor residual, const float* tile_s
   MSB_REQUIRE(groups == 1 || groups == n, "msb_bn_act_bwd_reduce: groups must be 1 or n");
   MSB_DISPATCH_DTYPE(y.dtype, MSB_BOOL_DISPATCH2(has_res, tile_src != nullptr,
                                                  MSB_LAUNCH_PDL((bn_act_bwd_reduce_kernel<T, B0, B1>),
-                                                                plane_grid(n, y.c, s), dim3(kThreads), 0,
+                                                                plane_grid_capped(n, y.c, s), dim3(kThreads), 0,
                                                                 as_stream(stream), y, residual, tile_src, tile_c, gout,
                                                                 bnbuf, alpha1, alpha2, s, groups, red);););
   return MSB_OK;
@@ -605,15 +732,13 @@ int msb_bn_act_bwd_apply(msb_tensor y, msb_tensor residual, const float* tile_sr
       y.dtype, MSB_BOOL_DISPATCH2(has_res, tile_src != nullptr, {
         if (has_dres)
           MSB_LAUNCH_PDL((bn_act_bwd_apply_kernel<T, B0, B1, true>), grid, dim3(kThreads), 0, st, y, residual, tile_src,
-                         tile_c, gout, bnbuf, alpha1, alpha2, red, count, training, dy, dres, dres_accumulate, s, groups);
+                         tile_c, gout, bnbuf, alpha1, alpha2, red, count, training, dy, dres, dres_accumulate, s, groups,
+                         dgamma, dbeta, dalpha1, has_res ? dalpha2 : nullptr);
         else
           MSB_LAUNCH_PDL((bn_act_bwd_apply_kernel<T, B0, B1, false>), grid, dim3(kThreads), 0, st, y, residual,
                          tile_src, tile_c, gout, bnbuf, alpha1, alpha2, red, count, training, dy, dres, dres_accumulate,
-                         s, groups);
+                         s, groups, dgamma, dbeta, dalpha1, has_res ? dalpha2 : nullptr);
       }););
-  if (dgamma || dbeta || dalpha1 || dalpha2)
-    MSB_LAUNCH_PDL(bn_param_grad_kernel, dim3((y.c + 127) / 128), dim3(128), 0, st, red, y.c, groups, dgamma, dbeta,
-                   dalpha1, has_res ? dalpha2 : nullptr);
   return MSB_OK;
 }
 

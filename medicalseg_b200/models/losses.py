@@ -15,6 +15,8 @@ from __future__ import annotations
 
 from typing import List, Optional
 
+import weakref
+
 import numpy as np
 import torch
 
@@ -118,16 +120,22 @@ def class_weights(logits: torch.Tensor) -> torch.Tensor:
 
 
 class _FusedEval:
-    """one fused forward shared by the CE and Dice objects of a MixedLoss (keyed on the logits tensor identity)"""
+    """one fused forward shared by the CE and Dice objects of a MixedLoss.  The cache is keyed on the IDENTITY of the
+    logits / labels / weight tensor objects (weak references: an id() or data_ptr() can be reused by the next step's
+    tensors once the old ones are freed, which would hand out a result whose autograd graph is already consumed)."""
+    refs = None
     key = None
     result = None
 
 
 def _fused(logits, labels, class_w, ignore_index):
-    key = (logits.data_ptr(), labels.data_ptr(), class_w.data_ptr(), logits._version, ignore_index, id(logits))
-    if _FusedEval.key == key and _FusedEval.result is not None:
+    key = (logits._version, ignore_index)
+    r = _FusedEval.refs
+    if (r is not None and r[0]() is logits and r[1]() is labels and r[2]() is class_w and _FusedEval.key == key
+            and _FusedEval.result is not None):
         return _FusedEval.result
     res = _DiceCEFunction.apply(logits, labels, class_w, ignore_index)
+    _FusedEval.refs = (weakref.ref(logits), weakref.ref(labels), weakref.ref(class_w))
     _FusedEval.key, _FusedEval.result = key, res
     return res
 

@@ -160,11 +160,10 @@ class _BnAct:
         if self.bnbuf is None or self.bnbuf.numel() != 4 * g * c:
             self.bnbuf = torch.empty(4 * g * c, dtype=torch.float32, device=y.buf.device)
         count = y.s * (y.n if g == 1 else 1)
-        ops.bn_finalize(sums if eng.training else None, count, st.phys(self.bn.weight), st.phys(self.bn.bias),
-                        st.phys(self.bn.mean), st.phys(self.bn.var), BN_MOMENTUM, BN_EPS, eng.training, c, g,
-                        self.bnbuf)
         a2 = st.phys(self.relu2._weight) if (self.relu2 is not None and residual is not None) else None
-        ops.bn_act_fwd(y, out, residual, tile, tile_c, self.bnbuf, st.phys(self.relu1._weight), a2, g)
+        ops.bn_fwd_fused(y, out, residual, tile, tile_c, sums if eng.training else None, count,
+                         st.phys(self.bn.weight), st.phys(self.bn.bias), st.phys(self.bn.mean), st.phys(self.bn.var),
+                         BN_MOMENTUM, BN_EPS, eng.training, self.bnbuf, st.phys(self.relu1._weight), a2, g)
         self.saved = (y, residual, tile, tile_c, count, g)
 
     def bwd(self, gout: B8, dy: B8, dres: Optional[B8] = None, dres_acc=False):

@@ -101,6 +101,13 @@ def bn_act_fwd(y: B8, out: B8, residual: Optional[B8], tile_src, tile_c, bnbuf, 
          _ptr(alpha2), y.n, y.s, groups, _stream())
 
 
+def bn_fwd_fused(y: B8, out: B8, residual: Optional[B8], tile_src, tile_c, sums, count, gamma, beta, rmean, rvar,
+                 momentum, eps, training, bnbuf, alpha1, alpha2, groups):
+    call("msb_bn_fwd_fused", y.mt, out.mt, _mt(residual), _ptr(tile_src), int(tile_c), _ptr(sums), float(count),
+         _ptr(gamma), _ptr(beta), _ptr(rmean), _ptr(rvar), float(momentum), float(eps), int(training), _ptr(bnbuf),
+         _ptr(alpha1), _ptr(alpha2), y.n, y.s, groups, _stream())
+
+
 def bn_act_bwd_reduce(y: B8, residual, tile_src, tile_c, gout: B8, bnbuf, alpha1, alpha2, groups, red):
     call("msb_bn_act_bwd_reduce", y.mt, _mt(residual), _ptr(tile_src), int(tile_c), gout.mt, _ptr(bnbuf),
          _ptr(alpha1), _ptr(alpha2), y.n, y.s, groups, _ptr(red), _stream())

@@ -72,6 +72,12 @@ def test_bn_prelu_residual_fwd_bwd(dt, groups):
     t2 = act1 + rq
     ref = torch.where(t2 > 0, t2, v(a2_) * t2)
     assert rel(out.to_ncdhw(), ref.detach()) <= tol(dt)
+    # the fused finalize + normalise launch (what VNet uses) gives the same output, bnbuf and running statistics
+    rm2, rv2 = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    bnbuf2, out2 = torch.zeros(4 * g * c, device="cuda"), B8(n, c, dims, dt, device="cuda")
+    ops.bn_fwd_fused(yb, out2, rb, None, 0, sums, count, gamma, beta, rm2, rv2, 0.9, 1e-5, True, bnbuf2, a1, a2, g)
+    assert torch.equal(out2.buf, out.buf) and torch.equal(bnbuf2, bnbuf)
+    assert torch.equal(rm2, rm) and torch.equal(rv2, rv)
     if g == 1:  # Paddle running-stat convention: 0.9*running + 0.1*batch, biased variance
         assert float((rm - 0.1 * mean.flatten()).abs().max()) < 1e-6
         assert float((rv - (0.9 + 0.1 * var.flatten())).abs().max()) < 1e-5
@@ -179,7 +185,8 @@ def test_down_conv_and_up_conv(k, s, ci, co, dims, dt):
 
 
 K5_CASES = [(32, 32, (6, 16, 8)), (16, 16, (5, 20, 11)), (64, 64, (4, 16, 16)), (128, 128, (3, 16, 8)),
-            (256, 256, (2, 8, 8)), (32, 2, (6, 18, 10)), (32, 32, (9, 7, 13))]
+            (256, 256, (2, 8, 8)), (32, 2, (6, 18, 10)), (32, 32, (9, 7, 13)), (32, 32, (16, 16, 16)),
+            (16, 16, (8, 16, 8)), (64, 64, (7, 9, 8)), (32, 16, (19, 16, 8))]
 
 
 @pytest.mark.parametrize("cin,cout,dims", K5_CASES)

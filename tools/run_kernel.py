@@ -19,11 +19,52 @@ CASES = {  # name -> (channels, cube edge)
 GFLOP = lambda c, e: 2 * 125 * c * c * e ** 3 / 1e9  # noqa: E731  (per volume, one pass)
 
 
+def k2s2(what, reps):
+    """k2scatter: up_tr32.up_conv fwd (64 -> 16, 64^3 -> 128^3); k2scatter_acc: down_tr32.down_conv dgrad (32 -> 16,
+    accumulate); k2gather: down_tr32.down_conv fwd (16 -> 32, 128^3 -> 64^3)"""
+    from medicalseg_b200 import ops
+    from medicalseg_b200.ops import B8
+    dev = torch.device("cuda", 0)
+    n, big, small = 2, (128, 128, 128), (64, 64, 64)
+    if what == "k2gather":
+        a, b = 32, 16            # weight [A][B][2][2][2]: gather produces A from B
+        w = torch.randn(a, b, 2, 2, 2, device=dev) * 0.1
+        x = B8(n, b, big, torch.bfloat16, device=dev); x.buf.normal_()
+        out = B8(n, a, small, torch.bfloat16, device=dev)
+        packed = torch.empty(ops.k2s2_packed_bytes(b, 32), dtype=torch.uint8, device=dev)
+        ops.k2s2_pack(w, packed, b, a, 0, b, 32)
+        fn = lambda: ops.k2s2_gather(x, packed, None, a, out, 1, None)  # noqa: E731
+        mb = (x.buf.numel() + out.buf.numel()) * 2 / 1e6
+    else:
+        a, b = (64, 16) if what == "k2scatter" else (32, 16)
+        acc = what == "k2scatter_acc"
+        w = torch.randn(a, b, 2, 2, 2, device=dev) * 0.1
+        x = B8(n, a, small, torch.bfloat16, device=dev); x.buf.normal_()
+        out = B8(n, b, big, torch.bfloat16, device=dev, zero=True)
+        packed = torch.empty(ops.k2s2_packed_bytes(a, 16), dtype=torch.uint8, device=dev)
+        ops.k2s2_pack(w, packed, a, b, 1, a, 16)
+        fn = lambda: ops.k2s2_scatter(x, packed, None, b, out, acc, 1, None)  # noqa: E731
+        mb = (x.buf.numel() + out.buf.numel() * (2 if acc else 1)) * 2 / 1e6
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print("%s: %.4f ms/call, %.1f MB algorithmic -> %.0f GB/s" % (what, ms, mb, mb / ms))
+
+
 def main():
     from medicalseg_b200 import ops
     from medicalseg_b200.ops import B8
     what = sys.argv[1] if len(sys.argv) > 1 else "fwd32"
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    if what.startswith("k2"):
+        return k2s2(what, reps)
     kind = "wgrad" if what.startswith("wgrad") else "fwd"
     c, e = CASES[what[len(kind):]]
     n, dims = 2, (e, e, e)
