@@ -516,6 +516,9 @@ struct WgParams {
   float* ws;                            // [125][cout_real][cin_real] f32
   int dbg_swap;
   int pad, units_total;                 // 2 / 25 for the 5x5x5 conv; 0 / 1 for the pointwise (1x1x1) weight gradient
+  int s2_c8n;                           // > 0: x is the BIG grid of a 2x2x2/stride-2 conv (s2_c8n = its planes); the
+                                        // M rows are (tap, channel) and every tap's sub-lattice is fetched by a
+                                        // stride-2 5-D TMA box (tmap_x built by make_b8_tmap_s2) - no space-to-depth copy
 };
 
 template <int NPAD, int TH>
@@ -578,6 +581,16 @@ __global__ void __launch_bounds__(256, 1)
           const uint32_t b = use & 1, ph = (use >> 1) & 1;
           ptx::mbar_wait(BAR(2 + b), ph ^ 1);
           ptx::mbar_expect_tx(BAR(b), bytes);
+          if (p.s2_c8n > 0) {
+            const int per_tap = p.s2_c8n < 16 ? p.s2_c8n : 16;  // planes of one tap inside this 16-plane M tile
+            for (int i = 0; i < 16 / per_tap; ++i) {
+              const int plane0 = mh * 16 + i * per_tap;
+              const int tap = plane0 / p.s2_c8n, c8 = plane0 % p.s2_c8n;
+              ptx::tma_load_5d(ptx::smem_u32(x_smem + b * Cfg::kXBytes + i * per_tap * Cfg::kGroupBytes), &tmap_x, BAR(b),
+                               0, 2 * tw * kWgTileW + (tap & 1), 2 * th * TH + ((tap >> 1) & 1), 2 * d + (tap >> 2),
+                               n * p.x_c8_total + c8);
+            }
+          } else
           for (int q = 0; q < planes_valid; ++q)
             ptx::tma_load_4d(ptx::smem_u32(x_smem + b * Cfg::kXBytes + q * x_planes * Cfg::kGroupBytes), &tmap_x, BAR(b),
                              (tw * kWgTileW - p.pad) * 8, th * TH - p.pad, d + g * p.qm + q - p.pad,
@@ -1049,7 +1062,10 @@ static int launch_wgrad(const msb_tensor& x, const msb_tensor& dy, WgParams& p, 
   p.chunks = (p.total_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
   CUtensorMap tmx, tmdy;
   int rc;
-  if ((rc = make_b8_tmap(&tmx, x, p.n, dims, kWgTileW + 4, TH + 4, 1, p.cin_m / 8))) return rc;
+  if (p.s2_c8n > 0) {  // x = big grid (extents 2 * dims), sampled on the tap sub-lattices
+    const msb_dim3 big = {2 * dims.d, 2 * dims.h, 2 * dims.w};
+    if ((rc = make_b8_tmap_s2(&tmx, x, p.n, big, kWgTileW + 4, TH + 4, p.s2_c8n < 16 ? p.s2_c8n : 16))) return rc;
+  } else if ((rc = make_b8_tmap(&tmx, x, p.n, dims, kWgTileW + 4, TH + 4, 1, p.cin_m / 8))) return rc;
   if ((rc = make_b8_tmap(&tmdy, dy, p.n, dims, kWgTileW, TH, 1, dy.c / 8))) return rc;
   const int items = p.num_passes * p.chunks;
   const int grid = items < kNumSMs ? items : kNumSMs;
@@ -1209,7 +1225,7 @@ int msb_conv_k5_wgrad(msb_tensor x, msb_tensor dy, float* dw, float* dbias, int 
   p.kd_groups = (5 + qeff - 1) / qeff;
   p.ws = reinterpret_cast<float*>(workspace);
   p.dbg_swap = g_debug_flags[1];
-  p.pad = 2; p.units_total = 25;
+  p.pad = 2; p.units_total = 25; p.s2_c8n = 0;
   const int npad = msb_conv_k5_out_pad(dy.c);
   int rc = MSB_ERR_UNSUPPORTED;
   if (g_debug_flags[2] == 0) rc = launch_wgrad_v2(x, dy, cout, cin, n, dims, p.ws, st);
@@ -1291,8 +1307,8 @@ int msb_channel_sum(msb_tensor x, int c_real, int n, int64_t s, float* out, void
 }
 
 size_t msb_conv_k2s2_wgrad_workspace_bytes(int n, int c_big, int c_small, msb_dim3 big_dims) {
-  const size_t xs = (size_t)n * c_big * big_dims.d * big_dims.h * big_dims.w * sizeof(__nv_bfloat16);
-  return ((xs + 255) / 256) * 256 + (size_t)c_small * 8 * c_big * sizeof(float);
+  (void)n; (void)big_dims;
+  return (size_t)c_small * 8 * c_big * sizeof(float);
 }
 
 int msb_conv_k2s2_wgrad(msb_tensor big, msb_tensor small, float* dw, float* dbias, int n, msb_dim3 big_dims,
@@ -1310,25 +1326,17 @@ int msb_conv_k2s2_wgrad(msb_tensor big, msb_tensor small, float* dw, float* dbia
   cudaStream_t st = as_stream(stream);
   const msb_dim3 sd = {big_dims.d / 2, big_dims.h / 2, big_dims.w / 2};
   const int64_t Ss = (int64_t)sd.d * sd.h * sd.w, Sb = Ss * 8;
-  const int c8n = big.c / 8, cxs = 8 * big.c;
-  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(workspace);
-  const size_t xs_bytes = (((size_t)n * big.c * Sb * sizeof(__nv_bfloat16) + 255) / 256) * 256;
-  float* ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + xs_bytes);
-  {
-    int bx = (int)((Ss + 255) / 256);
-    if (bx > 1024) bx = 1024;
-    MSB_LAUNCH_PDL(s2d_k2_kernel, dim3(bx, 8 * c8n, n), dim3(256), 0, st, big, xs, c8n, sd.d, sd.h, sd.w);
-  }
+  const int cxs = 8 * big.c;  // M rows = (tap, big channel): a pointwise weight gradient over the 8 tap sub-lattices
+  float* ws = reinterpret_cast<float*>(workspace);
   MSB_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)small.c * cxs * sizeof(float), st));
-  msb_tensor xst;
-  xst.ptr = xs; xst.n_stride = (int64_t)cxs * Ss; xst.c = cxs; xst.dtype = MSB_BF16;
   WgParams p;
   p.n = n; p.cin_pad = cxs; p.cin_real = cxs; p.cout_real = small.c; p.dy_c8 = small.c / 8;
   p.d = sd.d; p.h = sd.h; p.w = sd.w;
-  p.x_c8_total = cxs / 8;
+  p.x_c8_total = (int)(big.n_stride / (Sb * 8));
   p.dy_c8_total = (int)(small.n_stride / (Ss * 8));
   p.cin_m = 128; p.mhalves = cxs / 128; p.qm = 1; p.kd_groups = 1;
-  p.ws = ws; p.dbg_swap = 0; p.pad = 0; p.units_total = 1;
+  p.ws = ws; p.dbg_swap = 0; p.pad = 0; p.units_total = 1; p.s2_c8n = big.c / 8;
+  const msb_tensor& xst = big;
   int rc;
   switch (msb_conv_k5_out_pad(small.c)) {
     case 16: rc = launch_wgrad<16, 8>(xst, small, p, sd, st); break;

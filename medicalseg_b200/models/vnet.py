@@ -187,11 +187,20 @@ class _K5:
         self.eng, self.conv, self.cin, self.cout = eng, conv, cin, cout
         self.packed_f = self.packed_b = None
         self.packed_version = -1
+        self.pack_args = None   # remembered after the first (lazy) pack: lets the engine re-pack ahead of use
+        self.pack_event = None  # set when the last pack ran on the engine's side stream
+        eng.register_packer(self)
+
+    def repack(self):
+        self._pack(*self.pack_args)
 
     def _pack(self, x_c, out_c):
         eng, st = self.eng, self.eng.store
         if self.packed_version == eng.param_version and self.packed_f is not None:
+            eng.wait_pack(self)
             return
+        eng.wait_pack(self)  # an older side-stream pack of the same buffers must have finished
+        self.pack_args = (x_c, out_c)
         w = st.view(self.conv.weight)
         dev = w.device
         cin_pad, cout_pad = x_c, ops.k5_out_pad(out_c)
@@ -250,6 +259,15 @@ class _K2S2:
                    and a % 16 == 0 and b % 16 == 0 and a <= 256 and b <= 256)
         self.packed = [None, None]
         self.version = [-1, -1]
+        self.pack_args = [None, None]
+        self.pack_event = None
+        if self.ok:
+            eng.register_packer(self)
+
+    def repack(self):
+        for mode in (0, 1):
+            if self.pack_args[mode] is not None:
+                self._pack(mode, *self.pack_args[mode])
 
     def usable(self, big_dims):
         return self.ok and all(d % 2 == 0 for d in big_dims)
@@ -257,7 +275,10 @@ class _K2S2:
     def _pack(self, mode, c_red_pad, c_out_pad):
         eng = self.eng
         if self.version[mode] == eng.param_version and self.packed[mode] is not None:
+            eng.wait_pack(self)
             return self.packed[mode]
+        eng.wait_pack(self)
+        self.pack_args[mode] = (c_red_pad, c_out_pad)
         w = eng.store.view(self.conv.weight)
         if self.packed[mode] is None:
             self.packed[mode] = torch.empty(ops.k2s2_packed_bytes(c_red_pad, c_out_pad), dtype=torch.uint8,
@@ -289,11 +310,20 @@ class _K551:
         assert self.cout_f <= 16 or fold_side == 0
         self.packed_f = self.packed_b = None
         self.packed_version = -1
+        self.pack_args = None
+        self.pack_event = None
+        eng.register_packer(self)
+
+    def repack(self):
+        self._pack()
 
     def _pack(self):
         eng, st = self.eng, self.eng.store
         if self.packed_version == eng.param_version and self.packed_f is not None:
+            eng.wait_pack(self)
             return
+        eng.wait_pack(self)
+        self.pack_args = ()
         w = st.view(self.conv.weight)
         self.f_cin_pad, self.f_cout_pad = _pad(self.cin_f, 16), ops.k5_out_pad(_pad(self.cout_f, 8))
         if self.packed_f is None:
@@ -466,6 +496,7 @@ class VNet(_Module):
         self._wg_ws = None
         self._k2_ws = None
         self._sk_ws = None
+        self._side_stream = None
         self._masks: Optional[Dict[str, torch.Tensor]] = None
         self._tape = None
         self.grad_ready_hook = None  # callable(lo, hi) on flat-grad ranges, fired in backward order (DDP buckets)
@@ -531,6 +562,40 @@ class VNet(_Module):
     def mark_parameters_updated(self):
         """called by the optimizer after a step so packed tensor-core operands are rebuilt"""
         self.param_version += 1
+        self.prepack_async()
+
+    def register_packer(self, packer):
+        if not hasattr(self, "_packers"):
+            self._packers = []
+        self._packers.append(packer)
+
+    def prepack_async(self):
+        """Re-packs the bf16 tensor-core weight images of every layer (in forward order) on a SIDE stream right after
+        the optimizer step: the packing kernels are HBM-bound and small, the convolutions they feed are tensor-bound,
+        so they overlap instead of sitting on the critical path in front of every conv.  Each layer waits on its own
+        event just before its first use (wait_pack)."""
+        if self.dtype != torch.bfloat16 or not getattr(self, "async_prepack", True):
+            return
+        ready = [p for p in self._packers if p.pack_args is not None and (not isinstance(p.pack_args, list) or
+                                                                          any(a is not None for a in p.pack_args))]
+        if not ready:
+            return
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream()
+        self._side_stream.wait_stream(cur)
+        with torch.cuda.stream(self._side_stream):
+            for p in ready:
+                p.repack()
+                ev = torch.cuda.Event()
+                ev.record(self._side_stream)
+                p.pack_event = ev
+
+    def wait_pack(self, packer):
+        ev = packer.pack_event
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            packer.pack_event = None
 
     def set_dropout_masks(self, masks: Optional[Dict[str, torch.Tensor]]):
         """explicit Dropout3D masks ([N,C] of 0 / 2) for the next train-mode forward; None -> draw internally"""

@@ -97,7 +97,8 @@ def test_param_store_layout_matches_reference_parameter_tree():
     from oracle import vnet_oracle as vo
 
     class Eng:  # minimal engine stand-in: only the store is needed to build the tree
-        pass
+        def register_packer(self, packer):
+            pass
     eng = Eng()
     eng.store = V.ParamStore()
     eng.dtype = torch.float32

@@ -16,16 +16,25 @@ import torch  # noqa: E402
 
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    mri = len(sys.argv) > 2 and sys.argv[2] == "mri"  # BASELINE configs[3]: 512x512x12, 20 classes, anisotropic
     import bench
     from medicalseg_b200.models import VNet, losses as L
     from medicalseg_b200.optimizer import Momentum, PolynomialDecay
 
     device = torch.device("cuda", 0)
-    model = VNet(num_classes=bench.NUM_CLASSES, compute_dtype="bf16", seed=0)
+    if mri:
+        model = VNet(num_classes=20, compute_dtype="bf16", seed=0,
+                     kernel_size=[[2, 2, 4], [2, 2, 2], [2, 2, 2], [2, 2, 2]],
+                     stride_size=[[2, 2, 1], [2, 2, 1], [2, 2, 2], [2, 2, 2]])
+    else:
+        model = VNet(num_classes=bench.NUM_CLASSES, compute_dtype="bf16", seed=0)
     model.train()
     losses = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1])], "coef": [1]}
     opt = Momentum(PolynomialDecay(0.001, 15000), model.parameters(), 0.9, 1e-4)
     img, lab = bench.synthetic_gpu_batch(device, seed=0)
+    if mri:
+        img = torch.rand(2, 1, 512, 512, 12, device=device)
+        lab = torch.randint(0, 20, (2, 512, 512, 12), device=device, dtype=torch.int32)
 
     def step():
         logits_list = model(img)
