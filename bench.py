@@ -118,12 +118,18 @@ def run_ours(args):
     reducer = DistributedGradReducer(model.store.grad).attach(model)
     opt = Momentum(PolynomialDecay(0.001, 15000), model.parameters(), 0.9, 1e-4, grad_scale=reducer.grad_scale)
     img, lab = synthetic_gpu_batch(device, seed=rank)
-    calls = {"n": 0}
     orig_call = _lib.call
+    # world == 1: the whole step is ONE CUDA graph (medicalseg_b200.graph.GraphedTrainStep, the `to_static_training`
+    # hook of core.train); world > 1 keeps the eager path (bucketed NCCL all-reduce overlapping backward)
+    use_graph = world == 1 and not args.no_graph
+    gstep = None
+    if use_graph:
+        from medicalseg_b200.graph import GraphedTrainStep
+        gstep = GraphedTrainStep(model, losses, opt, reducer=reducer)
 
-    def step(images, labels):
+    def eager_step(images, labels):
         logits_list = model(images)
-        loss_list, dice = L.loss_computation(logits_list, labels, losses)  # dice: D2H sync, as the reference
+        loss_list, dice = L.loss_computation(logits_list, labels, losses)  # dice: lazy D2H (read on first use)
         loss = sum(loss_list)
         loss.backward()
         reducer.wait()
@@ -131,6 +137,9 @@ def run_ours(args):
         opt._learning_rate.step()
         model.clear_gradients()
         return loss, dice
+
+    def step(images, labels):
+        return gstep(images, labels) if use_graph else eager_step(images, labels)
 
     def barrier():
         if world > 1:
@@ -140,11 +149,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()  # started before the warm-up so that nvidia-smi is already streaming in the timed regions
-    for _ in range(args.warmup):
-        step(img, lab)
-    barrier()
-
-    # ---- device-resident timing (value) -------------------------------------------------------------
+    # ---- count this library's C-ABI calls of ONE step (every call launches >= 1 kernel of libmedseg_b200.so) ----------
     import medicalseg_b200.ops as ops_mod
     counter = {"n": 0}
 
@@ -152,7 +157,16 @@ def run_ours(args):
         counter["n"] += 1
         return orig_call(name, *a)
 
+    eager_step(img, lab)
     ops_mod.call = counting_call
+    eager_step(img, lab)
+    ops_mod.call = orig_call
+    calls_per_step = counter["n"]
+    for _ in range(args.warmup):
+        step(img, lab)
+    barrier()
+
+    # ---- device-resident timing (value) -------------------------------------------------------------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     windows = []
@@ -163,7 +177,6 @@ def run_ours(args):
     e1.record()
     barrier()
     windows.append((w0, time.time()))
-    ops_mod.call = orig_call
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
@@ -178,11 +191,21 @@ def run_ours(args):
     w0 = time.time()
     e0.record()
     last = None
-    for _ in range(e2e_steps):
-        d_img = h_img.to(device, non_blocking=True)
-        d_lab = h_lab.to(device, non_blocking=True)
-        loss, dice = step(d_img, d_lab)
-        last = float(loss.item())  # D2H read of the step's result
+    if use_graph:
+        # input pipelining: the H2D copy of batch i+1 (pinned host memory -> staging buffers, copy stream) is issued
+        # right after the replay of step i was launched, so it overlaps that step; every step still copies its inputs
+        # H2D and reads its loss D2H inside the timed region
+        gstep.prefetch(h_img, h_lab)
+        for _ in range(e2e_steps):
+            loss, dice = gstep()
+            gstep.prefetch(h_img, h_lab)
+            last = float(loss.item())  # D2H read of the step's result
+    else:
+        for _ in range(e2e_steps):
+            d_img = h_img.to(device, non_blocking=True)
+            d_lab = h_lab.to(device, non_blocking=True)
+            loss, dice = step(d_img, d_lab)
+            last = float(loss.item())  # D2H read of the step's result
     e1.record()
     barrier()
     windows.append((w0, time.time()))
@@ -230,7 +253,10 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(h_img.numel() * 4 + h_lab.numel() * 4),
                     "d2h_bytes_per_step": int(4 * (1 + 2 + NUM_CLASSES)), "ms_per_step": round(e2e_ms, 3),
                     "last_loss": last},
-            "gpu_launches": counter["n"],
+            # C-ABI calls of one eager step x timed steps (a graph replay launches the same kernels; several calls
+            # launch 2-3 kernels, so this is a lower bound of the kernel count)
+            "gpu_launches": calls_per_step * args.steps,
+            "launch_mode": "cuda-graph replay (1 cudaGraphLaunch/step)" if use_graph else "eager (python -> C ABI)",
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": round(achieved, 2), "peak": burst, "unit": "TFLOP/s",
                          "frac": round(achieved / burst, 4),
@@ -315,6 +341,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph (N=1)")
     ap.add_argument("--cpu-depth", type=int, default=32, help="depth of the 128x128 slab the CPU arm processes per step")
     args = ap.parse_args()
     if args.impl == "reference":

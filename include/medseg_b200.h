@@ -238,6 +238,10 @@ int msb_dice_ce_bwd(const float* logits, const int32_t* labels, const float* cla
  * g' = grad_scale*g + wd*p;  v = mu*v + g';  p -= lr*v                                                 */
 int msb_momentum_step(float* p, const float* g, float* v, int64_t count, float lr, float mu, float wd,
                       float grad_scale, void* stream);
+/* same update with the learning rate read from DEVICE memory (one f32): lets a captured CUDA graph of the whole
+ * train step be replayed while the PolynomialDecay schedule advances */
+int msb_momentum_step_lrdev(float* p, const float* g, float* v, int64_t count, const float* lr_dev, float mu, float wd,
+                            float grad_scale, void* stream);
 
 /* ---- preprocessing (tools/preprocess_utils/values.py:54-87, geometry.py:31-69) -----------------------*/
 int msb_hunorm(const float* src, float* dst, int64_t count, float hu_min, float hu_max, float hu_nan, void* stream);

@@ -74,6 +74,7 @@ SIGNATURES = {
     "msb_dice_ce_finalize": (I, [P, I, P, P]),
     "msb_dice_ce_bwd": (I, [P, P, P, P, I, I, L, I, F, F, P, P, P]),
     "msb_momentum_step": (I, [P, P, P, L, F, F, F, F, P]),
+    "msb_momentum_step_lrdev": (I, [P, P, P, L, P, F, F, F, P]),
     "msb_hunorm": (I, [P, P, L, F, F, F, P]),
     "msb_minmax": (I, [P, L, P, P]),
     "msb_normalize": (I, [P, P, L, F, F, P, P]),

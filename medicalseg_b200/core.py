@@ -85,6 +85,13 @@ def train(model, train_dataset, val_dataset=None, optimizer=None, save_dir="outp
     os.makedirs(save_dir, exist_ok=True)
     reducer = DistributedGradReducer(model.store.grad).attach(model)
     optimizer.grad_scale = reducer.grad_scale
+    # `to_static_training` (the reference switches Paddle to its static-graph mode here, core/train.py:97-99): capture
+    # the whole step into ONE CUDA graph.  Needs fixed batch shapes and a single process (the bucketed NCCL all-reduce
+    # of world > 1 stays eager); a trailing short batch falls back to the eager step.
+    graphed = None
+    if to_static_training and world == 1:
+        from .graph import GraphedTrainStep
+        graphed = GraphedTrainStep(model, losses, optimizer, reducer=reducer)
     prof_range = None
     if profiler_options:  # "batch_range=[10,20]" -> cudaProfilerStart/Stop window (ncu / nsys --capture-range)
         import re
@@ -95,6 +102,7 @@ def train(model, train_dataset, val_dataset=None, optimizer=None, save_dir="outp
     iters_per_epoch = max((n // world + batch_size - 1) // batch_size, 1)
     avg_loss, mdice, save_models, best_mean_dice, best_model_iter = 0.0, 0.0, deque(), -1.0, -1
     it = start_iter
+    n_acc = 0
     batch_start = time.time()
     reader_cost = batch_cost = 0.0
     while it < iters:
@@ -106,34 +114,53 @@ def train(model, train_dataset, val_dataset=None, optimizer=None, save_dir="outp
             reader_cost += time.time() - batch_start
             if prof_range and it == prof_range[0]:
                 torch.cuda.cudart().cudaProfilerStart()
-            logits_list = model(images)
-            loss_list, per_channel_dice = loss_computation(logits_list, labels.to(torch.int32), losses)
-            loss = sum(loss_list)
-            loss.backward()
-            reducer.wait()
-            optimizer.step()
-            lr = optimizer.get_lr()
-            it += 1
-            if hasattr(optimizer._learning_rate, "step"):
-                optimizer._learning_rate.step()
-            model.clear_gradients()
+            use_graph = graphed is not None and (not graphed.captured or tuple(images.shape) == tuple(graphed.s_img.shape))
+            if use_graph:
+                first = not graphed.captured
+                lr = optimizer.get_lr()
+                loss, per_channel_dice = graphed(images, labels.to(torch.int32))
+                it += 1 + (graphed.warmup if first else 0)  # the capture's warm-up steps are real optimizer steps
+            else:
+                if graphed is not None and graphed.captured:  # odd-shaped batch: eager step with a host-side LR
+                    saved_lr_dev, optimizer.lr_dev = optimizer.lr_dev, None
+                    model._defer_prepack = False
+                logits_list = model(images)
+                loss_list, per_channel_dice = loss_computation(logits_list, labels.to(torch.int32), losses)
+                loss = sum(loss_list)
+                loss.backward()
+                reducer.wait()
+                optimizer.step()
+                lr = optimizer.get_lr()
+                it += 1
+                if hasattr(optimizer._learning_rate, "step"):
+                    optimizer._learning_rate.step()
+                model.clear_gradients()
+                if graphed is not None and graphed.captured:
+                    optimizer.lr_dev = saved_lr_dev
+                    optimizer.lr_dev.fill_(float(optimizer.get_lr()))
+                    model._defer_prepack = True
+                    if model._side_stream is not None:  # eager re-pack of this step must not overlap the next replay's
+                        torch.cuda.current_stream().wait_stream(model._side_stream)
             if prof_range and it == prof_range[1]:
                 torch.cuda.cudart().cudaProfilerStop()
             avg_loss += float(loss.detach())
             mdice += float(np.mean(per_channel_dice)) * 100
             batch_cost += time.time() - batch_start
+            n_acc += 1
             if it % log_iters == 0 and rank == 0:
-                avg_loss /= log_iters
-                mdice /= log_iters
-                bc, rc = batch_cost / log_iters, reader_cost / log_iters
+                avg_loss /= n_acc  # (== log_iters except after a graph capture, whose warm-up steps are not logged)
+                mdice /= n_acc
+                bc, rc = batch_cost / n_acc, reader_cost / n_acc
                 eta = int((iters - it) * bc)
                 _log("[TRAIN] epoch: {}, iter: {}/{}, loss: {:.4f}, DSC: {:.4f}, lr: {:.6f}, batch_cost: {:.4f}, "
                      "reader_cost: {:.5f}, ips: {:.4f} samples/sec | ETA {:02d}:{:02d}:{:02d}".format(
                          it // iters_per_epoch, it, iters, avg_loss, mdice, lr, bc, rc, batch_size / bc,
                          eta // 3600, (eta % 3600) // 60, eta % 60))
                 avg_loss = mdice = reader_cost = batch_cost = 0.0
+                n_acc = 0
             elif it % log_iters == 0:
                 avg_loss = mdice = reader_cost = batch_cost = 0.0
+                n_acc = 0
             if (it % save_interval == 0 or it == iters) and val_dataset is not None:
                 result = evaluate(model, val_dataset, losses, print_detail=True, save_dir=save_dir)
                 model.train()

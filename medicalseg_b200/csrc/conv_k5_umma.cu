@@ -730,27 +730,9 @@ __global__ void __launch_bounds__(256) channel_sum_bf16_kernel(msb_tensor x, int
 }
 
 // ---- 2x2x2 / stride-2 weight gradients on the tensor cores ---------------------------------------------
-// space-to-depth: xs[n][tap*C8 + c8][o][8] = x[n][c8][2o + tap][8]  (tap = kd*4 + kh*2 + kw), so that
-// dW[sc][bc][tap] = sum_o big[2o+tap][bc] * small[o][sc] becomes a pointwise (1x1x1) weight gradient.
-__global__ void __launch_bounds__(256) s2d_k2_kernel(msb_tensor x, __nv_bfloat16* __restrict__ xs, int c8n, int sd,
-                                                     int sh, int sw) {
-  pdl_wait();
-  pdl_trigger();
-  const int plane = blockIdx.y, n = blockIdx.z;  // plane = tap * c8n + c8
-  const int tap = plane / c8n, c8 = plane % c8n;
-  const int kd = tap >> 2, kh = (tap >> 1) & 1, kw = tap & 1;
-  const int64_t ss = (int64_t)sd * sh * sw;
-  const int bh = sh * 2, bw = sw * 2;
-  const int64_t sb = (int64_t)sd * 2 * bh * bw;
-  const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(x.ptr) + (int64_t)n * x.n_stride + (int64_t)c8 * sb * 8;
-  __nv_bfloat16* dst = xs + (((int64_t)n * 8 * c8n + plane) * ss) * 8;
-  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < ss; o += (int64_t)gridDim.x * blockDim.x) {
-    const int ow = (int)(o % sw), oh = (int)((o / sw) % sh), od = (int)(o / ((int64_t)sw * sh));
-    const int64_t vb = ((int64_t)(od * 2 + kd) * bh + (oh * 2 + kh)) * bw + (ow * 2 + kw);
-    *reinterpret_cast<uint4*>(dst + o * 8) = __ldg(reinterpret_cast<const uint4*>(src + vb * 8));
-  }
-}
-
+// dW[sc][bc][tap] = sum_o big[2o+tap][bc] * small[o][sc] is a pointwise (1x1x1) weight gradient whose M rows are
+// (tap, big channel); conv_k5_wgrad_kernel fetches every tap's sub-lattice of the big grid with a stride-2 5-D TMA box
+// (WgParams::s2_c8n), so no space-to-depth copy is materialised.
 // dw[sc][bc][tap] += ws[sc][tap*cbig + bc]
 __global__ void __launch_bounds__(256) k2s2_unpack_kernel(const float* __restrict__ ws, float* __restrict__ dw,
                                                           int csmall, int cbig) {

@@ -208,10 +208,9 @@ __global__ void __launch_bounds__(kThreads)
   const int c8 = blockIdx.y, n = blockIdx.z, c = y.c;
   const int g = groups == 1 ? 0 : n;
   const int64_t gc = (int64_t)groups * c;
-  BnActParams p;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int ch = c8 * 8 + j;
+  __shared__ float sh_scale[8], sh_shift[8];
+  if (threadIdx.x < 8) {  // f64 statistics -> f32 scale/shift: one thread per channel, broadcast through smem
+    const int ch = c8 * 8 + threadIdx.x;
     double mean, var;
     if (training) {
       mean = sums[(int64_t)g * c + ch] / count;
@@ -223,16 +222,25 @@ __global__ void __launch_bounds__(kThreads)
     }
     const float invstd = (float)(1.0 / sqrt(var + (double)eps));
     const float scale = __ldg(gamma + ch) * invstd;
-    p.scale[j] = scale;
-    p.shift[j] = __ldg(beta + ch) - (float)mean * scale;
-    p.a1[j] = __ldg(alpha1 + ch);
-    p.a2[j] = alpha2 ? __ldg(alpha2 + ch) : 0.f;
-    if (blockIdx.x == 0 && threadIdx.x == j) {
+    const float shift = __ldg(beta + ch) - (float)mean * scale;
+    sh_scale[threadIdx.x] = scale;
+    sh_shift[threadIdx.x] = shift;
+    if (blockIdx.x == 0) {
       bnbuf[0 * gc + (int64_t)g * c + ch] = scale;
-      bnbuf[1 * gc + (int64_t)g * c + ch] = p.shift[j];
+      bnbuf[1 * gc + (int64_t)g * c + ch] = shift;
       bnbuf[2 * gc + (int64_t)g * c + ch] = (float)mean;
       bnbuf[3 * gc + (int64_t)g * c + ch] = invstd;
     }
+  }
+  __syncthreads();
+  BnActParams p;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = c8 * 8 + j;
+    p.scale[j] = sh_scale[j];
+    p.shift[j] = sh_shift[j];
+    p.a1[j] = __ldg(alpha1 + ch);
+    p.a2[j] = alpha2 ? __ldg(alpha2 + ch) : 0.f;
   }
   if (training && rmean != nullptr && blockIdx.x == 0 && n == 0 && threadIdx.x < 8) {
     const int ch = c8 * 8 + threadIdx.x;
@@ -408,26 +416,6 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
-__global__ void bn_param_grad_kernel(const double* __restrict__ red, int c, int groups, float* dgamma, float* dbeta,
-                                     float* dalpha1, float* dalpha2) {
-  pdl_wait();
-  pdl_trigger();
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
-  const int64_t gc = (int64_t)groups * c;
-  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-  for (int g = 0; g < groups; ++g) {
-    s0 += red[0 * gc + (int64_t)g * c + ch];
-    s1 += red[1 * gc + (int64_t)g * c + ch];
-    s2 += red[2 * gc + (int64_t)g * c + ch];
-    s3 += red[3 * gc + (int64_t)g * c + ch];
-  }
-  if (dbeta) dbeta[ch] += (float)s0;
-  if (dgamma) dgamma[ch] += (float)s1;
-  if (dalpha1) dalpha1[ch] += (float)s2;
-  if (dalpha2) dalpha2[ch] += (float)s3;
-}
-
 // ---------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kThreads) channel_scale_kernel(msb_tensor src, msb_tensor dst,
@@ -573,10 +561,11 @@ __global__ void __launch_bounds__(kHeadTile)
 
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) momentum_kernel(float* __restrict__ p, const float* __restrict__ g,
-                                                       float* __restrict__ v, int64_t count, float lr, float mu,
-                                                       float wd, float gs) {
+                                                       float* __restrict__ v, int64_t count, float lr,
+                                                       const float* __restrict__ lr_dev, float mu, float wd, float gs) {
   pdl_wait();
   pdl_trigger();
+  if (lr_dev != nullptr) lr = __ldg(lr_dev);  // learning rate read from device memory (CUDA-graph replays)
   const int64_t n4 = count >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -791,7 +780,19 @@ int msb_momentum_step(float* p, const float* g, float* v, int64_t count, float l
               "msb_momentum_step: buffers must be 16-byte aligned");
   int64_t want = (count / 4 + 255) / 256 + 1;
   const int blocks = (int)(want < (int64_t)kNumSMs * 8 ? want : (int64_t)kNumSMs * 8);
-  MSB_LAUNCH_PDL(momentum_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), p, g, v, count, lr, mu, wd,
+  MSB_LAUNCH_PDL(momentum_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), p, g, v, count, lr,
+                 (const float*)nullptr, mu, wd, grad_scale);
+  return MSB_OK;
+}
+
+int msb_momentum_step_lrdev(float* p, const float* g, float* v, int64_t count, const float* lr_dev, float mu, float wd,
+                            float grad_scale, void* stream) {
+  MSB_REQUIRE(p && g && v && lr_dev && count > 0, "msb_momentum_step_lrdev: bad arguments");
+  MSB_REQUIRE((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(v)) % 16 == 0,
+              "msb_momentum_step_lrdev: buffers must be 16-byte aligned");
+  int64_t want = (count / 4 + 255) / 256 + 1;
+  const int blocks = (int)(want < (int64_t)kNumSMs * 8 ? want : (int64_t)kNumSMs * 8);
+  MSB_LAUNCH_PDL(momentum_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), p, g, v, count, 0.f, lr_dev, mu, wd,
                  grad_scale);
   return MSB_OK;
 }

@@ -31,17 +31,26 @@ class LazyHostArray:
     __array_priority__ = 100
 
     def __init__(self, dev: torch.Tensor):
+        self._np = None
+        self._dev = None
+        if torch.cuda.is_current_stream_capturing():
+            # inside a CUDA-graph capture nothing may touch the host: keep the (static) device tensor; the graph owner
+            # (GraphedTrainStep) hands out a fresh LazyHostArray of it after every replay
+            self._dev, self._pinned, self._event = dev, None, None
+            return
         self._pinned = torch.empty(dev.shape, dtype=dev.dtype, pin_memory=True)
         self._pinned.copy_(dev, non_blocking=True)
         self._event = torch.cuda.Event()
         self._event.record()
-        self._np = None
 
     def numpy(self) -> np.ndarray:
         if self._np is None:
-            self._event.synchronize()
-            self._np = self._pinned.numpy().copy()
-            self._pinned = None
+            if self._dev is not None:
+                self._np = self._dev.detach().cpu().numpy()
+            else:
+                self._event.synchronize()
+                self._np = self._pinned.numpy().copy()
+                self._pinned = None
         return self._np
 
     def __array__(self, dtype=None, copy=None):

@@ -497,6 +497,7 @@ class VNet(_Module):
         self._k2_ws = None
         self._sk_ws = None
         self._side_stream = None
+        self._defer_prepack = False  # GraphedTrainStep: the re-pack is issued at the START of the captured step
         self._masks: Optional[Dict[str, torch.Tensor]] = None
         self._tape = None
         self.grad_ready_hook = None  # callable(lo, hi) on flat-grad ranges, fired in backward order (DDP buckets)
@@ -562,7 +563,8 @@ class VNet(_Module):
     def mark_parameters_updated(self):
         """called by the optimizer after a step so packed tensor-core operands are rebuilt"""
         self.param_version += 1
-        self.prepack_async()
+        if not self._defer_prepack:
+            self.prepack_async()
 
     def register_packer(self, packer):
         if not hasattr(self, "_packers"):
@@ -597,10 +599,12 @@ class VNet(_Module):
             torch.cuda.current_stream().wait_event(ev)
             packer.pack_event = None
 
-    def set_dropout_masks(self, masks: Optional[Dict[str, torch.Tensor]]):
-        """explicit Dropout3D masks ([N,C] of 0 / 2) for the next train-mode forward; None -> draw internally"""
+    def set_dropout_masks(self, masks: Optional[Dict[str, torch.Tensor]], persistent: bool = False):
+        """explicit Dropout3D masks ([N,C] of 0 / 2) for the next train-mode forward (every forward until changed when
+        `persistent`); None -> draw internally"""
         self._masks = None if masks is None else {k: v.to(self.device, torch.float32).contiguous()
                                                   for k, v in masks.items()}
+        self._masks_persistent = bool(persistent) and masks is not None
 
     def __call__(self, x):
         return self.forward(x)
@@ -825,7 +829,8 @@ class VNet(_Module):
                         self.num_classes)
         tape["ao"] = ao
         self._tape = tape if record else None
-        self._masks = None
+        if not getattr(self, "_masks_persistent", False):
+            self._masks = None
         return logits
 
     # ---------------------------------------------------------------- backward

@@ -295,6 +295,11 @@ def momentum_step(p, g, v, lr, mu, wd, grad_scale=1.0):
          float(grad_scale), _stream())
 
 
+def momentum_step_lrdev(p, g, v, lr_dev, mu, wd, grad_scale=1.0):
+    call("msb_momentum_step_lrdev", _ptr(p), _ptr(g), _ptr(v), p.numel(), _ptr(lr_dev), float(mu), float(wd),
+         float(grad_scale), _stream())
+
+
 # ---- preprocessing --------------------------------------------------------------------------------------------
 def hunorm(src, dst, hu_min, hu_max, hu_nan):
     call("msb_hunorm", _ptr(src), _ptr(dst), src.numel(), float(hu_min), float(hu_max), float(hu_nan), _stream())

@@ -43,14 +43,19 @@ class Momentum:
         self._store, self._owner = store, getattr(parameters, "owner", None)
         self.momentum, self.weight_decay, self.grad_scale = momentum, float(weight_decay or 0.0), grad_scale
         self.velocity = torch.zeros_like(store.flat)
+        self.lr_dev = None  # device copy of the learning rate (set by GraphedTrainStep: graph replays read it)
 
     def get_lr(self):
         lr = self._learning_rate
         return lr.get_lr() if hasattr(lr, "get_lr") else float(lr)
 
     def step(self):
-        ops.momentum_step(self._store.flat, self._store.grad, self.velocity, self.get_lr(), self.momentum,
-                          self.weight_decay, self.grad_scale)
+        if self.lr_dev is not None:
+            ops.momentum_step_lrdev(self._store.flat, self._store.grad, self.velocity, self.lr_dev, self.momentum,
+                                    self.weight_decay, self.grad_scale)
+        else:
+            ops.momentum_step(self._store.flat, self._store.grad, self.velocity, self.get_lr(), self.momentum,
+                              self.weight_decay, self.grad_scale)
         if self._owner is not None:
             self._owner.mark_parameters_updated()
 

@@ -112,3 +112,20 @@ def test_train_and_val_entry_points_run_on_synthetic_config(tmp_path):
                          "--save_dir", str(tmp_path / "out2")], capture_output=True, text=True, env=env, timeout=600)
     assert r3.returncode == 0, r3.stderr[-2000:]
     assert "iter: 7/8" in r3.stdout and "iter: 6/8" not in r3.stdout  # resumed at iteration 6
+
+
+@pytest.mark.gpu
+def test_train_entry_point_with_to_static_training_cuda_graph(tmp_path):
+    """--to_static_training (reference flag, train.py:88) captures the train step into one CUDA graph; the run must log,
+    evaluate (eager forward with lazily re-packed weights) and checkpoint like the eager one, and learn."""
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    cfg = os.path.join(ROOT, "configs/synthetic/vnet_synthetic_64.yml")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "train.py"), "--config", cfg, "--iters", "10", "--log_iters", "2",
+                        "--save_interval", "10", "--do_eval", "--save_dir", str(tmp_path / "out"), "--seed", "0",
+                        "--to_static_training"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "[TRAIN] epoch:" in r.stdout and "[EVAL] #Images: 2, Dice:" in r.stdout
+    assert os.path.exists(tmp_path / "out" / "iter_10" / "model.pdparams")
+    assert os.path.exists(tmp_path / "out" / "best_model" / "model.pdparams")
+    losses = [float(l.split("loss: ")[1].split(",")[0]) for l in r.stdout.splitlines() if "[TRAIN]" in l]
+    assert len(losses) >= 3 and losses[-1] < losses[0]

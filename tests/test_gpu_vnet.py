@@ -140,3 +140,56 @@ def test_product_path_rejects_cpu_tensors():
         m(torch.rand(1, 1, 16, 16, 16))
     with pytest.raises(RuntimeError):
         L.DiceLoss()(torch.rand(1, 2, 4, 4, 4), torch.zeros(1, 4, 4, 4, dtype=torch.int32))
+
+
+def test_graphed_train_step_matches_eager():
+    """GraphedTrainStep (whole step = one CUDA graph, LR read from device memory, weight re-packing forked onto a side
+    stream inside the capture) performs the same optimizer steps as the eager loop: 2 eager warm-up steps + 3 replays
+    vs 5 eager steps on the same batch with the same (persistent) dropout masks.  Tolerance: the f32 atomics of the
+    weight-gradient kernels make the last bits order dependent -> parameters within 2e-3 of the largest |param| change."""
+    from oracle import vnet_oracle as vo
+    from medicalseg_b200.models import VNet as V, losses as L
+    from medicalseg_b200.optimizer import Momentum as M, PolynomialDecay as P
+    from medicalseg_b200.graph import GraphedTrainStep
+    img, lab = vo.synthetic_batch(2, (32, 32, 32), 2, seed=3)
+    masks = vo.make_dropout_masks(2, seed=5)
+    img, lab = img.cuda(), lab.cuda()
+
+    def make():
+        m = V(num_classes=2, compute_dtype="bf16", seed=0)
+        m.train()
+        m.set_dropout_masks(masks, persistent=True)
+        losses = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1])], "coef": [1]}
+        opt = M(P(0.01, 100), m.parameters(), 0.9, 1e-4)
+        return m, losses, opt
+
+    m1, l1, o1 = make()
+    p0 = m1.store.flat.clone()
+    eager_losses = []
+    for _ in range(5):
+        ll, dice = L.loss_computation(m1(img), lab, l1)
+        loss = sum(ll)
+        loss.backward()
+        o1.step()
+        o1._learning_rate.step()
+        m1.clear_gradients()
+        eager_losses.append(float(loss))
+    m2, l2, o2 = make()
+    g = GraphedTrainStep(m2, l2, o2, warmup=2)
+    graph_losses = []
+    for _ in range(3):
+        loss, dice = g(img, lab)
+        graph_losses.append(float(loss))
+        assert np.all(np.isfinite(np.asarray(dice)))
+    assert g.captured and o2._learning_rate.last_epoch == o1._learning_rate.last_epoch == 5
+    for a, b in zip(eager_losses[2:], graph_losses):
+        assert abs(a - b) <= 2e-3 * abs(a), (eager_losses, graph_losses)
+    moved = float((m1.store.flat - p0).abs().max())
+    assert moved > 0
+    assert float((m1.store.flat - m2.store.flat).abs().max()) <= 2e-3 * moved + 1e-6
+    # running statistics of the deep levels amplify the last-bit differences of the bf16 activations: 1e-2 of the range
+    assert float((m1.store.buffers - m2.store.buffers).abs().max()) <= 1e-2 * float(m1.store.buffers.abs().max())
+    # a different batch through the captured graph (static input buffers are refreshed)
+    img2, lab2 = vo.synthetic_batch(2, (32, 32, 32), 2, seed=9)
+    loss2, _ = g(img2.cuda(), lab2.cuda())
+    assert np.isfinite(float(loss2)) and abs(float(loss2) - graph_losses[-1]) > 0

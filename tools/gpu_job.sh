@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
-timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench.log 2>&1; tail -1 gpurun_out/bench.log | cut -c1-300
-timeout 200 python tools/step_timeline.py 3 > gpurun_out/timeline.log 2>&1; head -60 gpurun_out/timeline.log | cut -c1-130
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; tail -8 gpurun_out/pytest_gpu.log | cut -c1-250
+MSB_NO_PDL=1 timeout 300 python tools/step_timeline.py 2 mri > gpurun_out/timeline_mri.log 2>&1; head -45 gpurun_out/timeline_mri.log | cut -c1-130

@@ -45,9 +45,20 @@ def main():
         opt._learning_rate.step()
         model.clear_gradients()
 
+    from medicalseg_b200 import _lib
+    if os.environ.get("MSB_NO_PDL"):
+        _lib.call("msb_debug_set", 7, 1)  # serialised kernels: per-kernel durations are not inflated by PDL waits
     for _ in range(5):
         step()
     torch.cuda.synchronize()
+    import time
+    t0 = time.perf_counter()
+    for _ in range(10):
+        step()
+    t_cpu = (time.perf_counter() - t0) / 10
+    torch.cuda.synchronize()
+    t_all = (time.perf_counter() - t0) / 10
+    print("host enqueue time %.3f ms/step (python + launches, no sync); wall %.3f ms/step" % (t_cpu * 1e3, t_all * 1e3))
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         for _ in range(steps):
