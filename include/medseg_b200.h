@@ -103,6 +103,27 @@ int msb_conv1x1_fwd(msb_tensor a, const float* w, const float* b, float* logits,
 int msb_conv1x1_bwd(msb_tensor a, const float* w, const float* dlogits, msb_tensor da, float* dw, float* db,
                     int n, int ci, int co, int64_t s, void* stream);
 
+/* ---- strided Conv3D / Conv3DTranspose without padding on tcgen05 tensor cores (general kernel / stride) ------
+ * vnet.py:98-99 (down_conv), :133-137 (up_conv) incl. the anisotropic MRISpineSeg kernels (2,2,4)/(2,2,1) and
+ * (2,2,2)/(2,2,1) whose windows overlap along the last axis.  mode 0 = gather (conv forward / transposed-conv input
+ * gradient; weight [c_out][c_red][kd*kh*kw]), mode 1 = scatter (transposed-conv forward / conv input gradient; weight
+ * [c_red][c_out][kd*kh*kw]; needs stride == kernel along d and h, and stride == kernel or stride == 1 along w).
+ * big_dims = extents of the LARGE grid; (big - kernel) % stride == 0 per axis.  MSB_ERR_UNSUPPORTED otherwise (callers
+ * fall back to msb_conv_strided_*).  msb_conv_tc_packed_bytes returns 0 for unsupported geometry. */
+size_t msb_conv_tc_packed_bytes(int c_red_pad, int c_out_pad, msb_dim3 kernel, msb_dim3 stride, int mode);
+int msb_conv_tc_pack(const float* w, void* packed, int c_red, int c_out, int mode, int c_red_pad, int c_out_pad,
+                     msb_dim3 kernel, msb_dim3 stride, void* stream);
+int msb_conv_tc_gather(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
+                       msb_dim3 big_dims, msb_dim3 kernel, msb_dim3 stride, int groups, double* sums, void* stream);
+int msb_conv_tc_scatter(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
+                        msb_dim3 big_dims, msb_dim3 kernel, msb_dim3 stride, int accumulate, int groups, double* sums,
+                        void* stream);
+/* dw [small.c][big.c][taps] f32 += weight gradient (both Conv3D [out][in][k] with big = input, and Conv3DTranspose
+ * [in][out][k] with big = output gradient); taps * big.c must be a multiple of 128, big.c in {16,32,64,128} */
+size_t msb_conv_tc_wgrad_workspace_bytes(int c_big, int c_small, msb_dim3 kernel);
+int msb_conv_tc_wgrad(msb_tensor big, msb_tensor small, float* dw, float* dbias, int n, msb_dim3 big_dims,
+                      msb_dim3 kernel, msb_dim3 stride, int bias_from_big, void* workspace, size_t workspace_bytes,
+                      void* stream);
 /* ---- direct (CUDA-core) Conv3D / Conv3DTranspose for the HBM-bound layers ---------------------------
  * vnet.py:67-68 (in_tr 1->16, k5), :98-99 (down_conv k=kernel,s=stride), :133-137 (up_conv, transposed).
  * Weights/grads stay in the reference (Paddle) layouts: conv [Cout,Cin,kD,kH,kW]; convT [Cin,Cout,kD,kH,kW]. */

@@ -43,6 +43,12 @@ SIGNATURES = {
     "msb_conv_strided_fwd": (I, [T, P, P, T, I, D3, D3, D3, D3, I, I, I, P, P]),
     "msb_conv_strided_bwd_data": (I, [T, P, P, T, I, D3, D3, D3, D3, I, I, I, I, P, P]),
     "msb_conv_strided_wgrad": (I, [T, T, P, P, I, D3, D3, D3, D3, I, I, I, P]),
+    "msb_conv_tc_packed_bytes": (SZ, [I, I, D3, D3, I]),
+    "msb_conv_tc_pack": (I, [P, P, I, I, I, I, I, D3, D3, P]),
+    "msb_conv_tc_gather": (I, [T, P, P, I, T, I, D3, D3, D3, I, P, P]),
+    "msb_conv_tc_scatter": (I, [T, P, P, I, T, I, D3, D3, D3, I, I, P, P]),
+    "msb_conv_tc_wgrad_workspace_bytes": (SZ, [I, I, D3]),
+    "msb_conv_tc_wgrad": (I, [T, T, P, P, I, D3, D3, D3, I, P, SZ, P]),
     "msb_conv_k2s2_wgrad_workspace_bytes": (SZ, [I, I, I, D3]),
     "msb_conv_k2s2_wgrad": (I, [T, T, P, P, I, D3, I, P, SZ, P]),
     "msb_conv_k2s2_packed_bytes": (SZ, [I, I]),
@@ -84,7 +90,8 @@ SIGNATURES = {
 }
 
 _NO_STATUS = {"msb_version", "msb_last_error_string", "msb_conv_k5_packed_bytes", "msb_conv_k5_out_pad",
-              "msb_conv_k2s2_wgrad_workspace_bytes", "msb_conv_k5_fwd_workspace_bytes",
+              "msb_conv_k2s2_wgrad_workspace_bytes", "msb_conv_k5_fwd_workspace_bytes", "msb_conv_tc_packed_bytes",
+              "msb_conv_tc_wgrad_workspace_bytes",
               "msb_conv_k5_wgrad_workspace_bytes", "msb_conv_k551_packed_bytes", "msb_conv_k2s2_packed_bytes",
               "msb_conv_k551_wgrad_workspace_bytes"}
 

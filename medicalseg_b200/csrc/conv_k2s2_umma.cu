@@ -1,5 +1,14 @@
-// 2x2x2 / stride-2 Conv3D and Conv3DTranspose (DownTransition.down_conv vnet.py:98-99, UpTransition.up_conv
-// vnet.py:133-137, and each other's input gradients) as pointwise GEMMs on tcgen05 tensor cores.
+// Strided Conv3D and Conv3DTranspose without padding (DownTransition.down_conv vnet.py:98-99, UpTransition.up_conv
+// vnet.py:133-137, and each other's input gradients) as pointwise GEMMs on tcgen05 tensor cores: the default
+// 2x2x2 / stride 2 and the anisotropic MRISpineSeg kernels (2,2,4)/(2,2,1), (2,2,2)/(2,2,1) whose windows overlap along
+// the last axis (vnet_mri_spine_seg_512_512_12_15k.yml:9-10).  General form (taps = kd*kh*kw, any strides):
+//   gather : out[v, co] = bias[co] + sum_{tap, cr} x[s*v + tap, cr] * w[co][cr][tap]; the strided 5-D TMA box uses
+//            elementStrides (s_w, s_h) and the start coordinate (s*v0 + tap).
+//   scatter: the d and h axes must have stride == kernel (disjoint windows: their taps go to N and the epilogue writes
+//            them depth-to-space); the w axis is either disjoint as well ("scatter-w", taps on N) or has stride 1
+//            ("gather-w": out[.., w'] = sum_kw x[.., w' - kw] W[kw] - the kw taps join the K loop as shifted boxes,
+//            zero-filled out of bounds, so overlapping windows need no atomics).
+// The text below describes the default 2x2x2 / stride-2 case.
 //
 // The windows do not overlap, so both directions are plain GEMMs over 128-voxel tiles (8 w x 16 h of one d-plane of
 // the SMALL grid) with bf16 operands and f32 accumulation in TMEM:
@@ -36,6 +45,11 @@ struct K2Params {
   int tg, tap_groups;    // scatter: taps per MMA and number of tap groups (tg * tap_groups = 8); gather: 1, 1
   int cout_real, out_c8;
   int sd, sh, sw;        // small-grid extents
+  int bd, bh, bw;        // big-grid extents
+  int kdn, khn, kwn;     // kernel extents
+  int std, sth, stw;     // strides
+  int wmode;             // scatter only: 0 = w taps on N (disjoint windows), 1 = w taps in the K loop (stride 1)
+  int ntap_n;            // scatter: taps carried on N (kd*kh[*kw])
   int tiles_w, tiles_h;
   int x_c8_total;        // planes per n in the TMA coordinate space of x
   const void* packed;
@@ -78,7 +92,8 @@ __global__ void __launch_bounds__(kK2Threads, 1)
 
   const int tiles_per_n = p.sd * p.tiles_h * p.tiles_w;
   const int num_items = p.n * tiles_per_n * p.tap_groups;
-  const int kiters = p.mode == 0 ? 8 * p.chunks : p.chunks;
+  const int ktaps = p.mode == 0 ? p.kdn * p.khn * p.kwn : (p.wmode == 1 ? p.kwn : 1);  // taps carried by the K loop
+  const int kiters = ktaps * p.chunks;
   const uint32_t b_bytes = (uint32_t)p.nmma * 32u;
 
   if (warp == 0) {
@@ -92,20 +107,21 @@ __global__ void __launch_bounds__(kK2Threads, 1)
       const int tw = r % p.tiles_w; r /= p.tiles_w;
       const int th = r % p.tiles_h; const int d = r / p.tiles_h;
       for (int ki = 0; ki < kiters; ++ki, ++use) {
-        const int tap = p.mode == 0 ? ki / p.chunks : 0;
-        const int ck = p.mode == 0 ? ki % p.chunks : ki;
+        const int tap = ki / p.chunks, ck = ki % p.chunks;
         const uint32_t s = use % kK2Stages, ph = (use / kK2Stages) & 1;
         ptx::mbar_wait(BAR(kEmpty + s), ph ^ 1);
         if (leader) {
           uint8_t* st = stage_smem + s * kK2StageBytes;
           ptx::mbar_expect_tx(BAR(kFull + s), kK2ABytes + b_bytes);
-          if (p.mode == 0)
-            ptx::tma_load_5d(ptx::smem_u32(st), &tmap_x, BAR(kFull + s), 0, 2 * tw * kK2TileW + (tap & 1),
-                             2 * th * kK2TileH + ((tap >> 1) & 1), 2 * d + (tap >> 2), n * p.x_c8_total + ck * 2);
-          else
-            ptx::tma_load_4d(ptx::smem_u32(st), &tmap_x, BAR(kFull + s), tw * kK2TileW * 8, th * kK2TileH, d,
-                             n * p.x_c8_total + ck * 2);
-          const int blk = (p.mode == 0 ? tap : tgp) * p.chunks + ck;
+          if (p.mode == 0) {
+            const int kw = tap % p.kwn, kh = (tap / p.kwn) % p.khn, kd = tap / (p.kwn * p.khn);
+            ptx::tma_load_5d(ptx::smem_u32(st), &tmap_x, BAR(kFull + s), 0, p.stw * tw * kK2TileW + kw,
+                             p.sth * th * kK2TileH + kh, p.std * d + kd, n * p.x_c8_total + ck * 2);
+          } else {  // gather-w: the tile runs over OUTPUT w', tap kw reads x[.., w' - kw] (zero outside the volume)
+            ptx::tma_load_4d(ptx::smem_u32(st), &tmap_x, BAR(kFull + s), (tw * kK2TileW - (p.wmode == 1 ? tap : 0)) * 8,
+                             th * kK2TileH, d, n * p.x_c8_total + ck * 2);
+          }
+          const int blk = (p.mode == 0 ? tap : tgp * ktaps + tap) * p.chunks + ck;
           ptx::bulk_load(ptx::smem_u32(st + kK2ABytes), reinterpret_cast<const uint8_t*>(p.packed) + (size_t)blk * b_bytes,
                          b_bytes, BAR(kFull + s));
         }
@@ -149,7 +165,7 @@ __global__ void __launch_bounds__(kK2Threads, 1)
     const int row = q * 32 + lane;
     const int hh = row >> 3, ww = row & 7;
     const int64_t Ss = (int64_t)p.sd * p.sh * p.sw;
-    const int64_t So = p.mode == 0 ? Ss : Ss * 8;  // voxels of the output grid
+    const int64_t So = p.mode == 0 ? Ss : (int64_t)p.bd * p.bh * p.bw;  // voxels of the output grid
     float* my_stats = stat_smem + (warp - 4) * 2 * 256;
     const int nblk16 = p.nmma / 16;
     const int t_start = (wg * 16) / p.cpad, co_start = (wg * 16) % p.cpad;
@@ -164,10 +180,12 @@ __global__ void __launch_bounds__(kK2Threads, 1)
       const int tw = r % p.tiles_w; r /= p.tiles_w;
       const int th = r % p.tiles_h; const int d = r / p.tiles_h;
       const int h = th * kK2TileH + hh, w = tw * kK2TileW + ww;
-      const bool ok = h < p.sh && w < p.sw;
+      // gather: (d, h, w) is an output voxel of the small grid; scatter: an input voxel (scatter-w) or, in gather-w
+      // mode, w already is the OUTPUT coordinate along w
+      const bool ok = h < p.sh && w < ((p.mode == 1 && p.wmode == 1) ? p.bw : p.sw);
       const uint32_t as = iuse & 1, aph = (iuse >> 1) & 1;
       const int64_t v_small = ((int64_t)d * p.sh + h) * p.sw + w;
-      const int64_t v_big0 = ((int64_t)(2 * d) * (2 * p.sh) + 2 * h) * (2 * p.sw) + 2 * w;  // tap (0,0,0) voxel
+      const int64_t v_big0 = ((int64_t)(p.std * d) * p.bh + p.sth * h) * p.bw + (p.wmode == 1 ? w : p.stw * w);
       __nv_bfloat16* out_n = reinterpret_cast<__nv_bfloat16*>(p.out.ptr) + (int64_t)n * p.out.n_stride;
       ptx::mbar_wait(BAR(kAccFull + as), aph);
       ptx::tc_fence_after();
@@ -178,9 +196,14 @@ __global__ void __launch_bounds__(kK2Threads, 1)
         float acc[16];
         ptx::tmem_ld16(t_base + cb * 16, acc);
         int64_t v = v_small;
+        bool tap_ok = true;
         if (p.mode != 0) {
-          const int tap = tgp * p.tg + t;
-          v = v_big0 + ((int64_t)(tap >> 2) * (2 * p.sh) + ((tap >> 1) & 1)) * (2 * p.sw) + (tap & 1);
+          const int tap = tgp * p.tg + t;  // N-side tap: (kd, kh[, kw]) row-major
+          tap_ok = tap < p.ntap_n;
+          const int kwl = p.wmode == 1 ? 0 : tap % p.kwn;
+          const int r2 = p.wmode == 1 ? tap : tap / p.kwn;
+          const int kh = r2 % p.khn, kd = r2 / p.khn;
+          v = v_big0 + ((int64_t)kd * p.bh + kh) * p.bw + kwl;
         }
         if (has_bias) {
           if (bias_vec && co0 + 16 <= p.cout_real) {
@@ -198,7 +221,7 @@ __global__ void __launch_bounds__(kK2Threads, 1)
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const int c8 = (co0 >> 3) + k;
-          const bool live = ok && c8 < p.out_c8;
+          const bool live = ok && tap_ok && c8 < p.out_c8;
           uint32_t pk[4] = {0u, 0u, 0u, 0u};
           if (live) {
             __nv_bfloat16* dst = out_n + ((int64_t)c8 * So + v) * 8;
@@ -268,55 +291,98 @@ __global__ void __launch_bounds__(kK2Threads, 1)
   }
 }
 
-// gather : packed[tap][chunk][k8][co < cpad][j]            = w[co][cr][tap]   (w = [c_out][c_red][8])
-// scatter: packed[tgp][chunk][k8][t*cpad + co][j]          = w[cr][co][tap]   (w = [c_red][c_out][8]), tap = tgp*tg + t
-// with cr = chunk*16 + k8*8 + j
+// gather : packed[tap][chunk][k8][co < cpad][j]                 = w[co][cr][tap]   (w = [c_out][c_red][taps])
+// scatter: packed[tgp][ktap][chunk][k8][t*cpad + co][j]         = w[cr][co][tap]   (w = [c_red][c_out][taps])
+//          tap = (N-side tap tgp*tg + t, K-side tap ktap) -> (kd, kh, kw); cr = chunk*16 + k8*8 + j
+struct K2Geom {
+  int kdn, khn, kwn;   // kernel
+  int wmode;           // scatter: 1 = kw taps in the K loop
+  int tg, tap_groups;  // scatter: taps per MMA / number of tap groups
+  int ntap_n, ktaps;   // scatter: taps on N in total / taps in the K loop
+};
+
 __global__ void __launch_bounds__(256) pack_k2s2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed,
-                                                        int c_red, int c_out, int mode, int c_red_pad, int cpad, int tg) {
+                                                        int c_red, int c_out, int mode, int c_red_pad, int cpad,
+                                                        K2Geom g) {
   pdl_wait();
   pdl_trigger();
   const int chunks = c_red_pad / 16;
-  const int64_t total = (int64_t)8 * c_red_pad * cpad;
+  const int taps = g.kdn * g.khn * g.kwn;
+  const int64_t total = mode == 0 ? (int64_t)taps * c_red_pad * cpad
+                                  : (int64_t)g.tap_groups * g.ktaps * c_red_pad * g.tg * cpad;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int j = (int)(i & 7);
     int64_t r = i >> 3;
     int tap, co, k8, ck;
+    bool tap_ok = true;
     if (mode == 0) {
       co = (int)(r % cpad); r /= cpad;
       k8 = (int)(r & 1); r >>= 1;
       ck = (int)(r % chunks); tap = (int)(r / chunks);
     } else {
-      const int nm = tg * cpad;
+      const int nm = g.tg * cpad;
       const int col = (int)(r % nm); r /= nm;
       k8 = (int)(r & 1); r >>= 1;
-      ck = (int)(r % chunks);
-      const int tgp = (int)(r / chunks);
-      tap = tgp * tg + col / cpad; co = col % cpad;
+      ck = (int)(r % chunks); r /= chunks;
+      const int ktap = (int)(r % g.ktaps);
+      const int tgp = (int)(r / g.ktaps);
+      const int ntap = tgp * g.tg + col / cpad;  // N-side tap: (kd, kh[, kw])
+      co = col % cpad;
+      tap_ok = ntap < g.ntap_n;
+      tap = g.wmode == 1 ? ntap * g.kwn + ktap : ntap;  // full tap index (kd*khn + kh)*kwn + kw
     }
     const int cr = ck * 16 + k8 * 8 + j;
     float v = 0.f;
-    if (cr < c_red && co < c_out)
-      v = mode == 0 ? __ldg(w + ((int64_t)co * c_red + cr) * 8 + tap) : __ldg(w + ((int64_t)cr * c_out + co) * 8 + tap);
+    if (tap_ok && cr < c_red && co < c_out)
+      v = mode == 0 ? __ldg(w + ((int64_t)co * c_red + cr) * taps + tap) : __ldg(w + ((int64_t)cr * c_out + co) * taps + tap);
     packed[i] = __float2bfloat16_rn(v);
   }
 }
 
 static inline int k2_pad16(int c) { return (c + 15) / 16 * 16; }
-static inline int k2_tg(int cpad) { int tg = 8; while (tg > 1 && tg * cpad > 256) tg >>= 1; return tg; }
+
+// scatter geometry for an output of cpad channels; returns false when the shape is not supported
+static bool k2_geom(int mode, msb_dim3 kernel, msb_dim3 stride, int cpad, K2Geom* g) {
+  g->kdn = kernel.d; g->khn = kernel.h; g->kwn = kernel.w;
+  g->wmode = 0; g->tg = 1; g->tap_groups = 1; g->ntap_n = 1; g->ktaps = kernel.d * kernel.h * kernel.w;
+  if (kernel.d < 1 || kernel.h < 1 || kernel.w < 1 || stride.d < 1 || stride.h < 1 || stride.w < 1) return false;
+  if (kernel.d * kernel.h * kernel.w > 64 || stride.w > 4 || stride.h > 4) return false;
+  if (mode == 0) return true;
+  if (kernel.d != stride.d || kernel.h != stride.h) return false;  // d / h windows must be disjoint
+  if (kernel.w == stride.w) g->wmode = 0;
+  else if (stride.w == 1) g->wmode = 1;
+  else return false;
+  g->ntap_n = kernel.d * kernel.h * (g->wmode == 1 ? 1 : kernel.w);
+  g->ktaps = g->wmode == 1 ? kernel.w : 1;
+  int tg = 1;
+  while (tg * 2 <= g->ntap_n && tg * 2 * cpad <= 256) tg *= 2;
+  g->tg = tg;
+  g->tap_groups = (g->ntap_n + tg - 1) / tg;
+  return true;
+}
 
 static int launch_k2s2(int mode, const msb_tensor& x, const void* packed, const float* bias, int cout,
-                       const msb_tensor& out, int n, msb_dim3 big, int accumulate, int groups, double* sums,
-                       cudaStream_t st) {
-  const msb_dim3 sd = {big.d / 2, big.h / 2, big.w / 2};
+                       const msb_tensor& out, int n, msb_dim3 big, msb_dim3 kernel, msb_dim3 stride, int accumulate,
+                       int groups, double* sums, cudaStream_t st) {
   K2Params p;
-  p.mode = mode; p.n = n; p.chunks = x.c / 16;
+  K2Geom g;
   p.cpad = k2_pad16(out.c);
-  p.tg = mode == 0 ? 1 : k2_tg(p.cpad);
-  p.tap_groups = mode == 0 ? 1 : 8 / p.tg;
+  if (!k2_geom(mode, kernel, stride, p.cpad, &g)) {
+    set_error("strided tensor-core conv: unsupported kernel / stride combination");
+    return MSB_ERR_UNSUPPORTED;
+  }
+  const msb_dim3 sd = {(big.d - kernel.d) / stride.d + 1, (big.h - kernel.h) / stride.h + 1,
+                       (big.w - kernel.w) / stride.w + 1};
+  p.mode = mode; p.n = n; p.chunks = x.c / 16;
+  p.tg = g.tg; p.tap_groups = g.tap_groups; p.ntap_n = g.ntap_n; p.wmode = g.wmode;
   p.nmma = mode == 0 ? p.cpad : p.tg * p.cpad;
   p.cout_real = cout; p.out_c8 = out.c / 8;
   p.sd = sd.d; p.sh = sd.h; p.sw = sd.w;
-  p.tiles_w = (sd.w + kK2TileW - 1) / kK2TileW;
+  p.bd = big.d; p.bh = big.h; p.bw = big.w;
+  p.kdn = kernel.d; p.khn = kernel.h; p.kwn = kernel.w;
+  p.std = stride.d; p.sth = stride.h; p.stw = stride.w;
+  const int tile_w_extent = (mode == 1 && p.wmode == 1) ? big.w : sd.w;
+  p.tiles_w = (tile_w_extent + kK2TileW - 1) / kK2TileW;
   p.tiles_h = (sd.h + kK2TileH - 1) / kK2TileH;
   p.packed = packed; p.bias = bias; p.out = out; p.accumulate = accumulate;
   p.groups = groups; p.sums = sums; p.sums_c = out.c;
@@ -325,7 +391,7 @@ static int launch_k2s2(int mode, const msb_tensor& x, const void* packed, const 
   if (mode == 0) {
     const int64_t Sb = (int64_t)big.d * big.h * big.w;
     p.x_c8_total = (int)(x.n_stride / (Sb * 8));
-    if ((rc = make_b8_tmap_s2(&tmap, x, n, big, kK2TileW, kK2TileH, 2))) return rc;
+    if ((rc = make_b8_tmap_s2(&tmap, x, n, big, kK2TileW, kK2TileH, 2, stride.w, stride.h))) return rc;
   } else {
     const int64_t Ss = (int64_t)sd.d * sd.h * sd.w;
     p.x_c8_total = (int)(x.n_stride / (Ss * 8));
@@ -348,45 +414,78 @@ using namespace msb;
 
 extern "C" {
 
+static const msb_dim3 kTwo = {2, 2, 2};
+
+size_t msb_conv_tc_packed_bytes(int c_red_pad, int c_out_pad, msb_dim3 kernel, msb_dim3 stride, int mode) {
+  K2Geom g;
+  if (!k2_geom(mode, kernel, stride, c_out_pad, &g)) return 0;
+  const size_t taps = (size_t)kernel.d * kernel.h * kernel.w;
+  if (mode == 0) return taps * c_red_pad * c_out_pad * sizeof(__nv_bfloat16);
+  return (size_t)g.tap_groups * g.ktaps * c_red_pad * g.tg * c_out_pad * sizeof(__nv_bfloat16);
+}
+
+int msb_conv_tc_pack(const float* w, void* packed, int c_red, int c_out, int mode, int c_red_pad, int c_out_pad,
+                     msb_dim3 kernel, msb_dim3 stride, void* stream) {
+  MSB_REQUIRE(w && packed && c_red > 0 && c_out > 0 && (mode == 0 || mode == 1), "msb_conv_tc_pack: bad arguments");
+  MSB_REQUIRE(c_red_pad % 16 == 0 && c_out_pad % 16 == 0 && c_red_pad >= c_red && c_out_pad >= c_out && c_out_pad <= 256,
+              "msb_conv_tc_pack: padded channel counts must be multiples of 16 covering the real ones (out <= 256)");
+  K2Geom g;
+  MSB_REQUIRE(k2_geom(mode, kernel, stride, c_out_pad, &g), "msb_conv_tc_pack: unsupported kernel / stride combination");
+  const int64_t total = (int64_t)(msb_conv_tc_packed_bytes(c_red_pad, c_out_pad, kernel, stride, mode) / 2);
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  MSB_LAUNCH_PDL(pack_k2s2_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), w,
+                 reinterpret_cast<__nv_bfloat16*>(packed), c_red, c_out, mode, c_red_pad, c_out_pad, g);
+  return MSB_OK;
+}
+
+static int k2s2_check(const char* who, const msb_tensor& x, const msb_tensor& out, const void* packed, int cout, int n,
+                      msb_dim3 big, msb_dim3 kernel, msb_dim3 stride, int groups) {
+  MSB_REQUIRE(view_ok(x) && view_ok(out) && x.dtype == MSB_BF16 && out.dtype == MSB_BF16 && packed && n > 0,
+              "%s: bf16 B8 views required", who);
+  MSB_REQUIRE(big.d >= kernel.d && big.h >= kernel.h && big.w >= kernel.w && kernel.d > 0 && stride.d > 0,
+              "%s: the large grid must be at least one window in every direction", who);
+  MSB_REQUIRE((big.d - kernel.d) % stride.d == 0 && (big.h - kernel.h) % stride.h == 0 && (big.w - kernel.w) % stride.w == 0,
+              "%s: (big - kernel) must be a multiple of the stride in every direction (the transposed conv's output "
+              "extent (small-1)*stride+kernel)", who);
+  MSB_REQUIRE(x.c % 16 == 0 && out.c <= 256 && cout > 0 && cout <= out.c, "%s: x.c must be a multiple of 16, out.c <= 256", who);
+  MSB_REQUIRE(groups == 1 || groups == n, "%s: groups must be 1 or n", who);
+  return MSB_OK;
+}
+
+int msb_conv_tc_gather(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
+                       msb_dim3 big_dims, msb_dim3 kernel, msb_dim3 stride, int groups, double* sums, void* stream) {
+  int rc = k2s2_check("msb_conv_tc_gather", x, out, packed, cout, n, big_dims, kernel, stride, groups);
+  if (rc) return rc;
+  return launch_k2s2(0, x, packed, bias, cout, out, n, big_dims, kernel, stride, 0, groups, sums, as_stream(stream));
+}
+
+int msb_conv_tc_scatter(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
+                        msb_dim3 big_dims, msb_dim3 kernel, msb_dim3 stride, int accumulate, int groups, double* sums,
+                        void* stream) {
+  int rc = k2s2_check("msb_conv_tc_scatter", x, out, packed, cout, n, big_dims, kernel, stride, groups);
+  if (rc) return rc;
+  return launch_k2s2(1, x, packed, bias, cout, out, n, big_dims, kernel, stride, accumulate, groups, sums,
+                     as_stream(stream));
+}
+
+// ---- the 2x2x2 / stride-2 entry points (kept: thin wrappers) ------------------------------------------------
 size_t msb_conv_k2s2_packed_bytes(int c_red_pad, int c_out_pad) {
   return (size_t)8 * c_red_pad * c_out_pad * sizeof(__nv_bfloat16);
 }
 
 int msb_conv_k2s2_pack(const float* w, void* packed, int c_red, int c_out, int mode, int c_red_pad, int c_out_pad,
                        void* stream) {
-  MSB_REQUIRE(w && packed && c_red > 0 && c_out > 0 && (mode == 0 || mode == 1), "msb_conv_k2s2_pack: bad arguments");
-  MSB_REQUIRE(c_red_pad % 16 == 0 && c_out_pad % 16 == 0 && c_red_pad >= c_red && c_out_pad >= c_out && c_out_pad <= 256,
-              "msb_conv_k2s2_pack: padded channel counts must be multiples of 16 covering the real ones (out <= 256)");
-  const int64_t total = (int64_t)8 * c_red_pad * c_out_pad;
-  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  MSB_LAUNCH_PDL(pack_k2s2_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), w,
-                 reinterpret_cast<__nv_bfloat16*>(packed), c_red, c_out, mode, c_red_pad, c_out_pad, k2_tg(c_out_pad));
-  return MSB_OK;
-}
-
-static int k2s2_check(const char* who, const msb_tensor& x, const msb_tensor& out, const void* packed, int cout, int n,
-                      msb_dim3 big, int groups) {
-  MSB_REQUIRE(view_ok(x) && view_ok(out) && x.dtype == MSB_BF16 && out.dtype == MSB_BF16 && packed && n > 0,
-              "%s: bf16 B8 views required", who);
-  MSB_REQUIRE(big.d > 0 && big.h > 0 && big.w > 0 && big.d % 2 == 0 && big.h % 2 == 0 && big.w % 2 == 0,
-              "%s: the large grid must have even extents", who);
-  MSB_REQUIRE(x.c % 16 == 0 && out.c <= 256 && cout > 0 && cout <= out.c, "%s: x.c must be a multiple of 16, out.c <= 256", who);
-  MSB_REQUIRE(groups == 1 || groups == n, "%s: groups must be 1 or n", who);
-  return MSB_OK;
+  return msb_conv_tc_pack(w, packed, c_red, c_out, mode, c_red_pad, c_out_pad, kTwo, kTwo, stream);
 }
 
 int msb_conv_k2s2_gather(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
                          msb_dim3 big_dims, int groups, double* sums, void* stream) {
-  int rc = k2s2_check("msb_conv_k2s2_gather", x, out, packed, cout, n, big_dims, groups);
-  if (rc) return rc;
-  return launch_k2s2(0, x, packed, bias, cout, out, n, big_dims, 0, groups, sums, as_stream(stream));
+  return msb_conv_tc_gather(x, packed, bias, cout, out, n, big_dims, kTwo, kTwo, groups, sums, stream);
 }
 
 int msb_conv_k2s2_scatter(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
                           msb_dim3 big_dims, int accumulate, int groups, double* sums, void* stream) {
-  int rc = k2s2_check("msb_conv_k2s2_scatter", x, out, packed, cout, n, big_dims, groups);
-  if (rc) return rc;
-  return launch_k2s2(1, x, packed, bias, cout, out, n, big_dims, accumulate, groups, sums, as_stream(stream));
+  return msb_conv_tc_scatter(x, packed, bias, cout, out, n, big_dims, kTwo, kTwo, accumulate, groups, sums, stream);
 }
 
 }  // extern "C"

@@ -17,8 +17,9 @@ int make_b8_tmap(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 dims, in
 int make_b8_tmap_hmajor(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 dims, int box_w, int box_p, int box_h,
                         int box_d);
 
-// stride-2 sub-lattice map (5-D, elementStrides 2 along w and h): shared-memory image [plane][box_h][box_w][8]
-int make_b8_tmap_s2(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 dims, int box_w, int box_h, int box_p);
+// strided sub-lattice map (5-D, elementStrides sw / sh along w / h): shared-memory image [plane][box_h][box_w][8]
+int make_b8_tmap_s2(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 dims, int box_w, int box_h, int box_p,
+                    int sw = 2, int sh = 2);
 
 // kh-stacked weight-gradient kernel (conv_k5_wgrad2.cu); returns MSB_ERR_UNSUPPORTED when not applicable
 // kw_taps: 5 = 5x5x5 kernel (ws [125][cout][cin]); 1 = 5x5x1 kernel of the w-folded convs (ws [25][cout][cin])

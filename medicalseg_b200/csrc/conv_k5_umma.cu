@@ -516,9 +516,11 @@ struct WgParams {
   float* ws;                            // [125][cout_real][cin_real] f32
   int dbg_swap;
   int pad, units_total;                 // 2 / 25 for the 5x5x5 conv; 0 / 1 for the pointwise (1x1x1) weight gradient
-  int s2_c8n;                           // > 0: x is the BIG grid of a 2x2x2/stride-2 conv (s2_c8n = its planes); the
-                                        // M rows are (tap, channel) and every tap's sub-lattice is fetched by a
-                                        // stride-2 5-D TMA box (tmap_x built by make_b8_tmap_s2) - no space-to-depth copy
+  int s2_c8n;                           // > 0: x is the BIG grid of a strided conv (s2_c8n = its planes); the M rows
+                                        // are (tap, channel) and every tap's sub-lattice is fetched by a strided 5-D
+                                        // TMA box (tmap_x built by make_b8_tmap_s2) - no space-to-depth copy
+  int s2_khn, s2_kwn;                   // kernel extents along h, w (tap = (kd*khn + kh)*kwn + kw)
+  int s2_sd, s2_sh, s2_sw;              // strides
 };
 
 template <int NPAD, int TH>
@@ -586,8 +588,9 @@ __global__ void __launch_bounds__(256, 1)
             for (int i = 0; i < 16 / per_tap; ++i) {
               const int plane0 = mh * 16 + i * per_tap;
               const int tap = plane0 / p.s2_c8n, c8 = plane0 % p.s2_c8n;
+              const int kw = tap % p.s2_kwn, kh = (tap / p.s2_kwn) % p.s2_khn, kd = tap / (p.s2_kwn * p.s2_khn);
               ptx::tma_load_5d(ptx::smem_u32(x_smem + b * Cfg::kXBytes + i * per_tap * Cfg::kGroupBytes), &tmap_x, BAR(b),
-                               0, 2 * tw * kWgTileW + (tap & 1), 2 * th * TH + ((tap >> 1) & 1), 2 * d + (tap >> 2),
+                               0, p.s2_sw * tw * kWgTileW + kw, p.s2_sh * th * TH + kh, p.s2_sd * d + kd,
                                n * p.x_c8_total + c8);
             }
           } else
@@ -735,15 +738,16 @@ __global__ void __launch_bounds__(256) channel_sum_bf16_kernel(msb_tensor x, int
 // (WgParams::s2_c8n), so no space-to-depth copy is materialised.
 // dw[sc][bc][tap] += ws[sc][tap*cbig + bc]
 __global__ void __launch_bounds__(256) k2s2_unpack_kernel(const float* __restrict__ ws, float* __restrict__ dw,
-                                                          int csmall, int cbig) {
+                                                          int csmall, int cbig, int taps, int cbig_real) {
   pdl_wait();
   pdl_trigger();
-  const int64_t total = (int64_t)csmall * cbig * 8;
+  // dw is [csmall_real][cbig_real][taps] or [cbig_real][csmall_real][taps] - the caller passes the matching strides
+  const int64_t total = (int64_t)csmall * cbig_real * taps;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int tap = (int)(i & 7);
-    const int64_t r = i >> 3;
-    const int bc = (int)(r % cbig), sc = (int)(r / cbig);
-    dw[i] += ws[((int64_t)sc * 8 + tap) * cbig + bc];
+    const int tap = (int)(i % taps);
+    const int64_t r = i / taps;
+    const int bc = (int)(r % cbig_real), sc = (int)(r / cbig_real);
+    dw[i] += ws[((int64_t)sc * taps + tap) * cbig + bc];
   }
 }
 
@@ -916,10 +920,11 @@ int make_b8_tmap_hmajor(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 d
   return MSB_OK;
 }
 
-// 5-D map over a B8 bf16 view that samples every SECOND voxel along w and h (elementStrides 2): dims (8, W, H, D,
-// planes), box (8, 2*box_w, 2*box_h, 1, box_p) -> shared-memory image [plane][box_h][box_w][8].  The start coordinate
-// selects the (kd, kh, kw) sub-lattice of a 2x2x2 / stride-2 window.
-int make_b8_tmap_s2(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 dims, int box_w, int box_h, int box_p) {
+// 5-D map over a B8 bf16 view that samples every sw-th / sh-th voxel along w / h (elementStrides): dims (8, W, H, D,
+// planes), box (8, sw*box_w, sh*box_h, 1, box_p) -> shared-memory image [plane][box_h][box_w][8].  The start coordinate
+// selects the (kd, kh, kw) sub-lattice of a strided conv window (stride 1 = plain shifted box).
+int make_b8_tmap_s2(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 dims, int box_w, int box_h, int box_p,
+                    int sw, int sh) {
   EncodeTiledFn enc = get_encode_fn();
   if (enc == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -930,17 +935,21 @@ int make_b8_tmap_s2(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 dims,
     set_error("tensor view: n_stride must be a multiple of D*H*W*8");
     return MSB_ERR_INVALID;
   }
+  if (sw * box_w > 256 || sh * box_h > 256) {
+    set_error("strided tensor map: box exceeds 256 elements per dimension");
+    return MSB_ERR_UNSUPPORTED;
+  }
   const int64_t planes_total = t.n_stride / (S * 8);
   const cuuint64_t gdim[5] = {8, (cuuint64_t)dims.w, (cuuint64_t)dims.h, (cuuint64_t)dims.d,
                               (cuuint64_t)((n - 1) * planes_total + t.c / 8)};
   const cuuint64_t gstr[4] = {16, (cuuint64_t)dims.w * 16, (cuuint64_t)dims.h * dims.w * 16, (cuuint64_t)S * 16};
-  const cuuint32_t box[5] = {8, (cuuint32_t)(2 * box_w), (cuuint32_t)(2 * box_h), 1, (cuuint32_t)box_p};
-  const cuuint32_t estr[5] = {1, 2, 2, 1, 1};
+  const cuuint32_t box[5] = {8, (cuuint32_t)(sw * box_w), (cuuint32_t)(sh * box_h), 1, (cuuint32_t)box_p};
+  const cuuint32_t estr[5] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, t.ptr, gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled (stride-2) failed with CUresult %d", (int)r);
+    set_error("cuTensorMapEncodeTiled (strided) failed with CUresult %d", (int)r);
     return MSB_ERR_CUDA;
   }
   return MSB_OK;
@@ -1027,7 +1036,8 @@ static int splitk_slices(int npad, int n, msb_dim3 dims, int cin_pad) {
 static inline int pad16(int c) { return (c + 15) / 16 * 16; }
 
 template <int NPAD, int TH>
-static int launch_wgrad(const msb_tensor& x, const msb_tensor& dy, WgParams& p, msb_dim3 dims, cudaStream_t st) {
+static int launch_wgrad(const msb_tensor& x, const msb_tensor& dy, WgParams& p, msb_dim3 dims, cudaStream_t st,
+                        msb_dim3 p_big_dims = msb_dim3{0, 0, 0}) {
   using Cfg = WgCfg<NPAD, TH>;
   p.tiles_w = (dims.w + kWgTileW - 1) / kWgTileW;
   p.tiles_h = (dims.h + TH - 1) / TH;
@@ -1044,9 +1054,10 @@ static int launch_wgrad(const msb_tensor& x, const msb_tensor& dy, WgParams& p, 
   p.chunks = (p.total_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
   CUtensorMap tmx, tmdy;
   int rc;
-  if (p.s2_c8n > 0) {  // x = big grid (extents 2 * dims), sampled on the tap sub-lattices
-    const msb_dim3 big = {2 * dims.d, 2 * dims.h, 2 * dims.w};
-    if ((rc = make_b8_tmap_s2(&tmx, x, p.n, big, kWgTileW + 4, TH + 4, p.s2_c8n < 16 ? p.s2_c8n : 16))) return rc;
+  if (p.s2_c8n > 0) {  // x = big grid, sampled on the tap sub-lattices
+    if ((rc = make_b8_tmap_s2(&tmx, x, p.n, p_big_dims, kWgTileW + 4, TH + 4, p.s2_c8n < 16 ? p.s2_c8n : 16, p.s2_sw,
+                              p.s2_sh)))
+      return rc;
   } else if ((rc = make_b8_tmap(&tmx, x, p.n, dims, kWgTileW + 4, TH + 4, 1, p.cin_m / 8))) return rc;
   if ((rc = make_b8_tmap(&tmdy, dy, p.n, dims, kWgTileW, TH, 1, dy.c / 8))) return rc;
   const int items = p.num_passes * p.chunks;
@@ -1207,7 +1218,7 @@ int msb_conv_k5_wgrad(msb_tensor x, msb_tensor dy, float* dw, float* dbias, int 
   p.kd_groups = (5 + qeff - 1) / qeff;
   p.ws = reinterpret_cast<float*>(workspace);
   p.dbg_swap = g_debug_flags[1];
-  p.pad = 2; p.units_total = 25; p.s2_c8n = 0;
+  p.pad = 2; p.units_total = 25; p.s2_c8n = 0; p.s2_khn = p.s2_kwn = p.s2_sd = p.s2_sh = p.s2_sw = 1;
   const int npad = msb_conv_k5_out_pad(dy.c);
   int rc = MSB_ERR_UNSUPPORTED;
   if (g_debug_flags[2] == 0) rc = launch_wgrad_v2(x, dy, cout, cin, n, dims, p.ws, st);
@@ -1288,29 +1299,33 @@ int msb_channel_sum(msb_tensor x, int c_real, int n, int64_t s, float* out, void
   return MSB_OK;
 }
 
-size_t msb_conv_k2s2_wgrad_workspace_bytes(int n, int c_big, int c_small, msb_dim3 big_dims) {
-  (void)n; (void)big_dims;
-  return (size_t)c_small * 8 * c_big * sizeof(float);
+size_t msb_conv_tc_wgrad_workspace_bytes(int c_big, int c_small, msb_dim3 kernel) {
+  return (size_t)c_small * kernel.d * kernel.h * kernel.w * c_big * sizeof(float);
 }
 
-int msb_conv_k2s2_wgrad(msb_tensor big, msb_tensor small, float* dw, float* dbias, int n, msb_dim3 big_dims,
-                        int bias_from_big, void* workspace, size_t workspace_bytes, void* stream) {
+int msb_conv_tc_wgrad(msb_tensor big, msb_tensor small, float* dw, float* dbias, int n, msb_dim3 big_dims,
+                      msb_dim3 kernel, msb_dim3 stride, int bias_from_big, void* workspace, size_t workspace_bytes,
+                      void* stream) {
   MSB_REQUIRE(view_ok(big) && view_ok(small) && big.dtype == MSB_BF16 && small.dtype == MSB_BF16 && dw && n > 0,
-              "msb_conv_k2s2_wgrad: bf16 B8 views required");
-  MSB_REQUIRE(big_dims.d > 0 && big_dims.h > 0 && big_dims.w > 0 && big_dims.d % 2 == 0 && big_dims.h % 2 == 0 &&
-                  big_dims.w % 2 == 0,
-              "msb_conv_k2s2_wgrad: the large grid must have even extents");
-  MSB_REQUIRE(big.c == 16 || big.c == 32 || big.c == 64 || big.c == 128, "msb_conv_k2s2_wgrad: big.c in {16,32,64,128}");
-  MSB_REQUIRE(small.c % 16 == 0 && small.c <= 256, "msb_conv_k2s2_wgrad: small.c must be a multiple of 16 (<= 256)");
-  const size_t need = msb_conv_k2s2_wgrad_workspace_bytes(n, big.c, small.c, big_dims);
-  MSB_REQUIRE(workspace && workspace_bytes >= need, "msb_conv_k2s2_wgrad: workspace too small (%zu < %zu)",
+              "msb_conv_tc_wgrad: bf16 B8 views required");
+  MSB_REQUIRE(kernel.d > 0 && kernel.h > 0 && kernel.w > 0 && stride.d > 0 && stride.h > 0 && stride.w > 0 &&
+                  stride.w <= 4 && stride.h <= 4 && big_dims.d >= kernel.d && big_dims.h >= kernel.h &&
+                  big_dims.w >= kernel.w,
+              "msb_conv_tc_wgrad: bad kernel / stride / dims");
+  const int taps = kernel.d * kernel.h * kernel.w;
+  MSB_REQUIRE(big.c == 16 || big.c == 32 || big.c == 64 || big.c == 128, "msb_conv_tc_wgrad: big.c in {16,32,64,128}");
+  MSB_REQUIRE((taps * big.c) % 128 == 0, "msb_conv_tc_wgrad: taps * big.c must be a multiple of 128");
+  MSB_REQUIRE(small.c % 16 == 0 && small.c <= 256, "msb_conv_tc_wgrad: small.c must be a multiple of 16 (<= 256)");
+  const size_t need = msb_conv_tc_wgrad_workspace_bytes(big.c, small.c, kernel);
+  MSB_REQUIRE(workspace && workspace_bytes >= need, "msb_conv_tc_wgrad: workspace too small (%zu < %zu)",
               workspace_bytes, need);
   cudaStream_t st = as_stream(stream);
-  const msb_dim3 sd = {big_dims.d / 2, big_dims.h / 2, big_dims.w / 2};
-  const int64_t Ss = (int64_t)sd.d * sd.h * sd.w, Sb = Ss * 8;
-  const int cxs = 8 * big.c;  // M rows = (tap, big channel): a pointwise weight gradient over the 8 tap sub-lattices
+  const msb_dim3 sd = {(big_dims.d - kernel.d) / stride.d + 1, (big_dims.h - kernel.h) / stride.h + 1,
+                       (big_dims.w - kernel.w) / stride.w + 1};
+  const int64_t Ss = (int64_t)sd.d * sd.h * sd.w, Sb = (int64_t)big_dims.d * big_dims.h * big_dims.w;
+  const int cxs = taps * big.c;  // M rows = (tap, big channel): a pointwise weight gradient over the tap sub-lattices
   float* ws = reinterpret_cast<float*>(workspace);
-  MSB_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)small.c * cxs * sizeof(float), st));
+  MSB_CUDA_OK(cudaMemsetAsync(ws, 0, need, st));
   WgParams p;
   p.n = n; p.cin_pad = cxs; p.cin_real = cxs; p.cout_real = small.c; p.dy_c8 = small.c / 8;
   p.d = sd.d; p.h = sd.h; p.w = sd.w;
@@ -1318,20 +1333,20 @@ int msb_conv_k2s2_wgrad(msb_tensor big, msb_tensor small, float* dw, float* dbia
   p.dy_c8_total = (int)(small.n_stride / (Ss * 8));
   p.cin_m = 128; p.mhalves = cxs / 128; p.qm = 1; p.kd_groups = 1;
   p.ws = ws; p.dbg_swap = 0; p.pad = 0; p.units_total = 1; p.s2_c8n = big.c / 8;
-  const msb_tensor& xst = big;
+  p.s2_khn = kernel.h; p.s2_kwn = kernel.w; p.s2_sd = stride.d; p.s2_sh = stride.h; p.s2_sw = stride.w;
   int rc;
   switch (msb_conv_k5_out_pad(small.c)) {
-    case 16: rc = launch_wgrad<16, 8>(xst, small, p, sd, st); break;
-    case 32: rc = launch_wgrad<32, 8>(xst, small, p, sd, st); break;
-    case 64: rc = launch_wgrad<64, 8>(xst, small, p, sd, st); break;
-    case 128: rc = launch_wgrad<128, 8>(xst, small, p, sd, st); break;
-    default: rc = launch_wgrad<256, 4>(xst, small, p, sd, st); break;
+    case 16: rc = launch_wgrad<16, 8>(big, small, p, sd, st, big_dims); break;
+    case 32: rc = launch_wgrad<32, 8>(big, small, p, sd, st, big_dims); break;
+    case 64: rc = launch_wgrad<64, 8>(big, small, p, sd, st, big_dims); break;
+    case 128: rc = launch_wgrad<128, 8>(big, small, p, sd, st, big_dims); break;
+    default: rc = launch_wgrad<256, 4>(big, small, p, sd, st, big_dims); break;
   }
   if (rc) return rc;
   {
-    const int64_t total = (int64_t)small.c * big.c * 8;
+    const int64_t total = (int64_t)small.c * big.c * taps;
     const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-    MSB_LAUNCH_PDL(k2s2_unpack_kernel, dim3(blocks), dim3(256), 0, st, ws, dw, small.c, big.c);
+    MSB_LAUNCH_PDL(k2s2_unpack_kernel, dim3(blocks), dim3(256), 0, st, ws, dw, small.c, big.c, taps, big.c);
   }
   if (dbias != nullptr) {
     const msb_tensor& bt = bias_from_big ? big : small;
@@ -1340,6 +1355,19 @@ int msb_conv_k2s2_wgrad(msb_tensor big, msb_tensor small, float* dw, float* dbia
     MSB_LAUNCH_PDL(channel_sum_bf16_kernel, grid, dim3(256), 0, st, bt, sbt, bt.c, dbias);
   }
   return MSB_OK;
+}
+
+size_t msb_conv_k2s2_wgrad_workspace_bytes(int n, int c_big, int c_small, msb_dim3 big_dims) {
+  (void)n; (void)big_dims;
+  return msb_conv_tc_wgrad_workspace_bytes(c_big, c_small, msb_dim3{2, 2, 2});
+}
+
+int msb_conv_k2s2_wgrad(msb_tensor big, msb_tensor small, float* dw, float* dbias, int n, msb_dim3 big_dims,
+                        int bias_from_big, void* workspace, size_t workspace_bytes, void* stream) {
+  MSB_REQUIRE(big_dims.d % 2 == 0 && big_dims.h % 2 == 0 && big_dims.w % 2 == 0,
+              "msb_conv_k2s2_wgrad: the large grid must have even extents");
+  return msb_conv_tc_wgrad(big, small, dw, dbias, n, big_dims, msb_dim3{2, 2, 2}, msb_dim3{2, 2, 2}, bias_from_big,
+                           workspace, workspace_bytes, stream);
 }
 
 int msb_conv_k5_out_pad(int cout_view) {

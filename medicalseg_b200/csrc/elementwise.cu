@@ -475,87 +475,100 @@ __global__ void __launch_bounds__(kThreads) conv1x1_fwd_kernel(msb_tensor a, con
   }
 }
 
-constexpr int kHeadTile = 128;  // voxels staged per inner step of the backward kernel
+constexpr int kHeadTile = 128;     // voxels staged per inner step of the backward kernel
+constexpr int kHeadThreads = 512;  // threads 0..127: one voxel each (da); all threads: one (o, i) weight pair each
 
+// dlogits -> da (B8) and dW / db.  Phase 1: threads < 128 load one voxel, write da and stage (a, dlogits) in shared
+// memory.  Phase 2: thread t < co*ci + co owns ONE weight (or bias) gradient and runs over the 128 staged voxels with
+// broadcast shared-memory reads - no shuffles, no per-pair warp reductions (the C = 20 MRI head has 420 pairs).
 template <typename T, int CI8>
-__global__ void __launch_bounds__(kHeadTile)
+__global__ void __launch_bounds__(kHeadThreads)
     conv1x1_bwd_kernel(msb_tensor a, const float* __restrict__ w, const float* __restrict__ dlogits, msb_tensor da,
                        float* __restrict__ dw, float* __restrict__ db, int ci, int co, int64_t s) {
   pdl_wait();
   pdl_trigger();
-  // smem: W, staged a [ci][tile+1], staged dl [co][tile+1], per-pair accumulators
-  __shared__ float ws[kHeadMaxC * kHeadMaxC];
+  __shared__ __align__(16) float ws[kHeadMaxC][CI8 * 8];  // W[o][i], rows zero-padded to the plane width
   __shared__ float as[CI8 * 8][kHeadTile + 1];
-  __shared__ float ds[CI8 * 8][kHeadTile + 1];
-  __shared__ float accw[kHeadMaxC * kHeadMaxC + kHeadMaxC];
-  for (int i = threadIdx.x; i < co * ci; i += kHeadTile) ws[i] = w[i];
-  for (int i = threadIdx.x; i < kHeadMaxC * kHeadMaxC + kHeadMaxC; i += kHeadTile) accw[i] = 0.f;
-  __syncthreads();
+  __shared__ float ds[kHeadMaxC][kHeadTile + 1];
+  for (int i = threadIdx.x; i < kHeadMaxC * CI8 * 8; i += kHeadThreads) {
+    const int o = i / (CI8 * 8), c = i % (CI8 * 8);
+    ws[o][c] = (o < co && c < ci) ? w[o * ci + c] : 0.f;
+  }
   const int n = blockIdx.z;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock;
-  const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
   const int npairs = co * ci + co;  // last `co` pseudo-pairs accumulate the bias gradient
-  for (int64_t base = v0; base < v1; base += kHeadTile) {
-    const int64_t v = base + threadIdx.x;
-    const bool valid = v < v1;
-    float x[CI8 * 8], g[CI8 * 8];
+  // pairs beyond 512 threads (co*ci + co <= 32*32 + 32) are strided over
+  constexpr int kSlots = (kHeadMaxC * kHeadMaxC + kHeadMaxC + kHeadThreads - 1) / kHeadThreads;
+  float accp[kSlots];
 #pragma unroll
-    for (int i = 0; i < CI8 * 8; ++i) x[i] = g[i] = 0.f;
-    if (valid) {
+  for (int k = 0; k < kSlots; ++k) accp[k] = 0.f;
+  __syncthreads();
+  // grid-stride over 128-voxel tiles: the launch uses a few blocks per SM, so the final atomics (all blocks hit the
+  // same <= 1056 addresses - a few cache lines) stay in the low hundreds per address
+  for (int64_t base = (int64_t)blockIdx.x * kHeadTile; base < s; base += (int64_t)gridDim.x * kHeadTile) {
+    if (threadIdx.x < kHeadTile) {
+      const int64_t v = base + threadIdx.x;
+      const bool valid = v < s;
 #pragma unroll
       for (int k = 0; k < CI8; ++k) {
         float t[8];
-        Vec8<T>::load(view_ptr<T>(a, n, k, s, v), t);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[k * 8 + j] = t[j];
+        for (int j = 0; j < 8; ++j) t[j] = 0.f;
+        if (valid) Vec8<T>::load(view_ptr<T>(a, n, k, s, v), t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) as[k * 8 + j][threadIdx.x] = t[j];
       }
+      // da[i] = sum_o W[o][i] * g[o]: runtime loop over the classes, the da accumulators stay in registers
+      float dacc[CI8 * 8];
 #pragma unroll
-      for (int o = 0; o < CI8 * 8; ++o)
-        if (o < co) g[o] = __ldg(dlogits + ((int64_t)n * co + o) * s + v);
-    }
+      for (int i = 0; i < CI8 * 8; ++i) dacc[i] = 0.f;
+      for (int o = 0; o < co; ++o) {
+        const float go = valid ? __ldg(dlogits + ((int64_t)n * co + o) * s + v) : 0.f;
+        ds[o][threadIdx.x] = go;
 #pragma unroll
-    for (int i = 0; i < CI8 * 8; ++i) {
-      as[i][threadIdx.x] = x[i];
-      ds[i][threadIdx.x] = g[i];
-    }
-    if (valid) {
-      // da[i] = sum_o W[o][i] * g[o]
-#pragma unroll
-      for (int k = 0; k < CI8; ++k) {
-        float t[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int i = k * 8 + j;
-          float acc = 0.f;
-          if (i < ci) {
-#pragma unroll
-            for (int o = 0; o < CI8 * 8; ++o)
-              if (o < co) acc = fmaf(ws[o * ci + i], g[o], acc);
-          }
-          t[j] = acc;
+        for (int i4 = 0; i4 < CI8 * 2; ++i4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(&ws[o][i4 * 4]);  // broadcast read
+          dacc[i4 * 4 + 0] = fmaf(w4.x, go, dacc[i4 * 4 + 0]);
+          dacc[i4 * 4 + 1] = fmaf(w4.y, go, dacc[i4 * 4 + 1]);
+          dacc[i4 * 4 + 2] = fmaf(w4.z, go, dacc[i4 * 4 + 2]);
+          dacc[i4 * 4 + 3] = fmaf(w4.w, go, dacc[i4 * 4 + 3]);
         }
-        Vec8<T>::store(view_ptr<T>(da, n, k, s, v), t);
+      }
+      if (valid) {
+#pragma unroll
+        for (int k = 0; k < CI8; ++k) {
+          float t[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[j] = dacc[k * 8 + j];
+          Vec8<T>::store(view_ptr<T>(da, n, k, s, v), t);
+        }
       }
     }
     __syncthreads();
-    for (int pidx = warp; pidx < npairs; pidx += kHeadTile / 32) {
+#pragma unroll
+    for (int slot = 0; slot < kSlots; ++slot) {
+      const int pidx = threadIdx.x + slot * kHeadThreads;
+      if (pidx >= npairs) continue;
       float acc = 0.f;
       if (pidx < co * ci) {
-        const int o = pidx / ci, i = pidx % ci;
-        for (int t = lane; t < kHeadTile; t += 32) acc = fmaf(as[i][t], ds[o][t], acc);
+        const float* ar = as[pidx % ci];
+        const float* dr = ds[pidx / ci];
+#pragma unroll 8
+        for (int t = 0; t < kHeadTile; ++t) acc = fmaf(ar[t], dr[t], acc);
       } else {
-        const int o = pidx - co * ci;
-        for (int t = lane; t < kHeadTile; t += 32) acc += ds[o][t];
+        const float* dr = ds[pidx - co * ci];
+#pragma unroll 8
+        for (int t = 0; t < kHeadTile; ++t) acc += dr[t];
       }
-      acc = warp_sum(acc);
-      if (lane == 0) accw[pidx] += acc;
+      accp[slot] += acc;
     }
     __syncthreads();
   }
-  for (int pidx = threadIdx.x; pidx < npairs; pidx += kHeadTile) {
-    if (pidx < co * ci) atomicAdd(dw + pidx, accw[pidx]);
-    else if (db) atomicAdd(db + (pidx - co * ci), accw[pidx]);
+#pragma unroll
+  for (int slot = 0; slot < kSlots; ++slot) {
+    const int pidx = threadIdx.x + slot * kHeadThreads;
+    if (pidx >= npairs) continue;
+    if (pidx < co * ci) atomicAdd(dw + pidx, accp[slot]);
+    else if (db) atomicAdd(db + (pidx - co * ci), accp[slot]);
   }
 }
 
@@ -761,13 +774,16 @@ int msb_conv1x1_bwd(msb_tensor a, const float* w, const float* dlogits, msb_tens
   MSB_REQUIRE(view_ok(a) && view_ok(da) && da.c == a.c && da.dtype == a.dtype && w && dlogits && dw && ci > 0 &&
                   ci <= a.c && a.c <= kHeadMaxC && co > 0 && co <= a.c,
               "msb_conv1x1_bwd: needs ci <= a.c <= 32 and co <= a.c");
-  const dim3 grid((unsigned)((s + kVoxPerBlock - 1) / kVoxPerBlock), 1, (unsigned)n);
+  int64_t gx = (s + kHeadTile - 1) / kHeadTile;
+  const int64_t cap = (kNumSMs * 3 + n - 1) / n;
+  if (gx > cap) gx = cap;
+  const dim3 grid((unsigned)gx, 1, (unsigned)n);
   cudaStream_t st = as_stream(stream);
   MSB_DISPATCH_DTYPE(a.dtype, {
-    if (a.c == 8) MSB_LAUNCH_PDL((conv1x1_bwd_kernel<T, 1>), grid, dim3(kHeadTile), 0, st, a, w, dlogits, da, dw, db, ci, co, s);
-    else if (a.c == 16) MSB_LAUNCH_PDL((conv1x1_bwd_kernel<T, 2>), grid, dim3(kHeadTile), 0, st, a, w, dlogits, da, dw, db, ci, co, s);
-    else if (a.c == 24) MSB_LAUNCH_PDL((conv1x1_bwd_kernel<T, 3>), grid, dim3(kHeadTile), 0, st, a, w, dlogits, da, dw, db, ci, co, s);
-    else MSB_LAUNCH_PDL((conv1x1_bwd_kernel<T, 4>), grid, dim3(kHeadTile), 0, st, a, w, dlogits, da, dw, db, ci, co, s);
+    if (a.c == 8) MSB_LAUNCH_PDL((conv1x1_bwd_kernel<T, 1>), grid, dim3(kHeadThreads), 0, st, a, w, dlogits, da, dw, db, ci, co, s);
+    else if (a.c == 16) MSB_LAUNCH_PDL((conv1x1_bwd_kernel<T, 2>), grid, dim3(kHeadThreads), 0, st, a, w, dlogits, da, dw, db, ci, co, s);
+    else if (a.c == 24) MSB_LAUNCH_PDL((conv1x1_bwd_kernel<T, 3>), grid, dim3(kHeadThreads), 0, st, a, w, dlogits, da, dw, db, ci, co, s);
+    else MSB_LAUNCH_PDL((conv1x1_bwd_kernel<T, 4>), grid, dim3(kHeadThreads), 0, st, a, w, dlogits, da, dw, db, ci, co, s);
   });
   MSB_LAUNCH_OK();
   return MSB_OK;

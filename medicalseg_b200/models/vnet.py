@@ -249,19 +249,23 @@ class _K5:
 
 
 class _K2S2:
-    """tensor-core path of a 2x2x2 / stride-2 down_conv (vnet.py:98-99) or up_conv (vnet.py:133-137) and its input
-    gradient: `gather` reduces 8 big-grid voxels into one small-grid voxel, `scatter` expands one into eight.  The
-    5-D weight is [A][B][2][2][2]: gather produces A channels from B, scatter produces B channels from A."""
+    """tensor-core path of a strided, unpadded down_conv (vnet.py:98-99) or up_conv (vnet.py:133-137) and its input
+    gradient: `gather` reduces a window of big-grid voxels into one small-grid voxel, `scatter` expands one into a
+    window.  The 5-D weight is [A][B][kd][kh][kw]: gather produces A channels from B, scatter produces B channels from A.
+    Handles the default 2x2x2 / stride 2 and the anisotropic MRI kernels (stride 1 along the last axis)."""
 
     def __init__(self, eng, conv: _Conv, a, b, kernel, stride):
         self.eng, self.conv, self.a, self.b = eng, conv, a, b
-        self.ok = (eng.dtype == torch.bfloat16 and tuple(kernel) == (2, 2, 2) and tuple(stride) == (2, 2, 2)
-                   and a % 16 == 0 and b % 16 == 0 and a <= 256 and b <= 256)
+        self.kernel, self.stride = tuple(kernel), tuple(stride)
+        chan_ok = eng.dtype == torch.bfloat16 and a % 16 == 0 and b % 16 == 0 and a <= 256 and b <= 256
+        # packed-operand size 0 = geometry not supported by the tensor-core kernel
+        self.ok = [chan_ok and ops.tc_packed_bytes(b, _pad(a, 16), self.kernel, self.stride, 0) > 0,
+                   chan_ok and ops.tc_packed_bytes(a, _pad(b, 16), self.kernel, self.stride, 1) > 0]
         self.packed = [None, None]
         self.version = [-1, -1]
         self.pack_args = [None, None]
         self.pack_event = None
-        if self.ok:
+        if any(self.ok):
             eng.register_packer(self)
 
     def repack(self):
@@ -269,8 +273,14 @@ class _K2S2:
             if self.pack_args[mode] is not None:
                 self._pack(mode, *self.pack_args[mode])
 
-    def usable(self, big_dims):
-        return self.ok and all(d % 2 == 0 for d in big_dims)
+    def _dims_ok(self, big_dims):
+        return all(d >= k and (d - k) % s == 0 for d, k, s in zip(big_dims, self.kernel, self.stride))
+
+    def can_gather(self, big_dims):
+        return self.ok[0] and self._dims_ok(big_dims)
+
+    def can_scatter(self, big_dims):
+        return self.ok[1] and self._dims_ok(big_dims)
 
     def _pack(self, mode, c_red_pad, c_out_pad):
         eng = self.eng
@@ -281,20 +291,20 @@ class _K2S2:
         self.pack_args[mode] = (c_red_pad, c_out_pad)
         w = eng.store.view(self.conv.weight)
         if self.packed[mode] is None:
-            self.packed[mode] = torch.empty(ops.k2s2_packed_bytes(c_red_pad, c_out_pad), dtype=torch.uint8,
-                                            device=w.device)
+            self.packed[mode] = torch.empty(ops.tc_packed_bytes(c_red_pad, c_out_pad, self.kernel, self.stride, mode),
+                                            dtype=torch.uint8, device=w.device)
         c_red, c_out = (self.b, self.a) if mode == 0 else (self.a, self.b)
-        ops.k2s2_pack(w, self.packed[mode], c_red, c_out, mode, c_red_pad, c_out_pad)
+        ops.tc_pack(w, self.packed[mode], c_red, c_out, mode, c_red_pad, c_out_pad, self.kernel, self.stride)
         self.version[mode] = eng.param_version
         return self.packed[mode]
 
     def gather(self, x: B8, out: B8, bias, groups=1, sums=None):
         packed = self._pack(0, x.c, _pad(out.c, 16))
-        ops.k2s2_gather(x, packed, bias, self.a, out, groups, sums)
+        ops.tc_gather(x, packed, bias, self.a, out, self.kernel, self.stride, groups, sums)
 
     def scatter(self, x: B8, out: B8, bias, accumulate=False, groups=1, sums=None):
         packed = self._pack(1, x.c, _pad(out.c, 16))
-        ops.k2s2_scatter(x, packed, bias, self.b, out, accumulate, groups, sums)
+        ops.tc_scatter(x, packed, bias, self.b, out, self.kernel, self.stride, accumulate, groups, sums)
 
 
 class _K551:
@@ -637,15 +647,18 @@ class VNet(_Module):
         return self.dtype == torch.bfloat16 and self.bn_training_bwd
 
     def strided_wgrad(self, big: B8, small: B8, dw, dbias, kernel, stride, bias_from_big):
-        """weight gradient of a down / up conv: tensor-core path for the 2x2x2 stride-2 bf16 case"""
+        """weight gradient of a down / up conv: tensor-core path (pointwise GEMM over the tap sub-lattices) for bf16"""
         if self.bias_grad_is_zero():
             dbias = None
-        if (self.dtype == torch.bfloat16 and tuple(kernel) == (2, 2, 2) and tuple(stride) == (2, 2, 2)
-                and all(d % 2 == 0 for d in big.dims) and big.c in (16, 32, 64, 128) and small.c % 16 == 0):
-            need = ops.k2s2_wgrad_workspace_bytes(big.n, big.c, small.c, big.dims)
+        kernel, stride = tuple(kernel), tuple(stride)
+        taps = kernel[0] * kernel[1] * kernel[2]
+        if (self.dtype == torch.bfloat16 and big.c in (16, 32, 64, 128) and (taps * big.c) % 128 == 0
+                and small.c % 16 == 0 and small.c <= 256 and max(stride[1], stride[2]) <= 4
+                and all(d >= k and (d - k) % s == 0 for d, k, s in zip(big.dims, kernel, stride))):
+            need = ops.tc_wgrad_workspace_bytes(big.c, small.c, kernel)
             if self._k2_ws is None or self._k2_ws.numel() < need:
                 self._k2_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-            ops.k2s2_wgrad(big, small, dw, dbias, bias_from_big, self._k2_ws)
+            ops.tc_wgrad(big, small, dw, dbias, kernel, stride, bias_from_big, self._k2_ws)
         else:
             ops.conv_strided_wgrad(big, small, dw, dbias, kernel, stride, (0, 0, 0), bias_from_big)
 
@@ -739,7 +752,7 @@ class VNet(_Module):
             c = tr.out_ch
             yd = self._new(n, c, dims[lvl])
             sd = sums(c)
-            if tr.k2.usable(xin.dims):
+            if tr.k2.can_gather(xin.dims):
                 tr.k2.gather(xin, yd, st.view(tr.down_conv.bias), g, sd)
             else:
                 ops.conv_strided_fwd(xin, st.view(tr.down_conv.weight), st.view(tr.down_conv.bias), yd, tr.kernel,
@@ -785,7 +798,7 @@ class VNet(_Module):
                 ops.channel_scale(skip, xcat.view(half, half), ms, False)
             yu = self._new(n, half, dims[lvl])
             su = sums(half)
-            if tr.k2.usable(dims[lvl]):
+            if tr.k2.can_scatter(dims[lvl]):
                 tr.k2.scatter(xd, yu, st.view(tr.up_conv.bias), False, g, su)
             else:
                 ops.conv_strided_bwd_data(xd, st.view(tr.up_conv.weight), st.view(tr.up_conv.bias), yu, tr.kernel,
@@ -898,7 +911,7 @@ class VNet(_Module):
             dyu = self._new(n, half, dims[lvl])
             tr.act_up.bwd(g_xcat.view(0, half), dyu)
             g_xin = self._new(n, tr.in_ch, rec["xin"].dims)
-            if tr.k2.usable(dims[lvl]):
+            if tr.k2.can_gather(dims[lvl]):
                 tr.k2.gather(dyu, g_xin, None)
             else:
                 ops.conv_strided_fwd(dyu, st.view(tr.up_conv.weight), None, g_xin, tr.kernel, tr.stride, (0, 0, 0), 1,
@@ -925,7 +938,7 @@ class VNet(_Module):
             lu_chain_bwd(tr, rec, g_out, g_down, lvl, rec["mask"])
             dyd = self._new(n, c, dims[lvl])
             tr.act_down.bwd(g_down, dyd)
-            if tr.k2.usable(g_xin.dims):
+            if tr.k2.can_scatter(g_xin.dims):
                 tr.k2.scatter(dyd, g_xin, None, True)
             else:
                 ops.conv_strided_bwd_data(dyd, st.view(tr.down_conv.weight), None, g_xin, tr.kernel, tr.stride,

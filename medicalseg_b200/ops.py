@@ -186,6 +186,35 @@ def k2s2_scatter(x: B8, packed, bias, cout, out: B8, accumulate=False, groups=1,
          groups, _ptr(sums), _stream())
 
 
+# general strided tensor-core convs (any kernel / stride; see include/medseg_b200.h)
+def tc_packed_bytes(c_red_pad, c_out_pad, kernel, stride, mode) -> int:
+    return call("msb_conv_tc_packed_bytes", c_red_pad, c_out_pad, dim3(kernel), dim3(stride), mode)
+
+
+def tc_pack(w, packed, c_red, c_out, mode, c_red_pad, c_out_pad, kernel, stride):
+    call("msb_conv_tc_pack", _ptr(w), _ptr(packed), c_red, c_out, mode, c_red_pad, c_out_pad, dim3(kernel),
+         dim3(stride), _stream())
+
+
+def tc_gather(x: B8, packed, bias, cout, out: B8, kernel, stride, groups=1, sums=None):
+    call("msb_conv_tc_gather", x.mt, _ptr(packed), _ptr(bias), cout, out.mt, x.n, dim3(x.dims), dim3(kernel),
+         dim3(stride), groups, _ptr(sums), _stream())
+
+
+def tc_scatter(x: B8, packed, bias, cout, out: B8, kernel, stride, accumulate=False, groups=1, sums=None):
+    call("msb_conv_tc_scatter", x.mt, _ptr(packed), _ptr(bias), cout, out.mt, x.n, dim3(out.dims), dim3(kernel),
+         dim3(stride), int(accumulate), groups, _ptr(sums), _stream())
+
+
+def tc_wgrad_workspace_bytes(c_big, c_small, kernel) -> int:
+    return call("msb_conv_tc_wgrad_workspace_bytes", c_big, c_small, dim3(kernel))
+
+
+def tc_wgrad(big: B8, small: B8, dw, dbias, kernel, stride, bias_from_big, workspace: torch.Tensor):
+    call("msb_conv_tc_wgrad", big.mt, small.mt, _ptr(dw), _ptr(dbias), big.n, dim3(big.dims), dim3(kernel),
+         dim3(stride), int(bias_from_big), _ptr(workspace), workspace.numel() * workspace.element_size(), _stream())
+
+
 def k5_out_pad(c_view: int) -> int:
     return call("msb_conv_k5_out_pad", c_view)
 

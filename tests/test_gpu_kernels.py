@@ -336,6 +336,81 @@ def test_k2s2_tensor_core_wgrad(ci, co, dims):
     assert rel(dbt, xb.to_ncdhw().sum((0, 2, 3, 4))) <= 1e-5
 
 
+TC_CASES = [((2, 2, 2), (2, 2, 2), 16, 32, (8, 32, 16)), ((2, 2, 4), (2, 2, 1), 16, 32, (8, 32, 12)),
+            ((2, 2, 2), (2, 2, 1), 32, 64, (8, 16, 9)), ((2, 2, 4), (2, 2, 1), 16, 32, (6, 34, 12)),
+            ((2, 2, 2), (2, 2, 1), 64, 128, (4, 36, 9)), ((2, 2, 2), (2, 2, 2), 128, 256, (4, 8, 16))]
+
+
+@pytest.mark.parametrize("k,s,ci,co,dims", TC_CASES)
+def test_strided_tensor_core_convs_any_kernel_stride(k, s, ci, co, dims):
+    """msb_conv_tc_*: down_conv (gather), up_conv (scatter, incl. overlapping windows along w via the gather-w form),
+    their input gradients and weight gradients on tensor cores, vs torch on the same bf16-rounded operands.
+    Shapes: the default 2x2x2/stride 2 and the MRISpineSeg kernels (2,2,4)/(2,2,1), (2,2,2)/(2,2,1)."""
+    ops, B8 = _imp()
+    torch.manual_seed(13)
+    n = 2
+    od = tuple((d - kk) // ss + 1 for d, kk, ss in zip(dims, k, s))
+    taps = k[0] * k[1] * k[2]
+    # ---- Conv3D ci -> co (weight [co][ci][k]): forward = gather, input gradient = scatter (accumulating)
+    w = torch.randn(co, ci, *k, device="cuda") * (1.0 / (ci * taps)) ** 0.5
+    b = torch.randn(co, device="cuda")
+    xb = B8.from_ncdhw(torch.randn(n, ci, *dims, device="cuda"), torch.bfloat16)
+    xq = xb.to_ncdhw().requires_grad_(True)
+    wq = w.bfloat16().float().requires_grad_(True)
+    ref = F.conv3d(xq, wq, b, stride=s)
+    assert tuple(ref.shape[2:]) == od
+    pk = torch.empty(ops.tc_packed_bytes(ci, co, k, s, 0), dtype=torch.uint8, device="cuda")
+    ops.tc_pack(w, pk, ci, co, 0, ci, co, k, s)
+    out = B8(n, co, od, torch.bfloat16, device="cuda")
+    sums = torch.zeros(2 * co, dtype=torch.float64, device="cuda")
+    ops.tc_gather(xb, pk, b, co, out, k, s, 1, sums)
+    o = out.to_ncdhw()
+    assert rel(o, ref.detach()) <= BF16_TOL
+    s_ref = o.double().sum((0, 2, 3, 4))
+    assert float((sums[:co] - s_ref).abs().max()) <= 1e-3 * float(s_ref.abs().max() + 1)
+    dyb = B8.from_ncdhw(torch.randn_like(ref), torch.bfloat16)
+    ref.backward(dyb.to_ncdhw())
+    pk1 = torch.empty(ops.tc_packed_bytes(co, ci, k, s, 1), dtype=torch.uint8, device="cuda")
+    assert pk1.numel() > 0
+    ops.tc_pack(w, pk1, co, ci, 1, co, ci, k, s)
+    dx = B8.from_ncdhw(torch.randn(n, ci, *dims, device="cuda"), torch.bfloat16)
+    base = dx.to_ncdhw()
+    ops.tc_scatter(dyb, pk1, None, ci, dx, k, s, True)
+    assert rel(dx.to_ncdhw(), base + xq.grad) <= BF16_TOL
+    dw, db = torch.zeros_like(w), torch.zeros(co, device="cuda")
+    ws = torch.empty(ops.tc_wgrad_workspace_bytes(ci, co, k), dtype=torch.uint8, device="cuda")
+    ops.tc_wgrad(xb, dyb, dw, db, k, s, False, ws)
+    assert rel(dw, wq.grad) <= 1e-4
+    assert rel(db, dyb.to_ncdhw().sum((0, 2, 3, 4))) <= 1e-5
+    # ---- Conv3DTranspose co -> ci (weight [co][ci][k]): forward = scatter with bias + BN sums, input gradient = gather
+    wt = torch.randn(co, ci, *k, device="cuda") * (1.0 / (co * taps)) ** 0.5
+    bt = torch.randn(ci, device="cuda")
+    sb = B8.from_ncdhw(torch.randn(n, co, *od, device="cuda"), torch.bfloat16)
+    sq_ = sb.to_ncdhw().requires_grad_(True)
+    wtq = wt.bfloat16().float().requires_grad_(True)
+    reft = F.conv_transpose3d(sq_, wtq, bt, stride=s)
+    assert tuple(reft.shape[2:]) == tuple(dims)
+    pkt = torch.empty(ops.tc_packed_bytes(co, ci, k, s, 1), dtype=torch.uint8, device="cuda")
+    ops.tc_pack(wt, pkt, co, ci, 1, co, ci, k, s)
+    up = B8(n, ci, dims, torch.bfloat16, device="cuda", zero=True)
+    sums2 = torch.zeros(2 * ci, dtype=torch.float64, device="cuda")
+    ops.tc_scatter(sb, pkt, bt, ci, up, k, s, False, 1, sums2)
+    u = up.to_ncdhw()
+    assert rel(u, reft.detach()) <= BF16_TOL
+    q_ref = (u.double() ** 2).sum((0, 2, 3, 4))
+    assert float((sums2[ci:] - q_ref).abs().max()) <= 1e-4 * float(q_ref.abs().max() + 1)
+    dub = B8.from_ncdhw(torch.randn_like(reft), torch.bfloat16)
+    reft.backward(dub.to_ncdhw())
+    pkg = torch.empty(ops.tc_packed_bytes(ci, co, k, s, 0), dtype=torch.uint8, device="cuda")
+    ops.tc_pack(wt, pkg, ci, co, 0, ci, co, k, s)
+    dsm = B8(n, co, od, torch.bfloat16, device="cuda")
+    ops.tc_gather(dub, pkg, None, co, dsm, k, s)
+    assert rel(dsm.to_ncdhw(), sq_.grad) <= BF16_TOL
+    dwt = torch.zeros_like(wt)
+    ops.tc_wgrad(dub, sb, dwt, None, k, s, True, ws)
+    assert rel(dwt, wtq.grad) <= 1e-4
+
+
 @pytest.mark.parametrize("c", [2, 3, 20])
 def test_fused_dice_ce_loss_matches_oracle(c):
     from oracle import vnet_oracle as vo
@@ -357,29 +432,31 @@ def test_fused_dice_ce_loss_matches_oracle(c):
     assert rel(lg.grad.cpu(), lo.grad) <= 1e-5
 
 
-def test_conv1x1_head():
+@pytest.mark.parametrize("c,cpad,dims", [(3, 16, (5, 6, 7)), (2, 8, (9, 17, 20)), (20, 32, (6, 30, 12)), (32, 32, (3, 40, 9))])
+def test_conv1x1_head(c, cpad, dims):
     ops, B8 = _imp()
     torch.manual_seed(7)
-    n, c, dims = 2, 3, (5, 6, 7)
-    a = torch.zeros(n, 16, *dims, device="cuda")
+    n = 2
+    a = torch.zeros(n, cpad, *dims, device="cuda")
     a[:, :c] = torch.randn(n, c, *dims, device="cuda")
     w, b = torch.randn(c, c, device="cuda"), torch.randn(c, device="cuda")
     ab = B8.from_ncdhw(a, torch.float32)
     logits = torch.empty(n, c, *dims, device="cuda")
     ops.conv1x1_fwd(ab, w, b, logits, c, c)
-    a_ = a[:, :c].clone().requires_grad_(True)
-    w_ = w.clone().requires_grad_(True)
-    b_ = b.clone().requires_grad_(True)
+    a_ = a[:, :c].double().requires_grad_(True)   # f64 reference (torch's f32 conv may use TF32)
+    w_ = w.double().requires_grad_(True)
+    b_ = b.double().requires_grad_(True)
     ref = F.conv3d(a_, w_.view(c, c, 1, 1, 1), b_)
-    assert rel(logits, ref.detach()) <= 1e-5
-    dl = torch.randn_like(ref)
-    ref.backward(dl)
-    da = B8(n, 16, dims, torch.float32, device="cuda")
+    assert rel(logits, ref.detach().float()) <= 1e-5
+    dl = torch.randn_like(logits)
+    ref.backward(dl.double())
+    da = B8(n, cpad, dims, torch.float32, device="cuda")
     dw, db = torch.zeros_like(w), torch.zeros_like(b)
     ops.conv1x1_bwd(ab, w, dl, da, dw, db, c, c)
-    assert rel(da.to_ncdhw(c), a_.grad) <= 1e-5
-    assert rel(dw, w_.grad) <= 1e-4 and rel(db, b_.grad) <= 1e-5
-    assert float(da.to_ncdhw(16)[:, c:].abs().max()) == 0.0
+    assert rel(da.to_ncdhw(c), a_.grad.float()) <= 1e-5
+    assert rel(dw, w_.grad.float()) <= 1e-4 and rel(db, b_.grad.float()) <= 1e-5
+    if cpad > c:
+        assert float(da.to_ncdhw(cpad)[:, c:].abs().max()) == 0.0
 
 
 def test_momentum_step_matches_oracle():
