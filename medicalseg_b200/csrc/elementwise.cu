@@ -4,6 +4,7 @@
 #include <stdarg.h>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace msb {
 
@@ -147,6 +148,94 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
 }
 
 // ---------------------------------------------------------------------------------------------------
+// TMA-staged plane streaming for the HBM-bound BatchNorm kernels.  A (n, 8-channel plane) of a B8 tensor is one
+// contiguous run of S * 8 elements, so a chunk of voxels is a single 1-D bulk copy (cp.async.bulk + mbarrier).  One
+// block per SM keeps kStreamStages chunks of every input tensor in flight in shared memory (up to 192 KB), which
+// decouples the bytes in flight from the register file: the register-staged version needed 128 registers per thread
+// for two voxels in flight and ran at 25 % occupancy / 49-54 % of the HBM peak (ncu, profiles/r1n_*).
+constexpr int kStreamStages = 3;
+constexpr int kStreamChunkBytes = 16384;  // per tensor and stage: 1024 bf16 voxels (x 8 channels) or 512 f32 voxels
+constexpr int kStreamThreads = 512;
+
+template <typename T, int NIN>
+struct PlaneStream {
+  static constexpr int kVox = kStreamChunkBytes / (8 * (int)sizeof(T));
+  static constexpr int kSmemBytes = kStreamStages * NIN * kStreamChunkBytes + 64;
+  uint8_t* data;      // [stage][NIN][kStreamChunkBytes]
+  uint32_t bar0;      // full barriers [stage]
+  const T* src[NIN];  // plane base pointers (element 0 of voxel 0)
+  int64_t s, nchunks;
+  bool on[NIN];       // inputs that are really streamed (others are skipped)
+
+  __device__ __forceinline__ void init(uint8_t* smem_raw) {
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 15) & ~uintptr_t(15));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base);
+    data = base + 64;
+    bar0 = ptx::smem_u32(bars);
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < kStreamStages; ++i) ptx::mbar_init(bar0 + 8u * i, 1);
+      ptx::fence_mbar_init();
+    }
+    __syncthreads();
+  }
+  __device__ __forceinline__ int chunk_voxels(int64_t chunk) const {
+    const int64_t v0 = chunk * kVox;
+    return (int)min((int64_t)kVox, s - v0);
+  }
+  // thread 0 only
+  __device__ __forceinline__ void issue(int64_t chunk, int slot) {
+    const int nv = chunk_voxels(chunk);
+    const uint32_t bytes = (uint32_t)nv * 8u * (uint32_t)sizeof(T);
+    int active = 0;
+#pragma unroll
+    for (int i = 0; i < NIN; ++i) active += on[i] ? 1 : 0;
+    ptx::mbar_expect_tx(bar0 + 8u * slot, bytes * active);
+#pragma unroll
+    for (int i = 0; i < NIN; ++i)
+      if (on[i])
+        ptx::bulk_load(ptx::smem_u32(data + ((size_t)slot * NIN + i) * kStreamChunkBytes), src[i] + chunk * kVox * 8, bytes,
+                       bar0 + 8u * slot);
+  }
+  __device__ __forceinline__ void prologue() {
+    if (threadIdx.x == 0) {
+      int slot = 0;
+      for (int64_t c = blockIdx.x; c < nchunks && slot < kStreamStages; c += gridDim.x, ++slot) issue(c, slot);
+    }
+  }
+  __device__ __forceinline__ void wait(int64_t k) {  // k = index of the chunk in this block's sequence
+    ptx::mbar_wait(bar0 + 8u * (uint32_t)(k % kStreamStages), (uint32_t)((k / kStreamStages) & 1));
+  }
+  __device__ __forceinline__ const T* stage(int64_t k, int i) const {
+    return reinterpret_cast<const T*>(data + ((size_t)(k % kStreamStages) * NIN + i) * kStreamChunkBytes);
+  }
+  // all threads finished reading chunk k of this block's sequence: refill its slot
+  __device__ __forceinline__ void release(int64_t k, int64_t chunk) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int64_t next = chunk + (int64_t)kStreamStages * gridDim.x;
+      if (next < nchunks) issue(next, (int)(k % kStreamStages));
+    }
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ const T* plane_base(const msb_tensor& t, int n, int c8, int64_t s) {
+  return reinterpret_cast<const T*>(t.ptr) + (int64_t)n * t.n_stride + (int64_t)c8 * s * 8;
+}
+
+// grid for the streaming kernels: about one block per SM, at most one block per chunk
+template <typename T>
+static inline dim3 stream_grid(int n, int c, int64_t s) {
+  const int kvox = kStreamChunkBytes / (8 * (int)sizeof(T));
+  const int64_t chunks = (s + kvox - 1) / kvox;
+  const int64_t planes = (int64_t)(c / 8) * n;
+  int64_t gx = kNumSMs / planes;
+  if (gx < 1) gx = 1;
+  if (gx > chunks) gx = chunks;
+  return dim3((unsigned)gx, (unsigned)(c / 8), (unsigned)n);
+}
+
+// ---------------------------------------------------------------------------------------------------
 struct BnActParams {
   float scale[8], shift[8], a1[8], a2[8];
 };
@@ -165,7 +254,7 @@ __device__ __forceinline__ void load_params(BnActParams& p, const float* bnbuf, 
 }
 
 template <typename T, bool HAS_RES, bool HAS_TILE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kStreamThreads)
     bn_act_fwd_kernel(msb_tensor y, msb_tensor out, msb_tensor res, const float* __restrict__ tile_src, int tile_c,
                       const float* __restrict__ bnbuf, const float* __restrict__ alpha1,
                       const float* __restrict__ alpha2, int64_t s, int groups) {
@@ -174,22 +263,39 @@ __global__ void __launch_bounds__(kThreads)
   const int c8 = blockIdx.y, n = blockIdx.z;
   BnActParams p;
   load_params(p, bnbuf, alpha1, alpha2, y.c, groups, groups == 1 ? 0 : n, c8);
-  const int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock;
-  const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
-#pragma unroll 2
-  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
-    float a[8], r[8];
-    Vec8<T>::load(view_ptr<T>(y, n, c8, s, v), a);
-    if (HAS_RES) Vec8<T>::load(view_ptr<T>(res, n, c8, s, v), r);
+  extern __shared__ uint8_t stream_smem[];
+  using PS = PlaneStream<T, 2>;
+  PS ps;
+  ps.s = s; ps.nchunks = (s + PS::kVox - 1) / PS::kVox;
+  ps.src[0] = plane_base<T>(y, n, c8, s); ps.on[0] = true;
+  ps.src[1] = HAS_RES ? plane_base<T>(res, n, c8, s) : nullptr; ps.on[1] = HAS_RES;
+  ps.init(stream_smem);
+  ps.prologue();
+  T* outp = const_cast<T*>(plane_base<T>(out, n, c8, s));
+  int64_t k = 0;
+  for (int64_t chunk = blockIdx.x; chunk < ps.nchunks; chunk += gridDim.x, ++k) {
+    ps.wait(k);
+    const int nv = ps.chunk_voxels(chunk);
+    const T* ys = ps.stage(k, 0);
+    const T* rs = ps.stage(k, 1);
+    const int64_t v0 = chunk * PS::kVox;
+    for (int lv = threadIdx.x; lv < nv; lv += kStreamThreads) {
+      float a[8], r[8];
+      Vec8<T>::load(ys + lv * 8, a);
+      if (HAS_RES) Vec8<T>::load(rs + lv * 8, r);
+      float tile1 = 0.f;  // in_channels == 1 (every reference config): one load per voxel instead of eight
+      if (HAS_TILE && tile_c == 1) tile1 = __ldg(tile_src + (int64_t)n * s + v0 + lv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = fmaf(a[j], p.scale[j], p.shift[j]);
-      if (HAS_TILE) t += __ldg(tile_src + ((int64_t)n * tile_c + ((c8 * 8 + j) % tile_c)) * s + v);
-      t = prelu(t, p.a1[j]);
-      if (HAS_RES) t = prelu(t + r[j], p.a2[j]);
-      a[j] = t;
+      for (int j = 0; j < 8; ++j) {
+        float t = fmaf(a[j], p.scale[j], p.shift[j]);
+        if (HAS_TILE) t += tile_c == 1 ? tile1 : __ldg(tile_src + ((int64_t)n * tile_c + ((c8 * 8 + j) % tile_c)) * s + v0 + lv);
+        t = prelu(t, p.a1[j]);
+        if (HAS_RES) t = prelu(t + r[j], p.a2[j]);
+        a[j] = t;
+      }
+      Vec8<T>::store(outp + (v0 + lv) * 8, a);
     }
-    Vec8<T>::store(view_ptr<T>(out, n, c8, s, v), a);
+    ps.release(k, chunk);
   }
 }
 
@@ -197,7 +303,7 @@ __global__ void __launch_bounds__(kThreads)
 // (training) or the running statistics (eval); block x == 0 of each (n, plane) also publishes them in bnbuf for the
 // backward kernels, and block (x == 0, n == 0) applies the running-statistics update.
 template <typename T, bool HAS_RES, bool HAS_TILE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kStreamThreads)
     bn_fwd_fused_kernel(msb_tensor y, msb_tensor out, msb_tensor res, const float* __restrict__ tile_src, int tile_c,
                         const double* __restrict__ sums, double count, const float* __restrict__ gamma,
                         const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
@@ -255,22 +361,39 @@ __global__ void __launch_bounds__(kThreads)
     rmean[ch] = momentum * rmean[ch] + (1.f - momentum) * (float)(mean_acc / groups);
     rvar[ch] = momentum * rvar[ch] + (1.f - momentum) * (float)(var_acc / groups);
   }
-  const int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock;
-  const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
-#pragma unroll 2
-  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
-    float a[8], r[8];
-    Vec8<T>::load(view_ptr<T>(y, n, c8, s, v), a);
-    if (HAS_RES) Vec8<T>::load(view_ptr<T>(res, n, c8, s, v), r);
+  extern __shared__ uint8_t stream_smem[];
+  using PS = PlaneStream<T, 2>;
+  PS ps;
+  ps.s = s; ps.nchunks = (s + PS::kVox - 1) / PS::kVox;
+  ps.src[0] = plane_base<T>(y, n, c8, s); ps.on[0] = true;
+  ps.src[1] = HAS_RES ? plane_base<T>(res, n, c8, s) : nullptr; ps.on[1] = HAS_RES;
+  ps.init(stream_smem);
+  ps.prologue();
+  T* outp = const_cast<T*>(plane_base<T>(out, n, c8, s));
+  int64_t k = 0;
+  for (int64_t chunk = blockIdx.x; chunk < ps.nchunks; chunk += gridDim.x, ++k) {
+    ps.wait(k);
+    const int nv = ps.chunk_voxels(chunk);
+    const T* ys = ps.stage(k, 0);
+    const T* rs = ps.stage(k, 1);
+    const int64_t v0 = chunk * PS::kVox;
+    for (int lv = threadIdx.x; lv < nv; lv += kStreamThreads) {
+      float a[8], r[8];
+      Vec8<T>::load(ys + lv * 8, a);
+      if (HAS_RES) Vec8<T>::load(rs + lv * 8, r);
+      float tile1 = 0.f;  // in_channels == 1 (every reference config): one load per voxel instead of eight
+      if (HAS_TILE && tile_c == 1) tile1 = __ldg(tile_src + (int64_t)n * s + v0 + lv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = fmaf(a[j], p.scale[j], p.shift[j]);
-      if (HAS_TILE) t += __ldg(tile_src + ((int64_t)n * tile_c + ((c8 * 8 + j) % tile_c)) * s + v);
-      t = prelu(t, p.a1[j]);
-      if (HAS_RES) t = prelu(t + r[j], p.a2[j]);
-      a[j] = t;
+      for (int j = 0; j < 8; ++j) {
+        float t = fmaf(a[j], p.scale[j], p.shift[j]);
+        if (HAS_TILE) t += tile_c == 1 ? tile1 : __ldg(tile_src + ((int64_t)n * tile_c + ((c8 * 8 + j) % tile_c)) * s + v0 + lv);
+        t = prelu(t, p.a1[j]);
+        if (HAS_RES) t = prelu(t + r[j], p.a2[j]);
+        a[j] = t;
+      }
+      Vec8<T>::store(outp + (v0 + lv) * 8, a);
     }
-    Vec8<T>::store(view_ptr<T>(out, n, c8, s, v), a);
+    ps.release(k, chunk);
   }
 }
 
@@ -293,13 +416,13 @@ __device__ __forceinline__ void bwd_point(float yv, float rv, float tile, float 
 }
 
 template <typename T, bool HAS_RES, bool HAS_TILE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kStreamThreads)
     bn_act_bwd_reduce_kernel(msb_tensor y, msb_tensor res, const float* __restrict__ tile_src, int tile_c,
                              msb_tensor gout, const float* __restrict__ bnbuf, const float* __restrict__ alpha1,
                              const float* __restrict__ alpha2, int64_t s, int groups, double* __restrict__ red) {
   pdl_wait();
   pdl_trigger();
-  __shared__ float sred[kThreads / 32][32];
+  __shared__ float sred[kStreamThreads / 32][32];
   const int c8 = blockIdx.y, n = blockIdx.z;
   const int g = groups == 1 ? 0 : n;
   BnActParams p;
@@ -316,20 +439,36 @@ __global__ void __launch_bounds__(kThreads)
   float acc[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-  // grid-stride over 2048-voxel chunks: the launch caps the blocks per (n, plane) so that the per-channel f64
-  // atomics at the end (same 32 addresses for every block of a plane) stay a few hundred per address
-  for (int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock; v0 < s; v0 += (int64_t)gridDim.x * kVoxPerBlock) {
-    const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
-#pragma unroll 2
-    for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
+  // streamed over this block's chunks of the plane (about one block per SM: the per-channel f64 atomics at the end hit
+  // the same 32 addresses for every block of a plane, so few blocks also keep that tail short)
+  extern __shared__ uint8_t stream_smem[];
+  using PS = PlaneStream<T, 3>;
+  PS ps;
+  ps.s = s; ps.nchunks = (s + PS::kVox - 1) / PS::kVox;
+  ps.src[0] = plane_base<T>(y, n, c8, s); ps.on[0] = true;
+  ps.src[1] = plane_base<T>(gout, n, c8, s); ps.on[1] = true;
+  ps.src[2] = HAS_RES ? plane_base<T>(res, n, c8, s) : nullptr; ps.on[2] = HAS_RES;
+  ps.init(stream_smem);
+  ps.prologue();
+  int64_t k = 0;
+  for (int64_t chunk = blockIdx.x; chunk < ps.nchunks; chunk += gridDim.x, ++k) {
+    ps.wait(k);
+    const int nv = ps.chunk_voxels(chunk);
+    const T* ys = ps.stage(k, 0);
+    const T* gs = ps.stage(k, 1);
+    const T* rs = ps.stage(k, 2);
+    const int64_t v0 = chunk * PS::kVox;
+    for (int lv = threadIdx.x; lv < nv; lv += kStreamThreads) {
       float a[8], r[8], go[8];
-      Vec8<T>::load(view_ptr<T>(y, n, c8, s, v), a);
-      Vec8<T>::load(view_ptr<T>(gout, n, c8, s, v), go);
-      if (HAS_RES) Vec8<T>::load(view_ptr<T>(res, n, c8, s, v), r);
+      Vec8<T>::load(ys + lv * 8, a);
+      Vec8<T>::load(gs + lv * 8, go);
+      if (HAS_RES) Vec8<T>::load(rs + lv * 8, r);
+      float tile1 = 0.f;  // in_channels == 1 (every reference config): one load per voxel instead of eight
+      if (HAS_TILE && tile_c == 1) tile1 = __ldg(tile_src + (int64_t)n * s + v0 + lv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float tile = 0.f;
-        if (HAS_TILE) tile = __ldg(tile_src + ((int64_t)n * tile_c + ((c8 * 8 + j) % tile_c)) * s + v);
+        if (HAS_TILE) tile = tile_c == 1 ? tile1 : __ldg(tile_src + ((int64_t)n * tile_c + ((c8 * 8 + j) % tile_c)) * s + v0 + lv);
         float g1, g2, da1, da2;
         bwd_point<HAS_RES>(a[j], HAS_RES ? r[j] : 0.f, tile, go[j], p.scale[j], p.shift[j], p.a1[j], p.a2[j], g1, g2,
                            da1, da2);
@@ -340,19 +479,20 @@ __global__ void __launch_bounds__(kThreads)
         acc[24 + j] += da2;
       }
     }
+    ps.release(k, chunk);
   }
   block_reduce_to_smem<32>(acc, &sred[0][0]);
   if (threadIdx.x < 32) {
     double t = 0;
 #pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) t += (double)sred[w][threadIdx.x];
+    for (int w = 0; w < kStreamThreads / 32; ++w) t += (double)sred[w][threadIdx.x];
     const int stat = threadIdx.x >> 3, j = threadIdx.x & 7;
     atomicAdd(&red[((int64_t)stat * groups + g) * y.c + c8 * 8 + j], t);
   }
 }
 
 template <typename T, bool HAS_RES, bool HAS_TILE, bool HAS_DRES>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kStreamThreads)
     bn_act_bwd_apply_kernel(msb_tensor y, msb_tensor res, const float* __restrict__ tile_src, int tile_c,
                             msb_tensor gout, const float* __restrict__ bnbuf, const float* __restrict__ alpha1,
                             const float* __restrict__ alpha2, const double* __restrict__ red, double count,
@@ -391,28 +531,50 @@ __global__ void __launch_bounds__(kThreads)
       m_g1x[j] = training ? (float)(red[gc + off + j] / count) : 0.f;
     }
   }
-  const int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock;
-  const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
-#pragma unroll 2
-  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
-    float a[8], r[8], go[8], dr[8];
-    Vec8<T>::load(view_ptr<T>(y, n, c8, s, v), a);
-    Vec8<T>::load(view_ptr<T>(gout, n, c8, s, v), go);
-    if (HAS_RES) Vec8<T>::load(view_ptr<T>(res, n, c8, s, v), r);
-    if (HAS_DRES && dres_acc) Vec8<T>::load(view_ptr<T>(dres, n, c8, s, v), dr);
+  extern __shared__ uint8_t stream_smem[];
+  using PS = PlaneStream<T, 4>;
+  PS ps;
+  ps.s = s; ps.nchunks = (s + PS::kVox - 1) / PS::kVox;
+  ps.src[0] = plane_base<T>(y, n, c8, s); ps.on[0] = true;
+  ps.src[1] = plane_base<T>(gout, n, c8, s); ps.on[1] = true;
+  ps.src[2] = HAS_RES ? plane_base<T>(res, n, c8, s) : nullptr; ps.on[2] = HAS_RES;
+  ps.src[3] = (HAS_DRES && dres_acc) ? plane_base<T>(dres, n, c8, s) : nullptr; ps.on[3] = HAS_DRES && dres_acc;
+  ps.init(stream_smem);
+  ps.prologue();
+  T* dyp = const_cast<T*>(plane_base<T>(dy, n, c8, s));
+  T* drp = HAS_DRES ? const_cast<T*>(plane_base<T>(dres, n, c8, s)) : nullptr;
+  int64_t k = 0;
+  for (int64_t chunk = blockIdx.x; chunk < ps.nchunks; chunk += gridDim.x, ++k) {
+    ps.wait(k);
+    const int nv = ps.chunk_voxels(chunk);
+    const T* ys = ps.stage(k, 0);
+    const T* gs = ps.stage(k, 1);
+    const T* rs = ps.stage(k, 2);
+    const T* ds_ = ps.stage(k, 3);
+    const int64_t v0 = chunk * PS::kVox;
+    for (int lv = threadIdx.x; lv < nv; lv += kStreamThreads) {
+      float a[8], r[8], go[8], dr[8];
+      Vec8<T>::load(ys + lv * 8, a);
+      Vec8<T>::load(gs + lv * 8, go);
+      if (HAS_RES) Vec8<T>::load(rs + lv * 8, r);
+      if (HAS_DRES && dres_acc) Vec8<T>::load(ds_ + lv * 8, dr);
+      float tile1 = 0.f;  // in_channels == 1 (every reference config): one load per voxel instead of eight
+      if (HAS_TILE && tile_c == 1) tile1 = __ldg(tile_src + (int64_t)n * s + v0 + lv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float tile = 0.f;
-      if (HAS_TILE) tile = __ldg(tile_src + ((int64_t)n * tile_c + ((c8 * 8 + j) % tile_c)) * s + v);
-      float g1, g2, da1, da2;
-      bwd_point<HAS_RES>(a[j], HAS_RES ? r[j] : 0.f, tile, go[j], p.scale[j], p.shift[j], p.a1[j], p.a2[j], g1, g2,
-                         da1, da2);
-      const float xhat = (a[j] - mean[j]) * invstd[j];
-      a[j] = p.scale[j] * (g1 - m_g1[j] - xhat * m_g1x[j]);
-      if (HAS_DRES) dr[j] = (dres_acc ? dr[j] : 0.f) + g2;
+      for (int j = 0; j < 8; ++j) {
+        float tile = 0.f;
+        if (HAS_TILE) tile = tile_c == 1 ? tile1 : __ldg(tile_src + ((int64_t)n * tile_c + ((c8 * 8 + j) % tile_c)) * s + v0 + lv);
+        float g1, g2, da1, da2;
+        bwd_point<HAS_RES>(a[j], HAS_RES ? r[j] : 0.f, tile, go[j], p.scale[j], p.shift[j], p.a1[j], p.a2[j], g1, g2,
+                           da1, da2);
+        const float xhat = (a[j] - mean[j]) * invstd[j];
+        a[j] = p.scale[j] * (g1 - m_g1[j] - xhat * m_g1x[j]);
+        if (HAS_DRES) dr[j] = (dres_acc ? dr[j] : 0.f) + g2;
+      }
+      Vec8<T>::store(dyp + (v0 + lv) * 8, a);
+      if (HAS_DRES) Vec8<T>::store(drp + (v0 + lv) * 8, dr);
     }
-    Vec8<T>::store(view_ptr<T>(dy, n, c8, s, v), a);
-    if (HAS_DRES) Vec8<T>::store(view_ptr<T>(dres, n, c8, s, v), dr);
+    ps.release(k, chunk);
   }
 }
 
@@ -645,6 +807,18 @@ int msb_bn_finalize(const double* sums, double count, const float* gamma, const 
   return MSB_OK;
 }
 
+// launches a PlaneStream kernel: ~1 block per SM, kStreamThreads threads, NIN * 48 KB of dynamic shared memory
+#define MSB_LAUNCH_STREAM(kernel, T_, NIN_, n_, c_, s_, st_, ...)                                              \
+  do {                                                                                                         \
+    constexpr int _smem = PlaneStream<T_, NIN_>::kSmemBytes;                                                   \
+    static bool _attr = false;                                                                                 \
+    if (!_attr) {                                                                                              \
+      MSB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, _smem));           \
+      _attr = true;                                                                                            \
+    }                                                                                                          \
+    MSB_LAUNCH_PDL(kernel, stream_grid<T_>(n_, c_, s_), dim3(kStreamThreads), _smem, st_, __VA_ARGS__);        \
+  } while (0)
+
 #define MSB_BOOL_DISPATCH2(b0, b1, ...)                          \
   do {                                                           \
     if (b0) {                                                    \
@@ -669,9 +843,9 @@ int msb_bn_act_fwd(msb_tensor y, msb_tensor out, msb_tensor residual, const floa
   MSB_REQUIRE(!tile_src || tile_c > 0, "msb_bn_act_fwd: tile_c must be > 0");
   MSB_REQUIRE(groups == 1 || groups == n, "msb_bn_act_fwd: groups must be 1 or n");
   MSB_DISPATCH_DTYPE(y.dtype, MSB_BOOL_DISPATCH2(has_res, tile_src != nullptr,
-                                                 MSB_LAUNCH_PDL((bn_act_fwd_kernel<T, B0, B1>), plane_grid(n, y.c, s),
-                                                                dim3(kThreads), 0, as_stream(stream), y, out, residual,
-                                                                tile_src, tile_c, bnbuf, alpha1, alpha2, s, groups);););
+                                                 MSB_LAUNCH_STREAM((bn_act_fwd_kernel<T, B0, B1>), T, 2, n, y.c, s,
+                                                                   as_stream(stream), y, out, residual, tile_src, tile_c,
+                                                                   bnbuf, alpha1, alpha2, s, groups);););
   return MSB_OK;
 }
 
@@ -689,11 +863,11 @@ int msb_bn_fwd_fused(msb_tensor y, msb_tensor out, msb_tensor residual, const fl
   MSB_REQUIRE(training ? (sums != nullptr && count > 0) : (running_mean && running_var),
               "msb_bn_fwd_fused: training needs sums, eval needs running stats");
   MSB_DISPATCH_DTYPE(y.dtype, MSB_BOOL_DISPATCH2(has_res, tile_src != nullptr,
-                                                 MSB_LAUNCH_PDL((bn_fwd_fused_kernel<T, B0, B1>), plane_grid(n, y.c, s),
-                                                                dim3(kThreads), 0, as_stream(stream), y, out, residual,
-                                                                tile_src, tile_c, sums, count, gamma, beta,
-                                                                running_mean, running_var, momentum, eps, training,
-                                                                bnbuf, alpha1, alpha2, s, groups);););
+                                                 MSB_LAUNCH_STREAM((bn_fwd_fused_kernel<T, B0, B1>), T, 2, n, y.c, s,
+                                                                   as_stream(stream), y, out, residual, tile_src, tile_c,
+                                                                   sums, count, gamma, beta, running_mean, running_var,
+                                                                   momentum, eps, training, bnbuf, alpha1, alpha2, s,
+                                                                   groups);););
   return MSB_OK;
 }
 
@@ -707,10 +881,9 @@ int msb_bn_act_bwd_reduce(msb_tensor y, msb_tensor residual, const float* tile_s
               "msb_bn_act_bwd_reduce: residual needs matching view and alpha2");
   MSB_REQUIRE(groups == 1 || groups == n, "msb_bn_act_bwd_reduce: groups must be 1 or n");
   MSB_DISPATCH_DTYPE(y.dtype, MSB_BOOL_DISPATCH2(has_res, tile_src != nullptr,
-                                                 MSB_LAUNCH_PDL((bn_act_bwd_reduce_kernel<T, B0, B1>),
-                                                                plane_grid_capped(n, y.c, s), dim3(kThreads), 0,
-                                                                as_stream(stream), y, residual, tile_src, tile_c, gout,
-                                                                bnbuf, alpha1, alpha2, s, groups, red);););
+                                                 MSB_LAUNCH_STREAM((bn_act_bwd_reduce_kernel<T, B0, B1>), T, 3, n, y.c, s,
+                                                                   as_stream(stream), y, residual, tile_src, tile_c, gout,
+                                                                   bnbuf, alpha1, alpha2, s, groups, red);););
   return MSB_OK;
 }
 
@@ -729,17 +902,16 @@ int msb_bn_act_bwd_apply(msb_tensor y, msb_tensor residual, const float* tile_sr
               "msb_bn_act_bwd_apply: dres needs a residual and a matching view");
   MSB_REQUIRE(groups == 1 || groups == n, "msb_bn_act_bwd_apply: groups must be 1 or n");
   cudaStream_t st = as_stream(stream);
-  const dim3 grid = plane_grid(n, y.c, s);
   MSB_DISPATCH_DTYPE(
       y.dtype, MSB_BOOL_DISPATCH2(has_res, tile_src != nullptr, {
         if (has_dres)
-          MSB_LAUNCH_PDL((bn_act_bwd_apply_kernel<T, B0, B1, true>), grid, dim3(kThreads), 0, st, y, residual, tile_src,
-                         tile_c, gout, bnbuf, alpha1, alpha2, red, count, training, dy, dres, dres_accumulate, s, groups,
-                         dgamma, dbeta, dalpha1, has_res ? dalpha2 : nullptr);
+          MSB_LAUNCH_STREAM((bn_act_bwd_apply_kernel<T, B0, B1, true>), T, 4, n, y.c, s, st, y, residual, tile_src,
+                            tile_c, gout, bnbuf, alpha1, alpha2, red, count, training, dy, dres, dres_accumulate, s,
+                            groups, dgamma, dbeta, dalpha1, has_res ? dalpha2 : nullptr);
         else
-          MSB_LAUNCH_PDL((bn_act_bwd_apply_kernel<T, B0, B1, false>), grid, dim3(kThreads), 0, st, y, residual,
-                         tile_src, tile_c, gout, bnbuf, alpha1, alpha2, red, count, training, dy, dres, dres_accumulate,
-                         s, groups, dgamma, dbeta, dalpha1, has_res ? dalpha2 : nullptr);
+          MSB_LAUNCH_STREAM((bn_act_bwd_apply_kernel<T, B0, B1, false>), T, 4, n, y.c, s, st, y, residual, tile_src,
+                            tile_c, gout, bnbuf, alpha1, alpha2, red, count, training, dy, dres, dres_accumulate, s,
+                            groups, dgamma, dbeta, dalpha1, has_res ? dalpha2 : nullptr);
       }););
   return MSB_OK;
 }

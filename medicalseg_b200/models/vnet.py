@@ -160,6 +160,9 @@ class _BnAct:
         if self.bnbuf is None or self.bnbuf.numel() != 4 * g * c:
             self.bnbuf = torch.empty(4 * g * c, dtype=torch.float32, device=y.buf.device)
         count = y.s * (y.n if g == 1 else 1)
+        if eng.training and eng.sync_world() > 1:
+            torch.distributed.all_reduce(sums)  # [2][g][C] f64 sums over all ranks (stream-ordered NCCL call)
+            count *= eng.sync_world()
         a2 = st.phys(self.relu2._weight) if (self.relu2 is not None and residual is not None) else None
         ops.bn_fwd_fused(y, out, residual, tile, tile_c, sums if eng.training else None, count,
                          st.phys(self.bn.weight), st.phys(self.bn.bias), st.phys(self.bn.mean), st.phys(self.bn.var),
@@ -173,10 +176,26 @@ class _BnAct:
         a1 = st.phys(self.relu1._weight)
         a2 = st.phys(self.relu2._weight) if (self.relu2 is not None and residual is not None) else None
         ops.bn_act_bwd_reduce(y, residual, tile, tile_c, gout, self.bnbuf, a1, a2, g, red)
-        ops.bn_act_bwd_apply(y, residual, tile, tile_c, gout, self.bnbuf, a1, a2, red, count, eng.bn_training_bwd,
-                             dy, dres, dres_acc, st.grad_phys(self.bn.weight), st.grad_phys(self.bn.bias),
-                             st.grad_phys(self.relu1._weight),
-                             st.grad_phys(self.relu2._weight) if a2 is not None else None, g)
+        dg, db = st.grad_phys(self.bn.weight), st.grad_phys(self.bn.bias)
+        da1 = st.grad_phys(self.relu1._weight)
+        da2 = st.grad_phys(self.relu2._weight) if a2 is not None else None
+        if eng.bn_training_bwd and eng.sync_world() > 1:
+            # SyncBatchNorm backward: the input gradient needs sum(g1), sum(g1*xhat) over ALL ranks, the parameter
+            # gradients stay per-rank sums (the data-parallel all-reduce averages them afterwards)
+            local = red.clone()
+            torch.distributed.all_reduce(red)
+            ops.bn_act_bwd_apply(y, residual, tile, tile_c, gout, self.bnbuf, a1, a2, red, count, True, dy, dres,
+                                 dres_acc, None, None, None, None, g)
+            c = y.c
+            lf = local.view(4, c).float()  # g == 1 in batch scope
+            db[:c] += lf[0]
+            dg[:c] += lf[1]
+            da1[:c] += lf[2]
+            if da2 is not None:
+                da2[:c] += lf[3]
+        else:
+            ops.bn_act_bwd_apply(y, residual, tile, tile_c, gout, self.bnbuf, a1, a2, red, count, eng.bn_training_bwd,
+                                 dy, dres, dres_acc, dg, db, da1, da2, g)
         self.saved = None
 
 
@@ -466,7 +485,7 @@ class VNet(_Module):
     def __init__(self, elu=False, in_channels=1, num_classes=4, pretrained=None,
                  kernel_size=((2, 2, 2), (2, 2, 2), (2, 2, 2), (2, 2, 2)),
                  stride_size=((2, 2, 2), (2, 2, 2), (2, 2, 2), (2, 2, 2)),
-                 compute_dtype="bf16", stat_scope="batch", device=None, seed=None):
+                 compute_dtype="bf16", stat_scope="batch", device=None, seed=None, sync_bn=False):
         super().__init__("")
         if elu:
             raise NotImplementedError("elu=True (nn.ELU) is not supported; the reference itself reports NaN gradients "
@@ -482,6 +501,10 @@ class VNet(_Module):
         self.device = torch.device(device or ("cuda:%d" % torch.cuda.current_device()))
         self.dtype = {"bf16": torch.bfloat16, "f32": torch.float32}[compute_dtype]
         self.stat_scope = stat_scope
+        # sync_bn=True: batch statistics over ALL ranks, the reference's behaviour at world > 1 (cvlibs/config.py:322
+        # converts every BatchNorm to SyncBatchNorm).  Costs two tiny f64 all-reduces per BN layer (forward sums,
+        # backward sums); the default keeps statistics per rank (north_star: "allreduce for the gradient step only").
+        self.sync_bn = bool(sync_bn)
         self.training = True
         self.bn_training_bwd = True
         self.param_version = 0
@@ -630,6 +653,13 @@ class VNet(_Module):
     # ---------------------------------------------------------------- helpers
     def groups(self, n):
         return 1 if self.stat_scope == "batch" else n
+
+    def sync_world(self):
+        """number of ranks the BatchNorm statistics are shared with (1 = per-rank statistics)"""
+        if not self.sync_bn or self.stat_scope != "batch":
+            return 1
+        d = torch.distributed
+        return d.get_world_size() if d.is_available() and d.is_initialized() else 1
 
     def scratch_f64(self, count):
         count = _pad(count, 2)

@@ -58,6 +58,48 @@ def k2s2(what, reps):
     print("%s: %.4f ms/call, %.1f MB algorithmic -> %.0f GB/s" % (what, ms, mb, mb / ms))
 
 
+def bn(what, reps):
+    """bn32: the BatchNorm + residual + PReLU kernels of up_tr32.ops[0] (32 channels @128^3, batch 2)"""
+    from medicalseg_b200 import ops
+    from medicalseg_b200.ops import B8
+    dev = torch.device("cuda", 0)
+    n, c, dims = 2, 32, (128, 128, 128)
+    mk = lambda: B8(n, c, dims, torch.bfloat16, device=dev)  # noqa: E731
+    y, r, out, go, dy, dres = mk(), mk(), mk(), mk(), mk(), mk()
+    for t in (y, r, go):
+        t.buf.normal_()
+    gamma, beta = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+    a1, a2 = torch.full((c,), 0.25, device=dev), torch.full((c,), 0.25, device=dev)
+    rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+    sums = torch.zeros(2 * c, dtype=torch.float64, device=dev)
+    ops.bn_stats(y, 1, sums)
+    bnbuf = torch.empty(4 * c, device=dev)
+    count = y.s * n
+    red = torch.zeros(4 * c, dtype=torch.float64, device=dev)
+    grads = [torch.zeros(c, device=dev) for _ in range(4)]
+    mb = y.buf.numel() * 2 / 1e6
+    cases = {
+        "fwd": (lambda: ops.bn_fwd_fused(y, out, r, None, 0, sums, count, gamma, beta, rm, rv, 0.9, 1e-5, True, bnbuf, a1,
+                                         a2, 1), 3 * mb),
+        "reduce": (lambda: ops.bn_act_bwd_reduce(y, r, None, 0, go, bnbuf, a1, a2, 1, red), 3 * mb),
+        "apply": (lambda: ops.bn_act_bwd_apply(y, r, None, 0, go, bnbuf, a1, a2, red, count, True, dy, dres, False,
+                                               *grads, 1), 5 * mb),
+    }
+    cases["fwd"][0]()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, (fn, mbytes) in cases.items():
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        print("bn %s 32ch @128^3 batch 2: %.4f ms, %.0f MB -> %.0f GB/s" % (name, ms, mbytes, mbytes / ms))
+
+
 def main():
     from medicalseg_b200 import ops
     from medicalseg_b200.ops import B8
@@ -65,6 +107,8 @@ def main():
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
     if what.startswith("k2"):
         return k2s2(what, reps)
+    if what.startswith("bn"):
+        return bn(what, reps)
     kind = "wgrad" if what.startswith("wgrad") else "fwd"
     c, e = CASES[what[len(kind):]]
     n, dims = 2, (e, e, e)
