@@ -34,8 +34,16 @@ struct Wg2Params {
                                          // one heavy + one light pass instead of two heavy ones
   float* ws;
   int kw_taps, kw_base;                  // 5 / 0 for the 5x5x5 kernel, 1 / 2 (centre tap only) for the 5x5x1 kernel
+  int csize;                             // cluster size: the (kh-group, kw-subset) passes of one (channel half, kd group)
+                                         // load identical tiles -> they run as ONE cluster sharing them by TMA multicast
 };
 
+// CL = true: launched in clusters of p.csize CTAs.  All CTAs of a cluster walk the same tiles of the same (channel half,
+// kd group) and differ only in the accumulators they own (kh group x kw subset = cluster rank); every TMA box is issued
+// by ONE rank and multicast to all, a stage is refilled once the MMAs of ALL ranks have consumed it (multicast
+// tcgen05.commit on the empty barriers).  L2 -> SM traffic drops by the cluster size (4.97 GB per launch for the 32 -> 32
+// layer at 128^3 before, ncu) - the kernel was bound by re-loading its tiles once per pass, not by the tensor pipe.
+template <bool CL>
 __global__ void __launch_bounds__(256, 1)
     conv_k5_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                           const Wg2Params p) {
@@ -49,8 +57,11 @@ __global__ void __launch_bounds__(256, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = ptx::smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const uint32_t crank = CL ? ptx::cluster_ctarank() : 0u;
+  const int csize = CL ? p.csize : 1;
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kW2Stages; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(3 + i), 1); }
+    for (int i = 0; i < kW2Stages; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(3 + i), (uint32_t)csize); }
     ptx::mbar_init(BAR(6), 1);
     ptx::mbar_init(BAR(7), 4);
     ptx::fence_mbar_init();
@@ -61,18 +72,30 @@ __global__ void __launch_bounds__(256, 1)
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (CL) ptx::cluster_sync();  // every CTA's barriers are initialised before any peer multicasts into them
   pdl_trigger();  // after our own TMEM allocation (common.cuh, PDL rules)
   pdl_wait();
 
-  const int num_items = p.num_passes * p.chunks;
+  // work items: CL = false: (pass, chunk) per CTA; CL = true: (channel half x kd group, chunk) per CLUSTER
+  const int num_items = CL ? p.mhalves * p.kd_groups * p.chunks : p.num_passes * p.chunks;
+  const int item0 = CL ? (int)blockIdx.x / csize : (int)blockIdx.x;
+  const int item_step = CL ? (int)gridDim.x / csize : (int)gridDim.x;
   const int tiles_per_n = p.d * p.tiles_h * p.tiles_w;
   auto decode_pass = [&](int pass_slot, int& mh, int& g, int& jg, int& kw0, int& kw1) {
-    const int pass = p.pass_order[pass_slot];
-    const int pg = pass % p.passes_per_group;
-    int r = pass / p.passes_per_group;
-    jg = r % p.jgroups; r /= p.jgroups;
-    g = r % p.kd_groups;
-    mh = r / p.kd_groups;
+    int pg;
+    if (CL) {  // pass_slot = channel half x kd group; the cluster rank picks (kh group, kw subset)
+      g = pass_slot % p.kd_groups;
+      mh = pass_slot / p.kd_groups;
+      pg = (int)crank % p.passes_per_group;
+      jg = (int)crank / p.passes_per_group;
+    } else {
+      const int pass = p.pass_order[pass_slot];
+      pg = pass % p.passes_per_group;
+      int r = pass / p.passes_per_group;
+      jg = r % p.jgroups; r /= p.jgroups;
+      g = r % p.kd_groups;
+      mh = r / p.kd_groups;
+    }
     kw0 = pg * p.units_per_pass;
     kw1 = min(p.kw_taps, kw0 + p.units_per_pass);
   };
@@ -81,7 +104,7 @@ __global__ void __launch_bounds__(256, 1)
     if (lane == 0) {
       uint32_t use = 0;
       const int x_planes = p.cin_m / 8;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      for (int item = item0; item < num_items; item += item_step) {
         const int pass = item / p.chunks, chunk = item % p.chunks;
         int mh, g, jg, kw0, kw1;
         decode_pass(pass, mh, g, jg, kw0, kw1);
@@ -97,12 +120,23 @@ __global__ void __launch_bounds__(256, 1)
           const uint32_t s = use % kW2Stages, ph = (use / kW2Stages) & 1;
           ptx::mbar_wait(BAR(3 + s), ph ^ 1);
           ptx::mbar_expect_tx(BAR(s), bytes);
-          for (int q = 0; q < planes_valid; ++q)
-            ptx::tma_load_4d(ptx::smem_u32(x_smem + s * kW2XBytes + q * x_planes * kW2GroupBytes), &tmap_x, BAR(s),
-                             (tw * kW2TileW - 2) * 8, th * kW2TileH, d + g * p.qm + q - 2,
-                             n * p.x_c8_total + mh * 16);
-          ptx::tma_load_4d(ptx::smem_u32(dy_smem + s * p.dy_stage_bytes), &tmap_dy, BAR(s), tw * kW2TileW * 8,
-                           n * p.dy_c8_total, th * kW2TileH - 2, d);
+          if (CL) {  // box i of the tile (planes_valid X planes + the dY tile) is issued by rank i % csize for everyone
+            for (int q = 0; q < planes_valid; ++q)
+              if ((uint32_t)(q % csize) == crank)
+                ptx::tma_load_4d_mc(ptx::smem_u32(x_smem + s * kW2XBytes + q * x_planes * kW2GroupBytes), &tmap_x, BAR(s),
+                                    (tw * kW2TileW - 2) * 8, th * kW2TileH, d + g * p.qm + q - 2,
+                                    n * p.x_c8_total + mh * 16, cmask);
+            if ((uint32_t)(planes_valid % csize) == crank)
+              ptx::tma_load_4d_mc(ptx::smem_u32(dy_smem + s * p.dy_stage_bytes), &tmap_dy, BAR(s), tw * kW2TileW * 8,
+                                  n * p.dy_c8_total, th * kW2TileH - 2, d, cmask);
+          } else {
+            for (int q = 0; q < planes_valid; ++q)
+              ptx::tma_load_4d(ptx::smem_u32(x_smem + s * kW2XBytes + q * x_planes * kW2GroupBytes), &tmap_x, BAR(s),
+                               (tw * kW2TileW - 2) * 8, th * kW2TileH, d + g * p.qm + q - 2,
+                               n * p.x_c8_total + mh * 16);
+            ptx::tma_load_4d(ptx::smem_u32(dy_smem + s * p.dy_stage_bytes), &tmap_dy, BAR(s), tw * kW2TileW * 8,
+                             n * p.dy_c8_total, th * kW2TileH - 2, d);
+          }
         }
       }
     }
@@ -115,7 +149,7 @@ __global__ void __launch_bounds__(256, 1)
     const uint32_t b_row16 = (uint32_t)(p.dyp * kW2RowBytes) >> 4;  // one h row of the dY tile, 16-byte units
     const uint32_t npad = (uint32_t)p.npad;
     uint32_t use = 0, iuse = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
+    for (int item = item0; item < num_items; item += item_step, ++iuse) {
       const int pass = item / p.chunks, chunk = item % p.chunks;
       int mh, g, jg, kw0, kw1;
       decode_pass(pass, mh, g, jg, kw0, kw1);
@@ -141,7 +175,10 @@ __global__ void __launch_bounds__(256, 1)
                                   b_hi, idesc, acc);
           }
         }
-        if (leader) ptx::mma_commit(BAR(3 + s));
+        if (leader) {
+          if (CL) ptx::mma_commit_mc(BAR(3 + s), cmask);  // the stage is shared: free once every rank's MMAs retired
+          else ptx::mma_commit(BAR(3 + s));
+        }
       }
       if (leader) ptx::mma_commit(BAR(6));
       __syncwarp();
@@ -152,7 +189,7 @@ __global__ void __launch_bounds__(256, 1)
     const int qplane = row / p.cin_m, ci_local = row % p.cin_m;
     const int cw = 8 * p.dyp;  // channels per stacked kh group
     uint32_t iuse = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
+    for (int item = item0; item < num_items; item += item_step, ++iuse) {
       const int pass = item / p.chunks;
       int mh, g, jg, kw0, kw1;
       decode_pass(pass, mh, g, jg, kw0, kw1);
@@ -189,6 +226,7 @@ __global__ void __launch_bounds__(256, 1)
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL) ptx::cluster_sync();  // no CTA may exit while a peer can still multicast into it or signal its barriers
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem_base);
@@ -257,14 +295,41 @@ int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin
   int rc;
   if ((rc = make_b8_tmap(&tmx, x, n, dims, kW2TileW + 4, kW2TileH, 1, p.cin_m / 8))) return rc;
   if ((rc = make_b8_tmap_hmajor(&tmdy, dy, n, dims, kW2TileW, dyp, kW2TileH + 4, 1))) return rc;
+  // cluster path: the jgroups x passes_per_group passes of one (channel half, kd group) share their tiles
+  int csize = p.jgroups * p.passes_per_group;
+  if (g_debug_flags[6] & 2) csize = 1;  // msb_debug_set(6, 2): force the unclustered kernel (A/B measurements)
+  const int groups = p.mhalves * p.kd_groups;
+  if (csize >= 2 && csize <= 8 && (kNumSMs / csize) >= groups && p.total_tiles >= 8 * (kNumSMs / csize)) {
+    const int nclusters = kNumSMs / csize;
+    int chunks = nclusters / groups;  // one (group, chunk) item per cluster
+    if (chunks > p.total_tiles) chunks = p.total_tiles;
+    p.tiles_per_chunk = (p.total_tiles + chunks - 1) / chunks;
+    p.chunks = (p.total_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+    p.csize = csize;
+    const int items = groups * p.chunks;
+    const int grid = (items < nclusters ? items : nclusters) * csize;
+    static bool attr_set_cl = false;
+    if (!attr_set_cl) {
+      MSB_CUDA_OK(cudaFuncSetAttribute(conv_k5_wgrad2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set_cl = true;
+    }
+    cudaError_t e = launch_pdl_cluster(conv_k5_wgrad2_kernel<true>, dim3(grid), dim3(256), smem_bytes, st, csize, tmx,
+                                       tmdy, p);
+    if (e != cudaSuccess) {
+      set_error("clustered wgrad launch failed: %s", cudaGetErrorString(e));
+      return MSB_ERR_CUDA;
+    }
+    return MSB_OK;
+  }
+  p.csize = 1;
   const int items = p.num_passes * p.chunks;
   const int grid = items < kNumSMs ? items : kNumSMs;
   static bool attr_set = false;
   if (!attr_set) {
-    MSB_CUDA_OK(cudaFuncSetAttribute(conv_k5_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MSB_CUDA_OK(cudaFuncSetAttribute(conv_k5_wgrad2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  MSB_LAUNCH_PDL(conv_k5_wgrad2_kernel, dim3(grid), dim3(256), smem_bytes, st, tmx, tmdy, p);
+  MSB_LAUNCH_PDL(conv_k5_wgrad2_kernel<false>, dim3(grid), dim3(256), smem_bytes, st, tmx, tmdy, p);
   return MSB_OK;
 }
 
