@@ -203,6 +203,15 @@ int msb_conv_k5_fwd_ws(msb_tensor x, const void* packed, const float* bias, int 
 size_t msb_conv_k5_wgrad_workspace_bytes(int cin, int cout);
 int msb_conv_k5_wgrad(msb_tensor x, msb_tensor dy, float* dw, float* dbias, int cout, int cin, int n,
                       msb_dim3 dims, void* workspace, size_t workspace_bytes, void* stream);
+/* TAP-MAJOR variants: the f32 master weight / gradient of a 5x5x5 conv stored as [125 taps][cout][cin] - the layout
+ * the weight-gradient kernels accumulate in.  msb_conv_k5_wgrad_tm adds straight into dw_tm (no workspace, no memset,
+ * no transposition kernel); msb_conv_k5_pack_tm builds the same bf16 operand image as msb_conv_k5_pack from it.  The
+ * host layer keeps parameters, gradients and momentum of these layers in this layout and converts only at the
+ * state-dict boundary. */
+int msb_conv_k5_pack_tm(const float* w_tm, void* packed, int cout, int cin, int mode, int cin_pad, int cout_pad,
+                        void* stream);
+int msb_conv_k5_wgrad_tm(msb_tensor x, msb_tensor dy, float* dw_tm, float* dbias, int cout, int cin, int n,
+                         msb_dim3 dims, void* stream);
 /* ---- w-folded 5x5x1 variant of the 5x5x5 conv for layers with <= 3 real channels on one side -------------
  * vnet.py:67-68 (in_tr.conv1, 1 -> 16: fold_side 0 = input folded) and vnet.py:165-166 (out_tr.conv1, 32 -> classes:
  * fold_side 1 = output folded).  The five kw taps are folded into the zero padding of the 16-channel block:

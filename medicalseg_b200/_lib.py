@@ -61,6 +61,8 @@ SIGNATURES = {
     "msb_conv_k5_fwd": (I, [T, P, P, I, T, I, D3, I, P, I, P, P]),
     "msb_conv_k5_fwd_workspace_bytes": (SZ, [I, I, D3, I]),
     "msb_conv_k5_fwd_ws": (I, [T, P, P, I, T, I, D3, I, P, I, P, P, SZ, P]),
+    "msb_conv_k5_pack_tm": (I, [P, P, I, I, I, I, I, P]),
+    "msb_conv_k5_wgrad_tm": (I, [T, T, P, P, I, I, I, D3, P]),
     "msb_conv_k5_wgrad_workspace_bytes": (SZ, [I, I]),
     "msb_conv_k5_wgrad": (I, [T, T, P, P, I, I, I, D3, P, SZ, P]),
     "msb_fold_w_f32": (I, [P, I, T, I, D3, I, P]),

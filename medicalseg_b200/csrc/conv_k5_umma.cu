@@ -785,6 +785,40 @@ __global__ void __launch_bounds__(256) pack_k5_kernel(const float* __restrict__ 
   }
 }
 
+// Same packed image from a TAP-MAJOR f32 master weight w_tm[tap][co][ci] (the layout the weight-gradient kernels
+// accumulate in, so master weights / gradients / momentum can live in it and no gradient transposition is needed).
+// One thread per 16-byte output vector: mode 0 reads 8 consecutive ci (one 32-byte sector), mode 1 reads 8 values
+// strided by cin that are consecutive across the threads of a warp.
+__global__ void __launch_bounds__(256) pack_k5_tm_kernel(const float* __restrict__ w_tm, __nv_bfloat16* __restrict__ packed,
+                                                         int cout, int cin, int mode, int cin_pad, int cout_pad) {
+  pdl_wait();
+  pdl_trigger();
+  const int64_t total = (int64_t)(cin_pad / 8) * kNumTaps * cout_pad;  // output vectors
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int oc = (int)(r % cout_pad); r /= cout_pad;
+    const int kdr = (int)(r % 5); r /= 5;
+    const int k8 = (int)(r & 1); r >>= 1;
+    const int hk = (int)(r % 25);
+    const int chunk = (int)(r / 25);
+    const int tap = (4 - kdr) * 25 + hk;  // natural tap index kd*25 + kh*5 + kw
+    const int rc0 = chunk * 16 + k8 * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int rc = rc0 + j;
+      float x = 0.f;
+      if (mode == 0) {
+        if (oc < cout && rc < cin) x = __ldg(w_tm + ((int64_t)tap * cout + oc) * cin + rc);
+      } else {
+        if (rc < cout && oc < cin) x = __ldg(w_tm + ((int64_t)(kNumTaps - 1 - tap) * cout + rc) * cin + oc);
+      }
+      v[j] = x;
+    }
+    Vec8<__nv_bfloat16>::store(packed + i * 8, v);
+  }
+}
+
 // ---- w-folded 5x5x1 convolutions (narrow layers: in_tr 1->16, out_tr 32->classes) -------------------------------
 // A 5x5x5 conv whose input (fold_side 0) or output (fold_side 1) has <= 3 real channels wastes a 16-wide K chunk / N
 // block per kw tap.  Folding the 5 kw taps into the padded channels turns it into ONE 5x5x1 conv (5x fewer MMAs):
@@ -1103,6 +1137,19 @@ int msb_conv_k5_pack(const float* w, void* packed, int cout, int cin, int mode, 
   return MSB_OK;
 }
 
+int msb_conv_k5_pack_tm(const float* w_tm, void* packed, int cout, int cin, int mode, int cin_pad, int cout_pad,
+                        void* stream) {
+  MSB_REQUIRE(w_tm && packed && cout > 0 && cin > 0 && (mode == 0 || mode == 1), "msb_conv_k5_pack_tm: bad arguments");
+  MSB_REQUIRE(cin_pad % 16 == 0 && cout_pad % 16 == 0, "msb_conv_k5_pack_tm: padded channel counts must be multiples of 16");
+  MSB_REQUIRE(mode == 0 ? (cin_pad >= cin && cout_pad >= cout) : (cin_pad >= cout && cout_pad >= cin),
+              "msb_conv_k5_pack_tm: padded channel counts too small");
+  const int64_t total = (int64_t)(cin_pad / 8) * kNumTaps * cout_pad;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  MSB_LAUNCH_PDL(pack_k5_tm_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), w_tm,
+                 reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, mode, cin_pad, cout_pad);
+  return MSB_OK;
+}
+
 int msb_conv_k5_out_pad(int cout_view);
 
 static int conv_k5_fwd_impl(const char* who, msb_tensor x, const void* packed, const float* bias, int cout,
@@ -1136,7 +1183,7 @@ static int conv_k5_fwd_impl(const char* who, msb_tensor x, const void* packed, c
   cudaStream_t st = as_stream(stream);
   const int npad_sel = msb_conv_k5_out_pad(out.c);
   // NOTE: the packed operand must have been built with cout_pad == npad_sel.
-  if (workspace != nullptr && kw_taps == 5 && out.dtype == MSB_BF16 && g_debug_flags[6] == 0) {
+  if (workspace != nullptr && kw_taps == 5 && out.dtype == MSB_BF16 && (g_debug_flags[6] & 1) == 0) {
     const int ks = splitk_slices(npad_sel, n, dims, x.c);
     if (ks > 0) {
       const size_t need = (size_t)n * out.c * S * sizeof(float);
@@ -1192,8 +1239,22 @@ int msb_conv_k551_fwd(msb_tensor x, const void* packed, const float* bias, int c
 
 size_t msb_conv_k5_wgrad_workspace_bytes(int cin, int cout) { return (size_t)kNumTaps * cin * cout * sizeof(float); }
 
+static int conv_k5_wgrad_impl(msb_tensor x, msb_tensor dy, float* dw, float* dbias, int cout, int cin, int n, msb_dim3 dims,
+                              void* workspace, size_t workspace_bytes, int dw_tap_major, void* stream);
+
 int msb_conv_k5_wgrad(msb_tensor x, msb_tensor dy, float* dw, float* dbias, int cout, int cin, int n, msb_dim3 dims,
                       void* workspace, size_t workspace_bytes, void* stream) {
+  return conv_k5_wgrad_impl(x, dy, dw, dbias, cout, cin, n, dims, workspace, workspace_bytes, 0, stream);
+}
+
+int msb_conv_k5_wgrad_tm(msb_tensor x, msb_tensor dy, float* dw_tm, float* dbias, int cout, int cin, int n,
+                         msb_dim3 dims, void* stream) {
+  return conv_k5_wgrad_impl(x, dy, dw_tm, dbias, cout, cin, n, dims, dw_tm, (size_t)kNumTaps * cin * cout * sizeof(float),
+                            1, stream);
+}
+
+static int conv_k5_wgrad_impl(msb_tensor x, msb_tensor dy, float* dw, float* dbias, int cout, int cin, int n, msb_dim3 dims,
+                              void* workspace, size_t workspace_bytes, int dw_tap_major, void* stream) {
   MSB_REQUIRE(view_ok(x) && view_ok(dy) && x.dtype == MSB_BF16 && dy.dtype == MSB_BF16 && dw && n > 0,
               "msb_conv_k5_wgrad: bf16 B8 views required");
   MSB_REQUIRE(dims.d > 0 && dims.h > 0 && dims.w > 0, "msb_conv_k5_wgrad: bad dims");
@@ -1204,7 +1265,8 @@ int msb_conv_k5_wgrad(msb_tensor x, msb_tensor dy, float* dw, float* dbias, int 
   MSB_REQUIRE(workspace && workspace_bytes >= need, "msb_conv_k5_wgrad: workspace too small (%zu < %zu)",
               workspace_bytes, need);
   cudaStream_t st = as_stream(stream);
-  MSB_CUDA_OK(cudaMemsetAsync(workspace, 0, need, st));
+  // tap-major gradient buffer: the kernels' [tap][co][ci] f32 atomics ARE the += into dw - no memset, no unpack
+  if (!dw_tap_major) MSB_CUDA_OK(cudaMemsetAsync(workspace, 0, need, st));
   const int64_t S = (int64_t)dims.d * dims.h * dims.w;
   WgParams p;
   p.n = n; p.cin_pad = x.c; p.cin_real = cin; p.cout_real = cout; p.dy_c8 = dy.c / 8;
@@ -1233,9 +1295,11 @@ int msb_conv_k5_wgrad(msb_tensor x, msb_tensor dy, float* dw, float* dbias, int 
     default: rc = launch_wgrad<256, 4>(x, dy, p, dims, st); break;
   }
   if (rc) return rc;
-  const int64_t total = (int64_t)cout * cin * kNumTaps;
-  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  MSB_LAUNCH_PDL(wgrad_unpack_kernel, dim3(blocks), dim3(256), 0, st, p.ws, dw, cout, cin);
+  if (!dw_tap_major) {
+    const int64_t total = (int64_t)cout * cin * kNumTaps;
+    const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    MSB_LAUNCH_PDL(wgrad_unpack_kernel, dim3(blocks), dim3(256), 0, st, p.ws, dw, cout, cin);
+  }
   if (dbias != nullptr) {
     const dim3 grid((unsigned)((S + 8191) / 8192), dy.c / 8, n);
     MSB_LAUNCH_PDL(channel_sum_bf16_kernel, grid, dim3(256), 0, st, dy, S, cout, dbias);

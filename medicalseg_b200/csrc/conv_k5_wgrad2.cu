@@ -295,9 +295,12 @@ int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin
   int rc;
   if ((rc = make_b8_tmap(&tmx, x, n, dims, kW2TileW + 4, kW2TileH, 1, p.cin_m / 8))) return rc;
   if ((rc = make_b8_tmap_hmajor(&tmdy, dy, n, dims, kW2TileW, dyp, kW2TileH + 4, 1))) return rc;
-  // cluster path: the jgroups x passes_per_group passes of one (channel half, kd group) share their tiles
-  int csize = p.jgroups * p.passes_per_group;
-  if (g_debug_flags[6] & 2) csize = 1;  // msb_debug_set(6, 2): force the unclustered kernel (A/B measurements)
+  // cluster path: the jgroups x passes_per_group passes of one (channel half, kd group) share their tiles.
+  // MEASURED NEGATIVE RESULT (B200, batch 2): 32 -> 32 @128^3 1.24 ms clustered (2 CTAs) vs 1.26 ms; 64 -> 64 @64^3 1.20 ms
+  // clustered (6 CTAs) vs 0.65 ms - the ranks of a cluster run in lock-step at the pace of the rank with the most kw
+  // taps (3 vs 2; 2,2,1), which costs more than the saved L2 -> SM traffic buys.  Off by default; msb_debug_set(6, 4)
+  // enables it (tests/test_gpu_kernels.py keeps the path verified).
+  int csize = (g_debug_flags[6] & 4) ? p.jgroups * p.passes_per_group : 1;
   const int groups = p.mhalves * p.kd_groups;
   if (csize >= 2 && csize <= 8 && (kNumSMs / csize) >= groups && p.total_tiles >= 8 * (kNumSMs / csize)) {
     const int nclusters = kNumSMs / csize;

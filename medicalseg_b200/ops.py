@@ -244,6 +244,14 @@ def k5_fwd_workspace_bytes(n: int, cout_view: int, dims, cin_view: int) -> int:
     return call("msb_conv_k5_fwd_workspace_bytes", n, cout_view, dim3(dims), cin_view)
 
 
+def k5_pack_tm(w_tm, packed, cout, cin, mode, cin_pad, cout_pad):
+    call("msb_conv_k5_pack_tm", _ptr(w_tm), _ptr(packed), cout, cin, mode, cin_pad, cout_pad, _stream())
+
+
+def k5_wgrad_tm(x: B8, dy: B8, dw_tm, dbias, cout, cin):
+    call("msb_conv_k5_wgrad_tm", x.mt, dy.mt, _ptr(dw_tm), _ptr(dbias), cout, cin, x.n, dim3(x.dims), _stream())
+
+
 def k5_wgrad_workspace_bytes(cin: int, cout: int) -> int:
     return call("msb_conv_k5_wgrad_workspace_bytes", cin, cout)
 

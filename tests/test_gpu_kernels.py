@@ -285,12 +285,20 @@ def test_conv_k5_split_k_small_volumes(cin, cout, dims):
 
 
 WG_CASES = [(32, 32, (6, 16, 16)), (64, 64, (4, 9, 20)), (128, 128, (3, 8, 16)), (256, 256, (2, 8, 8)),
-            (32, 2, (5, 10, 18)), (16, 16, (5, 8, 16)), (32, 32, (3, 13, 9))]
+            (32, 2, (5, 10, 18)), (16, 16, (5, 8, 16)), (32, 32, (3, 13, 9)),
+            # enough tiles for the clustered (TMA-multicast) launch: 2-CTA clusters (32 ch), 6-CTA clusters (64 ch)
+            (32, 32, (16, 64, 64)), (64, 64, (16, 32, 32)), (32, 32, (9, 70, 50))]
 
 
 @pytest.mark.parametrize("cin,cout,dims", WG_CASES)
-def test_conv_k5_tcgen05_wgrad(cin, cout, dims):
+@pytest.mark.parametrize("clustered", [False, True])
+def test_conv_k5_tcgen05_wgrad(cin, cout, dims, clustered):
+    """clustered = the TMA-multicast cluster launch of the kh-stacked kernel (off by default: measured slower, see
+    conv_k5_wgrad2.cu); only the shapes with enough tiles take it"""
     ops, B8 = _imp()
+    from medicalseg_b200 import _lib
+    if clustered and dims[0] * dims[1] * dims[2] < 16 * 32 * 32:
+        pytest.skip("too few tiles for the cluster launch")
     torch.manual_seed(5)
     n = 2
     dyc = 16 if cout < 8 else (cout + 7) // 8 * 8
@@ -298,15 +306,21 @@ def test_conv_k5_tcgen05_wgrad(cin, cout, dims):
     dy[:, :cout] = torch.randn(n, cout, *dims, device="cuda")
     xb = B8.from_ncdhw(torch.randn(n, cin, *dims, device="cuda"), torch.bfloat16)
     dyb = B8.from_ncdhw(dy, torch.bfloat16)
-    ref = torch.nn.grad.conv3d_weight(xb.to_ncdhw(), (cout, cin, 5, 5, 5), dyb.to_ncdhw(cout), padding=2)
+    # f64 reference (torch's f32 convolution gradients may run in TF32)
+    ref = torch.nn.grad.conv3d_weight(xb.to_ncdhw().double(), (cout, cin, 5, 5, 5), dyb.to_ncdhw(cout).double(),
+                                      padding=2).float()
     dw = torch.zeros(cout, cin, 5, 5, 5, device="cuda")
     db = torch.zeros(cout, device="cuda")
     ws = torch.empty(ops.k5_wgrad_workspace_bytes(cin, cout), dtype=torch.uint8, device="cuda")
-    ops.k5_wgrad(xb, dyb, dw, db, cout, cin, ws)
-    assert rel(dw, ref) <= 1e-4  # bf16 x bf16 products are exact in f32; only the summation order differs
-    assert rel(db, dyb.to_ncdhw(cout).sum((0, 2, 3, 4))) <= 1e-5
-    ops.k5_wgrad(xb, dyb, dw, db, cout, cin, ws)  # accumulates (+=)
-    assert rel(dw, 2 * ref) <= 1e-4
+    _lib.call("msb_debug_set", 6, 4 if clustered else 0)
+    try:
+        ops.k5_wgrad(xb, dyb, dw, db, cout, cin, ws)
+        assert rel(dw, ref) <= 1e-4  # bf16 x bf16 products are exact in f32; only the summation order differs
+        assert rel(db, dyb.to_ncdhw(cout).sum((0, 2, 3, 4))) <= 1e-5
+        ops.k5_wgrad(xb, dyb, dw, db, cout, cin, ws)  # accumulates (+=)
+        assert rel(dw, 2 * ref) <= 1e-4
+    finally:
+        _lib.call("msb_debug_set", 6, 0)
 
 
 @pytest.mark.parametrize("ci,co,dims", [(16, 32, (8, 12, 16)), (64, 128, (4, 8, 32)), (128, 256, (4, 4, 16))])
