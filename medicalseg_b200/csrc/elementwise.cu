@@ -637,11 +637,14 @@ __global__ void __launch_bounds__(kThreads) conv1x1_fwd_kernel(msb_tensor a, con
   }
 }
 
-constexpr int kHeadTile = 128;     // voxels staged per inner step of the backward kernel
-constexpr int kHeadThreads = 512;  // threads 0..127: one voxel each (da); all threads: one (o, i) weight pair each
+constexpr int kHeadThreads = 512;  // phase 1: one voxel per thread (da); phase 2: one (o, i) weight pair per thread
+constexpr int kHeadTile = 512;     // voxels staged per inner step of the backward kernel
+constexpr int kHeadPitch = kHeadTile + 1;
+template <int CI8>
+constexpr int head_bwd_smem() { return (CI8 * 8 + kHeadMaxC) * kHeadPitch * (int)sizeof(float); }
 
-// dlogits -> da (B8) and dW / db.  Phase 1: threads < 128 load one voxel, write da and stage (a, dlogits) in shared
-// memory.  Phase 2: thread t < co*ci + co owns ONE weight (or bias) gradient and runs over the 128 staged voxels with
+// dlogits -> da (B8) and dW / db.  Phase 1: every thread loads one voxel, writes da and stages (a, dlogits) in shared
+// memory.  Phase 2: thread t < co*ci + co owns ONE weight (or bias) gradient and runs over the 512 staged voxels with
 // broadcast shared-memory reads - no shuffles, no per-pair warp reductions (the C = 20 MRI head has 420 pairs).
 template <typename T, int CI8>
 __global__ void __launch_bounds__(kHeadThreads)
@@ -650,8 +653,9 @@ __global__ void __launch_bounds__(kHeadThreads)
   pdl_wait();
   pdl_trigger();
   __shared__ __align__(16) float ws[kHeadMaxC][CI8 * 8];  // W[o][i], rows zero-padded to the plane width
-  __shared__ float as[CI8 * 8][kHeadTile + 1];
-  __shared__ float ds[kHeadMaxC][kHeadTile + 1];
+  extern __shared__ float head_smem[];
+  float (*as)[kHeadPitch] = reinterpret_cast<float (*)[kHeadPitch]>(head_smem);                          // [CI8*8]
+  float (*ds)[kHeadPitch] = reinterpret_cast<float (*)[kHeadPitch]>(head_smem + CI8 * 8 * kHeadPitch);   // [kHeadMaxC]
   for (int i = threadIdx.x; i < kHeadMaxC * CI8 * 8; i += kHeadThreads) {
     const int o = i / (CI8 * 8), c = i % (CI8 * 8);
     ws[o][c] = (o < co && c < ci) ? w[o * ci + c] : 0.f;
@@ -667,7 +671,7 @@ __global__ void __launch_bounds__(kHeadThreads)
   // grid-stride over 128-voxel tiles: the launch uses a few blocks per SM, so the final atomics (all blocks hit the
   // same <= 1056 addresses - a few cache lines) stay in the low hundreds per address
   for (int64_t base = (int64_t)blockIdx.x * kHeadTile; base < s; base += (int64_t)gridDim.x * kHeadTile) {
-    if (threadIdx.x < kHeadTile) {
+    {
       const int64_t v = base + threadIdx.x;
       const bool valid = v < s;
 #pragma unroll
@@ -951,12 +955,24 @@ int msb_conv1x1_bwd(msb_tensor a, const float* w, const float* dlogits, msb_tens
   if (gx > cap) gx = cap;
   const dim3 grid((unsigned)gx, 1, (unsigned)n);
   cudaStream_t st = as_stream(stream);
+#define MSB_HEAD_BWD(CI8_)                                                                                          \
+  do {                                                                                                              \
+    static bool _attr = false;                                                                                      \
+    if (!_attr) {                                                                                                   \
+      MSB_CUDA_OK(cudaFuncSetAttribute(conv1x1_bwd_kernel<T, CI8_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                       head_bwd_smem<CI8_>()));                                                    \
+      _attr = true;                                                                                                 \
+    }                                                                                                               \
+    MSB_LAUNCH_PDL((conv1x1_bwd_kernel<T, CI8_>), grid, dim3(kHeadThreads), head_bwd_smem<CI8_>(), st, a, w, dlogits, \
+                   da, dw, db, ci, co, s);                                                                          \
+  } while (0)
   MSB_DISPATCH_DTYPE(a.dtype, {
-    if (a.c == 8) MSB_LAUNCH_PDL((conv1x1_bwd_kernel<T, 1>), grid, dim3(kHeadThreads), 0, st, a, w, dlogits, da, dw, db, ci, co, s);
-    else if (a.c == 16) MSB_LAUNCH_PDL((conv1x1_bwd_kernel<T, 2>), grid, dim3(kHeadThreads), 0, st, a, w, dlogits, da, dw, db, ci, co, s);
-    else if (a.c == 24) MSB_LAUNCH_PDL((conv1x1_bwd_kernel<T, 3>), grid, dim3(kHeadThreads), 0, st, a, w, dlogits, da, dw, db, ci, co, s);
-    else MSB_LAUNCH_PDL((conv1x1_bwd_kernel<T, 4>), grid, dim3(kHeadThreads), 0, st, a, w, dlogits, da, dw, db, ci, co, s);
+    if (a.c == 8) MSB_HEAD_BWD(1);
+    else if (a.c == 16) MSB_HEAD_BWD(2);
+    else if (a.c == 24) MSB_HEAD_BWD(3);
+    else MSB_HEAD_BWD(4);
   });
+#undef MSB_HEAD_BWD
   MSB_LAUNCH_OK();
   return MSB_OK;
 }

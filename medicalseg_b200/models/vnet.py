@@ -34,13 +34,16 @@ def _pad(c: int, m: int) -> int:
 # zero-padded channel counts never read out of bounds.
 # =========================================================================================================
 class _Slot:
-    __slots__ = ("name", "shape", "numel", "phys", "offset", "is_buffer", "init")
+    __slots__ = ("name", "shape", "numel", "phys", "offset", "is_buffer", "init", "tap_major")
 
     def __init__(self, name, shape, phys, is_buffer, init):
         self.name, self.shape, self.is_buffer, self.init = name, tuple(shape), is_buffer, init
         self.numel = int(np.prod(shape))
         self.phys = _pad(max(phys, self.numel), 4)
         self.offset = -1
+        # tap_major: a [co][ci][5][5][5] conv weight physically stored as [125][co][ci] - the layout the tensor-core
+        # weight-gradient kernels accumulate in (parameters, gradients and momentum share it; `view` permutes back)
+        self.tap_major = False
 
 
 class ParamStore:
@@ -66,9 +69,27 @@ class ParamStore:
     def _base(self, s: _Slot):
         return self.buffers if s.is_buffer else self.flat
 
-    def view(self, name) -> torch.Tensor:
+    def view_of(self, base: torch.Tensor, name) -> torch.Tensor:
+        """the slot of `name` inside any flat buffer laid out like the parameters (params, grads, momentum), in the
+        reference (Paddle) shape; for tap-major slots this is a permuted, non-contiguous VIEW of the same memory"""
         s = self.slots[name]
-        return self._base(s)[s.offset:s.offset + s.numel].view(s.shape)
+        flat = base[s.offset:s.offset + s.numel]
+        if s.tap_major:
+            co, ci = s.shape[:2]
+            return flat.view(-1, co, ci).permute(1, 2, 0).unflatten(2, s.shape[2:])
+        return flat.view(s.shape)
+
+    def view(self, name) -> torch.Tensor:
+        return self.view_of(self._base(self.slots[name]), name)
+
+    def raw(self, name) -> torch.Tensor:
+        """physical 1-D storage of the slot (what the kernels of a tap-major layer read)"""
+        s = self.slots[name]
+        return self._base(s)[s.offset:s.offset + s.numel]
+
+    def grad_raw(self, name) -> torch.Tensor:
+        s = self.slots[name]
+        return self.grad[s.offset:s.offset + s.numel]
 
     def phys(self, name) -> torch.Tensor:
         """physical (zero-padded) 1-D slot, what kernels index"""
@@ -76,8 +97,7 @@ class ParamStore:
         return self._base(s)[s.offset:s.offset + s.phys]
 
     def grad_view(self, name) -> torch.Tensor:
-        s = self.slots[name]
-        return self.grad[s.offset:s.offset + s.numel].view(s.shape)
+        return self.view_of(self.grad, name)
 
     def grad_phys(self, name) -> torch.Tensor:
         s = self.slots[name]
@@ -202,13 +222,17 @@ class _BnAct:
 class _K5:
     """5x5x5 pad-2 conv: tcgen05 kernels for bf16, direct kernels for the f32 parity path."""
 
-    def __init__(self, eng, conv: _Conv, cin, cout):
+    def __init__(self, eng, conv: _Conv, cin, cout, tap_major=True):
         self.eng, self.conv, self.cin, self.cout = eng, conv, cin, cout
         self.packed_f = self.packed_b = None
         self.packed_version = -1
         self.pack_args = None   # remembered after the first (lazy) pack: lets the engine re-pack ahead of use
         self.pack_event = None  # set when the last pack ran on the engine's side stream
         eng.register_packer(self)
+        # bf16 engine: master weight / gradient / momentum of this layer live tap-major ([125][co][ci]), so the weight-
+        # gradient atomics land in the gradient buffer itself (no workspace memset, no transposition kernel)
+        self.tap_major = bool(tap_major) and eng.dtype == torch.bfloat16
+        eng.store.slots[conv.weight].tap_major = self.tap_major
 
     def repack(self):
         self._pack(*self.pack_args)
@@ -229,8 +253,13 @@ class _K5:
             self.bk_cin_pad, self.bk_cout_pad = _pad(out_c, 16), ops.k5_out_pad(x_c)
             self.packed_b = torch.empty(ops.k5_packed_bytes(self.bk_cin_pad, self.bk_cout_pad), dtype=torch.uint8,
                                         device=dev)
-        ops.k5_pack(w, self.packed_f, self.cout, self.cin, 0, cin_pad, cout_pad)
-        ops.k5_pack(w, self.packed_b, self.cout, self.cin, 1, self.bk_cin_pad, self.bk_cout_pad)
+        if self.tap_major:
+            w = st.raw(self.conv.weight)
+            ops.k5_pack_tm(w, self.packed_f, self.cout, self.cin, 0, cin_pad, cout_pad)
+            ops.k5_pack_tm(w, self.packed_b, self.cout, self.cin, 1, self.bk_cin_pad, self.bk_cout_pad)
+        else:
+            ops.k5_pack(w, self.packed_f, self.cout, self.cin, 0, cin_pad, cout_pad)
+            ops.k5_pack(w, self.packed_b, self.cout, self.cin, 1, self.bk_cin_pad, self.bk_cout_pad)
         self.packed_version = eng.param_version
 
     def fwd(self, x: B8, out: B8, sums):
@@ -253,7 +282,10 @@ class _K5:
             if dx is not None:
                 ops.k5_fwd(dy, self.packed_b, None, self.cin, dx, accumulate, ch_scale, 1, None,
                            eng.splitk_workspace(dy.n, dx.c, dy.dims, dy.c))
-            ops.k5_wgrad(x, dy, dw, db, self.cout, self.cin, eng.wgrad_workspace(self.cin, self.cout))
+            if self.tap_major:
+                ops.k5_wgrad_tm(x, dy, st.grad_raw(self.conv.weight), db, self.cout, self.cin)
+            else:
+                ops.k5_wgrad(x, dy, dw, db, self.cout, self.cin, eng.wgrad_workspace(self.cin, self.cout))
         else:
             if dx is not None:
                 if ch_scale is None:
@@ -458,7 +490,7 @@ class OutputTransition(_Module):  # vnet.py:159-175
         self.conv2 = _Conv(st, prefix + ".conv2", (num_classes, num_classes, 1, 1, 1), num_classes,
                            ("conv", num_classes))
         self.relu1 = _PReLU(st, prefix + ".relu1", num_classes, self.cp)
-        self.k5 = _K5(eng, self.conv1, in_channels, num_classes)
+        self.k5 = _K5(eng, self.conv1, in_channels, num_classes, tap_major=not self.folded)  # folded: Paddle layout
         self.k551 = _K551(eng, self.conv1, in_channels, num_classes, 1) if self.folded else None
         self.act = _BnAct(eng, self.bn1, self.relu1)
 
@@ -568,7 +600,7 @@ class VNet(_Module):
                 yield name, self.store.view(name)
 
     def state_dict(self):
-        return OrderedDict((name, self.store.view(name).detach().clone()) for name in self.store.slots)
+        return OrderedDict((name, self.store.view(name).detach().contiguous().clone()) for name in self.store.slots)
 
     def set_state_dict(self, sd, strict=True):
         missing = []

@@ -63,12 +63,19 @@ class Momentum:
         self._store.grad.zero_()
 
     def state_dict(self):
-        sd = {"velocity": self.velocity.clone()}
+        # per-parameter momentum in the reference (Paddle) shapes: independent of the internal (tap-major) layout
+        sd = {"velocity": {name: self._store.view_of(self.velocity, name).detach().contiguous().clone()
+                           for name, slot in self._store.slots.items() if not slot.is_buffer}}
         if hasattr(self._learning_rate, "state_dict"):
             sd["LR_Scheduler"] = self._learning_rate.state_dict()
         return sd
 
     def set_state_dict(self, sd):
-        self.velocity.copy_(sd["velocity"])
+        vel = sd["velocity"]
+        if torch.is_tensor(vel):  # legacy flat buffer (same layout only)
+            self.velocity.copy_(vel)
+        else:
+            for name, v in vel.items():
+                self._store.view_of(self.velocity, name).copy_(torch.as_tensor(v).to(self.velocity.device))
         if "LR_Scheduler" in sd and hasattr(self._learning_rate, "set_state_dict"):
             self._learning_rate.set_state_dict(sd["LR_Scheduler"])

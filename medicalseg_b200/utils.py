@@ -49,8 +49,13 @@ def save_checkpoint(model, optimizer, save_dir):
     os.makedirs(save_dir, exist_ok=True)
     torch.save({k: v.cpu() for k, v in model.state_dict().items()}, os.path.join(save_dir, "model.pdparams"))
     if optimizer is not None:
-        torch.save({k: (v.cpu() if torch.is_tensor(v) else v) for k, v in optimizer.state_dict().items()},
-                   os.path.join(save_dir, "model.pdopt"))
+        def to_cpu(v):
+            if torch.is_tensor(v):
+                return v.cpu()
+            if isinstance(v, dict):
+                return {k: to_cpu(x) for k, x in v.items()}
+            return v
+        torch.save({k: to_cpu(v) for k, v in optimizer.state_dict().items()}, os.path.join(save_dir, "model.pdopt"))
 
 
 def resume(model, optimizer, resume_model):
@@ -63,6 +68,5 @@ def resume(model, optimizer, resume_model):
     model.set_state_dict(torch.load(os.path.join(resume_model, "model.pdparams"), map_location="cpu"))
     if optimizer is not None:
         opt_sd = torch.load(os.path.join(resume_model, "model.pdopt"), map_location="cpu", weights_only=False)
-        opt_sd["velocity"] = opt_sd["velocity"].to(optimizer.velocity.device)
         optimizer.set_state_dict(opt_sd)
     return int(resume_model.split("_")[-1])

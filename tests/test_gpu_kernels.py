@@ -323,6 +323,39 @@ def test_conv_k5_tcgen05_wgrad(cin, cout, dims, clustered):
         _lib.call("msb_debug_set", 6, 0)
 
 
+@pytest.mark.parametrize("cin,cout,dims", [(32, 32, (6, 16, 16)), (64, 64, (4, 9, 20)), (128, 128, (3, 8, 16)),
+                                           (32, 20, (5, 10, 18))])
+def test_conv_k5_tap_major_pack_and_wgrad(cin, cout, dims):
+    """tap-major master layout [125][co][ci]: msb_conv_k5_pack_tm builds byte-identical operand images, and
+    msb_conv_k5_wgrad_tm accumulates straight into the tap-major gradient (no workspace / unpack) with the same values
+    as the Paddle-layout entry point."""
+    ops, B8 = _imp()
+    torch.manual_seed(6)
+    n = 2
+    w = torch.randn(cout, cin, 5, 5, 5, device="cuda")
+    w_tm = w.reshape(cout, cin, 125).permute(2, 0, 1).contiguous()
+    dyc = (cout + 7) // 8 * 8
+    for mode, (cin_pad, cout_pad) in ((0, (cin, ops.k5_out_pad(dyc))), (1, ((cout + 15) // 16 * 16, ops.k5_out_pad(cin)))):
+        a = torch.zeros(ops.k5_packed_bytes(cin_pad, cout_pad), dtype=torch.uint8, device="cuda")
+        b = torch.ones_like(a)
+        ops.k5_pack(w, a, cout, cin, mode, cin_pad, cout_pad)
+        ops.k5_pack_tm(w_tm, b, cout, cin, mode, cin_pad, cout_pad)
+        assert torch.equal(a, b)
+    dy = torch.zeros(n, dyc, *dims, device="cuda")
+    dy[:, :cout] = torch.randn(n, cout, *dims, device="cuda")
+    xb = B8.from_ncdhw(torch.randn(n, cin, *dims, device="cuda"), torch.bfloat16)
+    dyb = B8.from_ncdhw(dy, torch.bfloat16)
+    dw, db = torch.zeros(cout, cin, 5, 5, 5, device="cuda"), torch.zeros(cout, device="cuda")
+    ws = torch.empty(ops.k5_wgrad_workspace_bytes(cin, cout), dtype=torch.uint8, device="cuda")
+    ops.k5_wgrad(xb, dyb, dw, db, cout, cin, ws)
+    dw_tm, db2 = torch.zeros(125, cout, cin, device="cuda"), torch.zeros(cout, device="cuda")
+    ops.k5_wgrad_tm(xb, dyb, dw_tm, db2, cout, cin)
+    back = dw_tm.permute(1, 2, 0).reshape(cout, cin, 5, 5, 5)
+    assert rel(back, dw) <= 1e-5 and rel(db2, db) <= 1e-6
+    ops.k5_wgrad_tm(xb, dyb, dw_tm, None, cout, cin)  # += semantics
+    assert rel(dw_tm.permute(1, 2, 0).reshape(cout, cin, 5, 5, 5), 2 * dw) <= 1e-5
+
+
 @pytest.mark.parametrize("ci,co,dims", [(16, 32, (8, 12, 16)), (64, 128, (4, 8, 32)), (128, 256, (4, 4, 16))])
 def test_k2s2_tensor_core_wgrad(ci, co, dims):
     """2x2x2 stride-2 weight gradients (space-to-depth + pointwise tcgen05 GEMM) for conv and transposed conv"""
