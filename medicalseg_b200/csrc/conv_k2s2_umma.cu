@@ -81,6 +81,14 @@ __global__ void __launch_bounds__(kK2Threads, 1)
     ptx::fence_mbar_init();
   }
   for (int i = threadIdx.x; i < 8 * 2 * 256; i += kK2Threads) stat_smem[i] = 0.f;
+  __shared__ int tap_off[64];  // scatter: big-grid voxel offset of every N-side tap (kd, kh[, kw])
+  if (threadIdx.x < 64) {
+    const int tap = threadIdx.x;
+    const int kwl = p.wmode == 1 ? 0 : tap % p.kwn;
+    const int r2 = p.wmode == 1 ? tap : tap / p.kwn;
+    const int kh = r2 % p.khn, kd = r2 / p.khn;
+    tap_off[tap] = (kd * p.bh + kh) * p.bw + kwl;
+  }
   if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tmap_x);
   if (warp == 2) ptx::tmem_alloc<512>(ptx::smem_u32(tmem_slot));
   ptx::tc_fence_before();
@@ -198,12 +206,9 @@ __global__ void __launch_bounds__(kK2Threads, 1)
         int64_t v = v_small;
         bool tap_ok = true;
         if (p.mode != 0) {
-          const int tap = tgp * p.tg + t;  // N-side tap: (kd, kh[, kw]) row-major
+          const int tap = tgp * p.tg + t;  // N-side tap: (kd, kh[, kw]) row-major; voxel offsets precomputed in smem
           tap_ok = tap < p.ntap_n;
-          const int kwl = p.wmode == 1 ? 0 : tap % p.kwn;
-          const int r2 = p.wmode == 1 ? tap : tap / p.kwn;
-          const int kh = r2 % p.khn, kd = r2 / p.khn;
-          v = v_big0 + ((int64_t)kd * p.bh + kh) * p.bw + kwl;
+          v = v_big0 + tap_off[tap_ok ? tap : 0];
         }
         if (has_bias) {
           if (bias_vec && co0 + 16 <= p.cout_real) {

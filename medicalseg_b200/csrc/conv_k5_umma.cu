@@ -521,9 +521,15 @@ struct WgParams {
                                         // TMA box (tmap_x built by make_b8_tmap_s2) - no space-to-depth copy
   int s2_khn, s2_kwn;                   // kernel extents along h, w (tap = (kd*khn + kh)*kwn + kw)
   int s2_sd, s2_sh, s2_sw;              // strides
+  int csize, rounds;                    // CL kernels: cluster size and ceil(passes_per_group / csize) - the (kh,kw)
+                                        // passes of one (channel half, kd plane) share their tiles by TMA multicast
 };
 
-template <int NPAD, int TH>
+// CL = true: clusters of p.csize CTAs walk the same tiles of one (channel half, kd plane) and own different (kh,kw)
+// units (pass = round * csize + cluster rank); every TMA box is issued by one rank and multicast to all, a stage is
+// refilled once the MMAs of all ranks retired (multicast tcgen05.commit).  One 256 x 256 (or 128 x 128 x 4) tap set
+// fills the TMEM, so without sharing every loaded tile feeds only 2-4 taps and the kernel is L2 -> SM bound.
+template <int NPAD, int TH, bool CL = false>
 __global__ void __launch_bounds__(256, 1)
     conv_k5_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                          const WgParams p) {
@@ -538,8 +544,11 @@ __global__ void __launch_bounds__(256, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = ptx::smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const uint32_t crank = CL ? ptx::cluster_ctarank() : 0u;
+  const int csize = CL ? p.csize : 1;
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(2 + i), 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(2 + i), (uint32_t)csize); }
     ptx::mbar_init(BAR(4), 1);
     ptx::mbar_init(BAR(5), 4);
     ptx::fence_mbar_init();
@@ -550,24 +559,35 @@ __global__ void __launch_bounds__(256, 1)
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (CL) ptx::cluster_sync();  // every CTA's barriers are initialised before any peer multicasts into them
   pdl_trigger();  // after our own TMEM allocation (common.cuh, PDL rules)
   pdl_wait();
 
-  const int num_items = p.num_passes * p.chunks;
+  // CL = false: item = (pass, chunk) per CTA;  CL = true: item = ((channel half, kd group, round), chunk) per CLUSTER
+  const int num_items = CL ? p.mhalves * p.kd_groups * p.rounds * p.chunks : p.num_passes * p.chunks;
+  const int item0 = CL ? (int)blockIdx.x / csize : (int)blockIdx.x;
+  const int item_step = CL ? (int)gridDim.x / csize : (int)gridDim.x;
   const int tiles_per_n = p.d * p.tiles_h * p.tiles_w;
 
   auto decode_pass = [&](int pass, int& mh, int& g, int& u0, int& u1) {
-    const int pg = pass % p.passes_per_group;
-    g = (pass / p.passes_per_group) % p.kd_groups;
-    mh = pass / (p.passes_per_group * p.kd_groups);
-    u0 = pg * p.units_per_pass;
+    int pg;
+    if (CL) {
+      pg = (pass % p.rounds) * csize + (int)crank;  // may exceed the last pass: that rank idles (u0 == u1)
+      g = (pass / p.rounds) % p.kd_groups;
+      mh = pass / (p.rounds * p.kd_groups);
+    } else {
+      pg = pass % p.passes_per_group;
+      g = (pass / p.passes_per_group) % p.kd_groups;
+      mh = pass / (p.passes_per_group * p.kd_groups);
+    }
+    u0 = min(p.units_total, pg * p.units_per_pass);
     u1 = min(p.units_total, u0 + p.units_per_pass);
   };
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t use = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      for (int item = item0; item < num_items; item += item_step) {
         const int pass = item / p.chunks, chunk = item % p.chunks;
         int mh, g, u0, u1;
         decode_pass(pass, mh, g, u0, u1);
@@ -593,11 +613,23 @@ __global__ void __launch_bounds__(256, 1)
                                0, p.s2_sw * tw * kWgTileW + kw, p.s2_sh * th * TH + kh, p.s2_sd * d + kd,
                                n * p.x_c8_total + c8);
             }
+          } else if (CL) {  // box i of the tile is issued by rank i % csize for every rank
+            for (int q = 0; q < planes_valid; ++q)
+              if ((uint32_t)(q % csize) == crank)
+                ptx::tma_load_4d_mc(ptx::smem_u32(x_smem + b * Cfg::kXBytes + q * x_planes * Cfg::kGroupBytes), &tmap_x,
+                                    BAR(b), (tw * kWgTileW - p.pad) * 8, th * TH - p.pad, d + g * p.qm + q - p.pad,
+                                    n * p.x_c8_total + mh * 16, cmask);
+          } else {
+            for (int q = 0; q < planes_valid; ++q)
+              ptx::tma_load_4d(ptx::smem_u32(x_smem + b * Cfg::kXBytes + q * x_planes * Cfg::kGroupBytes), &tmap_x, BAR(b),
+                               (tw * kWgTileW - p.pad) * 8, th * TH - p.pad, d + g * p.qm + q - p.pad,
+                               n * p.x_c8_total + mh * 16);
+          }
+          if (CL) {
+            if ((uint32_t)(planes_valid % csize) == crank)
+              ptx::tma_load_4d_mc(ptx::smem_u32(dy_smem + b * Cfg::kDyBytes), &tmap_dy, BAR(b), tw * kWgTileW * 8, th * TH, d,
+                                  n * p.dy_c8_total, cmask);
           } else
-          for (int q = 0; q < planes_valid; ++q)
-            ptx::tma_load_4d(ptx::smem_u32(x_smem + b * Cfg::kXBytes + q * x_planes * Cfg::kGroupBytes), &tmap_x, BAR(b),
-                             (tw * kWgTileW - p.pad) * 8, th * TH - p.pad, d + g * p.qm + q - p.pad,
-                             n * p.x_c8_total + mh * 16);
           ptx::tma_load_4d(ptx::smem_u32(dy_smem + b * Cfg::kDyBytes), &tmap_dy, BAR(b), tw * kWgTileW * 8, th * TH, d,
                            n * p.dy_c8_total);
         }
@@ -613,7 +645,7 @@ __global__ void __launch_bounds__(256, 1)
     const uint32_t b_lbo16 = p.dbg_swap ? (uint32_t)Cfg::kDyPlaneBytes >> 4 : 8u;
     const uint32_t b_hi = ptx::desc_hi(p.dbg_swap ? 128u : (uint32_t)Cfg::kDyPlaneBytes);
     uint32_t use = 0, iuse = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
+    for (int item = item0; item < num_items; item += item_step, ++iuse) {
       const int pass = item / p.chunks, chunk = item % p.chunks;
       int mh, g, u0, u1;
       decode_pass(pass, mh, g, u0, u1);
@@ -638,7 +670,10 @@ __global__ void __launch_bounds__(256, 1)
             if (++kw == 5u) { kw = 0u; ++kh; }
           }
         }
-        if (leader) ptx::mma_commit(BAR(2 + b));
+        if (leader) {
+          if (CL) ptx::mma_commit_mc(BAR(2 + b), cmask);  // shared stage: free once every rank's MMAs retired
+          else ptx::mma_commit(BAR(2 + b));
+        }
       }
       if (leader) ptx::mma_commit(BAR(4));
       __syncwarp();
@@ -648,7 +683,7 @@ __global__ void __launch_bounds__(256, 1)
     const int row = q4 * 32 + lane;
     const int qplane = row / p.cin_m, ci_local = row % p.cin_m;
     uint32_t iuse = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
+    for (int item = item0; item < num_items; item += item_step, ++iuse) {
       const int pass = item / p.chunks;
       int mh, g, u0, u1;
       decode_pass(pass, mh, g, u0, u1);
@@ -681,6 +716,7 @@ __global__ void __launch_bounds__(256, 1)
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL) ptx::cluster_sync();  // no CTA may exit while a peer can still multicast into it or signal its barriers
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem_base);
@@ -1094,6 +1130,40 @@ static int launch_wgrad(const msb_tensor& x, const msb_tensor& dy, WgParams& p, 
       return rc;
   } else if ((rc = make_b8_tmap(&tmx, x, p.n, dims, kWgTileW + 4, TH + 4, 1, p.cin_m / 8))) return rc;
   if ((rc = make_b8_tmap(&tmdy, dy, p.n, dims, kWgTileW, TH, 1, dy.c / 8))) return rc;
+  p.csize = 1; p.rounds = p.passes_per_group;
+  // cluster launch: the passes of one (half, kd plane) share their tiles by TMA multicast.  MEASURED NEGATIVE RESULT
+  // (B200, batch 2, 4-CTA clusters): 128 -> 128 @32^3 0.324 ms vs 0.210 ms, 256 -> 256 @16^3 0.538 vs 0.183 ms - with a
+  // 2-stage ring every refill waits for the commits of all four ranks (cross-SM round trip per 0.5 us of MMA work) and
+  // every (group, chunk) item pays a 64 K-atomic epilogue.  Off unless msb_debug_set(6, 8) (kept verified by the tests).
+  if (p.s2_c8n == 0 && p.passes_per_group >= 4 && (g_debug_flags[6] & 8)) {
+    const int csize = 4;
+    const int nclusters = kNumSMs / csize;
+    const int rounds = (p.passes_per_group + csize - 1) / csize;
+    const int groups = p.mhalves * p.kd_groups * rounds;
+    // chunks: makespan of the static round-robin = ceil(groups * c / nclusters) / c pass-times; a few items per cluster
+    // smooth the tail, too many multiply the epilogue (every item flushes its accumulators with atomics)
+    int best_c = 1;
+    double best = 1e30;
+    for (int c = 1; c <= 16 && c <= p.total_tiles; ++c) {
+      const int waves = (groups * c + nclusters - 1) / nclusters;
+      const double cost = (double)waves / c + 0.01 * c;
+      if (cost < best) { best = cost; best_c = c; }
+    }
+    p.tiles_per_chunk = (p.total_tiles + best_c - 1) / best_c;
+    p.chunks = (p.total_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+    p.csize = csize; p.rounds = rounds;
+    const int items = groups * p.chunks;
+    const int grid = (items < nclusters ? items : nclusters) * csize;
+    MSB_CUDA_OK(cudaFuncSetAttribute(conv_k5_wgrad_kernel<NPAD, TH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::kSmemBytes));
+    cudaError_t e = launch_pdl_cluster(conv_k5_wgrad_kernel<NPAD, TH, true>, dim3(grid), dim3(256), Cfg::kSmemBytes, st,
+                                       csize, tmx, tmdy, p);
+    if (e != cudaSuccess) {
+      set_error("clustered per-tap wgrad launch failed: %s", cudaGetErrorString(e));
+      return MSB_ERR_CUDA;
+    }
+    return MSB_OK;
+  }
   const int items = p.num_passes * p.chunks;
   const int grid = items < kNumSMs ? items : kNumSMs;
   MSB_CUDA_OK(cudaFuncSetAttribute(conv_k5_wgrad_kernel<NPAD, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1208,7 +1278,13 @@ static int conv_k5_fwd_impl(const char* who, msb_tensor x, const void* packed, c
       return stack ? launch_fwd<32, 4, 4>(x, dims, p, st) : launch_fwd<32, 4>(x, dims, p, st);
     case 64: return stack ? launch_fwd<64, 4, 4>(x, dims, p, st) : launch_fwd<64, 4>(x, dims, p, st);
     case 128: return launch_fwd<128, 2>(x, dims, p, st);
-    default: return launch_fwd<256, 1>(x, dims, p, st);
+    default: {
+      // 256 channels: every item streams the whole 16 MB weight set, so two planes per item (all 512 TMEM columns, one
+      // accumulator set) halve the L2 -> SM traffic; worth it as soon as the two-plane tiles still fill most SMs
+      const int tiles2 = n * ((dims.d + 1) / 2) * p.tiles_h * p.tiles_w;
+      if (dims.d >= 2 && tiles2 * 4 >= kNumSMs * 3) return launch_fwd<256, 2, 1, 1>(x, dims, p, st);
+      return launch_fwd<256, 1>(x, dims, p, st);
+    }
   }
 }
 

@@ -36,6 +36,8 @@ struct Wg2Params {
   int kw_taps, kw_base;                  // 5 / 0 for the 5x5x5 kernel, 1 / 2 (centre tap only) for the 5x5x1 kernel
   int csize;                             // cluster size: the (kh-group, kw-subset) passes of one (channel half, kd group)
                                          // load identical tiles -> they run as ONE cluster sharing them by TMA multicast
+  int balance;                           // 2-CTA clusters, 5 kw taps: rank 0 owns kw {0,1}, rank 1 kw {3,4}, the middle
+                                         // tap alternates with the tile parity (2.5 MMAs per row each instead of 3 / 2)
 };
 
 // CL = true: launched in clusters of p.csize CTAs.  All CTAs of a cluster walk the same tiles of the same (channel half,
@@ -157,6 +159,7 @@ __global__ void __launch_bounds__(256, 1)
       const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
       ptx::mbar_wait(BAR(7), (iuse & 1) ^ 1);
       ptx::tc_fence_after();
+      bool mid_started = false;
       for (int t = t0; t < t1; ++t, ++use) {
         const uint32_t s = use % kW2Stages, ph = (use / kW2Stages) & 1;
         ptx::mbar_wait(BAR(s), ph);
@@ -164,15 +167,35 @@ __global__ void __launch_bounds__(256, 1)
         const uint32_t a_lo0 = ptx::desc_lo(ptx::smem_u32(x_smem + s * kW2XBytes), 8u) + (uint32_t)(kw0 + p.kw_base);
         const uint32_t b_lo0 =
             ptx::desc_lo(ptx::smem_u32(dy_smem + s * p.dy_stage_bytes), 8u) + (uint32_t)(jg * p.jh) * b_row16;
+        if (CL && p.balance) {
+          // accumulator slots 0,1 = this rank's fixed taps (kw 0,1 or 3,4), slot 2 = the middle tap on the tiles it owns
+          const uint32_t a_base = ptx::desc_lo(ptx::smem_u32(x_smem + s * kW2XBytes), 8u);
+          const uint32_t kwf = crank == 0 ? 0u : 3u;
+          const bool own_mid = (uint32_t)(t & 1) == crank;
 #pragma unroll
-        for (int u = 0; u < kW2TileH; ++u) {
-          const uint32_t acc = (t != t0 || u != 0) ? 1u : 0u;
-          const uint32_t b_lo = b_lo0 + (uint32_t)u * b_row16;
+          for (int u = 0; u < kW2TileH; ++u) {
+            const uint32_t acc = (t != t0 || u != 0) ? 1u : 0u;
+            const uint32_t b_lo = b_lo0 + (uint32_t)u * b_row16;
+            const uint32_t a_row = a_base + (uint32_t)(u * (kW2TileW + 4));
+            if (leader) {
+              ptx::mma_bf16_split(tmem_u, a_row + kwf, a_hi, b_lo, b_hi, idesc, acc);
+              ptx::mma_bf16_split(tmem_u + npad, a_row + kwf + 1u, a_hi, b_lo, b_hi, idesc, acc);
+              if (own_mid)
+                ptx::mma_bf16_split(tmem_u + 2u * npad, a_row + 2u, a_hi, b_lo, b_hi, idesc, (mid_started || u != 0) ? 1u : 0u);
+            }
+          }
+          if (own_mid) mid_started = true;
+        } else {
 #pragma unroll
-          for (int k = 0; k < 5; ++k) {
-            if (k < nkw && leader)
-              ptx::mma_bf16_split(tmem_u + (uint32_t)k * npad, a_lo0 + (uint32_t)(u * (kW2TileW + 4) + k), a_hi, b_lo,
-                                  b_hi, idesc, acc);
+          for (int u = 0; u < kW2TileH; ++u) {
+            const uint32_t acc = (t != t0 || u != 0) ? 1u : 0u;
+            const uint32_t b_lo = b_lo0 + (uint32_t)u * b_row16;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+              if (k < nkw && leader)
+                ptx::mma_bf16_split(tmem_u + (uint32_t)k * npad, a_lo0 + (uint32_t)(u * (kW2TileW + 4) + k), a_hi, b_lo,
+                                    b_hi, idesc, acc);
+            }
           }
         }
         if (leader) {
@@ -199,12 +222,15 @@ __global__ void __launch_bounds__(256, 1)
       ptx::mbar_wait(BAR(6), iuse & 1);
       ptx::tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
+      const bool bal = CL && p.balance;
+      const int nslots = bal ? 3 : kw1 - kw0;
 #pragma unroll 1
-      for (int kw = kw0; kw < kw1; ++kw) {
+      for (int slot = 0; slot < nslots; ++slot) {
+        const int kw = bal ? (slot == 2 ? 2 : (crank == 0 ? 0 : 3) + slot) : kw0 + slot;
 #pragma unroll 1
         for (int cb = 0; cb < p.npad / 16; ++cb) {
           float acc[16];
-          ptx::tmem_ld16(t_base + (kw - kw0) * p.npad + cb * 16, acc);
+          ptx::tmem_ld16(t_base + slot * p.npad + cb * 16, acc);
           if (row_ok) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -296,11 +322,14 @@ int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin
   if ((rc = make_b8_tmap(&tmx, x, n, dims, kW2TileW + 4, kW2TileH, 1, p.cin_m / 8))) return rc;
   if ((rc = make_b8_tmap_hmajor(&tmdy, dy, n, dims, kW2TileW, dyp, kW2TileH + 4, 1))) return rc;
   // cluster path: the jgroups x passes_per_group passes of one (channel half, kd group) share their tiles.
-  // MEASURED NEGATIVE RESULT (B200, batch 2): 32 -> 32 @128^3 1.24 ms clustered (2 CTAs) vs 1.26 ms; 64 -> 64 @64^3 1.20 ms
-  // clustered (6 CTAs) vs 0.65 ms - the ranks of a cluster run in lock-step at the pace of the rank with the most kw
-  // taps (3 vs 2; 2,2,1), which costs more than the saved L2 -> SM traffic buys.  Off by default; msb_debug_set(6, 4)
-  // enables it (tests/test_gpu_kernels.py keeps the path verified).
-  int csize = (g_debug_flags[6] & 4) ? p.jgroups * p.passes_per_group : 1;
+  // MEASURED (B200, batch 2): 2-CTA clusters with the middle kw tap alternating between the ranks (`balance`): 32 -> 32
+  // @128^3 1.11 ms vs 1.26 ms unclustered, @64^3 0.167 vs 0.199 ms -> ON by default for that shape family.  Unbalanced
+  // clusters are a NEGATIVE result: 32 -> 32 1.24 ms (ranks run in lock-step at the pace of the rank with 3 of the 5 kw
+  // taps), 64 -> 64 @64^3 with 6-CTA clusters 1.20 ms vs 0.65 ms -> OFF unless msb_debug_set(6, 4) forces them (the GPU
+  // tests keep that path verified); msb_debug_set(6, 2) disables clustering altogether.
+  int csize = p.jgroups * p.passes_per_group;
+  const bool balanced_shape = csize == 2 && p.passes_per_group == 2 && kw_taps == 5;
+  if ((g_debug_flags[6] & 2) || !(balanced_shape || (g_debug_flags[6] & 4))) csize = 1;
   const int groups = p.mhalves * p.kd_groups;
   if (csize >= 2 && csize <= 8 && (kNumSMs / csize) >= groups && p.total_tiles >= 8 * (kNumSMs / csize)) {
     const int nclusters = kNumSMs / csize;
@@ -309,6 +338,7 @@ int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin
     p.tiles_per_chunk = (p.total_tiles + chunks - 1) / chunks;
     p.chunks = (p.total_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
     p.csize = csize;
+    p.balance = (csize == 2 && p.passes_per_group == 2 && p.jgroups == 1 && kw_taps == 5 && p.tiles_per_chunk >= 4) ? 1 : 0;
     const int items = groups * p.chunks;
     const int grid = (items < nclusters ? items : nclusters) * csize;
     static bool attr_set_cl = false;
@@ -325,6 +355,7 @@ int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin
     return MSB_OK;
   }
   p.csize = 1;
+  p.balance = 0;
   const int items = p.num_passes * p.chunks;
   const int grid = items < kNumSMs ? items : kNumSMs;
   static bool attr_set = false;

@@ -653,6 +653,8 @@ __global__ void __launch_bounds__(kHeadThreads)
   pdl_wait();
   pdl_trigger();
   __shared__ __align__(16) float ws[kHeadMaxC][CI8 * 8];  // W[o][i], rows zero-padded to the plane width
+  __shared__ float accw[kHeadThreads / 32 * 4];           // per-pair sums of the warp-per-pair path
+  if (threadIdx.x < kHeadThreads / 32 * 4) accw[threadIdx.x] = 0.f;
   extern __shared__ float head_smem[];
   float (*as)[kHeadPitch] = reinterpret_cast<float (*)[kHeadPitch]>(head_smem);                          // [CI8*8]
   float (*ds)[kHeadPitch] = reinterpret_cast<float (*)[kHeadPitch]>(head_smem + CI8 * 8 * kHeadPitch);   // [kHeadMaxC]
@@ -710,24 +712,50 @@ __global__ void __launch_bounds__(kHeadThreads)
       }
     }
     __syncthreads();
-#pragma unroll
-    for (int slot = 0; slot < kSlots; ++slot) {
-      const int pidx = threadIdx.x + slot * kHeadThreads;
-      if (pidx >= npairs) continue;
-      float acc = 0.f;
-      if (pidx < co * ci) {
-        const float* ar = as[pidx % ci];
-        const float* dr = ds[pidx / ci];
-#pragma unroll 8
-        for (int t = 0; t < kHeadTile; ++t) acc = fmaf(ar[t], dr[t], acc);
-      } else {
-        const float* dr = ds[pidx - co * ci];
-#pragma unroll 8
-        for (int t = 0; t < kHeadTile; ++t) acc += dr[t];
+    if (npairs <= kHeadThreads / 32 * 4) {
+      // few pairs (2-3 classes): one WARP per pair, lanes stride over the staged voxels (a thread-per-pair loop would
+      // be one 512-long dependent FMA chain on a handful of threads)
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      for (int pidx = warp; pidx < npairs; pidx += kHeadThreads / 32) {
+        float acc = 0.f;
+        if (pidx < co * ci) {
+          const float* ar = as[pidx % ci];
+          const float* dr = ds[pidx / ci];
+          for (int t = lane; t < kHeadTile; t += 32) acc = fmaf(ar[t], dr[t], acc);
+        } else {
+          const float* dr = ds[pidx - co * ci];
+          for (int t = lane; t < kHeadTile; t += 32) acc += dr[t];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) accw[pidx] += acc;
       }
-      accp[slot] += acc;
+    } else {
+#pragma unroll
+      for (int slot = 0; slot < kSlots; ++slot) {
+        const int pidx = threadIdx.x + slot * kHeadThreads;
+        if (pidx >= npairs) continue;
+        float acc = 0.f;
+        if (pidx < co * ci) {
+          const float* ar = as[pidx % ci];
+          const float* dr = ds[pidx / ci];
+#pragma unroll 8
+          for (int t = 0; t < kHeadTile; ++t) acc = fmaf(ar[t], dr[t], acc);
+        } else {
+          const float* dr = ds[pidx - co * ci];
+#pragma unroll 8
+          for (int t = 0; t < kHeadTile; ++t) acc += dr[t];
+        }
+        accp[slot] += acc;
+      }
     }
     __syncthreads();
+  }
+  if (npairs <= kHeadThreads / 32 * 4) {
+    for (int pidx = threadIdx.x; pidx < npairs; pidx += kHeadThreads) {
+      if (pidx < co * ci) atomicAdd(dw + pidx, accw[pidx]);
+      else if (db) atomicAdd(db + (pidx - co * ci), accw[pidx]);
+    }
+    return;
   }
 #pragma unroll
   for (int slot = 0; slot < kSlots; ++slot) {

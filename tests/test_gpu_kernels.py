@@ -287,14 +287,16 @@ def test_conv_k5_split_k_small_volumes(cin, cout, dims):
 WG_CASES = [(32, 32, (6, 16, 16)), (64, 64, (4, 9, 20)), (128, 128, (3, 8, 16)), (256, 256, (2, 8, 8)),
             (32, 2, (5, 10, 18)), (16, 16, (5, 8, 16)), (32, 32, (3, 13, 9)),
             # enough tiles for the clustered (TMA-multicast) launch: 2-CTA clusters (32 ch), 6-CTA clusters (64 ch)
-            (32, 32, (16, 64, 64)), (64, 64, (16, 32, 32)), (32, 32, (9, 70, 50))]
+            (32, 32, (16, 64, 64)), (64, 64, (16, 32, 32)), (32, 32, (9, 70, 50)), (128, 128, (16, 32, 32)),
+            (256, 256, (8, 32, 32))]
 
 
 @pytest.mark.parametrize("cin,cout,dims", WG_CASES)
 @pytest.mark.parametrize("clustered", [False, True])
 def test_conv_k5_tcgen05_wgrad(cin, cout, dims, clustered):
-    """clustered = the TMA-multicast cluster launch of the kh-stacked kernel (off by default: measured slower, see
-    conv_k5_wgrad2.cu); only the shapes with enough tiles take it"""
+    """clustered: True forces the TMA-multicast cluster launch of the kh-stacked kernel for every shape family (default:
+    only the balanced 2-CTA clusters of the 32-channel layers, see conv_k5_wgrad2.cu), False disables it; only the
+    shapes with enough tiles take it"""
     ops, B8 = _imp()
     from medicalseg_b200 import _lib
     if clustered and dims[0] * dims[1] * dims[2] < 16 * 32 * 32:
@@ -312,7 +314,7 @@ def test_conv_k5_tcgen05_wgrad(cin, cout, dims, clustered):
     dw = torch.zeros(cout, cin, 5, 5, 5, device="cuda")
     db = torch.zeros(cout, device="cuda")
     ws = torch.empty(ops.k5_wgrad_workspace_bytes(cin, cout), dtype=torch.uint8, device="cuda")
-    _lib.call("msb_debug_set", 6, 4 if clustered else 0)
+    _lib.call("msb_debug_set", 6, (4 | 8) if clustered else 2)  # 8: clustered per-tap kernel (>= 128 channels)
     try:
         ops.k5_wgrad(xb, dyb, dw, db, cout, cin, ws)
         assert rel(dw, ref) <= 1e-4  # bf16 x bf16 products are exact in f32; only the summation order differs

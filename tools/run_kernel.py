@@ -105,6 +105,9 @@ def main():
     from medicalseg_b200.ops import B8
     what = sys.argv[1] if len(sys.argv) > 1 else "fwd32"
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    if os.environ.get("MSB_DEBUG6"):  # e.g. 4 = clustered (TMA multicast) kh-stacked wgrad
+        from medicalseg_b200 import _lib
+        _lib.call("msb_debug_set", 6, int(os.environ["MSB_DEBUG6"]))
     if what.startswith("k2"):
         return k2s2(what, reps)
     if what.startswith("bn"):
