@@ -261,9 +261,9 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "achieved": round(achieved, 2), "peak": burst, "unit": "TFLOP/s",
                          "frac": round(achieved / burst, 4),
                          # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at this shape
-                         # (ncu --set full, profiles/r1e_ncu_full_fwd32_wgrad32.txt): 268.7 + 227.9 MB, vs 536.9 MB of
-                         # algorithmic activation bytes (x + y, bf16) -> every byte moves once
-                         "traffic": 496.6e6, "traffic_unit": "bytes/launch (ncu dram read+write)",
+                         # (ncu --set full, profiles/r1s_ncu_full_fwd32_wgrad32_final.txt): 268.7 + 224.1 MB, vs 536.9 MB
+                         # of algorithmic activation bytes (x + y, bf16) -> every byte moves once
+                         "traffic": 492.9e6, "traffic_unit": "bytes/launch (ncu dram read+write)",
                          "peak_source": src + " (burst, kernel timed alone)",
                          "kernel": "conv_k5_fwd_kernel<32,8,8> (up_tr32.ops[0].conv1 32->32 5x5x5 @128^3, batch 2)",
                          "kernel_ms": round(k_ms, 4),

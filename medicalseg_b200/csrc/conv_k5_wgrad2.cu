@@ -146,7 +146,12 @@ __global__ void __launch_bounds__(256, 1)
     // whole warp runs the uniform control flow / descriptor arithmetic; one elected lane issues (see conv_k5_umma.cu)
     const bool leader = ptx::elect_one();
     const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);
-    const uint32_t idesc = ptx::make_idesc_bf16(128, p.npad, 1, 1);
+    // N of a pass = the kh shifts its group really holds (the last group of a 3+2 split is narrower: 128 instead of 192
+    // columns for 64 output channels - a third fewer tensor-pipe cycles for those passes)
+    auto pass_n = [&](int jg) {
+      const int jcount = min(p.jh, 5 - jg * p.jh);
+      return (uint32_t)((jcount * 8 * p.dyp + 15) / 16 * 16);
+    };
     constexpr uint32_t a_hi = ptx::desc_hi(kW2GroupBytes), b_hi = ptx::desc_hi(kW2RowBytes);
     const uint32_t b_row16 = (uint32_t)(p.dyp * kW2RowBytes) >> 4;  // one h row of the dY tile, 16-byte units
     const uint32_t npad = (uint32_t)p.npad;
@@ -156,6 +161,7 @@ __global__ void __launch_bounds__(256, 1)
       int mh, g, jg, kw0, kw1;
       decode_pass(pass, mh, g, jg, kw0, kw1);
       const int nkw = kw1 - kw0;
+      const uint32_t idesc = ptx::make_idesc_bf16(128, (int)pass_n(jg), 1, 1);
       const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
       ptx::mbar_wait(BAR(7), (iuse & 1) ^ 1);
       ptx::tc_fence_after();
@@ -227,8 +233,10 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll 1
       for (int slot = 0; slot < nslots; ++slot) {
         const int kw = bal ? (slot == 2 ? 2 : (crank == 0 ? 0 : 3) + slot) : kw0 + slot;
+        const int jcount_e = min(p.jh, 5 - jg * p.jh);
+        const int npass_e = (jcount_e * 8 * p.dyp + 15) / 16 * 16;
 #pragma unroll 1
-        for (int cb = 0; cb < p.npad / 16; ++cb) {
+        for (int cb = 0; cb < npass_e / 16; ++cb) {
           float acc[16];
           ptx::tmem_ld16(t_base + slot * p.npad + cb * 16, acc);
           if (row_ok) {

@@ -24,16 +24,6 @@ constexpr int kVoxPerBlock = 2048;
 static inline dim3 plane_grid(int n, int c, int64_t s) {
   return dim3((unsigned)((s + kVoxPerBlock - 1) / kVoxPerBlock), (unsigned)(c / 8), (unsigned)n);
 }
-// same planes, but about `target` blocks in total (kernels that loop over chunks and finish with atomics)
-static inline dim3 plane_grid_capped(int n, int c, int64_t s, int target = kNumSMs * 8) {
-  const int64_t chunks = (s + kVoxPerBlock - 1) / kVoxPerBlock;
-  const int64_t planes = (int64_t)(c / 8) * n;
-  int64_t gx = (target + planes - 1) / planes;
-  if (gx > chunks) gx = chunks;
-  if (gx < 1) gx = 1;
-  return dim3((unsigned)gx, (unsigned)(c / 8), (unsigned)n);
-}
-
 // block-level reduction of K per-thread floats; result valid in threads [0, K) of warp 0.. returned via smem
 template <int K>
 __device__ __forceinline__ void block_reduce_to_smem(float (&v)[K], float* smem /*[kThreads/32][K]*/) {
