@@ -3,6 +3,7 @@ anisotropic kernels) and configs[4] (preprocess 512^3 -> 128^3), each with its C
 
     python tools/bench_extra.py mri        # VNet MRISpineSeg train step, batch 2, bf16
     python tools/bench_extra.py preprocess # HUnorm + resample (order 1) and label resample (order 0)
+    python tools/bench_extra.py infer      # eval-mode forward, both configs
 """
 import json
 import os
@@ -49,6 +50,25 @@ def mri():
                       "tflops": round(2 * 12817 / ms, 1)}))
 
 
+def infer():
+    """eval-mode forward (core/val.py:101-118, core/infer.py:79-92): logits for a batch of 2 volumes, bf16 engine"""
+    from medicalseg_b200.models import VNet
+    for name, kw, shape in (("128^3 2-class", {}, (128, 128, 128)),
+                            ("MRISpineSeg 512x512x12 20-class",
+                             dict(num_classes=20, kernel_size=[[2, 2, 4], [2, 2, 2], [2, 2, 2], [2, 2, 2]],
+                                  stride_size=[[2, 2, 1], [2, 2, 1], [2, 2, 2], [2, 2, 2]]), (512, 512, 12))):
+        kw.setdefault("num_classes", 2)
+        m = VNet(compute_dtype="bf16", **kw)
+        m.eval()
+        img = torch.rand(2, 1, *shape, device="cuda")
+        with torch.no_grad():
+            for _ in range(3):
+                m(img)
+            ms = ev_time(lambda: m(img), 10)
+        print(json.dumps({"metric": "VNet %s eval forward volumes/sec" % name, "value": round(2e3 / ms, 2),
+                          "unit": "volumes/s", "ms_per_batch": round(ms, 3), "batch": 2, "n_gpus": 1}))
+
+
 def preprocess():
     from medicalseg_b200 import preprocess as P
     from oracle import preprocess_oracle as po
@@ -88,4 +108,4 @@ def preprocess():
 
 
 if __name__ == "__main__":
-    {"mri": mri, "preprocess": preprocess}[sys.argv[1]]()
+    {"mri": mri, "preprocess": preprocess, "infer": infer}[sys.argv[1]]()
