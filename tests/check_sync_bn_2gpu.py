@@ -1,7 +1,8 @@
-"""2-GPU check of VNet(sync_bn=True): two ranks with batch 2 each must reproduce ONE process with batch 4 - the
+"""(test infrastructure: lives under tests/ because it uses the oracle's synthetic batch / dropout-mask helpers)
+2-GPU check of VNet(sync_bn=True): two ranks with batch 2 each must reproduce ONE process with batch 4 - the
 reference converts every BatchNorm to SyncBatchNorm when world > 1 (cvlibs/config.py:322).
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_sync_bn.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/check_sync_bn_2gpu.py
 
 Forward: logits of the local half == the matching half of the single-process logits.  Backward (given the same
 d(loss)/d(logits)): the SUM over ranks of the flat gradient buffers == the single-process gradients, running statistics

@@ -1,8 +1,8 @@
 """Bring-up probe: runs each kernel family against a torch reference in its OWN subprocess (a faulting kernel
 cannot poison the rest) and prints one line per check.  Usage on the GPU box:
 
-    python tools/probe_kernels.py            # all checks
-    python tools/probe_kernels.py k5_fwd     # names containing the substring
+    python tests/probe_kernels.py            # all checks
+    python tests/probe_kernels.py k5_fwd     # names containing the substring
 """
 import os
 import subprocess

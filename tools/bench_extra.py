@@ -71,7 +71,6 @@ def infer():
 
 def preprocess():
     from medicalseg_b200 import preprocess as P
-    from oracle import preprocess_oracle as po
     import scipy.ndimage
     rng = np.random.default_rng(0)
     vol = rng.uniform(-2000, 2000, size=(512, 512, 512)).astype(np.float32)
@@ -92,7 +91,8 @@ def preprocess():
     t_host = (time.perf_counter() - t0) / 3 * 1e3
     # CPU baseline: what the reference executes (numpy HUnorm + scipy.ndimage.zoom, single-threaded C)
     t0 = time.perf_counter()
-    hu = po.HUnorm(vol)
+    # tools/preprocess_utils/values.py:67-87 restated inline: nan_to_num(nan=-2000) -> window [-1200, 600] -> [0, 255]
+    hu = np.clip((np.nan_to_num(vol, nan=-2000.0) - (-1200.0)) / ((600.0 - (-1200.0)) / 255.0), 0, 255)
     ref = scipy.ndimage.zoom(hu.astype(np.float32), 0.25, mode="nearest", order=1)
     t_cpu = (time.perf_counter() - t0) * 1e3
     err = float(np.abs(res.numpy() - ref).max())
