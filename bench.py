@@ -201,9 +201,13 @@ def run_ours(args):
             gstep.prefetch(h_img, h_lab)
             last = float(loss.item())  # D2H read of the step's result
     else:
+        # eager path (world > 1): the same input pipelining through medicalseg_b200.utils.DevicePrefetcher
+        from medicalseg_b200.utils import DevicePrefetcher
+        pre = DevicePrefetcher(device)
+        pre.stage(h_img, h_lab)
         for _ in range(e2e_steps):
-            d_img = h_img.to(device, non_blocking=True)
-            d_lab = h_lab.to(device, non_blocking=True)
+            d_img, d_lab = pre.get()
+            pre.stage(h_img, h_lab)  # H2D of the next batch overlaps this step
             loss, dice = step(d_img, d_lab)
             last = float(loss.item())  # D2H read of the step's result
     e1.record()

@@ -70,3 +70,42 @@ def resume(model, optimizer, resume_model):
         opt_sd = torch.load(os.path.join(resume_model, "model.pdopt"), map_location="cpu", weights_only=False)
         optimizer.set_state_dict(opt_sd)
     return int(resume_model.split("_")[-1])
+
+
+class DevicePrefetcher:
+    """Double-buffered host -> device input staging on a copy stream (the role of the reference's DataLoader worker
+    prefetch, core/train.py:100-107, moved to the device side): `stage(images, labels)` starts the asynchronous copy
+    of the NEXT batch (pinned host tensors) while the current step runs; `get()` makes the compute stream wait for it
+    and hands out the device tensors.  Two buffer pairs alternate, so a batch is never overwritten while a step that
+    was launched on it may still be running - provided the caller synchronises (e.g. reads the loss) once per step."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.bufs = [None, None]
+        self.events = [None, None]
+        self.next = 0
+        self.ready = None
+
+    def stage(self, images: torch.Tensor, labels: torch.Tensor):
+        i = self.next
+        if self.bufs[i] is None or self.bufs[i][0].shape != images.shape or self.bufs[i][1].shape != labels.shape:
+            self.bufs[i] = (torch.empty(images.shape, dtype=images.dtype, device=self.device),
+                            torch.empty(labels.shape, dtype=labels.dtype, device=self.device))
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))  # earlier consumers of this buffer are queued
+        with torch.cuda.stream(self.stream):
+            self.bufs[i][0].copy_(images, non_blocking=True)
+            self.bufs[i][1].copy_(labels, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.events[i] = ev
+        self.ready = i
+        self.next = 1 - i
+
+    def get(self):
+        i = self.ready
+        if i is None:
+            raise RuntimeError("DevicePrefetcher.get() without a staged batch")
+        torch.cuda.current_stream(self.device).wait_event(self.events[i])
+        self.ready = None
+        return self.bufs[i]
