@@ -218,6 +218,7 @@ using namespace msb;
   do {                                                    \
     if ((c) <= 4) { constexpr int CMAX = 4; __VA_ARGS__ } \
     else if ((c) <= 8) { constexpr int CMAX = 8; __VA_ARGS__ } \
+    else if ((c) <= 20) { constexpr int CMAX = 20; __VA_ARGS__ } \
     else { constexpr int CMAX = 32; __VA_ARGS__ }         \
   } while (0)
 
