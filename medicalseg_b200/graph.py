@@ -13,7 +13,8 @@ Everything that varies between steps lives in device memory: the batch (static i
 re-packing for the tensor-core kernels is issued at the START of the captured step on a side stream (each conv waits
 for its own layer), so it overlaps the first convolutions as in the eager path.
 
-Single-process only: with world_size > 1 the bucketed NCCL all-reduce keeps the eager path (core.train falls back).
+world_size > 1: core.train keeps the eager path (bucketed NCCL all-reduce overlapping backward).  Capturing the
+all-reduces as well is experimental (`bench.py --graph-ddp`).
 """
 from __future__ import annotations
 
@@ -80,7 +81,10 @@ class GraphedTrainStep:
             pk.pack_event = None  # completed (synchronize above); a capturing stream must not wait on outside events
         m._defer_prepack = True
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # with a data-parallel reducer the capture contains NCCL all-reduces on its communication stream; NCCL's
+        # watchdog thread may touch the CUDA API meanwhile, which only the thread-local capture mode tolerates
+        multi = self.reducer is not None and getattr(self.reducer, "world", 1) > 1
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local" if multi else "global"):
             loss, dice = self._body()
         self.s_loss = loss
         self.s_dice = dice._dev if isinstance(dice, L.LazyHostArray) else None

@@ -50,6 +50,30 @@ def mri():
                       "tflops": round(2 * 12817 / ms, 1)}))
 
 
+def fp32():
+    """BASELINE configs[2] on one GPU: the f32 PARITY path (CUDA-core direct convolutions, f32 storage) - there is no
+    tensor-core fp32 (TF32 / 3xbf16-split) path yet, so this is the cost of that gap, not a tuned number"""
+    from medicalseg_b200.models import VNet, losses as L
+    from medicalseg_b200.optimizer import Momentum, PolynomialDecay
+    m = VNet(num_classes=2, compute_dtype="f32")
+    m.train()
+    losses = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1])], "coef": [1]}
+    opt = Momentum(PolynomialDecay(0.001, 15000), m.parameters(), 0.9, 1e-4)
+    img = torch.rand(2, 1, 128, 128, 128, device="cuda")
+    lab = torch.randint(0, 2, (2, 128, 128, 128), device="cuda", dtype=torch.int32)
+
+    def step():
+        ll, dice = L.loss_computation(m(img), lab, losses)
+        sum(ll).backward()
+        opt.step(); opt._learning_rate.step(); m.clear_gradients()
+
+    step()
+    ms = ev_time(step, 2)
+    print(json.dumps({"metric": "VNet 128^3 fp32 (CUDA-core parity path) train-step volumes/sec", "value": round(2e3 / ms, 3),
+                      "unit": "volumes/s", "ms_per_step": round(ms, 1), "n_gpus": 1, "batch": 2,
+                      "tflops": round(2 * 4380.9 / ms, 1)}))
+
+
 def infer():
     """eval-mode forward (core/val.py:101-118, core/infer.py:79-92): logits for a batch of 2 volumes, bf16 engine"""
     from medicalseg_b200.models import VNet
@@ -108,4 +132,4 @@ def preprocess():
 
 
 if __name__ == "__main__":
-    {"mri": mri, "preprocess": preprocess, "infer": infer}[sys.argv[1]]()
+    {"mri": mri, "preprocess": preprocess, "infer": infer, "fp32": fp32}[sys.argv[1]]()
