@@ -121,8 +121,7 @@ def run_ours(args):
     orig_call = _lib.call
     # world == 1: the whole step is ONE CUDA graph (medicalseg_b200.graph.GraphedTrainStep, the `to_static_training`
     # hook of core.train); world > 1 keeps the eager path (bucketed NCCL all-reduce overlapping backward)
-    # --graph-ddp (experimental): also capture the NCCL bucket all-reduces of world > 1 into the graph
-    use_graph = (world == 1 or args.graph_ddp) and not args.no_graph
+    use_graph = world == 1 and not args.no_graph
     gstep = None
     if use_graph:
         from medicalseg_b200.graph import GraphedTrainStep
@@ -347,7 +346,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph (N=1)")
-    ap.add_argument("--graph-ddp", action="store_true", help="experimental: CUDA graph including the NCCL all-reduces (N>1)")
     ap.add_argument("--cpu-depth", type=int, default=32, help="depth of the 128x128 slab the CPU arm processes per step")
     args = ap.parse_args()
     if args.impl == "reference":

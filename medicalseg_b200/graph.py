@@ -14,7 +14,8 @@ re-packing for the tensor-core kernels is issued at the START of the captured st
 for its own layer), so it overlaps the first convolutions as in the eager path.
 
 world_size > 1: core.train keeps the eager path (bucketed NCCL all-reduce overlapping backward).  Capturing the
-all-reduces as well is experimental (`bench.py --graph-ddp`).
+all-reduces too was tried on 2 x B200 (async NCCL work on the communication stream inside the capture, thread-local
+capture mode) and DEADLOCKED in the warm-up / capture phase, so the graph stays single-process.
 """
 from __future__ import annotations
 
@@ -81,10 +82,10 @@ class GraphedTrainStep:
             pk.pack_event = None  # completed (synchronize above); a capturing stream must not wait on outside events
         m._defer_prepack = True
         self.graph = torch.cuda.CUDAGraph()
-        # with a data-parallel reducer the capture contains NCCL all-reduces on its communication stream; NCCL's
-        # watchdog thread may touch the CUDA API meanwhile, which only the thread-local capture mode tolerates
-        multi = self.reducer is not None and getattr(self.reducer, "world", 1) > 1
-        with torch.cuda.graph(self.graph, capture_error_mode="thread_local" if multi else "global"):
+        if self.reducer is not None and getattr(self.reducer, "world", 1) > 1:
+            raise RuntimeError("GraphedTrainStep is single-process: capturing the NCCL all-reduces deadlocked when it "
+                               "was tried (see the module docstring); use the eager step with world_size > 1")
+        with torch.cuda.graph(self.graph):
             loss, dice = self._body()
         self.s_loss = loss
         self.s_dice = dice._dev if isinstance(dice, L.LazyHostArray) else None
