@@ -59,6 +59,9 @@ class GraphedTrainStep:
         return loss.detach(), dice
 
     def _capture(self, images, labels):
+        if self.reducer is not None and getattr(self.reducer, "world", 1) > 1:
+            raise RuntimeError("GraphedTrainStep is single-process: capturing the NCCL all-reduces deadlocked when it "
+                               "was tried (see the module docstring); use the eager step with world_size > 1")
         m, opt = self.model, self.optimizer
         dev = m.device
         self.s_img = torch.empty_like(images, device=dev)
@@ -82,9 +85,6 @@ class GraphedTrainStep:
             pk.pack_event = None  # completed (synchronize above); a capturing stream must not wait on outside events
         m._defer_prepack = True
         self.graph = torch.cuda.CUDAGraph()
-        if self.reducer is not None and getattr(self.reducer, "world", 1) > 1:
-            raise RuntimeError("GraphedTrainStep is single-process: capturing the NCCL all-reduces deadlocked when it "
-                               "was tried (see the module docstring); use the eager step with world_size > 1")
         with torch.cuda.graph(self.graph):
             loss, dice = self._body()
         self.s_loss = loss
