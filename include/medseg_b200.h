@@ -149,8 +149,9 @@ int msb_conv_strided_wgrad(msb_tensor big, msb_tensor small, float* dw, float* d
                            msb_dim3 big_dims, msb_dim3 kernel, msb_dim3 stride, msb_dim3 pad, int c_big_real,
                            int c_small_real, int bias_from_big, void* stream);
 
-/* tensor-core weight gradient for the non-overlapping kernel = stride = (2,2,2) case (bf16 views, even extents):
- * space-to-depth of `big` + a pointwise tcgen05 weight-gradient GEMM.  Same result layout as
+/* tensor-core weight gradient for the non-overlapping kernel = stride = (2,2,2) case (bf16 views, even extents) - the
+ * wrapper of msb_conv_tc_wgrad: a pointwise tcgen05 weight-gradient GEMM whose M rows are (tap, channel); every tap's
+ * sub-lattice of `big` is fetched by a strided TMA box (no space-to-depth copy).  Same result layout as
  * msb_conv_strided_wgrad.  workspace: msb_conv_k2s2_wgrad_workspace_bytes(...) bytes of device scratch. */
 size_t msb_conv_k2s2_wgrad_workspace_bytes(int n, int c_big, int c_small, msb_dim3 big_dims);
 int msb_conv_k2s2_wgrad(msb_tensor big, msb_tensor small, float* dw, float* dbias, int n, msb_dim3 big_dims,

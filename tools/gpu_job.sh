@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python tools/bench_extra.py fp32 > gpurun_out/fp32.log 2>&1; tail -1 gpurun_out/fp32.log
-timeout 300 python tools/bench_extra.py mri > gpurun_out/mri.log 2>&1; tail -1 gpurun_out/mri.log
-timeout 300 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "dice_ce" 2>&1 | tail -2
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log | cut -c1-250
+timeout 300 python bench.py > gpurun_out/bench.log 2>&1; tail -1 gpurun_out/bench.log | cut -c1-2500
+timeout 200 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1; tail -1 gpurun_out/bench_ref.log | cut -c1-600
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
