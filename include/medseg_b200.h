@@ -211,6 +211,13 @@ int msb_conv_k5_wgrad(msb_tensor x, msb_tensor dy, float* dw, float* dbias, int 
  * state-dict boundary. */
 int msb_conv_k5_pack_tm(const float* w_tm, void* packed, int cout, int cin, int mode, int cin_pad, int cout_pad,
                         void* stream);
+/* ---- 3 x bf16 fp32 path (BASELINE configs[2]: fp32 storage, tensor-core convolutions) -------------------------
+ * An f32 operand a is split into bf16 hi = bf16(a) and lo = bf16(a - hi); conv(x, w) ~ conv(x_hi, w_hi) + conv(x_lo, w_hi)
+ * + conv(x_hi, w_lo) with f32 accumulation (relative error ~2^-16; the lo*lo term is dropped).  msb_split_hi_lo splits
+ * an f32 B8 activation; msb_conv_k5_pack_tm with mode | 2 packs the lo part of the weights; msb_conv_k5_fwd with an f32
+ * B8 `out` view stores f32 and honours `accumulate` / `ch_scale` / `sums` (pass bias on the first and sums on the
+ * last of the three passes); msb_conv_k5_wgrad_tm is simply called for the three operand pairs. */
+int msb_split_hi_lo(msb_tensor x, msb_tensor hi, msb_tensor lo, int n, int64_t s, void* stream);
 int msb_conv_k5_wgrad_tm(msb_tensor x, msb_tensor dy, float* dw_tm, float* dbias, int cout, int cin, int n,
                          msb_dim3 dims, void* stream);
 /* ---- w-folded 5x5x1 variant of the 5x5x5 conv for layers with <= 3 real channels on one side -------------

@@ -345,12 +345,33 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
             const bool live = ok && c8 < p.out_c8;
             uint32_t pk[4] = {0u, 0u, 0u, 0u};
             if (p.out_f32) {
+              // f32 output (folded 5x5x1 partial sums; the hi/lo passes of the 3 x bf16 fp32 path, which accumulate)
+              float o[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = 0.f;
               if (live) {
-                float o[8];
+                float* dst = view_ptr<float>(p.out, n, c8, S, v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[j] = acc[k * 8 + j];
-                Vec8<float>::store(view_ptr<float>(p.out, n, c8, S, v), o);
+                if (p.accumulate) {
+                  float old[8];
+                  Vec8<float>::load(dst, old);
+                  if (p.ch_scale != nullptr) {
+                    const float* scp = p.ch_scale + (int64_t)n * p.out.c + c8 * 8;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = fmaf(o[j], __ldg(scp + j), old[j]);
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] += old[j];
+                  }
+                }
+                Vec8<float>::store(dst, o);
               }
+              if (want_stats) {  // statistics of the final f32 values (callers pass sums on the last pass only)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[k * 8 + j] = o[j];
+              }
+              continue;
             } else if (live) {
               __nv_bfloat16* dst = view_ptr<__nv_bfloat16>(p.out, n, c8, S, v);
               if (p.accumulate) {
@@ -826,9 +847,11 @@ __global__ void __launch_bounds__(256) pack_k5_kernel(const float* __restrict__ 
 // One thread per 16-byte output vector: mode 0 reads 8 consecutive ci (one 32-byte sector), mode 1 reads 8 values
 // strided by cin that are consecutive across the threads of a warp.
 __global__ void __launch_bounds__(256) pack_k5_tm_kernel(const float* __restrict__ w_tm, __nv_bfloat16* __restrict__ packed,
-                                                         int cout, int cin, int mode, int cin_pad, int cout_pad) {
+                                                         int cout, int cin, int mode_bits, int cin_pad, int cout_pad) {
   pdl_wait();
   pdl_trigger();
+  const int mode = mode_bits & 1;
+  const bool lo_part = (mode_bits & 2) != 0;  // 3 x bf16 fp32 path: pack w - bf16(w) instead of w
   const int64_t total = (int64_t)(cin_pad / 8) * kNumTaps * cout_pad;  // output vectors
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i;
@@ -849,9 +872,28 @@ __global__ void __launch_bounds__(256) pack_k5_tm_kernel(const float* __restrict
       } else {
         if (rc < cout && oc < cin) x = __ldg(w_tm + ((int64_t)(kNumTaps - 1 - tap) * cout + rc) * cin + oc);
       }
+      if (lo_part) x -= __bfloat162float(__float2bfloat16_rn(x));
       v[j] = x;
     }
     Vec8<__nv_bfloat16>::store(packed + i * 8, v);
+  }
+}
+
+// f32 B8 tensor -> bf16 hi = bf16(x) and lo = bf16(x - hi): x = hi + lo up to 2^-17 relative (3 x bf16 fp32 path)
+__global__ void __launch_bounds__(256) split_hi_lo_kernel(msb_tensor x, msb_tensor hi, msb_tensor lo, int64_t s) {
+  pdl_wait();
+  pdl_trigger();
+  const int c8 = blockIdx.y, n = blockIdx.z;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < s; v += (int64_t)gridDim.x * blockDim.x) {
+    float a[8], h[8], l[8];
+    Vec8<float>::load(view_ptr<float>(x, n, c8, s, v), a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      h[j] = __bfloat162float(__float2bfloat16_rn(a[j]));
+      l[j] = a[j] - h[j];
+    }
+    Vec8<__nv_bfloat16>::store(view_ptr<__nv_bfloat16>(hi, n, c8, s, v), h);
+    Vec8<__nv_bfloat16>::store(view_ptr<__nv_bfloat16>(lo, n, c8, s, v), l);
   }
 }
 
@@ -1207,16 +1249,28 @@ int msb_conv_k5_pack(const float* w, void* packed, int cout, int cin, int mode, 
   return MSB_OK;
 }
 
-int msb_conv_k5_pack_tm(const float* w_tm, void* packed, int cout, int cin, int mode, int cin_pad, int cout_pad,
+int msb_split_hi_lo(msb_tensor x, msb_tensor hi, msb_tensor lo, int n, int64_t s, void* stream) {
+  MSB_REQUIRE(view_ok(x) && view_ok(hi) && view_ok(lo) && x.dtype == MSB_F32 && hi.dtype == MSB_BF16 &&
+                  lo.dtype == MSB_BF16 && hi.c == x.c && lo.c == x.c && n > 0 && s > 0,
+              "msb_split_hi_lo: f32 B8 input and two bf16 B8 outputs of the same channel count required");
+  int64_t bx = (s + 255) / 256;
+  if (bx > 2048) bx = 2048;
+  MSB_LAUNCH_PDL(split_hi_lo_kernel, dim3((unsigned)bx, (unsigned)(x.c / 8), (unsigned)n), dim3(256), 0, as_stream(stream),
+                 x, hi, lo, s);
+  return MSB_OK;
+}
+
+int msb_conv_k5_pack_tm(const float* w_tm, void* packed, int cout, int cin, int mode_bits, int cin_pad, int cout_pad,
                         void* stream) {
-  MSB_REQUIRE(w_tm && packed && cout > 0 && cin > 0 && (mode == 0 || mode == 1), "msb_conv_k5_pack_tm: bad arguments");
+  const int mode = mode_bits & 1;
+  MSB_REQUIRE(w_tm && packed && cout > 0 && cin > 0 && mode_bits >= 0 && mode_bits <= 3, "msb_conv_k5_pack_tm: bad arguments");
   MSB_REQUIRE(cin_pad % 16 == 0 && cout_pad % 16 == 0, "msb_conv_k5_pack_tm: padded channel counts must be multiples of 16");
   MSB_REQUIRE(mode == 0 ? (cin_pad >= cin && cout_pad >= cout) : (cin_pad >= cout && cout_pad >= cin),
               "msb_conv_k5_pack_tm: padded channel counts too small");
   const int64_t total = (int64_t)(cin_pad / 8) * kNumTaps * cout_pad;
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   MSB_LAUNCH_PDL(pack_k5_tm_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), w_tm,
-                 reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, mode, cin_pad, cout_pad);
+                 reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, mode_bits, cin_pad, cout_pad);
   return MSB_OK;
 }
 
@@ -1227,8 +1281,7 @@ static int conv_k5_fwd_impl(const char* who, msb_tensor x, const void* packed, c
                            double* sums, int kw_taps, void* stream, void* workspace = nullptr,
                            size_t workspace_bytes = 0) {
   MSB_REQUIRE(view_ok(x) && view_ok(out) && x.dtype == MSB_BF16 && packed && n > 0, "%s: bf16 B8 input view required", who);
-  MSB_REQUIRE(out.dtype == MSB_BF16 || (kw_taps == 1 && !accumulate && sums == nullptr),
-              "%s: f32 output only for the 5x5x1 kernel without accumulate / BN sums", who);
+  MSB_REQUIRE(out.dtype == MSB_BF16 || out.dtype == MSB_F32, "%s: bf16 or f32 B8 output view required", who);
   MSB_REQUIRE(dims.d > 0 && dims.h > 0 && dims.w > 0, "%s: bad dims", who);
   MSB_REQUIRE(x.c % 16 == 0, "%s: input channels must be a multiple of 16 (pad the buffer)", who);
   MSB_REQUIRE(cout > 0 && cout <= out.c && out.c <= 256, "%s: cout must fit the output view (<= 256)", who);

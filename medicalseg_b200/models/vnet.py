@@ -231,8 +231,10 @@ class _K5:
         eng.register_packer(self)
         # bf16 engine: master weight / gradient / momentum of this layer live tap-major ([125][co][ci]), so the weight-
         # gradient atomics land in the gradient buffer itself (no workspace memset, no transposition kernel)
-        self.tap_major = bool(tap_major) and eng.dtype == torch.bfloat16
+        self.tc3 = bool(getattr(eng, "tc3", False))
+        self.tap_major = (bool(tap_major) and eng.dtype == torch.bfloat16) or self.tc3
         eng.store.slots[conv.weight].tap_major = self.tap_major
+        self.packed_f_lo = self.packed_b_lo = None
 
     def repack(self):
         self._pack(*self.pack_args)
@@ -257,6 +259,12 @@ class _K5:
             w = st.raw(self.conv.weight)
             ops.k5_pack_tm(w, self.packed_f, self.cout, self.cin, 0, cin_pad, cout_pad)
             ops.k5_pack_tm(w, self.packed_b, self.cout, self.cin, 1, self.bk_cin_pad, self.bk_cout_pad)
+            if self.tc3:  # lo parts (w - bf16(w)) of both operand images
+                if self.packed_f_lo is None:
+                    self.packed_f_lo = torch.empty_like(self.packed_f)
+                    self.packed_b_lo = torch.empty_like(self.packed_b)
+                ops.k5_pack_tm(w, self.packed_f_lo, self.cout, self.cin, 0 | 2, cin_pad, cout_pad)
+                ops.k5_pack_tm(w, self.packed_b_lo, self.cout, self.cin, 1 | 2, self.bk_cin_pad, self.bk_cout_pad)
         else:
             ops.k5_pack(w, self.packed_f, self.cout, self.cin, 0, cin_pad, cout_pad)
             ops.k5_pack(w, self.packed_b, self.cout, self.cin, 1, self.bk_cin_pad, self.bk_cout_pad)
@@ -265,7 +273,14 @@ class _K5:
     def fwd(self, x: B8, out: B8, sums):
         eng, st = self.eng, self.eng.store
         g = eng.groups(x.n)
-        if eng.dtype == torch.bfloat16:
+        if self.tc3:
+            self._pack(x.c, out.c)
+            xh, xl = eng.split_hi_lo(x)
+            bias = st.view(self.conv.bias)
+            ops.k5_fwd(xh, self.packed_f, bias, self.cout, out, False, None, g, None)
+            ops.k5_fwd(xl, self.packed_f, None, self.cout, out, True, None, g, None)
+            ops.k5_fwd(xh, self.packed_f_lo, None, self.cout, out, True, None, g, sums)
+        elif eng.dtype == torch.bfloat16:
             self._pack(x.c, out.c)
             ops.k5_fwd(x, self.packed_f, st.view(self.conv.bias), self.cout, out, False, None, g, sums,
                        eng.splitk_workspace(x.n, out.c, x.dims, x.c))
@@ -278,7 +293,20 @@ class _K5:
         w, dw, db = st.view(self.conv.weight), st.grad_view(self.conv.weight), st.grad_view(self.conv.bias)
         if eng.bias_grad_is_zero():
             db = None
-        if eng.dtype == torch.bfloat16:
+        if self.tc3:
+            dyh, dyl = eng.split_hi_lo(dy)
+            if dx is not None:
+                ops.k5_fwd(dyh, self.packed_b, None, self.cin, dx, accumulate, ch_scale, 1, None)
+                ops.k5_fwd(dyl, self.packed_b, None, self.cin, dx, True, ch_scale, 1, None)
+                ops.k5_fwd(dyh, self.packed_b_lo, None, self.cin, dx, True, ch_scale, 1, None)
+            xh, xl = eng.split_hi_lo(x)
+            dw_tm = st.grad_raw(self.conv.weight)
+            ops.k5_wgrad_tm(xh, dyh, dw_tm, None, self.cout, self.cin)
+            ops.k5_wgrad_tm(xl, dyh, dw_tm, None, self.cout, self.cin)
+            ops.k5_wgrad_tm(xh, dyl, dw_tm, None, self.cout, self.cin)
+            if db is not None:
+                db += dy.to_ncdhw(self.cout).sum((0, 2, 3, 4))  # eval-mode backward only (a torch reduction: rare path)
+        elif eng.dtype == torch.bfloat16:
             if dx is not None:
                 ops.k5_fwd(dy, self.packed_b, None, self.cin, dx, accumulate, ch_scale, 1, None,
                            eng.splitk_workspace(dy.n, dx.c, dy.dims, dy.c))
@@ -531,7 +559,10 @@ class VNet(_Module):
         self.best_loss = 1000000
         self.num_classes, self.in_channels, self.pretrained = num_classes, in_channels, pretrained
         self.device = torch.device(device or ("cuda:%d" % torch.cuda.current_device()))
-        self.dtype = {"bf16": torch.bfloat16, "f32": torch.float32}[compute_dtype]
+        # 'bf16': tensor-core path; 'f32': CUDA-core parity path; 'f32x3': f32 storage with the 5x5x5 convs on tensor
+        # cores as three bf16 passes (hi*hi + lo*hi + hi*lo, ~2^-16 relative) - BASELINE configs[2]
+        self.dtype = {"bf16": torch.bfloat16, "f32": torch.float32, "f32x3": torch.float32}[compute_dtype]
+        self.tc3 = compute_dtype == "f32x3"
         self.stat_scope = stat_scope
         # sync_bn=True: batch statistics over ALL ranks, the reference's behaviour at world > 1 (cvlibs/config.py:322
         # converts every BatchNorm to SyncBatchNorm).  Costs two tiny f64 all-reduces per BN layer (forward sums,
@@ -706,7 +737,7 @@ class VNet(_Module):
         the normalisation subtracts the per-channel mean, so sum_v dL/dy[v, c] = 0 exactly.  The bf16 path leaves the
         (pre-zeroed) gradient slot untouched instead of summing bf16 rounding noise over millions of voxels; the f32
         parity path still computes the sum like the reference's autograd does."""
-        return self.dtype == torch.bfloat16 and self.bn_training_bwd
+        return (self.dtype == torch.bfloat16 or self.tc3) and self.bn_training_bwd
 
     def strided_wgrad(self, big: B8, small: B8, dw, dbias, kernel, stride, bias_from_big):
         """weight gradient of a down / up conv: tensor-core path (pointwise GEMM over the tap sub-lattices) for bf16"""
@@ -733,6 +764,13 @@ class VNet(_Module):
         if self._sk_ws is None or self._sk_ws.numel() < need:
             self._sk_ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
         return self._sk_ws
+
+    def split_hi_lo(self, x: B8):
+        """f32 B8 activation -> (hi, lo) bf16 B8 tensors for the 3 x bf16 tensor-core passes"""
+        hi = B8(x.n, x.c, x.dims, torch.bfloat16, device=self.device)
+        lo = B8(x.n, x.c, x.dims, torch.bfloat16, device=self.device)
+        ops.split_hi_lo(x, hi, lo)
+        return hi, lo
 
     def workspace(self, nbytes):
         if self._wg_ws is None or self._wg_ws.numel() < nbytes:

@@ -248,6 +248,10 @@ def k5_pack_tm(w_tm, packed, cout, cin, mode, cin_pad, cout_pad):
     call("msb_conv_k5_pack_tm", _ptr(w_tm), _ptr(packed), cout, cin, mode, cin_pad, cout_pad, _stream())
 
 
+def split_hi_lo(x: B8, hi: B8, lo: B8):
+    call("msb_split_hi_lo", x.mt, hi.mt, lo.mt, x.n, x.s, _stream())
+
+
 def k5_wgrad_tm(x: B8, dy: B8, dw_tm, dbias, cout, cin):
     call("msb_conv_k5_wgrad_tm", x.mt, dy.mt, _ptr(dw_tm), _ptr(dbias), cout, cin, x.n, dim3(x.dims), _stream())
 

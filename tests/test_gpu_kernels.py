@@ -358,6 +358,39 @@ def test_conv_k5_tap_major_pack_and_wgrad(cin, cout, dims):
     assert rel(dw_tm.permute(1, 2, 0).reshape(cout, cin, 5, 5, 5), 2 * dw) <= 1e-5
 
 
+@pytest.mark.parametrize("cin,cout,dims", [(32, 32, (9, 16, 16)), (64, 64, (4, 16, 8)), (128, 128, (3, 16, 8))])
+def test_conv_k5_three_pass_fp32(cin, cout, dims):
+    """3 x bf16 fp32 path at the kernel level: split_hi_lo + lo-part weight images + f32-accumulating epilogue reproduce
+    an f64 convolution to ~2^-16 (tolerance 1e-4 of the output range; a single bf16 pass is at 4e-3)."""
+    ops, B8 = _imp()
+    torch.manual_seed(21)
+    n = 2
+    x = torch.randn(n, cin, *dims, device="cuda")
+    w = torch.randn(cout, cin, 5, 5, 5, device="cuda") * (2.0 / (cin * 125)) ** 0.5
+    b = torch.randn(cout, device="cuda")
+    ref = F.conv3d(x.double(), w.double(), b.double(), padding=2).float()
+    xb = B8.from_ncdhw(x, torch.float32)
+    hi, lo = B8(n, cin, dims, torch.bfloat16, device="cuda"), B8(n, cin, dims, torch.bfloat16, device="cuda")
+    ops.split_hi_lo(xb, hi, lo)
+    assert rel(hi.to_ncdhw() + lo.to_ncdhw(), x) <= 2e-5
+    w_tm = w.reshape(cout, cin, 125).permute(2, 0, 1).contiguous()
+    cp = ops.k5_out_pad(cout)
+    p_hi = torch.empty(ops.k5_packed_bytes(cin, cp), dtype=torch.uint8, device="cuda")
+    p_lo = torch.empty_like(p_hi)
+    ops.k5_pack_tm(w_tm, p_hi, cout, cin, 0, cin, cp)
+    ops.k5_pack_tm(w_tm, p_lo, cout, cin, 0 | 2, cin, cp)
+    out = B8(n, cout, dims, torch.float32, device="cuda", zero=True)
+    sums = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
+    ops.k5_fwd(hi, p_hi, b, cout, out, False, None, 1, None)
+    one_pass = rel(out.to_ncdhw(), ref)
+    ops.k5_fwd(lo, p_hi, None, cout, out, True, None, 1, None)
+    ops.k5_fwd(hi, p_lo, None, cout, out, True, None, 1, sums)
+    o = out.to_ncdhw()
+    assert rel(o, ref) <= 1e-4 < one_pass
+    s_ref = o.double().sum((0, 2, 3, 4))
+    assert float((sums[:cout] - s_ref).abs().max()) <= 1e-3 * float(s_ref.abs().max() + 1)
+
+
 @pytest.mark.parametrize("ci,co,dims", [(16, 32, (8, 12, 16)), (64, 128, (4, 8, 32)), (128, 256, (4, 4, 16))])
 def test_k2s2_tensor_core_wgrad(ci, co, dims):
     """2x2x2 stride-2 weight gradients (space-to-depth + pointwise tcgen05 GEMM) for conv and transposed conv"""

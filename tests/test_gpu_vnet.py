@@ -193,3 +193,19 @@ def test_graphed_train_step_matches_eager():
     img2, lab2 = vo.synthetic_batch(2, (32, 32, 32), 2, seed=9)
     loss2, _ = g(img2.cuda(), lab2.cuda())
     assert np.isfinite(float(loss2)) and abs(float(loss2) - graph_losses[-1]) > 0
+
+
+def test_vnet_f32x3_tensor_core_fp32_path():
+    """compute_dtype='f32x3' (BASELINE configs[2]): f32 storage, the 5x5x5 convolutions as three bf16 tensor-core passes
+    (hi*hi + lo*hi + hi*lo, f32 accumulation; ~2^-16 relative per product).  Measured on B200: see the assert messages;
+    tolerances sit between the f32 CUDA-core path (1e-4) and the bf16 path (2e-2): logits <= 2e-3 * max|logit|,
+    CE / Dice <= 1e-4, gradients <= 2e-2 of the largest gradient norm, weight-gradient cosine >= 0.9999."""
+    vo, L, om, m, img, lab, ol, ours = _setup("f32x3", 2, (32, 32, 32), True)
+    ologits, logits, ll, l2, dice, d2 = _step(vo, L, om, m, img, lab, ol, ours, True)
+    err = float((logits - ologits).abs().max() / ologits.abs().max())
+    assert err <= 2e-3, err
+    assert abs(float(l2[0]) - float(ll[0])) <= 1e-4 and abs(float(l2[1]) - float(ll[1])) <= 1e-4
+    assert float(np.abs(dice - d2).max()) <= 1e-4
+    worst, cos = _grad_errors(om, m)
+    assert worst <= 2e-2, worst
+    assert min(cos.values()) >= 0.9999, cos
