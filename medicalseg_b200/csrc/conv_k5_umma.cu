@@ -446,7 +446,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
   }
 }
 
-// split-K tail: out = round_bf16(ws + bias [* ch_scale + out]), BN partial sums of the rounded values, ws <- 0
+// split-K tail: out = round_T(ws + bias [* ch_scale + out]), BN partial sums of the rounded values, ws <- 0
+// (T = bf16, or f32 for the three-pass fp32 engine where each pass accumulates into the f32 output)
+template <typename T>
 __global__ void __launch_bounds__(256) splitk_finalize_kernel(float* __restrict__ ws, const float* __restrict__ bias,
                                                               int cout_real, msb_tensor out, int64_t s, int accumulate,
                                                               const float* __restrict__ ch_scale, int groups,
@@ -471,22 +473,22 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(float* __restrict_
     Vec8<float>::load(wp + v * 8, o);
     *reinterpret_cast<float4*>(wp + v * 8) = make_float4(0.f, 0.f, 0.f, 0.f);
     *reinterpret_cast<float4*>(wp + v * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-    __nv_bfloat16* dst = view_ptr<__nv_bfloat16>(out, n, c8, s, v);
+    T* dst = view_ptr<T>(out, n, c8, s, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] += b[j];
     if (accumulate) {
       float old[8];
-      Vec8<__nv_bfloat16>::load(dst, old);
+      Vec8<T>::load(dst, old);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaf(o[j], sc[j], old[j]);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      o[j] = Vec8<__nv_bfloat16>::round(o[j]);
+      o[j] = Vec8<T>::round(o[j]);
       acc[j] += o[j];
       acc[8 + j] += o[j] * o[j];
     }
-    Vec8<__nv_bfloat16>::store(dst, o);
+    Vec8<T>::store(dst, o);
   }
   if (sums == nullptr) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1127,8 +1129,13 @@ static int launch_fwd_splitk(const msb_tensor& x, msb_dim3 dims, FwdParams& p, i
   MSB_LAUNCH_PDL((conv_k5_fwd_kernel<NPAD, TD, 1, 1, 1, true>), dim3(grid), dim3(kFwdThreads), Cfg::kSmemBytes, st, tmap, p);
   const int64_t S = (int64_t)p.d * p.h * p.w;
   const dim3 fgrid((unsigned)((S + 2047) / 2048), (unsigned)p.out_c8, (unsigned)p.n);
-  MSB_LAUNCH_PDL(splitk_finalize_kernel, fgrid, dim3(256), 0, st, p.ws, bias, p.cout_real, p.out, S, p.accumulate,
-                 p.ch_scale, p.groups, p.sums, p.sums_c);
+  if (p.out_f32) {
+    MSB_LAUNCH_PDL(splitk_finalize_kernel<float>, fgrid, dim3(256), 0, st, p.ws, bias, p.cout_real, p.out, S,
+                   p.accumulate, p.ch_scale, p.groups, p.sums, p.sums_c);
+  } else {
+    MSB_LAUNCH_PDL(splitk_finalize_kernel<__nv_bfloat16>, fgrid, dim3(256), 0, st, p.ws, bias, p.cout_real, p.out, S,
+                   p.accumulate, p.ch_scale, p.groups, p.sums, p.sums_c);
+  }
   return MSB_OK;
 }
 
@@ -1306,7 +1313,7 @@ static int conv_k5_fwd_impl(const char* who, msb_tensor x, const void* packed, c
   cudaStream_t st = as_stream(stream);
   const int npad_sel = msb_conv_k5_out_pad(out.c);
   // NOTE: the packed operand must have been built with cout_pad == npad_sel.
-  if (workspace != nullptr && kw_taps == 5 && out.dtype == MSB_BF16 && (g_debug_flags[6] & 1) == 0) {
+  if (workspace != nullptr && kw_taps == 5 && (g_debug_flags[6] & 1) == 0) {
     const int ks = splitk_slices(npad_sel, n, dims, x.c);
     if (ks > 0) {
       const size_t need = (size_t)n * out.c * S * sizeof(float);

@@ -277,9 +277,10 @@ class _K5:
             self._pack(x.c, out.c)
             xh, xl = eng.split_hi_lo(x)
             bias = st.view(self.conv.bias)
-            ops.k5_fwd(xh, self.packed_f, bias, self.cout, out, False, None, g, None)
-            ops.k5_fwd(xl, self.packed_f, None, self.cout, out, True, None, g, None)
-            ops.k5_fwd(xh, self.packed_f_lo, None, self.cout, out, True, None, g, sums)
+            ws = eng.splitk_workspace(x.n, out.c, x.dims, x.c)
+            ops.k5_fwd(xh, self.packed_f, bias, self.cout, out, False, None, g, None, ws)
+            ops.k5_fwd(xl, self.packed_f, None, self.cout, out, True, None, g, None, ws)
+            ops.k5_fwd(xh, self.packed_f_lo, None, self.cout, out, True, None, g, sums, ws)
         elif eng.dtype == torch.bfloat16:
             self._pack(x.c, out.c)
             ops.k5_fwd(x, self.packed_f, st.view(self.conv.bias), self.cout, out, False, None, g, sums,
@@ -296,9 +297,10 @@ class _K5:
         if self.tc3:
             dyh, dyl = eng.split_hi_lo(dy)
             if dx is not None:
-                ops.k5_fwd(dyh, self.packed_b, None, self.cin, dx, accumulate, ch_scale, 1, None)
-                ops.k5_fwd(dyl, self.packed_b, None, self.cin, dx, True, ch_scale, 1, None)
-                ops.k5_fwd(dyh, self.packed_b_lo, None, self.cin, dx, True, ch_scale, 1, None)
+                ws = eng.splitk_workspace(dy.n, dx.c, dy.dims, dy.c)
+                ops.k5_fwd(dyh, self.packed_b, None, self.cin, dx, accumulate, ch_scale, 1, None, ws)
+                ops.k5_fwd(dyl, self.packed_b, None, self.cin, dx, True, ch_scale, 1, None, ws)
+                ops.k5_fwd(dyh, self.packed_b_lo, None, self.cin, dx, True, ch_scale, 1, None, ws)
             xh, xl = eng.split_hi_lo(x)
             dw_tm = st.grad_raw(self.conv.weight)
             ops.k5_wgrad_tm(xh, dyh, dw_tm, None, self.cout, self.cin)
@@ -745,13 +747,24 @@ class VNet(_Module):
             dbias = None
         kernel, stride = tuple(kernel), tuple(stride)
         taps = kernel[0] * kernel[1] * kernel[2]
-        if (self.dtype == torch.bfloat16 and big.c in (16, 32, 64, 128) and (taps * big.c) % 128 == 0
-                and small.c % 16 == 0 and small.c <= 256 and max(stride[1], stride[2]) <= 4
-                and all(d >= k and (d - k) % s == 0 for d, k, s in zip(big.dims, kernel, stride))):
+        tc_ok = (big.c in (16, 32, 64, 128) and (taps * big.c) % 128 == 0 and small.c % 16 == 0 and small.c <= 256
+                 and max(stride[1], stride[2]) <= 4
+                 and all(d >= k and (d - k) % s == 0 for d, k, s in zip(big.dims, kernel, stride)))
+        if tc_ok and (self.dtype == torch.bfloat16 or self.tc3):
             need = ops.tc_wgrad_workspace_bytes(big.c, small.c, kernel)
             if self._k2_ws is None or self._k2_ws.numel() < need:
                 self._k2_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-            ops.tc_wgrad(big, small, dw, dbias, kernel, stride, bias_from_big, self._k2_ws)
+            if self.tc3:  # f32 storage: three bf16 passes (hi*hi + lo*hi + hi*lo) accumulate into the same f32 dw
+                bh, bl = self.split_hi_lo(big)
+                sh, sl = self.split_hi_lo(small)
+                ops.tc_wgrad(bh, sh, dw, None, kernel, stride, bias_from_big, self._k2_ws)
+                ops.tc_wgrad(bl, sh, dw, None, kernel, stride, bias_from_big, self._k2_ws)
+                ops.tc_wgrad(bh, sl, dw, None, kernel, stride, bias_from_big, self._k2_ws)
+                if dbias is not None:  # eval-mode backward only
+                    src = big if bias_from_big else small
+                    dbias += src.to_ncdhw().sum((0, 2, 3, 4))
+            else:
+                ops.tc_wgrad(big, small, dw, dbias, kernel, stride, bias_from_big, self._k2_ws)
         else:
             ops.conv_strided_wgrad(big, small, dw, dbias, kernel, stride, (0, 0, 0), bias_from_big)
 

@@ -17,6 +17,7 @@ import torch  # noqa: E402
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
     mri = len(sys.argv) > 2 and sys.argv[2] == "mri"  # BASELINE configs[3]: 512x512x12, 20 classes, anisotropic
+    cdt = "f32x3" if len(sys.argv) > 2 and sys.argv[2] == "f32x3" else "bf16"  # BASELINE configs[2]
     import bench
     from medicalseg_b200.models import VNet, losses as L
     from medicalseg_b200.optimizer import Momentum, PolynomialDecay
@@ -27,7 +28,7 @@ def main():
                      kernel_size=[[2, 2, 4], [2, 2, 2], [2, 2, 2], [2, 2, 2]],
                      stride_size=[[2, 2, 1], [2, 2, 1], [2, 2, 2], [2, 2, 2]])
     else:
-        model = VNet(num_classes=bench.NUM_CLASSES, compute_dtype="bf16", seed=0)
+        model = VNet(num_classes=bench.NUM_CLASSES, compute_dtype=cdt, seed=0)
     model.train()
     losses = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1])], "coef": [1]}
     opt = Momentum(PolynomialDecay(0.001, 15000), model.parameters(), 0.9, 1e-4)
