@@ -199,6 +199,16 @@ size_t msb_conv_k5_fwd_workspace_bytes(int n, int cout_view, msb_dim3 dims, int 
 int msb_conv_k5_fwd_ws(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
                        msb_dim3 dims, int accumulate, const float* ch_scale, int groups, double* sums, void* workspace,
                        size_t workspace_bytes, void* stream);
+/* Evaluation-mode LUConv in one kernel (vnet.py:41 `relu1(bn1(conv1(x)))`, and :110 / :154 where the block's residual
+ * is added before the last PReLU, with BatchNorm using its running statistics - core/val.py:93, model.eval()):
+ *   t = prelu((conv(x) + bias) * scale[c] + shift[c], alpha[c]);  out = residual ? prelu(t + residual, alpha2[c]) : t
+ * scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale (f32 [>= out.c], like alpha/alpha2);
+ * residual: NULL or a bf16 B8 view shaped like out (then alpha2 is required).  bf16 output only.  workspace as for
+ * msb_conv_k5_fwd_ws (NULL = regular path). */
+int msb_conv_k5_fwd_act(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
+                        msb_dim3 dims, const float* scale, const float* shift, const float* alpha,
+                        const msb_tensor* residual, const float* alpha2, void* workspace, size_t workspace_bytes,
+                        void* stream);
 /* dw [cout][cin][125] f32 += sum_v x[v+tap] (x) dy[v];  dbias[cout] += sum_v dy[v] (dbias may be NULL).
  * workspace: msb_conv_k5_wgrad_workspace_bytes(cin, cout) bytes of device scratch. */
 size_t msb_conv_k5_wgrad_workspace_bytes(int cin, int cout);
@@ -266,6 +276,12 @@ int msb_dice_ce_fwd(const float* logits, const int32_t* labels, const float* cla
                     int ignore_index, double* acc, void* stream);
 /* result f32 [2+C] = { ce, dice_loss, per_channel_dice[C] } */
 int msb_dice_ce_finalize(const double* acc, int c, float* result, void* stream);
+/* Fused evaluation head (core/infer.py:79-92 argmax + core/val.py:101-118 loss behind out_tr.conv2, vnet.py:173-174):
+ * logits = conv1x1(a) stay in registers.  a: B8 view (8, 16 or 32 channels, the first C live), w [C][C], b [C] or NULL.
+ * Optional outputs (NULL = skip): pred int32 [N][S] (first maximum wins), acc double [3C+2] (+=, as msb_dice_ce_fwd;
+ * needs labels + class_w), psum double [C] (+= softmax sums, as msb_class_weight_sums). */
+int msb_eval_head(msb_tensor a, const float* w, const float* b, const int32_t* labels, const float* class_w, int n,
+                  int c, int64_t s, int ignore_index, int32_t* pred, double* acc, double* psum, void* stream);
 /* dlogits = coef_ce * dCE/dz + coef_dice * dDice/dz; coef_dev (device f32[2], may be NULL) multiplies the
  * two host coefficients so upstream gradients need no host synchronisation. */
 int msb_dice_ce_bwd(const float* logits, const int32_t* labels, const float* class_w, const double* acc,
@@ -293,6 +309,20 @@ int msb_resample_f32(const float* src, msb_dim3 in_dims, float* dst, msb_dim3 ou
                      float p0, float p1, float p2, void* stream);
 int msb_resample_i32(const int32_t* src, msb_dim3 in_dims, int32_t* dst, msb_dim3 out_dims, void* stream);
 int msb_label_remap(int32_t* labels, int64_t count, const int32_t* keys, const int32_t* vals, int nmap, void* stream);
+
+/* ---- training augmentations on the device (medicalseg/transforms/functional.py:77-110, transform.py:46-72) ----
+ * scipy.ndimage.rotate(axes=(axis_a, axis_b), reshape=False, mode='constant', order 0|1) of a [D][H][W] volume:
+ * dst[o] = interp(src, M @ o + off) in every plane, cval outside 0 <= c <= n-1.  M = [[c, s], [-s, c]] with
+ * scipy.special.cosdg/sindg of the angle and off = (n-1)/2 - M @ (n-1)/2, all f64 computed by the caller.  The i32
+ * variant interpolates in f64 and rounds like SciPy (the reference rotates labels with order 1, transform.py:163-165). */
+int msb_rotate3d_f32(const float* src, float* dst, msb_dim3 dims, int axis_a, int axis_b, double m00, double m01,
+                     double m10, double m11, double off0, double off1, int order, float cval, void* stream);
+int msb_rotate3d_i32(const int32_t* src, int32_t* dst, msb_dim3 dims, int axis_a, int axis_b, double m00, double m01,
+                     double m10, double m11, double off0, double off1, int order, int32_t cval, void* stream);
+/* np.flip(volume, axis) for 4-byte elements, out of place (functional.py:77-85) */
+int msb_flip3d(const void* src, void* dst, msb_dim3 dims, int axis, void* stream);
+/* Compose (transform.py:67-69): dst = src / max if max > 0 else src; minmax = device {min, max} from msb_minmax */
+int msb_scale_by_max(const float* src, float* dst, int64_t count, const float* minmax, void* stream);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,7 @@ SIGNATURES = {
     "msb_conv_k5_fwd": (I, [T, P, P, I, T, I, D3, I, P, I, P, P]),
     "msb_conv_k5_fwd_workspace_bytes": (SZ, [I, I, D3, I]),
     "msb_conv_k5_fwd_ws": (I, [T, P, P, I, T, I, D3, I, P, I, P, P, SZ, P]),
+    "msb_conv_k5_fwd_act": (I, [T, P, P, I, T, I, D3, P, P, P, C.POINTER(MsbTensor), P, P, SZ, P]),
     "msb_conv_k5_pack_tm": (I, [P, P, I, I, I, I, I, P]),
     "msb_split_hi_lo": (I, [T, T, T, I, L, P]),
     "msb_conv_k5_wgrad_tm": (I, [T, T, P, P, I, I, I, D3, P]),
@@ -81,6 +82,7 @@ SIGNATURES = {
     "msb_class_weight_finalize": (I, [P, D, I, P, P]),
     "msb_dice_ce_fwd": (I, [P, P, P, I, I, L, I, P, P]),
     "msb_dice_ce_finalize": (I, [P, I, P, P]),
+    "msb_eval_head": (I, [T, P, P, P, P, I, I, L, I, P, P, P, P]),
     "msb_dice_ce_bwd": (I, [P, P, P, P, I, I, L, I, F, F, P, P, P]),
     "msb_momentum_step": (I, [P, P, P, L, F, F, F, F, P]),
     "msb_momentum_step_lrdev": (I, [P, P, P, L, P, F, F, F, P]),
@@ -90,6 +92,10 @@ SIGNATURES = {
     "msb_resample_f32": (I, [P, D3, P, D3, I, I, F, F, F, P]),
     "msb_resample_i32": (I, [P, D3, P, D3, P]),
     "msb_label_remap": (I, [P, L, P, P, I, P]),
+    "msb_rotate3d_f32": (I, [P, P, D3, I, I, D, D, D, D, D, D, I, F, P]),
+    "msb_rotate3d_i32": (I, [P, P, D3, I, I, D, D, D, D, D, D, I, I, P]),
+    "msb_flip3d": (I, [P, P, D3, I, P]),
+    "msb_scale_by_max": (I, [P, P, L, P, P]),
 }
 
 _NO_STATUS = {"msb_version", "msb_last_error_string", "msb_conv_k5_packed_bytes", "msb_conv_k5_out_pad",

@@ -51,8 +51,12 @@ def evaluate(model, eval_dataset, losses, num_workers=0, print_detail=True, save
     with torch.no_grad():
         for it, idx in enumerate(indices):
             im, label = _collate(eval_dataset, [idx], device)
-            pred, logits = inference(model, im, ori_shape=label.shape[-3:])
-            loss, per_channel_dice = loss_computation([logits], label.to(torch.int32), new_loss)
+            fused = model.predict_with_losses(im, label, new_loss) if hasattr(model, "predict_with_losses") else None
+            if fused is not None:  # 1x1x1 head + argmax + loss sums in one kernel (no logits round trip)
+                pred, loss, per_channel_dice = fused
+            else:
+                pred, logits = inference(model, im, ori_shape=label.shape[-3:])
+                loss, per_channel_dice = loss_computation([logits], label.to(torch.int32), new_loss)
             loss_all += float(sum(loss))
             mdice += float(np.mean(per_channel_dice))
             channel_dice = per_channel_dice if channel_dice is None else channel_dice + per_channel_dice

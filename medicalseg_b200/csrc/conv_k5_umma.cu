@@ -81,6 +81,12 @@ struct FwdParams {
   msb_tensor out;
   int accumulate;
   const float* ch_scale;
+  const float* ep_scale;   // evaluation epilogue (all three per output channel, length >= out.c) or nullptr
+  const float* ep_shift;
+  const float* ep_alpha;
+  const float* ep_alpha2;  // PReLU applied after the residual add (required with ep_res)
+  msb_tensor ep_res;       // optional residual (bf16 B8 view of the output's shape)
+  int ep_has_res;
   int groups;
   double* sums;
   int sums_c;                            // channel count of the sums array
@@ -386,6 +392,28 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
                   for (int j = 0; j < 8; ++j) acc[k * 8 + j] += old[j];
                 }
               }
+              if (p.ep_scale != nullptr) {
+                // evaluation epilogue: running-statistics BatchNorm folded to y*scale + shift, PReLU, and for a
+                // block's last LUConv the residual add + second PReLU (vnet.py:41, :110, :154 in eval mode) - the
+                // conv output never makes a separate BN pass
+                float r[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[j] = 0.f;
+                if (p.ep_has_res) Vec8<__nv_bfloat16>::load(view_ptr<__nv_bfloat16>(p.ep_res, n, c8, S, v), r);
+                const float* scp = p.ep_scale + c8 * 8;
+                const float* shp = p.ep_shift + c8 * 8;
+                const float* alp = p.ep_alpha + c8 * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float t = fmaf(acc[k * 8 + j], __ldg(scp + j), __ldg(shp + j));
+                  t = t > 0.f ? t : t * __ldg(alp + j);
+                  if (p.ep_has_res) {  // block tail: relu2(relu1(bn(conv)) + residual)
+                    t += r[j];
+                    t = t > 0.f ? t : t * __ldg(p.ep_alpha2 + c8 * 8 + j);
+                  }
+                  acc[k * 8 + j] = t;
+                }
+              }
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const __nv_bfloat162 hpair = __floats2bfloat162_rn(acc[k * 8 + 2 * i], acc[k * 8 + 2 * i + 1]);
@@ -452,7 +480,12 @@ template <typename T>
 __global__ void __launch_bounds__(256) splitk_finalize_kernel(float* __restrict__ ws, const float* __restrict__ bias,
                                                               int cout_real, msb_tensor out, int64_t s, int accumulate,
                                                               const float* __restrict__ ch_scale, int groups,
-                                                              double* __restrict__ sums, int sums_c) {
+                                                              double* __restrict__ sums, int sums_c,
+                                                              const float* __restrict__ ep_scale,
+                                                              const float* __restrict__ ep_shift,
+                                                              const float* __restrict__ ep_alpha,
+                                                              const float* __restrict__ ep_alpha2, msb_tensor ep_res,
+                                                              int ep_has_res) {
   pdl_wait();
   pdl_trigger();
   __shared__ float red[8][16];
@@ -481,6 +514,22 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(float* __restrict_
       Vec8<T>::load(dst, old);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaf(o[j], sc[j], old[j]);
+    }
+    if (ep_scale != nullptr) {  // evaluation epilogue, as in conv_k5_fwd_kernel
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = 0.f;
+      if (ep_has_res) Vec8<T>::load(view_ptr<T>(ep_res, n, c8, s, v), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = fmaf(o[j], __ldg(ep_scale + c8 * 8 + j), __ldg(ep_shift + c8 * 8 + j));
+        t = t > 0.f ? t : t * __ldg(ep_alpha + c8 * 8 + j);
+        if (ep_has_res) {
+          t += r[j];
+          t = t > 0.f ? t : t * __ldg(ep_alpha2 + c8 * 8 + j);
+        }
+        o[j] = t;
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -1131,10 +1180,12 @@ static int launch_fwd_splitk(const msb_tensor& x, msb_dim3 dims, FwdParams& p, i
   const dim3 fgrid((unsigned)((S + 2047) / 2048), (unsigned)p.out_c8, (unsigned)p.n);
   if (p.out_f32) {
     MSB_LAUNCH_PDL(splitk_finalize_kernel<float>, fgrid, dim3(256), 0, st, p.ws, bias, p.cout_real, p.out, S,
-                   p.accumulate, p.ch_scale, p.groups, p.sums, p.sums_c);
+                   p.accumulate, p.ch_scale, p.groups, p.sums, p.sums_c, p.ep_scale, p.ep_shift, p.ep_alpha, p.ep_alpha2,
+                   p.ep_res, p.ep_has_res);
   } else {
     MSB_LAUNCH_PDL(splitk_finalize_kernel<__nv_bfloat16>, fgrid, dim3(256), 0, st, p.ws, bias, p.cout_real, p.out, S,
-                   p.accumulate, p.ch_scale, p.groups, p.sums, p.sums_c);
+                   p.accumulate, p.ch_scale, p.groups, p.sums, p.sums_c, p.ep_scale, p.ep_shift, p.ep_alpha, p.ep_alpha2,
+                   p.ep_res, p.ep_has_res);
   }
   return MSB_OK;
 }
@@ -1286,7 +1337,9 @@ int msb_conv_k5_out_pad(int cout_view);
 static int conv_k5_fwd_impl(const char* who, msb_tensor x, const void* packed, const float* bias, int cout,
                            msb_tensor out, int n, msb_dim3 dims, int accumulate, const float* ch_scale, int groups,
                            double* sums, int kw_taps, void* stream, void* workspace = nullptr,
-                           size_t workspace_bytes = 0) {
+                           size_t workspace_bytes = 0, const float* ep_scale = nullptr, const float* ep_shift = nullptr,
+                           const float* ep_alpha = nullptr, const float* ep_alpha2 = nullptr,
+                           const msb_tensor* ep_res = nullptr) {
   MSB_REQUIRE(view_ok(x) && view_ok(out) && x.dtype == MSB_BF16 && packed && n > 0, "%s: bf16 B8 input view required", who);
   MSB_REQUIRE(out.dtype == MSB_BF16 || out.dtype == MSB_F32, "%s: bf16 or f32 B8 output view required", who);
   MSB_REQUIRE(dims.d > 0 && dims.h > 0 && dims.w > 0, "%s: bad dims", who);
@@ -1303,6 +1356,15 @@ static int conv_k5_fwd_impl(const char* who, msb_tensor x, const void* packed, c
   p.packed = packed; p.bias = bias; p.out = out; p.accumulate = accumulate; p.ch_scale = ch_scale;
   p.groups = groups; p.sums = sums; p.sums_c = out.c; p.dbg_swap = 0;
   p.kw_taps = kw_taps; p.out_f32 = out.dtype == MSB_F32;
+  p.ep_scale = ep_scale; p.ep_shift = ep_shift; p.ep_alpha = ep_alpha; p.ep_alpha2 = ep_alpha2;
+  p.ep_has_res = ep_res != nullptr;
+  p.ep_res = ep_res != nullptr ? *ep_res : out;
+  if (ep_scale != nullptr) {
+    MSB_REQUIRE(ep_shift && ep_alpha && out.dtype == MSB_BF16 && !accumulate && sums == nullptr,
+                "%s: the evaluation epilogue needs scale, shift and alpha, a bf16 output, no accumulate and no BN sums", who);
+    MSB_REQUIRE(ep_res == nullptr || (view_ok(*ep_res) && ep_res->dtype == MSB_BF16 && ep_res->c >= out.c && ep_alpha2),
+                "%s: the residual must be a bf16 B8 view with at least the output's channels and needs alpha2", who);
+  }
   p.prof = nullptr;
   if (g_debug_flags[5]) {
     if (g_prof_buf == nullptr) MSB_CUDA_OK(cudaMalloc(&g_prof_buf, kNumSMs * 4 * sizeof(long long)));
@@ -1365,6 +1427,15 @@ int msb_conv_k5_fwd_ws(msb_tensor x, const void* packed, const float* bias, int 
                        size_t workspace_bytes, void* stream) {
   return conv_k5_fwd_impl("msb_conv_k5_fwd_ws", x, packed, bias, cout, out, n, dims, accumulate, ch_scale, groups, sums,
                           5, stream, workspace, workspace_bytes);
+}
+
+int msb_conv_k5_fwd_act(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
+                        msb_dim3 dims, const float* scale, const float* shift, const float* alpha,
+                        const msb_tensor* residual, const float* alpha2, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  MSB_REQUIRE(scale != nullptr, "msb_conv_k5_fwd_act: scale / shift / alpha are required");
+  return conv_k5_fwd_impl("msb_conv_k5_fwd_act", x, packed, bias, cout, out, n, dims, 0, nullptr, 1, nullptr, 5, stream,
+                          workspace, workspace_bytes, scale, shift, alpha, alpha2, residual);
 }
 
 int msb_conv_k551_fwd(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,

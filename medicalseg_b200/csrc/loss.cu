@@ -210,6 +210,130 @@ __global__ void __launch_bounds__(kLossThreads)
   }
 }
 
+// ---- fused evaluation head ---------------------------------------------------------------------------
+// core/infer.py:79-92 (argmax of the logits) + core/val.py:101-118 (loss of the same logits) behind out_tr's 1x1x1
+// conv (vnet.py:173-174): the logits of a voxel live only in registers - they are never written to HBM (252 MB per
+// MRI volume in f32).  Same fmaf order as conv1x1_fwd_kernel, so the logits are bit-identical to the unfused path.
+// Optional outputs: pred (int32 argmax, first maximum wins like paddle/torch argmax), acc ([3C+2] as
+// dice_ce_fwd_kernel), psum ([C] softmax sums for the CE class weights, loss_utils.py:31-40).
+// MODE 0: prediction only; 1: prediction + loss sums; 2: class-weight softmax sums only (separate instantiations
+// keep the 3*CMAX+2 loss accumulators and the CMAX softmax sums out of each other's register budget)
+template <typename T, int CI8, int CMAX, int MODE>
+__global__ void __launch_bounds__(kLossThreads)
+    eval_head_kernel(msb_tensor a, const float* __restrict__ w2, const float* __restrict__ b2,
+                     const int32_t* __restrict__ labels, const float* __restrict__ class_w, int c, int64_t s,
+                     int ignore_index, int32_t* __restrict__ pred, double* __restrict__ out,
+                     double* __restrict__ psum) {
+  constexpr int kAcc = MODE == 1 ? 3 * CMAX + 2 : (MODE == 2 ? CMAX : 1);
+  __shared__ __align__(16) float wsm[CMAX * CI8 * 8 + 2 * CMAX];
+  __shared__ float red[kLossThreads / 32][kAcc];
+  float* bsm = wsm + CMAX * CI8 * 8;
+  float* cwsm = bsm + CMAX;
+  const int ci = c;  // the 1x1x1 conv is C -> C
+  for (int i = threadIdx.x; i < CMAX * CI8 * 8; i += kLossThreads) {  // transposed: wsm[input j][output o]
+    const int j = i / CMAX, o = i % CMAX;
+    wsm[i] = (o < c && j < ci) ? w2[o * ci + j] : 0.f;
+  }
+  for (int i = threadIdx.x; i < CMAX; i += kLossThreads) {
+    bsm[i] = (b2 != nullptr && i < c) ? b2[i] : 0.f;
+    cwsm[i] = (MODE == 1 && i < c) ? class_w[i] : 0.f;
+  }
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int64_t v0 = (int64_t)blockIdx.x * kLossVoxPerBlock;
+  const int64_t v1 = min(v0 + (int64_t)kLossVoxPerBlock, s);
+  float acc[kAcc];
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) acc[k] = 0.f;
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += kLossThreads) {
+    // z[o] = b[o] + sum_i w[o][i] * x[i], i ascending per output (the order of conv1x1_fwd_kernel).  One 8-channel
+    // group per (rolled) iteration: a fully unrolled C x C product makes ptxas give up on register allocation.
+    float z[CMAX];
+#pragma unroll
+    for (int o = 0; o < CMAX; ++o) z[o] = bsm[o];
+    const int groups = (ci + 7) >> 3;
+#pragma unroll 1
+    for (int k = 0; k < groups; ++k) {
+      float t[8];
+      Vec8<T>::load(view_ptr<T>(a, n, k, s, v), t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4* wrow = reinterpret_cast<const float4*>(wsm + (k * 8 + j) * CMAX);
+#pragma unroll
+        for (int o4 = 0; o4 < CMAX / 4; ++o4) {
+          const float4 w4 = wrow[o4];  // rows j >= ci are zero: fmaf(0, finite, z) == z
+          z[o4 * 4 + 0] = fmaf(w4.x, t[j], z[o4 * 4 + 0]);
+          z[o4 * 4 + 1] = fmaf(w4.y, t[j], z[o4 * 4 + 1]);
+          z[o4 * 4 + 2] = fmaf(w4.z, t[j], z[o4 * 4 + 2]);
+          z[o4 * 4 + 3] = fmaf(w4.w, t[j], z[o4 * 4 + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < CMAX; ++o)
+      if (o >= c) z[o] = -INFINITY;
+    if constexpr (MODE != 2) {
+      int best = 0;
+      float zbest = z[0];
+#pragma unroll
+      for (int o = 1; o < CMAX; ++o)
+        if (z[o] > zbest) { zbest = z[o]; best = o; }
+      if (pred != nullptr) pred[(int64_t)n * s + v] = best;
+    }
+    if constexpr (MODE == 1) {
+      const int y = __ldg(labels + (int64_t)n * s + v);
+      float zy = 0.f, wy = 0.f;
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k) {
+        if (k < c) {
+          const float p = 1.f / (1.f + expf(-z[k]));
+          const bool hit = (y == k);
+          acc[k] += hit ? p : 0.f;
+          acc[CMAX + k] += p * p;
+          acc[2 * CMAX + k] += hit ? 1.f : 0.f;
+          if (hit) { zy = z[k]; wy = cwsm[k]; }
+        }
+      }
+      if (y != ignore_index && y >= 0 && y < c) {
+        float ls;
+        const float m = softmax_inplace<CMAX>(z, c, ls);
+        acc[3 * CMAX] += wy * (m + ls - zy);
+        acc[3 * CMAX + 1] += wy;
+      }
+    }
+    if constexpr (MODE == 2) {
+      float ls;
+      softmax_inplace<CMAX>(z, c, ls);
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k) acc[k] += z[k];
+    }
+  }
+  if constexpr (MODE == 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < kAcc; ++i) {
+    const float r = warp_sum(acc[i]);
+    if (lane == 0) red[warp][i] = r;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kAcc; i += kLossThreads) {
+    int dst;
+    if constexpr (MODE == 1) {
+      const int grp = i / CMAX, k = i % CMAX;
+      if (i >= 3 * CMAX) dst = 3 * c + (i - 3 * CMAX);
+      else if (k < c) dst = grp * c + k;
+      else continue;
+    } else {
+      if (i >= c) continue;
+      dst = i;
+    }
+    double t = 0;
+#pragma unroll
+    for (int wv = 0; wv < kLossThreads / 32; ++wv) t += (double)red[wv][i];
+    atomicAdd((MODE == 1 ? out : psum) + dst, t);
+  }
+}
+
 }  // namespace msb
 
 using namespace msb;
@@ -265,6 +389,38 @@ int msb_dice_ce_bwd(const float* logits, const int32_t* labels, const float* cla
   const dim3 grid((unsigned)((s + kLossVoxPerBlock - 1) / kLossVoxPerBlock), (unsigned)n);
   MSB_DISPATCH_CMAX(c, dice_ce_bwd_kernel<CMAX><<<grid, kLossThreads, 0, as_stream(stream)>>>(
                            logits, labels, class_w, acc, c, s, ignore_index, coef_ce, coef_dice, coef_dev, dlogits););
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+int msb_eval_head(msb_tensor a, const float* w, const float* b, const int32_t* labels, const float* class_w, int n,
+                  int c, int64_t s, int ignore_index, int32_t* pred, double* acc, double* psum, void* stream) {
+  MSB_REQUIRE(view_ok(a) && w && n > 0 && c > 0 && c <= 32 && c <= a.c && s > 0 &&
+                  (a.c == 8 || a.c == 16 || a.c == 32),
+              "msb_eval_head: needs 1 <= C <= 32 and an 8-, 16- or 32-channel B8 view with C <= channels");
+  MSB_REQUIRE((pred != nullptr || acc != nullptr) != (psum != nullptr),
+              "msb_eval_head: request either pred / acc, or psum (the class-weight pass), not both or neither");
+  MSB_REQUIRE(acc == nullptr || (labels != nullptr && class_w != nullptr),
+              "msb_eval_head: the loss sums need labels and class weights");
+  const dim3 grid((unsigned)((s + kLossVoxPerBlock - 1) / kLossVoxPerBlock), (unsigned)n);
+  cudaStream_t st = as_stream(stream);
+  const int mode = psum != nullptr ? 2 : (acc != nullptr ? 1 : 0);
+#define MSB_EVAL_HEAD_M(CI8_, CMAX_, MODE_)                                                                        \
+  eval_head_kernel<T, CI8_, CMAX_, MODE_><<<grid, kLossThreads, 0, st>>>(a, w, b, labels, class_w, c, s,           \
+                                                                          ignore_index, pred, acc, psum)
+#define MSB_EVAL_HEAD(CI8_, CMAX_)                      \
+  do {                                                  \
+    if (mode == 0) MSB_EVAL_HEAD_M(CI8_, CMAX_, 0);     \
+    else if (mode == 1) MSB_EVAL_HEAD_M(CI8_, CMAX_, 1); \
+    else MSB_EVAL_HEAD_M(CI8_, CMAX_, 2);               \
+  } while (0)
+  MSB_DISPATCH_DTYPE(a.dtype, {
+    if (a.c == 8) { if (c <= 4) MSB_EVAL_HEAD(1, 4); else MSB_EVAL_HEAD(1, 8); }
+    else if (a.c == 16) { if (c <= 4) MSB_EVAL_HEAD(2, 4); else if (c <= 8) MSB_EVAL_HEAD(2, 8); else MSB_EVAL_HEAD(2, 16); }
+    else { if (c <= 20) MSB_EVAL_HEAD(4, 20); else MSB_EVAL_HEAD(4, 32); }
+  });
+#undef MSB_EVAL_HEAD
+#undef MSB_EVAL_HEAD_M
   MSB_LAUNCH_OK();
   return MSB_OK;
 }

@@ -62,8 +62,10 @@ def _register_defaults():
     from .models import VNet
     from .models.losses import CrossEntropyLoss, DiceLoss, MixedLoss
     from .datasets import NpyVolumeDataset, SyntheticVolumes
+    from .transforms import Compose, RandomFlip3D, RandomResizedCrop3D, RandomRotation3D, Resize3D
     for mgr, comps in ((MODELS, [VNet]), (LOSSES, [CrossEntropyLoss, DiceLoss, MixedLoss]),
-                       (DATASETS, [NpyVolumeDataset, SyntheticVolumes])):
+                       (DATASETS, [NpyVolumeDataset, SyntheticVolumes]),
+                       (TRANSFORMS, [Compose, RandomFlip3D, RandomResizedCrop3D, RandomRotation3D, Resize3D])):
         for c in comps:
             if c.__name__ not in mgr.components_dict:
                 mgr.add_component(c)

@@ -1,7 +1,8 @@
 """Datasets (reference: medicalseg/datasets/dataset.py:28-125).  The .npy reader keeps the reference contract —
 `<dataset_root>/{train,val}_list.txt` with "image.npy label.npy" pairs, items are (im [1,D,H,W] f32 scaled by its
-max as transforms/transform.py:67-69, label [D,H,W] int, path).  Augmentation transforms stay out of scope
-(CPU data plumbing); `SyntheticVolumes` feeds the benchmark / smoke configurations."""
+max as transforms/transform.py:67-69, label [D,H,W] int, path).  A `transforms` list (configs: RandomResizedCrop3D,
+RandomRotation3D, RandomFlip3D ...) is wrapped in `transforms.Compose` as dataset.py:113 does and runs ON THE DEVICE:
+the item then comes back as CUDA tensors.  `SyntheticVolumes` feeds the benchmark / smoke configurations."""
 from __future__ import annotations
 
 import os
@@ -40,7 +41,10 @@ class NpyVolumeDataset:
                  ignore_index=255, dataset_json_path="", **_):
         self.dataset_root, self.result_dir, self.mode = dataset_root, result_dir, mode.lower()
         self.num_classes, self.ignore_index, self.dataset_json_path = num_classes, ignore_index, dataset_json_path
-        self.transforms = transforms
+        self.transforms = None
+        if transforms:  # dataset.py:113: T.Compose(transforms); an empty list means "only read the volumes"
+            from .transforms import Compose
+            self.transforms = transforms if isinstance(transforms, Compose) else Compose(list(transforms))
         if self.mode not in ("train", "val"):
             raise ValueError("`mode` should be 'train' or 'val', but got {}.".format(mode))
         if num_classes is None:
@@ -62,6 +66,9 @@ class NpyVolumeDataset:
 
     def __getitem__(self, idx):
         image_path, label_path = self.file_list[idx]
+        if self.transforms is not None:
+            im, label = self.transforms(image_path, label_path)  # device tensors: [1,D,H,W] f32 / max, [D,H,W] i32
+            return im, label, image_path
         im = np.load(image_path).astype(np.float32)
         label = np.load(label_path)
         im = im[None]

@@ -249,3 +249,67 @@ def loss_computation(logits_list, labels, losses, edges=None):
         else:
             loss_list.append(coef_i * loss_i(logits, labels))
     return loss_list, per_channel_dice
+
+
+# ---- evaluation fast path: losses + argmax fused behind the model's 1x1x1 head ---------------------------------
+def fused_head_plan(losses):
+    """(ce, dice, terms) for the loss configurations the fused evaluation head covers - one logits tensor scored by a
+    DiceLoss, a CrossEntropyLoss or a MixedLoss of those (what core/val.py:95 builds from the shipped configs) - else
+    None.  terms = [(kind, coefficient)] in loss_computation's output order."""
+    if losses is None or len(losses["types"]) != 1:
+        return None
+    obj, coef = losses["types"][0], losses["coef"][0]
+    name = type(obj).__name__
+    if name == "MixedLoss":
+        parts = [(type(l).__name__, l, c) for l, c in zip(obj.losses, obj.coef)]
+    else:
+        parts = [(name, obj, 1)]
+    ce = dice = None
+    terms = []
+    for kind, l, c in parts:
+        if kind == "CrossEntropyLoss" and ce is None:
+            ce = l
+            terms.append((0, coef * c))
+        elif kind == "DiceLoss" and dice is None:
+            dice = l
+            terms.append((1, coef * c))
+        else:
+            return None
+    return ce, dice, terms
+
+
+def fused_head_losses(ao, w2, b2, c, dims, labels, losses, plan):
+    """runs ops.eval_head on the activated out_tr features `ao` (B8); see VNet.predict_with_losses"""
+    n, dev = ao.n, ao.buf.device
+    pred = torch.empty((n, 1, *dims), dtype=torch.int32, device=dev)
+    if labels is None:
+        ops.eval_head(ao, w2, b2, None, None, c, 255, pred=pred)
+        return pred, None, None
+    ce, dice, terms = plan
+    if labels.dim() == 3:
+        labels = labels.unsqueeze(0)
+    assert "int" in str(labels.dtype), "The label should be int but got {}".format(labels.dtype)
+    labels = labels.to(torch.int32).contiguous()
+    ignore_index = ce.ignore_index if ce is not None else 255
+    if ce is not None:
+        if ce.weight is None:  # first logits ever seen define the class weights (cross_entropy_loss.py:68-69)
+            psum = torch.zeros(c, dtype=torch.float64, device=dev)
+            ops.eval_head(ao, w2, b2, None, None, c, ignore_index, psum=psum)
+            ce.weight = torch.empty(c, dtype=torch.float32, device=dev)
+            ops.class_weight_finalize(psum, float(n * ao.s), c, ce.weight)
+        ce.weight = ce.weight.to(dev)
+        if c != len(ce.weight):
+            raise ValueError("The number of weights = {} must be the same as the number of classes = {}.".format(
+                len(ce.weight), c))
+        class_w = ce.weight
+    else:
+        if dice._ones is None or dice._ones.numel() != c or dice._ones.device != dev:
+            dice._ones = torch.ones(c, dtype=torch.float32, device=dev)
+        class_w = dice._ones
+    acc = torch.zeros(3 * c + 2, dtype=torch.float64, device=dev)
+    result = torch.empty(2 + c, dtype=torch.float32, device=dev)
+    ops.eval_head(ao, w2, b2, labels, class_w, c, ignore_index, pred=pred, acc=acc)
+    ops.dice_ce_finalize(acc, c, result)
+    loss_list = [result[kind] * coef for kind, coef in terms]
+    per_channel_dice = LazyHostArray(result[2:]) if dice is not None else None
+    return pred, loss_list, per_channel_dice

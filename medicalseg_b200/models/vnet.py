@@ -172,6 +172,19 @@ class _BnAct:
         self.eng, self.bn, self.relu1, self.relu2 = eng, bn, relu1, relu2
         self.saved = None
         self.bnbuf = None
+        self._affine, self._affine_key = None, None
+
+    def eval_affine(self):
+        """(scale, shift) of the running-statistics BatchNorm: y*scale + shift with scale = gamma/sqrt(var+eps) and
+        shift = beta - mean*scale, cached until the parameters or the running statistics change"""
+        eng, st = self.eng, self.eng.store
+        key = (eng.param_version, eng.bn_stats_version)
+        if self._affine_key != key:
+            var = st.phys(self.bn.var).double()
+            scale = (st.phys(self.bn.weight).double() / torch.sqrt(var + BN_EPS)).float()  # kernels: f64 rsqrt, f32 product
+            shift = st.phys(self.bn.bias) - st.phys(self.bn.mean) * scale
+            self._affine, self._affine_key = (scale.contiguous(), shift.contiguous()), key
+        return self._affine
 
     def fwd(self, y: B8, out: B8, sums, residual: Optional[B8] = None, tile=None, tile_c=0):
         eng, st = self.eng, self.eng.store
@@ -288,6 +301,16 @@ class _K5:
         else:
             ops.conv_strided_fwd(x, st.view(self.conv.weight), st.view(self.conv.bias), out, (5, 5, 5), (1, 1, 1),
                                  (2, 2, 2), g, sums, self.cin, self.cout)
+
+    def fwd_act(self, x: B8, out: B8, act: "_BnAct", residual: Optional[B8] = None):
+        """evaluation-mode LUConv in one kernel: running-statistics BN, PReLU and (block tail) residual + second PReLU
+        run in the conv epilogue (msb_conv_k5_fwd_act) instead of a separate pass over the activation"""
+        eng, st = self.eng, self.eng.store
+        self._pack(x.c, out.c)
+        scale, shift = act.eval_affine()
+        a2 = st.phys(act.relu2._weight) if residual is not None else None
+        ops.k5_fwd_act(x, self.packed_f, st.view(self.conv.bias), self.cout, out, scale, shift,
+                       st.phys(act.relu1._weight), residual, a2, eng.splitk_workspace(x.n, out.c, x.dims, x.c))
 
     def bwd(self, x: B8, dy: B8, dx: Optional[B8], accumulate=False, ch_scale=None):
         eng, st = self.eng, self.eng.store
@@ -572,6 +595,7 @@ class VNet(_Module):
         self.sync_bn = bool(sync_bn)
         self.training = True
         self.bn_training_bwd = True
+        self.bn_stats_version = 0
         self.param_version = 0
         self.store = ParamStore()
         k, s = [tuple(v) for v in kernel_size], [tuple(v) for v in stride_size]
@@ -715,6 +739,26 @@ class VNet(_Module):
             return [_VNetFunction.apply(x, self._anchor, self)]
         return [self._forward(x, record=False)]
 
+    def predict_with_losses(self, x, labels=None, losses=None):
+        """Evaluation fast path (core/val.py:101-118 = infer.inference argmax + loss_computation of the same logits):
+        out_tr's 1x1x1 conv, the argmax and the Dice / CE sums run in ONE kernel, so the logits never reach HBM.
+        Returns (pred int32 [N,1,D,H,W], loss_list, per_channel_dice) - the last two None without labels - or None when
+        the loss configuration is not one the fused head covers (the caller then uses forward() + loss_computation)."""
+        from . import losses as L
+        if self.training:
+            raise RuntimeError("predict_with_losses is an eval-mode path: call model.eval() first")
+        if not x.is_cuda:
+            raise RuntimeError("VNet.predict_with_losses needs a CUDA tensor (no CPU fallback)")
+        plan = L.fused_head_plan(losses) if labels is not None else ()
+        if plan is None:
+            return None
+        x = x.to(torch.float32).contiguous()
+        with torch.no_grad():
+            ao = self._forward(x, record=False, head=False)
+            ot, st = self.out_tr, self.store
+            return L.fused_head_losses(ao, st.view(ot.conv2.weight), st.view(ot.conv2.bias), self.num_classes,
+                                       tuple(x.shape[2:]), labels, losses, plan)
+
     # ---------------------------------------------------------------- helpers
     def groups(self, n):
         return 1 if self.stat_scope == "batch" else n
@@ -825,7 +869,7 @@ class VNet(_Module):
         return tuple((d - kk) // ss + 1 for d, kk, ss in zip(dims, k, s))
 
     # ---------------------------------------------------------------- forward
-    def _forward(self, x: torch.Tensor, record: bool = False) -> torch.Tensor:
+    def _forward(self, x: torch.Tensor, record: bool = False, head: bool = True):
         st, T = self.store, self.training
         n = x.shape[0]
         g = self.groups(n)
@@ -839,6 +883,13 @@ class VNet(_Module):
 
         def sums(c):
             return self.scratch_f64(2 * g * c) if T else None
+
+        # evaluation (running-statistics BN, nothing recorded for backward): every LUConv is ONE kernel - BN, PReLU and
+        # the block's residual tail run in the conv epilogue (eval_fused_epilogue=False keeps the separate BN pass)
+        fuse_eval = (not T and not record and self.dtype == torch.bfloat16 and not self.tc3
+                     and getattr(self, "eval_fused_epilogue", True))
+        if T:
+            self.bn_stats_version += 1  # a train-mode forward moves the running statistics
 
         # concat buffers: [up-branch | skip] (vnet.py:152 order)
         xcat32 = self._new(n, 32, dims[0])
@@ -880,12 +931,15 @@ class VNet(_Module):
             rec = {"xin": xin, "down": dwn, "mask": mask, "lu_in": []}
             for i, lu in enumerate(tr.ops):
                 rec["lu_in"].append(cur)
-                y = self._new(n, c, dims[lvl])
-                sl = sums(c)
-                lu.k5.fwd(cur, y, sl)
                 last = i == len(tr.ops) - 1
                 nxt = out if last else self._new(n, c, dims[lvl])
-                lu.act.fwd(y, nxt, sl, residual=dwn if last else None)
+                if fuse_eval:
+                    lu.k5.fwd_act(cur, nxt, lu.act, residual=dwn if last else None)
+                else:
+                    y = self._new(n, c, dims[lvl])
+                    sl = sums(c)
+                    lu.k5.fwd(cur, y, sl)
+                    lu.act.fwd(y, nxt, sl, residual=dwn if last else None)
                 cur = nxt
             return rec
 
@@ -922,12 +976,15 @@ class VNet(_Module):
             out = self._new(n, c, dims[lvl])
             for i, lu in enumerate(tr.ops):
                 rec["lu_in"].append(cur)
-                y = self._new(n, c, dims[lvl])
-                sl = sums(c)
-                lu.k5.fwd(cur, y, sl)
                 last = i == len(tr.ops) - 1
                 nxt = out if last else self._new(n, c, dims[lvl])
-                lu.act.fwd(y, nxt, sl, residual=xcat if last else None)
+                if fuse_eval:
+                    lu.k5.fwd_act(cur, nxt, lu.act, residual=xcat if last else None)
+                else:
+                    y = self._new(n, c, dims[lvl])
+                    sl = sums(c)
+                    lu.k5.fwd(cur, y, sl)
+                    lu.act.fwd(y, nxt, sl, residual=xcat if last else None)
                 cur = nxt
             rec["out"] = out
             return rec
@@ -946,10 +1003,18 @@ class VNet(_Module):
             pf = B8(n, 16, dims[0], torch.float32, device=self.device)
             ot.k551.fwd(tape["u32"]["out"], pf, None)
             ops.unfold_w(pf, st.view(ot.conv1.bias), ot.c, yo, g, so)
+        elif fuse_eval:
+            ot.k5.fwd_act(tape["u32"]["out"], yo, ot.act)
         else:
             ot.k5.fwd(tape["u32"]["out"], yo, so)
-        ao = self._new(n, cp, dims[0])
-        ot.act.fwd(yo, ao, so)
+        if fuse_eval and not ot.folded:
+            ao = yo
+        else:
+            ao = self._new(n, cp, dims[0])
+            ot.act.fwd(yo, ao, so)
+        if not head:  # evaluate(): the fused head consumes the activated features directly (see predict_with_losses)
+            self._tape = None
+            return ao
         logits = torch.empty((n, self.num_classes, *dims[0]), dtype=torch.float32, device=self.device)
         ops.conv1x1_fwd(ao, st.view(ot.conv2.weight), st.view(ot.conv2.bias), logits, self.num_classes,
                         self.num_classes)

@@ -240,6 +240,17 @@ def k5_fwd(x: B8, packed, bias, cout, out: B8, accumulate=False, ch_scale=None, 
              _stream())
 
 
+def k5_fwd_act(x: B8, packed, bias, cout, out: B8, scale, shift, alpha, residual: Optional[B8] = None, alpha2=None,
+               workspace: Optional[torch.Tensor] = None):
+    """evaluation-mode LUConv: t = prelu((conv(x) + bias) * scale + shift, alpha); out = prelu(t + residual, alpha2)
+    when a residual is given, else t - all in the conv's own epilogue"""
+    import ctypes
+    res = ctypes.byref(residual.mt) if residual is not None else None
+    call("msb_conv_k5_fwd_act", x.mt, _ptr(packed), _ptr(bias), cout, out.mt, x.n, dim3(x.dims), _ptr(scale),
+         _ptr(shift), _ptr(alpha), res, _ptr(alpha2), _ptr(workspace),
+         0 if workspace is None else workspace.numel() * workspace.element_size(), _stream())
+
+
 def k5_fwd_workspace_bytes(n: int, cout_view: int, dims, cin_view: int) -> int:
     return call("msb_conv_k5_fwd_workspace_bytes", n, cout_view, dim3(dims), cin_view)
 
@@ -324,6 +335,12 @@ def dice_ce_finalize(acc, c, result):
     call("msb_dice_ce_finalize", _ptr(acc), c, _ptr(result), _stream())
 
 
+def eval_head(a: B8, w, b, labels, class_w, c, ignore_index, pred=None, acc=None, psum=None):
+    """fused 1x1x1 conv + argmax + Dice/CE sums (+ class-weight softmax sums); the logits never reach HBM"""
+    call("msb_eval_head", a.mt, _ptr(w), _ptr(b), _ptr(labels), _ptr(class_w), a.n, c, a.s, ignore_index,
+         _ptr(pred), _ptr(acc), _ptr(psum), _stream())
+
+
 def dice_ce_bwd(logits, labels, class_w, acc, ignore_index, coef_ce, coef_dice, coef_dev, dlogits):
     n, c = logits.shape[:2]
     call("msb_dice_ce_bwd", _ptr(logits), _ptr(labels), _ptr(class_w), _ptr(acc), n, c, logits[0, 0].numel(),
@@ -369,3 +386,20 @@ def label_remap(labels, keys: Sequence[int], vals: Sequence[int]):
     va = (C.c_int32 * max(n, 1))(*vals)
     call("msb_label_remap", _ptr(labels), labels.numel(), C.cast(ka, C.c_void_p), C.cast(va, C.c_void_p), n,
          _stream())
+
+
+# ---- augmentations ----------------------------------------------------------------------------------------------
+def rotate3d(src, dst, axis_a, axis_b, m, off, order, cval=0):
+    """m = (m00, m01, m10, m11), off = (off0, off1) as Python floats (f64); src/dst f32 or i32 [D,H,W]"""
+    name = "msb_rotate3d_f32" if src.dtype == torch.float32 else "msb_rotate3d_i32"
+    cv = float(cval) if src.dtype == torch.float32 else int(cval)
+    call(name, _ptr(src), _ptr(dst), dim3(src.shape), int(axis_a), int(axis_b), float(m[0]), float(m[1]), float(m[2]),
+         float(m[3]), float(off[0]), float(off[1]), int(order), cv, _stream())
+
+
+def flip3d(src, dst, axis):
+    call("msb_flip3d", _ptr(src), _ptr(dst), dim3(src.shape), int(axis), _stream())
+
+
+def scale_by_max(src, dst, minmax_dev):
+    call("msb_scale_by_max", _ptr(src), _ptr(dst), src.numel(), _ptr(minmax_dev), _stream())

@@ -284,6 +284,46 @@ def test_conv_k5_split_k_small_volumes(cin, cout, dims):
     assert int(wsb.count_nonzero()) == 0
 
 
+@pytest.mark.parametrize("cin,cout,dims,res", [(32, 32, (9, 20, 24), True), (64, 64, (5, 16, 16), False),
+                                                (16, 32, (8, 16, 16), False), (128, 128, (8, 8, 8), True),
+                                                (256, 256, (8, 8, 8), True), (32, 20, (4, 16, 24), False)])
+def test_conv_k5_evaluation_epilogue(cin, cout, dims, res):
+    """msb_conv_k5_fwd_act (eval-mode LUConv in one kernel): prelu((conv + bias)*scale + shift) and the block tail
+    prelu2(. + residual), regular and split-K paths, against an f64 reference on the same bf16-rounded operands."""
+    ops, B8 = _imp()
+    torch.manual_seed(5)
+    n = 2
+    x = torch.randn(n, cin, *dims, device="cuda")
+    w = torch.randn(cout, cin, 5, 5, 5, device="cuda") * (2.0 / (cin * 125)) ** 0.5
+    b = torch.randn(cout, device="cuda")
+    cp = ops.k5_out_pad(cout)
+    scale, shift = torch.rand(cp, device="cuda") + 0.5, torch.randn(cp, device="cuda")
+    a1, a2 = torch.rand(cp, device="cuda") * 0.5, torch.rand(cp, device="cuda") * 0.5
+    xb = B8.from_ncdhw(x, torch.bfloat16)
+    rb = B8.from_ncdhw(torch.randn(n, cout, *dims, device="cuda"), torch.bfloat16, c_pad=cp) if res else None
+    packed = torch.empty(ops.k5_packed_bytes(cin, cp), dtype=torch.uint8, device="cuda")
+    ops.k5_pack(w, packed, cout, cin, 0, cin, cp)
+    bc = lambda v: v[:cout].double().view(1, cout, 1, 1, 1)
+    t = F.conv3d(xb.to_ncdhw().double(), w.bfloat16().double(), b.double(), padding=2) * bc(scale) + bc(shift)
+    t = torch.where(t > 0, t, t * bc(a1))
+    if res:
+        t = t + rb.to_ncdhw(cout).double()
+        t = torch.where(t > 0, t, t * bc(a2))
+    need = ops.k5_fwd_workspace_bytes(n, cp, dims, cin)
+    assert (need > 0) == (cin >= 128), "the 8^3 cases are expected to take the split-K path"
+    ws = torch.zeros(need, dtype=torch.uint8, device="cuda") if need else None
+    out = B8(n, cp, dims, torch.bfloat16, device="cuda", zero=True)
+    ops.k5_fwd_act(xb, packed, b, cout, out, scale, shift, a1, rb, a2 if res else None, ws)
+    assert rel(out.to_ncdhw(cout).double(), t) <= BF16_TOL
+    if cp > cout:  # padded output channels: zero weights and bias -> prelu(shift) (the model pads shift with 0)
+        pad_ref = torch.where(shift[cout:] > 0, shift[cout:], shift[cout:] * a1[cout:]).bfloat16().float()
+        assert torch.equal(out.to_ncdhw(cp)[:, cout:], pad_ref.view(1, -1, 1, 1, 1).expand(n, -1, *dims))
+    if ws is not None:
+        assert int(ws.count_nonzero()) == 0
+    with pytest.raises(Exception, match="alpha2"):
+        ops.k5_fwd_act(xb, packed, b, cout, out, scale, shift, a1, out, None, ws)
+
+
 WG_CASES = [(32, 32, (6, 16, 16)), (64, 64, (4, 9, 20)), (128, 128, (3, 8, 16)), (256, 256, (2, 8, 8)),
             (32, 2, (5, 10, 18)), (16, 16, (5, 8, 16)), (32, 32, (3, 13, 9)),
             # enough tiles for the clustered (TMA-multicast) launch: 2-CTA clusters (32 ch), 6-CTA clusters (64 ch)

@@ -209,3 +209,75 @@ def test_vnet_f32x3_tensor_core_fp32_path():
     worst, cos = _grad_errors(om, m)
     assert worst <= 2e-2, worst
     assert min(cos.values()) >= 0.9999, cos
+
+
+@pytest.mark.parametrize("dtype,num_classes,shape,kw", [("bf16", 2, (32, 32, 32), {}), ("bf16", 5, (32, 32, 32), {}),
+                                                         ("f32", 3, (32, 32, 32), {}), ("bf16", 20, (64, 64, 12), MRI)])
+def test_fused_evaluation_head_matches_unfused_path_and_oracle(dtype, num_classes, shape, kw):
+    """core/val.py:101-118: argmax + CE + Dice behind the 1x1x1 head in ONE kernel (no logits in HBM).  The logits are
+    computed with the same fmaf order as the unfused head, so the prediction is identical to argmax(logits) and the
+    losses differ only in f32 summation order (1e-5 relative); against the f32 oracle the usual path tolerances hold."""
+    from medicalseg_b200 import ops
+    vo, L, om, m, img, lab, ol, ours = _setup(dtype, num_classes, shape, train=False, **kw)
+    ours2 = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1])], "coef": [1]}  # fresh CE weights
+    with torch.no_grad():
+        ologits = om(img, None)[0]
+        oll, odice = vo.loss_computation([ologits], lab, ol)
+        # both heads on the SAME activated features (two forwards differ in the last bit where the split-K convs'
+        # f32 atomics land in another order, which flips near-tied argmaxes)
+        ao = m._forward(img.cuda().float().contiguous(), record=False, head=False)
+        w2, b2 = m.store.view(m.out_tr.conv2.weight), m.store.view(m.out_tr.conv2.bias)
+        logits = torch.empty((2, num_classes, *shape), dtype=torch.float32, device="cuda")
+        ops.conv1x1_fwd(ao, w2, b2, logits, num_classes, num_classes)
+        l_ref, d_ref = L.loss_computation([logits], lab.cuda(), ours)
+        pred, l_fused, d_fused = L.fused_head_losses(ao, w2, b2, num_classes, shape, lab.cuda(), ours2,
+                                                     L.fused_head_plan(ours2))
+        # the public entry (its own forward): same result up to those near-ties
+        pred_api, l_api, d_api = m.predict_with_losses(img.cuda(), lab.cuda(), ours2)
+    assert pred.shape == (2, 1, *shape) and pred.dtype == torch.int32
+    assert torch.equal(pred[:, 0].long(), logits.argmax(1))
+    def near_optimal(p):  # a prediction of another forward may differ only where the top logits are near-tied
+        gap = logits.max(1, keepdim=True).values - logits.gather(1, p.long())
+        return float(gap.max()) <= 2e-2 * float(logits.abs().max()) and float((p != pred).float().mean()) <= 5e-2
+    assert near_optimal(pred_api)
+    assert np.allclose(np.asarray(d_api), np.asarray(d_fused), atol=1e-4)
+    cw_ref, cw_fused = ours["types"][0].losses[0].weight, ours2["types"][0].losses[0].weight
+    assert torch.allclose(cw_ref, cw_fused, rtol=1e-4)  # f32 partial sums in another order
+    for a, b in zip(l_ref, l_fused):
+        assert abs(float(a) - float(b)) <= 1e-4 * max(1.0, abs(float(a)))
+    assert np.allclose(np.asarray(d_ref), np.asarray(d_fused), atol=1e-6)
+    tol = 1e-5 if dtype == "f32" else 1e-3
+    assert np.abs(np.asarray(d_fused) - odice).max() <= tol
+    # agreement with the oracle's argmax wherever its top-2 logits are not within rounding distance
+    top2 = ologits.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > (1e-4 if dtype == "f32" else 0.1) * float(ologits.abs().max())
+    assert torch.equal(pred[:, 0].cpu().long()[clear], ologits.argmax(1)[clear])
+    # prediction only (infer.py without labels) and a Dice-only config
+    p2, none_l, none_d = m.predict_with_losses(img.cuda())
+    assert near_optimal(p2) and none_l is None and none_d is None
+    _, l3, d3 = m.predict_with_losses(img.cuda(), lab.cuda(), {"types": [L.DiceLoss()], "coef": [1]})
+    assert len(l3) == 1 and abs(float(l3[0]) - float(l_ref[1])) <= 1e-4
+    # configurations the fused head does not cover fall back to the caller's unfused path
+    assert m.predict_with_losses(img.cuda(), lab.cuda(), {"types": [L.DiceLoss(), L.DiceLoss()], "coef": [1, 1]}) is None
+
+
+@pytest.mark.parametrize("num_classes,shape,kw", [(2, (32, 32, 32), {}), (20, (64, 64, 12), MRI)])
+def test_eval_forward_with_bn_prelu_in_the_conv_epilogue(num_classes, shape, kw):
+    """eval-mode forward: every LUConv runs as ONE kernel (running-statistics BN + PReLU + residual tail in the conv
+    epilogue).  Same tolerance against the f32 oracle as the separate-pass path, and close to that path (it skips one
+    bf16 rounding per layer, so it is not bit-identical).  Non-trivial running statistics: a few train steps first."""
+    vo, L, om, m, img, lab, ol, ours = _setup("bf16", num_classes, shape, train=True, **kw)
+    for step in range(2):
+        _step(vo, L, om, m, img, lab, ol, ours, True, step=step)  # moves the running statistics on both sides
+    m.set_state_dict(om.state_dict())  # identical parameters and running statistics again
+    om.eval(); m.eval()
+    with torch.no_grad():
+        ref = om(img, None)[0]
+        fused = m(img.cuda())[0].cpu()
+        m.eval_fused_epilogue = False
+        separate = m(img.cuda())[0].cpu()
+        m.eval_fused_epilogue = True
+    rms = lambda a, b: float((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt())
+    assert rms(fused, ref) <= 2e-2 and rms(separate, ref) <= 2e-2
+    assert rms(fused, separate) <= 1e-2
+    assert rms(fused, ref) <= rms(separate, ref) * 1.25 + 1e-3  # skipping roundings must not cost accuracy

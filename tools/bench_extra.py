@@ -91,6 +91,25 @@ def infer():
             ms = ev_time(lambda: m(img), 10)
         print(json.dumps({"metric": "VNet %s eval forward volumes/sec" % name, "value": round(2e3 / ms, 2),
                           "unit": "volumes/s", "ms_per_batch": round(ms, 3), "batch": 2, "n_gpus": 1}))
+        # one evaluate() step (core/val.py:101-118): prediction + CE/Dice of the same logits
+        from medicalseg_b200.models import losses as L
+        lab = torch.randint(0, kw["num_classes"], (2, *shape), device="cuda", dtype=torch.int32)
+        cfg = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1])], "coef": [1]}
+
+        def unfused():
+            logits = m(img)[0]
+            pred = torch.argmax(logits, dim=1, keepdim=True).to(torch.int32)
+            loss, dice = L.loss_computation([logits], lab, cfg)
+            return pred, loss
+
+        with torch.no_grad():
+            for _ in range(2):
+                unfused(); m.predict_with_losses(img, lab, cfg)
+            ms_u = ev_time(unfused, 10)
+            ms_f = ev_time(lambda: m.predict_with_losses(img, lab, cfg), 10)
+        print(json.dumps({"metric": "VNet %s evaluate step (pred + CE/Dice) volumes/sec" % name,
+                          "fused_head": round(2e3 / ms_f, 2), "unfused": round(2e3 / ms_u, 2), "unit": "volumes/s",
+                          "ms_fused": round(ms_f, 3), "ms_unfused": round(ms_u, 3), "batch": 2}))
 
 
 def preprocess():

@@ -1,5 +1,2 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
-timeout 300 python tools/bench_extra.py fp32x3 > gpurun_out/fp32x3.log 2>&1; tail -3 gpurun_out/fp32x3.log
-timeout 300 python bench.py > gpurun_out/bench.log 2>&1; tail -1 gpurun_out/bench.log
-timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 600 python -m pytest tests/test_gpu_transforms.py tests/test_gpu_vnet.py -m gpu -q -k "transform or rotation or flip or full_size or dataset or evaluation or eval_forward" > gpurun_out/pytest_tf.log 2>&1; tail -25 gpurun_out/pytest_tf.log

@@ -16,7 +16,9 @@ import torch  # noqa: E402
 
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-    mri = len(sys.argv) > 2 and sys.argv[2] == "mri"  # BASELINE configs[3]: 512x512x12, 20 classes, anisotropic
+    mode = sys.argv[2] if len(sys.argv) > 2 else ""
+    mri = mode in ("mri", "evalmri")  # BASELINE configs[3]: 512x512x12, 20 classes, anisotropic
+    evaluate = mode in ("eval", "evalmri")  # one evaluate() step: eval-mode forward + fused head (core/val.py:101-118)
     cdt = "f32x3" if len(sys.argv) > 2 and sys.argv[2] == "f32x3" else "bf16"  # BASELINE configs[2]
     import bench
     from medicalseg_b200.models import VNet, losses as L
@@ -45,6 +47,14 @@ def main():
         opt.step()
         opt._learning_rate.step()
         model.clear_gradients()
+
+    if evaluate:
+        model.eval()
+        train_step = step
+
+        def step():
+            with torch.no_grad():
+                model.predict_with_losses(img, lab, losses)
 
     from medicalseg_b200 import _lib
     if os.environ.get("MSB_NO_PDL"):
