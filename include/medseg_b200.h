@@ -324,6 +324,13 @@ int msb_flip3d(const void* src, void* dst, msb_dim3 dims, int axis, void* stream
 /* Compose (transform.py:67-69): dst = src / max if max > 0 else src; minmax = device {min, max} from msb_minmax */
 int msb_scale_by_max(const float* src, float* dst, int64_t count, const float* minmax, void* stream);
 
+/* ---- deep-supervision heads (medicalseg/models/vnet_deepsup.py:257-272) ---------------------------------------
+ * F.interpolate(x, size, mode='trilinear') with Paddle's defaults (align_corners=False, align_mode=0) on NCDHW f32:
+ * per axis src = (in/out)*(dst+0.5)-0.5 clamped at 0.  nc = N*C planes.  _bwd is the exact adjoint (dsrc is
+ * overwritten; deterministic gather, no atomics). */
+int msb_trilinear_fwd(const float* src, int64_t nc, msb_dim3 in_dims, float* dst, msb_dim3 out_dims, void* stream);
+int msb_trilinear_bwd(const float* ddst, int64_t nc, msb_dim3 out_dims, float* dsrc, msb_dim3 in_dims, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

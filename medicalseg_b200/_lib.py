@@ -96,6 +96,8 @@ SIGNATURES = {
     "msb_rotate3d_i32": (I, [P, P, D3, I, I, D, D, D, D, D, D, I, I, P]),
     "msb_flip3d": (I, [P, P, D3, I, P]),
     "msb_scale_by_max": (I, [P, P, L, P, P]),
+    "msb_trilinear_fwd": (I, [P, L, D3, P, D3, P]),
+    "msb_trilinear_bwd": (I, [P, L, D3, P, D3, P]),
 }
 
 _NO_STATUS = {"msb_version", "msb_last_error_string", "msb_conv_k5_packed_bytes", "msb_conv_k5_out_pad",

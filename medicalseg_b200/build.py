@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmedseg_b200.so")
 SOURCES = ["elementwise.cu", "loss.cu", "preprocess.cu", "conv_direct.cu", "conv_k5_umma.cu", "conv_k5_wgrad2.cu",
-           "conv_fold.cu", "conv_k2s2_umma.cu", "augment.cu"]
+           "conv_fold.cu", "conv_k2s2_umma.cu", "augment.cu", "interp.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",

@@ -93,7 +93,7 @@ def train(model, train_dataset, val_dataset=None, optimizer=None, save_dir="outp
     # the whole step into ONE CUDA graph.  Needs fixed batch shapes and a single process (the bucketed NCCL all-reduce
     # of world > 1 stays eager); a trailing short batch falls back to the eager step.
     graphed = None
-    if to_static_training and world == 1:
+    if to_static_training and world == 1 and not getattr(model, "deep_supervision", False):
         from .graph import GraphedTrainStep
         graphed = GraphedTrainStep(model, losses, optimizer, reducer=reducer)
     prof_range = None

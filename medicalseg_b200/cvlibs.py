@@ -59,11 +59,11 @@ LOSSES = ComponentManager("losses")
 
 
 def _register_defaults():
-    from .models import VNet
+    from .models import VNet, VNetDeepSup
     from .models.losses import CrossEntropyLoss, DiceLoss, MixedLoss
     from .datasets import NpyVolumeDataset, SyntheticVolumes
     from .transforms import Compose, RandomFlip3D, RandomResizedCrop3D, RandomRotation3D, Resize3D
-    for mgr, comps in ((MODELS, [VNet]), (LOSSES, [CrossEntropyLoss, DiceLoss, MixedLoss]),
+    for mgr, comps in ((MODELS, [VNet, VNetDeepSup]), (LOSSES, [CrossEntropyLoss, DiceLoss, MixedLoss]),
                        (DATASETS, [NpyVolumeDataset, SyntheticVolumes]),
                        (TRANSFORMS, [Compose, RandomFlip3D, RandomResizedCrop3D, RandomRotation3D, Resize3D])):
         for c in comps:

@@ -63,6 +63,9 @@ class GraphedTrainStep:
             raise RuntimeError("GraphedTrainStep is single-process: capturing the NCCL all-reduces deadlocked when it "
                                "was tried (see the module docstring); use the eager step with world_size > 1")
         m, opt = self.model, self.optimizer
+        if getattr(m, "deep_supervision", False):
+            raise NotImplementedError("GraphedTrainStep captures the single-output VNet step; VNetDeepSup (four outputs) "
+                                      "runs the eager step")
         dev = m.device
         self.s_img = torch.empty_like(images, device=dev)
         self.s_lab = torch.empty_like(labels, device=dev, dtype=torch.int32)

@@ -567,6 +567,18 @@ class VNet(_Module):
     `stat_scope` ('batch' = reference BatchNorm semantics | 'instance'), `device`.
     """
 
+    _OUT_PREFIX = "out_tr"  # state-dict prefix of the output transition (VNetDeepSup: "out_tr32")
+
+    # hooks of the deep-supervision variant (models/vnet_deepsup.py); no-ops for the plain VNet
+    def _build_aux_heads(self):
+        pass
+
+    def _after_forward(self, tape):
+        pass
+
+    def _aux_dgrad(self, key, g_buf):
+        pass
+
     def __init__(self, elu=False, in_channels=1, num_classes=4, pretrained=None,
                  kernel_size=((2, 2, 2), (2, 2, 2), (2, 2, 2), (2, 2, 2)),
                  stride_size=((2, 2, 2), (2, 2, 2), (2, 2, 2), (2, 2, 2)),
@@ -609,7 +621,8 @@ class VNet(_Module):
         self.up_tr128 = UpTransition(self, "up_tr128", 256, 128, 2, True, True, s[2], k[2])
         self.up_tr64 = UpTransition(self, "up_tr64", 128, 64, 1, False, False, s[1], k[1])
         self.up_tr32 = UpTransition(self, "up_tr32", 64, 32, 1, False, False, s[0], k[0])
-        self.out_tr = OutputTransition(self, "out_tr", 32, num_classes)
+        self.out_tr = OutputTransition(self, self._OUT_PREFIX, 32, num_classes)
+        self._build_aux_heads()  # VNetDeepSup: extra parameter slots AFTER the main head (reference order)
         self.store.finalize(self.device)
         self._init_parameters(seed)
         self._anchor = torch.zeros(1, device=self.device, requires_grad=True)
@@ -1019,6 +1032,7 @@ class VNet(_Module):
         ops.conv1x1_fwd(ao, st.view(ot.conv2.weight), st.view(ot.conv2.bias), logits, self.num_classes,
                         self.num_classes)
         tape["ao"] = ao
+        self._after_forward(tape)
         self._tape = tape if record else None
         if not getattr(self, "_masks_persistent", False):
             self._masks = None
@@ -1102,11 +1116,14 @@ class VNet(_Module):
             return g_xin, g_xcat
 
         g_u64, g_xcat32 = up_bwd(self.up_tr32, tape["u32"], g_u32, 0, None)
+        self._aux_dgrad("u64", g_u64)  # (+= the deep-supervision head's input gradient; no-op for VNet)
         g_out16 = g_xcat32.view(16, 16)
         g_u128, g_xcat64 = up_bwd(self.up_tr64, tape["u64"], g_u64, 1, None)
+        self._aux_dgrad("u128", g_u128)
         g_out32 = g_xcat64.view(32, 32)
         g_out64 = self._new(n, 64, dims[2])
         g_u256, _ = up_bwd(self.up_tr128, tape["u128"], g_u128, 2, g_out64)
+        self._aux_dgrad("u256", g_u256)
         g_out128 = self._new(n, 128, dims[3])
         g_out256, _ = up_bwd(self.up_tr256, tape["u256"], g_u256, 3, g_out128)
 

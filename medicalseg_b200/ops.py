@@ -403,3 +403,15 @@ def flip3d(src, dst, axis):
 
 def scale_by_max(src, dst, minmax_dev):
     call("msb_scale_by_max", _ptr(src), _ptr(dst), src.numel(), _ptr(minmax_dev), _stream())
+
+
+# ---- deep-supervision heads -------------------------------------------------------------------------------------
+def trilinear_fwd(src, dst):
+    """src [N,C,d,h,w] f32 -> dst [N,C,D,H,W] f32 (F.interpolate trilinear, align_corners=False)"""
+    call("msb_trilinear_fwd", _ptr(src), src.shape[0] * src.shape[1], dim3(src.shape[2:]), _ptr(dst),
+         dim3(dst.shape[2:]), _stream())
+
+
+def trilinear_bwd(ddst, dsrc):
+    call("msb_trilinear_bwd", _ptr(ddst), ddst.shape[0] * ddst.shape[1], dim3(ddst.shape[2:]), _ptr(dsrc),
+         dim3(dsrc.shape[2:]), _stream())

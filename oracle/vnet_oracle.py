@@ -228,6 +228,65 @@ class VNetOracle(nn.Module):
         return [out]
 
 
+class VNetDeepSupOracle(nn.Module):
+    """vnet_deepsup.py:176-281: the VNet trunk with three 3x3x3 deep-supervision heads on the decoder stages,
+    trilinearly resized to the input size (F.interpolate(mode='trilinear'), Paddle defaults align_corners=False,
+    align_mode=0 == torch's align_corners=False).  forward -> [out, d1 (256-ch stage), d2 (128), d3 (64)].
+    `out_tr_all` is built but never used by the reference's forward (its parameters only exist in the state dict)."""
+
+    def __init__(self, elu=False, in_channels=1, num_classes=4, pretrained=None,
+                 kernel_size=((2, 2, 2),) * 4, stride_size=((2, 2, 2),) * 4):
+        super().__init__()
+        if elu:
+            raise NotImplementedError("elu=True (nn.ELU) is not restated")
+        self.best_loss = 1000000
+        self.num_classes, self.in_channels, self.pretrained = num_classes, in_channels, pretrained
+        k, s = kernel_size, stride_size
+        self.in_tr = InputTransition(in_channels)
+        self.down_tr32 = DownTransition(16, 1, stride=s[0], kernel=k[0])
+        self.down_tr64 = DownTransition(32, 2, stride=s[1], kernel=k[1])
+        self.down_tr128 = DownTransition(64, 3, dropout=True, stride=s[2], kernel=k[2])
+        self.down_tr256 = DownTransition(128, 2, dropout=True, stride=s[3], kernel=k[3])
+        self.up_tr256 = UpTransition(256, 256, 2, dropout=True, dropout2=True, stride=s[3], kernel=k[3])
+        self.up_tr128 = UpTransition(256, 128, 2, dropout=True, dropout2=True, stride=s[2], kernel=k[2])
+        self.up_tr64 = UpTransition(128, 64, 1, stride=s[1], kernel=k[1])
+        self.up_tr32 = UpTransition(64, 32, 1, stride=s[0], kernel=k[0])
+        self.out_tr32 = OutputTransition(32, num_classes)                      # vnet_deepsup.py:244
+        self.out_tr64 = nn.Conv3d(64, num_classes, kernel_size=3, padding=1)   # :245
+        self.out_tr128 = nn.Conv3d(128, num_classes, kernel_size=3, padding=1)
+        self.out_tr256 = nn.Conv3d(256, num_classes, kernel_size=3, padding=1)
+        for conv in (self.out_tr64, self.out_tr128, self.out_tr256):
+            _paddle_conv_init(conv)
+        self.out_tr_all = OutputTransition(4 * num_classes, num_classes)      # :248 (unused in forward)
+
+    def forward(self, x, masks: Optional[Dict[str, torch.Tensor]] = None):  # vnet_deepsup.py:256-275
+        m = masks or {}
+        if self.training and not masks:
+            raise ValueError("train-mode forward needs explicit dropout masks (make_dropout_masks)")
+        size = x.shape[2:]
+        out16 = self.in_tr(x)
+        out32 = self.down_tr32(out16)
+        out64 = self.down_tr64(out32)
+        out128 = self.down_tr128(out64, m.get("down_tr128"))
+        out256 = self.down_tr256(out128, m.get("down_tr256"))
+        out = self.up_tr256(out256, out128, m.get("up_tr256.x"), m.get("up_tr256.skip"))
+        d1 = F.interpolate(self.out_tr256(out), size=size, mode="trilinear", align_corners=False)
+        out = self.up_tr128(out, out64, m.get("up_tr128.x"), m.get("up_tr128.skip"))
+        d2 = F.interpolate(self.out_tr128(out), size=size, mode="trilinear", align_corners=False)
+        out = self.up_tr64(out, out32)
+        d3 = F.interpolate(self.out_tr64(out), size=size, mode="trilinear", align_corners=False)
+        out = self.up_tr32(out, out16)
+        out = self.out_tr32(out)
+        return [out, d1, d2, d3]
+
+
+def deepsup_losses():
+    """vnetdeepsup_mri_spine_seg_512_512_12_15k.yml:12-20: one MixedLoss(CE, Dice) PER output (config.py:265-267
+    repeats the single entry, _load_object builds four separate objects), coef 0.25 each"""
+    return {"types": [MixedLoss([CrossEntropyLoss(), DiceLoss()], [1, 1]) for _ in range(4)],
+            "coef": [0.25, 0.25, 0.25, 0.25]}
+
+
 # --------------------------------------------------------------------------------------------
 # Losses
 # --------------------------------------------------------------------------------------------

@@ -631,3 +631,26 @@ def test_resample_full_size_properties():
     ramp = torch.arange(256, device="cuda", dtype=torch.float32).view(1, 1, 256).expand(8, 8, 256).contiguous()
     r, _ = P.resample(ramp, new_shape=[8, 8, 64], order=1)
     assert bool((r[..., 1:] > r[..., :-1]).all())
+
+
+@pytest.mark.parametrize("small,big", [((16, 16, 16), (32, 32, 32)), ((4, 4, 4), (32, 32, 32)), ((8, 8, 4), (64, 64, 12)),
+                                       ((5, 7, 3), (12, 20, 9)), ((9, 6, 10), (9, 6, 10)), ((12, 10, 8), (5, 4, 3))])
+def test_trilinear_resize_and_adjoint(small, big):
+    """msb_trilinear_fwd / _bwd (VNetDeepSup heads, vnet_deepsup.py:259-272) vs torch F.interpolate(trilinear,
+    align_corners=False) and its autograd adjoint; f32, 2e-5 relative."""
+    ops, _ = _imp()
+    torch.manual_seed(2)
+    x = torch.randn(2, 3, *small, device="cuda", requires_grad=True)
+    ref = F.interpolate(x, size=big, mode="trilinear", align_corners=False)
+    out = torch.empty(2, 3, *big, device="cuda")
+    ops.trilinear_fwd(x.detach(), out)
+    assert rel(out, ref.detach()) <= F32_TOL
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    dx = torch.full_like(x, float("nan"))
+    ops.trilinear_bwd(g, dx)
+    assert rel(dx, x.grad) <= F32_TOL
+    # adjoint identity <A x, g> == <x, A^T g> in f64
+    lhs = float((out.double() * g.double()).sum())
+    rhs = float((x.detach().double() * dx.double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))

@@ -45,11 +45,14 @@ def _step(vo, L, om, m, img, lab, ol, ours, train, step=0):
 
 def _grad_errors(om, m):
     osd = dict(om.named_parameters())
-    gmax = max(float(p.grad.norm()) for p in osd.values())
+    gmax = max(float(p.grad.norm()) for p in osd.values() if p.grad is not None)
     worst = 0.0
     cos = {}
     for name, _ in m.named_parameters():
         g, og = m.store.grad_view(name).cpu(), osd[name].grad
+        if og is None:  # parameters the forward never touches (VNetDeepSup.out_tr_all): the gradient stays zero
+            assert float(g.abs().max()) == 0.0, name
+            continue
         worst = max(worst, float((g - og).norm()) / gmax)
         if name.endswith("conv1.weight") or name.endswith("_conv.weight"):
             cos[name] = float((g * og).sum() / (g.norm() * og.norm() + 1e-30))
@@ -281,3 +284,65 @@ def test_eval_forward_with_bn_prelu_in_the_conv_epilogue(num_classes, shape, kw)
     assert rms(fused, ref) <= 2e-2 and rms(separate, ref) <= 2e-2
     assert rms(fused, separate) <= 1e-2
     assert rms(fused, ref) <= rms(separate, ref) * 1.25 + 1e-3  # skipping roundings must not cost accuracy
+
+
+def _deepsup_setup(dtype, num_classes, shape, **kw):
+    from oracle import vnet_oracle as vo
+    from medicalseg_b200.models import VNetDeepSup, losses as L
+    torch.manual_seed(0)
+    om = vo.VNetDeepSupOracle(num_classes=num_classes, **kw)
+    img, lab = vo.synthetic_batch(2, shape, num_classes, seed=0)
+    m = VNetDeepSup(num_classes=num_classes, compute_dtype=dtype, **kw)
+    assert sorted(m.state_dict().keys()) == sorted(om.state_dict().keys())  # reference names incl. out_tr32 / out_tr_all
+    m.set_state_dict(om.state_dict())
+    ours = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1]) for _ in range(4)], "coef": [0.25] * 4}
+    return vo, L, om, m, img, lab, vo.deepsup_losses(), ours
+
+
+@pytest.mark.parametrize("dtype,num_classes,shape,kw", [("f32", 3, (32, 32, 32), {}), ("bf16", 2, (32, 32, 32), {}),
+                                                         ("bf16", 20, (64, 64, 12), MRI)])
+def test_vnet_deepsup_matches_oracle(dtype, num_classes, shape, kw):
+    """VNetDeepSup (vnet_deepsup.py:176-281): four outputs, the 0.25-weighted four-way MixedLoss of the shipped config,
+    one train step with explicit dropout masks.  Tolerances as for the VNet paths (f32: logits 1e-4*max, losses 1e-5,
+    gradients 1e-3 of the largest gradient norm; bf16: logits rel-RMS 2e-2, Dice 1e-3, head-weight gradient cosine
+    0.97)."""
+    vo, L, om, m, img, lab, ol, ours = _deepsup_setup(dtype, num_classes, shape, **kw)
+    om.train(); m.train()
+    masks = vo.make_dropout_masks(2, seed=0, step=0)
+    ologits = om(img, masks)
+    oll, odice = vo.loss_computation(ologits, lab, ol)
+    sum(oll).backward()
+    m.set_dropout_masks(masks)
+    logits = m(img.cuda())
+    assert len(logits) == 4 and all(tuple(t.shape) == (2, num_classes, *shape) for t in logits)
+    ll, dice = L.loss_computation(logits, lab.cuda(), ours)
+    assert len(ll) == 8
+    sum(ll).backward()
+    for o, t in zip(ologits, logits):
+        o, t = o.detach(), t.detach().cpu()
+        if dtype == "f32":
+            assert float((o - t).abs().max()) <= 1e-4 * float(o.abs().max())
+        else:
+            assert float((o - t).pow(2).mean().sqrt() / o.pow(2).mean().sqrt()) <= 2e-2
+    for a, b in zip(oll, ll):
+        assert abs(float(a) - float(b)) <= (1e-5 if dtype == "f32" else 1e-2 * max(abs(float(a)), 0.1))
+    assert np.abs(np.asarray(dice) - np.asarray(odice)).max() <= (1e-5 if dtype == "f32" else 1e-3)
+    worst, cos = _grad_errors(om, m)
+    osd = dict(om.named_parameters())
+    for name in ("out_tr64.weight", "out_tr128.weight", "out_tr256.weight"):
+        g, og = m.store.grad_view(name).cpu(), osd[name].grad
+        c = float((g * og).sum() / (g.norm() * og.norm() + 1e-30))
+        assert c >= (0.9999 if dtype == "f32" else 0.97), (name, c)
+    if dtype == "f32":
+        assert worst <= 1e-3, worst
+    else:
+        assert min(cos.values()) >= 0.97, cos
+    # eval mode: the heads still produce their outputs; evaluate()'s fused head scores the main output only
+    om.eval(); m.eval()
+    with torch.no_grad():
+        eo, et = om(img, None), m(img.cuda())
+    assert len(et) == 4
+    for o, t in zip(eo, et):
+        assert float((o - t.cpu()).pow(2).mean().sqrt() / o.pow(2).mean().sqrt()) <= (1e-4 if dtype == "f32" else 2e-2)
+    res = m.predict_with_losses(img.cuda(), lab.cuda(), {"types": [ours["types"][0]], "coef": [0.25]})
+    assert res is not None and tuple(res[0].shape) == (2, 1, *shape) and len(res[1]) == 2
