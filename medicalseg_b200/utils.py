@@ -31,6 +31,8 @@ def load_entire_model(model, pretrained):
     own = model.state_dict()
     ok = {}
     for k, v in sd.items():
+        if k == "StructuredToParameterName@@":  # Paddle's name table, not a parameter
+            continue
         if k not in own:
             print("[WARNING] {} is not in pretrained model".format(k))
             continue
@@ -56,6 +58,18 @@ def save_checkpoint(model, optimizer, save_dir):
                 return {k: to_cpu(x) for k, x in v.items()}
             return v
         torch.save({k: to_cpu(v) for k, v in optimizer.state_dict().items()}, os.path.join(save_dir, "model.pdopt"))
+
+
+def export_pdparams(model, path):
+    """Writes the parameters in the container PaddlePaddle 2.x itself uses for `paddle.save(layer.state_dict())`: a
+    protocol-2 pickle of {structured name: numpy array} (+ the `StructuredToParameterName@@` name table), so weights
+    trained here can be taken back to the reference (`paddle.load` + `set_dict`, utils/utils.py:84-104).  The same
+    container is what `load_entire_model` / `VNet(pretrained=...)` read when handed a reference checkpoint."""
+    sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    sd["StructuredToParameterName@@"] = {k: k for k in sd}
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    with open(path, "wb") as fh:
+        pickle.dump(sd, fh, protocol=2)
 
 
 def resume(model, optimizer, resume_model):

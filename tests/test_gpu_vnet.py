@@ -346,3 +346,38 @@ def test_vnet_deepsup_matches_oracle(dtype, num_classes, shape, kw):
         assert float((o - t.cpu()).pow(2).mean().sqrt() / o.pow(2).mean().sqrt()) <= (1e-4 if dtype == "f32" else 2e-2)
     res = m.predict_with_losses(img.cuda(), lab.cuda(), {"types": [ours["types"][0]], "coef": [0.25]})
     assert res is not None and tuple(res[0].shape) == (2, 1, *shape) and len(res[1]) == 2
+
+
+def test_paddle_style_checkpoint_round_trip(tmp_path):
+    """a `.pdparams` file as PaddlePaddle writes it (protocol-2 pickle of {name: ndarray} plus the
+    StructuredToParameterName@@ table) loads through `pretrained=` (utils/utils.py:76-112), and export_pdparams writes
+    the same container back."""
+    import pickle
+    from oracle import vnet_oracle as vo
+    from medicalseg_b200.models import VNet
+    from medicalseg_b200.utils import export_pdparams
+    torch.manual_seed(3)
+    om = vo.VNetOracle(num_classes=3)
+    for p in om.parameters():  # non-default values everywhere (BN scale, PReLU slopes, biases)
+        p.data.add_(torch.randn_like(p) * 0.05)
+    sd = {k: v.detach().numpy() for k, v in om.state_dict().items()}
+    sd["StructuredToParameterName@@"] = {k: "param_%d" % i for i, k in enumerate(sd)}
+    path = tmp_path / "ref" / "model.pdparams"
+    path.parent.mkdir()
+    with open(path, "wb") as fh:
+        pickle.dump(sd, fh, protocol=2)
+    m = VNet(num_classes=3, compute_dtype="f32", pretrained=str(path.parent))  # directory form, as the reference allows
+    om.eval(); m.eval()
+    img, _ = vo.synthetic_batch(1, (16, 16, 16), 3, seed=1)
+    with torch.no_grad():
+        ref, out = om(img, None)[0], m(img.cuda())[0].cpu()
+    assert float((ref - out).abs().max()) <= 1e-4 * float(ref.abs().max())
+    out_path = tmp_path / "export" / "model.pdparams"
+    export_pdparams(m, str(out_path))
+    with open(out_path, "rb") as fh:
+        back = pickle.load(fh)
+    assert set(back) == set(sd)
+    for k, v in sd.items():
+        if k != "StructuredToParameterName@@":
+            assert isinstance(back[k], np.ndarray) and back[k].shape == v.shape
+            np.testing.assert_allclose(back[k], v, rtol=0, atol=0)

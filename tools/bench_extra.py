@@ -26,13 +26,15 @@ def ev_time(fn, reps):
     return e0.elapsed_time(e1) / reps
 
 
-def mri():
-    from medicalseg_b200.models import VNet, losses as L
+def mri(deepsup=False):
+    from medicalseg_b200.models import VNet, VNetDeepSup, losses as L
     from medicalseg_b200.optimizer import Momentum, PolynomialDecay
     kw = dict(kernel_size=[[2, 2, 4], [2, 2, 2], [2, 2, 2], [2, 2, 2]], stride_size=[[2, 2, 1], [2, 2, 1], [2, 2, 2], [2, 2, 2]])
-    m = VNet(num_classes=20, compute_dtype="bf16", **kw)
+    m = (VNetDeepSup if deepsup else VNet)(num_classes=20, compute_dtype="bf16", **kw)
     m.train()
-    losses = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1])], "coef": [1]}
+    nl = 4 if deepsup else 1  # vnetdeepsup_mri_spine_seg_512_512_12_15k.yml: four MixedLoss objects x 0.25
+    losses = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1]) for _ in range(nl)],
+              "coef": [1.0 / nl] * nl}
     opt = Momentum(PolynomialDecay(0.1, 15000), m.parameters(), 0.9, 1e-4)
     img = torch.rand(2, 1, 512, 512, 12, device="cuda")
     lab = torch.randint(0, 20, (2, 512, 512, 12), device="cuda", dtype=torch.int32)
@@ -45,7 +47,8 @@ def mri():
     for _ in range(3):
         step()
     ms = ev_time(step, 5)
-    print(json.dumps({"metric": "VNet MRISpineSeg 512x512x12 20-class bf16 train-step volumes/sec", "value": round(2e3 / ms, 3),
+    print(json.dumps({"metric": "%s MRISpineSeg 512x512x12 20-class bf16 train-step volumes/sec" % type(m).__name__,
+                      "value": round(2e3 / ms, 3),
                       "unit": "volumes/s", "ms_per_step": round(ms, 2), "n_gpus": 1, "batch": 2,
                       "tflops": round(2 * 12817 / ms, 1)}))
 
@@ -201,4 +204,4 @@ def augment():
 
 if __name__ == "__main__":
     {"mri": mri, "preprocess": preprocess, "infer": infer, "fp32": fp32, "augment": augment,
-     "fp32x3": lambda: fp32("f32x3")}[sys.argv[1]]()
+     "deepsup": lambda: mri(True), "fp32x3": lambda: fp32("f32x3")}[sys.argv[1]]()
