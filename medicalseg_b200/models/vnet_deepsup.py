@@ -19,11 +19,65 @@ from ..ops import B8
 from .vnet import VNet, _BN, _Conv, _Module, _PReLU, _pad
 
 
-class _AuxHead(_Module):  # nn.Conv3D(cin, num_classes, kernel_size=3, padding=1), vnet_deepsup.py:245-247
+class _AuxHead(_Module):
+    """nn.Conv3D(cin, num_classes, kernel_size=3, padding=1), vnet_deepsup.py:245-247.
+
+    bf16 engine: the 3x3x3 kernel is the centre of a zero-bordered 5x5x5 kernel (padding 2 == padding 1 for the
+    embedded taps), so forward, input gradient and weight gradient run on the tcgen05 5x5x5 kernels - 4.6x the MACs, but
+    at tensor-core rate instead of the CUDA-core direct convolution (measured on the MRI config: the three heads cost
+    60 ms per step as direct convolutions).  f32 parity engine: direct kernels."""
+
     def __init__(self, store, prefix, cin, num_classes):
         super().__init__(prefix)
         self.cin, self.c, self.cp = cin, num_classes, _pad(num_classes, 16)
         self.conv = _Conv(store, prefix, (num_classes, cin, 3, 3, 3), num_classes, ("conv", cin * 27))
+        self.w5 = self.dw5 = self.packed_f = self.packed_b = None
+        self.version = -1
+
+    def pack(self, eng):
+        if self.version == eng.param_version and self.packed_f is not None:
+            return
+        dev = eng.device
+        if self.w5 is None:
+            self.w5 = torch.zeros((self.c, self.cin, 5, 5, 5), dtype=torch.float32, device=dev)
+            self.dw5 = torch.zeros_like(self.w5)
+            self.fw_pad = (self.cin, ops.k5_out_pad(self.cp))             # forward operand: reduce cin -> cp
+            self.bw_pad = (self.cp, ops.k5_out_pad(self.cin))             # input-gradient operand: reduce cp -> cin
+            self.packed_f = torch.empty(ops.k5_packed_bytes(*self.fw_pad), dtype=torch.uint8, device=dev)
+            self.packed_b = torch.empty(ops.k5_packed_bytes(*self.bw_pad), dtype=torch.uint8, device=dev)
+        self.w5[:, :, 1:4, 1:4, 1:4].copy_(eng.store.view(self.conv.weight))
+        ops.k5_pack(self.w5, self.packed_f, self.c, self.cin, 0, *self.fw_pad)
+        ops.k5_pack(self.w5, self.packed_b, self.c, self.cin, 1, *self.bw_pad)
+        self.version = eng.param_version
+
+    def fwd(self, eng, x: B8, y: B8):
+        st = eng.store
+        if eng.dtype == torch.bfloat16:
+            self.pack(eng)
+            ops.k5_fwd(x, self.packed_f, st.view(self.conv.bias), self.c, y, False, None, 1, None,
+                       eng.splitk_workspace(x.n, y.c, x.dims, x.c))
+        else:
+            ops.conv_strided_fwd(x, st.view(self.conv.weight), st.view(self.conv.bias), y, (3, 3, 3), (1, 1, 1),
+                                 (1, 1, 1), 1, None, self.cin, self.c)
+
+    def wgrad(self, eng, x: B8, dy: B8):
+        st = eng.store
+        dw, db = st.grad_view(self.conv.weight), st.grad_view(self.conv.bias)
+        if eng.dtype == torch.bfloat16:
+            self.pack(eng)
+            self.dw5.zero_()
+            ops.k5_wgrad(x, dy, self.dw5, db, self.c, self.cin, eng.wgrad_workspace(self.cin, self.c))
+            dw += self.dw5[:, :, 1:4, 1:4, 1:4]
+        else:
+            ops.conv_strided_wgrad(x, dy, dw, db, (3, 3, 3), (1, 1, 1), (1, 1, 1), False, self.cin, self.c)
+
+    def dgrad_into(self, eng, dy: B8, g_buf: B8):
+        if eng.dtype == torch.bfloat16:
+            ops.k5_fwd(dy, self.packed_b, None, self.cin, g_buf, True, None, 1, None,
+                       eng.splitk_workspace(dy.n, g_buf.c, dy.dims, dy.c))
+        else:
+            ops.conv_strided_bwd_data(dy, eng.store.view(self.conv.weight), None, g_buf, (3, 3, 3), (1, 1, 1),
+                                      (1, 1, 1), True, 1, None, self.c, self.cin)
 
 
 class _UnusedOutputTransition(_Module):  # out_tr_all, vnet_deepsup.py:248: parameters only (never in the forward)
@@ -111,8 +165,7 @@ class VNetDeepSup(VNet):
         for name, key, lvl in self._STAGES:
             head = getattr(self.aux, name)
             y = self._new(n, head.cp, dims[lvl])
-            ops.conv_strided_fwd(tape[key]["out"], st.view(head.conv.weight), st.view(head.conv.bias), y, (3, 3, 3),
-                                 (1, 1, 1), (1, 1, 1), 1, None, head.cin, c)
+            head.fwd(self, tape[key]["out"], y)
             small = y.to_ncdhw(c)
             big = torch.empty((n, c, *dims[0]), dtype=torch.float32, device=self.device)
             ops.trilinear_fwd(small, big)
@@ -132,8 +185,7 @@ class VNetDeepSup(VNet):
             small = torch.empty((n, c, *dims[lvl]), dtype=torch.float32, device=self.device)
             ops.trilinear_bwd(g.contiguous().float(), small)
             dy = B8.from_ncdhw(small, self.dtype, c_pad=head.cp)
-            ops.conv_strided_wgrad(tape[key]["out"], dy, st.grad_view(head.conv.weight), st.grad_view(head.conv.bias),
-                                   (3, 3, 3), (1, 1, 1), (1, 1, 1), False, head.cin, c)
+            head.wgrad(self, tape[key]["out"], dy)
             self._aux_dy[key] = (head, dy)
         self._fire(self.aux)
 
@@ -142,8 +194,7 @@ class VNetDeepSup(VNet):
         if item is None:
             return
         head, dy = item
-        ops.conv_strided_bwd_data(dy, self.store.view(head.conv.weight), None, g_buf, (3, 3, 3), (1, 1, 1), (1, 1, 1),
-                                  True, 1, None, self.num_classes, head.cin)
+        head.dgrad_into(self, dy, g_buf)
 
     def predict_with_losses(self, x, labels=None, losses=None):
         """evaluation scores the main output only (core/val.py:95 keeps the first loss); the heads are skipped"""

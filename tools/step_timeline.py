@@ -17,22 +17,25 @@ import torch  # noqa: E402
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
     mode = sys.argv[2] if len(sys.argv) > 2 else ""
-    mri = mode in ("mri", "evalmri")  # BASELINE configs[3]: 512x512x12, 20 classes, anisotropic
+    mri = mode in ("mri", "evalmri", "deepsup")  # BASELINE configs[3]: 512x512x12, 20 classes, anisotropic
     evaluate = mode in ("eval", "evalmri")  # one evaluate() step: eval-mode forward + fused head (core/val.py:101-118)
     cdt = "f32x3" if len(sys.argv) > 2 and sys.argv[2] == "f32x3" else "bf16"  # BASELINE configs[2]
     import bench
-    from medicalseg_b200.models import VNet, losses as L
+    from medicalseg_b200.models import VNet, VNetDeepSup, losses as L
     from medicalseg_b200.optimizer import Momentum, PolynomialDecay
 
     device = torch.device("cuda", 0)
     if mri:
-        model = VNet(num_classes=20, compute_dtype="bf16", seed=0,
+        model = (VNetDeepSup if mode == "deepsup" else VNet)(num_classes=20, compute_dtype="bf16", seed=0,
                      kernel_size=[[2, 2, 4], [2, 2, 2], [2, 2, 2], [2, 2, 2]],
                      stride_size=[[2, 2, 1], [2, 2, 1], [2, 2, 2], [2, 2, 2]])
     else:
         model = VNet(num_classes=bench.NUM_CLASSES, compute_dtype=cdt, seed=0)
     model.train()
     losses = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1])], "coef": [1]}
+    if mode == "deepsup":  # vnetdeepsup_mri_spine_seg_512_512_12_15k.yml: four MixedLoss objects x 0.25
+        losses = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1]) for _ in range(4)],
+                  "coef": [0.25] * 4}
     opt = Momentum(PolynomialDecay(0.001, 15000), model.parameters(), 0.9, 1e-4)
     img, lab = bench.synthetic_gpu_batch(device, seed=0)
     if mri:
