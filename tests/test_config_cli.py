@@ -129,3 +129,64 @@ def test_train_entry_point_with_to_static_training_cuda_graph(tmp_path):
     assert os.path.exists(tmp_path / "out" / "best_model" / "model.pdparams")
     losses = [float(l.split("loss: ")[1].split(",")[0]) for l in r.stdout.splitlines() if "[TRAIN]" in l]
     assert len(losses) >= 3 and losses[-1] < losses[0]
+
+
+@pytest.mark.gpu
+def test_train_entry_point_deep_supervision_and_device_transforms(tmp_path):
+    """VNetDeepSup through train.py (four losses, the heads' gradient bucket fires first - the reducer's planner checks
+    the end-to-front order), then a .npy dataset whose YAML `transforms` run on the device (datasets/dataset.py:113)."""
+    import numpy as np
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    cfg = os.path.join(ROOT, "configs/synthetic/vnetdeepsup_synthetic_64.yml")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "train.py"), "--config", cfg, "--iters", "6", "--log_iters", "2",
+                        "--save_interval", "6", "--do_eval", "--save_dir", str(tmp_path / "out"), "--seed", "0",
+                        "--to_static_training"],  # falls back to the eager step for the four-output model
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "[EVAL] #Images: 2, Dice:" in r.stdout
+    losses = [float(l.split("loss: ")[1].split(",")[0]) for l in r.stdout.splitlines() if "[TRAIN]" in l]
+    assert len(losses) == 3 and losses[-1] < losses[0]
+    root = tmp_path / "ds"
+    root.mkdir()
+    rng = np.random.default_rng(0)
+    lines = []
+    for i in range(2):
+        blob = rng.random((40, 44, 36)).astype(np.float32)
+        np.save(root / ("im%d.npy" % i), blob * 255)
+        np.save(root / ("lb%d.npy" % i), (blob > 0.5).astype(np.uint8))
+        lines.append("im%d.npy lb%d.npy" % (i, i))
+    (root / "train_list.txt").write_text("\n".join(lines) + "\n")
+    (root / "val_list.txt").write_text(lines[0] + "\n")
+    cfg2 = tmp_path / "npy.yml"
+    cfg2.write_text("""
+_base_: '%s'
+train_dataset:
+  _inherited_: False
+  type: LungCoronavirus
+  dataset_root: %s
+  result_dir: %s
+  transforms:
+    - type: RandomResizedCrop3D
+      size: 32
+      scale: [0.8, 1.2]
+    - type: RandomRotation3D
+      degrees: 90
+    - type: RandomFlip3D
+  mode: train
+  num_classes: 2
+val_dataset:
+  _inherited_: False
+  type: LungCoronavirus
+  dataset_root: %s
+  result_dir: %s
+  transforms:
+    - type: Resize3D
+      size: [32, 32, 32]
+  mode: val
+  num_classes: 2
+""" % (os.path.join(ROOT, "configs/synthetic/vnet_synthetic_64.yml"), root, root, root, root))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "train.py"), "--config", str(cfg2), "--iters", "4",
+                        "--log_iters", "2", "--save_interval", "4", "--do_eval", "--save_dir", str(tmp_path / "out2"),
+                        "--seed", "0"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "[TRAIN] epoch:" in r.stdout and "[EVAL] #Images: 1, Dice:" in r.stdout

@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_vnet.py tests/test_gpu_kernels.py -m gpu -q -k "deepsup or trilinear" 2>&1 | tail -2
-timeout 300 python tools/bench_extra.py deepsup > gpurun_out/deepsup.log 2>&1; tail -1 gpurun_out/deepsup.log
-MSB_NO_PDL=1 timeout 300 python tools/step_timeline.py 2 deepsup > gpurun_out/timeline_deepsup.log 2>&1; grep -n "trilinear\|traced" gpurun_out/timeline_deepsup.log | cut -c1-130
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; tail -6 gpurun_out/pytest_gpu.log
+timeout 300 python bench.py > gpurun_out/bench.log 2>&1; tail -1 gpurun_out/bench.log | cut -c1-330
+timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 300 python tools/bench_extra.py mri > gpurun_out/mri.log 2>&1; tail -1 gpurun_out/mri.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv python bench.py --no-graph --steps 2 --warmup 1 > gpurun_out/ncu_bench.log 2>&1; tail -2 gpurun_out/ncu_bench.log | cut -c1-200

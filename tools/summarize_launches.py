@@ -1,19 +1,20 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel name.
 
-usage: python tools/summarize_launches.py launches.csv [skip_first_n_launches]
+usage: python tools/summarize_launches.py launches.csv [skip_first_n_launches [count]]
 """
 import csv, collections, re, sys
 
 def main():
     path = sys.argv[1]
     skip = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    count = int(sys.argv[3]) if len(sys.argv) > 3 else None
     rows = list(csv.reader(open(path)))
     hdr = next(i for i, r in enumerate(rows) if r and r[0] == 'ID')
     h = rows[hdr]
     kn, mv, gs = h.index('Kernel Name'), h.index('Metric Value'), h.index('Grid Size')
     agg = collections.OrderedDict()
     total = 0.0
-    for r in rows[hdr + 1 + skip:]:
+    for r in rows[hdr + 1 + skip:][:count]:
         if len(r) <= mv:
             continue
         name = re.sub(r'\(.*$', '', r[kn])
