@@ -38,6 +38,23 @@ def inference(model, im, ori_shape=None, transforms=None):
     return pred, logit
 
 
+def reduce_eval_metrics(mdice_sum, loss_sum, channel_dice_sum, n_local, device, num_classes=1):
+    """per-rank sums over this rank's shard of the validation set -> GLOBAL means (mDice, loss, per-class Dice).  The
+    reference does not reduce its metrics across ranks (core/val.py:58-66,168: every rank reports its own shard); here
+    the sums and the sample count are all-reduced so every rank reports - and selects `best_model` on - the same figure."""
+    if channel_dice_sum is None:  # a rank whose shard is empty (fewer validation volumes than ranks)
+        channel_dice_sum = np.zeros(num_classes)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor([mdice_sum, loss_sum, float(n_local)], device=device, dtype=torch.float64)
+        cd = torch.as_tensor(np.asarray(channel_dice_sum), device=device, dtype=torch.float64)
+        dist.all_reduce(t)
+        dist.all_reduce(cd)
+        mdice_sum, loss_sum, n_local = float(t[0]), float(t[1]), float(t[2])
+        channel_dice_sum = cd.cpu().numpy()
+    n = max(float(n_local), 1.0)
+    return mdice_sum / n, loss_sum / n, np.asarray(channel_dice_sum) / n
+
+
 def evaluate(model, eval_dataset, losses, num_workers=0, print_detail=True, save_dir=None, **_):
     new_loss = {"types": [losses["types"][0]], "coef": [losses["coef"][0]]}
     model.eval()
@@ -63,15 +80,8 @@ def evaluate(model, eval_dataset, losses, num_workers=0, print_detail=True, save
             if save_dir is not None and it < 5 and rank == 0:
                 os.makedirs(os.path.join(save_dir, str(it)), exist_ok=True)
                 np.save(os.path.join(save_dir, str(it), "pred.npy"), pred.cpu().numpy())
-    n_local = max(len(indices), 1)
-    if world > 1:  # the reference does not reduce metrics across ranks (val.py:168); we report the global figure
-        t = torch.tensor([mdice, loss_all, float(len(indices))], device=device, dtype=torch.float64)
-        cd = torch.as_tensor(channel_dice, device=device, dtype=torch.float64)
-        dist.all_reduce(t); dist.all_reduce(cd)
-        mdice, loss_all, n_local = float(t[0]), float(t[1]), max(float(t[2]), 1.0)
-        channel_dice = cd.cpu().numpy()
-    mdice, loss_all = mdice / n_local, loss_all / n_local
-    channel_dice = channel_dice / n_local
+    mdice, loss_all, channel_dice = reduce_eval_metrics(mdice, loss_all, channel_dice, len(indices), device,
+                                                          getattr(model, "num_classes", 1))
     if print_detail:
         _log("[EVAL] #Images: {}, Dice: {:.4f}, Loss: {:6f}".format(len(eval_dataset), mdice, loss_all))
         _log("[EVAL] Class dice: \n" + str(np.round(channel_dice, 4)))

@@ -59,3 +59,43 @@ def test_bucketed_allreduce_world2():
         assert launched == [(650, 1000), (300, 650), (0, 300)]
         assert scale == 0.5
         assert vols == list(range(8))
+
+
+def _eval_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import numpy as np
+    from medicalseg_b200.core import reduce_eval_metrics
+    # 3 validation volumes over 2 ranks (core.evaluate shards indices[rank::world]): rank 0 scores volumes 0 and 2,
+    # rank 1 volume 1; per-volume (mean Dice, loss, per-class Dice) are made up but distinct
+    per_volume = {0: (0.8, 1.0, [0.9, 0.7]), 1: (0.6, 2.0, [0.5, 0.7]), 2: (0.4, 3.0, [0.3, 0.5])}
+    mine = list(range(3))[rank::world]
+    md = sum(per_volume[i][0] for i in mine)
+    ls = sum(per_volume[i][1] for i in mine)
+    cd = sum(np.asarray(per_volume[i][2]) for i in mine)
+    out = reduce_eval_metrics(md, ls, cd, len(mine), torch.device("cpu"), num_classes=2)
+    # a rank with an empty shard (1 volume, 2 ranks) must still take part in the collective
+    mine1 = [0][rank::world]
+    out1 = reduce_eval_metrics(0.8 if mine1 else 0.0, 1.0 if mine1 else 0.0, np.asarray([0.9, 0.7]) if mine1 else None,
+                               len(mine1), torch.device("cpu"), num_classes=2)
+    q.put((rank, out[0], out[1], out[2].tolist(), out1[0], out1[2].tolist()))
+    dist.destroy_process_group()
+
+
+def test_eval_metrics_are_global_means_world2():
+    """core.evaluate: every rank reports the mean over ALL validation volumes (the reference reports per-rank shards,
+    core/val.py:168), including when one rank's shard is empty"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_eval_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, md, ls, cd, md1, cd1 in res:
+        assert md == pytest.approx((0.8 + 0.6 + 0.4) / 3) and ls == pytest.approx(2.0)
+        assert cd == pytest.approx([(0.9 + 0.5 + 0.3) / 3, (0.7 + 0.7 + 0.5) / 3])
+        assert md1 == pytest.approx(0.8) and cd1 == pytest.approx([0.9, 0.7])
