@@ -196,6 +196,5 @@ class VNetDeepSup(VNet):
         head, dy = item
         head.dgrad_into(self, dy, g_buf)
 
-    def predict_with_losses(self, x, labels=None, losses=None):
-        """evaluation scores the main output only (core/val.py:95 keeps the first loss); the heads are skipped"""
-        return super().predict_with_losses(x, labels, losses)
+    # predict_with_losses (inherited): evaluation scores the main output only (core/val.py:95 keeps the first loss),
+    # and its forward stops before the deep-supervision heads
