@@ -627,15 +627,66 @@ __global__ void __launch_bounds__(kThreads) conv1x1_fwd_kernel(msb_tensor a, con
   }
 }
 
+// Fast path of the head for the channel widths the model produces (8 / 16 / 32): the logits of a voxel accumulate in
+// registers, the weights are read as float4 rows of the TRANSPOSED matrix (one broadcast shared-memory read feeds four
+// FMAs; the scalar loop above is bound by shared-memory bandwidth at C = 20).  Same fmaf order per output: bit-identical.
+template <typename T, int CI8, int CMAX>
+__global__ void __launch_bounds__(kThreads) conv1x1_fwd_reg_kernel(msb_tensor a, const float* __restrict__ w,
+                                                                   const float* __restrict__ b,
+                                                                   float* __restrict__ logits, int ci, int co,
+                                                                   int64_t s) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ __align__(16) float wt[CI8 * 8 * CMAX + CMAX];  // wt[input j][output o], then the bias
+  for (int i = threadIdx.x; i < CI8 * 8 * CMAX; i += kThreads) {
+    const int j = i / CMAX, o = i % CMAX;
+    wt[i] = (o < co && j < ci) ? w[o * ci + j] : 0.f;
+  }
+  for (int i = threadIdx.x; i < CMAX; i += kThreads) wt[CI8 * 8 * CMAX + i] = (b != nullptr && i < co) ? b[i] : 0.f;
+  __syncthreads();
+  const int n = blockIdx.z;
+  const int64_t v0 = (int64_t)blockIdx.x * kVoxPerBlock;
+  const int64_t v1 = min(v0 + (int64_t)kVoxPerBlock, s);
+  const int groups = (ci + 7) >> 3;
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
+    float z[CMAX];
+#pragma unroll
+    for (int o = 0; o < CMAX; ++o) z[o] = wt[CI8 * 8 * CMAX + o];
+#pragma unroll 1
+    for (int k = 0; k < groups; ++k) {
+      float t[8];
+      Vec8<T>::load(view_ptr<T>(a, n, k, s, v), t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4* wrow = reinterpret_cast<const float4*>(wt + (k * 8 + j) * CMAX);
+#pragma unroll
+        for (int o4 = 0; o4 < CMAX / 4; ++o4) {
+          const float4 w4 = wrow[o4];  // rows j >= ci are zero: fmaf(0, finite, z) == z
+          z[o4 * 4 + 0] = fmaf(w4.x, t[j], z[o4 * 4 + 0]);
+          z[o4 * 4 + 1] = fmaf(w4.y, t[j], z[o4 * 4 + 1]);
+          z[o4 * 4 + 2] = fmaf(w4.z, t[j], z[o4 * 4 + 2]);
+          z[o4 * 4 + 3] = fmaf(w4.w, t[j], z[o4 * 4 + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < CMAX; ++o)
+      if (o < co) logits[((int64_t)n * co + o) * s + v] = z[o];
+  }
+}
+
 constexpr int kHeadThreads = 512;  // phase 1: one voxel per thread (da); phase 2: one (o, i) weight pair per thread
 constexpr int kHeadTile = 512;     // voxels staged per inner step of the backward kernel
 constexpr int kHeadPitch = kHeadTile + 1;
 template <int CI8>
-constexpr int head_bwd_smem() { return (CI8 * 8 + kHeadMaxC) * kHeadPitch * (int)sizeof(float); }
+constexpr int head_bwd_smem() { return (CI8 * 8 + 1 + kHeadMaxC) * kHeadPitch * (int)sizeof(float); }
 
 // dlogits -> da (B8) and dW / db.  Phase 1: every thread loads one voxel, writes da and stages (a, dlogits) in shared
-// memory.  Phase 2: thread t < co*ci + co owns ONE weight (or bias) gradient and runs over the 512 staged voxels with
-// broadcast shared-memory reads - no shuffles, no per-pair warp reductions (the C = 20 MRI head has 420 pairs).
+// memory (plus a row of ones, so the bias gradient is one more column of the pair matrix).  Phase 2 (many pairs, e.g.
+// the 420 of the C = 20 MRI head): the [co] x [ci + 1] pair matrix is cut into 4 x 4 REGISTER tiles, one tile per lane,
+// and each of the 16 warps runs over its own 32 of the 512 staged voxels: 8 broadcast shared-memory reads feed 16 FMAs
+// (a thread-per-pair loop needs 2 reads per FMA and is bound by shared-memory bandwidth).  Few pairs (2-3 classes):
+// one warp per pair.  Block-level reduction in shared memory, then one atomic per pair and block.
 template <typename T, int CI8>
 __global__ void __launch_bounds__(kHeadThreads)
     conv1x1_bwd_kernel(msb_tensor a, const float* __restrict__ w, const float* __restrict__ dlogits, msb_tensor da,
@@ -646,19 +697,26 @@ __global__ void __launch_bounds__(kHeadThreads)
   __shared__ float accw[kHeadThreads / 32 * 4];           // per-pair sums of the warp-per-pair path
   if (threadIdx.x < kHeadThreads / 32 * 4) accw[threadIdx.x] = 0.f;
   extern __shared__ float head_smem[];
-  float (*as)[kHeadPitch] = reinterpret_cast<float (*)[kHeadPitch]>(head_smem);                          // [CI8*8]
-  float (*ds)[kHeadPitch] = reinterpret_cast<float (*)[kHeadPitch]>(head_smem + CI8 * 8 * kHeadPitch);   // [kHeadMaxC]
+  constexpr int kOnes = CI8 * 8;  // row of ones (valid voxels) behind the activation rows
+  float (*as)[kHeadPitch] = reinterpret_cast<float (*)[kHeadPitch]>(head_smem);                                // [CI8*8 + 1]
+  float (*ds)[kHeadPitch] = reinterpret_cast<float (*)[kHeadPitch]>(head_smem + (CI8 * 8 + 1) * kHeadPitch);   // [kHeadMaxC]
   for (int i = threadIdx.x; i < kHeadMaxC * CI8 * 8; i += kHeadThreads) {
     const int o = i / (CI8 * 8), c = i % (CI8 * 8);
     ws[o][c] = (o < co && c < ci) ? w[o * ci + c] : 0.f;
   }
   const int n = blockIdx.z;
   const int npairs = co * ci + co;  // last `co` pseudo-pairs accumulate the bias gradient
-  // pairs beyond 512 threads (co*ci + co <= 32*32 + 32) are strided over
-  constexpr int kSlots = (kHeadMaxC * kHeadMaxC + kHeadMaxC + kHeadThreads - 1) / kHeadThreads;
-  float accp[kSlots];
+  const bool few_pairs = npairs <= kHeadThreads / 32 * 4;
+  // register tiles of the many-pairs path: tile = (4 classes o) x (4 columns c of [a | ones]); <= 8 x 9 tiles
+  const int tiles_c = (ci + 1 + 3) / 4, ntiles = ((co + 3) / 4) * tiles_c;
+  constexpr int kTileSlots = (kHeadMaxC / 4 * (kHeadMaxC / 4 + 1) + 31) / 32;  // 72 tiles over 32 lanes
+  float acct[kTileSlots][16];
 #pragma unroll
-  for (int k = 0; k < kSlots; ++k) accp[k] = 0.f;
+  for (int k = 0; k < kTileSlots; ++k)
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acct[k][e] = 0.f;
+  for (int i = threadIdx.x; i < (kHeadMaxC - co) * kHeadPitch; i += kHeadThreads)
+    ds[co][i] = 0.f;  // class rows beyond co are read by the padded tiles: keep them finite
   __syncthreads();
   // grid-stride over 128-voxel tiles: the launch uses a few blocks per SM, so the final atomics (all blocks hit the
   // same <= 1056 addresses - a few cache lines) stay in the low hundreds per address
@@ -675,6 +733,7 @@ __global__ void __launch_bounds__(kHeadThreads)
 #pragma unroll
         for (int j = 0; j < 8; ++j) as[k * 8 + j][threadIdx.x] = t[j];
       }
+      as[kOnes][threadIdx.x] = valid ? 1.f : 0.f;
       // da[i] = sum_o W[o][i] * g[o]: runtime loop over the classes, the da accumulators stay in registers
       float dacc[CI8 * 8];
 #pragma unroll
@@ -702,7 +761,7 @@ __global__ void __launch_bounds__(kHeadThreads)
       }
     }
     __syncthreads();
-    if (npairs <= kHeadThreads / 32 * 4) {
+    if (few_pairs) {
       // few pairs (2-3 classes): one WARP per pair, lanes stride over the staged voxels (a thread-per-pair loop would
       // be one 512-long dependent FMA chain on a handful of threads)
       const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -720,39 +779,63 @@ __global__ void __launch_bounds__(kHeadThreads)
         if (lane == 0) accw[pidx] += acc;
       }
     } else {
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      const int t0 = warp * (kHeadTile / (kHeadThreads / 32));
 #pragma unroll
-      for (int slot = 0; slot < kSlots; ++slot) {
-        const int pidx = threadIdx.x + slot * kHeadThreads;
-        if (pidx >= npairs) continue;
-        float acc = 0.f;
-        if (pidx < co * ci) {
-          const float* ar = as[pidx % ci];
-          const float* dr = ds[pidx / ci];
-#pragma unroll 8
-          for (int t = 0; t < kHeadTile; ++t) acc = fmaf(ar[t], dr[t], acc);
-        } else {
-          const float* dr = ds[pidx - co * ci];
-#pragma unroll 8
-          for (int t = 0; t < kHeadTile; ++t) acc += dr[t];
+      for (int slot = 0; slot < kTileSlots; ++slot) {
+        const int tile = lane + slot * 32;
+        if (tile >= ntiles) continue;
+        const int o0 = (tile / tiles_c) * 4, c0 = (tile % tiles_c) * 4;
+        const float* ar[4];
+        const float* dr[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          ar[q] = as[c0 + q < ci ? c0 + q : kOnes];  // column ci (and the padding behind it) reads the ones row
+          dr[q] = ds[o0 + q];                        // rows >= co are zero
         }
-        accp[slot] += acc;
+#pragma unroll 4
+        for (int t = t0; t < t0 + kHeadTile / (kHeadThreads / 32); ++t) {
+          float av[4], dv[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { av[q] = ar[q][t]; dv[q] = dr[q][t]; }
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acct[slot][r * 4 + q] = fmaf(dv[r], av[q], acct[slot][r * 4 + q]);
+        }
       }
     }
     __syncthreads();
   }
-  if (npairs <= kHeadThreads / 32 * 4) {
+  if (few_pairs) {
     for (int pidx = threadIdx.x; pidx < npairs; pidx += kHeadThreads) {
       if (pidx < co * ci) atomicAdd(dw + pidx, accw[pidx]);
       else if (db) atomicAdd(db + (pidx - co * ci), accw[pidx]);
     }
     return;
   }
+  // block reduction of the 16 warps' register tiles through shared memory (the staging buffers are free now)
+  float* red = head_smem;  // [warps][ntiles * 16]
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int slot = 0; slot < kSlots; ++slot) {
-    const int pidx = threadIdx.x + slot * kHeadThreads;
-    if (pidx >= npairs) continue;
-    if (pidx < co * ci) atomicAdd(dw + pidx, accp[slot]);
-    else if (db) atomicAdd(db + (pidx - co * ci), accp[slot]);
+    for (int slot = 0; slot < kTileSlots; ++slot) {
+      const int tile = lane + slot * 32;
+      if (tile >= ntiles) continue;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) red[(warp * ntiles + tile) * 16 + e] = acct[slot][e];
+    }
+  }
+  __syncthreads();
+  for (int pidx = threadIdx.x; pidx < npairs; pidx += kHeadThreads) {
+    const int o = pidx < co * ci ? pidx / ci : pidx - co * ci;
+    const int c = pidx < co * ci ? pidx % ci : ci;
+    const int e = ((o >> 2) * tiles_c + (c >> 2)) * 16 + (o & 3) * 4 + (c & 3);
+    float sum = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < kHeadThreads / 32; ++wv) sum += red[wv * ntiles * 16 + e];
+    if (pidx < co * ci) atomicAdd(dw + pidx, sum);
+    else if (db) atomicAdd(db + (pidx - co * ci), sum);
   }
 }
 
@@ -953,6 +1036,18 @@ int msb_conv1x1_fwd(msb_tensor a, const float* w, const float* b, float* logits,
               "msb_conv1x1_fwd: needs ci <= a.c <= 32 and co <= a.c");
   const dim3 grid((unsigned)((s + kVoxPerBlock - 1) / kVoxPerBlock), 1, (unsigned)n);
   cudaStream_t st = as_stream(stream);
+#define MSB_HEAD_FWD(CI8_, CMAX_) \
+  MSB_LAUNCH_PDL((conv1x1_fwd_reg_kernel<T, CI8_, CMAX_>), grid, dim3(kThreads), 0, st, a, w, b, logits, ci, co, s)
+  if (a.c == 8 || a.c == 16 || a.c == 32) {
+    MSB_DISPATCH_DTYPE(a.dtype, {
+      if (a.c == 8) { if (co <= 4) MSB_HEAD_FWD(1, 4); else MSB_HEAD_FWD(1, 8); }
+      else if (a.c == 16) { if (co <= 4) MSB_HEAD_FWD(2, 4); else if (co <= 8) MSB_HEAD_FWD(2, 8); else MSB_HEAD_FWD(2, 16); }
+      else { if (co <= 20) MSB_HEAD_FWD(4, 20); else MSB_HEAD_FWD(4, 32); }
+    });
+    MSB_LAUNCH_OK();
+    return MSB_OK;
+  }
+#undef MSB_HEAD_FWD
   MSB_DISPATCH_DTYPE(a.dtype, {
     if (a.c == 8) MSB_LAUNCH_PDL((conv1x1_fwd_kernel<T, 1>), grid, dim3(kThreads), 0, st, a, w, b, logits, ci, co, s);
     else if (a.c == 16) MSB_LAUNCH_PDL((conv1x1_fwd_kernel<T, 2>), grid, dim3(kThreads), 0, st, a, w, b, logits, ci, co, s);
