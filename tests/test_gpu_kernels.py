@@ -634,7 +634,8 @@ def test_resample_full_size_properties():
 
 
 @pytest.mark.parametrize("small,big", [((16, 16, 16), (32, 32, 32)), ((4, 4, 4), (32, 32, 32)), ((8, 8, 4), (64, 64, 12)),
-                                       ((5, 7, 3), (12, 20, 9)), ((9, 6, 10), (9, 6, 10)), ((12, 10, 8), (5, 4, 3))])
+                                       ((5, 7, 3), (12, 20, 9)), ((9, 6, 10), (9, 6, 10)), ((12, 10, 8), (5, 4, 3)),
+                                       ((2, 3, 2), (48, 40, 64))])  # last: footprints beyond the cached-weight length
 def test_trilinear_resize_and_adjoint(small, big):
     """msb_trilinear_fwd / _bwd (VNetDeepSup heads, vnet_deepsup.py:259-272) vs torch F.interpolate(trilinear,
     align_corners=False) and its autograd adjoint; f32, 2e-5 relative."""
