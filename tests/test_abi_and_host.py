@@ -148,3 +148,50 @@ def test_loss_argument_errors_match_reference():
         L.loss_computation([1, 2], None, {"types": [L.DiceLoss()], "coef": [1]})
     with pytest.raises(NotImplementedError):
         L.DiceLoss(sigmoid_norm=False)
+
+
+def test_transform_parameter_draws_match_the_oracle_on_cpu():
+    """host side of medicalseg_b200.transforms (no device needed): same `random` seed -> same crop boxes as the
+    restated reference (transform.py:240-279), rotation coefficients = scipy.ndimage.rotate's matrix / offset"""
+    import random
+    from medicalseg_b200 import transforms as T
+    from oracle import transforms_oracle as to
+
+    class Shape:  # get_params only looks at .shape
+        def __init__(self, s):
+            self.shape = s
+    for seed in range(8):
+        for shape in ((20, 24, 22), (128, 128, 128), (12, 512, 512)):
+            random.seed(seed)
+            ours = T.RandomResizedCrop3D(size=16, scale=[0.8, 1.2]).get_params(Shape(shape), [0.8, 1.2], (3. / 4., 4. / 3.))
+            random.seed(seed)
+            ref = to.RandomResizedCrop3D(size=16, scale=[0.8, 1.2]).box(shape)
+            assert tuple(ours) == tuple(ref)
+        random.seed(seed)
+        a1 = T.RandomRotation3D(degrees=90).get_params((-90, 90))
+        random.seed(seed)
+        angle = random.uniform(-90, 90)
+        plane = [[0, 1], [0, 2], [1, 2]][random.randint(0, 2)]
+        assert a1 == (angle, plane)
+    m, off = T.rotation_coefficients((7, 5), 90.0)
+    assert m == (0.0, 1.0, -1.0, 0.0) and off == (3.0 - 2.0, 2.0 + 3.0)  # degree-exact quarter turn
+    m, off = T.rotation_coefficients((10, 10), 30.0)
+    c, s = np.cos(np.pi / 6), 0.5
+    assert abs(m[0] - c) < 1e-15 and abs(m[1] - s) < 1e-15 and abs(m[2] + s) < 1e-15
+    assert abs(off[0] - (4.5 - (c * 4.5 + s * 4.5))) < 1e-12 and abs(off[1] - (4.5 - (-s * 4.5 + c * 4.5))) < 1e-12
+    with pytest.raises(ValueError):
+        T.RandomRotation3D(degrees=-5)
+    with pytest.raises(TypeError):
+        T.Compose(transforms=(T.RandomFlip3D(),))
+
+
+def test_fused_head_plan_covers_the_shipped_loss_configs_only():
+    from medicalseg_b200.models import losses as L
+    ce, dice = L.CrossEntropyLoss(), L.DiceLoss()
+    plan = L.fused_head_plan({"types": [L.MixedLoss([ce, dice], [1, 2])], "coef": [0.5]})
+    assert plan[0] is ce and plan[1] is dice and plan[2] == [(0, 0.5), (1, 1.0)]
+    assert L.fused_head_plan({"types": [dice], "coef": [1]}) == (None, dice, [(1, 1)])
+    assert L.fused_head_plan({"types": [ce], "coef": [3]}) == (ce, None, [(0, 3)])
+    assert L.fused_head_plan({"types": [dice, dice], "coef": [1, 1]}) is None       # several logits (deep supervision)
+    assert L.fused_head_plan({"types": [L.MixedLoss([dice, dice], [1, 1])], "coef": [1]}) is None
+    assert L.fused_head_plan(None) is None
