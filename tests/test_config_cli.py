@@ -190,3 +190,24 @@ val_dataset:
                         "--seed", "0"], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "[TRAIN] epoch:" in r.stdout and "[EVAL] #Images: 1, Dice:" in r.stdout
+
+
+def test_shipped_configs_build_their_transform_pipelines():
+    """the lung / MRI recipes list the reference's augmentations (lung_coronavirus.yml:10-16,
+    mri_spine_seg_1e-1_big_rmresizecrop_class20.yml:10-13); the deep-supervision config inherits the VNet one and
+    repeats its loss entry four times.  Host-side construction only (the datasets themselves are not shipped)."""
+    from medicalseg_b200.cvlibs import Config
+    from medicalseg_b200 import transforms as T
+    lung = Config(os.path.join(ROOT, "configs/lung_coronavirus/vnet_lung_coronavirus_128_128_128_15k.yml"))
+    tl = [lung._load_object(t) for t in lung.dic["train_dataset"]["transforms"]]
+    assert [type(t) for t in tl] == [T.RandomResizedCrop3D, T.RandomRotation3D, T.RandomFlip3D]
+    assert tl[0].size == (128, 128, 128) and tl[0].scale == [0.8, 1.2] and tl[1].degrees == (-90, 90)
+    assert lung.dic["val_dataset"]["transforms"] == []
+    mri = Config(os.path.join(ROOT, "configs/mri_spine_seg/vnetdeepsup_mri_spine_seg_512_512_12_15k.yml"))
+    tm = [mri._load_object(t) for t in mri.dic["train_dataset"]["transforms"]]
+    assert [type(t) for t in tm] == [T.RandomRotation3D, T.RandomFlip3D] and tm[0].degrees == (-30, 30)
+    assert mri.dic["model"]["type"] == "VNetDeepSup" and mri.dic["model"]["num_classes"] == 20
+    assert mri.dic["model"]["kernel_size"][0] == [2, 2, 4] and mri.dic["model"]["stride_size"][1] == [2, 2, 1]
+    losses = mri.loss
+    assert len(losses["types"]) == 4 and losses["coef"] == [0.25] * 4
+    assert len({id(l) for l in losses["types"]}) == 4  # four separate objects (each caches its own CE class weights)
