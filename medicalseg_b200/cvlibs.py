@@ -9,7 +9,7 @@ import codecs
 import inspect
 import os
 from collections.abc import Sequence
-from typing import Any, Dict
+from typing import Any
 
 import yaml
 

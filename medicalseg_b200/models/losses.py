@@ -13,8 +13,6 @@ mixes_losses.py:22-60.  Behaviours kept on purpose:
 """
 from __future__ import annotations
 
-from typing import List, Optional
-
 import weakref
 
 import numpy as np

@@ -5,7 +5,7 @@ CUDA device: there is no CPU fallback (a CPU tensor raises)."""
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Sequence, Tuple
+from typing import Optional, Sequence
 
 import torch
 

@@ -4,8 +4,6 @@ Inputs may be numpy arrays (copied host->device, result returned as numpy — wh
 tools/prepare.py:236-249) or CUDA torch tensors (result stays on the device).  There is no CPU compute path."""
 from __future__ import annotations
 
-from typing import Optional, Sequence
-
 import numpy as np
 import torch
 

@@ -16,7 +16,6 @@ degree-exact cosdg / sindg it uses itself):
 """
 from __future__ import annotations
 
-import collections.abc
 import numbers
 import random
 

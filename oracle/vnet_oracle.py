@@ -19,7 +19,7 @@ Paddle defaults encoded here (third-party behaviour, not visible in /root/refere
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
