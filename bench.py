@@ -1,13 +1,17 @@
 #!/usr/bin/env python
-"""bench.py — VNet 128^3 train-step volumes/sec (BASELINE.json metric) on N B200s of one node.
+"""bench.py - the BASELINE.json metric (VNet 128^3 train-step volumes/sec) and the other BASELINE configurations on N
+B200s of one node.
 
-    python bench.py --gpus 1 --steps 20 --warmup 5                # our arm (N>1: launched by torchrun)
-    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1 # reference arm: CPU restatement on host cores
+    python bench.py --gpus 1 --steps 20 --warmup 5                  # our arm, headline config (N>1: launched by torchrun)
+    python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 # reference arm: CPU restatement, SAME config
+    python bench.py --config mri_bf16 | vnet128_fp32ddp | preprocess # BASELINE.json configs[3] / [2] / [4]
+    torchrun ... bench.py --gpus 2 --check                          # data-parallel equivalence leg (ddp_grad_rel_err)
 
-One JSON line on stdout (rank 0).  A "step" = forward + CE/Dice loss + backward + gradient all-reduce (N>1) +
-Momentum update of one batch of 2 synthetic 128^3 volumes per GPU (config 1 of BASELINE.json: "VNet 128^3 2-class
-bf16 train step, batch 2, 1xB200"); `value` times it with inputs resident in HBM, `e2e` through the public API with
-pinned HOST inputs (H2D inside the timed region) and the loss read back every step.
+One JSON line on stdout (rank 0).  VNet configs: a "step" = forward + CE/Dice loss + backward + gradient all-reduce
+(N>1) + Momentum update of one batch of 2 synthetic volumes per GPU, launched as ONE CUDA graph per step at every N
+(the data-parallel all-reduces are captured inside it); `value` times it with inputs resident in HBM, `e2e` through the
+public API with pinned HOST inputs (H2D inside the timed region) and the loss read back every step.  preprocess: a
+"step" = one scan = HUnorm + resample 512^3 -> 128^3 (order 1) of the image plus the order-0 resample of its label.
 """
 from __future__ import annotations
 
@@ -24,14 +28,33 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-METRIC = "VNet 128^3 train-step volumes/sec"
 UNIT = "volumes/s"
-SHAPE = (128, 128, 128)
 BATCH = 2
-NUM_CLASSES = 2
-# conv/convT MACs x2, fwd + dgrad + wgrad, 128^3, C=2 (per volume)
-GFLOP_PER_VOLUME = 4380.9
-DOMINANT_GFLOP_PER_VOLUME = 536.87  # up_tr32.ops[0].conv1, 32->32 5^3 @128^3, one pass
+MRI_KW = dict(kernel_size=[[2, 2, 4], [2, 2, 2], [2, 2, 2], [2, 2, 2]], stride_size=[[2, 2, 1], [2, 2, 1], [2, 2, 2], [2, 2, 2]])
+
+# conv/convT MACs x2, fwd + dgrad + wgrad per volume; dominant layer = up_tr32.ops[0].conv1 (32->32 5^3)
+CONFIGS = {
+    "vnet128_bf16": dict(
+        metric="VNet 128^3 train-step volumes/sec", shape=(128, 128, 128), classes=2, dtype="bf16", lr=0.001,
+        model_kw={}, gflop_per_volume=4380.9, dominant_gflop=536.87, passes=1,
+        workload="VNet(num_classes=2) 128x128x128 bf16 train step (fwd + CE/Dice + bwd + Momentum), batch 2 per GPU, "
+                 "BASELINE.json configs[1]"),
+    "vnet128_fp32ddp": dict(
+        metric="VNet 128^3 fp32 train-step volumes/sec", shape=(128, 128, 128), classes=2, dtype="f32x3", lr=0.001,
+        model_kw={}, gflop_per_volume=4380.9, dominant_gflop=536.87, passes=3,
+        workload="VNet(num_classes=2) 128x128x128 fp32-storage train step, 5x5x5 convs as 3 bf16 tensor-core passes "
+                 "(hi*hi + lo*hi + hi*lo), batch 2 per GPU, NCCL gradient all-reduce, BASELINE.json configs[2]"),
+    "mri_bf16": dict(
+        metric="VNet MRISpineSeg 512x512x12 train-step volumes/sec", shape=(512, 512, 12), classes=20, dtype="bf16",
+        lr=0.1, model_kw=MRI_KW, gflop_per_volume=12817.0, dominant_gflop=805.3, passes=1,
+        workload="VNet(num_classes=20, MRI anisotropic kernels) 512x512x12 bf16 train step, batch 2 per GPU, "
+                 "BASELINE.json configs[3]"),
+}
+PRE_METRIC = "preprocess HUnorm+resample 512^3->128^3 volumes/sec"
+PRE_WORKLOAD = ("one scan = HUnorm + resample 512x512x512 -> 128x128x128 (order 1) of the f32 image + order-0 resample of "
+                "its int32 label (tools/prepare_lung_coronavirus.py:81-90), one scan in flight per GPU, "
+                "BASELINE.json configs[4]")
+PRE_COMPULSORY_MB = 142.6  # bytes a fused gather must touch for the image (rows/planes actually sampled)
 
 
 def peaks():
@@ -80,30 +103,34 @@ class ClockSampler:
                 "sampled_over": "device-resident and e2e timed regions (nvidia-smi -lms 100)"}
 
 
-def synthetic_gpu_batch(device, seed):
-    """same recipe as oracle.vnet_oracle.synthetic_batch (SURVEY.md §8d cfg 2), generated on the device"""
+def synthetic_gpu_batch(cfg, device, seed):
+    """same recipe as oracle.vnet_oracle.synthetic_batch, generated on the device: images uniform / max,
+    labels = quantile classes of twice box-smoothed noise (spatially coherent, every class populated)"""
+    shape, classes = cfg["shape"], cfg["classes"]
     g = torch.Generator(device=device).manual_seed(seed)
-    img = torch.rand(BATCH, 1, *SHAPE, generator=g, device=device)
+    img = torch.rand(BATCH, 1, *shape, generator=g, device=device)
     img = img / img.amax(dim=(1, 2, 3, 4), keepdim=True)
-    noise = torch.rand(BATCH, 1, *SHAPE, generator=g, device=device)
-    sm = noise
+    sm = torch.rand(BATCH, 1, *shape, generator=g, device=device)
     for _ in range(2):
         sm = torch.nn.functional.avg_pool3d(torch.nn.functional.pad(sm, (2,) * 6, mode="replicate"), 5, stride=1)
-    thr = sm.flatten(1).median(dim=1).values.view(-1, 1, 1, 1)
-    lab = (sm[:, 0] > thr).to(torch.int32)
+    flat = sm.flatten(1)
+    sub = flat[:, ::max(1, flat.shape[1] // 65536)].float()
+    qs = torch.quantile(sub, torch.linspace(0, 1, classes + 1, device=device)[1:-1], dim=1)  # [classes-1, N]
+    lab = torch.zeros(BATCH, *shape, dtype=torch.int32, device=device)
+    for c in range(classes - 1):
+        lab += (sm[:, 0] > qs[c].view(-1, 1, 1, 1)).to(torch.int32)
     return img.contiguous(), lab.contiguous()
 
 
-def run_ours(args):
+def _dist_env():
+    return (int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def _init(args):
     import torch.distributed as dist
     from medicalseg_b200 import _lib
-    from medicalseg_b200.models import VNet, losses as L
-    from medicalseg_b200.optimizer import Momentum, PolynomialDecay
-    from medicalseg_b200.parallel import DistributedGradReducer
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world, rank, local = _dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
     torch.cuda.set_device(local)
@@ -111,17 +138,45 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     _lib.load()
+    return dist, world, rank, local, device
 
-    model = VNet(num_classes=NUM_CLASSES, compute_dtype="bf16", seed=0)
+
+# =====================================================================================================================
+# VNet train-step configurations
+# =====================================================================================================================
+def run_vnet(args, cfg):
+    dist, world, rank, local, device = _init(args)
+    from medicalseg_b200 import _lib
+    from medicalseg_b200.models import VNet, losses as L
+    from medicalseg_b200.optimizer import Momentum, PolynomialDecay
+    from medicalseg_b200.parallel import DistributedGradReducer
+
+    if args.check:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import ddp_check
+        if world < 2:
+            raise SystemExit("--check needs >= 2 ranks (torchrun --nproc-per-node 2 bench.py --gpus 2 --check)")
+        ok, e_grad = ddp_check.run_checks(device, rank, world)
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank == 0:
+            print(json.dumps({"check": "data-parallel equivalence (sync-BN + bucketed NCCL all-reduce vs one process, "
+                                       "captured graph step vs eager step)", "n_gpus": world, "ok": ok,
+                              "ddp_grad_rel_err": e_grad}))
+        raise SystemExit(0 if ok else 1)
+
+    shape, classes = cfg["shape"], cfg["classes"]
+    model = VNet(num_classes=classes, compute_dtype=cfg["dtype"], seed=0, sync_bn=bool(args.sync_bn), **cfg["model_kw"])
     model.train()
     losses = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1])], "coef": [1]}
     reducer = DistributedGradReducer(model.store.grad).attach(model)
-    opt = Momentum(PolynomialDecay(0.001, 15000), model.parameters(), 0.9, 1e-4, grad_scale=reducer.grad_scale)
-    img, lab = synthetic_gpu_batch(device, seed=rank)
+    opt = Momentum(PolynomialDecay(cfg["lr"], 15000), model.parameters(), 0.9, 1e-4, grad_scale=reducer.grad_scale)
+    img, lab = synthetic_gpu_batch(cfg, device, seed=rank)
     orig_call = _lib.call
-    # world == 1: the whole step is ONE CUDA graph (medicalseg_b200.graph.GraphedTrainStep, the `to_static_training`
-    # hook of core.train); world > 1 keeps the eager path (bucketed NCCL all-reduce overlapping backward)
-    use_graph = world == 1 and not args.no_graph
+    # the whole step is ONE CUDA graph at every N (medicalseg_b200.graph.GraphedTrainStep, the `to_static_training` hook
+    # of core.train); at N > 1 the bucketed NCCL all-reduces are captured inside it, overlapping backward
+    # (f32x3: ~36 ms of kernels per step against ~7 ms of host launch time - the eager loop already runs ahead)
+    use_graph = not args.no_graph and reducer.capturable and cfg["dtype"] == "bf16"
     gstep = None
     if use_graph:
         from medicalseg_b200.graph import GraphedTrainStep
@@ -200,7 +255,6 @@ def run_ours(args):
                 gstep.prefetch(h_img, h_lab)
                 last = float(loss.item())  # D2H read of the step's result
     else:
-        # eager path (world > 1): the same input pipelining through medicalseg_b200.utils.DevicePrefetcher
         from medicalseg_b200.utils import DevicePrefetcher
         pre = DevicePrefetcher(device)
 
@@ -230,60 +284,76 @@ def run_ours(args):
     out = None
     if rank == 0:
         burst, sustained, hbm, src = peaks()
-        # ---- roofline of the dominant kernel: the 32->32 5x5x5 conv at 128^3 (up_tr32.ops[0].conv1), timed alone
+        # ---- roofline of the dominant kernel: the 32->32 5x5x5 conv of up_tr32.ops[0] at this config's shape, timed
+        # alone with CUDA events on the launching stream (f32x3: its three bf16 passes = one f32 convolution)
         from medicalseg_b200 import ops
         from medicalseg_b200.ops import B8
         lu = model.up_tr32.ops[0]
-        xb = B8(BATCH, 32, SHAPE, torch.bfloat16, device=device)
+        xb = B8(BATCH, 32, shape, torch.bfloat16, device=device)
         xb.buf.normal_()
-        yb = B8(BATCH, 32, SHAPE, torch.bfloat16, device=device)
+        yb = B8(BATCH, 32, shape, torch.bfloat16 if cfg["passes"] == 1 else torch.float32, device=device)
         lu.k5._pack(32, 32)
         sums = torch.zeros(64, dtype=torch.float64, device=device)
+        bias = model.store.view(lu.conv1.bias)
+
+        def dominant():
+            if cfg["passes"] == 1:
+                ops.k5_fwd(xb, lu.k5.packed_f, bias, 32, yb, False, None, 1, sums)
+            else:  # hi*hi + lo*hi + hi*lo (the lo operand of a random bf16 tensor is the tensor itself here: same cost)
+                ops.k5_fwd(xb, lu.k5.packed_f, bias, 32, yb, False, None, 1, None)
+                ops.k5_fwd(xb, lu.k5.packed_f, None, 32, yb, True, None, 1, None)
+                ops.k5_fwd(xb, lu.k5.packed_f_lo, None, 32, yb, True, None, 1, sums)
+
         for _ in range(3):
-            ops.k5_fwd(xb, lu.k5.packed_f, model.store.view(lu.conv1.bias), 32, yb, False, None, 1, sums)
+            dominant()
         torch.cuda.synchronize()
         reps = 10
         e0.record()
         for _ in range(reps):
-            ops.k5_fwd(xb, lu.k5.packed_f, model.store.view(lu.conv1.bias), 32, yb, False, None, 1, sums)
+            dominant()
         e1.record()
         torch.cuda.synchronize()
         k_ms = e0.elapsed_time(e1) / reps
-        achieved = BATCH * DOMINANT_GFLOP_PER_VOLUME / k_ms  # GFLOP / ms = TFLOP/s
+        achieved = BATCH * cfg["dominant_gflop"] / k_ms  # algorithmic GFLOP / ms = TFLOP/s
         del xb, yb
         vols = world * BATCH * args.steps / (ms / 1e3)
+        dims = "x".join(str(v) for v in shape)
+        roof = {"bound": "tensor", "achieved": round(achieved, 2), "peak": burst, "unit": "TFLOP/s",
+                "frac": round(achieved / burst, 4), "traffic": None,
+                "peak_source": src + " (burst, kernel timed alone)",
+                "kernel": "conv_k5_fwd_kernel (up_tr32.ops[0].conv1 32->32 5x5x5 @%s, batch 2%s)"
+                          % (dims, "" if cfg["passes"] == 1 else ", 3 bf16 passes per f32 convolution: algorithmic "
+                             "FLOPs are counted once, so frac <= 1/3"),
+                "kernel_ms": round(k_ms, 4),
+                "step_tflops": round(world * BATCH * args.steps * cfg["gflop_per_volume"] / ms, 2),
+                "step_frac_of_sustained": round(BATCH * args.steps * cfg["gflop_per_volume"] / ms / sustained, 4)}
+        if args.config == "vnet128_bf16":
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at this shape (ncu --set full,
+            # profiles/r1s_ncu_full_fwd32_wgrad32_final.txt): 268.7 + 224.1 MB, vs 536.9 MB of algorithmic activation
+            # bytes (x + y, bf16) -> every byte moves once
+            roof["traffic"] = 492.9e6
+            roof["traffic_unit"] = "bytes/launch (ncu dram read+write)"
         out = {
-            "metric": METRIC, "value": round(vols, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": cfg["metric"], "value": round(vols, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "VNet(num_classes=2) 128x128x128 bf16 train step (fwd + CE/Dice + bwd + Momentum), "
-                                   "batch 2 per GPU, BASELINE.json configs[1]",
-                       "global_batch": world * BATCH, "parallelism": "dp%d" % world,
-                       "l2_policy": "per-step working set (~3 GB activations) is far larger than the 126 MB L2",
-                       "bn_statistics": "per-rank batch statistics (no collective in fwd/bwd)"},
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if cfg["dtype"] == "bf16" else "f32",
+            "data": "synthetic",
+            "config": _vnet_config_dict(cfg, world, args),
             "e2e": {"value": round(world * BATCH / (e2e_ms / 1e3), 3), "unit": UNIT,
                     "h2d_bytes_per_step": int(h_img.numel() * 4 + h_lab.numel() * 4),
-                    "d2h_bytes_per_step": int(4 * (1 + 2 + NUM_CLASSES)), "ms_per_step": round(e2e_ms, 3),
+                    "d2h_bytes_per_step": int(4 * (1 + 2 + classes)), "ms_per_step": round(e2e_ms, 3),
                     "last_loss": last},
             # C-ABI calls of one eager step x timed steps (a graph replay launches the same kernels; several calls
             # launch 2-3 kernels, so this is a lower bound of the kernel count)
             "gpu_launches": calls_per_step * args.steps,
-            "launch_mode": "cuda-graph replay (1 cudaGraphLaunch/step)" if use_graph else "eager (python -> C ABI)",
+            "launch_mode": "cuda-graph replay (1 cudaGraphLaunch/step%s)" % (", NCCL all-reduces inside the graph"
+                                                                             if world > 1 else "")
+                           if use_graph else "eager (python -> C ABI)",
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": round(achieved, 2), "peak": burst, "unit": "TFLOP/s",
-                         "frac": round(achieved / burst, 4),
-                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at this shape
-                         # (ncu --set full, profiles/r1s_ncu_full_fwd32_wgrad32_final.txt): 268.7 + 224.1 MB, vs 536.9 MB
-                         # of algorithmic activation bytes (x + y, bf16) -> every byte moves once
-                         "traffic": 492.9e6, "traffic_unit": "bytes/launch (ncu dram read+write)",
-                         "peak_source": src + " (burst, kernel timed alone)",
-                         "kernel": "conv_k5_fwd_kernel<32,8,8> (up_tr32.ops[0].conv1 32->32 5x5x5 @128^3, batch 2)",
-                         "kernel_ms": round(k_ms, 4),
-                         "step_tflops": round(world * BATCH * args.steps * GFLOP_PER_VOLUME / ms, 2),
-                         "step_frac_of_sustained": round(BATCH * args.steps * GFLOP_PER_VOLUME / ms / sustained, 4)},
+            "roofline": roof,
         }
         if not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"] = cpu_baseline(sample_depth=args.cpu_depth)
+            out["cpu_baseline"] = cpu_baseline(cfg)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -291,58 +361,229 @@ def run_ours(args):
         print(json.dumps(out))
 
 
-def cpu_step_time(depth, steps, warmup, batch=1):
-    """times the oracle (torch-CPU restatement of the reference; PaddlePaddle cannot be installed offline) on a
-    [batch,1,depth,128,128] slab of the 128^3 workload; returns (seconds per step, cores)"""
+def _vnet_config_dict(cfg, world, args):
+    return {"workload": cfg["workload"], "global_batch": world * BATCH, "parallelism": "dp%d" % world,
+            "l2_policy": "per-step working set (GBs of activations) is far larger than the 126 MB L2",
+            "bn_statistics": "SyncBatchNorm over all ranks (reference default at world > 1)" if getattr(args, "sync_bn", False)
+                             else "per-rank batch statistics (north_star: all-reduce for the gradient step only)"}
+
+
+def cpu_step_time(cfg, steps, warmup, batch, shape=None, budget_s=None):
+    """times the oracle (torch-CPU restatement of the reference; PaddlePaddle cannot be installed offline) on `batch`
+    volumes of this config; returns (seconds per step, cores[, steps actually timed when `budget_s` is given: the run
+    stops early once the wall-clock budget is spent, so a slow host cannot run into the driver's limit])"""
     from oracle import vnet_oracle as vo
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    model = vo.VNetOracle(num_classes=NUM_CLASSES)
+    shape = tuple(shape or cfg["shape"])
+    model = vo.VNetOracle(num_classes=cfg["classes"], **cfg["model_kw"])
     model.train()
     losses = vo.default_losses()
-    opt = vo.Momentum(vo.PolynomialDecay(0.001, 15000), list(model.parameters()), 0.9, 1e-4)
-    img, lab = vo.synthetic_batch(batch, (depth, SHAPE[1], SHAPE[2]), NUM_CLASSES, seed=0)
+    opt = vo.Momentum(vo.PolynomialDecay(cfg["lr"], 15000), list(model.parameters()), 0.9, 1e-4)
+    img, lab = vo.synthetic_batch(batch, shape, cfg["classes"], seed=0)
     times = []
+    start = time.perf_counter()
     for i in range(warmup + steps):
         masks = vo.make_dropout_masks(batch, seed=0, step=i)
         t0 = time.perf_counter()
         vo.train_step(model, losses, opt, img, lab, masks)
+        dt = time.perf_counter() - t0
         if i >= warmup:
-            times.append(time.perf_counter() - t0)
+            times.append(dt)
+        if budget_s is not None and times and time.perf_counter() - start + dt > budget_s:
+            break
+    if budget_s is not None:
+        return sum(times) / len(times), cores, len(times)
     return sum(times) / len(times), cores
 
 
-def cpu_baseline(sample_depth=32):
-    sec, cores = cpu_step_time(sample_depth, steps=1, warmup=1)
-    frac = sample_depth / SHAPE[0]
-    return {"value": round(frac / sec, 5), "unit": UNIT, "cores": cores, "kind": "port",
+def cpu_baseline(cfg):
+    """bounded sample next to the GPU number: ONE full volume of this config (batch 1) per step, 1 timed step after a
+    small warm-up slab (thread pool / oneDNN primitive caches)"""
+    d, h, w = cfg["shape"]
+    slab = (max(d // 8, 16) if d >= 64 else d, h if d >= 64 else h // 4, w if d >= 64 else w // 4)
+    cpu_step_time(cfg, steps=1, warmup=0, batch=1, shape=slab)
+    sec, cores = cpu_step_time(cfg, steps=1, warmup=0, batch=1)
+    return {"value": round(1.0 / sec, 5), "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "oracle (torch-CPU f32 restatement of the reference VNet; PaddlePaddle not installable offline): "
-                      "1 timed train step (after 1 warm-up) on a batch-1 %dx128x128 slab = %.3f of a 128^3 volume, "
-                      "%.2f s/step" % (sample_depth, frac, sec)}
+                      "1 timed train step on ONE full %dx%dx%d volume (batch 1) after a warm-up slab, %.2f s/step"
+                      % (d, h, w, sec)}
 
 
-def run_reference(args):
-    """reference arm: the reference's CPU path (oracle port) on the box's host cores, same metric/config."""
-    rank = int(os.environ.get("RANK", "0"))
+def run_reference_vnet(args, cfg):
+    """reference arm: the reference's CPU path (oracle port) on the box's host cores - the SAME configuration as our
+    arm: batch 2, full volumes, the requested steps and warm-up (the non-headline configs bound the sample, see `sample`)."""
+    world, rank, _ = _dist_env()
     if rank != 0:
         return
-    depth = args.cpu_depth
-    sec, cores = cpu_step_time(depth, steps=args.steps, warmup=min(args.warmup, 1))
-    frac = depth / SHAPE[0]
-    val = round(frac / sec, 5)
+    batch, steps, warmup, note = BATCH, args.steps, args.warmup, "batch 2, full volumes, every requested step"
+    if args.config != "vnet128_bf16":  # ~3x the FLOPs per volume (MRI): keep the run within a few minutes
+        steps, warmup, note = min(args.steps, 3), min(args.warmup, 1), "batch 2, full volumes, steps/warm-up capped at 3/1"
+    sec, cores, steps = cpu_step_time(cfg, steps=steps, warmup=warmup, batch=batch, budget_s=900.0)
+    val = round(batch / sec, 5)
+    n = max(args.gpus, 1)
+
+    class _A:
+        sync_bn = False
     out = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": cfg["metric"], "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "VNet(num_classes=2) 128x128x128 train step, reference CPU path (torch-CPU restatement; "
-                               "PaddlePaddle not installable offline), bounded sample: batch-1 %dx128x128 slab per step"
-                               % depth},
+        "config": _vnet_config_dict(cfg, n, _A),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "batch-1 %dx128x128 slab (%.3f volume) per step, %d timed steps" % (depth, frac, args.steps)},
+                         "sample": "oracle port of the reference train step (torch-CPU f32; PaddlePaddle not installable "
+                                   "offline), one host process on all %d cores: %s, %.2f s/step" % (cores, note, sec)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    print(json.dumps(out))
+
+
+# =====================================================================================================================
+# preprocess configuration (BASELINE.json configs[4])
+# =====================================================================================================================
+def _pre_inputs(seed):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    vol = rng.uniform(-2000, 2000, size=(512, 512, 512)).astype(np.float32)
+    vol[rng.random(vol.shape) < 0.001] = np.nan
+    lab = rng.integers(0, 3, size=(512, 512, 512)).astype(np.int32)
+    return vol, lab
+
+
+def run_preprocess(args):
+    dist, world, rank, local, device = _init(args)
+    from medicalseg_b200 import preprocess as P
+    vol, lab = _pre_inputs(rank)
+    h_vol, h_lab = torch.from_numpy(vol).pin_memory(), torch.from_numpy(lab).pin_memory()
+    d_vol, d_lab = h_vol.to(device), h_lab.to(device)
+    hu = ("hunorm", -1200, 600, -2000)
+
+    def scan_device():
+        a, _ = P.resample(d_vol, new_shape=[128, 128, 128], order=1, pre_op=hu)
+        b, _ = P.resample(d_lab, new_shape=[128, 128, 128], order=0)
+        return a, b
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        scan_device()
+    barrier()
+    # the 1 GiB source volume + label are far larger than the 126 MB L2; iterations re-read them from HBM
+    reps = 20  # scans per timed step group: one scan is ~0.13 ms, so a "step" is timed as a group of `reps` scans
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    windows = []
+    w0 = time.time()
+    e0.record()
+    for _ in range(args.steps * reps):
+        scan_device()
+    e1.record()
+    barrier()
+    windows.append((w0, time.time()))
+    t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_scan = float(t.item()) / (args.steps * reps)
+
+    # kernel alone (roofline): fused HUnorm + order-1 gather of the image
+    for _ in range(3):
+        P.resample(d_vol, new_shape=[128, 128, 128], order=1, pre_op=hu)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(50):
+        P.resample(d_vol, new_shape=[128, 128, 128], order=1, pre_op=hu)
+    e1.record()
+    torch.cuda.synchronize()
+    k_ms = e0.elapsed_time(e1) / 50
+
+    # ---- e2e: host-resident scans through the public pipeline (pinned inputs, H2D of scan i+1 overlapping the kernels
+    # and the D2H of scan i), results land in pinned host memory
+    pipe = P.ScanPipeline(new_shape=(128, 128, 128), pre_op=hu, device=device)
+    e2e_scans = max(4, min(args.steps, 12))
+    for _ in pipe.run([(h_vol, h_lab)] * 3):
+        pass
+    barrier()
+    w0 = time.time()
+    t0 = time.perf_counter()
+    n_out = 0
+    for o_img, o_lab in pipe.run([(h_vol, h_lab)] * e2e_scans):
+        n_out += 1
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    windows.append((w0, time.time()))
+    t2 = torch.tensor([e2e_s], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_s = float(t2.item())
+    clocks = sampler.stop(windows) if rank == 0 else None
+    out = None
+    if rank == 0:
+        burst, sustained, hbm, src = peaks()
+        achieved = PRE_COMPULSORY_MB / 1e3 / (k_ms / 1e3)  # GB/s
+        out = {
+            "metric": PRE_METRIC, "value": round(world / (ms_scan / 1e3), 2), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_scan * reps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": PRE_WORKLOAD, "scans_per_step": reps, "parallelism": "by-volume x%d (no collective)" % world,
+                       "l2_policy": "source volume + label (1.07 GB) exceed the 126 MB L2"},
+            "e2e": {"value": round(world * e2e_scans / e2e_s, 3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(h_vol.numel() * 4 + h_lab.numel() * 4),
+                    "d2h_bytes_per_step": int(2 * 128 ** 3 * 4), "ms_per_scan": round(e2e_s / e2e_scans * 1e3, 3),
+                    "note": "PCIe-bound: 1.07 GB host->device per scan; double-buffered pinned staging"},
+            "gpu_launches": 2 * args.steps * reps,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm, "unit": "GB/s",
+                         "frac": round(achieved / hbm, 4), "traffic": None,
+                         "peak_source": src, "kernel": "resample_f32 order 1 with fused HUnorm, 512^3 -> 128^3",
+                         "kernel_ms": round(k_ms, 4),
+                         "algorithmic_bytes": "142.6 MB compulsory per image (SURVEY §8d); full-scan equivalent 545.3 MB"},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline_preprocess(vol, lab)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+def cpu_baseline_preprocess(vol=None, lab=None, scans=1):
+    """the reference's NumPy/SciPy path (values.py:67-87 + geometry.py:31-69), restated in oracle/preprocess_oracle.py,
+    on one core (scipy.ndimage.zoom is single-threaded)"""
+    from oracle import preprocess_oracle as po
+    if vol is None:
+        vol, lab = _pre_inputs(0)
+    t0 = time.perf_counter()
+    for _ in range(scans):
+        po.resample(po.HUnorm(vol), new_shape=[128, 128, 128], order=1)
+        po.resample(lab, new_shape=[128, 128, 128], order=0)
+    sec = (time.perf_counter() - t0) / scans
+    return {"value": round(1.0 / sec, 4), "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "oracle (numpy/scipy restatement pinned to the reference's own values.py/geometry.py outputs): %d "
+                      "full 512^3 scan(s) (image HUnorm + zoom order 1, label zoom order 0), %.2f s/scan; CuPy absent"
+                      % (scans, sec)}
+
+
+def run_reference_preprocess(args):
+    world, rank, _ = _dist_env()
+    if rank != 0:
+        return
+    scans = max(1, min(args.steps, 5))
+    cb = cpu_baseline_preprocess(scans=scans)
+    out = {"impl": "reference", "metric": PRE_METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+           "steps": scans, "warmup": 0, "ms_per_step": round(1e3 / cb["value"], 1), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": PRE_WORKLOAD}, "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
     print(json.dumps(out))
 
 
@@ -352,14 +593,19 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="vnet128_bf16", choices=list(CONFIGS) + ["preprocess"],
+                    help="BASELINE.json configuration (default: the headline, configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph (N=1)")
-    ap.add_argument("--cpu-depth", type=int, default=32, help="depth of the 128x128 slab the CPU arm processes per step")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
+    ap.add_argument("--sync-bn", action="store_true", help="SyncBatchNorm over all ranks (reference default at N>1)")
+    ap.add_argument("--check", action="store_true", help="N>=2: data-parallel equivalence checks instead of timing")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
+    if args.config == "preprocess":
+        (run_reference_preprocess if args.impl == "reference" else run_preprocess)(args)
+    elif args.impl == "reference":
+        run_reference_vnet(args, CONFIGS[args.config])
     else:
-        run_ours(args)
+        run_vnet(args, CONFIGS[args.config])
 
 
 if __name__ == "__main__":

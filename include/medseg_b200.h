@@ -310,6 +310,14 @@ int msb_resample_f32(const float* src, msb_dim3 in_dims, float* dst, msb_dim3 ou
 int msb_resample_i32(const int32_t* src, msb_dim3 in_dims, int32_t* dst, msb_dim3 out_dims, void* stream);
 int msb_label_remap(int32_t* labels, int64_t count, const int32_t* keys, const int32_t* vals, int nmap, void* stream);
 
+/* paddle.argmax(logit, axis=1, keepdim=True, dtype='int32') of NCDHW f32 logits (medicalseg/core/infer.py:92): pred int32
+ * [N][S], the first maximum wins. */
+int msb_argmax_channels(const float* logits, int n, int c, int64_t s, int32_t* pred, void* stream);
+/* nn.Dropout3D(p) masks of every dropout site of one forward (medicalseg/models/vnet.py:103,108,144-145,149-150):
+ * out[i] = 0 or 1/(1-p), i over the concatenated [N][C] masks.  Counter-based generator keyed by (seed, *step_counter, i);
+ * the kernel advances *step_counter (device memory), so a CUDA-graph replay draws new masks each step. */
+int msb_dropout_masks(uint64_t seed, uint64_t* step_counter, float* out, int total, float p, void* stream);
+
 /* ---- training augmentations on the device (medicalseg/transforms/functional.py:77-110, transform.py:46-72) ----
  * scipy.ndimage.rotate(axes=(axis_a, axis_b), reshape=False, mode='constant', order 0|1) of a [D][H][W] volume:
  * dst[o] = interp(src, M @ o + off) in every plane, cval outside 0 <= c <= n-1.  M = [[c, s], [-s, c]] with

@@ -96,6 +96,8 @@ SIGNATURES = {
     "msb_rotate3d_i32": (I, [P, P, D3, I, I, D, D, D, D, D, D, I, I, P]),
     "msb_flip3d": (I, [P, P, D3, I, P]),
     "msb_scale_by_max": (I, [P, P, L, P, P]),
+    "msb_argmax_channels": (I, [P, I, I, L, P, P]),
+    "msb_dropout_masks": (I, [C.c_uint64, P, P, I, F, P]),
     "msb_trilinear_fwd": (I, [P, L, D3, P, D3, P]),
     "msb_trilinear_bwd": (I, [P, L, D3, P, D3, P]),
 }

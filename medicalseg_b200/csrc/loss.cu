@@ -334,6 +334,41 @@ __global__ void __launch_bounds__(kLossThreads)
   }
 }
 
+// paddle.argmax(logit, axis=1, keepdim=True, dtype='int32') (core/infer.py:92): first maximum wins.  One thread per
+// voxel; consecutive threads read consecutive voxels of every class plane (coalesced), writes int32.
+__global__ void argmax_channels_kernel(const float* __restrict__ logits, int c, int64_t s, int32_t* __restrict__ pred) {
+  const int n = blockIdx.y;
+  const float* src = logits + (int64_t)n * c * s;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < s; v += (int64_t)gridDim.x * blockDim.x) {
+    int best = 0;
+    float zbest = __ldg(src + v);
+    for (int o = 1; o < c; ++o) {
+      const float z = __ldg(src + (int64_t)o * s + v);
+      if (z > zbest) { zbest = z; best = o; }
+    }
+    pred[(int64_t)n * s + v] = best;
+  }
+}
+
+// nn.Dropout3D(p) channel masks (vnet.py:103,144-145): out[i] = 0 or 1/(1-p) per (sample, channel), all dropout sites
+// of one forward in ONE launch.  Counter-based generator (splitmix64 finaliser of (seed, step, i)); the step counter
+// lives in device memory and is advanced by the kernel itself, so a CUDA-graph replay draws fresh masks every step.
+__global__ void dropout_masks_kernel(uint64_t seed, unsigned long long* __restrict__ step_counter, float* __restrict__ out,
+                                     int total, float p, float keep_scale) {
+  const unsigned long long step = *step_counter;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(step * 0x100000001B3ull + (uint64_t)i + 1ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const float u = (float)(z >> 40) * (1.0f / 16777216.0f);  // 24 random bits -> [0, 1)
+    out[i] = u >= p ? keep_scale : 0.f;
+  }
+  // every thread has read the counter before any block can finish: a single-block launch is required by the wrapper
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *step_counter = step + 1ull;
+}
+
 }  // namespace msb
 
 using namespace msb;
@@ -421,6 +456,23 @@ int msb_eval_head(msb_tensor a, const float* w, const float* b, const int32_t* l
   });
 #undef MSB_EVAL_HEAD
 #undef MSB_EVAL_HEAD_M
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+int msb_argmax_channels(const float* logits, int n, int c, int64_t s, int32_t* pred, void* stream) {
+  MSB_REQUIRE(logits && pred && n > 0 && c > 0 && s > 0, "msb_argmax_channels: bad arguments");
+  int64_t blocks = (s + 255) / 256;
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  argmax_channels_kernel<<<dim3((unsigned)blocks, (unsigned)n), 256, 0, as_stream(stream)>>>(logits, c, s, pred);
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+int msb_dropout_masks(uint64_t seed, uint64_t* step_counter, float* out, int total, float p, void* stream) {
+  MSB_REQUIRE(step_counter && out && total > 0 && p >= 0.f && p < 1.f, "msb_dropout_masks: bad arguments");
+  dropout_masks_kernel<<<1, 1024, 0, as_stream(stream)>>>(seed, reinterpret_cast<unsigned long long*>(step_counter), out,
+                                                          total, p, 1.f / (1.f - p));
   MSB_LAUNCH_OK();
   return MSB_OK;
 }

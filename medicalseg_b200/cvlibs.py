@@ -2,7 +2,8 @@
 config.py:29-429).  Same semantics: components are looked up by class name from `type:`, `_inherited_: False`
 opts a sub-dict out of the merge, CLI learning_rate / batch_size / iters override the file, loss `types` are
 broadcast over `coef`, `num_classes` is injected from the dataset when the model section omits it.
-Difference (documented in DESIGN.md): the model is NOT converted to SyncBatchNorm (config.py:322)."""
+With more than one rank the model is built with `sync_bn=True` - the reference converts every BatchNorm to
+SyncBatchNorm there (config.py:322) - unless the YAML says `sync_bn: false` (per-rank statistics)."""
 from __future__ import annotations
 
 import codecs
@@ -181,6 +182,11 @@ class Config:
             if ds is not None and hasattr(ds, "num_classes"):
                 model_cfg["num_classes"] = ds.num_classes
         if self._model is None:
+            component = self._load_component(model_cfg["type"])
+            import torch.distributed as dist
+            if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+                    and "sync_bn" not in model_cfg and "sync_bn" in inspect.signature(component).parameters):
+                model_cfg["sync_bn"] = True  # config.py:322: paddle.nn.SyncBatchNorm.convert_sync_batchnorm(model)
             self._model = self._load_object(model_cfg)
         return self._model
 

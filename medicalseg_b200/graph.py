@@ -13,9 +13,12 @@ Everything that varies between steps lives in device memory: the batch (static i
 re-packing for the tensor-core kernels is issued at the START of the captured step on a side stream (each conv waits
 for its own layer), so it overlaps the first convolutions as in the eager path.
 
-world_size > 1: core.train keeps the eager path (bucketed NCCL all-reduce overlapping backward).  Capturing the
-all-reduces too was tried on 2 x B200 (async NCCL work on the communication stream inside the capture, thread-local
-capture mode) and DEADLOCKED in the warm-up / capture phase, so the graph stays single-process.
+world_size > 1: the bucketed gradient all-reduces are captured too.  Capturing torch.distributed's ProcessGroupNCCL
+work objects deadlocked on 2 x B200 in round 1 (its own streams / events / watchdog bookkeeping inside the capture), so
+the reducer now owns a plain NCCL communicator (nccl.py) and every bucket is one `ncclAllReduce` on the reducer's side
+stream, forked from / joined to the capturing stream by events - the data-parallel step is the same single graph launch
+as the single-GPU step, with the collectives overlapping backward inside the graph.  A reducer on the
+torch.distributed transport (gloo CPU tests) is not capturable and is rejected.
 """
 from __future__ import annotations
 
@@ -51,7 +54,7 @@ class GraphedTrainStep:
         loss.backward()
         m._backward(leaf.grad)
         if self.reducer is not None:
-            self.reducer.wait()  # single process: only resets the bucket planner fed by the model's grad-ready hook
+            self.reducer.wait()  # joins the all-reduce side stream (world > 1) and resets the bucket planner
         opt.step()
         m.clear_gradients()
         if m._defer_prepack and m._side_stream is not None:
@@ -59,9 +62,10 @@ class GraphedTrainStep:
         return loss.detach(), dice
 
     def _capture(self, images, labels):
-        if self.reducer is not None and getattr(self.reducer, "world", 1) > 1:
-            raise RuntimeError("GraphedTrainStep is single-process: capturing the NCCL all-reduces deadlocked when it "
-                               "was tried (see the module docstring); use the eager step with world_size > 1")
+        if self.reducer is not None and not getattr(self.reducer, "capturable", True):
+            raise RuntimeError("GraphedTrainStep at world_size > 1 needs DistributedGradReducer(backend='direct') (plain "
+                               "ncclAllReduce calls a capture can record); torch.distributed work objects are not "
+                               "capturable (see the module docstring)")
         m, opt = self.model, self.optimizer
         if getattr(m, "deep_supervision", False):
             raise NotImplementedError("GraphedTrainStep captures the single-output VNet step; VNetDeepSup (four outputs) "
@@ -88,7 +92,9 @@ class GraphedTrainStep:
             pk.pack_event = None  # completed (synchronize above); a capturing stream must not wait on outside events
         m._defer_prepack = True
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread-local error mode: other threads (torch.distributed's NCCL watchdog, the clock sampler) may call CUDA
+        # APIs while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             loss, dice = self._body()
         self.s_loss = loss
         self.s_dice = dice._dev if isinstance(dice, L.LazyHostArray) else None

@@ -194,7 +194,7 @@ class _BnAct:
             self.bnbuf = torch.empty(4 * g * c, dtype=torch.float32, device=y.buf.device)
         count = y.s * (y.n if g == 1 else 1)
         if eng.training and eng.sync_world() > 1:
-            torch.distributed.all_reduce(sums)  # [2][g][C] f64 sums over all ranks (stream-ordered NCCL call)
+            eng.stat_all_reduce(sums)  # [2][g][C] f64 sums over all ranks (stream-ordered NCCL call)
             count *= eng.sync_world()
         a2 = st.phys(self.relu2._weight) if (self.relu2 is not None and residual is not None) else None
         ops.bn_fwd_fused(y, out, residual, tile, tile_c, sums if eng.training else None, count,
@@ -216,7 +216,7 @@ class _BnAct:
             # SyncBatchNorm backward: the input gradient needs sum(g1), sum(g1*xhat) over ALL ranks, the parameter
             # gradients stay per-rank sums (the data-parallel all-reduce averages them afterwards)
             local = red.clone()
-            torch.distributed.all_reduce(red)
+            eng.stat_all_reduce(red)
             ops.bn_act_bwd_apply(y, residual, tile, tile_c, gout, self.bnbuf, a1, a2, red, count, True, dy, dres,
                                  dres_acc, None, None, None, None, g)
             c = y.c
@@ -330,7 +330,8 @@ class _K5:
             ops.k5_wgrad_tm(xl, dyh, dw_tm, None, self.cout, self.cin)
             ops.k5_wgrad_tm(xh, dyl, dw_tm, None, self.cout, self.cin)
             if db is not None:
-                db += dy.to_ncdhw(self.cout).sum((0, 2, 3, 4))  # eval-mode backward only (a torch reduction: rare path)
+                ops.channel_sum(dyh, self.cout, db)  # eval-mode backward only; hi + lo = the f32 gradient
+                ops.channel_sum(dyl, self.cout, db)
         elif eng.dtype == torch.bfloat16:
             if dx is not None:
                 ops.k5_fwd(dy, self.packed_b, None, self.cin, dx, accumulate, ch_scale, 1, None,
@@ -487,7 +488,10 @@ class InputTransition(_Module):  # vnet.py:57-79
         self.bn1 = _BN(st, prefix + ".bn1", 16, 16)
         self.relu1 = _PReLU(st, prefix + ".relu1", 16, 16)
         self.act = _BnAct(eng, self.bn1, self.relu1)
-        self.k551 = _K551(eng, self.conv1, in_channels, 16, 0) if eng.dtype == torch.bfloat16 else None
+        # 1 input channel (every shipped config): w-folded 5x5x1 tensor-core conv (bf16) / direct kernel (f32).
+        # 2, 4, 8, 16 input channels (vnet.py:74-79 tiles x 16/Cin times): the regular 5x5x5 path on a zero-padded view.
+        self.k551 = _K551(eng, self.conv1, in_channels, 16, 0) if (eng.dtype == torch.bfloat16 and in_channels == 1) else None
+        self.k5 = _K5(eng, self.conv1, in_channels, 16) if in_channels > 1 else None
 
 
 class DownTransition(_Module):  # vnet.py:82-113
@@ -587,8 +591,10 @@ class VNet(_Module):
         if elu:
             raise NotImplementedError("elu=True (nn.ELU) is not supported; the reference itself reports NaN gradients "
                                       "with it (medicalseg/core/train.py:139)")
-        if in_channels != 1:
-            raise NotImplementedError("in_channels != 1 is not supported by the in_tr kernel (reference configs use 1)")
+        if in_channels not in (1, 2, 4, 8, 16):
+            # vnet.py:78-79: x is tiled int(16 / in_channels) times and added to the 16-channel conv output
+            raise ValueError("in_channels must divide 16 (InputTransition tiles the input to 16 channels), got %r"
+                             % (in_channels,))
         if not torch.cuda.is_available():
             raise RuntimeError("medicalseg_b200.VNet needs a CUDA device (sm_100a); there is no CPU fallback")
         from .. import _lib
@@ -634,8 +640,12 @@ class VNet(_Module):
         self._side_stream = None
         self._defer_prepack = False  # GraphedTrainStep: the re-pack is issued at the START of the captured step
         self._masks: Optional[Dict[str, torch.Tensor]] = None
+        self._drawn: Optional[Dict[str, torch.Tensor]] = None
+        self._dropout_step = None
+        self._dropout_seed = int(torch.initial_seed() if seed is None else seed) * 2654435761 + 12345
         self._tape = None
         self.grad_ready_hook = None  # callable(lo, hi) on flat-grad ranges, fired in backward order (DDP buckets)
+        self.stat_all_reduce = self._torch_stat_all_reduce  # replaced by DistributedGradReducer.attach (own NCCL comm)
         if pretrained is not None:
             self.init_weight()
 
@@ -783,6 +793,10 @@ class VNet(_Module):
         d = torch.distributed
         return d.get_world_size() if d.is_available() and d.is_initialized() else 1
 
+    @staticmethod
+    def _torch_stat_all_reduce(t):
+        torch.distributed.all_reduce(t)
+
     def scratch_f64(self, count):
         count = _pad(count, 2)
         if self._scratch_off + count > self._scratch.numel():
@@ -818,8 +832,9 @@ class VNet(_Module):
                 ops.tc_wgrad(bl, sh, dw, None, kernel, stride, bias_from_big, self._k2_ws)
                 ops.tc_wgrad(bh, sl, dw, None, kernel, stride, bias_from_big, self._k2_ws)
                 if dbias is not None:  # eval-mode backward only
-                    src = big if bias_from_big else small
-                    dbias += src.to_ncdhw().sum((0, 2, 3, 4))
+                    sh2, sl2 = (bh, bl) if bias_from_big else (sh, sl)
+                    ops.channel_sum(sh2, dbias.numel(), dbias)
+                    ops.channel_sum(sl2, dbias.numel(), dbias)
             else:
                 ops.tc_wgrad(big, small, dw, dbias, kernel, stride, bias_from_big, self._k2_ws)
         else:
@@ -874,8 +889,24 @@ class VNet(_Module):
             return None
         if self._masks is not None:
             return self._masks[site]
-        keep = (torch.rand(n, c, device=self.device) >= 0.5).to(torch.float32) * 2.0
-        return keep
+        return self._drawn[site]
+
+    _DROPOUT_SITES = (("down_tr128", 128), ("down_tr256", 256), ("up_tr256.x", 256), ("up_tr256.skip", 128),
+                      ("up_tr128.x", 256), ("up_tr128.skip", 64))  # vnet.py:103,108,144-145,149-150 via :201-232
+
+    def _draw_masks(self, n):
+        """Dropout3D(p=0.5) masks of all six sites in ONE kernel launch (msb_dropout_masks): counter-based generator
+        keyed by (seed, device-side step counter), so eager steps and CUDA-graph replays both draw fresh masks"""
+        if self._dropout_step is None:
+            self._dropout_step = torch.zeros(1, dtype=torch.int64, device=self.device)
+        total = sum(c for _, c in self._DROPOUT_SITES)
+        buf = torch.empty(n * total, dtype=torch.float32, device=self.device)
+        ops.dropout_masks(self._dropout_seed, self._dropout_step, buf, 0.5)
+        out, off = {}, 0
+        for site, c in self._DROPOUT_SITES:
+            out[site] = buf[off:off + n * c].view(n, c)
+            off += n * c
+        return out
 
     @staticmethod
     def _down_dims(dims, k, s):
@@ -903,6 +934,8 @@ class VNet(_Module):
                      and getattr(self, "eval_fused_epilogue", True))
         if T:
             self.bn_stats_version += 1  # a train-mode forward moves the running statistics
+            if self._masks is None:
+                self._drawn = self._draw_masks(n)
 
         # concat buffers: [up-branch | skip] (vnet.py:152 order)
         xcat32 = self._new(n, 32, dims[0])
@@ -919,6 +952,11 @@ class VNet(_Module):
             ops.fold_w_f32(x, self.in_channels, xf, 1)
             it.k551.fwd(xf, y0, st.view(it.conv1.bias), g, s0)
             tape["xf"] = xf
+        elif it.k5 is not None:
+            xb = B8.from_ncdhw(x, self.dtype, c_pad=16 if (self.dtype == torch.bfloat16 or self.tc3) else
+                               _pad(self.in_channels, 8))
+            it.k5.fwd(xb, y0, s0)
+            tape["xb"] = xb
         else:
             ops.conv_in_fwd(x, st.view(it.conv1.weight), st.view(it.conv1.bias), y0, g, s0)
         out16 = xcat32.view(16, 16)
@@ -1155,6 +1193,8 @@ class VNet(_Module):
             it.k551.wgrad(tape["xf"], dy0)
             if not self.bias_grad_is_zero():
                 ops.channel_sum(dy0, 16, st.grad_view(it.conv1.bias))
+        elif it.k5 is not None:
+            it.k5.bwd(tape["xb"], dy0, None)
         else:
             ops.conv_in_wgrad(x, dy0, st.grad_view(it.conv1.weight), st.grad_view(it.conv1.bias))
         self._fire(it)

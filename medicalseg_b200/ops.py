@@ -347,6 +347,18 @@ def dice_ce_bwd(logits, labels, class_w, acc, ignore_index, coef_ce, coef_dice, 
          ignore_index, float(coef_ce), float(coef_dice), _ptr(coef_dev), _ptr(dlogits), _stream())
 
 
+def argmax_channels(logits, pred):
+    """pred int32 [N,1,D,H,W] = argmax over the channel axis of NCDHW f32 logits (first maximum wins)"""
+    n, c = logits.shape[:2]
+    call("msb_argmax_channels", _ptr(logits), n, c, logits[0, 0].numel(), _ptr(pred), _stream())
+
+
+def dropout_masks(seed: int, step_counter, out, p: float = 0.5):
+    """out (f32, all Dropout3D sites of one forward concatenated) <- 0 or 1/(1-p); advances the device step counter"""
+    call("msb_dropout_masks", int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(step_counter), _ptr(out), out.numel(), float(p),
+         _stream())
+
+
 # ---- optimizer ------------------------------------------------------------------------------------------------
 def momentum_step(p, g, v, lr, mu, wd, grad_scale=1.0):
     call("msb_momentum_step", _ptr(p), _ptr(g), _ptr(v), p.numel(), float(lr), float(mu), float(wd),

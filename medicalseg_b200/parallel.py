@@ -7,8 +7,13 @@ finishes its backward fires `grad_ready_hook(lo, hi)`, and we launch the all-red
 side stream right away, overlapping it with the rest of backward.  Small slices are coalesced into buckets.
 Averaging (1/world) is folded into the optimizer kernel (Momentum.grad_scale) — no extra pass over the grads.
 
-BatchNorm statistics stay per-rank (north_star: "allreduce for the gradient step only"); the reference converts
-to SyncBatchNorm (cvlibs/config.py:322), which differs at world > 1 — see DESIGN.md.
+Two transports: `backend="direct"` (default on CUDA) calls ncclAllReduce on our own communicator (nccl.py) on the
+reducer's side stream - plain stream-ordered work, so the whole data-parallel step can be captured into ONE CUDA graph
+exactly like the single-GPU step; `backend="torch"` goes through torch.distributed (gloo in the CPU tests).
+
+BatchNorm statistics: `VNet(sync_bn=True)` shares them across ranks like the reference's SyncBatchNorm conversion
+(cvlibs/config.py:322; `train.py` enables it by default at world > 1); `sync_bn=False` keeps them per rank
+(north_star: "allreduce for the gradient step only") - see DESIGN.md §6.
 """
 from __future__ import annotations
 
@@ -52,7 +57,7 @@ class DistributedGradReducer:
     """Attach to a model: reducer = DistributedGradReducer(model); after loss.backward() call reducer.wait()
     before optimizer.step().  Works with any torch.distributed backend (nccl on GPUs, gloo in CPU tests)."""
 
-    def __init__(self, flat_grad: torch.Tensor, bucket_mb: float = 32.0, group=None):
+    def __init__(self, flat_grad: torch.Tensor, bucket_mb: float = 32.0, group=None, backend: Optional[str] = None):
         self.flat_grad = flat_grad
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -60,9 +65,36 @@ class DistributedGradReducer:
         self.handles: List = []
         self.comm_stream = torch.cuda.Stream() if flat_grad.is_cuda else None
         self.launched: List[Tuple[int, int]] = []
+        if backend is None:
+            backend = "direct" if (flat_grad.is_cuda and group is None) else "torch"
+        self.backend = backend
+        self.comm = self.stat_comm = None
+        if self.world > 1 and backend == "direct":
+            from .nccl import Communicator
+            self.comm = Communicator(flat_grad.device)
+
+    @property
+    def capturable(self) -> bool:
+        """True when the all-reduces are plain stream-ordered NCCL calls that a CUDA-graph capture can record"""
+        return self.world == 1 or self.comm is not None
+
+    def all_reduce_(self, t: torch.Tensor):
+        """small in-place sum on the CURRENT stream (SyncBatchNorm statistics); same transport as the gradients"""
+        if self.world == 1:
+            return
+        if self.stat_comm is not None:
+            self.stat_comm.all_reduce_(t)
+        else:
+            dist.all_reduce(t, group=self.group)
 
     def attach(self, model):
         model.grad_ready_hook = self.on_ready
+        model.stat_all_reduce = self.all_reduce_
+        if self.comm is not None and self.stat_comm is None and getattr(model, "sync_bn", False):
+            # SyncBatchNorm sums run on the COMPUTE stream while gradient buckets are in flight on the side stream: one
+            # NCCL communicator must not be used from two streams concurrently, so the statistics get their own
+            from .nccl import Communicator
+            self.stat_comm = Communicator(self.flat_grad.device)
         return self
 
     def _launch(self, lo: int, hi: int):
@@ -70,7 +102,10 @@ class DistributedGradReducer:
         if self.world == 1:
             return
         view = self.flat_grad[lo:hi]
-        if self.comm_stream is not None:
+        if self.comm is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())  # fork (an event edge inside a capture)
+            self.comm.all_reduce_(view, self.comm_stream)
+        elif self.comm_stream is not None:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
                 self.handles.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))

@@ -9,7 +9,27 @@ import numpy as np
 import torch
 
 
+class _NumpyOnlyUnpickler(pickle.Unpickler):
+    """Unpickler for Paddle-format checkpoints (pickled dicts of numpy arrays): only the constructors numpy's own
+    array / dtype / scalar reduction uses and plain containers are allowed, so a crafted file cannot run code."""
+
+    _ALLOWED = {
+        ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+        ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+        ("numpy", "ndarray"), ("numpy", "dtype"), ("collections", "OrderedDict"),
+        ("numpy.core.numeric", "_frombuffer"), ("numpy._core.numeric", "_frombuffer"),
+        ("_codecs", "encode"),  # protocol-2 pickles carry the array bytes as a latin-1 string re-encoded on load
+    }
+
+    def find_class(self, module, name):
+        if (module, name) in self._ALLOWED:
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError("checkpoint refers to %s.%s: only numpy arrays and plain containers are accepted"
+                                     % (module, name))
+
+
 def _load_any(path):
+    """reads a checkpoint file: a torch tensor pickle (weights_only) or a Paddle-style pickle of numpy arrays"""
     if path.startswith("http://") or path.startswith("https://"):
         raise RuntimeError("downloading pretrained weights is not supported offline; pass a local file: %s" % path)
     if os.path.isdir(path):
@@ -17,10 +37,11 @@ def _load_any(path):
     if not os.path.exists(path):
         raise ValueError("The pretrained model directory is not Found: {}".format(path))
     try:
-        return torch.load(path, map_location="cpu", weights_only=False)
-    except Exception:
+        return torch.load(path, map_location="cpu", weights_only=True)
+    except (pickle.UnpicklingError, RuntimeError, EOFError, ValueError, KeyError, AttributeError):
+        # not a torch zip / a pickle with numpy objects: the Paddle container (protocol-2 pickle of numpy arrays)
         with open(path, "rb") as fh:
-            return pickle.load(fh, encoding="latin1")
+            return _NumpyOnlyUnpickler(fh, encoding="latin1").load()
 
 
 def load_entire_model(model, pretrained):
@@ -46,18 +67,23 @@ def load_entire_model(model, pretrained):
     print("[INFO] There are {}/{} variables loaded into {}.".format(len(ok), len(own), model.__class__.__name__))
 
 
+def _to_numpy_tree(v):
+    if torch.is_tensor(v):
+        return v.detach().cpu().numpy()
+    if isinstance(v, dict):
+        return {k: _to_numpy_tree(x) for k, x in v.items()}
+    return v
+
+
 def save_checkpoint(model, optimizer, save_dir):
-    """core/train.py:230-236 layout: <dir>/model.pdparams + model.pdopt (torch pickles of plain tensors)."""
+    """core/train.py:230-236 layout: <dir>/model.pdparams + model.pdopt, both in the container `paddle.save` writes
+    (protocol-2 pickles of numpy arrays, parameter names = the reference's), so the reference's `paddle.load` +
+    `set_dict` reads a checkpoint trained here and `resume` / `pretrained=` read the reference's."""
     os.makedirs(save_dir, exist_ok=True)
-    torch.save({k: v.cpu() for k, v in model.state_dict().items()}, os.path.join(save_dir, "model.pdparams"))
+    export_pdparams(model, os.path.join(save_dir, "model.pdparams"))
     if optimizer is not None:
-        def to_cpu(v):
-            if torch.is_tensor(v):
-                return v.cpu()
-            if isinstance(v, dict):
-                return {k: to_cpu(x) for k, x in v.items()}
-            return v
-        torch.save({k: to_cpu(v) for k, v in optimizer.state_dict().items()}, os.path.join(save_dir, "model.pdopt"))
+        with open(os.path.join(save_dir, "model.pdopt"), "wb") as fh:
+            pickle.dump(_to_numpy_tree(optimizer.state_dict()), fh, protocol=2)
 
 
 def export_pdparams(model, path):
@@ -79,10 +105,11 @@ def resume(model, optimizer, resume_model):
     resume_model = os.path.normpath(resume_model)
     if not os.path.exists(resume_model):
         raise ValueError("Directory of the model needed to resume is not Found: {}".format(resume_model))
-    model.set_state_dict(torch.load(os.path.join(resume_model, "model.pdparams"), map_location="cpu"))
+    sd = _load_any(os.path.join(resume_model, "model.pdparams"))
+    sd.pop("StructuredToParameterName@@", None)
+    model.set_state_dict(sd)
     if optimizer is not None:
-        opt_sd = torch.load(os.path.join(resume_model, "model.pdopt"), map_location="cpu", weights_only=False)
-        optimizer.set_state_dict(opt_sd)
+        optimizer.set_state_dict(_load_any(os.path.join(resume_model, "model.pdopt")))
     return int(resume_model.split("_")[-1])
 
 
