@@ -457,12 +457,18 @@ def run_preprocess(args):
     from medicalseg_b200 import preprocess as P
     vol, lab = _pre_inputs(rank)
     h_vol, h_lab = torch.from_numpy(vol).pin_memory(), torch.from_numpy(lab).pin_memory()
-    d_vol, d_lab = h_vol.to(device), h_lab.to(device)
+    # L2 policy: a scan touches ~210 MB of its 1.07 GB (the sampled rows / planes), which would half-fit the 126 MB L2
+    # if the same buffers were re-read back to back -> rotate over 4 resident copies (840 MB touched between re-uses)
+    NCOPY = 4
+    d_vols = [h_vol.to(device) for _ in range(NCOPY)]
+    d_labs = [h_lab.to(device) for _ in range(NCOPY)]
     hu = ("hunorm", -1200, 600, -2000)
+    turn = {"i": 0}
 
     def scan_device():
-        a, _ = P.resample(d_vol, new_shape=[128, 128, 128], order=1, pre_op=hu)
-        b, _ = P.resample(d_lab, new_shape=[128, 128, 128], order=0)
+        i = turn["i"] = (turn["i"] + 1) % NCOPY
+        a, _ = P.resample(d_vols[i], new_shape=[128, 128, 128], order=1, pre_op=hu)
+        b, _ = P.resample(d_labs[i], new_shape=[128, 128, 128], order=0)
         return a, b
 
     def barrier():
@@ -493,15 +499,15 @@ def run_preprocess(args):
     ms_scan = float(t.item()) / (args.steps * reps)
 
     # kernel alone (roofline): fused HUnorm + order-1 gather of the image
-    for _ in range(3):
-        P.resample(d_vol, new_shape=[128, 128, 128], order=1, pre_op=hu)
+    for i in range(3):
+        P.resample(d_vols[i % NCOPY], new_shape=[128, 128, 128], order=1, pre_op=hu)
     torch.cuda.synchronize()
     e0.record()
-    for _ in range(50):
-        P.resample(d_vol, new_shape=[128, 128, 128], order=1, pre_op=hu)
+    for i in range(48):
+        P.resample(d_vols[i % NCOPY], new_shape=[128, 128, 128], order=1, pre_op=hu)
     e1.record()
     torch.cuda.synchronize()
-    k_ms = e0.elapsed_time(e1) / 50
+    k_ms = e0.elapsed_time(e1) / 48
 
     # ---- e2e: host-resident scans through the public pipeline (pinned inputs, H2D of scan i+1 overlapping the kernels
     # and the D2H of scan i), results land in pinned host memory
@@ -533,7 +539,7 @@ def run_preprocess(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_scan * reps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": PRE_WORKLOAD, "scans_per_step": reps, "parallelism": "by-volume x%d (no collective)" % world,
-                       "l2_policy": "source volume + label (1.07 GB) exceed the 126 MB L2"},
+                       "l2_policy": "4 resident scan copies used in rotation: 840 MB touched between re-uses of a buffer (L2 is 126 MB)"},
             "e2e": {"value": round(world * e2e_scans / e2e_s, 3), "unit": UNIT,
                     "h2d_bytes_per_step": int(h_vol.numel() * 4 + h_lab.numel() * 4),
                     "d2h_bytes_per_step": int(2 * 128 ** 3 * 4), "ms_per_scan": round(e2e_s / e2e_scans * 1e3, 3),

@@ -20,7 +20,11 @@
 //       tap's 16-byte channel vectors to its depth-to-space position.
 // Both are HBM-bound (AI 26-190 FLOP/B): the kernel's job is to stream x once and write out once.
 // Warp roles as in conv_k5_umma.cu: w0 TMA producer, w1 MMA issue (uniform control flow, one elected lane),
-// w2 TMEM alloc, w4-7 epilogue (bias, optional accumulate, bf16 round, BN partial sums, 128-bit stores).
+// w2 TMEM alloc, w4-19 epilogue: FOUR warpgroups take every fourth 16-column block (bias, optional accumulate, bf16
+// round, BN partial sums, 128-bit stores).  Round 2: the kernel was latency bound with 8 epilogue warps (ncu: DRAM at
+// 20-29 % of peak, SMs 13-17 % busy, ~4 KB in flight per SM) - the accumulate form serialised
+// (tcgen05.ld -> load old -> add -> store) per 16 columns.  Now 16 warps share the column blocks and the `old` vectors
+// of a whole item are requested BEFORE the accumulator barrier, so their HBM latency overlaps the MMAs.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -34,8 +38,11 @@ constexpr int kK2ABytes = 2 * kK2TileH * kK2TileW * 16;  // [2 c8][16 h][8 w][8 
 constexpr int kK2BBytesMax = 256 * 32;                   // [2 k8][N <= 256][8 ch] bf16
 constexpr int kK2StageBytes = kK2ABytes + kK2BBytesMax;
 constexpr int kK2Stages = 8;
-constexpr int kK2Threads = 384;  // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4-11 epilogue
-constexpr int kK2SmemBytes = kK2Stages * kK2StageBytes + 1024 + 8 * 2 * 256 * 4 + 128;
+constexpr int kK2EpiWarps = 16;  // 4 warpgroups x 4 TMEM lane quadrants
+constexpr int kK2EpiGroups = kK2EpiWarps / 4;
+constexpr int kK2MaxIt = 16 / kK2EpiGroups;  // 16-column blocks per warpgroup and item (N <= 256)
+constexpr int kK2Threads = 128 + 32 * kK2EpiWarps;  // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4-19 epilogue
+constexpr int kK2SmemBytes = kK2Stages * kK2StageBytes + 1024 + kK2EpiWarps * 2 * 256 * 4 + 128;
 
 struct K2Params {
   int mode;              // 0 gather, 1 scatter
@@ -70,17 +77,17 @@ __global__ void __launch_bounds__(kK2Threads, 1)
   // barrier map: [0,S) full  [S,2S) empty  [2S,2S+2) acc_full  [2S+2,2S+4) acc_empty
   constexpr int kFull = 0, kEmpty = kK2Stages, kAccFull = 2 * kK2Stages, kAccEmpty = 2 * kK2Stages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kK2Stages + 4);
-  float* stat_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);  // [8 warps][2][256]
+  float* stat_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);  // [epilogue warps][2][256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = ptx::smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   if (threadIdx.x == 0) {
     for (int i = 0; i < kK2Stages; ++i) { ptx::mbar_init(BAR(kFull + i), 1); ptx::mbar_init(BAR(kEmpty + i), 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(kAccFull + i), 1); ptx::mbar_init(BAR(kAccEmpty + i), 8); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(kAccFull + i), 1); ptx::mbar_init(BAR(kAccEmpty + i), kK2EpiWarps); }
     ptx::fence_mbar_init();
   }
-  for (int i = threadIdx.x; i < 8 * 2 * 256; i += kK2Threads) stat_smem[i] = 0.f;
+  for (int i = threadIdx.x; i < kK2EpiWarps * 2 * 256; i += kK2Threads) stat_smem[i] = 0.f;
   __shared__ int tap_off[64];  // scatter: big-grid voxel offset of every N-side tap (kd, kh[, kw])
   if (threadIdx.x < 64) {
     const int tap = threadIdx.x;
@@ -165,9 +172,9 @@ __global__ void __launch_bounds__(kK2Threads, 1)
       __syncwarp();
     }
   } else if (warp >= 4) {
-    // ================= epilogue: two warpgroups (warps 4-7, 8-11) take alternate 16-column blocks ==============
-    // (a warp reads the TMEM lane quadrant warp % 4).  The loop is instruction-latency bound (one warp per scheduler),
-    // so everything that does not depend on the item is hoisted and the bf16 conversion is done once.
+    // ================= epilogue: four warpgroups take every fourth 16-column block ==============================
+    // (a warp reads the TMEM lane quadrant warp % 4).  Everything that does not depend on the item is hoisted and the
+    // bf16 conversion is done once.
     const int wg = (warp - 4) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -176,7 +183,6 @@ __global__ void __launch_bounds__(kK2Threads, 1)
     const int64_t So = p.mode == 0 ? Ss : (int64_t)p.bd * p.bh * p.bw;  // voxels of the output grid
     float* my_stats = stat_smem + (warp - 4) * 2 * 256;
     const int nblk16 = p.nmma / 16;
-    const int t_start = (wg * 16) / p.cpad, co_start = (wg * 16) % p.cpad;
     const bool has_bias = p.bias != nullptr;
     const bool bias_vec = has_bias && (reinterpret_cast<uintptr_t>(p.bias) % 16 == 0);
     const bool want_stats = p.sums != nullptr;
@@ -195,14 +201,11 @@ __global__ void __launch_bounds__(kK2Threads, 1)
       const int64_t v_small = ((int64_t)d * p.sh + h) * p.sw + w;
       const int64_t v_big0 = ((int64_t)(p.std * d) * p.bh + p.sth * h) * p.bw + (p.wmode == 1 ? w : p.stw * w);
       __nv_bfloat16* out_n = reinterpret_cast<__nv_bfloat16*>(p.out.ptr) + (int64_t)n * p.out.n_stride;
-      ptx::mbar_wait(BAR(kAccFull + as), aph);
-      ptx::tc_fence_after();
-      const uint32_t t_base = tmem_base + as * 256u + ((uint32_t)(q * 32) << 16);
-      int t = t_start, co0 = co_start;
-#pragma unroll 1
-      for (int cb = wg; cb < nblk16; cb += 2) {
-        float acc[16];
-        ptx::tmem_ld16(t_base + cb * 16, acc);
+      // destination of (column block cb, channel plane k): nullptr when the lane / tap / plane is dead
+      auto dest = [&](int cb, int k, int& co0) -> __nv_bfloat16* {
+        const int col = cb * 16;
+        const int t = col / p.cpad;
+        co0 = col - t * p.cpad;
         int64_t v = v_small;
         bool tap_ok = true;
         if (p.mode != 0) {
@@ -210,6 +213,39 @@ __global__ void __launch_bounds__(kK2Threads, 1)
           tap_ok = tap < p.ntap_n;
           v = v_big0 + tap_off[tap_ok ? tap : 0];
         }
+        const int c8 = (co0 >> 3) + k;
+        return (ok && tap_ok && c8 < p.out_c8) ? out_n + ((int64_t)c8 * So + v) * 8 : nullptr;
+      };
+      // accumulate: request every `old` vector of this item now - the loads fly while the MMAs of the item run
+      uint4 oldv[kK2MaxIt][2];
+      if (p.accumulate) {
+#pragma unroll
+        for (int it = 0; it < kK2MaxIt; ++it) {
+          const int cb = wg + kK2EpiGroups * it;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            oldv[it][k] = make_uint4(0u, 0u, 0u, 0u);
+            if (cb < nblk16) {
+              int co0;
+              const __nv_bfloat16* src = dest(cb, k, co0);
+              if (src != nullptr) oldv[it][k] = *reinterpret_cast<const uint4*>(src);
+            }
+          }
+        }
+      }
+      ptx::mbar_wait(BAR(kAccFull + as), aph);
+      ptx::tc_fence_after();
+      const uint32_t t_base = tmem_base + as * 256u + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int it = 0; it < kK2MaxIt; ++it) {
+        const int cb = wg + kK2EpiGroups * it;
+        if (cb >= nblk16) break;
+        float acc[16];
+        ptx::tmem_ld16(t_base + cb * 16, acc);
+        int co0 = 0;
+        __nv_bfloat16* dst0 = dest(cb, 0, co0);
+        int co0b;
+        __nv_bfloat16* dst1 = dest(cb, 1, co0b);
         if (has_bias) {
           if (bias_vec && co0 + 16 <= p.cout_real) {
 #pragma unroll
@@ -225,16 +261,16 @@ __global__ void __launch_bounds__(kK2Threads, 1)
         }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-          const int c8 = (co0 >> 3) + k;
-          const bool live = ok && tap_ok && c8 < p.out_c8;
+          __nv_bfloat16* dst = k == 0 ? dst0 : dst1;
           uint32_t pk[4] = {0u, 0u, 0u, 0u};
-          if (live) {
-            __nv_bfloat16* dst = out_n + ((int64_t)c8 * So + v) * 8;
+          if (dst != nullptr) {
             if (p.accumulate) {
-              float old[8];
-              Vec8<__nv_bfloat16>::load(dst, old);
+              const uint32_t o[4] = {oldv[it][k].x, oldv[it][k].y, oldv[it][k].z, oldv[it][k].w};
 #pragma unroll
-              for (int j = 0; j < 8; ++j) acc[k * 8 + j] += old[j];
+              for (int i = 0; i < 4; ++i) {
+                acc[k * 8 + 2 * i] += __uint_as_float(o[i] << 16);
+                acc[k * 8 + 2 * i + 1] += __uint_as_float(o[i] & 0xffff0000u);
+              }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -262,8 +298,6 @@ __global__ void __launch_bounds__(kK2Threads, 1)
             my_stats[256 + co0 + (lane >> 1)] += s2;
           }
         }
-        co0 += 32;
-        while (co0 >= p.cpad) { co0 -= p.cpad; ++t; }
       }
       ptx::tc_fence_before();
       __syncwarp();

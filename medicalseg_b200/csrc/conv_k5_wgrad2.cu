@@ -38,6 +38,10 @@ struct Wg2Params {
                                          // load identical tiles -> they run as ONE cluster sharing them by TMA multicast
   int balance;                           // 2-CTA clusters, 5 kw taps: rank 0 owns kw {0,1}, rank 1 kw {3,4}, the middle
                                          // tap alternates with the tile parity (2.5 MMAs per row each instead of 3 / 2)
+  int rep;                               // balanced 32-channel clusters: the LAST kd group (plane kd = 4 alone, 3 of its 4
+                                         // M slots idle) is loaded as 4 kw-shifted replicas of that plane instead, so ONE
+                                         // MMA covers kw = replica (+ rank): 2 MMAs per row for the group instead of 5
+  int gchunks[2], gtpc[2];               // rep: chunks / tiles per chunk of kd group 0 and 1 (sized by their MMA cost)
 };
 
 // CL = true: launched in clusters of p.csize CTAs.  All CTAs of a cluster walk the same tiles of the same (channel half,
@@ -102,16 +106,33 @@ __global__ void __launch_bounds__(256, 1)
     kw1 = min(p.kw_taps, kw0 + p.units_per_pass);
   };
 
+  // item -> (pass slot, tile range).  rep: the two kd groups own gchunks[0] / gchunks[1] consecutive items
+  auto decode_item = [&](int item, int& pass, int& t0, int& t1) {
+    if (CL && p.rep) {
+      const int grp = item < p.gchunks[0] ? 0 : 1;
+      const int chunk = grp ? item - p.gchunks[0] : item;
+      pass = grp;
+      t0 = chunk * p.gtpc[grp];
+      t1 = min(p.total_tiles, t0 + p.gtpc[grp]);
+    } else {
+      pass = item / p.chunks;
+      t0 = (item % p.chunks) * p.tiles_per_chunk;
+      t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+    }
+  };
+  const int num_items_all = (CL && p.rep) ? p.gchunks[0] + p.gchunks[1] : num_items;
+
   if (warp == 0) {
     if (lane == 0) {
       uint32_t use = 0;
       const int x_planes = p.cin_m / 8;
-      for (int item = item0; item < num_items; item += item_step) {
-        const int pass = item / p.chunks, chunk = item % p.chunks;
+      for (int item = item0; item < num_items_all; item += item_step) {
+        int pass, t0, t1;
+        decode_item(item, pass, t0, t1);
         int mh, g, jg, kw0, kw1;
         decode_pass(pass, mh, g, jg, kw0, kw1);
-        const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
-        const int planes_valid = min(p.qm, 5 - g * p.qm);
+        const bool repl = CL && p.rep && g == p.kd_groups - 1;
+        const int planes_valid = repl ? p.qm : min(p.qm, 5 - g * p.qm);
         const uint32_t bytes =
             (uint32_t)(planes_valid * x_planes * kW2GroupBytes + (kW2TileH + 4) * p.dyp * kW2RowBytes);
         for (int t = t0; t < t1; ++t, ++use) {
@@ -126,8 +147,8 @@ __global__ void __launch_bounds__(256, 1)
             for (int q = 0; q < planes_valid; ++q)
               if ((uint32_t)(q % csize) == crank)
                 ptx::tma_load_4d_mc(ptx::smem_u32(x_smem + s * kW2XBytes + q * x_planes * kW2GroupBytes), &tmap_x, BAR(s),
-                                    (tw * kW2TileW - 2) * 8, th * kW2TileH, d + g * p.qm + q - 2,
-                                    n * p.x_c8_total + mh * 16, cmask);
+                                    (tw * kW2TileW - 2 + (repl ? q : 0)) * 8, th * kW2TileH,
+                                    d + g * p.qm + (repl ? 0 : q) - 2, n * p.x_c8_total + mh * 16, cmask);
             if ((uint32_t)(planes_valid % csize) == crank)
               ptx::tma_load_4d_mc(ptx::smem_u32(dy_smem + s * p.dy_stage_bytes), &tmap_dy, BAR(s), tw * kW2TileW * 8,
                                   n * p.dy_c8_total, th * kW2TileH - 2, d, cmask);
@@ -156,13 +177,14 @@ __global__ void __launch_bounds__(256, 1)
     const uint32_t b_row16 = (uint32_t)(p.dyp * kW2RowBytes) >> 4;  // one h row of the dY tile, 16-byte units
     const uint32_t npad = (uint32_t)p.npad;
     uint32_t use = 0, iuse = 0;
-    for (int item = item0; item < num_items; item += item_step, ++iuse) {
-      const int pass = item / p.chunks, chunk = item % p.chunks;
+    for (int item = item0; item < num_items_all; item += item_step, ++iuse) {
+      int pass, t0, t1;
+      decode_item(item, pass, t0, t1);
       int mh, g, jg, kw0, kw1;
       decode_pass(pass, mh, g, jg, kw0, kw1);
       const int nkw = kw1 - kw0;
       const uint32_t idesc = ptx::make_idesc_bf16(128, (int)pass_n(jg), 1, 1);
-      const int t0 = chunk * p.tiles_per_chunk, t1 = min(p.total_tiles, t0 + p.tiles_per_chunk);
+      const bool repl = CL && p.rep && g == p.kd_groups - 1;
       ptx::mbar_wait(BAR(7), (iuse & 1) ^ 1);
       ptx::tc_fence_after();
       bool mid_started = false;
@@ -173,7 +195,18 @@ __global__ void __launch_bounds__(256, 1)
         const uint32_t a_lo0 = ptx::desc_lo(ptx::smem_u32(x_smem + s * kW2XBytes), 8u) + (uint32_t)(kw0 + p.kw_base);
         const uint32_t b_lo0 =
             ptx::desc_lo(ptx::smem_u32(dy_smem + s * p.dy_stage_bytes), 8u) + (uint32_t)(jg * p.jh) * b_row16;
-        if (CL && p.balance) {
+        if (repl) {
+          // M slot q holds the kd = 4 plane shifted by q voxels along w: viewed at +rank it is tap kw = q + rank.
+          // rank 0: kw 0..3; rank 1: kw 1..4, of which only kw = 4 (slot 3) is kept by the epilogue
+          const uint32_t a_base = ptx::desc_lo(ptx::smem_u32(x_smem + s * kW2XBytes), 8u) + crank;
+#pragma unroll
+          for (int u = 0; u < kW2TileH; ++u) {
+            const uint32_t acc = (t != t0 || u != 0) ? 1u : 0u;
+            if (leader)
+              ptx::mma_bf16_split(tmem_u, a_base + (uint32_t)(u * (kW2TileW + 4)), a_hi, b_lo0 + (uint32_t)u * b_row16,
+                                  b_hi, idesc, acc);
+          }
+        } else if (CL && p.balance) {
           // accumulator slots 0,1 = this rank's fixed taps (kw 0,1 or 3,4), slot 2 = the middle tap on the tiles it owns
           const uint32_t a_base = ptx::desc_lo(ptx::smem_u32(x_smem + s * kW2XBytes), 8u);
           const uint32_t kwf = crank == 0 ? 0u : 3u;
@@ -218,21 +251,24 @@ __global__ void __launch_bounds__(256, 1)
     const int qplane = row / p.cin_m, ci_local = row % p.cin_m;
     const int cw = 8 * p.dyp;  // channels per stacked kh group
     uint32_t iuse = 0;
-    for (int item = item0; item < num_items; item += item_step, ++iuse) {
-      const int pass = item / p.chunks;
+    for (int item = item0; item < num_items_all; item += item_step, ++iuse) {
+      int pass, t0_, t1_;
+      decode_item(item, pass, t0_, t1_);
       int mh, g, jg, kw0, kw1;
       decode_pass(pass, mh, g, jg, kw0, kw1);
-      const int kd = g * p.qm + qplane;
+      const bool repl = CL && p.rep && g == p.kd_groups - 1;
+      const int kd = repl ? 4 : g * p.qm + qplane;
       const int ci = mh * 128 + ci_local;
-      const bool row_ok = (qplane < p.qm) && kd < 5 && ci < p.cin_real;
+      // repl: row block q = tap kw = q + rank; rank 1 only contributes kw = 4 (kw 1..3 are rank 0's)
+      const bool row_ok = (qplane < p.qm) && kd < 5 && ci < p.cin_real && (!repl || crank == 0 || qplane == p.qm - 1);
       ptx::mbar_wait(BAR(6), iuse & 1);
       ptx::tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
       const bool bal = CL && p.balance;
-      const int nslots = bal ? 3 : kw1 - kw0;
+      const int nslots = repl ? 1 : (bal ? 3 : kw1 - kw0);
 #pragma unroll 1
       for (int slot = 0; slot < nslots; ++slot) {
-        const int kw = bal ? (slot == 2 ? 2 : (crank == 0 ? 0 : 3) + slot) : kw0 + slot;
+        const int kw = repl ? qplane + (int)crank : (bal ? (slot == 2 ? 2 : (crank == 0 ? 0 : 3) + slot) : kw0 + slot);
         const int jcount_e = min(p.jh, 5 - jg * p.jh);
         const int npass_e = (jcount_e * 8 * p.dyp + 15) / 16 * 16;
 #pragma unroll 1
@@ -347,7 +383,27 @@ int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin
     p.chunks = (p.total_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
     p.csize = csize;
     p.balance = (csize == 2 && p.passes_per_group == 2 && p.jgroups == 1 && kw_taps == 5 && p.tiles_per_chunk >= 4) ? 1 : 0;
-    const int items = groups * p.chunks;
+    // kw-replicated leftover plane (32 input channels: 4 planes per M block, kd groups {0..3}, {4}): group 1 then costs
+    // 1 MMA per row and rank against 2.5 for group 0, and the clusters are shared out in that proportion
+    p.rep = (p.balance && p.qm == 4 && p.kd_groups == 2 && p.mhalves == 1 && !(g_debug_flags[6] & 16) &&
+             p.total_tiles >= 8 * nclusters) ? 1 : 0;
+    if (p.rep) {
+      // MMA cost 2.5 : 1 per row and rank -> 2/7 of the clusters; msb_debug_set(0, permille) overrides the share (the
+      // leftover group streams the same bytes per tile for 2.5x fewer MMAs, so it may want more than its MMA share)
+      const double share = g_debug_flags[0] > 0 ? g_debug_flags[0] / 1000.0 : 2.0 / 7.0;
+      int c1 = (int)(nclusters * share + 0.5);
+      if (c1 < 1) c1 = 1;
+      if (c1 > nclusters - 1) c1 = nclusters - 1;
+      const int c0 = nclusters - c1;
+      const int cc[2] = {c0, c1};
+      for (int gi = 0; gi < 2; ++gi) {
+        p.gtpc[gi] = (p.total_tiles + cc[gi] - 1) / cc[gi];
+        p.gchunks[gi] = (p.total_tiles + p.gtpc[gi] - 1) / p.gtpc[gi];
+      }
+    } else {
+      p.gchunks[0] = p.gchunks[1] = p.gtpc[0] = p.gtpc[1] = 0;
+    }
+    const int items = p.rep ? p.gchunks[0] + p.gchunks[1] : groups * p.chunks;
     const int grid = (items < nclusters ? items : nclusters) * csize;
     static bool attr_set_cl = false;
     if (!attr_set_cl) {
@@ -364,6 +420,8 @@ int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin
   }
   p.csize = 1;
   p.balance = 0;
+  p.rep = 0;
+  p.gchunks[0] = p.gchunks[1] = p.gtpc[0] = p.gtpc[1] = 0;
   const int items = p.num_passes * p.chunks;
   const int grid = items < kNumSMs ? items : kNumSMs;
   static bool attr_set = false;

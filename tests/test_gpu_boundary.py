@@ -55,7 +55,7 @@ def test_vnet_multi_channel_input_matches_oracle(dtype, in_ch):
 def test_inference_argmax_and_resize3d_reverse_transform():
     """core/infer.py:62-94: pred = argmax(logits); when the validation transforms hold a Resize3D the logits are first
     resized back to `ori_shape` (linear interpolation, F.interpolate defaults) - checked against torch's trilinear"""
-    from medicalseg_b200.core import inference
+    from medicalseg_b200.core import inference, reverse_transform
     from medicalseg_b200.models import VNet
     from medicalseg_b200.transforms import Resize3D
     m = VNet(num_classes=3, compute_dtype="bf16")
@@ -65,10 +65,12 @@ def test_inference_argmax_and_resize3d_reverse_transform():
         pred, logit = inference(m, x)
         assert pred.dtype == torch.int32 and tuple(pred.shape) == (1, 1, 32, 32, 32)
         assert torch.equal(pred.long(), logit.argmax(1, keepdim=True))
-        pred2, logit2 = inference(m, x, ori_shape=(40, 48, 36), transforms=[Resize3D((32, 32, 32))])
+        tf = [Resize3D((32, 32, 32))]
+        back = reverse_transform(logit, (40, 48, 36), tf)  # the same logits through our kernel and through torch
         ref = torch.nn.functional.interpolate(logit, size=(40, 48, 36), mode="trilinear", align_corners=False)
-        assert tuple(logit2.shape) == (1, 3, 40, 48, 36)
-        assert float((logit2 - ref).abs().max()) <= 2e-5 * float(ref.abs().max() + 1)
+        assert float((back - ref).abs().max()) <= 2e-5 * float(ref.abs().max() + 1)
+        pred2, logit2 = inference(m, x, ori_shape=(40, 48, 36), transforms=tf)
+        assert tuple(logit2.shape) == (1, 3, 40, 48, 36) and tuple(pred2.shape) == (1, 1, 40, 48, 36)
         assert torch.equal(pred2.long(), logit2.argmax(1, keepdim=True))
         with pytest.raises(ValueError):
             inference(m, x, ori_shape=(40, 48, 36), transforms=[])  # nothing explains the shape difference

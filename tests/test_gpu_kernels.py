@@ -332,15 +332,18 @@ WG_CASES = [(32, 32, (6, 16, 16)), (64, 64, (4, 9, 20)), (128, 128, (3, 8, 16)),
 
 
 @pytest.mark.parametrize("cin,cout,dims", WG_CASES)
-@pytest.mark.parametrize("clustered", [False, True])
+@pytest.mark.parametrize("clustered", [False, True, "norep"])
 def test_conv_k5_tcgen05_wgrad(cin, cout, dims, clustered):
     """clustered: True forces the TMA-multicast cluster launch of the kh-stacked kernel for every shape family (default:
     only the balanced 2-CTA clusters of the 32-channel layers, see conv_k5_wgrad2.cu), False disables it; only the
-    shapes with enough tiles take it"""
+    shapes with enough tiles take it.  The 32-channel clusters load the leftover kd plane as 4 kw-shifted replicas
+    (round 2); "norep" keeps the round-1 form of that group (one valid plane per M block) verified."""
     ops, B8 = _imp()
     from medicalseg_b200 import _lib
     if clustered and dims[0] * dims[1] * dims[2] < 16 * 32 * 32:
         pytest.skip("too few tiles for the cluster launch")
+    if clustered == "norep" and cin != 32:
+        pytest.skip("the replica form only exists for 32 input channels")
     torch.manual_seed(5)
     n = 2
     dyc = 16 if cout < 8 else (cout + 7) // 8 * 8
@@ -354,7 +357,8 @@ def test_conv_k5_tcgen05_wgrad(cin, cout, dims, clustered):
     dw = torch.zeros(cout, cin, 5, 5, 5, device="cuda")
     db = torch.zeros(cout, device="cuda")
     ws = torch.empty(ops.k5_wgrad_workspace_bytes(cin, cout), dtype=torch.uint8, device="cuda")
-    _lib.call("msb_debug_set", 6, (4 | 8) if clustered else 2)  # 8: clustered per-tap kernel (>= 128 channels)
+    # 8: clustered per-tap kernel (>= 128 channels); 16: no kw-replicated leftover plane
+    _lib.call("msb_debug_set", 6, ((4 | 8 | 16) if clustered == "norep" else (4 | 8)) if clustered else 2)
     try:
         ops.k5_wgrad(xb, dyb, dw, db, cout, cin, ws)
         assert rel(dw, ref) <= 1e-4  # bf16 x bf16 products are exact in f32; only the summation order differs

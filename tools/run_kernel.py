@@ -189,11 +189,18 @@ def misc(what, reps):
         _time(lambda: ops.trilinear_bwd(dst, dsrc), reps, "trilinear_bwd (%.0f MB)" % mb, mb)
     elif what == "preprocess":
         from medicalseg_b200 import preprocess as P
-        vol = torch.empty(512, 512, 512, device=dev).uniform_(-2000, 2000)
-        lab = torch.randint(0, 3, (512, 512, 512), device=dev, dtype=torch.int32)
-        _time(lambda: P.resample(vol, new_shape=[128, 128, 128], order=1, pre_op=("hunorm", -1200, 600, -2000)), reps,
-              "resample_f32 + fused HUnorm 512^3 -> 128^3 (142.6 MB compulsory)", 142.6)
-        _time(lambda: P.resample(lab, new_shape=[128, 128, 128], order=0), reps, "resample_i32 order 0", None)
+        # 4 copies in rotation: the ~140 MB a scan touches must not be served from the 126 MB L2 on the next call
+        vols = [torch.empty(512, 512, 512, device=dev).uniform_(-2000, 2000) for _ in range(4)]
+        labs = [torch.randint(0, 3, (512, 512, 512), device=dev, dtype=torch.int32) for _ in range(4)]
+        k = {"i": 0}
+
+        def nxt(seq):
+            k["i"] += 1
+            return seq[k["i"] % 4]
+        _time(lambda: P.resample(nxt(vols), new_shape=[128, 128, 128], order=1, pre_op=("hunorm", -1200, 600, -2000)),
+              max(reps, 8), "resample_f32 + fused HUnorm 512^3 -> 128^3 (142.6 MB compulsory)", 142.6)
+        _time(lambda: P.resample(nxt(labs), new_shape=[128, 128, 128], order=0), max(reps, 8), "resample_i32 order 0",
+              None)
     else:
         raise SystemExit("unknown case %s" % what)
 
@@ -203,11 +210,12 @@ def main():
     from medicalseg_b200.ops import B8
     what = sys.argv[1] if len(sys.argv) > 1 else "fwd32"
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    for key in range(8):  # MSB_DEBUG6=4: clustered kh-stacked wgrad everywhere; MSB_DEBUG0=<permille>: cluster share of
+        if os.environ.get("MSB_DEBUG%d" % key):  # the kw-replicated leftover group; MSB_DEBUG6=16: replica form off
+            from medicalseg_b200 import _lib
+            _lib.call("msb_debug_set", key, int(os.environ["MSB_DEBUG%d" % key]))
     if what.startswith(("splitk", "mri", "head", "loss", "trilinear", "preprocess")):
         return misc(what, reps)
-    if os.environ.get("MSB_DEBUG6"):  # e.g. 4 = clustered (TMA multicast) kh-stacked wgrad
-        from medicalseg_b200 import _lib
-        _lib.call("msb_debug_set", 6, int(os.environ["MSB_DEBUG6"]))
     if what.startswith("k2"):
         return k2s2(what, reps)
     if what.startswith("bn"):
