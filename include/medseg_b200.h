@@ -190,11 +190,11 @@ int msb_conv_k5_fwd(msb_tensor x, const void* packed, const float* bias, int cou
                     msb_dim3 dims, int accumulate, const float* ch_scale, int groups, double* sums, void* stream);
 /* Same op with a split-K path for SMALL volumes (fewer 128-voxel tiles than SMs; the 8^3 / 16^3 levels of VNet):
  * the reduction over the input channels is split across CTAs so that every SM streams only a slice of the 4-16 MB
- * weight set, partial f32 tiles are added into `workspace` with vector reductions and a finalize kernel applies
- * bias / accumulate / bf16 rounding / BN sums.  msb_conv_k5_fwd_workspace_bytes() returns 0 when the shape uses the
- * regular path (workspace may then be NULL).  CONTRACT: the workspace must be all-zero on entry and is all-zero
- * again when the call's kernels have run (the finalize kernel clears what it reads), so one zero-initialised buffer
- * serves every layer of a model without memsets. */
+ * weight set; every K slice stores its partial f32 tile into its OWN copy inside `workspace` ([slices][n][c8][S][8])
+ * and a finalize kernel adds the copies in slice order - bit-reproducible, no atomics - and applies bias / accumulate
+ * / bf16 rounding / BN sums.  msb_conv_k5_fwd_workspace_bytes() returns 0 when the shape uses the regular path
+ * (workspace may then be NULL).  The workspace is pure scratch: no initial contents required, contents undefined
+ * afterwards, one buffer may serve every layer of a model (calls are stream-ordered). */
 size_t msb_conv_k5_fwd_workspace_bytes(int n, int cout_view, msb_dim3 dims, int cin_view);
 int msb_conv_k5_fwd_ws(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,
                        msb_dim3 dims, int accumulate, const float* ch_scale, int groups, double* sums, void* workspace,

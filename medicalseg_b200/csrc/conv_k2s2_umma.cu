@@ -20,11 +20,12 @@
 //       tap's 16-byte channel vectors to its depth-to-space position.
 // Both are HBM-bound (AI 26-190 FLOP/B): the kernel's job is to stream x once and write out once.
 // Warp roles as in conv_k5_umma.cu: w0 TMA producer, w1 MMA issue (uniform control flow, one elected lane),
-// w2 TMEM alloc, w4-19 epilogue: FOUR warpgroups take every fourth 16-column block (bias, optional accumulate, bf16
-// round, BN partial sums, 128-bit stores).  Round 2: the kernel was latency bound with 8 epilogue warps (ncu: DRAM at
-// 20-29 % of peak, SMs 13-17 % busy, ~4 KB in flight per SM) - the accumulate form serialised
-// (tcgen05.ld -> load old -> add -> store) per 16 columns.  Now 16 warps share the column blocks and the `old` vectors
-// of a whole item are requested BEFORE the accumulator barrier, so their HBM latency overlaps the MMAs.
+// w2 TMEM alloc, w4-11 epilogue: two warpgroups take alternate 16-column blocks (bias, optional accumulate, bf16
+// round, BN partial sums, 128-bit stores).  Round 2: the accumulate form serialised (tcgen05.ld -> load old -> add ->
+// store) per 16 columns with ~4 KB in flight per SM (ncu: DRAM at 20 % of peak); the `old` vectors of a whole item are
+// now requested BEFORE the accumulator barrier, so their HBM latency overlaps the MMAs: 190 -> 100 us for the
+// down_tr32 input gradient.  MEASURED negative result: 16 epilogue warps instead of 8 made the store-only forms slower
+// (scatter 55 -> 63 us, gather 73 -> 94 us: the extra warps spin on the accumulator barrier and take issue slots).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -38,10 +39,10 @@ constexpr int kK2ABytes = 2 * kK2TileH * kK2TileW * 16;  // [2 c8][16 h][8 w][8 
 constexpr int kK2BBytesMax = 256 * 32;                   // [2 k8][N <= 256][8 ch] bf16
 constexpr int kK2StageBytes = kK2ABytes + kK2BBytesMax;
 constexpr int kK2Stages = 8;
-constexpr int kK2EpiWarps = 16;  // 4 warpgroups x 4 TMEM lane quadrants
+constexpr int kK2EpiWarps = 8;   // 2 warpgroups x 4 TMEM lane quadrants
 constexpr int kK2EpiGroups = kK2EpiWarps / 4;
 constexpr int kK2MaxIt = 16 / kK2EpiGroups;  // 16-column blocks per warpgroup and item (N <= 256)
-constexpr int kK2Threads = 128 + 32 * kK2EpiWarps;  // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4-19 epilogue
+constexpr int kK2Threads = 128 + 32 * kK2EpiWarps;  // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4-11 epilogue
 constexpr int kK2SmemBytes = kK2Stages * kK2StageBytes + 1024 + kK2EpiWarps * 2 * 256 * 4 + 128;
 
 struct K2Params {
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(kK2Threads, 1)
       __syncwarp();
     }
   } else if (warp >= 4) {
-    // ================= epilogue: four warpgroups take every fourth 16-column block ==============================
+    // ================= epilogue: the warpgroups take alternate 16-column blocks ================================
     // (a warp reads the TMEM lane quadrant warp % 4).  Everything that does not depend on the item is hoisted and the
     // bf16 conversion is done once.
     const int wg = (warp - 4) >> 2;

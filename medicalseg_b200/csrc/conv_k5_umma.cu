@@ -107,7 +107,9 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // SPLITK: small volumes (fewer tiles than SMs).  The reduction over the input channels is split across CTAs (item =
 // (tile, slice of 16-channel chunks)): every CTA streams only ITS slice of the weight set (the layer is otherwise
 // bound by pulling the whole 4-16 MB weight set through every SM) and adds its f32 partial tile into p.ws with vector
-// reductions; splitk_finalize_kernel applies bias / accumulate / rounding / BN sums and re-zeroes the workspace.
+// stores into the slice's PRIVATE copy of the output (ws = [ksplit][n][c8][S][8] f32); splitk_finalize_kernel adds the
+// copies in slice order (deterministic - round 1 met in one copy through red.global atomics) and applies bias /
+// accumulate / rounding / BN sums.
 constexpr int kFwdThreads = 384;  // w0 halo TMA, w1 MMA, w2 TMEM alloc + weight TMA, w3 idle, w4-11 epilogue
 
 template <int NPAD, int TD, int J, int ACC_SETS, int NS, bool SPLITK = false>
@@ -325,9 +327,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
           for (int k = 0; k < 2; ++k) {
             const int c8 = cb * 2 + k;
             if (c8 < p.out_c8 && ok) {
-              float* dst = p.ws + (((int64_t)n * p.out_c8 + c8) * S + v) * 8;
-              red_add_v4(dst, acc[k * 8 + 0], acc[k * 8 + 1], acc[k * 8 + 2], acc[k * 8 + 3]);
-              red_add_v4(dst + 4, acc[k * 8 + 4], acc[k * 8 + 5], acc[k * 8 + 6], acc[k * 8 + 7]);
+              // every K slice owns a private copy of the output tile: plain stores, no atomics -> the finalize kernel
+              // adds the slices in a FIXED order and the result is bit-reproducible
+              float* dst = p.ws + ((((int64_t)(item % kdiv) * p.n + n) * p.out_c8 + c8) * S + v) * 8;
+              *reinterpret_cast<float4*>(dst) = make_float4(acc[k * 8 + 0], acc[k * 8 + 1], acc[k * 8 + 2], acc[k * 8 + 3]);
+              *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[k * 8 + 4], acc[k * 8 + 5], acc[k * 8 + 6], acc[k * 8 + 7]);
             }
           }
         } else {
@@ -474,10 +478,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
   }
 }
 
-// split-K tail: out = round_T(ws + bias [* ch_scale + out]), BN partial sums of the rounded values, ws <- 0
+// split-K tail: out = round_T(sum_slices ws[slice] + bias [* ch_scale + out]), BN partial sums of the rounded values
 // (T = bf16, or f32 for the three-pass fp32 engine where each pass accumulates into the f32 output)
 template <typename T>
-__global__ void __launch_bounds__(256) splitk_finalize_kernel(float* __restrict__ ws, const float* __restrict__ bias,
+__global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __restrict__ ws, int ksplit,
+                                                              const float* __restrict__ bias,
                                                               int cout_real, msb_tensor out, int64_t s, int accumulate,
                                                               const float* __restrict__ ch_scale, int groups,
                                                               double* __restrict__ sums, int sums_c,
@@ -500,12 +505,17 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(float* __restrict_
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  float* wp = ws + ((int64_t)n * out_c8 + c8) * s * 8;
+  const float* wp = ws + ((int64_t)n * out_c8 + c8) * s * 8;
+  const int64_t slice_stride = (int64_t)gridDim.z * out_c8 * s * 8;
   for (int64_t v = v0 + threadIdx.x; v < v1; v += 256) {
     float o[8];
     Vec8<float>::load(wp + v * 8, o);
-    *reinterpret_cast<float4*>(wp + v * 8) = make_float4(0.f, 0.f, 0.f, 0.f);
-    *reinterpret_cast<float4*>(wp + v * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ks = 1; ks < ksplit; ++ks) {  // fixed order: slice 0 + slice 1 + ...
+      float t[8];
+      Vec8<float>::load(wp + ks * slice_stride + v * 8, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += t[j];
+    }
     T* dst = view_ptr<T>(out, n, c8, s, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] += b[j];
@@ -1179,11 +1189,11 @@ static int launch_fwd_splitk(const msb_tensor& x, msb_dim3 dims, FwdParams& p, i
   const int64_t S = (int64_t)p.d * p.h * p.w;
   const dim3 fgrid((unsigned)((S + 2047) / 2048), (unsigned)p.out_c8, (unsigned)p.n);
   if (p.out_f32) {
-    MSB_LAUNCH_PDL(splitk_finalize_kernel<float>, fgrid, dim3(256), 0, st, p.ws, bias, p.cout_real, p.out, S,
+    MSB_LAUNCH_PDL(splitk_finalize_kernel<float>, fgrid, dim3(256), 0, st, p.ws, ksplit, bias, p.cout_real, p.out, S,
                    p.accumulate, p.ch_scale, p.groups, p.sums, p.sums_c, p.ep_scale, p.ep_shift, p.ep_alpha, p.ep_alpha2,
                    p.ep_res, p.ep_has_res);
   } else {
-    MSB_LAUNCH_PDL(splitk_finalize_kernel<__nv_bfloat16>, fgrid, dim3(256), 0, st, p.ws, bias, p.cout_real, p.out, S,
+    MSB_LAUNCH_PDL(splitk_finalize_kernel<__nv_bfloat16>, fgrid, dim3(256), 0, st, p.ws, ksplit, bias, p.cout_real, p.out, S,
                    p.accumulate, p.ch_scale, p.groups, p.sums, p.sums_c, p.ep_scale, p.ep_shift, p.ep_alpha, p.ep_alpha2,
                    p.ep_res, p.ep_has_res);
   }
@@ -1378,7 +1388,7 @@ static int conv_k5_fwd_impl(const char* who, msb_tensor x, const void* packed, c
   if (workspace != nullptr && kw_taps == 5 && (g_debug_flags[6] & 1) == 0) {
     const int ks = splitk_slices(npad_sel, n, dims, x.c);
     if (ks > 0) {
-      const size_t need = (size_t)n * out.c * S * sizeof(float);
+      const size_t need = (size_t)ks * n * out.c * S * sizeof(float);
       MSB_REQUIRE(workspace_bytes >= need && reinterpret_cast<uintptr_t>(workspace) % 16 == 0,
                   "%s: split-K workspace too small or misaligned (%zu < %zu)", who, workspace_bytes, need);
       p.ws = reinterpret_cast<float*>(workspace);
@@ -1418,8 +1428,9 @@ int msb_conv_k5_fwd(msb_tensor x, const void* packed, const float* bias, int cou
 
 size_t msb_conv_k5_fwd_workspace_bytes(int n, int cout_view, msb_dim3 dims, int cin_view) {
   const int npad = msb_conv_k5_out_pad(cout_view);
-  if (splitk_slices(npad, n, dims, cin_view) == 0) return 0;
-  return (size_t)n * cout_view * dims.d * dims.h * dims.w * sizeof(float);
+  const int ks = splitk_slices(npad, n, dims, cin_view);
+  if (ks == 0) return 0;
+  return (size_t)ks * n * cout_view * dims.d * dims.h * dims.w * sizeof(float);  // one private copy per K slice
 }
 
 int msb_conv_k5_fwd_ws(msb_tensor x, const void* packed, const float* bias, int cout, msb_tensor out, int n,

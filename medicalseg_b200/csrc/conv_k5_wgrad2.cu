@@ -386,11 +386,14 @@ int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin
     // kw-replicated leftover plane (32 input channels: 4 planes per M block, kd groups {0..3}, {4}): group 1 then costs
     // 1 MMA per row and rank against 2.5 for group 0, and the clusters are shared out in that proportion
     p.rep = (p.balance && p.qm == 4 && p.kd_groups == 2 && p.mhalves == 1 && !(g_debug_flags[6] & 16) &&
-             p.total_tiles >= 8 * nclusters) ? 1 : 0;
+             p.total_tiles >= 16384) ? 1 : 0;
     if (p.rep) {
-      // MMA cost 2.5 : 1 per row and rank -> 2/7 of the clusters; msb_debug_set(0, permille) overrides the share (the
-      // leftover group streams the same bytes per tile for 2.5x fewer MMAs, so it may want more than its MMA share)
-      const double share = g_debug_flags[0] > 0 ? g_debug_flags[0] / 1000.0 : 2.0 / 7.0;
+      // MMA cost 2.5 : 1 per row and rank would give the leftover group 2/7 of the clusters, but it streams the same
+      // bytes per tile for 2.5x fewer MMAs and is bound by the L2 -> SM delivery instead.  MEASURED (B200, 32 -> 32
+      // @128^3, batch 2): share 0.23 -> 1.74 ms, 2/7 -> 1.44, 0.35 -> 1.19, 0.42 -> 1.01 ms (round-1 form: 1.10 ms);
+      // the two groups balance near 0.43.  At 64^3 the replica form is slower (0.198 vs 0.172 ms) -> large volumes only.
+      // msb_debug_set(0, permille) overrides the share.
+      const double share = g_debug_flags[0] > 0 ? g_debug_flags[0] / 1000.0 : 0.43;
       int c1 = (int)(nclusters * share + 0.5);
       if (c1 < 1) c1 = 1;
       if (c1 > nclusters - 1) c1 = nclusters - 1;

@@ -139,6 +139,8 @@ class BatchLoader:
         import queue
         import threading
         self.dataset, self.device = dataset, torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.num_workers = max(int(num_workers), 0)
         self._it = iter(batches)
         self._seq = itertools.count()

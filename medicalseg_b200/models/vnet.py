@@ -841,13 +841,13 @@ class VNet(_Module):
             ops.conv_strided_wgrad(big, small, dw, dbias, kernel, stride, (0, 0, 0), bias_from_big)
 
     def splitk_workspace(self, n, cout_view, dims, cin_view):
-        """zero-initialised scratch for the split-K 5x5x5 conv on small volumes (None when the shape does not use it);
-        every call leaves it all-zero again, so it is allocated and cleared once"""
+        """scratch for the split-K 5x5x5 conv on small volumes (None when the shape does not use it): one private
+        partial-sum copy per K slice, no initial contents required"""
         need = ops.k5_fwd_workspace_bytes(n, cout_view, dims, cin_view)
         if need == 0:
             return None
         if self._sk_ws is None or self._sk_ws.numel() < need:
-            self._sk_ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
+            self._sk_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._sk_ws
 
     def split_hi_lo(self, x: B8):

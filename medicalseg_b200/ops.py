@@ -229,8 +229,8 @@ def k5_pack(w, packed, cout, cin, mode, cin_pad, cout_pad):
 
 def k5_fwd(x: B8, packed, bias, cout, out: B8, accumulate=False, ch_scale=None, groups=1, sums=None,
            workspace: Optional[torch.Tensor] = None):
-    """workspace: zero-initialised scratch of >= k5_fwd_workspace_bytes(...) bytes enables the split-K path on small
-    volumes (left all-zero again by the call); None = regular path only"""
+    """workspace: scratch of >= k5_fwd_workspace_bytes(...) bytes enables the split-K path on small volumes (one private
+    partial-sum copy per K slice, summed in fixed order: deterministic); None = regular path only"""
     if workspace is None:
         call("msb_conv_k5_fwd", x.mt, _ptr(packed), _ptr(bias), cout, out.mt, x.n, dim3(x.dims), int(accumulate),
              _ptr(ch_scale), groups, _ptr(sums), _stream())

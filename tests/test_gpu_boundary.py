@@ -175,8 +175,12 @@ def test_train_checkpoints_use_the_paddle_container_and_resume(tmp_path):
     m2 = VNet(num_classes=2, compute_dtype="bf16", seed=2)
     opt2 = Momentum(PolynomialDecay(0.01, 100), m2.parameters(), 0.9, 1e-4)
     assert resume(m2, opt2, d) == 7
-    assert torch.equal(m.store.flat, m2.store.flat) and torch.equal(m.store.buffers, m2.store.buffers)
-    assert torch.equal(opt.velocity, opt2.velocity) and opt2._learning_rate.last_epoch == 7
+    for name in m.store.slots:
+        assert torch.equal(m.store.view(name), m2.store.view(name)), name
+    for name, slot in m.store.slots.items():  # (the flat buffers also hold alignment padding that is not saved)
+        if not slot.is_buffer:
+            assert torch.equal(m.store.view_of(opt.velocity, name), m2.store.view_of(opt2.velocity, name)), name
+    assert opt2._learning_rate.last_epoch == 7
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")

@@ -82,11 +82,28 @@ def test_vnet128_bf16_train_step_matches_oracle_at_benchmark_shape():
     dmean = abs(float(np.mean(dice)) - float(np.mean(odice)))
     ce_rel = abs(float(ll[0]) - float(oll[0])) / abs(float(oll[0]))
     cos = _cosines(om, m)
-    # running statistics after the step (Paddle convention: biased variance, momentum 0.9)
-    bdiff = max(float((m.store.view(n).cpu() - b).abs().max() / (b.abs().max() + 1e-6)) for n, b in om.named_buffers())
+    # running statistics after the step (Paddle convention: biased variance, momentum 0.9): the running mean moved by
+    # 0.1 * batch mean - compare that step against the batch standard deviation of the same channel (a mean that is
+    # tiny relative to its channel's spread carries no information in its relative error); variances relatively
+    buf = dict(om.named_buffers())
+    worst_mean, worst_var, worst = 0.0, 0.0, {}
+    for name, b in buf.items():
+        ours_b = m.store.view(name).cpu()
+        if name.endswith("_mean"):
+            var = buf[name.replace("_mean", "_variance")]
+            batch_std = torch.sqrt(((var - 0.9) / 0.1).clamp_min(1e-12))  # running var = 0.9 * 1 + 0.1 * batch var
+            e = float(((ours_b - b).abs() / (0.1 * batch_std)).max())
+            if e > worst_mean:
+                worst_mean, worst["mean"] = e, name
+        else:
+            e = float(((ours_b - b).abs() / (b - 0.9).abs().clamp_min(1e-6)).max())
+            if e > worst_var:
+                worst_var, worst["var"] = e, name
+    bdiff = max(worst_mean, worst_var)
     pred_agree = float((lg.argmax(1) == ol.argmax(1)).float().mean())
     _record("vnet128_bf16_train_step", {"logits_rel_rms": rms, "dice_max_abs_err": ddice, "mean_dice_abs_err": dmean,
-                                        "ce_rel_err": ce_rel, "wgrad_cosine": cos, "running_stat_rel_err": bdiff,
+                                        "ce_rel_err": ce_rel, "wgrad_cosine": cos, "running_mean_err_over_batch_std": worst_mean, "running_var_step_rel_err": worst_var,
+                                        "worst_running_stat": worst,
                                         "argmax_agreement": pred_agree, "oracle_cpu_seconds": round(t_cpu, 1),
                                         "loss": [float(x) for x in ll], "oracle_loss": [float(x) for x in oll]})
     print("128^3 bf16 step vs oracle: logits rel-RMS %.3g, |dDice| %.3g, CE rel %.3g, min cos %.5f (%s), oracle %.1f s"
@@ -94,7 +111,7 @@ def test_vnet128_bf16_train_step_matches_oracle_at_benchmark_shape():
     assert rms <= 2e-2, rms                       # bf16 logits relative RMS
     assert ddice <= 1e-3 and dmean <= 1e-3        # BASELINE: Dice within 1e-3 of the reference
     assert ce_rel <= 1e-2, ce_rel
-    assert bdiff <= 2e-2, bdiff
+    assert worst_mean <= 2e-2 and worst_var <= 3e-2, (worst_mean, worst_var, worst)
     assert pred_agree >= 0.99, pred_agree
     # the dominant layer's weight gradient (clustered kh-stacked kernel at 128^3) and the head
     assert cos["up_tr32.ops.0.conv1.weight"] >= 0.997, cos
@@ -149,13 +166,17 @@ def test_vnet_mri_512x512x12_eval_forward_and_fused_head_match_oracle():
     worst_margin = float(margin[bad].max()) if bool(bad.any()) else 0.0
     ddice = float(np.abs(np.asarray(dice) - np.asarray(odice)).max())
     ce_rel = abs(float(ll[0]) - float(oll[0])) / abs(float(oll[0]))
-    assert bool((pred.cpu()[:, 0].long() == logits.argmax(1)).all())  # fused head == argmax of our own logits
+    # fused head (a second forward pass) vs the argmax of the first pass's logits: every kernel on the path is
+    # deterministic, so the two agree exactly
+    self_agree = float((pred.cpu()[:, 0].long() == logits.argmax(1)).float().mean())
     _record("vnet_mri_512x512x12_eval", {"logits_rel_rms": rms, "argmax_agreement": agree, "dice_max_abs_err": ddice,
+                                         "fused_head_vs_own_argmax": self_agree,
                                          "ce_rel_err": ce_rel, "worst_disagreeing_margin": worst_margin,
                                          "logit_abs_max": float(ologits.abs().max()), "oracle_cpu_seconds": round(t_cpu, 1)})
     print("MRI 512x512x12 eval vs oracle: logits rel-RMS %.3g, argmax agreement %.5f, |dDice| %.3g, CE rel %.3g, "
           "oracle %.1f s" % (rms, agree, ddice, ce_rel, t_cpu))
     assert rms <= 2e-2, rms
+    assert self_agree == 1.0, self_agree
     assert agree >= 0.98, agree
     assert worst_margin <= 0.1 * float(ologits.abs().max()), worst_margin
     assert ddice <= 1e-3, ddice

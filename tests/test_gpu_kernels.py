@@ -239,13 +239,14 @@ SPLITK_CASES = [(256, 256, (8, 8, 8)), (256, 256, (16, 16, 16)), (128, 128, (16,
 @pytest.mark.parametrize("cin,cout,dims", SPLITK_CASES)
 def test_conv_k5_split_k_small_volumes(cin, cout, dims):
     """split-K path (msb_conv_k5_fwd_ws) on the small deep-level volumes: forward + BN sums, then the input-gradient
-    form with accumulate + channel scale; the workspace must come back all-zero (header contract)."""
+    form with accumulate + channel scale.  The workspace is pure scratch (filled with garbage here) and the result is
+    bit-reproducible: every K slice owns a private partial-sum copy that the finalize kernel adds in slice order."""
     ops, B8 = _imp()
     torch.manual_seed(11)
     n = 2
     need = ops.k5_fwd_workspace_bytes(n, cout, dims, cin)
     assert need > 0, "shape is expected to take the split-K path"
-    ws = torch.zeros(need, dtype=torch.uint8, device="cuda")
+    ws = torch.full((need,), 0x7f, dtype=torch.uint8, device="cuda")  # NaN bit patterns: nothing may be read unwritten
     x = torch.randn(n, cin, *dims, device="cuda")
     w = torch.randn(cout, cin, 5, 5, 5, device="cuda") * (2.0 / (cin * 125)) ** 0.5
     b = torch.randn(cout, device="cuda")
@@ -259,7 +260,10 @@ def test_conv_k5_split_k_small_volumes(cin, cout, dims):
     ops.k5_fwd(xb, packed, b, cout, out, False, None, 1, sums, ws)
     o = out.to_ncdhw(cout)
     assert rel(o, ref) <= BF16_TOL
-    assert int(ws.count_nonzero()) == 0
+    for _ in range(3):  # deterministic: repeated calls give identical bits
+        out_r = B8(n, cout, dims, torch.bfloat16, device="cuda", zero=True)
+        ops.k5_fwd(xb, packed, b, cout, out_r, False, None, 1, None, ws)
+        assert torch.equal(out_r.buf, out.buf)
     s_ref = o.double().sum((0, 2, 3, 4))
     assert float((sums[:cout] - s_ref).abs().max()) <= 1e-3 * float(s_ref.abs().max() + 1)
     q_ref = (o.double() ** 2).sum((0, 2, 3, 4))
@@ -278,10 +282,9 @@ def test_conv_k5_split_k_small_volumes(cin, cout, dims):
     base = dx.to_ncdhw()
     scale = (torch.rand(n, cin, device="cuda") > 0.5).float() * 2
     need_b = ops.k5_fwd_workspace_bytes(n, cin, dims, cout)
-    wsb = torch.zeros(max(need_b, 16), dtype=torch.uint8, device="cuda")
+    wsb = torch.full((max(need_b, 16),), 0x7f, dtype=torch.uint8, device="cuda")
     ops.k5_fwd(dyb, packed_b, None, cin, dx, True, scale, 1, None, wsb if need_b else None)
     assert rel(dx.to_ncdhw(), base + refd * scale.view(n, cin, 1, 1, 1)) <= BF16_TOL
-    assert int(wsb.count_nonzero()) == 0
 
 
 @pytest.mark.parametrize("cin,cout,dims,res", [(32, 32, (9, 20, 24), True), (64, 64, (5, 16, 16), False),
@@ -318,8 +321,6 @@ def test_conv_k5_evaluation_epilogue(cin, cout, dims, res):
     if cp > cout:  # padded output channels: zero weights and bias -> prelu(shift) (the model pads shift with 0)
         pad_ref = torch.where(shift[cout:] > 0, shift[cout:], shift[cout:] * a1[cout:]).bfloat16().float()
         assert torch.equal(out.to_ncdhw(cp)[:, cout:], pad_ref.view(1, -1, 1, 1, 1).expand(n, -1, *dims))
-    if ws is not None:
-        assert int(ws.count_nonzero()) == 0
     with pytest.raises(Exception, match="alpha2"):
         ops.k5_fwd_act(xb, packed, b, cout, out, scale, shift, a1, out, None, ws)
 
