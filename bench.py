@@ -169,7 +169,7 @@ def run_vnet(args, cfg):
     model = VNet(num_classes=classes, compute_dtype=cfg["dtype"], seed=0, sync_bn=bool(args.sync_bn), **cfg["model_kw"])
     model.train()
     losses = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1])], "coef": [1]}
-    reducer = DistributedGradReducer(model.store.grad).attach(model)
+    reducer = DistributedGradReducer(model.store.grad, bucket_mb=args.bucket_mb).attach(model)
     opt = Momentum(PolynomialDecay(cfg["lr"], 15000), model.parameters(), 0.9, 1e-4, grad_scale=reducer.grad_scale)
     img, lab = synthetic_gpu_batch(cfg, device, seed=rank)
     orig_call = _lib.call
@@ -604,6 +604,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
     ap.add_argument("--sync-bn", action="store_true", help="SyncBatchNorm over all ranks (reference default at N>1)")
+    ap.add_argument("--bucket-mb", type=float, default=32.0, help="gradient all-reduce bucket size (N>1)")
     ap.add_argument("--check", action="store_true", help="N>=2: data-parallel equivalence checks instead of timing")
     args = ap.parse_args()
     if args.config == "preprocess":

@@ -60,16 +60,16 @@ def test_vnet128_bf16_train_step_matches_oracle_at_benchmark_shape():
     om.train()
     img, lab = vo.synthetic_batch(2, (128, 128, 128), 2, seed=0)
     masks = vo.make_dropout_masks(2, seed=0)
+    m = VNet(num_classes=2, compute_dtype="bf16")
+    m.set_state_dict(om.state_dict())  # BEFORE the oracle's step: its train-mode forward moves the running statistics
+    m.train()
+    m.set_dropout_masks(masks)
     t0 = time.time()
     ologits = om(img, masks)[0]
     oll, odice = vo.loss_computation([ologits], lab, vo.default_losses())
     sum(oll).backward()
     t_cpu = time.time() - t0
 
-    m = VNet(num_classes=2, compute_dtype="bf16")
-    m.set_state_dict(om.state_dict())
-    m.train()
-    m.set_dropout_masks(masks)
     ours = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1])], "coef": [1]}
     logits = m(img.cuda())[0]
     ll, dice = L.loss_computation([logits], lab.cuda(), ours)

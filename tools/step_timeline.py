@@ -1,7 +1,10 @@
 """GPU timeline of the bench train step via torch.profiler (CUPTI): per-kernel device time inside real steps
 (warm caches, real overlap) plus the idle gaps between kernels - complements the serialized ncu launch list.
 
-    python tools/step_timeline.py [steps]        # prints a per-kernel table for the traced steps
+    python tools/step_timeline.py [steps] [mode] # prints a per-kernel table for the traced steps
+    torchrun --nproc-per-node N tools/step_timeline.py 3   # data-parallel (eager launches): adds the NCCL report - every
+                                                           # all-reduce kernel with its start offset / duration and
+                                                           # the time the optimizer waited after the last backward kernel
 """
 import collections
 import os
@@ -21,23 +24,31 @@ def main():
     evaluate = mode in ("eval", "evalmri")  # one evaluate() step: eval-mode forward + fused head (core/val.py:101-118)
     cdt = "f32x3" if len(sys.argv) > 2 and sys.argv[2] == "f32x3" else "bf16"  # BASELINE configs[2]
     import bench
+    import torch.distributed as dist
     from medicalseg_b200.models import VNet, VNetDeepSup, losses as L
     from medicalseg_b200.optimizer import Momentum, PolynomialDecay
+    from medicalseg_b200.parallel import DistributedGradReducer
 
-    device = torch.device("cuda", 0)
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    cfg128 = bench.CONFIGS["vnet128_bf16"]
     if mri:
         model = (VNetDeepSup if mode == "deepsup" else VNet)(num_classes=20, compute_dtype="bf16", seed=0,
                      kernel_size=[[2, 2, 4], [2, 2, 2], [2, 2, 2], [2, 2, 2]],
                      stride_size=[[2, 2, 1], [2, 2, 1], [2, 2, 2], [2, 2, 2]])
     else:
-        model = VNet(num_classes=bench.NUM_CLASSES, compute_dtype=cdt, seed=0)
+        model = VNet(num_classes=cfg128["classes"], compute_dtype=cdt, seed=0)
     model.train()
     losses = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1])], "coef": [1]}
     if mode == "deepsup":  # vnetdeepsup_mri_spine_seg_512_512_12_15k.yml: four MixedLoss objects x 0.25
         losses = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1]) for _ in range(4)],
                   "coef": [0.25] * 4}
-    opt = Momentum(PolynomialDecay(0.001, 15000), model.parameters(), 0.9, 1e-4)
-    img, lab = bench.synthetic_gpu_batch(device, seed=0)
+    reducer = DistributedGradReducer(model.store.grad, bucket_mb=float(os.environ.get("MSB_BUCKET_MB", "32"))).attach(model)
+    opt = Momentum(PolynomialDecay(0.001, 15000), model.parameters(), 0.9, 1e-4, grad_scale=reducer.grad_scale)
+    img, lab = bench.synthetic_gpu_batch(cfg128, device, seed=rank)
     if mri:
         img = torch.rand(2, 1, 512, 512, 12, device=device)
         lab = torch.randint(0, 20, (2, 512, 512, 12), device=device, dtype=torch.int32)
@@ -47,6 +58,7 @@ def main():
         loss_list, dice = L.loss_computation(logits_list, lab, losses)
         loss = sum(loss_list)
         loss.backward()
+        reducer.wait()
         opt.step()
         opt._learning_rate.step()
         model.clear_gradients()
@@ -80,6 +92,28 @@ def main():
         torch.cuda.synchronize()
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     ks = sorted(((e.time_range.start, e.time_range.end, e.name) for e in evs), key=lambda t: t[0])
+    if world > 1:
+        dist.barrier()
+        if rank == 0:
+            # NCCL report: per step (delimited by momentum_kernel) the all-reduce kernels and the optimizer's wait
+            step_start = ks[0][0] if ks else 0
+            last_compute_end = None
+            print("NCCL report (rank 0, world %d, bucket %s MB): all-reduce kernels [start offset in step us, duration us]"
+                  % (world, os.environ.get("MSB_BUCKET_MB", "32")))
+            cur = []
+            for s_, e_, name in ks:
+                if "nccl" in name.lower():
+                    cur.append((round(s_ - step_start, 1), round(e_ - s_, 1)))
+                elif "momentum_kernel" in name:
+                    print("  step: span %.1f us, all-reduces %s, total NCCL kernel time %.1f us, optimizer started %.1f us "
+                          "after the last backward kernel ended" % (e_ - step_start, cur, sum(d for _, d in cur),
+                                                                    s_ - (last_compute_end or s_)))
+                    cur, step_start = [], e_
+                else:
+                    last_compute_end = e_
+        if rank != 0:
+            dist.destroy_process_group()
+            return
     if not ks:
         print("no CUDA events captured (CUPTI unavailable?)")
         return
