@@ -604,7 +604,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
     ap.add_argument("--sync-bn", action="store_true", help="SyncBatchNorm over all ranks (reference default at N>1)")
-    ap.add_argument("--bucket-mb", type=float, default=32.0, help="gradient all-reduce bucket size (N>1)")
+    ap.add_argument("--bucket-mb", type=float, default=8.0, help="gradient all-reduce bucket size (N>1)")
     ap.add_argument("--check", action="store_true", help="N>=2: data-parallel equivalence checks instead of timing")
     args = ap.parse_args()
     if args.config == "preprocess":

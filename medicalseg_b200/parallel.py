@@ -4,7 +4,9 @@ One process per GPU; whole volumes are sharded across ranks; the ONLY collective
 gradient all-reduce (NCCL over NVLink 5 / NVSwitch).  The model keeps all gradients in one flat f32 buffer laid
 out in forward order, so backward completes it from the END towards the front: every transition block that
 finishes its backward fires `grad_ready_hook(lo, hi)`, and we launch the all-reduce of that contiguous slice on a
-side stream right away, overlapping it with the rest of backward.  Small slices are coalesced into buckets.
+side stream right away, overlapping it with the rest of backward.  Small slices are coalesced into buckets of at
+least `bucket_mb` (default 8 MB; measured on 2 x B200: 12.30 ms/step with 32 MB buckets - the last ~30 MB were reduced
+after backward had finished - vs 12.02 ms with 8 MB: 5 all-reduces, the last one 4.6 MB / 41 us).
 Averaging (1/world) is folded into the optimizer kernel (Momentum.grad_scale) — no extra pass over the grads.
 
 Two transports: `backend="direct"` (default on CUDA) calls ncclAllReduce on our own communicator (nccl.py) on the
@@ -57,7 +59,7 @@ class DistributedGradReducer:
     """Attach to a model: reducer = DistributedGradReducer(model); after loss.backward() call reducer.wait()
     before optimizer.step().  Works with any torch.distributed backend (nccl on GPUs, gloo in CPU tests)."""
 
-    def __init__(self, flat_grad: torch.Tensor, bucket_mb: float = 32.0, group=None, backend: Optional[str] = None):
+    def __init__(self, flat_grad: torch.Tensor, bucket_mb: float = 8.0, group=None, backend: Optional[str] = None):
         self.flat_grad = flat_grad
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1

@@ -137,9 +137,11 @@ def misc(what, reps):
         bias = torch.zeros(c, device=dev)
         _time(lambda: ops.k5_fwd(x, packed, bias, c, y, False, None, 1, sums, ws), reps,
               "%s: %d->%d 5x5x5 @%d^3 split-K + finalize" % (what, c, c, e), n * GFLOP(c, e), "TFLOP/s")
-    elif what in ("mrifwd32", "mriwgrad128"):
+    elif what in ("mrifwd32", "mriwgrad128", "mriwgrad256"):
         if what == "mrifwd32":
             c, dims = 32, (512, 512, 12)
+        elif what == "mriwgrad256":
+            c, dims = 256, (64, 64, 4)
         else:
             c, dims = 128, (128, 128, 8)
         n = 2
@@ -157,7 +159,7 @@ def misc(what, reps):
         else:
             dw = torch.zeros(125 * c * c, device=dev)
             _time(lambda: ops.k5_wgrad_tm(x, y, dw, None, c, c), reps,
-                  "mriwgrad128: 128->128 5x5x5 wgrad @128x128x8 (per-tap kernel)", n * gf, "TFLOP/s")
+                  "%s: %d->%d 5x5x5 wgrad @%s (per-tap kernel)" % (what, c, c, "x".join(map(str, dims))), n * gf, "TFLOP/s")
     elif what in ("head20", "loss20"):
         c, dims, n = 20, (512, 512, 12), 2
         s = dims[0] * dims[1] * dims[2]
