@@ -51,6 +51,9 @@ int msb_version(void);
 const char* msb_last_error_string(void);
 
 /* ---- layout converters (boundary) ------------------------------------------------------------------ */
+/* Clears a device buffer on `stream` (cudaMemsetAsync: a memset node inside a CUDA-graph capture).  Replaces
+ * `Layer.clear_gradients()` / `paddle.zeros` on the train path (medicalseg/core/train.py:155). */
+int msb_zero(void* ptr, size_t bytes, void* stream);
 /* NCDHW f32 [N,C,S] -> B8 view (channels >= C zero-filled up to dst.c).  vnet.py:256 (network input side). */
 int msb_to_blocked(const float* src, int n, int c, int64_t s, msb_tensor dst, void* stream);
 /* B8 view -> NCDHW f32 [N,C,S]. */

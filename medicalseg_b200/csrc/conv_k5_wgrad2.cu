@@ -20,7 +20,7 @@ constexpr int kW2TileW = 16, kW2TileH = 8;
 constexpr int kW2GroupBytes = kW2TileH * (kW2TileW + 4) * 16;  // one 8-channel M-group of the X tile (w halo only)
 constexpr int kW2XBytes = 16 * kW2GroupBytes;                  // 128 M rows
 constexpr int kW2RowBytes = kW2TileW * 16;                     // one (h, c8) row of the dY tile
-constexpr int kW2Stages = 3;
+constexpr int kW2MaxStages = 4;  // stages are a launch parameter: 4 when the tiles fit (32 channels), else 3
 
 struct Wg2Params {
   int n, cin_real, cout_real, dyp, npad;
@@ -30,6 +30,7 @@ struct Wg2Params {
   int qm, kd_groups, mhalves, cin_m;
   int units_per_pass, passes_per_group, num_passes, chunks, tiles_per_chunk, total_tiles;
   int dy_stage_bytes;
+  int stages;                            // TMA ring depth (3 or 4)
   unsigned char pass_order[64];          // passes sorted by MMA cost (heavy first): CTA b gets items b, b+grid, ... =
                                          // one heavy + one light pass instead of two heavy ones
   float* ws;
@@ -56,10 +57,12 @@ __global__ void __launch_bounds__(256, 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* dy_smem = smem;                                        // [stages][dy_stage_bytes]
+  const int kW2Stages = p.stages;
   uint8_t* x_smem = dy_smem + kW2Stages * p.dy_stage_bytes;       // [stages][kW2XBytes]
   uint64_t* bars = reinterpret_cast<uint64_t*>(x_smem + kW2Stages * kW2XBytes);
-  // [0,3) full  [3,6) empty  [6] acc_full  [7] acc_empty
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  // [0,4) full  [4,8) empty  [8] acc_full  [9] acc_empty
+  constexpr int kEmpty = kW2MaxStages, kAccFull = 2 * kW2MaxStages, kAccEmpty = 2 * kW2MaxStages + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = ptx::smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -67,9 +70,9 @@ __global__ void __launch_bounds__(256, 1)
   const int csize = CL ? p.csize : 1;
   const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kW2Stages; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(3 + i), (uint32_t)csize); }
-    ptx::mbar_init(BAR(6), 1);
-    ptx::mbar_init(BAR(7), 4);
+    for (int i = 0; i < kW2Stages; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(kEmpty + i), (uint32_t)csize); }
+    ptx::mbar_init(BAR(kAccFull), 1);
+    ptx::mbar_init(BAR(kAccEmpty), 4);
     ptx::fence_mbar_init();
   }
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmap_x); ptx::prefetch_tmap(&tmap_dy); }
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(256, 1)
           const int tw = r % p.tiles_w; r /= p.tiles_w;
           const int th = r % p.tiles_h; const int d = r / p.tiles_h;
           const uint32_t s = use % kW2Stages, ph = (use / kW2Stages) & 1;
-          ptx::mbar_wait(BAR(3 + s), ph ^ 1);
+          ptx::mbar_wait(BAR(kEmpty + s), ph ^ 1);
           ptx::mbar_expect_tx(BAR(s), bytes);
           if (CL) {  // box i of the tile (planes_valid X planes + the dY tile) is issued by rank i % csize for everyone
             for (int q = 0; q < planes_valid; ++q)
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(256, 1)
       const int nkw = kw1 - kw0;
       const uint32_t idesc = ptx::make_idesc_bf16(128, (int)pass_n(jg), 1, 1);
       const bool repl = CL && p.rep && g == p.kd_groups - 1;
-      ptx::mbar_wait(BAR(7), (iuse & 1) ^ 1);
+      ptx::mbar_wait(BAR(kAccEmpty), (iuse & 1) ^ 1);
       ptx::tc_fence_after();
       bool mid_started = false;
       for (int t = t0; t < t1; ++t, ++use) {
@@ -238,11 +241,11 @@ __global__ void __launch_bounds__(256, 1)
           }
         }
         if (leader) {
-          if (CL) ptx::mma_commit_mc(BAR(3 + s), cmask);  // the stage is shared: free once every rank's MMAs retired
-          else ptx::mma_commit(BAR(3 + s));
+          if (CL) ptx::mma_commit_mc(BAR(kEmpty + s), cmask);  // the stage is shared: free once every rank's MMAs retired
+          else ptx::mma_commit(BAR(kEmpty + s));
         }
       }
-      if (leader) ptx::mma_commit(BAR(6));
+      if (leader) ptx::mma_commit(BAR(kAccFull));
       __syncwarp();
     }
   } else if (warp >= 4) {
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(256, 1)
       const int ci = mh * 128 + ci_local;
       // repl: row block q = tap kw = q + rank; rank 1 only contributes kw = 4 (kw 1..3 are rank 0's)
       const bool row_ok = (qplane < p.qm) && kd < 5 && ci < p.cin_real && (!repl || crank == 0 || qplane == p.qm - 1);
-      ptx::mbar_wait(BAR(6), iuse & 1);
+      ptx::mbar_wait(BAR(kAccFull), iuse & 1);
       ptx::tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
       const bool bal = CL && p.balance;
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__(256, 1)
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(BAR(7));
+      if (lane == 0) ptx::mbar_arrive(BAR(kAccEmpty));
     }
   }
   ptx::tc_fence_before();
@@ -359,7 +362,11 @@ int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin
   if (need > dy_rows) dy_rows = need;
   p.dy_stage_bytes = (dy_rows * kW2RowBytes + 1023) / 1024 * 1024;
   p.ws = ws;
-  const int smem_bytes = kW2Stages * (p.dy_stage_bytes + kW2XBytes) + 1024 + 128;
+  // ring depth: 4 stages when they fit (32 channels: 52 KB per stage) - the kw-replicated leftover group spends only
+  // 8 MMAs on a tile, so three tiles in flight did not cover the TMA round trip; 3 otherwise (msb_debug_set(6, 32): 3)
+  p.stages = kW2MaxStages;
+  if ((g_debug_flags[6] & 32) || p.stages * (p.dy_stage_bytes + kW2XBytes) + 1024 + 128 > 227 * 1024) p.stages = 3;
+  const int smem_bytes = p.stages * (p.dy_stage_bytes + kW2XBytes) + 1024 + 128;
   if (smem_bytes > 227 * 1024) return MSB_ERR_UNSUPPORTED;
   CUtensorMap tmx, tmdy;
   int rc;

@@ -876,6 +876,12 @@ extern "C" {
 int msb_version(void) { return MSB_VERSION; }
 const char* msb_last_error_string(void) { return msb::last_error(); }
 
+int msb_zero(void* ptr, size_t bytes, void* stream) {
+  MSB_REQUIRE(ptr != nullptr || bytes == 0, "msb_zero: null pointer");
+  if (bytes) MSB_CUDA_OK(cudaMemsetAsync(ptr, 0, bytes, as_stream(stream)));
+  return MSB_OK;
+}
+
 int msb_to_blocked(const float* src, int n, int c, int64_t s, msb_tensor dst, void* stream) {
   MSB_REQUIRE(src && view_ok(dst) && n > 0 && c > 0 && c <= dst.c && s > 0, "msb_to_blocked: bad arguments");
   MSB_DISPATCH_DTYPE(dst.dtype, to_blocked_kernel<T><<<plane_grid(n, dst.c, s), kThreads, 0, as_stream(stream)>>>(

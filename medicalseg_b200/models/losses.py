@@ -88,7 +88,7 @@ class _DiceCEFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, labels, class_w, ignore_index):
         n, c = logits.shape[:2]
-        acc = torch.zeros(3 * c + 2, dtype=torch.float64, device=logits.device)
+        acc = ops.zero_(torch.empty(3 * c + 2, dtype=torch.float64, device=logits.device))
         result = torch.empty(2 + c, dtype=torch.float32, device=logits.device)
         ops.dice_ce_fwd(logits, labels, class_w, ignore_index, acc)
         ops.dice_ce_finalize(acc, c, result)
@@ -119,7 +119,7 @@ def _prep(logits, labels):
 def class_weights(logits: torch.Tensor) -> torch.Tensor:
     """models/losses/loss_utils.py:31-40 on the GPU: w_c = sum(1-softmax_c) / sum(softmax_c)."""
     n, c = logits.shape[:2]
-    psum = torch.zeros(c, dtype=torch.float64, device=logits.device)
+    psum = ops.zero_(torch.empty(c, dtype=torch.float64, device=logits.device))
     w = torch.empty(c, dtype=torch.float32, device=logits.device)
     ops.class_weight_sums(logits, psum)
     ops.class_weight_finalize(psum, float(n * logits[0, 0].numel()), c, w)
@@ -291,7 +291,7 @@ def fused_head_losses(ao, w2, b2, c, dims, labels, losses, plan):
     ignore_index = ce.ignore_index if ce is not None else 255
     if ce is not None:
         if ce.weight is None:  # first logits ever seen define the class weights (cross_entropy_loss.py:68-69)
-            psum = torch.zeros(c, dtype=torch.float64, device=dev)
+            psum = ops.zero_(torch.empty(c, dtype=torch.float64, device=dev))
             ops.eval_head(ao, w2, b2, None, None, c, ignore_index, psum=psum)
             ce.weight = torch.empty(c, dtype=torch.float32, device=dev)
             ops.class_weight_finalize(psum, float(n * ao.s), c, ce.weight)
@@ -304,7 +304,7 @@ def fused_head_losses(ao, w2, b2, c, dims, labels, losses, plan):
         if dice._ones is None or dice._ones.numel() != c or dice._ones.device != dev:
             dice._ones = torch.ones(c, dtype=torch.float32, device=dev)
         class_w = dice._ones
-    acc = torch.zeros(3 * c + 2, dtype=torch.float64, device=dev)
+    acc = ops.zero_(torch.empty(3 * c + 2, dtype=torch.float64, device=dev))
     result = torch.empty(2 + c, dtype=torch.float32, device=dev)
     ops.eval_head(ao, w2, b2, labels, class_w, c, ignore_index, pred=pred, acc=acc)
     ops.dice_ce_finalize(acc, c, result)

@@ -701,7 +701,7 @@ class VNet(_Module):
     load_state_dict = set_state_dict
 
     def clear_gradients(self):
-        self.store.grad.zero_()
+        ops.zero_(self.store.grad)
 
     clear_grad = clear_gradients
 
@@ -917,7 +917,7 @@ class VNet(_Module):
         st, T = self.store, self.training
         n = x.shape[0]
         g = self.groups(n)
-        self._scratch.zero_()
+        ops.zero_(self._scratch)
         self._scratch_off = 0
         tape = {"x": x, "n": n}
         dims = [tuple(x.shape[2:])]

@@ -79,6 +79,12 @@ class B8:
         return out
 
 
+def zero_(t: torch.Tensor) -> torch.Tensor:
+    """clears a contiguous CUDA tensor with a stream-ordered memset (no fill kernel)"""
+    call("msb_zero", _ptr(t), t.numel() * t.element_size(), _stream())
+    return t
+
+
 NULL_T = MsbTensor(None, 0, 0, 0)
 
 

@@ -60,7 +60,7 @@ class Momentum:
             self._owner.mark_parameters_updated()
 
     def clear_grad(self):
-        self._store.grad.zero_()
+        ops.zero_(self._store.grad)
 
     def state_dict(self):
         # per-parameter momentum in the reference (Paddle) shapes: independent of the internal (tap-major) layout
