@@ -102,9 +102,11 @@ template <int ORDER, int PRE>
 __global__ void __launch_bounds__(256)
     resample_f32_kernel(const float* __restrict__ src, msb_dim3 in, float* __restrict__ dst, msb_dim3 out, float p0,
                         float p1, float p2) {
+  // block = (bx <= 256 threads along w, 256 / bx output rows): a 128-wide output row fills half a 256-thread block, so
+  // the block takes two rows - no idle half (round 1 launched 256 x 1 threads with 128 active)
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;  // last axis fastest -> coalesced stores
-  const int oy = blockIdx.y, oz = blockIdx.z;
-  if (ox >= out.w) return;
+  const int oy = blockIdx.y * blockDim.y + threadIdx.y, oz = blockIdx.z;
+  if (ox >= out.w || oy >= out.h) return;
   const double cz = axis_coord(oz, in.d, out.d), cy = axis_coord(oy, in.h, out.h), cx = axis_coord(ox, in.w, out.w);
   const int64_t sy = in.w, sz = (int64_t)in.h * in.w;
   float r;
@@ -136,8 +138,8 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256) resample_i32_kernel(const int32_t* __restrict__ src, msb_dim3 in,
                                                            int32_t* __restrict__ dst, msb_dim3 out) {
   const int ox = blockIdx.x * blockDim.x + threadIdx.x;
-  const int oy = blockIdx.y, oz = blockIdx.z;
-  if (ox >= out.w) return;
+  const int oy = blockIdx.y * blockDim.y + threadIdx.y, oz = blockIdx.z;
+  if (ox >= out.w || oy >= out.h) return;
   const int iz = min(max((int)floor(axis_coord(oz, in.d, out.d) + 0.5), 0), in.d - 1);
   const int iy = min(max((int)floor(axis_coord(oy, in.h, out.h) + 0.5), 0), in.h - 1);
   const int ix = min(max((int)floor(axis_coord(ox, in.w, out.w) + 0.5), 0), in.w - 1);
@@ -201,6 +203,12 @@ int msb_normalize(const float* src, float* dst, int64_t count, float lo, float h
   return MSB_OK;
 }
 
+static inline dim3 resample_block(int out_w) {
+  int bx = (out_w + 31) / 32 * 32;
+  if (bx > 256) bx = 256;
+  return dim3((unsigned)bx, (unsigned)(256 / bx), 1);
+}
+
 int msb_resample_f32(const float* src, msb_dim3 in_dims, float* dst, msb_dim3 out_dims, int order, int pre_op,
                      float p0, float p1, float p2, void* stream) {
   MSB_REQUIRE(src && dst && in_dims.d > 0 && in_dims.h > 0 && in_dims.w > 0 && out_dims.d > 0 && out_dims.h > 0 &&
@@ -210,9 +218,10 @@ int msb_resample_f32(const float* src, msb_dim3 in_dims, float* dst, msb_dim3 ou
   float q0 = p0, q1 = p1, q2 = p2;
   if (pre_op == 1) q1 = (float)(((double)p1 - (double)p0) / 255.0);  // (HU_min, HU_max, HU_nan) -> (min, div, nan)
   if (pre_op == 2) q1 = p1 - p0;                                     // (lo, hi) -> (lo, range)
-  const dim3 grid((out_dims.w + 255) / 256, out_dims.h, out_dims.d);
+  const dim3 block = resample_block(out_dims.w);
+  const dim3 grid((out_dims.w + block.x - 1) / block.x, (out_dims.h + block.y - 1) / block.y, out_dims.d);
   cudaStream_t st = as_stream(stream);
-#define MSB_RS(O, P) resample_f32_kernel<O, P><<<grid, 256, 0, st>>>(src, in_dims, dst, out_dims, q0, q1, q2)
+#define MSB_RS(O, P) resample_f32_kernel<O, P><<<grid, block, 0, st>>>(src, in_dims, dst, out_dims, q0, q1, q2)
   if (order == 0) { if (pre_op == 0) MSB_RS(0, 0); else if (pre_op == 1) MSB_RS(0, 1); else MSB_RS(0, 2); }
   else            { if (pre_op == 0) MSB_RS(1, 0); else if (pre_op == 1) MSB_RS(1, 1); else MSB_RS(1, 2); }
 #undef MSB_RS
@@ -224,8 +233,9 @@ int msb_resample_i32(const int32_t* src, msb_dim3 in_dims, int32_t* dst, msb_dim
   MSB_REQUIRE(src && dst && in_dims.d > 0 && in_dims.h > 0 && in_dims.w > 0 && out_dims.d > 0 && out_dims.h > 0 &&
                   out_dims.w > 0 && out_dims.h <= 65535 && out_dims.d <= 65535,
               "msb_resample_i32: bad dims");
-  const dim3 grid((out_dims.w + 255) / 256, out_dims.h, out_dims.d);
-  resample_i32_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, in_dims, dst, out_dims);
+  const dim3 block = resample_block(out_dims.w);
+  const dim3 grid((out_dims.w + block.x - 1) / block.x, (out_dims.h + block.y - 1) / block.y, out_dims.d);
+  resample_i32_kernel<<<grid, block, 0, as_stream(stream)>>>(src, in_dims, dst, out_dims);
   MSB_LAUNCH_OK();
   return MSB_OK;
 }
