@@ -169,7 +169,11 @@ def run_vnet(args, cfg):
     model = VNet(num_classes=classes, compute_dtype=cfg["dtype"], seed=0, sync_bn=bool(args.sync_bn), **cfg["model_kw"])
     model.train()
     losses = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1])], "coef": [1]}
+    if args.tile_scheduler == "static":
+        os.environ["MSB_TILE_SCHEDULER"] = "0"
     reducer = DistributedGradReducer(model.store.grad, bucket_mb=args.bucket_mb).attach(model)
+    if args.tile_scheduler == "dynamic":
+        _lib.call("msb_set_tile_scheduler", 1)
     opt = Momentum(PolynomialDecay(cfg["lr"], 15000), model.parameters(), 0.9, 1e-4, grad_scale=reducer.grad_scale)
     img, lab = synthetic_gpu_batch(cfg, device, seed=rank)
     orig_call = _lib.call
@@ -349,6 +353,8 @@ def run_vnet(args, cfg):
             "launch_mode": "cuda-graph replay (1 cudaGraphLaunch/step%s)" % (", NCCL all-reduces inside the graph"
                                                                              if world > 1 else "")
                            if use_graph else "eager (python -> C ABI)",
+            "tile_scheduler": "dynamic (atomic counter)" if (args.tile_scheduler == "dynamic" or
+                                                              (args.tile_scheduler == "auto" and world > 1)) else "static",
             "clocks": clocks,
             "roofline": roof,
         }
@@ -605,6 +611,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured CUDA graph")
     ap.add_argument("--sync-bn", action="store_true", help="SyncBatchNorm over all ranks (reference default at N>1)")
     ap.add_argument("--bucket-mb", type=float, default=8.0, help="gradient all-reduce bucket size (N>1)")
+    ap.add_argument("--tile-scheduler", choices=["auto", "static", "dynamic"], default="auto",
+                    help="persistent-kernel tile assignment: auto = dynamic (atomic counter) at N>1, static at N=1")
     ap.add_argument("--check", action="store_true", help="N>=2: data-parallel equivalence checks instead of timing")
     args = ap.parse_args()
     if args.config == "preprocess":

@@ -51,6 +51,11 @@ int msb_version(void);
 const char* msb_last_error_string(void);
 
 /* ---- layout converters (boundary) ------------------------------------------------------------------ */
+/* Tile scheduling of the persistent tensor-core kernels (5x5x5 fwd / dgrad, both weight-gradient kernels, the strided
+ * convs): 0 = static round-robin over the grid (default), 1 = CTAs fetch tiles from a self-resetting atomic counter in
+ * device memory.  The data-parallel step (medicalseg/core/train.py:81-88) turns it on: NCCL's all-reduce CTAs occupy
+ * SMs while backward runs, and with static assignment the CTAs displaced by them set the kernel's makespan. */
+int msb_set_tile_scheduler(int dynamic);
 /* Clears a device buffer on `stream` (cudaMemsetAsync: a memset node inside a CUDA-graph capture).  Replaces
  * `Layer.clear_gradients()` / `paddle.zeros` on the train path (medicalseg/core/train.py:155). */
 int msb_zero(void* ptr, size_t bytes, void* stream);

@@ -27,6 +27,7 @@ T, D3, SZ = MsbTensor, MsbDim3, C.c_size_t
 SIGNATURES = {
     "msb_version": (I, []),
     "msb_last_error_string": (C.c_char_p, []),
+    "msb_set_tile_scheduler": (I, [I]),
     "msb_zero": (I, [P, SZ, P]),
     "msb_to_blocked": (I, [P, I, I, L, T, P]),
     "msb_from_blocked": (I, [T, P, I, I, L, P]),

@@ -67,7 +67,21 @@ struct K2Params {
   int groups;
   double* sums;
   int sums_c;
+  unsigned int* sched;   // dynamic tile scheduler counters {next, done} (nullptr = static round-robin)
 };
+
+static __device__ unsigned int g_sched_k2[2];
+static unsigned int* g_sched_k2_ptr = nullptr;
+static int g_dynamic_tiles_k2 = 0;
+
+int msb_set_tile_scheduler_k2s2(int dynamic) {
+  if (dynamic && g_sched_k2_ptr == nullptr) {
+    MSB_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void**>(&g_sched_k2_ptr), g_sched_k2));
+    MSB_CUDA_OK(cudaMemset(g_sched_k2_ptr, 0, 2 * sizeof(unsigned int)));
+  }
+  g_dynamic_tiles_k2 = dynamic ? 1 : 0;
+  return MSB_OK;
+}
 
 __global__ void __launch_bounds__(kK2Threads, 1)
     conv_k2s2_kernel(const __grid_constant__ CUtensorMap tmap_x, const K2Params p) {
@@ -77,6 +91,9 @@ __global__ void __launch_bounds__(kK2Threads, 1)
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_smem + kK2Stages * kK2StageBytes);
   // barrier map: [0,S) full  [S,2S) empty  [2S,2S+2) acc_full  [2S+2,2S+4) acc_empty
   constexpr int kFull = 0, kEmpty = kK2Stages, kAccFull = 2 * kK2Stages, kAccEmpty = 2 * kK2Stages + 2;
+  constexpr int kSF = 40, kSE = 40 + sched::kDepth;  // tile-scheduler ring; item slots at byte 512 of the barrier KB
+  static_assert(2 * kK2Stages + 4 + 1 <= 40, "barrier map overlap");
+  volatile int* sched_slots = reinterpret_cast<volatile int*>(reinterpret_cast<uint8_t*>(bars) + 512);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kK2Stages + 4);
   float* stat_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);  // [epilogue warps][2][256]
 
@@ -86,6 +103,7 @@ __global__ void __launch_bounds__(kK2Threads, 1)
   if (threadIdx.x == 0) {
     for (int i = 0; i < kK2Stages; ++i) { ptx::mbar_init(BAR(kFull + i), 1); ptx::mbar_init(BAR(kEmpty + i), 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(kAccFull + i), 1); ptx::mbar_init(BAR(kAccEmpty + i), kK2EpiWarps); }
+    sched::init(BAR(kSF), BAR(kSE), 2 + kK2EpiWarps);  // consumers: producer and MMA warps + the epilogue warps
     ptx::fence_mbar_init();
   }
   for (int i = threadIdx.x; i < kK2EpiWarps * 2 * 256; i += kK2Threads) stat_smem[i] = 0.f;
@@ -111,12 +129,23 @@ __global__ void __launch_bounds__(kK2Threads, 1)
   const int ktaps = p.mode == 0 ? p.kdn * p.khn * p.kwn : (p.wmode == 1 ? p.kwn : 1);  // taps carried by the K loop
   const int kiters = ktaps * p.chunks;
   const uint32_t b_bytes = (uint32_t)p.nmma * 32u;
+  // k-th item of this CTA: static round-robin, or from the scheduler warp (umma.cuh, namespace sched)
+  const bool dyn = p.sched != nullptr;
+  auto get_item = [&](uint32_t k) -> int {
+    if (dyn) return sched::next(BAR(kSF), BAR(kSE), sched_slots, k, lane);
+    const int it = (int)blockIdx.x + (int)k * (int)gridDim.x;
+    return it < num_items ? it : -1;
+  };
 
-  if (warp == 0) {
+  if (warp == 3) {
+    if (dyn && lane == 0) sched::run(BAR(kSF), BAR(kSE), sched_slots, p.sched, num_items);
+  } else if (warp == 0) {
     // ================= TMA producer: one (tap, 16-channel chunk) A tile + its weight block per stage ==========
     const bool leader = ptx::elect_one();
     uint32_t use = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    for (uint32_t ik = 0;; ++ik) {
+      const int item = get_item(ik);
+      if (item < 0) break;
       const int tile = item / p.tap_groups, tgp = item % p.tap_groups;
       const int n = tile / tiles_per_n;
       int r = tile % tiles_per_n;
@@ -152,7 +181,8 @@ __global__ void __launch_bounds__(kK2Threads, 1)
     constexpr uint32_t a_hi = ptx::desc_hi(128u), b_hi = ptx::desc_hi(128u);
     const uint32_t a_lbo16 = (uint32_t)(kK2TileH * kK2TileW * 16) >> 4, b_lbo16 = (uint32_t)p.nmma;  // nmma*16 B >> 4
     uint32_t use = 0, iuse = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
+    for (;; ++iuse) {
+      if (get_item(iuse) < 0) break;
       const uint32_t as = iuse & 1, aph = (iuse >> 1) & 1;
       ptx::mbar_wait(BAR(kAccEmpty + as), aph ^ 1);
       ptx::tc_fence_after();
@@ -188,7 +218,9 @@ __global__ void __launch_bounds__(kK2Threads, 1)
     const bool bias_vec = has_bias && (reinterpret_cast<uintptr_t>(p.bias) % 16 == 0);
     const bool want_stats = p.sums != nullptr;
     uint32_t iuse = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
+    for (;; ++iuse) {
+      const int item = get_item(iuse);
+      if (item < 0) break;
       const int tile = item / p.tap_groups, tgp = item % p.tap_groups;
       const int n = tile / tiles_per_n;
       int r = tile % tiles_per_n;
@@ -426,6 +458,7 @@ static int launch_k2s2(int mode, const msb_tensor& x, const void* packed, const 
   p.tiles_h = (sd.h + kK2TileH - 1) / kK2TileH;
   p.packed = packed; p.bias = bias; p.out = out; p.accumulate = accumulate;
   p.groups = groups; p.sums = sums; p.sums_c = out.c;
+  p.sched = g_dynamic_tiles_k2 ? g_sched_k2_ptr : nullptr;
   CUtensorMap tmap;
   int rc;
   if (mode == 0) {

@@ -9,6 +9,7 @@ namespace msb {
 constexpr int kNumTaps = 125;
 
 extern int g_debug_flags[8];
+extern int g_dynamic_tiles;  // msb_set_tile_scheduler(): 1 = persistent kernels fetch tiles from an atomic counter
 
 // 4-D TMA map over a B8 bf16 view: dims (W*8, H, D, planes), box (box_w*8, box_h, box_d, box_p)
 int make_b8_tmap(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 dims, int box_w, int box_h, int box_d,
@@ -20,6 +21,10 @@ int make_b8_tmap_hmajor(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 d
 // strided sub-lattice map (5-D, elementStrides sw / sh along w / h): shared-memory image [plane][box_h][box_w][8]
 int make_b8_tmap_s2(CUtensorMap* map, const msb_tensor& t, int n, msb_dim3 dims, int box_w, int box_h, int box_p,
                     int sw = 2, int sh = 2);
+
+// per-translation-unit halves of msb_set_tile_scheduler (each .cu owns the counters of its kernels)
+int msb_set_tile_scheduler_wgrad2(int dynamic);
+int msb_set_tile_scheduler_k2s2(int dynamic);
 
 // kh-stacked weight-gradient kernel (conv_k5_wgrad2.cu); returns MSB_ERR_UNSUPPORTED when not applicable
 // kw_taps: 5 = 5x5x5 kernel (ws [125][cout][cin]); 1 = 5x5x1 kernel of the w-folded convs (ws [25][cout][cin])

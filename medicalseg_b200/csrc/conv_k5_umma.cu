@@ -97,7 +97,12 @@ struct FwdParams {
   long long* prof;                       // bring-up: per-CTA clocks the MMA warp spent {total, w_full, halo_full, acc_empty}
   float* ws;                             // split-K: f32 partial sums [n][out_c8][D*H*W][8], zero on entry
   int ksplit, chunks_per_split;          // split-K: item = tile * ksplit + slice; slice covers chunks_per_split 16-channel chunks
+  unsigned int* sched;                   // dynamic tile scheduler counters {next, done} (nullptr = static round-robin)
 };
+
+static __device__ unsigned int g_sched_fwd[2];
+static __device__ unsigned int g_sched_wg[2];
+int g_dynamic_tiles = 0;
 
 // f32 vector reduction into global memory (sm_90+): 4 consecutive floats per instruction
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -125,6 +130,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_smem + Cfg::kWStages * Cfg::kWStageBytes);
   // barrier map: [0,2) halo_full  [2,4) halo_empty  [4,6) acc_full  [6,8) acc_empty  [8,8+S) w_full  [8+S,8+2S) w_empty
   constexpr int kWF = 8, kWE = 8 + Cfg::kWStages;
+  constexpr int kSF = 40, kSE = 40 + sched::kDepth;  // tile-scheduler ring (full / empty), item slots at byte 512
+  static_assert(8 + 2 * Cfg::kWStages + 1 <= 40, "barrier map overlap");
+  volatile int* sched_slots = reinterpret_cast<volatile int*>(reinterpret_cast<uint8_t*>(bars) + 512);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * Cfg::kWStages);
   float* stat_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);  // [8 warps][2][NPAD]
 
@@ -136,6 +144,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(0 + i), 1); ptx::mbar_init(BAR(2 + i), 1); }
     for (int i = 0; i < Cfg::kWStages; ++i) { ptx::mbar_init(BAR(kWF + i), 1); ptx::mbar_init(BAR(kWE + i), 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(4 + i), 1); ptx::mbar_init(BAR(6 + i), 8); }
+    sched::init(BAR(kSF), BAR(kSE), 11);  // consumers: halo, weight and MMA warps + 8 epilogue warps
     ptx::fence_mbar_init();
   }
   for (int i = threadIdx.x; i < 8 * 2 * NPAD; i += kFwdThreads) stat_smem[i] = 0.f;
@@ -162,11 +171,23 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
     }
   };
 
-  if (warp == 0) {
+  // k-th item of this CTA: static round-robin, or handed out by the scheduler warp (see umma.cuh, namespace sched)
+  const bool dyn = p.sched != nullptr;
+  auto get_item = [&](uint32_t k) -> int {
+    if (dyn) return sched::next(BAR(kSF), BAR(kSE), sched_slots, k, lane);
+    const int it = (int)blockIdx.x + (int)k * (int)gridDim.x;
+    return it < num_items ? it : -1;
+  };
+
+  if (warp == 3) {
+    if (dyn && lane == 0) sched::run(BAR(kSF), BAR(kSE), sched_slots, p.sched, num_items);
+  } else if (warp == 0) {
     // ================= halo TMA producer (whole warp runs the uniform loop, one elected lane issues) ==========
     const bool leader = ptx::elect_one();
     uint32_t use = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    for (uint32_t ik = 0;; ++ik) {
+      const int item = get_item(ik);
+      if (item < 0) break;
       const int tile = item / kdiv;
       const int n = tile / items_per_n;
       int r = tile % items_per_n;
@@ -190,7 +211,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
     const bool leader = ptx::elect_one();
     uint32_t use = 0;
     const int stages_per_chunk = 5 * p.kw_taps;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    for (uint32_t ik = 0;; ++ik) {
+      const int item = get_item(ik);
+      if (item < 0) break;
       int ck0, ck1;
       chunk_range(item, ck0, ck1);
       for (int ck = ck0; ck < ck1; ++ck) {
@@ -224,7 +247,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
     const int stages_per_chunk = 5 * p.kw_taps;
     const bool prof = p.prof != nullptr;
     long long t_w = 0, t_h = 0, t_a = 0, t_begin = prof ? clock64() : 0, tq = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
+    for (;; ++iuse) {
+      const int item = get_item(iuse);
+      if (item < 0) break;
       const uint32_t as = iuse % ACC_SETS, aph = (iuse / ACC_SETS) & 1;
       if (prof) tq = clock64();
       ptx::mbar_wait(BAR(6 + as), aph ^ 1);
@@ -301,7 +326,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
     const bool bias_vec = has_bias && (reinterpret_cast<uintptr_t>(p.bias) % 16 == 0);
     const bool want_stats = !SPLITK && p.sums != nullptr;
     uint32_t iuse = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++iuse) {
+    for (;; ++iuse) {
+      const int item = get_item(iuse);
+      if (item < 0) break;
       const int tile = item / kdiv;
       const int c_first = SPLITK ? 0 : (item % NS) * n_slice;  // first output channel of this slice (nsplit > 1 only with J == 1)
       const int n = tile / items_per_n;
@@ -605,6 +632,7 @@ struct WgParams {
   int s2_sd, s2_sh, s2_sw;              // strides
   int csize, rounds;                    // CL kernels: cluster size and ceil(passes_per_group / csize) - the (kh,kw)
                                         // passes of one (channel half, kd plane) share their tiles by TMA multicast
+  unsigned int* sched;                  // dynamic tile scheduler counters (nullptr = static; never with clusters)
 };
 
 // CL = true: clusters of p.csize CTAs walk the same tiles of one (channel half, kd plane) and own different (kh,kw)
@@ -621,7 +649,9 @@ __global__ void __launch_bounds__(256, 1)
   uint8_t* x_smem = smem;                           // [2][kXBytes]
   uint8_t* dy_smem = x_smem + 2 * Cfg::kXBytes;     // [2][kDyBytes]
   uint64_t* bars = reinterpret_cast<uint64_t*>(dy_smem + 2 * Cfg::kDyBytes);
-  // [0,2) full  [2,4) empty  [4] acc_full  [5] acc_empty
+  // [0,2) full  [2,4) empty  [4] acc_full  [5] acc_empty  [16,16+2D) tile-scheduler ring, item slots at byte 512
+  constexpr int kSF = 16, kSE = 16 + sched::kDepth;
+  volatile int* sched_slots = reinterpret_cast<volatile int*>(reinterpret_cast<uint8_t*>(bars) + 512);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = ptx::smem_u32(bars);
@@ -633,6 +663,7 @@ __global__ void __launch_bounds__(256, 1)
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(2 + i), (uint32_t)csize); }
     ptx::mbar_init(BAR(4), 1);
     ptx::mbar_init(BAR(5), 4);
+    sched::init(BAR(kSF), BAR(kSE), 6);  // consumers: the producer thread, the MMA warp, 4 epilogue warps
     ptx::fence_mbar_init();
   }
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmap_x); ptx::prefetch_tmap(&tmap_dy); }
@@ -650,6 +681,13 @@ __global__ void __launch_bounds__(256, 1)
   const int item0 = CL ? (int)blockIdx.x / csize : (int)blockIdx.x;
   const int item_step = CL ? (int)gridDim.x / csize : (int)gridDim.x;
   const int tiles_per_n = p.d * p.tiles_h * p.tiles_w;
+  // k-th item of this CTA (cluster): static round-robin, or from the scheduler warp (umma.cuh, namespace sched)
+  const bool dyn = !CL && p.sched != nullptr;
+  auto static_item = [&](uint32_t k) -> int {
+    const int it = item0 + (int)k * item_step;
+    return it < num_items ? it : -1;
+  };
+  if (warp == 3 && dyn && lane == 0) sched::run(BAR(kSF), BAR(kSE), sched_slots, p.sched, num_items);
 
   auto decode_pass = [&](int pass, int& mh, int& g, int& u0, int& u1) {
     int pg;
@@ -669,7 +707,9 @@ __global__ void __launch_bounds__(256, 1)
   if (warp == 0) {
     if (lane == 0) {
       uint32_t use = 0;
-      for (int item = item0; item < num_items; item += item_step) {
+      for (uint32_t ik = 0;; ++ik) {
+        const int item = dyn ? sched::next_lane(BAR(kSF), BAR(kSE), sched_slots, ik) : static_item(ik);
+        if (item < 0) break;
         const int pass = item / p.chunks, chunk = item % p.chunks;
         int mh, g, u0, u1;
         decode_pass(pass, mh, g, u0, u1);
@@ -727,7 +767,9 @@ __global__ void __launch_bounds__(256, 1)
     const uint32_t b_lbo16 = p.dbg_swap ? (uint32_t)Cfg::kDyPlaneBytes >> 4 : 8u;
     const uint32_t b_hi = ptx::desc_hi(p.dbg_swap ? 128u : (uint32_t)Cfg::kDyPlaneBytes);
     uint32_t use = 0, iuse = 0;
-    for (int item = item0; item < num_items; item += item_step, ++iuse) {
+    for (;; ++iuse) {
+      const int item = dyn ? sched::next(BAR(kSF), BAR(kSE), sched_slots, iuse, lane) : static_item(iuse);
+      if (item < 0) break;
       const int pass = item / p.chunks, chunk = item % p.chunks;
       int mh, g, u0, u1;
       decode_pass(pass, mh, g, u0, u1);
@@ -765,7 +807,9 @@ __global__ void __launch_bounds__(256, 1)
     const int row = q4 * 32 + lane;
     const int qplane = row / p.cin_m, ci_local = row % p.cin_m;
     uint32_t iuse = 0;
-    for (int item = item0; item < num_items; item += item_step, ++iuse) {
+    for (;; ++iuse) {
+      const int item = dyn ? sched::next(BAR(kSF), BAR(kSE), sched_slots, iuse, lane) : static_item(iuse);
+      if (item < 0) break;
       const int pass = item / p.chunks;
       int mh, g, u0, u1;
       decode_pass(pass, mh, g, u0, u1);
@@ -1295,6 +1339,25 @@ int msb_debug_read_prof(long long* host_out /* [148][4] */) {
   return MSB_OK;
 }
 
+// device addresses of the scheduler counters, resolved once (outside any stream capture) by msb_set_tile_scheduler
+static unsigned int* g_sched_fwd_ptr = nullptr;
+static unsigned int* g_sched_wg_ptr = nullptr;
+
+int msb_set_tile_scheduler(int dynamic) {
+  if (dynamic && g_sched_fwd_ptr == nullptr) {
+    MSB_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void**>(&g_sched_fwd_ptr), g_sched_fwd));
+    MSB_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void**>(&g_sched_wg_ptr), g_sched_wg));
+    MSB_CUDA_OK(cudaMemset(g_sched_fwd_ptr, 0, 2 * sizeof(unsigned int)));
+    MSB_CUDA_OK(cudaMemset(g_sched_wg_ptr, 0, 2 * sizeof(unsigned int)));
+  }
+  int rc = msb_set_tile_scheduler_wgrad2(dynamic);
+  if (rc) return rc;
+  rc = msb_set_tile_scheduler_k2s2(dynamic);
+  if (rc) return rc;
+  g_dynamic_tiles = dynamic ? 1 : 0;
+  return MSB_OK;
+}
+
 int msb_debug_set(int key, int value) {
   if (key < 0 || key >= 8) return MSB_ERR_INVALID;
   g_debug_flags[key] = value;
@@ -1382,6 +1445,7 @@ static int conv_k5_fwd_impl(const char* who, msb_tensor x, const void* packed, c
     p.prof = g_prof_buf;
   }
   p.ws = nullptr; p.ksplit = 1; p.chunks_per_split = x.c / 16;
+  p.sched = g_dynamic_tiles ? g_sched_fwd_ptr : nullptr;
   cudaStream_t st = as_stream(stream);
   const int npad_sel = msb_conv_k5_out_pad(out.c);
   // NOTE: the packed operand must have been built with cout_pad == npad_sel.
@@ -1497,6 +1561,7 @@ static int conv_k5_wgrad_impl(msb_tensor x, msb_tensor dy, float* dw, float* dbi
   const int qeff = p.qm < 5 ? p.qm : 5;
   p.kd_groups = (5 + qeff - 1) / qeff;
   p.ws = reinterpret_cast<float*>(workspace);
+  p.sched = g_dynamic_tiles ? g_sched_wg_ptr : nullptr;
   p.dbg_swap = g_debug_flags[1];
   p.pad = 2; p.units_total = 25; p.s2_c8n = 0; p.s2_khn = p.s2_kwn = p.s2_sd = p.s2_sh = p.s2_sw = 1;
   const int npad = msb_conv_k5_out_pad(dy.c);
@@ -1615,6 +1680,7 @@ int msb_conv_tc_wgrad(msb_tensor big, msb_tensor small, float* dw, float* dbias,
   p.dy_c8_total = (int)(small.n_stride / (Ss * 8));
   p.cin_m = 128; p.mhalves = cxs / 128; p.qm = 1; p.kd_groups = 1;
   p.ws = ws; p.dbg_swap = 0; p.pad = 0; p.units_total = 1; p.s2_c8n = big.c / 8;
+  p.sched = g_dynamic_tiles ? g_sched_wg_ptr : nullptr;
   p.s2_khn = kernel.h; p.s2_kwn = kernel.w; p.s2_sd = stride.d; p.s2_sh = stride.h; p.s2_sw = stride.w;
   int rc;
   switch (msb_conv_k5_out_pad(small.c)) {

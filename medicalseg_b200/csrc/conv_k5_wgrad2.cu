@@ -43,7 +43,21 @@ struct Wg2Params {
                                          // M slots idle) is loaded as 4 kw-shifted replicas of that plane instead, so ONE
                                          // MMA covers kw = replica (+ rank): 2 MMAs per row for the group instead of 5
   int gchunks[2], gtpc[2];               // rep: chunks / tiles per chunk of kd group 0 and 1 (sized by their MMA cost)
+  unsigned int* sched;                   // dynamic tile scheduler counters (nullptr = static; never with clusters)
 };
+
+static __device__ unsigned int g_sched_wg2[2];
+static unsigned int* g_sched_wg2_ptr = nullptr;
+static int g_dynamic_tiles_wg2 = 0;
+
+int msb_set_tile_scheduler_wgrad2(int dynamic) {
+  if (dynamic && g_sched_wg2_ptr == nullptr) {
+    MSB_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void**>(&g_sched_wg2_ptr), g_sched_wg2));
+    MSB_CUDA_OK(cudaMemset(g_sched_wg2_ptr, 0, 2 * sizeof(unsigned int)));
+  }
+  g_dynamic_tiles_wg2 = dynamic ? 1 : 0;
+  return MSB_OK;
+}
 
 // CL = true: launched in clusters of p.csize CTAs.  All CTAs of a cluster walk the same tiles of the same (channel half,
 // kd group) and differ only in the accumulators they own (kh group x kw subset = cluster rank); every TMA box is issued
@@ -60,8 +74,10 @@ __global__ void __launch_bounds__(256, 1)
   const int kW2Stages = p.stages;
   uint8_t* x_smem = dy_smem + kW2Stages * p.dy_stage_bytes;       // [stages][kW2XBytes]
   uint64_t* bars = reinterpret_cast<uint64_t*>(x_smem + kW2Stages * kW2XBytes);
-  // [0,4) full  [4,8) empty  [8] acc_full  [9] acc_empty
+  // [0,4) full  [4,8) empty  [8] acc_full  [9] acc_empty  [16,16+2D) tile-scheduler ring, item slots at byte 512
   constexpr int kEmpty = kW2MaxStages, kAccFull = 2 * kW2MaxStages, kAccEmpty = 2 * kW2MaxStages + 1;
+  constexpr int kSF = 16, kSE = 16 + sched::kDepth;
+  volatile int* sched_slots = reinterpret_cast<volatile int*>(reinterpret_cast<uint8_t*>(bars) + 512);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = ptx::smem_u32(bars);
@@ -73,6 +89,7 @@ __global__ void __launch_bounds__(256, 1)
     for (int i = 0; i < kW2Stages; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(kEmpty + i), (uint32_t)csize); }
     ptx::mbar_init(BAR(kAccFull), 1);
     ptx::mbar_init(BAR(kAccEmpty), 4);
+    sched::init(BAR(kSF), BAR(kSE), 6);  // consumers: the producer thread, the MMA warp, 4 epilogue warps
     ptx::fence_mbar_init();
   }
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmap_x); ptx::prefetch_tmap(&tmap_dy); }
@@ -124,12 +141,21 @@ __global__ void __launch_bounds__(256, 1)
     }
   };
   const int num_items_all = (CL && p.rep) ? p.gchunks[0] + p.gchunks[1] : num_items;
+  // k-th item of this CTA (cluster): static round-robin, or from the scheduler warp (umma.cuh, namespace sched)
+  const bool dyn = !CL && p.sched != nullptr;
+  auto static_item = [&](uint32_t k) -> int {
+    const int it = item0 + (int)k * item_step;
+    return it < num_items_all ? it : -1;
+  };
+  if (warp == 3 && dyn && lane == 0) sched::run(BAR(kSF), BAR(kSE), sched_slots, p.sched, num_items_all);
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t use = 0;
       const int x_planes = p.cin_m / 8;
-      for (int item = item0; item < num_items_all; item += item_step) {
+      for (uint32_t ik = 0;; ++ik) {
+        const int item = dyn ? sched::next_lane(BAR(kSF), BAR(kSE), sched_slots, ik) : static_item(ik);
+        if (item < 0) break;
         int pass, t0, t1;
         decode_item(item, pass, t0, t1);
         int mh, g, jg, kw0, kw1;
@@ -180,7 +206,9 @@ __global__ void __launch_bounds__(256, 1)
     const uint32_t b_row16 = (uint32_t)(p.dyp * kW2RowBytes) >> 4;  // one h row of the dY tile, 16-byte units
     const uint32_t npad = (uint32_t)p.npad;
     uint32_t use = 0, iuse = 0;
-    for (int item = item0; item < num_items_all; item += item_step, ++iuse) {
+    for (;; ++iuse) {
+      const int item = dyn ? sched::next(BAR(kSF), BAR(kSE), sched_slots, iuse, lane) : static_item(iuse);
+      if (item < 0) break;
       int pass, t0, t1;
       decode_item(item, pass, t0, t1);
       int mh, g, jg, kw0, kw1;
@@ -254,7 +282,9 @@ __global__ void __launch_bounds__(256, 1)
     const int qplane = row / p.cin_m, ci_local = row % p.cin_m;
     const int cw = 8 * p.dyp;  // channels per stacked kh group
     uint32_t iuse = 0;
-    for (int item = item0; item < num_items_all; item += item_step, ++iuse) {
+    for (;; ++iuse) {
+      const int item = dyn ? sched::next(BAR(kSF), BAR(kSE), sched_slots, iuse, lane) : static_item(iuse);
+      if (item < 0) break;
       int pass, t0_, t1_;
       decode_item(item, pass, t0_, t1_);
       int mh, g, jg, kw0, kw1;
@@ -389,6 +419,7 @@ int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin
     p.tiles_per_chunk = (p.total_tiles + chunks - 1) / chunks;
     p.chunks = (p.total_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
     p.csize = csize;
+    p.sched = nullptr;
     p.balance = (csize == 2 && p.passes_per_group == 2 && p.jgroups == 1 && kw_taps == 5 && p.tiles_per_chunk >= 4) ? 1 : 0;
     // kw-replicated leftover plane (32 input channels: 4 planes per M block, kd groups {0..3}, {4}): group 1 then costs
     // 1 MMA per row and rank against 2.5 for group 0, and the clusters are shared out in that proportion
@@ -431,6 +462,7 @@ int launch_wgrad_v2(const msb_tensor& x, const msb_tensor& dy, int cout, int cin
   p.csize = 1;
   p.balance = 0;
   p.rep = 0;
+  p.sched = g_dynamic_tiles_wg2 ? g_sched_wg2_ptr : nullptr;
   p.gchunks[0] = p.gchunks[1] = p.gtpc[0] = p.gtpc[1] = 0;
   const int items = p.num_passes * p.chunks;
   const int grid = items < kNumSMs ? items : kNumSMs;

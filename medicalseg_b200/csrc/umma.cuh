@@ -172,4 +172,59 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_ma
 }
 
 }  // namespace ptx
+
+// ---- dynamic tile scheduler for the persistent tensor-core kernels ------------------------------------------------
+// Static round-robin (item = blockIdx.x + k * gridDim.x) makes the makespan of a persistent grid the finish time of
+// its LAST-STARTED CTA: when NCCL's all-reduce CTAs hold some SMs at launch (data-parallel step),
+// the CTAs that wanted those SMs start late and still have their full share of tiles to do.  With the scheduler one
+// otherwise idle warp fetches item numbers from a global atomic counter and hands them to the role warps through a
+// small shared-memory ring (mbarrier full / empty pairs), so late CTAs simply take fewer tiles.  The first item stays
+// static (no atomic latency before the first TMA), the counter pair {next, done} resets itself: the CTA that finishes
+// last writes zeros (every CTA's final fetch precedes its `done` increment).
+namespace sched {
+constexpr int kDepth = 4;
+
+__device__ __forceinline__ void init(uint32_t full0, uint32_t empty0, uint32_t consumer_warps) {  // one thread
+  for (int i = 0; i < kDepth; ++i) {
+    ptx::mbar_init(full0 + 8u * i, 1);
+    ptx::mbar_init(empty0 + 8u * i, consumer_warps);
+  }
+}
+// one lane of the scheduler warp
+__device__ __forceinline__ void run(uint32_t full0, uint32_t empty0, volatile int* slots, unsigned int* counters,
+                                    int num_items) {
+  const int grid = (int)gridDim.x;
+  for (uint32_t k = 0;; ++k) {
+    const uint32_t s = k % kDepth, ph = (k / kDepth) & 1u;
+    ptx::mbar_wait(empty0 + 8u * s, ph ^ 1u);
+    int item = k == 0 ? (int)blockIdx.x : grid + (int)atomicAdd(counters, 1u);
+    if (item >= num_items) item = -1;
+    slots[s] = item;
+    ptx::mbar_arrive(full0 + 8u * s);  // release: the slot write is visible to the waiters
+    if (item < 0) break;
+  }
+  __threadfence();
+  if (atomicAdd(counters + 1, 1u) == (unsigned int)grid - 1u) {  // last CTA: nobody fetches any more
+    atomicExch(counters, 0u);
+    atomicExch(counters + 1, 0u);
+  }
+}
+// every lane of a consumer warp; returns -1 when the work is exhausted
+__device__ __forceinline__ int next(uint32_t full0, uint32_t empty0, const volatile int* slots, uint32_t k, int lane) {
+  const uint32_t s = k % kDepth, ph = (k / kDepth) & 1u;
+  ptx::mbar_wait(full0 + 8u * s, ph);
+  const int item = slots[s];
+  __syncwarp();
+  if (lane == 0) ptx::mbar_arrive(empty0 + 8u * s);
+  return item;
+}
+// the same for a role that runs on a single thread (TMA producers written under `if (lane == 0)`)
+__device__ __forceinline__ int next_lane(uint32_t full0, uint32_t empty0, const volatile int* slots, uint32_t k) {
+  const uint32_t s = k % kDepth, ph = (k / kDepth) & 1u;
+  ptx::mbar_wait(full0 + 8u * s, ph);
+  const int item = slots[s];
+  ptx::mbar_arrive(empty0 + 8u * s);
+  return item;
+}
+}  // namespace sched
 }  // namespace msb

@@ -19,6 +19,7 @@ BatchNorm statistics: `VNet(sync_bn=True)` shares them across ranks like the ref
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -92,6 +93,10 @@ class DistributedGradReducer:
     def attach(self, model):
         model.grad_ready_hook = self.on_ready
         model.stat_all_reduce = self.all_reduce_
+        if self.world > 1 and self.flat_grad.is_cuda and os.environ.get("MSB_TILE_SCHEDULER", "1") != "0":
+            # NCCL's CTAs share the SMs with the persistent conv grids: let late CTAs take fewer tiles (umma.cuh)
+            from . import _lib
+            _lib.call("msb_set_tile_scheduler", 1)
         if self.comm is not None and self.stat_comm is None and getattr(model, "sync_bn", False):
             # SyncBatchNorm sums run on the COMPUTE stream while gradient buckets are in flight on the side stream: one
             # NCCL communicator must not be used from two streams concurrently, so the statistics get their own

@@ -660,3 +660,85 @@ def test_trilinear_resize_and_adjoint(small, big):
     lhs = float((out.double() * g.double()).sum())
     rhs = float((x.detach().double() * dx.double()).sum())
     assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+
+
+def test_dynamic_tile_scheduler_matches_static_assignment():
+    """msb_set_tile_scheduler(1): the persistent kernels fetch tiles from a self-resetting atomic counter (used by the
+    data-parallel step, where NCCL's CTAs displace some conv CTAs).  Forward / dgrad and the strided convs must be
+    bit-identical to the static round-robin, the weight gradients equal up to the order of their f32 atomics; every
+    call is repeated to prove that the counters reset themselves."""
+    ops, B8 = _imp()
+    from medicalseg_b200 import _lib
+    torch.manual_seed(31)
+    n = 2
+
+    def fwd_case(c, dims):
+        x = B8.from_ncdhw(torch.randn(n, c, *dims, device="cuda"), torch.bfloat16)
+        w = torch.randn(c, c, 5, 5, 5, device="cuda") * 0.02
+        cp = ops.k5_out_pad(c)
+        packed = torch.empty(ops.k5_packed_bytes(c, cp), dtype=torch.uint8, device="cuda")
+        ops.k5_pack(w, packed, c, c, 0, c, cp)
+        bias = torch.randn(c, device="cuda")
+
+        def run():
+            out = B8(n, c, dims, torch.bfloat16, device="cuda", zero=True)
+            sums = torch.zeros(2 * c, dtype=torch.float64, device="cuda")
+            ops.k5_fwd(x, packed, bias, c, out, False, None, 1, sums)
+            return out.buf.clone(), sums
+        return run
+
+    def wgrad_case(c, dims):
+        x = B8.from_ncdhw(torch.randn(n, c, *dims, device="cuda"), torch.bfloat16)
+        dy = B8.from_ncdhw(torch.randn(n, c, *dims, device="cuda"), torch.bfloat16)
+
+        def run():
+            dw = torch.zeros(125 * c * c, device="cuda")
+            ops.k5_wgrad_tm(x, dy, dw, None, c, c)
+            return dw, None
+        return run
+
+    def k2_case(scatter, accumulate=False):
+        a, b, big, small = 32, 16, (24, 32, 32), (12, 16, 16)
+        w = torch.randn(a, b, 2, 2, 2, device="cuda") * 0.1
+        if scatter:
+            x = B8.from_ncdhw(torch.randn(n, a, *small, device="cuda"), torch.bfloat16)
+            packed = torch.empty(ops.k2s2_packed_bytes(a, 16), dtype=torch.uint8, device="cuda")
+            ops.k2s2_pack(w, packed, a, b, 1, a, 16)
+            base = torch.randn(n, b, *big, device="cuda")
+
+            def run():
+                out = B8.from_ncdhw(base, torch.bfloat16)
+                ops.k2s2_scatter(x, packed, None, b, out, accumulate, 1, None)
+                return out.buf.clone(), None
+        else:
+            x = B8.from_ncdhw(torch.randn(n, b, *big, device="cuda"), torch.bfloat16)
+            packed = torch.empty(ops.k2s2_packed_bytes(b, 32), dtype=torch.uint8, device="cuda")
+            ops.k2s2_pack(w, packed, b, a, 0, b, 32)
+
+            def run():
+                out = B8(n, a, small, torch.bfloat16, device="cuda", zero=True)
+                ops.k2s2_gather(x, packed, None, a, out, 1, None)
+                return out.buf.clone(), None
+        return run
+
+    cases = [("fwd32 multi-item", fwd_case(32, (24, 64, 64)), True), ("fwd64", fwd_case(64, (8, 32, 40)), True),
+             ("fwd128 small", fwd_case(128, (4, 16, 16)), True),
+             ("wgrad2 64", wgrad_case(64, (8, 32, 32)), False), ("wgrad2 32 clustered", wgrad_case(32, (16, 64, 64)), False),
+             ("wgrad per-tap 128", wgrad_case(128, (4, 16, 32)), False),
+             ("k2 gather", k2_case(False), True), ("k2 scatter", k2_case(True), True),
+             ("k2 scatter-accumulate", k2_case(True, True), True)]
+    try:
+        for name, run, exact in cases:
+            _lib.call("msb_set_tile_scheduler", 0)
+            ref, ref_s = run()
+            _lib.call("msb_set_tile_scheduler", 1)
+            for rep in range(3):
+                got, got_s = run()
+                if exact:
+                    assert torch.equal(got, ref), (name, rep)
+                else:
+                    assert rel(got, ref) <= 1e-5, (name, rep)
+                if ref_s is not None:
+                    assert float((got_s - ref_s).abs().max()) <= 1e-9 * float(ref_s.abs().max() + 1), (name, rep)
+    finally:
+        _lib.call("msb_set_tile_scheduler", 0)
