@@ -353,8 +353,7 @@ def run_vnet(args, cfg):
             "launch_mode": "cuda-graph replay (1 cudaGraphLaunch/step%s)" % (", NCCL all-reduces inside the graph"
                                                                              if world > 1 else "")
                            if use_graph else "eager (python -> C ABI)",
-            "tile_scheduler": "dynamic (atomic counter)" if (args.tile_scheduler == "dynamic" or
-                                                              (args.tile_scheduler == "auto" and world > 1)) else "static",
+            "tile_scheduler": "dynamic (atomic counter)" if args.tile_scheduler == "dynamic" else "static",
             "clocks": clocks,
             "roofline": roof,
         }
@@ -612,7 +611,7 @@ def main():
     ap.add_argument("--sync-bn", action="store_true", help="SyncBatchNorm over all ranks (reference default at N>1)")
     ap.add_argument("--bucket-mb", type=float, default=8.0, help="gradient all-reduce bucket size (N>1)")
     ap.add_argument("--tile-scheduler", choices=["auto", "static", "dynamic"], default="auto",
-                    help="persistent-kernel tile assignment: auto = dynamic (atomic counter) at N>1, static at N=1")
+                    help="persistent-kernel tile assignment: auto = static (dynamic = atomic counter, measured no gain)")
     ap.add_argument("--check", action="store_true", help="N>=2: data-parallel equivalence checks instead of timing")
     args = ap.parse_args()
     if args.config == "preprocess":

@@ -738,7 +738,7 @@ def test_dynamic_tile_scheduler_matches_static_assignment():
                     assert torch.equal(got, ref), (name, rep)
                 else:
                     assert rel(got, ref) <= 1e-5, (name, rep)
-                if ref_s is not None:
-                    assert float((got_s - ref_s).abs().max()) <= 1e-9 * float(ref_s.abs().max() + 1), (name, rep)
+                if ref_s is not None:  # per-CTA f32 partial sums group different tiles: last bits of the f64 totals move
+                    assert float((got_s - ref_s).abs().max()) <= 1e-6 * float(ref_s.abs().max() + 1), (name, rep)
     finally:
         _lib.call("msb_set_tile_scheduler", 0)
