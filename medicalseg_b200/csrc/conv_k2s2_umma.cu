@@ -36,14 +36,8 @@ namespace msb {
 
 constexpr int kK2TileW = 8, kK2TileH = 16;
 constexpr int kK2ABytes = 2 * kK2TileH * kK2TileW * 16;  // [2 c8][16 h][8 w][8 ch] bf16 = 4 KB
-constexpr int kK2BBytesMax = 256 * 32;                   // [2 k8][N <= 256][8 ch] bf16
-constexpr int kK2StageBytes = kK2ABytes + kK2BBytesMax;
-constexpr int kK2Stages = 8;
-constexpr int kK2EpiWarps = 8;   // 2 warpgroups x 4 TMEM lane quadrants
-constexpr int kK2EpiGroups = kK2EpiWarps / 4;
-constexpr int kK2MaxIt = 16 / kK2EpiGroups;  // 16-column blocks per warpgroup and item (N <= 256)
-constexpr int kK2Threads = 128 + 32 * kK2EpiWarps;  // w0 TMA, w1 MMA, w2 TMEM alloc, w3 idle, w4-11 epilogue
-constexpr int kK2SmemBytes = kK2Stages * kK2StageBytes + 1024 + kK2EpiWarps * 2 * 256 * 4 + 128;
+// shared memory of a kernel variant: stages x (A tile + [2 k8][N <= ACCN][8 ch] weights) + barriers + BN statistics
+constexpr int k2_smem_bytes(int ew, int st, int accn) { return st * (kK2ABytes + accn * 32) + 1024 + ew * 2 * 256 * 4 + 128; }
 
 struct K2Params {
   int mode;              // 0 gather, 1 scatter
@@ -83,8 +77,16 @@ int msb_set_tile_scheduler_k2s2(int dynamic) {
   return MSB_OK;
 }
 
-__global__ void __launch_bounds__(kK2Threads, 1)
+// EW epilogue warps, ST TMA stages, ACCN TMEM columns per accumulator (two accumulators are allocated), ACC = the
+// accumulate form.  <8, 8, 256, *>: one CTA per SM, any N <= 256.  <4, 4, 128, false>: the store-only forms with
+// N <= 128 run TWO CTAs per SM (256 TMEM columns, 41 KB of shared memory, 256 threads each): the kernel is latency
+// bound (ncu: DRAM 21-25 % of peak, SMs 18-35 % busy with one CTA per SM), a second independent TMA -> MMA -> epilogue
+// chain per SM doubles what is in flight.
+template <int EW, int ST, int ACCN, bool ACC>
+__global__ void __launch_bounds__(128 + 32 * EW, ACCN == 128 ? 2 : 1)
     conv_k2s2_kernel(const __grid_constant__ CUtensorMap tmap_x, const K2Params p) {
+  constexpr int kK2Stages = ST, kK2EpiWarps = EW, kK2EpiGroups = EW / 4, kK2MaxIt = (ACCN / 16) / (EW / 4);
+  constexpr int kK2StageBytes = kK2ABytes + ACCN * 32, kK2Threads = 128 + 32 * EW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* stage_smem = smem;
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(kK2Threads, 1)
     tap_off[tap] = (kd * p.bh + kh) * p.bw + kwl;
   }
   if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tmap_x);
-  if (warp == 2) ptx::tmem_alloc<512>(ptx::smem_u32(tmem_slot));
+  if (warp == 2) ptx::tmem_alloc<2 * ACCN>(ptx::smem_u32(tmem_slot));
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(kK2Threads, 1)
       const uint32_t as = iuse & 1, aph = (iuse >> 1) & 1;
       ptx::mbar_wait(BAR(kAccEmpty + as), aph ^ 1);
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_u + as * 256u;
+      const uint32_t d_tmem = tmem_u + as * (uint32_t)ACCN;
       for (int ki = 0; ki < kiters; ++ki, ++use) {
         const uint32_t s = use % kK2Stages, ph = (use / kK2Stages) & 1;
         ptx::mbar_wait(BAR(kFull + s), ph);
@@ -250,8 +252,8 @@ __global__ void __launch_bounds__(kK2Threads, 1)
         return (ok && tap_ok && c8 < p.out_c8) ? out_n + ((int64_t)c8 * So + v) * 8 : nullptr;
       };
       // accumulate: request every `old` vector of this item now - the loads fly while the MMAs of the item run
-      uint4 oldv[kK2MaxIt][2];
-      if (p.accumulate) {
+      uint4 oldv[ACC ? kK2MaxIt : 1][2];
+      if (ACC) {
 #pragma unroll
         for (int it = 0; it < kK2MaxIt; ++it) {
           const int cb = wg + kK2EpiGroups * it;
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(kK2Threads, 1)
       }
       ptx::mbar_wait(BAR(kAccFull + as), aph);
       ptx::tc_fence_after();
-      const uint32_t t_base = tmem_base + as * 256u + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_base = tmem_base + as * (uint32_t)ACCN + ((uint32_t)(q * 32) << 16);
 #pragma unroll
       for (int it = 0; it < kK2MaxIt; ++it) {
         const int cb = wg + kK2EpiGroups * it;
@@ -297,8 +299,9 @@ __global__ void __launch_bounds__(kK2Threads, 1)
           __nv_bfloat16* dst = k == 0 ? dst0 : dst1;
           uint32_t pk[4] = {0u, 0u, 0u, 0u};
           if (dst != nullptr) {
-            if (p.accumulate) {
-              const uint32_t o[4] = {oldv[it][k].x, oldv[it][k].y, oldv[it][k].z, oldv[it][k].w};
+            if (ACC) {
+              const uint32_t o[4] = {oldv[ACC ? it : 0][k].x, oldv[ACC ? it : 0][k].y, oldv[ACC ? it : 0][k].z,
+                                     oldv[ACC ? it : 0][k].w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 acc[k * 8 + 2 * i] += __uint_as_float(o[i] << 16);
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(kK2Threads, 1)
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<512>(tmem_base);
+    ptx::tmem_dealloc<2 * ACCN>(tmem_base);
   }
 }
 
@@ -427,7 +430,9 @@ static bool k2_geom(int mode, msb_dim3 kernel, msb_dim3 stride, int cpad, K2Geom
   g->ntap_n = kernel.d * kernel.h * (g->wmode == 1 ? 1 : kernel.w);
   g->ktaps = g->wmode == 1 ? kernel.w : 1;
   int tg = 1;
-  while (tg * 2 <= g->ntap_n && tg * 2 * cpad <= 256) tg *= 2;
+  // N = tg * cpad <= 128: every scatter then fits the 128-column accumulators of the two-CTAs-per-SM variant (wider
+  // outputs fall back to one tap per MMA)
+  while (tg * 2 <= g->ntap_n && tg * 2 * cpad <= 128) tg *= 2;
   g->tg = tg;
   g->tap_groups = (g->ntap_n + tg - 1) / tg;
   return true;
@@ -471,13 +476,26 @@ static int launch_k2s2(int mode, const msb_tensor& x, const void* packed, const 
     if ((rc = make_b8_tmap(&tmap, x, n, sd, kK2TileW, kK2TileH, 1, 2))) return rc;
   }
   const int items = n * sd.d * p.tiles_h * p.tiles_w * p.tap_groups;
-  const int grid = items < kNumSMs ? items : kNumSMs;
   static bool attr_set = false;
   if (!attr_set) {
-    MSB_CUDA_OK(cudaFuncSetAttribute(conv_k2s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2SmemBytes));
+    MSB_CUDA_OK(cudaFuncSetAttribute(conv_k2s2_kernel<8, 8, 256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     k2_smem_bytes(8, 8, 256)));
+    MSB_CUDA_OK(cudaFuncSetAttribute(conv_k2s2_kernel<8, 8, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     k2_smem_bytes(8, 8, 256)));
+    MSB_CUDA_OK(cudaFuncSetAttribute(conv_k2s2_kernel<4, 4, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     k2_smem_bytes(4, 4, 128)));
     attr_set = true;
   }
-  MSB_LAUNCH_PDL(conv_k2s2_kernel, dim3(grid), dim3(kK2Threads), kK2SmemBytes, st, tmap, p);
+  if (!accumulate && p.nmma <= 128 && !(g_debug_flags[6] & 64)) {  // store-only, narrow N: two CTAs per SM
+    const int grid = items < 2 * kNumSMs ? items : 2 * kNumSMs;
+    MSB_LAUNCH_PDL((conv_k2s2_kernel<4, 4, 128, false>), dim3(grid), dim3(128 + 32 * 4), k2_smem_bytes(4, 4, 128), st, tmap, p);
+  } else {
+    const int grid = items < kNumSMs ? items : kNumSMs;
+    if (accumulate)
+      MSB_LAUNCH_PDL((conv_k2s2_kernel<8, 8, 256, true>), dim3(grid), dim3(128 + 32 * 8), k2_smem_bytes(8, 8, 256), st, tmap, p);
+    else
+      MSB_LAUNCH_PDL((conv_k2s2_kernel<8, 8, 256, false>), dim3(grid), dim3(128 + 32 * 8), k2_smem_bytes(8, 8, 256), st, tmap, p);
+  }
   return MSB_OK;
 }
 
