@@ -139,8 +139,7 @@ def train(model, train_dataset, val_dataset=None, optimizer=None, save_dir="outp
     # the whole step - at world > 1 including the bucketed NCCL all-reduces - into ONE CUDA graph.  Needs fixed batch
     # shapes; a trailing short batch falls back to the eager step.
     graphed = None
-    if (to_static_training and reducer.capturable and not getattr(model, "deep_supervision", False)
-            and iters - start_iter >= 2):
+    if to_static_training and reducer.capturable and iters - start_iter >= 2:
         from .graph import GraphedTrainStep
         # the capture's warm-up steps are real optimizer steps on the first batch: never run past `iters`
         graphed = GraphedTrainStep(model, losses, optimizer, reducer=reducer, warmup=min(3, iters - start_iter - 1))

@@ -48,11 +48,16 @@ class GraphedTrainStep:
         # - would make the engine wait on uncaptured work: cudaErrorStreamCaptureIsolation).
         with torch.no_grad():
             logits = m._forward(self.s_img, record=True)
-        leaf = logits.detach().requires_grad_(True)
-        loss_list, dice = L.loss_computation([leaf], self.s_lab, self.losses)
+            extra = list(m._extra_logits) if getattr(m, "deep_supervision", False) else []
+        # VNetDeepSup: [out, d1, d2, d3] (vnet_deepsup.py:256-275) - one leaf per output, the heads' gradients enter the
+        # trunk's backward through the same hooks the eager autograd function uses
+        leaves = [t.detach().requires_grad_(True) for t in [logits] + extra]
+        loss_list, dice = L.loss_computation(leaves, self.s_lab, self.losses)
         loss = sum(loss_list)
         loss.backward()
-        m._backward(leaf.grad)
+        if extra:
+            m._aux_backward_begin(tuple(l.grad for l in leaves[1:]))
+        m._backward(leaves[0].grad)
         if self.reducer is not None:
             self.reducer.wait()  # joins the all-reduce side stream (world > 1) and resets the bucket planner
         opt.step()
@@ -67,9 +72,6 @@ class GraphedTrainStep:
                                "ncclAllReduce calls a capture can record); torch.distributed work objects are not "
                                "capturable (see the module docstring)")
         m, opt = self.model, self.optimizer
-        if getattr(m, "deep_supervision", False):
-            raise NotImplementedError("GraphedTrainStep captures the single-output VNet step; VNetDeepSup (four outputs) "
-                                      "runs the eager step")
         dev = m.device
         self.s_img = torch.empty_like(images, device=dev)
         self.s_lab = torch.empty_like(labels, device=dev, dtype=torch.int32)

@@ -140,12 +140,12 @@ def test_train_entry_point_deep_supervision_and_device_transforms(tmp_path):
     cfg = os.path.join(ROOT, "configs/synthetic/vnetdeepsup_synthetic_64.yml")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "train.py"), "--config", cfg, "--iters", "6", "--log_iters", "2",
                         "--save_interval", "6", "--do_eval", "--save_dir", str(tmp_path / "out"), "--seed", "0",
-                        "--to_static_training"],  # falls back to the eager step for the four-output model
+                        "--to_static_training"],  # the four-output step is captured into one CUDA graph as well
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "[EVAL] #Images: 2, Dice:" in r.stdout
     losses = [float(l.split("loss: ")[1].split(",")[0]) for l in r.stdout.splitlines() if "[TRAIN]" in l]
-    assert len(losses) == 3 and losses[-1] < losses[0]
+    assert len(losses) >= 2 and losses[-1] < losses[0]  # (the capture's 3 warm-up steps are not logged)
     root = tmp_path / "ds"
     root.mkdir()
     rng = np.random.default_rng(0)

@@ -145,15 +145,18 @@ def test_product_path_rejects_cpu_tensors():
         L.DiceLoss()(torch.rand(1, 2, 4, 4, 4), torch.zeros(1, 4, 4, 4, dtype=torch.int32))
 
 
-def test_graphed_train_step_matches_eager():
+@pytest.mark.parametrize("deepsup", [False, True])
+def test_graphed_train_step_matches_eager(deepsup):
     """GraphedTrainStep (whole step = one CUDA graph, LR read from device memory, weight re-packing forked onto a side
     stream inside the capture) performs the same optimizer steps as the eager loop: 2 eager warm-up steps + 3 replays
     vs 5 eager steps on the same batch with the same (persistent) dropout masks.  Tolerance: the f32 atomics of the
     weight-gradient kernels make the last bits order dependent -> parameters within 2e-3 of the largest |param| change."""
     from oracle import vnet_oracle as vo
-    from medicalseg_b200.models import VNet as V, losses as L
+    from medicalseg_b200.models import VNet, VNetDeepSup, losses as L
     from medicalseg_b200.optimizer import Momentum as M, PolynomialDecay as P
     from medicalseg_b200.graph import GraphedTrainStep
+    V = VNetDeepSup if deepsup else VNet  # four outputs x 0.25 (vnetdeepsup_mri_spine_seg_512_512_12_15k.yml:12-20)
+    nl = 4 if deepsup else 1
     img, lab = vo.synthetic_batch(2, (32, 32, 32), 2, seed=3)
     masks = vo.make_dropout_masks(2, seed=5)
     img, lab = img.cuda(), lab.cuda()
@@ -162,7 +165,8 @@ def test_graphed_train_step_matches_eager():
         m = V(num_classes=2, compute_dtype="bf16", seed=0)
         m.train()
         m.set_dropout_masks(masks, persistent=True)
-        losses = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1])], "coef": [1]}
+        losses = {"types": [L.MixedLoss([L.CrossEntropyLoss(), L.DiceLoss()], [1, 1]) for _ in range(nl)],
+                  "coef": [1.0 / nl] * nl}
         opt = M(P(0.01, 100), m.parameters(), 0.9, 1e-4)
         return m, losses, opt
 
