@@ -102,10 +102,16 @@ __global__ void __launch_bounds__(kLossThreads, CMAX > 8 ? 2 : 1)
   // class.  The label-dependent sums (I_c, count_c) touch ONE class per voxel, so they live in a per-thread column of
   // shared memory indexed by the label ([class][thread]: conflict free), and the class weights are read from shared
   // memory (broadcast).
-  __shared__ float s_hit[2][CMAX][kLossThreads];
+  // (static shared memory ends at 48 KB: beyond 20 classes the label sums go back to registers)
+  constexpr bool kSmemHit = CMAX <= 20;
+  __shared__ float s_hit[2][kSmemHit ? CMAX : 1][kSmemHit ? kLossThreads : 1];
   __shared__ float s_w[CMAX];
+  float r_hit[2][kSmemHit ? 1 : CMAX];
 #pragma unroll
-  for (int k = 0; k < CMAX; ++k) { s_hit[0][k][threadIdx.x] = 0.f; s_hit[1][k][threadIdx.x] = 0.f; }
+  for (int k = 0; k < CMAX; ++k) {
+    if (kSmemHit) { s_hit[0][k][threadIdx.x] = 0.f; s_hit[1][k][threadIdx.x] = 0.f; }
+    else { r_hit[0][kSmemHit ? 0 : k] = 0.f; r_hit[1][kSmemHit ? 0 : k] = 0.f; }
+  }
   if (threadIdx.x < CMAX) s_w[threadIdx.x] = threadIdx.x < c ? __ldg(class_w + threadIdx.x) : 0.f;
   __syncthreads();
   float psq[CMAX];
@@ -122,7 +128,14 @@ __global__ void __launch_bounds__(kLossThreads, CMAX > 8 ? 2 : 1)
       if (k < c) {
         const float p = 1.f / (1.f + expf(-z[k]));
         psq[k] += p * p;
-        if (y == k) { zy = z[k]; s_hit[0][k][threadIdx.x] += p; s_hit[1][k][threadIdx.x] += 1.f; }
+        if (kSmemHit) {
+          if (y == k) { zy = z[k]; s_hit[0][k][threadIdx.x] += p; s_hit[1][k][threadIdx.x] += 1.f; }
+        } else {
+          const bool hit = (y == k);
+          if (hit) zy = z[k];
+          r_hit[0][kSmemHit ? 0 : k] += hit ? p : 0.f;
+          r_hit[1][kSmemHit ? 0 : k] += hit ? 1.f : 0.f;
+        }
       }
     }
     if (y != ignore_index && y >= 0 && y < c) {
@@ -136,9 +149,9 @@ __global__ void __launch_bounds__(kLossThreads, CMAX > 8 ? 2 : 1)
   float acc[3 * CMAX + 2];
 #pragma unroll
   for (int k = 0; k < CMAX; ++k) {
-    acc[k] = s_hit[0][k][threadIdx.x];
+    acc[k] = kSmemHit ? s_hit[0][kSmemHit ? k : 0][kSmemHit ? threadIdx.x : 0] : r_hit[0][kSmemHit ? 0 : k];
     acc[CMAX + k] = psq[k];
-    acc[2 * CMAX + k] = s_hit[1][k][threadIdx.x];
+    acc[2 * CMAX + k] = kSmemHit ? s_hit[1][kSmemHit ? k : 0][kSmemHit ? threadIdx.x : 0] : r_hit[1][kSmemHit ? 0 : k];
   }
   acc[3 * CMAX] = ce_num;
   acc[3 * CMAX + 1] = ce_den;
