@@ -1407,6 +1407,10 @@ int msb_conv_k5_pack_tm(const float* w_tm, void* packed, int cout, int cin, int 
 
 int msb_conv_k5_out_pad(int cout_view);
 
+// J = TD = 8 stacks cost 736 clk per 8 output planes, J = TD = 4 stacks 416 clk per 4 (measured for N_pad = 32, see the
+// dispatch below): the deep stack pays when it does not round the depth up by more than that ratio
+static inline bool deep_stack_pays(int d) { return ((d + 7) / 8) * 736 <= ((d + 3) / 4) * 416; }
+
 static int conv_k5_fwd_impl(const char* who, msb_tensor x, const void* packed, const float* bias, int cout,
                            msb_tensor out, int n, msb_dim3 dims, int accumulate, const float* ch_scale, int groups,
                            double* sums, int kw_taps, void* stream, void* workspace = nullptr,
@@ -1466,11 +1470,14 @@ static int conv_k5_fwd_impl(const char* who, msb_tensor x, const void* packed, c
   switch (npad_sel) {
     // deep stacks (J = TD = 8) amortise the triangular ends of the tap band best (736 clk per 8 planes vs 416 per 4
     // for N_pad = 32) and re-fetch less halo ((TD+4)/TD); shallow volumes keep TD = 4
+    // ... unless the depth wastes planes: d = 12 (MRISpineSeg 512x512x12) is two 8-plane blocks with 4 idle planes
+    // (2 x 736 clk per tile column) but three full 4-plane blocks (3 x 416 clk): pick the cheaper block count
     case 16:
-      if (stack && dims.d >= 8) return launch_fwd<16, 8, 8>(x, dims, p, st);
+      if (stack && dims.d >= 8 && deep_stack_pays(dims.d)) return launch_fwd<16, 8, 8>(x, dims, p, st);
       return stack ? launch_fwd<16, 4, 4>(x, dims, p, st) : launch_fwd<16, 4>(x, dims, p, st);
     case 32:
-      if (stack && dims.d >= 8 && g_debug_flags[3] != 2) return launch_fwd<32, 8, 8>(x, dims, p, st);
+      if (stack && dims.d >= 8 && g_debug_flags[3] != 2 && deep_stack_pays(dims.d))
+        return launch_fwd<32, 8, 8>(x, dims, p, st);
       return stack ? launch_fwd<32, 4, 4>(x, dims, p, st) : launch_fwd<32, 4>(x, dims, p, st);
     case 64: return stack ? launch_fwd<64, 4, 4>(x, dims, p, st) : launch_fwd<64, 4>(x, dims, p, st);
     case 128: return launch_fwd<128, 2>(x, dims, p, st);
