@@ -284,6 +284,15 @@ int msb_dice_ce_fwd(const float* logits, const int32_t* labels, const float* cla
                     int ignore_index, double* acc, void* stream);
 /* result f32 [2+C] = { ce, dice_loss, per_channel_dice[C] } */
 int msb_dice_ce_finalize(const double* acc, int c, float* result, void* stream);
+/* The same three calls with DiceLoss's constructor options (medicalseg/models/losses/dice_loss.py:36-43,64-65):
+ * dice_softmax != 0 normalises with softmax over the classes instead of the sigmoid (`sigmoid_norm=False`), dice_w
+ * (device f32 [C] or NULL) multiplies the per-class intersections (`weight`).  The plain names are these with (0, NULL). */
+int msb_dice_ce_fwd_ex(const float* logits, const int32_t* labels, const float* class_w, int n, int c, int64_t s,
+                       int ignore_index, int dice_softmax, double* acc, void* stream);
+int msb_dice_ce_finalize_ex(const double* acc, int c, const float* dice_w, float* result, void* stream);
+int msb_dice_ce_bwd_ex(const float* logits, const int32_t* labels, const float* class_w, const double* acc, int n,
+                       int c, int64_t s, int ignore_index, float coef_ce, float coef_dice, const float* coef_dev,
+                       const float* dice_w, int dice_softmax, float* dlogits, void* stream);
 /* Fused evaluation head (core/infer.py:79-92 argmax + core/val.py:101-118 loss behind out_tr.conv2, vnet.py:173-174):
  * logits = conv1x1(a) stay in registers.  a: B8 view (8, 16 or 32 channels, the first C live), w [C][C], b [C] or NULL.
  * Optional outputs (NULL = skip): pred int32 [N][S] (first maximum wins), acc double [3C+2] (+=, as msb_dice_ce_fwd;

@@ -84,6 +84,9 @@ SIGNATURES = {
     "msb_class_weight_finalize": (I, [P, D, I, P, P]),
     "msb_dice_ce_fwd": (I, [P, P, P, I, I, L, I, P, P]),
     "msb_dice_ce_finalize": (I, [P, I, P, P]),
+    "msb_dice_ce_fwd_ex": (I, [P, P, P, I, I, L, I, I, P, P]),
+    "msb_dice_ce_finalize_ex": (I, [P, I, P, P, P]),
+    "msb_dice_ce_bwd_ex": (I, [P, P, P, P, I, I, L, I, F, F, P, P, I, P, P]),
     "msb_eval_head": (I, [T, P, P, P, P, I, I, L, I, P, P, P, P]),
     "msb_dice_ce_bwd": (I, [P, P, P, P, I, I, L, I, F, F, P, P, P]),
     "msb_momentum_step": (I, [P, P, P, L, F, F, F, F, P]),

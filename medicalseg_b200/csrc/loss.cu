@@ -93,7 +93,7 @@ __global__ void class_weight_finalize_kernel(const double* __restrict__ psum, do
 template <int CMAX>
 __global__ void __launch_bounds__(kLossThreads, CMAX > 8 ? 2 : 1)
     dice_ce_fwd_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
-                       const float* __restrict__ class_w, int c, int64_t s, int ignore_index,
+                       const float* __restrict__ class_w, int c, int64_t s, int ignore_index, int dice_softmax,
                        double* __restrict__ out) {
   const int n = blockIdx.y;
   const int64_t v0 = (int64_t)blockIdx.x * kLossVoxPerBlock;
@@ -122,11 +122,18 @@ __global__ void __launch_bounds__(kLossThreads, CMAX > 8 ? 2 : 1)
     float z[CMAX];
     load_logits<CMAX>(logits, n, c, s, v, z);
     const int y = __ldg(labels + (int64_t)n * s + v);
+    const bool ce_on = y != ignore_index && y >= 0 && y < c;
+    // softmax statistics: needed by the cross-entropy term and by DiceLoss(sigmoid_norm=False) (dice_loss.py:41-43)
+    float m = 0.f, sum = 1.f, inv = 0.f;
+    if (ce_on || dice_softmax) {
+      m = logsumexp<CMAX>(z, c, sum);
+      inv = 1.f / sum;
+    }
     float zy = 0.f;
 #pragma unroll
     for (int k = 0; k < CMAX; ++k) {
       if (k < c) {
-        const float p = 1.f / (1.f + expf(-z[k]));
+        const float p = dice_softmax ? expf(z[k] - m) * inv : 1.f / (1.f + expf(-z[k]));
         psq[k] += p * p;
         if (kSmemHit) {
           if (y == k) { zy = z[k]; s_hit[0][k][threadIdx.x] += p; s_hit[1][k][threadIdx.x] += 1.f; }
@@ -138,9 +145,7 @@ __global__ void __launch_bounds__(kLossThreads, CMAX > 8 ? 2 : 1)
         }
       }
     }
-    if (y != ignore_index && y >= 0 && y < c) {
-      float sum;
-      const float m = logsumexp<CMAX>(z, c, sum);
+    if (ce_on) {
       const float wy = s_w[y];
       ce_num += wy * (m + logf(sum) - zy);
       ce_den += wy;
@@ -177,13 +182,15 @@ __global__ void __launch_bounds__(kLossThreads, CMAX > 8 ? 2 : 1)
   }
 }
 
-__global__ void dice_ce_finalize_kernel(const double* __restrict__ acc, int c, float* __restrict__ result) {
+__global__ void dice_ce_finalize_kernel(const double* __restrict__ acc, int c, const float* __restrict__ dice_w,
+                                        float* __restrict__ result) {
   if (threadIdx.x != 0) return;
   double mean = 0;
   for (int k = 0; k < c; ++k) {
     double den = acc[c + k] + acc[2 * c + k];
     if (den < 1e-6) den = 1e-6;
-    const double d = 2.0 * acc[k] / den;
+    const double wk = dice_w ? (double)dice_w[k] : 1.0;  // dice_loss.py:64-65: intersect = weight * intersect
+    const double d = 2.0 * wk * acc[k] / den;
     result[2 + k] = (float)d;
     mean += d;
   }
@@ -196,7 +203,7 @@ __global__ void __launch_bounds__(kLossThreads, CMAX > 8 ? 2 : 1)
     dice_ce_bwd_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
                        const float* __restrict__ class_w, const double* __restrict__ acc, int c, int64_t s,
                        int ignore_index, float coef_ce, float coef_dice, const float* __restrict__ coef_dev,
-                       float* __restrict__ dlogits) {
+                       const float* __restrict__ dice_w, int dice_softmax, float* __restrict__ dlogits) {
   const int n = blockIdx.y;
   if (coef_dev != nullptr) {
     coef_ce *= __ldg(coef_dev);
@@ -212,13 +219,14 @@ __global__ void __launch_bounds__(kLossThreads, CMAX > 8 ? 2 : 1)
     float wk = 0.f, a = 0.f, b = 0.f;
     if (k < c) {
       wk = __ldg(class_w + k);
+      const double dw = dice_w ? (double)__ldg(dice_w + k) : 1.0;
       const double inter = acc[k];
       double den = acc[c + k] + acc[2 * c + k];
       if (den < 1e-6) {
-        a = (float)(2.0 / 1e-6);
+        a = (float)(2.0 * dw / 1e-6);
       } else {
-        a = (float)(2.0 / den);
-        b = (float)(-4.0 * inter / (den * den));
+        a = (float)(2.0 * dw / den);
+        b = (float)(-4.0 * dw * inter / (den * den));
       }
     }
     w[k] = wk; ka[k] = a; kb[k] = b;
@@ -232,20 +240,42 @@ __global__ void __launch_bounds__(kLossThreads, CMAX > 8 ? 2 : 1)
     const int y = __ldg(labels + (int64_t)n * s + v);
     const bool ce_on = y != ignore_index && y >= 0 && y < c;
     float m = 0.f, inv = 0.f, f = 0.f;
-    if (ce_on) {
+    if (ce_on || dice_softmax) {
       float sum;
       m = logsumexp<CMAX>(z, c, sum);
       inv = 1.f / sum;
-      f = ce_scale * w[y];
     }
+    if (ce_on) f = ce_scale * w[y];
+    if (dice_softmax) {
+      // p = softmax(z): dL/dz_k = p_k (dL/dp_k - sum_j dL/dp_j p_j)
+      float dot = 0.f;
 #pragma unroll
-    for (int k = 0; k < CMAX; ++k) {
-      if (k < c) {
-        const float p = 1.f / (1.f + expf(-z[k]));
-        const float t = (y == k) ? 1.f : 0.f;
-        float g = dscale * (ka[k] * t + kb[k] * p) * p * (1.f - p);
-        if (ce_on) g += f * (expf(z[k] - m) * inv - t);
-        dlogits[((int64_t)n * c + k) * s + v] = g;
+      for (int k = 0; k < CMAX; ++k) {
+        if (k < c) {
+          const float p = expf(z[k] - m) * inv;
+          dot += dscale * (ka[k] * ((y == k) ? 1.f : 0.f) + kb[k] * p) * p;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k) {
+        if (k < c) {
+          const float p = expf(z[k] - m) * inv;
+          const float t = (y == k) ? 1.f : 0.f;
+          float g = p * (dscale * (ka[k] * t + kb[k] * p) - dot);
+          if (ce_on) g += f * (p - t);
+          dlogits[((int64_t)n * c + k) * s + v] = g;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k) {
+        if (k < c) {
+          const float p = 1.f / (1.f + expf(-z[k]));
+          const float t = (y == k) ? 1.f : 0.f;
+          float g = dscale * (ka[k] * t + kb[k] * p) * p * (1.f - p);
+          if (ce_on) g += f * (expf(z[k] - m) * inv - t);
+          dlogits[((int64_t)n * c + k) * s + v] = g;
+        }
       }
     }
   }
@@ -439,20 +469,42 @@ int msb_class_weight_finalize(const double* psum, double count, int c, float* we
   return MSB_OK;
 }
 
-int msb_dice_ce_fwd(const float* logits, const int32_t* labels, const float* class_w, int n, int c, int64_t s,
-                    int ignore_index, double* acc, void* stream) {
+int msb_dice_ce_fwd_ex(const float* logits, const int32_t* labels, const float* class_w, int n, int c, int64_t s,
+                       int ignore_index, int dice_softmax, double* acc, void* stream) {
   MSB_REQUIRE(logits && labels && class_w && acc && n > 0 && c > 0 && c <= 32 && s > 0,
               "msb_dice_ce_fwd: needs 1 <= C <= 32");
   const dim3 grid((unsigned)((s + kLossVoxPerBlock - 1) / kLossVoxPerBlock), (unsigned)n);
   MSB_DISPATCH_CMAX(c, dice_ce_fwd_kernel<CMAX><<<grid, kLossThreads, 0, as_stream(stream)>>>(
-                           logits, labels, class_w, c, s, ignore_index, acc););
+                           logits, labels, class_w, c, s, ignore_index, dice_softmax, acc););
+  MSB_LAUNCH_OK();
+  return MSB_OK;
+}
+
+int msb_dice_ce_fwd(const float* logits, const int32_t* labels, const float* class_w, int n, int c, int64_t s,
+                    int ignore_index, double* acc, void* stream) {
+  return msb_dice_ce_fwd_ex(logits, labels, class_w, n, c, s, ignore_index, 0, acc, stream);
+}
+
+int msb_dice_ce_finalize_ex(const double* acc, int c, const float* dice_w, float* result, void* stream) {
+  MSB_REQUIRE(acc && result && c > 0 && c <= 32, "msb_dice_ce_finalize: bad arguments");
+  dice_ce_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>(acc, c, dice_w, result);
   MSB_LAUNCH_OK();
   return MSB_OK;
 }
 
 int msb_dice_ce_finalize(const double* acc, int c, float* result, void* stream) {
-  MSB_REQUIRE(acc && result && c > 0 && c <= 32, "msb_dice_ce_finalize: bad arguments");
-  dice_ce_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>(acc, c, result);
+  return msb_dice_ce_finalize_ex(acc, c, nullptr, result, stream);
+}
+
+int msb_dice_ce_bwd_ex(const float* logits, const int32_t* labels, const float* class_w, const double* acc, int n,
+                       int c, int64_t s, int ignore_index, float coef_ce, float coef_dice, const float* coef_dev,
+                       const float* dice_w, int dice_softmax, float* dlogits, void* stream) {
+  MSB_REQUIRE(logits && labels && class_w && acc && dlogits && n > 0 && c > 0 && c <= 32 && s > 0,
+              "msb_dice_ce_bwd: needs 1 <= C <= 32");
+  const dim3 grid((unsigned)((s + kLossVoxPerBlock - 1) / kLossVoxPerBlock), (unsigned)n);
+  MSB_DISPATCH_CMAX(c, dice_ce_bwd_kernel<CMAX><<<grid, kLossThreads, 0, as_stream(stream)>>>(
+                           logits, labels, class_w, acc, c, s, ignore_index, coef_ce, coef_dice, coef_dev, dice_w,
+                           dice_softmax, dlogits););
   MSB_LAUNCH_OK();
   return MSB_OK;
 }
@@ -460,13 +512,8 @@ int msb_dice_ce_finalize(const double* acc, int c, float* result, void* stream) 
 int msb_dice_ce_bwd(const float* logits, const int32_t* labels, const float* class_w, const double* acc, int n, int c,
                     int64_t s, int ignore_index, float coef_ce, float coef_dice, const float* coef_dev, float* dlogits,
                     void* stream) {
-  MSB_REQUIRE(logits && labels && class_w && acc && dlogits && n > 0 && c > 0 && c <= 32 && s > 0,
-              "msb_dice_ce_bwd: needs 1 <= C <= 32");
-  const dim3 grid((unsigned)((s + kLossVoxPerBlock - 1) / kLossVoxPerBlock), (unsigned)n);
-  MSB_DISPATCH_CMAX(c, dice_ce_bwd_kernel<CMAX><<<grid, kLossThreads, 0, as_stream(stream)>>>(
-                           logits, labels, class_w, acc, c, s, ignore_index, coef_ce, coef_dice, coef_dev, dlogits););
-  MSB_LAUNCH_OK();
-  return MSB_OK;
+  return msb_dice_ce_bwd_ex(logits, labels, class_w, acc, n, c, s, ignore_index, coef_ce, coef_dice, coef_dev, nullptr,
+                            0, dlogits, stream);
 }
 
 int msb_eval_head(msb_tensor a, const float* w, const float* b, const int32_t* labels, const float* class_w, int n,

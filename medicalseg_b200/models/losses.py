@@ -86,14 +86,14 @@ class _DiceCEFunction(torch.autograd.Function):
     """result[0] = CE, result[1] = Dice loss, result[2:] = per-channel Dice; gradient flows to logits only."""
 
     @staticmethod
-    def forward(ctx, logits, labels, class_w, ignore_index):
+    def forward(ctx, logits, labels, class_w, ignore_index, dice_w=None, dice_softmax=False):
         n, c = logits.shape[:2]
         acc = ops.zero_(torch.empty(3 * c + 2, dtype=torch.float64, device=logits.device))
         result = torch.empty(2 + c, dtype=torch.float32, device=logits.device)
-        ops.dice_ce_fwd(logits, labels, class_w, ignore_index, acc)
-        ops.dice_ce_finalize(acc, c, result)
+        ops.dice_ce_fwd(logits, labels, class_w, ignore_index, acc, dice_softmax)
+        ops.dice_ce_finalize(acc, c, result, dice_w)
         ctx.save_for_backward(logits, labels, class_w, acc)
-        ctx.ignore_index = ignore_index
+        ctx.ignore_index, ctx.dice_w, ctx.dice_softmax = ignore_index, dice_w, dice_softmax
         return result
 
     @staticmethod
@@ -101,8 +101,9 @@ class _DiceCEFunction(torch.autograd.Function):
         logits, labels, class_w, acc = ctx.saved_tensors
         dlogits = torch.empty_like(logits)
         coef = g[:2].contiguous().float()
-        ops.dice_ce_bwd(logits, labels, class_w, acc, ctx.ignore_index, 1.0, 1.0, coef, dlogits)
-        return dlogits, None, None, None
+        ops.dice_ce_bwd(logits, labels, class_w, acc, ctx.ignore_index, 1.0, 1.0, coef, dlogits, ctx.dice_w,
+                        ctx.dice_softmax)
+        return dlogits, None, None, None, None, None
 
 
 def _prep(logits, labels):
@@ -135,13 +136,15 @@ class _FusedEval:
     result = None
 
 
-def _fused(logits, labels, class_w, ignore_index):
-    key = (logits._version, ignore_index)
+def _fused(logits, labels, class_w, ignore_index, dice_opts=(None, False)):
+    """dice_opts = (per-class Dice weight tensor or None, softmax-normalised Dice) - DiceLoss's constructor options"""
+    dice_w, dice_softmax = dice_opts
+    key = (logits._version, ignore_index, None if dice_w is None else dice_w.data_ptr(), bool(dice_softmax))
     r = _FusedEval.refs
     if (r is not None and r[0]() is logits and r[1]() is labels and r[2]() is class_w and _FusedEval.key == key
             and _FusedEval.result is not None):
         return _FusedEval.result
-    res = _DiceCEFunction.apply(logits, labels, class_w, ignore_index)
+    res = _DiceCEFunction.apply(logits, labels, class_w, ignore_index, dice_w, bool(dice_softmax))
     _FusedEval.refs = (weakref.ref(logits), weakref.ref(labels), weakref.ref(class_w))
     _FusedEval.key, _FusedEval.result = key, res
     return res
@@ -149,12 +152,18 @@ def _fused(logits, labels, class_w, ignore_index):
 
 class DiceLoss:
     def __init__(self, sigmoid_norm=True, weight=None):
-        if not sigmoid_norm:
-            raise NotImplementedError("softmax-normalised Dice is not implemented (reference default is sigmoid)")
-        if weight is not None:
-            raise NotImplementedError("per-class Dice weights are not implemented (reference configs use None)")
-        self.weight, self.eps = weight, 1e-5
+        # dice_loss.py:36-43: nn.Sigmoid() or nn.Softmax(axis=1); `weight` scales the per-class intersections (:64-65)
+        self.sigmoid_norm, self.eps = bool(sigmoid_norm), 1e-5
+        self.weight = None if weight is None else torch.as_tensor(weight, dtype=torch.float32).flatten()
         self._ones = None
+
+    def _opts(self, device, c):
+        if self.weight is not None:
+            if self.weight.numel() != c:
+                raise ValueError("DiceLoss: {} class weights for {} classes".format(self.weight.numel(), c))
+            if self.weight.device != device:
+                self.weight = self.weight.to(device)
+        return (self.weight, not self.sigmoid_norm)
 
     def __call__(self, logits, labels):
         return self.forward(logits, labels)
@@ -166,7 +175,7 @@ class DiceLoss:
             if self._ones is None or self._ones.numel() != c:
                 self._ones = torch.ones(c, dtype=torch.float32, device=logits.device)
             _class_w = self._ones
-        res = _fused(logits, labels, _class_w, _ignore_index)
+        res = _fused(logits, labels, _class_w, _ignore_index, self._opts(logits.device, c))
         per_channel_dice = LazyHostArray(res[2:].detach())  # dice_loss.py:99 without draining the GPU here
         return res[1], per_channel_dice
 
@@ -181,7 +190,7 @@ class CrossEntropyLoss:
     def __call__(self, logit, label):
         return self.forward(logit, label)
 
-    def forward(self, logit, label):
+    def forward(self, logit, label, _dice_opts=(None, False)):
         logit, label = _prep(logit, label)
         if self.weight is None:
             self.weight = class_weights(logit.detach())  # cached forever (cross_entropy_loss.py:68-69)
@@ -189,7 +198,7 @@ class CrossEntropyLoss:
         if logit.shape[1] != len(self.weight):
             raise ValueError("The number of weights = {} must be the same as the number of classes = {}.".format(
                 len(self.weight), logit.shape[1]))
-        return _fused(logit, label, self.weight, self.ignore_index)[0]
+        return _fused(logit, label, self.weight, self.ignore_index, _dice_opts)[0]
 
 
 class MixedLoss:
@@ -210,6 +219,9 @@ class MixedLoss:
         logits, labels = _prep(logits, labels)
         loss_list, per_channel_dice = [], None
         ce = next((l for l in self.losses if type(l).__name__ == "CrossEntropyLoss"), None)
+        dice = next((l for l in self.losses if type(l).__name__ == "DiceLoss"), None)
+        # the CE and Dice objects share ONE fused pass: the CE call runs it with the Dice object's options
+        dice_opts = dice._opts(logits.device, logits.shape[1]) if dice is not None else (None, False)
         for i, loss in enumerate(self.losses):
             if type(loss).__name__ == "DiceLoss":
                 if ce is not None:  # share the CE object's class weights so both run in the same fused pass
@@ -218,6 +230,8 @@ class MixedLoss:
                     out, per_channel_dice = loss.forward(logits, labels, ce.weight.to(logits.device), ce.ignore_index)
                 else:
                     out, per_channel_dice = loss(logits, labels)
+            elif loss is ce:
+                out = loss.forward(logits, labels, dice_opts)
             else:
                 out = loss(logits, labels)
             loss_list.append(out * self.coef[i])
@@ -269,6 +283,8 @@ def fused_head_plan(losses):
             ce = l
             terms.append((0, coef * c))
         elif kind == "DiceLoss" and dice is None:
+            if not l.sigmoid_norm or l.weight is not None:
+                return None  # the fused head computes the default sigmoid Dice: other options take the unfused path
             dice = l
             terms.append((1, coef * c))
         else:

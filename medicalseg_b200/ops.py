@@ -331,14 +331,14 @@ def class_weight_finalize(psum, count, c, weights):
     call("msb_class_weight_finalize", _ptr(psum), float(count), c, _ptr(weights), _stream())
 
 
-def dice_ce_fwd(logits, labels, class_w, ignore_index, acc):
+def dice_ce_fwd(logits, labels, class_w, ignore_index, acc, dice_softmax=False):
     n, c = logits.shape[:2]
-    call("msb_dice_ce_fwd", _ptr(logits), _ptr(labels), _ptr(class_w), n, c, logits[0, 0].numel(), ignore_index,
-         _ptr(acc), _stream())
+    call("msb_dice_ce_fwd_ex", _ptr(logits), _ptr(labels), _ptr(class_w), n, c, logits[0, 0].numel(), ignore_index,
+         int(bool(dice_softmax)), _ptr(acc), _stream())
 
 
-def dice_ce_finalize(acc, c, result):
-    call("msb_dice_ce_finalize", _ptr(acc), c, _ptr(result), _stream())
+def dice_ce_finalize(acc, c, result, dice_w=None):
+    call("msb_dice_ce_finalize_ex", _ptr(acc), c, _ptr(dice_w), _ptr(result), _stream())
 
 
 def eval_head(a: B8, w, b, labels, class_w, c, ignore_index, pred=None, acc=None, psum=None):
@@ -347,10 +347,12 @@ def eval_head(a: B8, w, b, labels, class_w, c, ignore_index, pred=None, acc=None
          _ptr(pred), _ptr(acc), _ptr(psum), _stream())
 
 
-def dice_ce_bwd(logits, labels, class_w, acc, ignore_index, coef_ce, coef_dice, coef_dev, dlogits):
+def dice_ce_bwd(logits, labels, class_w, acc, ignore_index, coef_ce, coef_dice, coef_dev, dlogits, dice_w=None,
+                dice_softmax=False):
     n, c = logits.shape[:2]
-    call("msb_dice_ce_bwd", _ptr(logits), _ptr(labels), _ptr(class_w), _ptr(acc), n, c, logits[0, 0].numel(),
-         ignore_index, float(coef_ce), float(coef_dice), _ptr(coef_dev), _ptr(dlogits), _stream())
+    call("msb_dice_ce_bwd_ex", _ptr(logits), _ptr(labels), _ptr(class_w), _ptr(acc), n, c, logits[0, 0].numel(),
+         ignore_index, float(coef_ce), float(coef_dice), _ptr(coef_dev), _ptr(dice_w), int(bool(dice_softmax)),
+         _ptr(dlogits), _stream())
 
 
 def argmax_channels(logits, pred):

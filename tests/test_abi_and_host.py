@@ -146,8 +146,11 @@ def test_loss_argument_errors_match_reference():
         L.MixedLoss([L.DiceLoss()], [1, 2])
     with pytest.raises(RuntimeError):
         L.loss_computation([1, 2], None, {"types": [L.DiceLoss()], "coef": [1]})
+    d = L.DiceLoss(sigmoid_norm=False, weight=[1.0, 2.0])  # both constructor options of dice_loss.py:36-43 exist
+    assert d.sigmoid_norm is False and d.weight.tolist() == [1.0, 2.0]
+    assert L.fused_head_plan({"types": [d], "coef": [1]}) is None  # non-default Dice: evaluate() takes the unfused path
     with pytest.raises(NotImplementedError):
-        L.DiceLoss(sigmoid_norm=False)
+        L.CrossEntropyLoss(data_format="NDHWC")
 
 
 def test_transform_parameter_draws_match_the_oracle_on_cpu():

@@ -742,3 +742,32 @@ def test_dynamic_tile_scheduler_matches_static_assignment():
                     assert float((got_s - ref_s).abs().max()) <= 1e-6 * float(ref_s.abs().max() + 1), (name, rep)
     finally:
         _lib.call("msb_set_tile_scheduler", 0)
+
+
+@pytest.mark.parametrize("c,sigmoid_norm,weighted", [(3, False, False), (3, True, True), (20, False, True), (2, False, True)])
+def test_dice_loss_constructor_options_match_oracle(c, sigmoid_norm, weighted):
+    """DiceLoss(sigmoid_norm=False) = softmax-normalised Dice and DiceLoss(weight=...) = per-class intersection weights
+    (dice_loss.py:36-43,64-65), alone and inside MixedLoss (one fused pass with the cross-entropy), values and gradients."""
+    from oracle import vnet_oracle as vo
+    from medicalseg_b200.models import losses as L
+    torch.manual_seed(8)
+    logits = torch.randn(2, c, 8, 9, 10) * 2
+    labels = torch.randint(0, c, (2, 8, 9, 10), dtype=torch.int32)
+    w = (torch.rand(c) + 0.5) if weighted else None
+    for mixed in (False, True):
+        lo = logits.clone().requires_grad_(True)
+        lg = logits.clone().cuda().requires_grad_(True)
+        od = vo.DiceLoss(sigmoid_norm=sigmoid_norm, weight=w)
+        gd = L.DiceLoss(sigmoid_norm=sigmoid_norm, weight=None if w is None else w.tolist())
+        if mixed:
+            oll, odice = vo.MixedLoss([vo.CrossEntropyLoss(), od], [1, 1])(lo, labels)
+            gll, gdice = L.MixedLoss([L.CrossEntropyLoss(), gd], [1, 1])(lg, labels.cuda())
+            ol, gl = sum(oll), sum(gll)
+        else:
+            ol, odice = od(lo, labels)
+            gl, gdice = gd(lg, labels.cuda())
+        ol.backward()
+        gl.backward()
+        assert abs(float(ol) - float(gl)) <= 1e-5, (mixed, float(ol), float(gl))
+        assert float(np.abs(np.asarray(gdice) - np.asarray(odice)).max()) <= 1e-5
+        assert float((lg.grad.cpu() - lo.grad).abs().max()) <= 1e-5 * float(lo.grad.abs().max()) + 1e-9
