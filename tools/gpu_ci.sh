@@ -6,9 +6,10 @@ TAG=${1:-ci}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_smi.log 2>&1
-timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 -p no:cacheprovider > $OUT/${TAG}_pytest.log 2>&1
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 -p no:cacheprovider > $OUT/${TAG}_pytest.log 2>&1
 echo "pytest rc=$?" >> $OUT/${TAG}_pytest.log
 tail -5 $OUT/${TAG}_pytest.log
+timeout 300 python -m pytest tests/test_gpu_boundary.py -q -s -k loader -p no:cacheprovider 2>&1 | grep "reader_cost per log window" | tee $OUT/${TAG}_loader.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"
 timeout 600 python bench.py --steps 20 --warmup 5 > $OUT/${TAG}_bench.log 2>&1; echo "bench rc=$?"; tail -1 $OUT/${TAG}_bench.log | cut -c1-400
 for cfg in mri_bf16 vnet128_fp32ddp preprocess; do
