@@ -252,21 +252,25 @@ __global__ void __launch_bounds__(128 + 32 * EW, ACCN == 128 ? 2 : 1)
         return (ok && tap_ok && c8 < p.out_c8) ? out_n + ((int64_t)c8 * So + v) * 8 : nullptr;
       };
       // accumulate: request every `old` vector of this item now - the loads fly while the MMAs of the item run
-      uint4 oldv[ACC ? kK2MaxIt : 1][2];
-      if (ACC) {
+      // kPF column blocks are in flight per thread: all of an item's for the one-CTA variant, a rotating window of
+      // kPF for the two-CTAs-per-SM variant (128 registers per thread)
+      constexpr int kPF = ACC ? (ACCN == 128 ? 3 : kK2MaxIt) : 1;
+      uint4 oldv[kPF][2];
+      auto fetch_old = [&](int it, uint4 (&slot)[2]) {
+        const int cb = wg + kK2EpiGroups * it;
 #pragma unroll
-        for (int it = 0; it < kK2MaxIt; ++it) {
-          const int cb = wg + kK2EpiGroups * it;
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            oldv[it][k] = make_uint4(0u, 0u, 0u, 0u);
-            if (cb < nblk16) {
-              int co0;
-              const __nv_bfloat16* src = dest(cb, k, co0);
-              if (src != nullptr) oldv[it][k] = *reinterpret_cast<const uint4*>(src);
-            }
+        for (int k = 0; k < 2; ++k) {
+          slot[k] = make_uint4(0u, 0u, 0u, 0u);
+          if (cb < nblk16) {
+            int co0;
+            const __nv_bfloat16* src = dest(cb, k, co0);
+            if (src != nullptr) slot[k] = *reinterpret_cast<const uint4*>(src);
           }
         }
+      };
+      if (ACC) {
+#pragma unroll
+        for (int it = 0; it < kPF; ++it) fetch_old(it, oldv[it]);
       }
       ptx::mbar_wait(BAR(kAccFull + as), aph);
       ptx::tc_fence_after();
@@ -300,8 +304,8 @@ __global__ void __launch_bounds__(128 + 32 * EW, ACCN == 128 ? 2 : 1)
           uint32_t pk[4] = {0u, 0u, 0u, 0u};
           if (dst != nullptr) {
             if (ACC) {
-              const uint32_t o[4] = {oldv[ACC ? it : 0][k].x, oldv[ACC ? it : 0][k].y, oldv[ACC ? it : 0][k].z,
-                                     oldv[ACC ? it : 0][k].w};
+              const uint4 ov = oldv[ACC ? it % kPF : 0][k];
+              const uint32_t o[4] = {ov.x, ov.y, ov.z, ov.w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 acc[k * 8 + 2 * i] += __uint_as_float(o[i] << 16);
@@ -323,6 +327,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, ACCN == 128 ? 2 : 1)
             }
           }
         }
+        if (ACC && kPF < kK2MaxIt && it + kPF < kK2MaxIt) fetch_old(it + kPF, oldv[it % kPF]);  // refill the window
         if (want_stats) {
           float sq[16];
 #pragma unroll
@@ -484,11 +489,17 @@ static int launch_k2s2(int mode, const msb_tensor& x, const void* packed, const 
                                      k2_smem_bytes(8, 8, 256)));
     MSB_CUDA_OK(cudaFuncSetAttribute(conv_k2s2_kernel<4, 4, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      k2_smem_bytes(4, 4, 128)));
+    MSB_CUDA_OK(cudaFuncSetAttribute(conv_k2s2_kernel<4, 4, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     k2_smem_bytes(4, 4, 128)));
     attr_set = true;
   }
-  if (!accumulate && p.nmma <= 128 && !(g_debug_flags[6] & 64)) {  // store-only, narrow N: two CTAs per SM
+  if (p.nmma <= 128 && !(g_debug_flags[6] & 64) && !(accumulate && (g_debug_flags[6] & 128))) {
+    // narrow N: two CTAs per SM (the accumulate form prefetches a rotating window of 3 column blocks instead of all 8)
     const int grid = items < 2 * kNumSMs ? items : 2 * kNumSMs;
-    MSB_LAUNCH_PDL((conv_k2s2_kernel<4, 4, 128, false>), dim3(grid), dim3(128 + 32 * 4), k2_smem_bytes(4, 4, 128), st, tmap, p);
+    if (accumulate)
+      MSB_LAUNCH_PDL((conv_k2s2_kernel<4, 4, 128, true>), dim3(grid), dim3(128 + 32 * 4), k2_smem_bytes(4, 4, 128), st, tmap, p);
+    else
+      MSB_LAUNCH_PDL((conv_k2s2_kernel<4, 4, 128, false>), dim3(grid), dim3(128 + 32 * 4), k2_smem_bytes(4, 4, 128), st, tmap, p);
   } else {
     const int grid = items < kNumSMs ? items : kNumSMs;
     if (accumulate)
