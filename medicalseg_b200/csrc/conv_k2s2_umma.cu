@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, ACCN == 128 ? 2 : 1)
     const uint32_t a_lbo16 = (uint32_t)(kK2TileH * kK2TileW * 16) >> 4, b_lbo16 = (uint32_t)p.nmma;  // nmma*16 B >> 4
     uint32_t use = 0, iuse = 0;
     for (;; ++iuse) {
-      if (get_item(iuse) < 0) break;
+      if ((int)__reduce_or_sync(0xffffffffu, (unsigned int)get_item(iuse)) < 0) break;
       const uint32_t as = iuse & 1, aph = (iuse >> 1) & 1;
       ptx::mbar_wait(BAR(kAccEmpty + as), aph ^ 1);
       ptx::tc_fence_after();

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
     const bool prof = p.prof != nullptr;
     long long t_w = 0, t_h = 0, t_a = 0, t_begin = prof ? clock64() : 0, tq = 0;
     for (;; ++iuse) {
-      const int item = get_item(iuse);
+      const int item = (int)__reduce_or_sync(0xffffffffu, (unsigned int)get_item(iuse));  // provably warp-uniform
       if (item < 0) break;
       const uint32_t as = iuse % ACC_SETS, aph = (iuse / ACC_SETS) & 1;
       if (prof) tq = clock64();
@@ -768,7 +768,11 @@ __global__ void __launch_bounds__(256, 1)
     const uint32_t b_hi = ptx::desc_hi(p.dbg_swap ? 128u : (uint32_t)Cfg::kDyPlaneBytes);
     uint32_t use = 0, iuse = 0;
     for (;; ++iuse) {
-      const int item = dyn ? sched::next(BAR(kSF), BAR(kSE), sched_slots, iuse, lane) : static_item(iuse);
+      // REDUX keeps the item number provably warp-uniform: everything derived from it (tap offsets, descriptor words,
+      // TMEM columns) must live in uniform registers or the issue loop costs ~11 extra SASS instructions per MMA -
+      // without it the static path lost 35-45 % on these kernels when the scheduler branch was introduced
+      const int item = (int)__reduce_or_sync(
+          0xffffffffu, (unsigned int)(dyn ? sched::next(BAR(kSF), BAR(kSE), sched_slots, iuse, lane) : static_item(iuse)));
       if (item < 0) break;
       const int pass = item / p.chunks, chunk = item % p.chunks;
       int mh, g, u0, u1;
@@ -830,7 +834,7 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int co = cb * 16 + j;
-              if (co < p.cout_real) atomicAdd(p.ws + ((int64_t)tap * p.cout_real + co) * p.cin_real + ci, acc[j]);
+              if (co < p.cout_real) red_add_f32(p.ws + ((int64_t)tap * p.cout_real + co) * p.cin_real + ci, acc[j]);
             }
           }
         }

@@ -207,7 +207,9 @@ __global__ void __launch_bounds__(256, 1)
     const uint32_t npad = (uint32_t)p.npad;
     uint32_t use = 0, iuse = 0;
     for (;; ++iuse) {
-      const int item = dyn ? sched::next(BAR(kSF), BAR(kSE), sched_slots, iuse, lane) : static_item(iuse);
+      // (REDUX: the item number - and every descriptor word derived from it - stays provably warp-uniform)
+      const int item = (int)__reduce_or_sync(
+          0xffffffffu, (unsigned int)(dyn ? sched::next(BAR(kSF), BAR(kSE), sched_slots, iuse, lane) : static_item(iuse)));
       if (item < 0) break;
       int pass, t0, t1;
       decode_item(item, pass, t0, t1);
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(256, 1)
               const int jh = jg * p.jh + jj;  // dY row shift: v_h = u_h - 2 + jh  <=>  kh = 4 - jh
               if (jj < p.jh && jh < 5 && co < p.cout_real) {
                 const int tap = (kd * 5 + (4 - jh)) * p.kw_taps + kw;
-                atomicAdd(p.ws + ((int64_t)tap * p.cout_real + co) * p.cin_real + ci, acc[j]);
+                red_add_f32(p.ws + ((int64_t)tap * p.cout_real + co) * p.cin_real + ci, acc[j]);
               }
             }
           }

@@ -173,6 +173,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_ma
 
 }  // namespace ptx
 
+// fire-and-forget f32 add (RED): the weight-gradient epilogues issue tens of thousands of these per CTA.  Written as
+// PTX because `atomicAdd` with an unused result is only turned into RED by a compiler heuristic - the kernels that also
+// contain value-returning atomics (the tile scheduler's counter) got ATOMG for all of them and ran 35-45 % slower.
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
 // ---- dynamic tile scheduler for the persistent tensor-core kernels ------------------------------------------------
 // Static round-robin (item = blockIdx.x + k * gridDim.x) makes the makespan of a persistent grid the finish time of
 // its LAST-STARTED CTA: when NCCL's all-reduce CTAs hold some SMs at launch (data-parallel step),
