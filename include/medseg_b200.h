@@ -53,8 +53,10 @@ const char* msb_last_error_string(void);
 /* ---- layout converters (boundary) ------------------------------------------------------------------ */
 /* Tile scheduling of the persistent tensor-core kernels (5x5x5 fwd / dgrad, both weight-gradient kernels, the strided
  * convs): 0 = static round-robin over the grid (default), 1 = CTAs fetch tiles from a self-resetting atomic counter in
- * device memory.  The data-parallel step (medicalseg/core/train.py:81-88) turns it on: NCCL's all-reduce CTAs occupy
- * SMs while backward runs, and with static assignment the CTAs displaced by them set the kernel's makespan. */
+ * device memory - an experiment for the data-parallel step (medicalseg/core/train.py:81-88), where NCCL's all-reduce
+ * CTAs occupy SMs while backward runs.  Measured to gain nothing on 2 and 8 GPUs, so the default build compiles it out
+ * (msb_set_tile_scheduler(1) -> MSB_ERR_UNSUPPORTED); `MSB_DYNAMIC_TILES=1 python -m medicalseg_b200.build --force`
+ * builds it in. */
 int msb_set_tile_scheduler(int dynamic);
 /* Clears a device buffer on `stream` (cudaMemsetAsync: a memset node inside a CUDA-graph capture).  Replaces
  * `Layer.clear_gradients()` / `paddle.zeros` on the train path (medicalseg/core/train.py:155). */

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, ACCN == 128 ? 2 : 1)
   if (threadIdx.x == 0) {
     for (int i = 0; i < kK2Stages; ++i) { ptx::mbar_init(BAR(kFull + i), 1); ptx::mbar_init(BAR(kEmpty + i), 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(kAccFull + i), 1); ptx::mbar_init(BAR(kAccEmpty + i), kK2EpiWarps); }
-    sched::init(BAR(kSF), BAR(kSE), 2 + kK2EpiWarps);  // consumers: producer and MMA warps + the epilogue warps
+    if (sched::kEnabled) sched::init(BAR(kSF), BAR(kSE), 2 + kK2EpiWarps);  // consumers: producer and MMA warps + the epilogue warps
     ptx::fence_mbar_init();
   }
   for (int i = threadIdx.x; i < kK2EpiWarps * 2 * 256; i += kK2Threads) stat_smem[i] = 0.f;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, ACCN == 128 ? 2 : 1)
   const int kiters = ktaps * p.chunks;
   const uint32_t b_bytes = (uint32_t)p.nmma * 32u;
   // k-th item of this CTA: static round-robin, or from the scheduler warp (umma.cuh, namespace sched)
-  const bool dyn = p.sched != nullptr;
+  const bool dyn = sched::kEnabled && p.sched != nullptr;
   auto get_item = [&](uint32_t k) -> int {
     if (dyn) return sched::next(BAR(kSF), BAR(kSE), sched_slots, k, lane);
     const int it = (int)blockIdx.x + (int)k * (int)gridDim.x;
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(128 + 32 * EW, ACCN == 128 ? 2 : 1)
     const uint32_t a_lbo16 = (uint32_t)(kK2TileH * kK2TileW * 16) >> 4, b_lbo16 = (uint32_t)p.nmma;  // nmma*16 B >> 4
     uint32_t use = 0, iuse = 0;
     for (;; ++iuse) {
-      if ((int)__reduce_or_sync(0xffffffffu, (unsigned int)get_item(iuse)) < 0) break;
+      if (sched::uniform(get_item(iuse)) < 0) break;
       const uint32_t as = iuse & 1, aph = (iuse >> 1) & 1;
       ptx::mbar_wait(BAR(kAccEmpty + as), aph ^ 1);
       ptx::tc_fence_after();

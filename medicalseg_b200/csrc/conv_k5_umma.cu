@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(0 + i), 1); ptx::mbar_init(BAR(2 + i), 1); }
     for (int i = 0; i < Cfg::kWStages; ++i) { ptx::mbar_init(BAR(kWF + i), 1); ptx::mbar_init(BAR(kWE + i), 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(4 + i), 1); ptx::mbar_init(BAR(6 + i), 8); }
-    sched::init(BAR(kSF), BAR(kSE), 11);  // consumers: halo, weight and MMA warps + 8 epilogue warps
+    if (sched::kEnabled) sched::init(BAR(kSF), BAR(kSE), 11);  // consumers: halo, weight and MMA warps + 8 epilogue warps
     ptx::fence_mbar_init();
   }
   for (int i = threadIdx.x; i < 8 * 2 * NPAD; i += kFwdThreads) stat_smem[i] = 0.f;
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
   };
 
   // k-th item of this CTA: static round-robin, or handed out by the scheduler warp (see umma.cuh, namespace sched)
-  const bool dyn = p.sched != nullptr;
+  const bool dyn = sched::kEnabled && p.sched != nullptr;
   auto get_item = [&](uint32_t k) -> int {
     if (dyn) return sched::next(BAR(kSF), BAR(kSE), sched_slots, k, lane);
     const int it = (int)blockIdx.x + (int)k * (int)gridDim.x;
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
     const bool prof = p.prof != nullptr;
     long long t_w = 0, t_h = 0, t_a = 0, t_begin = prof ? clock64() : 0, tq = 0;
     for (;; ++iuse) {
-      const int item = (int)__reduce_or_sync(0xffffffffu, (unsigned int)get_item(iuse));  // provably warp-uniform
+      const int item = sched::uniform(get_item(iuse));
       if (item < 0) break;
       const uint32_t as = iuse % ACC_SETS, aph = (iuse / ACC_SETS) & 1;
       if (prof) tq = clock64();
@@ -663,7 +663,7 @@ __global__ void __launch_bounds__(256, 1)
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(2 + i), (uint32_t)csize); }
     ptx::mbar_init(BAR(4), 1);
     ptx::mbar_init(BAR(5), 4);
-    sched::init(BAR(kSF), BAR(kSE), 6);  // consumers: the producer thread, the MMA warp, 4 epilogue warps
+    if (sched::kEnabled) sched::init(BAR(kSF), BAR(kSE), 6);  // consumers: the producer thread, the MMA warp, 4 epilogue warps
     ptx::fence_mbar_init();
   }
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmap_x); ptx::prefetch_tmap(&tmap_dy); }
@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(256, 1)
   const int item_step = CL ? (int)gridDim.x / csize : (int)gridDim.x;
   const int tiles_per_n = p.d * p.tiles_h * p.tiles_w;
   // k-th item of this CTA (cluster): static round-robin, or from the scheduler warp (umma.cuh, namespace sched)
-  const bool dyn = !CL && p.sched != nullptr;
+  const bool dyn = sched::kEnabled && !CL && p.sched != nullptr;
   auto static_item = [&](uint32_t k) -> int {
     const int it = item0 + (int)k * item_step;
     return it < num_items ? it : -1;
@@ -768,11 +768,7 @@ __global__ void __launch_bounds__(256, 1)
     const uint32_t b_hi = ptx::desc_hi(p.dbg_swap ? 128u : (uint32_t)Cfg::kDyPlaneBytes);
     uint32_t use = 0, iuse = 0;
     for (;; ++iuse) {
-      // REDUX keeps the item number provably warp-uniform: everything derived from it (tap offsets, descriptor words,
-      // TMEM columns) must live in uniform registers or the issue loop costs ~11 extra SASS instructions per MMA -
-      // without it the static path lost 35-45 % on these kernels when the scheduler branch was introduced
-      const int item = (int)__reduce_or_sync(
-          0xffffffffu, (unsigned int)(dyn ? sched::next(BAR(kSF), BAR(kSE), sched_slots, iuse, lane) : static_item(iuse)));
+      const int item = sched::uniform(dyn ? sched::next(BAR(kSF), BAR(kSE), sched_slots, iuse, lane) : static_item(iuse));
       if (item < 0) break;
       const int pass = item / p.chunks, chunk = item % p.chunks;
       int mh, g, u0, u1;
@@ -1348,6 +1344,10 @@ static unsigned int* g_sched_fwd_ptr = nullptr;
 static unsigned int* g_sched_wg_ptr = nullptr;
 
 int msb_set_tile_scheduler(int dynamic) {
+  if (dynamic && !sched::kEnabled) {
+    set_error("msb_set_tile_scheduler: the dynamic scheduler is compiled out (rebuild with -DMSB_DYNAMIC_TILES=1)");
+    return MSB_ERR_UNSUPPORTED;
+  }
   if (dynamic && g_sched_fwd_ptr == nullptr) {
     MSB_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void**>(&g_sched_fwd_ptr), g_sched_fwd));
     MSB_CUDA_OK(cudaGetSymbolAddress(reinterpret_cast<void**>(&g_sched_wg_ptr), g_sched_wg));

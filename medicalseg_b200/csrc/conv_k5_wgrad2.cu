@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256, 1)
     for (int i = 0; i < kW2Stages; ++i) { ptx::mbar_init(BAR(i), 1); ptx::mbar_init(BAR(kEmpty + i), (uint32_t)csize); }
     ptx::mbar_init(BAR(kAccFull), 1);
     ptx::mbar_init(BAR(kAccEmpty), 4);
-    sched::init(BAR(kSF), BAR(kSE), 6);  // consumers: the producer thread, the MMA warp, 4 epilogue warps
+    if (sched::kEnabled) sched::init(BAR(kSF), BAR(kSE), 6);  // consumers: the producer thread, the MMA warp, 4 epilogue warps
     ptx::fence_mbar_init();
   }
   if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmap_x); ptx::prefetch_tmap(&tmap_dy); }
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256, 1)
   };
   const int num_items_all = (CL && p.rep) ? p.gchunks[0] + p.gchunks[1] : num_items;
   // k-th item of this CTA (cluster): static round-robin, or from the scheduler warp (umma.cuh, namespace sched)
-  const bool dyn = !CL && p.sched != nullptr;
+  const bool dyn = sched::kEnabled && !CL && p.sched != nullptr;
   auto static_item = [&](uint32_t k) -> int {
     const int it = item0 + (int)k * item_step;
     return it < num_items_all ? it : -1;
@@ -207,9 +207,7 @@ __global__ void __launch_bounds__(256, 1)
     const uint32_t npad = (uint32_t)p.npad;
     uint32_t use = 0, iuse = 0;
     for (;; ++iuse) {
-      // (REDUX: the item number - and every descriptor word derived from it - stays provably warp-uniform)
-      const int item = (int)__reduce_or_sync(
-          0xffffffffu, (unsigned int)(dyn ? sched::next(BAR(kSF), BAR(kSE), sched_slots, iuse, lane) : static_item(iuse)));
+      const int item = sched::uniform(dyn ? sched::next(BAR(kSF), BAR(kSE), sched_slots, iuse, lane) : static_item(iuse));
       if (item < 0) break;
       int pass, t0, t1;
       decode_item(item, pass, t0, t1);

@@ -188,8 +188,22 @@ __device__ __forceinline__ void red_add_f32(float* addr, float v) {
 // small shared-memory ring (mbarrier full / empty pairs), so late CTAs simply take fewer tiles.  The first item stays
 // static (no atomic latency before the first TMA), the counter pair {next, done} resets itself: the CTA that finishes
 // last writes zeros (every CTA's final fetch precedes its `done` increment).
+#ifndef MSB_DYNAMIC_TILES
+#define MSB_DYNAMIC_TILES 0
+#endif
 namespace sched {
+// Compiled OUT by default (build with -DMSB_DYNAMIC_TILES=1 to get it back): measured on 2 and 8 B200s it gains nothing
+// (DESIGN 6), and merely carrying the branch cost the static path 3.5 % on the forward kernel (the ring's barriers, and
+// the BatchNorm-statistics REDG turned into ATOMG next to the counter's value-returning atomics).
+constexpr bool kEnabled = MSB_DYNAMIC_TILES != 0;
 constexpr int kDepth = 4;
+
+// REDUX keeps an item number that came out of the ring provably warp-uniform (everything the MMA issue loop derives
+// from it must live in uniform registers: without this the loop costs ~11 extra SASS instructions per MMA, 35-45 % on
+// the per-tap weight-gradient kernels).  The static round-robin number is built from blockIdx / gridDim and needs none.
+__device__ __forceinline__ int uniform(int v) {
+  return kEnabled ? (int)__reduce_or_sync(0xffffffffu, (unsigned int)v) : v;
+}
 
 __device__ __forceinline__ void init(uint32_t full0, uint32_t empty0, uint32_t consumer_warps) {  // one thread
   for (int i = 0; i < kDepth; ++i) {

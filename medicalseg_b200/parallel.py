@@ -94,9 +94,10 @@ class DistributedGradReducer:
         model.grad_ready_hook = self.on_ready
         model.stat_all_reduce = self.all_reduce_
         if self.world > 1 and self.flat_grad.is_cuda and os.environ.get("MSB_TILE_SCHEDULER", "0") == "1":
-            # opt-in: persistent conv grids fetch tiles from an atomic counter (umma.cuh, namespace sched).  MEASURED on
-            # 2 x B200 (profiles/r2t_bench_n2*.log): 12.43 ms per step with it vs 12.41 ms without on the same box -
-            # the cost of NCCL's CTAs is not a late-CTA tail effect, so static assignment stays the default
+            # opt-in experiment (needs a library built with MSB_DYNAMIC_TILES=1, raises otherwise): persistent conv grids
+            # fetch tiles from an atomic counter (umma.cuh, namespace sched).  MEASURED on 2 x B200
+            # (profiles/r2t_bench_n2*.log): 12.43 ms per step with it vs 12.41 ms without on the same box - the cost of
+            # NCCL's CTAs is not a late-CTA tail effect, so static assignment is what ships
             from . import _lib
             _lib.call("msb_set_tile_scheduler", 1)
         if self.comm is not None and self.stat_comm is None and getattr(model, "sync_bn", False):

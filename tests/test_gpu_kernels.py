@@ -669,6 +669,12 @@ def test_dynamic_tile_scheduler_matches_static_assignment():
     call is repeated to prove that the counters reset themselves."""
     ops, B8 = _imp()
     from medicalseg_b200 import _lib
+    if _lib.load().msb_set_tile_scheduler(1) != 0:
+        # the default build compiles the scheduler out (umma.cuh, MSB_DYNAMIC_TILES): the entry point must refuse, loudly
+        with pytest.raises(RuntimeError, match="compiled out"):
+            _lib.call("msb_set_tile_scheduler", 1)
+        _lib.call("msb_set_tile_scheduler", 0)
+        pytest.skip("dynamic tile scheduler compiled out (MSB_DYNAMIC_TILES=1 python -m medicalseg_b200.build --force)")
     torch.manual_seed(31)
     n = 2
 
