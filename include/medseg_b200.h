@@ -231,6 +231,12 @@ int msb_conv_k5_wgrad(msb_tensor x, msb_tensor dy, float* dw, float* dbias, int 
  * state-dict boundary. */
 int msb_conv_k5_pack_tm(const float* w_tm, void* packed, int cout, int cin, int mode, int cin_pad, int cout_pad,
                         void* stream);
+/* Both operand images of a layer in one pass over the master weight (what the train step calls after every optimizer
+ * step: medicalseg/core/train.py:152 `optimizer.step()` changes every weight): packed_f = the mode-0 image built with
+ * (f_cin_pad, f_cout_pad), packed_b = the mode-1 image built with (b_cin_pad, b_cout_pad); lo_part = 1 packs w - bf16(w)
+ * (3 x bf16 path).  Bit-identical to two msb_conv_k5_pack_tm calls. */
+int msb_conv_k5_pack_tm_pair(const float* w_tm, void* packed_f, void* packed_b, int cout, int cin, int lo_part,
+                             int f_cin_pad, int f_cout_pad, int b_cin_pad, int b_cout_pad, void* stream);
 /* ---- 3 x bf16 fp32 path (BASELINE configs[2]: fp32 storage, tensor-core convolutions) -------------------------
  * An f32 operand a is split into bf16 hi = bf16(a) and lo = bf16(a - hi); conv(x, w) ~ conv(x_hi, w_hi) + conv(x_lo, w_hi)
  * + conv(x_hi, w_lo) with f32 accumulation (relative error ~2^-16; the lo*lo term is dropped).  msb_split_hi_lo splits

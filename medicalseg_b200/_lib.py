@@ -65,6 +65,7 @@ SIGNATURES = {
     "msb_conv_k5_fwd_ws": (I, [T, P, P, I, T, I, D3, I, P, I, P, P, SZ, P]),
     "msb_conv_k5_fwd_act": (I, [T, P, P, I, T, I, D3, P, P, P, C.POINTER(MsbTensor), P, P, SZ, P]),
     "msb_conv_k5_pack_tm": (I, [P, P, I, I, I, I, I, P]),
+    "msb_conv_k5_pack_tm_pair": (I, [P, P, P, I, I, I, I, I, I, I, P]),
     "msb_split_hi_lo": (I, [T, T, T, I, L, P]),
     "msb_conv_k5_wgrad_tm": (I, [T, T, P, P, I, I, I, D3, P]),
     "msb_conv_k5_wgrad_workspace_bytes": (SZ, [I, I]),

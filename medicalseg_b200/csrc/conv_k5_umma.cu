@@ -984,6 +984,59 @@ __global__ void __launch_bounds__(256) pack_k5_tm_kernel(const float* __restrict
   }
 }
 
+// BOTH operand images of one layer (forward: mode 0, input-gradient: mode 1) from ONE coalesced read of the tap-major
+// master weight.  A block owns one source tap and a 16 co x 32 ci tile of it: it stages the tile in shared memory
+// (16 rows of 128 contiguous bytes) and then warps 0-1 write the forward image - 256-byte runs of (16 co) x (8 ci) per
+// (16-ci chunk, k8) - while warps 2-3 write the input-gradient image, whose K dimension is co and whose tap is mirrored:
+// 512-byte runs of (32 ci) x (8 co) per k8.  8 bytes of traffic per weight instead of 12 and no 32-byte strided gathers
+// (the single-image kernel above reads one sector per thread in mode 0: ~1.3 TB/s).  The 2.3 KB tile fits beside the
+// largest forward CTA (3 968 B of an SM's shared memory stay free next to conv_k5_fwd_kernel<32, 8, 8>), so the
+// re-pack on the side stream still overlaps the convolutions of the next forward.
+constexpr int kPairCi = 32, kPairRow = kPairCi + 4;  // +4 floats: 8-float reads of consecutive rows hit distinct banks
+__global__ void __launch_bounds__(128)
+    pack_k5_tm_pair_kernel(const float* __restrict__ w_tm, __nv_bfloat16* __restrict__ packed_f,
+                           __nv_bfloat16* __restrict__ packed_b, int cout, int cin, int lo_part, int f_cin_pad,
+                           int f_cout_pad, int b_cin_pad, int b_cout_pad) {
+  __shared__ __align__(16) float s[16][kPairRow];
+  pdl_wait();
+  pdl_trigger();
+  const int t = blockIdx.x;               // source tap kd*25 + kh*5 + kw
+  const int co0 = blockIdx.y * 16;        // first of the tile's 16 output channels
+  const int ci0 = blockIdx.z * kPairCi;   // first of the tile's 32 input channels
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int e = tid + k * 128, r = e >> 5, c = e & 31;
+    float x = 0.f;
+    if (co0 + r < cout && ci0 + c < cin) x = __ldg(w_tm + ((int64_t)t * cout + co0 + r) * cin + ci0 + c);
+    if (lo_part) x -= __bfloat162float(__float2bfloat16_rn(x));
+    s[r][c] = x;
+  }
+  __syncthreads();
+  if (tid < 64) {  // forward image: vector (chunk, hk, k8, kdr, oc = co) holds 8 consecutive ci
+    const int ocl = tid & 15, k8 = (tid >> 4) & 1, cl = tid >> 5;
+    const int chunk = blockIdx.z * 2 + cl;
+    if (co0 < f_cout_pad && chunk * 16 < f_cin_pad) {
+      const int kdr = 4 - t / 25, hk = t % 25;
+      float v[8];
+      Vec8<float>::load(&s[ocl][cl * 16 + k8 * 8], v);
+      const int64_t i = ((((int64_t)chunk * 25 + hk) * 2 + k8) * 5 + kdr) * f_cout_pad + co0 + ocl;
+      Vec8<__nv_bfloat16>::store(packed_f + i * 8, v);
+    }
+  } else {  // input-gradient image: tap mirrored, vector (chunk = co / 16, hk, k8, kdr, oc = ci) holds 8 consecutive co
+    const int e = tid - 64, k8 = e >> 5, ocl = e & 31, oc = ci0 + ocl;
+    if (co0 < b_cin_pad && oc < b_cout_pad) {
+      const int tb = kNumTaps - 1 - t;
+      const int kdr = 4 - tb / 25, hk = tb % 25, chunk = blockIdx.y;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = s[k8 * 8 + j][ocl];
+      const int64_t i = ((((int64_t)chunk * 25 + hk) * 2 + k8) * 5 + kdr) * b_cout_pad + oc;
+      Vec8<__nv_bfloat16>::store(packed_b + i * 8, v);
+    }
+  }
+}
+
 // f32 B8 tensor -> bf16 hi = bf16(x) and lo = bf16(x - hi): x = hi + lo up to 2^-17 relative (3 x bf16 fp32 path)
 __global__ void __launch_bounds__(256) split_hi_lo_kernel(msb_tensor x, msb_tensor hi, msb_tensor lo, int64_t s) {
   pdl_wait();
@@ -1406,6 +1459,25 @@ int msb_conv_k5_pack_tm(const float* w_tm, void* packed, int cout, int cin, int 
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   MSB_LAUNCH_PDL(pack_k5_tm_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), w_tm,
                  reinterpret_cast<__nv_bfloat16*>(packed), cout, cin, mode_bits, cin_pad, cout_pad);
+  return MSB_OK;
+}
+
+int msb_conv_k5_pack_tm_pair(const float* w_tm, void* packed_f, void* packed_b, int cout, int cin, int lo_part,
+                             int f_cin_pad, int f_cout_pad, int b_cin_pad, int b_cout_pad, void* stream) {
+  MSB_REQUIRE(w_tm && packed_f && packed_b && cout > 0 && cin > 0 && (lo_part == 0 || lo_part == 1),
+              "msb_conv_k5_pack_tm_pair: bad arguments");
+  MSB_REQUIRE(f_cin_pad % 16 == 0 && f_cout_pad % 16 == 0 && b_cin_pad % 16 == 0 && b_cout_pad % 16 == 0,
+              "msb_conv_k5_pack_tm_pair: padded channel counts must be multiples of 16");
+  MSB_REQUIRE(f_cin_pad >= cin && f_cout_pad >= cout && b_cin_pad >= cout && b_cout_pad >= cin,
+              "msb_conv_k5_pack_tm_pair: padded channel counts too small");
+  MSB_REQUIRE(f_cin_pad <= 256 && f_cout_pad <= 256 && b_cin_pad <= 256 && b_cout_pad <= 256,
+              "msb_conv_k5_pack_tm_pair: at most 256 (padded) channels");
+  const int rows = f_cout_pad > b_cin_pad ? f_cout_pad : b_cin_pad;
+  const int width = f_cin_pad > b_cout_pad ? f_cin_pad : b_cout_pad;
+  MSB_LAUNCH_PDL(pack_k5_tm_pair_kernel, dim3(kNumTaps, (unsigned)(rows / 16), (unsigned)((width + kPairCi - 1) / kPairCi)),
+                 dim3(128), 0, as_stream(stream), w_tm,
+                 reinterpret_cast<__nv_bfloat16*>(packed_f), reinterpret_cast<__nv_bfloat16*>(packed_b), cout, cin, lo_part,
+                 f_cin_pad, f_cout_pad, b_cin_pad, b_cout_pad);
   return MSB_OK;
 }
 

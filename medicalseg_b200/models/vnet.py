@@ -270,14 +270,15 @@ class _K5:
                                         device=dev)
         if self.tap_major:
             w = st.raw(self.conv.weight)
-            ops.k5_pack_tm(w, self.packed_f, self.cout, self.cin, 0, cin_pad, cout_pad)
-            ops.k5_pack_tm(w, self.packed_b, self.cout, self.cin, 1, self.bk_cin_pad, self.bk_cout_pad)
+            # both images from one read of the master weight (msb_conv_k5_pack_tm_pair)
+            ops.k5_pack_tm_pair(w, self.packed_f, self.packed_b, self.cout, self.cin, 0, cin_pad, cout_pad,
+                                self.bk_cin_pad, self.bk_cout_pad)
             if self.tc3:  # lo parts (w - bf16(w)) of both operand images
                 if self.packed_f_lo is None:
                     self.packed_f_lo = torch.empty_like(self.packed_f)
                     self.packed_b_lo = torch.empty_like(self.packed_b)
-                ops.k5_pack_tm(w, self.packed_f_lo, self.cout, self.cin, 0 | 2, cin_pad, cout_pad)
-                ops.k5_pack_tm(w, self.packed_b_lo, self.cout, self.cin, 1 | 2, self.bk_cin_pad, self.bk_cout_pad)
+                ops.k5_pack_tm_pair(w, self.packed_f_lo, self.packed_b_lo, self.cout, self.cin, 1, cin_pad, cout_pad,
+                                    self.bk_cin_pad, self.bk_cout_pad)
         else:
             ops.k5_pack(w, self.packed_f, self.cout, self.cin, 0, cin_pad, cout_pad)
             ops.k5_pack(w, self.packed_b, self.cout, self.cin, 1, self.bk_cin_pad, self.bk_cout_pad)

@@ -265,6 +265,12 @@ def k5_pack_tm(w_tm, packed, cout, cin, mode, cin_pad, cout_pad):
     call("msb_conv_k5_pack_tm", _ptr(w_tm), _ptr(packed), cout, cin, mode, cin_pad, cout_pad, _stream())
 
 
+def k5_pack_tm_pair(w_tm, packed_f, packed_b, cout, cin, lo_part, f_cin_pad, f_cout_pad, b_cin_pad, b_cout_pad):
+    """forward + input-gradient operand images from one read of the tap-major master weight"""
+    call("msb_conv_k5_pack_tm_pair", _ptr(w_tm), _ptr(packed_f), _ptr(packed_b), cout, cin, int(lo_part), f_cin_pad,
+         f_cout_pad, b_cin_pad, b_cout_pad, _stream())
+
+
 def split_hi_lo(x: B8, hi: B8, lo: B8):
     call("msb_split_hi_lo", x.mt, hi.mt, lo.mt, x.n, x.s, _stream())
 

@@ -370,6 +370,27 @@ def test_conv_k5_tcgen05_wgrad(cin, cout, dims, clustered):
         _lib.call("msb_debug_set", 6, 0)
 
 
+@pytest.mark.parametrize("cin,cout", [(16, 16), (32, 32), (64, 64), (128, 128), (256, 256), (32, 20), (2, 16), (16, 2),
+                                      (48, 24), (256, 128), (64, 256)])
+@pytest.mark.parametrize("lo_part", [0, 1])
+def test_conv_k5_pack_tm_pair_is_bit_identical_to_the_two_single_image_packs(cin, cout, lo_part):
+    """msb_conv_k5_pack_tm_pair (one read of the master weight, both operand images - what the train step calls after
+    every optimizer step) writes exactly the bytes of msb_conv_k5_pack_tm mode 0 and mode 1, padding included."""
+    ops, _ = _imp()
+    torch.manual_seed(7)
+    w_tm = torch.randn(125, cout, cin, device="cuda")
+    f_cin_pad, f_cout_pad = (cin + 15) // 16 * 16, ops.k5_out_pad((cout + 7) // 8 * 8)
+    b_cin_pad, b_cout_pad = (cout + 15) // 16 * 16, ops.k5_out_pad((cin + 7) // 8 * 8)
+    ref_f = torch.zeros(ops.k5_packed_bytes(f_cin_pad, f_cout_pad), dtype=torch.uint8, device="cuda")
+    ref_b = torch.zeros(ops.k5_packed_bytes(b_cin_pad, b_cout_pad), dtype=torch.uint8, device="cuda")
+    ops.k5_pack_tm(w_tm, ref_f, cout, cin, 0 | (2 * lo_part), f_cin_pad, f_cout_pad)
+    ops.k5_pack_tm(w_tm, ref_b, cout, cin, 1 | (2 * lo_part), b_cin_pad, b_cout_pad)
+    got_f, got_b = torch.full_like(ref_f, 0xAB), torch.full_like(ref_b, 0xAB)  # poisoned: every byte must be written
+    ops.k5_pack_tm_pair(w_tm, got_f, got_b, cout, cin, lo_part, f_cin_pad, f_cout_pad, b_cin_pad, b_cout_pad)
+    assert torch.equal(got_f, ref_f)
+    assert torch.equal(got_b, ref_b)
+
+
 @pytest.mark.parametrize("cin,cout,dims", [(32, 32, (6, 16, 16)), (64, 64, (4, 9, 20)), (128, 128, (3, 8, 16)),
                                            (32, 20, (5, 10, 18))])
 def test_conv_k5_tap_major_pack_and_wgrad(cin, cout, dims):
